@@ -1,0 +1,238 @@
+/*
+ * tbrm.h — C ABI of the B200-native raymarch / illumination-sweep hot path.
+ *
+ * This is the drop-in boundary for the two data-parallel hot paths of
+ * tommybazar/TBRaymarcherPlugin (reference paths are relative to the plugin root):
+ *
+ *   URaymarchUtils::AddDirLightToSingleVolume      Source/Raymarcher/Public/Util/RaymarchUtils.h:33-35
+ *   URaymarchUtils::ChangeDirLightInSingleVolume   Source/Raymarcher/Public/Util/RaymarchUtils.h:39-41
+ *   URaymarchUtils::ClearResourceLightVolumes      Source/Raymarcher/Public/Util/RaymarchUtils.h:49
+ *   URaymarchUtils::MakeDefaultTFTexture           Source/Raymarcher/Public/Util/RaymarchUtils.h:60
+ *   URaymarchUtils::ColorCurveToTexture            Source/Raymarcher/Public/Util/RaymarchUtils.h:64
+ *   PerformRaymarchCubeSetup                       Source/Raymarcher/Shaders/Private/RaymarchMaterialCommon.usf:23-69
+ *   PerformWindowedLitRaymarch                     Source/Raymarcher/Shaders/Private/WindowedRaymarchMaterials.usf:36-96
+ *   PerformMandelbulbRaymarchReturnDistance        Source/FractalMarcher/Shaders/Private/SDFMarcher.usf:61-112
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; device pointers are passed as void*.
+ *   - every op is enqueued on the resource set's CUDA stream and returns immediately
+ *     (the reference enqueues onto UE's render thread, RaymarchUtils.cpp:63-66,87-91);
+ *     tbrm_flush() is FlushRenderingCommands().
+ *   - functions return a tbrm_status; the reference's `bool& LightAdded` out-parameter and its
+ *     silent no-op rules (zero light direction, LightingShaders.cpp:41-46,173-179) are preserved.
+ *   - volumes are x-fastest: idx = x + y*X + z*X*Y (TextureUtilities.cpp:43-78).
+ */
+#ifndef TBRM_H_
+#define TBRM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBRM_ABI_VERSION 1
+
+typedef enum tbrm_status {
+    TBRM_OK = 0,
+    TBRM_ERR_INVALID_ARGUMENT = 1,
+    TBRM_ERR_NOT_INITIALIZED = 2, /* a resource the reference null-checks is missing (RaymarchUtils.cpp:39-45) */
+    TBRM_ERR_CUDA = 3,
+    TBRM_ERR_UNSUPPORTED = 4,
+    TBRM_ERR_NO_DEVICE = 5
+} tbrm_status;
+
+/* EPixelFormat subset the path uses (RaymarchVolume.cpp:857-861, VolumeInfo.h) */
+typedef enum tbrm_format {
+    TBRM_FMT_G8 = 0,   /* UNORM8  */
+    TBRM_FMT_G16 = 1,  /* UNORM16 (data volume only) */
+    TBRM_FMT_R32F = 2  /* float   */
+} tbrm_format;
+
+/* FDirLightParameters — Source/Raymarcher/Public/Rendering/RaymarchTypes.h:20-41 */
+typedef struct tbrm_dir_light {
+    double direction[3]; /* FVector LightDirection (world space, need not be unit) */
+    float intensity;     /* float LightIntensity */
+} tbrm_dir_light;
+
+/* FClippingPlaneParameters — RaymarchTypes.h:45-71 */
+typedef struct tbrm_clip_plane {
+    double center[3];
+    double direction[3]; /* "the direction from the center that is NOT clipped away" */
+} tbrm_clip_plane;
+
+/* FRaymarchWorldParameters — RaymarchTypes.h:136-153. VolumeTransform is an FTransform
+ * {Translation, Rotation (quaternion x,y,z,w), Scale3D}. */
+typedef struct tbrm_world {
+    double translation[3];
+    double rotation[4];
+    double scale[3];
+    tbrm_clip_plane clip;
+} tbrm_world;
+
+/* FWindowingParameters — Source/VolumeTextureToolkit/Public/VolumeAsset/VolumeInfo.h:32-53 */
+typedef struct tbrm_windowing {
+    float center;
+    float width;
+    int32_t low_cutoff;
+    int32_t high_cutoff;
+} tbrm_windowing;
+
+/* Stand-in for the UE view the material reads (ResolvedView.WorldCameraOrigin, CameraVector,
+ * ViewToTranslatedWorld, SvPosition, View.StateFrameIndexMod8 — RaymarchMaterialCommon.usf:26-48,75-76):
+ * an explicit pinhole camera. Pixel (ix,iy) looks through the centre of the pixel; iy grows downwards. */
+typedef struct tbrm_camera {
+    double eye[3];     /* world space */
+    double look_at[3]; /* world space */
+    double up[3];      /* world space, need not be orthogonal to the view direction */
+    double hfov_deg;   /* horizontal field of view */
+    int32_t width;
+    int32_t height;
+    float scene_depth;  /* CalcSceneDepth stand-in (constant over the image); <= 0 selects 1e8 */
+    int32_t frame_index; /* View.StateFrameIndexMod8 is frame_index % 8 */
+    int32_t jitter;      /* 1 = JitterEntryPos with Rand3DPCG16 (reference), 0 = off */
+} tbrm_camera;
+
+/* Parameters of PerformMandelbulbRaymarchReturnDistance — SDFMarcher.usf:61-72 */
+typedef struct tbrm_mandelbulb {
+    float center[3];
+    float extent;
+    float power;
+    float max_steps;
+    float max_iterations;
+    float bailout;
+    float high_precision_eps;
+    float low_precision_eps;
+} tbrm_mandelbulb;
+
+/* Engine-semantics switches. Zero-initialised = reference-faithful. */
+typedef struct tbrm_options {
+    int32_t border_exact;     /* 0: 8-bit FColor round trip of sampler border colours (Q1,Q2); 1: exact values */
+    int32_t data_addr_wrap;   /* raymarch data sampler address mode: 0 clamp (default), 1 wrap (Q5) */
+    int32_t sweep_impl;       /* 0: auto, 1: per-slice launches (reference schedule), 2: fused persistent sweep */
+    int32_t reserved[5];
+} tbrm_options;
+
+/* Per-op counters written by the *_stats calls (for the metric definitions of SURVEY.md §8d). */
+typedef struct tbrm_sweep_stats {
+    int32_t passes;          /* axis passes executed (0, 1 or 2; 2..4 for a Change that fell back to Remove+Add) */
+    int32_t fell_back;       /* Change: 1 if the major axes differed and Remove+Add ran (LightingShaders.cpp:192-198) */
+    int64_t voxels;          /* light-volume voxels x passes */
+    int32_t kernel_launches; /* CUDA kernels launched by this op */
+    int32_t faces[4];        /* FCubeFace of each pass (0:+X 1:-X 2:+Y 3:-Y 4:+Z 5:-Z), -1 if unused */
+} tbrm_sweep_stats;
+
+/* Opaque FBasicRaymarchRenderingResources (RaymarchTypes.h:87-129): data volume, TF texture, light volume,
+ * windowing, the 3x4 propagation buffers, and the CUDA stream that plays the render-thread queue. */
+typedef struct tbrm_resources tbrm_resources;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int tbrm_abi_version(void);
+const char* tbrm_status_string(int status);
+const char* tbrm_last_error(void); /* thread-local message for the last non-OK status */
+int tbrm_device_count(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t tbrm_kernel_launch_count(void);
+
+/* ---- resources (ARaymarchVolume::InitializeRaymarchResources, RaymarchVolume.cpp:821-920) ------------ */
+/* data_dims: data volume (X,Y,Z). light volume dims = data dims, or ceil(dims/2) if half_res (:850-855).
+ * light_fmt: TBRM_FMT_G8 (reference default) or TBRM_FMT_R32F (bLightVolume32Bit, :857-861). */
+tbrm_status tbrm_create(int device, const int32_t data_dims[3], tbrm_format data_fmt, tbrm_format light_fmt,
+                        int half_res, tbrm_resources** out);
+tbrm_status tbrm_destroy(tbrm_resources* res); /* FreeRaymarchResources, RaymarchVolume.cpp:922-949 */
+tbrm_status tbrm_set_options(tbrm_resources* res, const tbrm_options* opts);
+
+/* Data volume upload: host or device pointer, x-fastest, data_fmt texels (UVolumeTexture contents). */
+tbrm_status tbrm_upload_volume(tbrm_resources* res, const void* src, int src_is_device);
+/* Use caller-owned device memory as the data volume without copying (must outlive res). */
+tbrm_status tbrm_bind_volume_device(tbrm_resources* res, const void* dptr);
+
+/* Transfer function: RGBA float32, `width` x `height` texels, rounded to fp16 like PF_FloatRGBA
+ * (ColorCurveToTexture, RaymarchUtils.cpp:143-174). width must be 256. */
+tbrm_status tbrm_set_transfer_function(tbrm_resources* res, const float* rgba, int width, int height);
+tbrm_status tbrm_make_default_tf(tbrm_resources* res); /* MakeDefaultTFTexture, RaymarchUtils.cpp:113-141 */
+tbrm_status tbrm_set_windowing(tbrm_resources* res, const tbrm_windowing* w);
+
+/* ---- illumination sweep ------------------------------------------------------------------------------- */
+/* ClearResourceLightVolumes (RaymarchUtils.cpp:104-111) */
+tbrm_status tbrm_clear_light_volume(tbrm_resources* res, float clear_value);
+/* AddDirLightToSingleVolume (RaymarchUtils.cpp:35-68). gpu_sync selects the single-launch fused sweep
+ * (the intent of the reference's disabled GPUSync shader); it produces the same numbers. */
+tbrm_status tbrm_add_dir_light(tbrm_resources* res, const tbrm_dir_light* light, int added, const tbrm_world* world,
+                               int* light_added, int gpu_sync);
+/* ChangeDirLightInSingleVolume (RaymarchUtils.cpp:70-92) */
+tbrm_status tbrm_change_dir_light(tbrm_resources* res, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
+                                  const tbrm_world* world, int* light_added, int gpu_sync);
+/* Same two ops, also reporting what ran. */
+tbrm_status tbrm_add_dir_light_stats(tbrm_resources* res, const tbrm_dir_light* light, int added,
+                                     const tbrm_world* world, int* light_added, int gpu_sync, tbrm_sweep_stats* stats);
+tbrm_status tbrm_change_dir_light_stats(tbrm_resources* res, const tbrm_dir_light* old_light,
+                                        const tbrm_dir_light* new_light, const tbrm_world* world, int* light_added,
+                                        int gpu_sync, tbrm_sweep_stats* stats);
+
+/* Host parameter math of one light (LightingShaderUtils.cpp:29-265, LightingShaders.cpp:100-130): what the
+ * render-thread functions compute on the CPU before dispatching. Pure host function, needs no GPU. */
+typedef struct tbrm_pass_plan {
+    int32_t face, axis, dirn; /* FCubeFace, face/2, GetAxisDirection */
+    int32_t td[3];            /* GetTransposedDimensions */
+    int32_t start, stop;      /* GetLoopStartStopIndexes */
+    float weight;             /* FMajorAxes::FaceWeight[i].second after the 0.99 rule */
+    float light_alpha;        /* GetLightAlpha */
+    float border;             /* read-buffer sampler border colour (GetBorderColorIntSingle round trip) */
+    float uv_offset[2];       /* GetUVOffset */
+    float uvw_offset[3];      /* GetStepSizeAndUVWOffset + longest-voxel-side renormalisation */
+    float step_size;
+} tbrm_pass_plan;
+typedef struct tbrm_light_plan {
+    int32_t zero_direction; /* 1: the reference returns without doing anything */
+    int32_t add_passes;     /* passes AddDirLight executes (0..2); ChangeDirLight always runs both */
+    tbrm_pass_plan pass[2];
+    float clip_center[3], clip_dir[3]; /* GetLocalClippingParameters */
+    float data_border;                 /* data sampler border colour (LightingShaders.h:82-89) */
+    double local_dir[3];               /* normalised local light direction */
+} tbrm_light_plan;
+tbrm_status tbrm_plan_dir_light(const int32_t light_dims[3], const tbrm_windowing* win, const tbrm_options* opts,
+                                const tbrm_dir_light* light, const tbrm_world* world, tbrm_light_plan* out);
+
+/* Light volume access (tests, multi-GPU plumbing). Texels are light_fmt. */
+tbrm_status tbrm_light_volume_dims(const tbrm_resources* res, int32_t dims[3]);
+tbrm_status tbrm_download_light_volume(tbrm_resources* res, void* dst_host);
+tbrm_status tbrm_upload_light_volume(tbrm_resources* res, const void* src_host);
+void* tbrm_light_volume_device_ptr(tbrm_resources* res);
+void* tbrm_data_volume_device_ptr(tbrm_resources* res);
+
+/* ---- raymarch ----------------------------------------------------------------------------------------- */
+/* PerformRaymarchCubeSetup for every pixel: out_entry_thickness[4*(iy*W+ix)] = (entry UVW, thickness). */
+tbrm_status tbrm_raymarch_cube_setup(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world,
+                                     float* out_entry_thickness, int out_is_device);
+/* PerformRaymarchCubeSetup + PerformWindowedLitRaymarch for pixel rows [row_begin,row_end) of the image.
+ * out_rgba receives premultiplied RGBA float32 for those rows only ((row_end-row_begin)*W*4 floats).
+ * out_steps (optional) receives the total number of executed march-loop iterations (incl. clipped ones and
+ * the final partial step) — the numerator of Mray-steps/s. */
+tbrm_status tbrm_raymarch_lit(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world, float step_count,
+                              int row_begin, int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps);
+
+/* PerformMandelbulbRaymarchReturnDistance over the image rows [row_begin,row_end): out[2*pixel] = (x, y).
+ * out_iterations (optional): total Mandelbulb_SDF inner-loop iterations executed. Needs no resources. */
+tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, const tbrm_camera* cam,
+                                  const tbrm_world* world, int row_begin, int row_end, float* out_xy,
+                                  int out_is_device, uint64_t* out_iterations);
+
+/* ---- queue control ------------------------------------------------------------------------------------ */
+tbrm_status tbrm_flush(tbrm_resources* res); /* FlushRenderingCommands(): wait for the resource set's stream */
+void* tbrm_stream(tbrm_resources* res);      /* the cudaStream_t ops are enqueued on */
+/* Device time in ms between two points of the resource set's stream: call begin, enqueue ops, call end
+ * (end synchronises). Used by bench.py so kernels launched on this stream are timed on this stream. */
+tbrm_status tbrm_timer_begin(tbrm_resources* res);
+tbrm_status tbrm_timer_end(tbrm_resources* res, float* out_ms);
+
+/* ---- synthetic inputs: written into device or host memory, U8 ------------------------ */
+typedef enum tbrm_synth_kind { TBRM_SYNTH_SPHERE = 0, TBRM_SYNTH_PERLIN_CT = 1 } tbrm_synth_kind;
+tbrm_status tbrm_synth_volume_u8(int device, int kind, const int32_t dims[3], uint32_t seed, void* dst,
+                                 int dst_is_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBRM_H_ */

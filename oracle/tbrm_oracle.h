@@ -1,0 +1,68 @@
+/* tbrm_oracle.h — C interface of the CPU oracle (TEST INFRASTRUCTURE ONLY, see tbrm_oracle.cpp header). */
+#ifndef TBRM_ORACLE_H_
+#define TBRM_ORACLE_H_
+#include <stdint.h>
+#include "../include/tbrm.h" /* POD parameter types only */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* One axis pass of one light. Field-for-field comparable with tbrm_pass_plan. */
+typedef struct tbo_pass {
+    int32_t face, axis, dirn;
+    int32_t td[3];
+    int32_t start, stop;
+    float weight, light_alpha, border;
+    float uv_offset[2];
+    float uvw_offset[3];
+    float step_size;
+} tbo_pass;
+
+typedef struct tbo_light_plan {
+    int32_t zero_direction;
+    int32_t add_passes; /* passes AddDirLight executes (0..2); Change always runs 2 */
+    tbo_pass pass[2];
+    float clip_center[3], clip_dir[3];
+    float data_border;
+    double local_dir[3];
+} tbo_light_plan;
+
+typedef struct tbo_volume {
+    const void* data;
+    int32_t ddims[3];
+    int32_t data_fmt;
+    void* light;
+    int32_t ldims[3];
+    int32_t light_fmt;
+    const float* tf; /* 256 x RGBA, output of tbo_prepare_tf */
+    tbrm_windowing win;
+    int32_t border_exact;
+    int32_t data_addr_wrap;
+} tbo_volume;
+
+void tbo_prepare_tf(const float* rgba, int width, int height, float* out_256x4);
+void tbo_default_tf(float* out_256x4);
+int tbo_plan_dir_light(const int32_t ldims[3], const tbrm_windowing* win, int border_exact, const tbrm_dir_light* light,
+                       const tbrm_world* world, tbo_light_plan* out);
+int tbo_clear_light_volume(void* light, const int32_t ldims[3], int light_fmt, float value);
+int tbo_add_dir_light(const tbo_volume* vol, const tbrm_dir_light* light, int added, const tbrm_world* world, uint8_t* near_gate);
+int tbo_change_dir_light(const tbo_volume* vol, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
+                         const tbrm_world* world, uint8_t* near_gate);
+int tbo_raymarch_cube_setup(const tbrm_camera* cam, const tbrm_world* world, float* out);
+int tbo_raymarch_lit(const tbo_volume* vol, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                     int row_end, float* out_rgba, uint64_t* out_steps, uint8_t* near_gate);
+int tbo_mandelbulb_march(const tbrm_mandelbulb* mb, const tbrm_camera* cam, const tbrm_world* world, int row_begin, int row_end,
+                         float* out_xy, uint64_t* out_iterations);
+float tbo_det_pow(float x, float y);
+float tbo_round_to_half(float x);
+void tbo_sample_windowed_tf(float value, float step, const float* tf, const tbrm_windowing* w, float out[4]);
+float tbo_sample_data(const void* data, const int32_t dims[3], int fmt, float u, float v, float w, int mode, float border);
+uint32_t tbo_pcg16_x(int x, int y, int z);
+int tbo_max_threads(void);
+void tbo_set_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,526 @@
+// api.cu — the C ABI of include/tbrm.h: resource lifetime, validation, the host drivers of the sweep
+// (AddDirLightToSingleLightVolume_RenderThread / ChangeDirLightInSingleLightVolume_RenderThread,
+// Source/Raymarcher/Private/Rendering/LightingShaders.cpp:35-326) and the raymarch / Mandelbulb entry points.
+// Every op is enqueued on the resource set's stream, which plays the role of UE's render-thread queue.
+#include <cuda_fp16.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "tbrm_internal.hpp"
+
+namespace tbrm {
+std::atomic<long long> g_kernel_launches{0};
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+}  // namespace tbrm
+
+using namespace tbrm;
+
+#define TBRM_CUDA(expr)                                                                            \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+            return TBRM_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define TBRM_REQUIRE(cond, msg)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            set_last_error(msg);                \
+            return TBRM_ERR_INVALID_ARGUMENT;   \
+        }                                       \
+    } while (0)
+
+// run `enqueue(d_out)` with a device output buffer and deliver it to a host or device destination
+template <typename F>
+static tbrm_status with_output(int device, cudaStream_t stream, void* dst, size_t bytes, int dst_is_device, F enqueue) {
+    if (dst_is_device) {
+        TBRM_CUDA(enqueue(dst));
+        return TBRM_OK;
+    }
+    void* tmp = nullptr;
+    TBRM_CUDA(cudaMalloc(&tmp, bytes));
+    cudaError_t e = enqueue(tmp);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tmp);
+    (void) device;
+    TBRM_CUDA(e);
+    return TBRM_OK;
+}
+
+extern "C" {
+
+int tbrm_abi_version(void) { return TBRM_ABI_VERSION; }
+
+const char* tbrm_status_string(int status) {
+    switch (status) {
+        case TBRM_OK: return "ok";
+        case TBRM_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case TBRM_ERR_NOT_INITIALIZED: return "resources not initialized";
+        case TBRM_ERR_CUDA: return "CUDA error";
+        case TBRM_ERR_UNSUPPORTED: return "unsupported configuration";
+        case TBRM_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown status";
+    }
+}
+const char* tbrm_last_error(void) { return t_last_error.c_str(); }
+
+int tbrm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int64_t tbrm_kernel_launch_count(void) { return (int64_t) g_kernel_launches.load(); }
+
+tbrm_status tbrm_plan_dir_light(const int32_t light_dims[3], const tbrm_windowing* win, const tbrm_options* opts,
+                                const tbrm_dir_light* light, const tbrm_world* world, tbrm_light_plan* out) {
+    TBRM_REQUIRE(light_dims && win && light && world && out, "tbrm_plan_dir_light: null argument");
+    TBRM_REQUIRE(light_dims[0] > 0 && light_dims[1] > 0 && light_dims[2] > 0, "tbrm_plan_dir_light: empty light volume");
+    host::plan_dir_light(light_dims, *win, opts ? opts->border_exact != 0 : false, *light, *world, *out);
+    return TBRM_OK;
+}
+
+// ---- resources --------------------------------------------------------------------------------------------
+tbrm_status tbrm_create(int device, const int32_t data_dims[3], tbrm_format data_fmt, tbrm_format light_fmt, int half_res,
+                        tbrm_resources** out) {
+    TBRM_REQUIRE(out && data_dims, "tbrm_create: null argument");
+    *out = nullptr;
+    // RaymarchVolume.cpp:833-841: a volume with a zero dimension is not initialised
+    TBRM_REQUIRE(data_dims[0] > 0 && data_dims[1] > 0 && data_dims[2] > 0, "tbrm_create: data volume has a zero dimension");
+    TBRM_REQUIRE(data_fmt == TBRM_FMT_G8 || data_fmt == TBRM_FMT_G16 || data_fmt == TBRM_FMT_R32F, "tbrm_create: bad data format");
+    TBRM_REQUIRE(light_fmt == TBRM_FMT_G8 || light_fmt == TBRM_FMT_R32F, "tbrm_create: light volume must be G8 or R32F");
+    if (tbrm_device_count() <= 0) {
+        set_last_error("tbrm_create: no CUDA device visible");
+        return TBRM_ERR_NO_DEVICE;
+    }
+    TBRM_CUDA(cudaSetDevice(device));
+    auto* r = new tbrm_resources();
+    r->device = device;
+    r->data_fmt = data_fmt;
+    r->light_fmt = light_fmt;
+    r->half_res = half_res != 0;
+    for (int k = 0; k < 3; ++k) {
+        r->ddims[k] = data_dims[k];
+        r->ldims[k] = half_res ? (data_dims[k] + 1) / 2 : data_dims[k];  // RaymarchVolume.cpp:850-855
+    }
+    auto fail = [&](cudaError_t e, const char* what) {
+        set_last_error(std::string(what) + ": " + cudaGetErrorString(e));
+        tbrm_destroy(r);
+        return TBRM_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&r->ev_begin)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&r->ev_end)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&r->light, r->light_voxels() * r->light_elem())) != cudaSuccess) return fail(e, "cudaMalloc(light volume)");
+    if ((e = cudaMalloc((void**) &r->tf, 256 * sizeof(float4))) != cudaSuccess) return fail(e, "cudaMalloc(tf)");
+    if ((e = cudaMalloc((void**) &r->counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
+    // 4 R/W buffers per axis sized X:(Y,Z) Y:(X,Z) Z:(X,Y) in the light pixel format (RaymarchVolume.cpp:864-866,889-891)
+    const size_t bsz[3] = {(size_t) r->ldims[1] * r->ldims[2], (size_t) r->ldims[0] * r->ldims[2], (size_t) r->ldims[0] * r->ldims[1]};
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 4; ++b)
+            if ((e = cudaMalloc(&r->rw[a][b], bsz[a] * r->light_elem())) != cudaSuccess) return fail(e, "cudaMalloc(rw buffer)");
+    // a freshly created render target is cleared (UTextureRenderTargetVolume::Init)
+    if ((e = cudaMemsetAsync(r->light, 0, r->light_voxels() * r->light_elem(), r->stream)) != cudaSuccess) return fail(e, "cudaMemset");
+    *out = r;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_destroy(tbrm_resources* r) {
+    if (!r) return TBRM_OK;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    if (r->data_owned && r->data) cudaFree(r->data);
+    if (r->light) cudaFree(r->light);
+    if (r->tf) cudaFree(r->tf);
+    if (r->counters) cudaFree(r->counters);
+    if (r->ring) cudaFree(r->ring);
+    if (r->flags) cudaFree(r->flags);
+    for (auto& axis : r->rw)
+        for (void* b : axis)
+            if (b) cudaFree(b);
+    if (r->ev_begin) cudaEventDestroy(r->ev_begin);
+    if (r->ev_end) cudaEventDestroy(r->ev_end);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_set_options(tbrm_resources* r, const tbrm_options* opts) {
+    TBRM_REQUIRE(r && opts, "tbrm_set_options: null argument");
+    r->options = *opts;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_upload_volume(tbrm_resources* r, const void* src, int src_is_device) {
+    TBRM_REQUIRE(r && src, "tbrm_upload_volume: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    const size_t bytes = r->data_voxels() * r->data_elem();
+    if (!r->data_owned) {
+        r->data = nullptr;
+        TBRM_CUDA(cudaMalloc(&r->data, bytes));
+        r->data_owned = true;
+    }
+    TBRM_CUDA(cudaMemcpyAsync(r->data, src, bytes, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, r->stream));
+    r->data_ready = true;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_bind_volume_device(tbrm_resources* r, const void* dptr) {
+    TBRM_REQUIRE(r && dptr, "tbrm_bind_volume_device: null argument");
+    if (r->data_owned && r->data) {
+        cudaSetDevice(r->device);
+        cudaStreamSynchronize(r->stream);
+        cudaFree(r->data);
+    }
+    r->data = const_cast<void*>(dptr);
+    r->data_owned = false;
+    r->data_ready = true;
+    return TBRM_OK;
+}
+
+// PF_FloatRGBA texels sampled at v = 0.5 by a bilinear clamp sampler collapse to one 256-entry row
+static tbrm_status upload_tf_rows(tbrm_resources* r, const float* rgba, int width, int height) {
+    float table[256 * 4];
+    const float y = 0.5f * (float) height - 0.5f;
+    const float fl = floorf(y), fy = y - fl;
+    const int j0 = (int) fminf(fmaxf(fl, 0.0f), (float) (height - 1));
+    const int j1 = (int) fminf(fmaxf(fl + 1.0f, 0.0f), (float) (height - 1));
+    for (int i = 0; i < 256; ++i)
+        for (int c = 0; c < 4; ++c) {
+            const float a = __half2float(__float2half_rn(rgba[((size_t) j0 * width + i) * 4 + c]));
+            const float b = __half2float(__float2half_rn(rgba[((size_t) j1 * width + i) * 4 + c]));
+            table[4 * i + c] = fmaf(fy, b - a, a);
+        }
+    TBRM_CUDA(cudaSetDevice(r->device));
+    // the table lives on the stack: synchronous w.r.t. the host, ordered on the stream
+    TBRM_CUDA(cudaMemcpyAsync(r->tf, table, sizeof(table), cudaMemcpyHostToDevice, r->stream));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    r->tf_ready = true;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_set_transfer_function(tbrm_resources* r, const float* rgba, int width, int height) {
+    TBRM_REQUIRE(r && rgba, "tbrm_set_transfer_function: null argument");
+    TBRM_REQUIRE(width == 256 && height >= 1, "tbrm_set_transfer_function: the TF texture is 256 x H (RaymarchUtils.cpp:145-148)");
+    return upload_tf_rows(r, rgba, width, height);
+}
+
+tbrm_status tbrm_make_default_tf(tbrm_resources* r) {
+    TBRM_REQUIRE(r, "tbrm_make_default_tf: null argument");
+    float samples[256 * 4];
+    for (unsigned i = 0; i < 256; ++i) {  // RaymarchUtils.cpp:121-128
+        const float whiteness = (float) i / (float) (256 - 1);
+        samples[4 * i] = samples[4 * i + 1] = samples[4 * i + 2] = whiteness;
+        samples[4 * i + 3] = 1.0f;
+    }
+    return upload_tf_rows(r, samples, 256, 1);
+}
+
+tbrm_status tbrm_set_windowing(tbrm_resources* r, const tbrm_windowing* w) {
+    TBRM_REQUIRE(r && w, "tbrm_set_windowing: null argument");
+    r->windowing = *w;
+    return TBRM_OK;
+}
+
+// ---- sweep ------------------------------------------------------------------------------------------------
+tbrm_status tbrm_clear_light_volume(tbrm_resources* r, float clear_value) {
+    if (!r || !r->light) return TBRM_OK;  // RaymarchUtils.cpp:106-109: silently returns without a render target
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(clear_light(*r, clear_value));
+    return TBRM_OK;
+}
+
+static bool resources_valid(const tbrm_resources* r) {  // the 7 null checks of RaymarchUtils.cpp:39-41
+    return r && r->data && r->data_ready && r->tf && r->tf_ready && r->light;
+}
+
+static void fill_pass(LightPass& lp, const tbrm_pass_plan& p) {
+    lp.uv_off[0] = p.uv_offset[0], lp.uv_off[1] = p.uv_offset[1];
+    for (int k = 0; k < 3; ++k) lp.uvw_off[k] = p.uvw_offset[k];
+    lp.step = p.step_size * 100.0f;  // StepSize * VOLUME_DENSITY (AddDirLightShader.usf:112)
+    lp.border = p.border;
+    lp.light_alpha = p.light_alpha;
+}
+
+static void fill_uniforms(const tbrm_resources& r, const tbrm_light_plan& plan, int pass, SweepUniforms& u) {
+    const tbrm_pass_plan& p = plan.pass[pass];
+    u.axis = p.axis, u.dirn = p.dirn, u.start = p.start;
+    for (int k = 0; k < 3; ++k) {
+        u.td[k] = p.td[k];
+        u.ldims[k] = r.ldims[k];
+        u.ddims[k] = r.ddims[k];
+        u.clip_center[k] = plan.clip_center[k];
+        u.clip_dir[k] = plan.clip_dir[k];
+    }
+    u.data_border = plan.data_border;
+    u.win = Windowing{r.windowing.center, r.windowing.width, r.windowing.low_cutoff ? 1.0f : 0.0f, r.windowing.high_cutoff ? 1.0f : 0.0f};
+    u.sign = 1.0f;
+    fill_pass(u.a, p);
+    u.r = u.a;
+    u.gate_saturate = 1;
+}
+
+static tbrm_status run_pass(tbrm_resources& r, const SweepUniforms& u, bool change, int gpu_sync, tbrm_sweep_stats* stats) {
+    int launches = 0;
+    bool handled = false;
+    const int impl = r.options.sweep_impl;  // 0 auto, 1 per-slice, 2 fused
+    if (impl == 2 || (impl == 0 && gpu_sync)) {
+        TBRM_CUDA(sweep_pass_fused(r, u, change, &launches, &handled));
+        if (!handled && impl == 2) {
+            set_last_error("fused sweep does not support this configuration");
+            return TBRM_ERR_UNSUPPORTED;
+        }
+    }
+    if (!handled) TBRM_CUDA(sweep_pass_per_slice(r, u, change, &launches));
+    if (stats) {
+        if (stats->passes < 4) stats->faces[stats->passes] = u.axis * 2 + (u.dirn > 0 ? 1 : 0);
+        stats->passes += 1;
+        stats->voxels += (int64_t) u.td[0] * u.td[1] * u.td[2];
+        stats->kernel_launches += launches;
+    }
+    return TBRM_OK;
+}
+
+// AddDirLightToSingleLightVolume_RenderThread — LightingShaders.cpp:35-166
+static tbrm_status add_dir_light_impl(tbrm_resources& r, const tbrm_dir_light& light, bool added, const tbrm_world& world, int gpu_sync,
+                                      tbrm_sweep_stats* stats) {
+    tbrm_light_plan plan;
+    host::plan_dir_light(r.ldims, r.windowing, r.options.border_exact != 0, light, world, plan);
+    if (plan.zero_direction) return TBRM_OK;  // :41-46
+    for (int i = 0; i < plan.add_passes; ++i) {  // "break if the axis weight == 0", :65-68, :94-97
+        SweepUniforms u;
+        fill_uniforms(r, plan, i, u);
+        u.sign = added ? 1.0f : -1.0f;
+        tbrm_status s = run_pass(r, u, false, gpu_sync, stats);
+        if (s != TBRM_OK) return s;
+    }
+    return TBRM_OK;
+}
+
+static void reset_stats(tbrm_sweep_stats* s) {
+    if (!s) return;
+    memset(s, 0, sizeof(*s));
+    for (int& f : s->faces) f = -1;
+}
+
+tbrm_status tbrm_add_dir_light_stats(tbrm_resources* r, const tbrm_dir_light* light, int added, const tbrm_world* world,
+                                     int* light_added, int gpu_sync, tbrm_sweep_stats* stats) {
+    reset_stats(stats);
+    if (!resources_valid(r)) {  // RaymarchUtils.cpp:39-45
+        if (light_added) *light_added = 0;
+        return TBRM_ERR_NOT_INITIALIZED;
+    }
+    TBRM_REQUIRE(light && world, "tbrm_add_dir_light: null light or world parameters");
+    if (light_added) *light_added = 1;  // :48
+    TBRM_CUDA(cudaSetDevice(r->device));
+    return add_dir_light_impl(*r, *light, added != 0, *world, gpu_sync, stats);
+}
+
+tbrm_status tbrm_add_dir_light(tbrm_resources* r, const tbrm_dir_light* light, int added, const tbrm_world* world, int* light_added,
+                               int gpu_sync) {
+    return tbrm_add_dir_light_stats(r, light, added, world, light_added, gpu_sync, nullptr);
+}
+
+// ChangeDirLightInSingleLightVolume_RenderThread — LightingShaders.cpp:168-326
+tbrm_status tbrm_change_dir_light_stats(tbrm_resources* r, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
+                                        const tbrm_world* world, int* light_added, int gpu_sync, tbrm_sweep_stats* stats) {
+    reset_stats(stats);
+    if (!resources_valid(r)) {  // RaymarchUtils.cpp:74-80
+        if (light_added) *light_added = 0;
+        return TBRM_ERR_NOT_INITIALIZED;
+    }
+    TBRM_REQUIRE(old_light && new_light && world, "tbrm_change_dir_light: null light or world parameters");
+    if (light_added) *light_added = 1;
+    TBRM_CUDA(cudaSetDevice(r->device));
+    tbrm_light_plan rem, add;
+    host::plan_dir_light(r->ldims, r->windowing, r->options.border_exact != 0, *old_light, *world, rem);
+    host::plan_dir_light(r->ldims, r->windowing, r->options.border_exact != 0, *new_light, *world, add);
+    if (rem.zero_direction || add.zero_direction) return TBRM_OK;  // :173-179
+    if (rem.pass[0].face != add.pass[0].face || rem.pass[1].face != add.pass[1].face) {  // :192-198
+        if (stats) stats->fell_back = 1;
+        tbrm_status s = add_dir_light_impl(*r, *old_light, false, *world, gpu_sync, stats);
+        if (s != TBRM_OK) return s;
+        return add_dir_light_impl(*r, *new_light, true, *world, gpu_sync, stats);
+    }
+    for (int i = 0; i < 2; ++i) {  // both axes, no weight test (:203, :238)
+        SweepUniforms u;
+        fill_uniforms(*r, rem, i, u);
+        fill_pass(u.r, rem.pass[i]);
+        fill_pass(u.a, add.pass[i]);
+        u.gate_saturate = 0;  // ChangeDirLightShader.usf:130,136 has no saturate gate
+        tbrm_status s = run_pass(*r, u, true, gpu_sync, stats);
+        if (s != TBRM_OK) return s;
+    }
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_change_dir_light(tbrm_resources* r, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
+                                  const tbrm_world* world, int* light_added, int gpu_sync) {
+    return tbrm_change_dir_light_stats(r, old_light, new_light, world, light_added, gpu_sync, nullptr);
+}
+
+tbrm_status tbrm_light_volume_dims(const tbrm_resources* r, int32_t dims[3]) {
+    TBRM_REQUIRE(r && dims, "tbrm_light_volume_dims: null argument");
+    for (int k = 0; k < 3; ++k) dims[k] = r->ldims[k];
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_download_light_volume(tbrm_resources* r, void* dst_host) {
+    TBRM_REQUIRE(r && dst_host, "tbrm_download_light_volume: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaMemcpyAsync(dst_host, r->light, r->light_voxels() * r->light_elem(), cudaMemcpyDeviceToHost, r->stream));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_upload_light_volume(tbrm_resources* r, const void* src_host) {
+    TBRM_REQUIRE(r && src_host, "tbrm_upload_light_volume: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaMemcpyAsync(r->light, src_host, r->light_voxels() * r->light_elem(), cudaMemcpyHostToDevice, r->stream));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    return TBRM_OK;
+}
+
+void* tbrm_light_volume_device_ptr(tbrm_resources* r) { return r ? r->light : nullptr; }
+void* tbrm_data_volume_device_ptr(tbrm_resources* r) { return r ? r->data : nullptr; }
+
+// ---- raymarch ---------------------------------------------------------------------------------------------
+static bool camera_valid(const tbrm_camera* cam) { return cam && cam->width > 0 && cam->height > 0 && cam->hfov_deg > 0.0; }
+
+tbrm_status tbrm_raymarch_cube_setup(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float* out, int out_is_device) {
+    TBRM_REQUIRE(r && world && out, "tbrm_raymarch_cube_setup: null argument");
+    TBRM_REQUIRE(camera_valid(cam), "tbrm_raymarch_cube_setup: invalid camera");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    host::CameraUniforms cu;
+    host::plan_camera(*cam, *world, cu);
+    const size_t bytes = (size_t) cam->width * cam->height * 4 * sizeof(float);
+    return with_output(r->device, r->stream, out, bytes, out_is_device,
+                       [&](void* d) { return raymarch_cube_setup(*r, cu, (float*) d); });
+}
+
+tbrm_status tbrm_raymarch_lit(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                              int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
+    TBRM_REQUIRE(world && out_rgba, "tbrm_raymarch_lit: null argument");
+    TBRM_REQUIRE(camera_valid(cam), "tbrm_raymarch_lit: invalid camera");
+    TBRM_REQUIRE(step_count > 0.0f, "tbrm_raymarch_lit: step count must be positive");
+    TBRM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= cam->height, "tbrm_raymarch_lit: bad row range");
+    if (row_begin == row_end) {
+        if (out_steps) *out_steps = 0;
+        return TBRM_OK;
+    }
+    TBRM_CUDA(cudaSetDevice(r->device));
+    host::CameraUniforms cu;
+    host::plan_camera(*cam, *world, cu);
+    float cc[3], cd[3];
+    host::plan_clip(*world, cc, cd);  // SetMaterialClippingParameters, RaymarchVolume.cpp:705-728
+    unsigned long long* d_steps = out_steps ? r->counters : nullptr;
+    if (d_steps) TBRM_CUDA(cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), r->stream));
+    const size_t bytes = (size_t) cam->width * (row_end - row_begin) * 4 * sizeof(float);
+    tbrm_status s = with_output(r->device, r->stream, out_rgba, bytes, out_is_device, [&](void* d) {
+        return raymarch_lit(*r, cu, cc, cd, step_count, row_begin, row_end, (float*) d, d_steps);
+    });
+    if (s != TBRM_OK) return s;
+    if (out_steps) {
+        unsigned long long h = 0;
+        TBRM_CUDA(cudaMemcpyAsync(&h, d_steps, sizeof(h), cudaMemcpyDeviceToHost, r->stream));
+        TBRM_CUDA(cudaStreamSynchronize(r->stream));
+        *out_steps = h;
+    }
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, const tbrm_camera* cam, const tbrm_world* world,
+                                  int row_begin, int row_end, float* out_xy, int out_is_device, uint64_t* out_iterations) {
+    TBRM_REQUIRE(params && world && out_xy, "tbrm_mandelbulb_march: null argument");
+    TBRM_REQUIRE(camera_valid(cam), "tbrm_mandelbulb_march: invalid camera");
+    TBRM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= cam->height, "tbrm_mandelbulb_march: bad row range");
+    TBRM_REQUIRE(params->extent != 0.0f, "tbrm_mandelbulb_march: extent must be non-zero");
+    if (tbrm_device_count() <= 0) {
+        set_last_error("tbrm_mandelbulb_march: no CUDA device visible");
+        return TBRM_ERR_NO_DEVICE;
+    }
+    if (row_begin == row_end) {
+        if (out_iterations) *out_iterations = 0;
+        return TBRM_OK;
+    }
+    TBRM_CUDA(cudaSetDevice(device));
+    host::CameraUniforms cu;
+    host::plan_camera(*cam, *world, cu);
+    unsigned long long* d_iters = nullptr;
+    if (out_iterations) {
+        TBRM_CUDA(cudaMalloc((void**) &d_iters, sizeof(unsigned long long)));
+        TBRM_CUDA(cudaMemsetAsync(d_iters, 0, sizeof(unsigned long long), cudaStreamPerThread));
+    }
+    const size_t bytes = (size_t) cam->width * (row_end - row_begin) * 2 * sizeof(float);
+    tbrm_status s = with_output(device, cudaStreamPerThread, out_xy, bytes, out_is_device, [&](void* d) {
+        return mandelbulb_march(cudaStreamPerThread, *params, cu, row_begin, row_end, (float*) d, d_iters);
+    });
+    if (s == TBRM_OK && out_iterations) {
+        unsigned long long h = 0;
+        cudaError_t e = cudaMemcpyAsync(&h, d_iters, sizeof(h), cudaMemcpyDeviceToHost, cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+        *out_iterations = h;
+        if (e != cudaSuccess) s = TBRM_ERR_CUDA;
+    }
+    if (s == TBRM_OK && out_is_device) {
+        if (cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) s = TBRM_ERR_CUDA;
+    }
+    if (d_iters) cudaFree(d_iters);
+    return s;
+}
+
+// ---- queue control ----------------------------------------------------------------------------------------
+tbrm_status tbrm_flush(tbrm_resources* r) {
+    TBRM_REQUIRE(r, "tbrm_flush: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    return TBRM_OK;
+}
+
+void* tbrm_stream(tbrm_resources* r) { return r ? (void*) r->stream : nullptr; }
+
+tbrm_status tbrm_timer_begin(tbrm_resources* r) {
+    TBRM_REQUIRE(r, "tbrm_timer_begin: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaEventRecord(r->ev_begin, r->stream));
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_timer_end(tbrm_resources* r, float* out_ms) {
+    TBRM_REQUIRE(r && out_ms, "tbrm_timer_end: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaEventRecord(r->ev_end, r->stream));
+    TBRM_CUDA(cudaEventSynchronize(r->ev_end));
+    TBRM_CUDA(cudaEventElapsedTime(out_ms, r->ev_begin, r->ev_end));
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_synth_volume_u8(int device, int kind, const int32_t dims[3], uint32_t seed, void* dst, int dst_is_device) {
+    TBRM_REQUIRE(dims && dst, "tbrm_synth_volume_u8: null argument");
+    TBRM_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "tbrm_synth_volume_u8: empty volume");
+    TBRM_REQUIRE(kind == TBRM_SYNTH_SPHERE || kind == TBRM_SYNTH_PERLIN_CT, "tbrm_synth_volume_u8: unknown kind");
+    if (tbrm_device_count() <= 0) {
+        set_last_error("tbrm_synth_volume_u8: no CUDA device visible");
+        return TBRM_ERR_NO_DEVICE;
+    }
+    TBRM_CUDA(cudaSetDevice(device));
+    const size_t bytes = (size_t) dims[0] * dims[1] * dims[2];
+    tbrm_status s = with_output(device, cudaStreamPerThread, dst, bytes, dst_is_device,
+                                [&](void* d) { return synth_volume_u8(cudaStreamPerThread, kind, dims, seed, (uint8_t*) d); });
+    if (s == TBRM_OK && dst_is_device) TBRM_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    return s;
+}
+
+}  // extern "C"

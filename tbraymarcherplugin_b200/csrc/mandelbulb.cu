@@ -1,0 +1,147 @@
+// mandelbulb.cu — procedural Mandelbulb SDF march (config 5), sm_100a.
+// Reference: Source/FractalMarcher/Shaders/Private/SDFMarcher.usf:24-58 (Mandelbulb_SDF, GetActualPosition),
+//            :61-112 (PerformMandelbulbRaymarchReturnDistance); entry from PerformRaymarchCubeSetup.
+// Pure FP32 + SFU work: no textures, the only memory traffic is the output image.
+#include "tbrm_internal.hpp"
+
+namespace tbrm {
+
+struct MbCam {
+    float eye[3], fwd[3], rt[3], ut[3];
+    float inv_w2, inv_h2;
+    float m[4][3];
+    float depth;
+    int width, height, frame_mod8, jitter;
+};
+
+struct MbUniforms {
+    MbCam cam;
+    tbrm_mandelbulb mb;
+    int row_begin, row_end;
+};
+
+__device__ __forceinline__ void mb_normalize(float& x, float& y, float& z) {
+    const float l = sqrtf(dot3(x, y, z, x, y, z));
+    x = x / l, y = y / l, z = z / l;
+}
+__device__ __forceinline__ void mb_mul3x3(float vx, float vy, float vz, const float m[4][3], float& ox, float& oy, float& oz) {
+    ox = ((vx * m[0][0]) + (vy * m[1][0])) + (vz * m[2][0]);
+    oy = ((vx * m[0][1]) + (vy * m[1][1])) + (vz * m[2][1]);
+    oz = ((vx * m[0][2]) + (vy * m[1][2])) + (vz * m[2][2]);
+}
+
+// Mandelbulb_SDF — SDFMarcher.usf:24-52
+__device__ __forceinline__ float mandelbulb_sdf(float px, float py, float pz, float bailout, float power, int iterations,
+                                                unsigned int& iters) {
+    float zx = px, zy = py, zz = pz;
+    float dr = 1.0f, r = 0.0f;
+    for (int i = 0; i < iterations; i++) {
+        r = sqrtf(dot3(zx, zy, zz, zx, zy, zz));
+        if (r > bailout) break;
+        ++iters;
+        float theta = acosf(zz / r);
+        float phi = atan2f(zy, zx);
+        dr = powf(r, power - 1.0f) * power * dr + 1.0f;
+        const float zr = powf(r, power);
+        theta = theta * power;
+        phi = phi * power;
+        float st, ct, sp, cp;
+        sincosf(theta, &st, &ct);
+        sincosf(phi, &sp, &cp);
+        zx = zr * (st * cp) + px;
+        zy = zr * (sp * st) + py;
+        zz = zr * ct + pz;
+    }
+    return 0.5f * logf(r) * r / dr;
+}
+
+__global__ void __launch_bounds__(256) mandelbulb_kernel(const MbUniforms U, float2* __restrict__ out,
+                                                         unsigned long long* __restrict__ iters_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ix = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int iy = U.row_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    unsigned int iters = 0;
+    if (ix < U.cam.width && iy < U.row_end) {
+        const MbCam& c = U.cam;
+        // CameraVector + PerformRaymarchCubeSetup (same arithmetic as raymarch.cu)
+        const float sx = ((float) ix + 0.5f) * c.inv_w2 - 1.0f;
+        const float sy = 1.0f - ((float) iy + 0.5f) * c.inv_h2;
+        float dx = (c.fwd[0] + c.rt[0] * sx) + c.ut[0] * sy, dy = (c.fwd[1] + c.rt[1] * sx) + c.ut[1] * sy,
+              dz = (c.fwd[2] + c.rt[2] * sx) + c.ut[2] * sy;
+        mb_normalize(dx, dy, dz);
+        const float Vx = -dx, Vy = -dy, Vz = -dz;
+        float nx = Vx, ny = Vy, nz = Vz;
+        mb_normalize(nx, ny, nz);
+        float wx, wy, wz;
+        mb_mul3x3(nx * c.depth, ny * c.depth, nz * c.depth, c.m, wx, wy, wz);
+        float depth = sqrtf(dot3(wx, wy, wz, wx, wy, wz));
+        depth = depth / fabsf(dot3(c.fwd[0], c.fwd[1], c.fwd[2], Vx, Vy, Vz));
+        float ox, oy, oz;
+        mb_mul3x3(c.eye[0], c.eye[1], c.eye[2], c.m, ox, oy, oz);
+        ox = ox + c.m[3][0], oy = oy + c.m[3][1], oz = oz + c.m[3][2];
+        float lx, ly, lz;
+        mb_mul3x3(Vx, Vy, Vz, c.m, lx, ly, lz);
+        mb_normalize(lx, ly, lz);
+        lx = -lx, ly = -ly, lz = -lz;
+        ox = ox + 0.5f, oy = oy + 0.5f, oz = oz + 0.5f;
+        const float ivx = 1.0f / lx, ivy = 1.0f / ly, ivz = 1.0f / lz;
+        const float tminx = (0.0f - ox) * ivx, tminy = (0.0f - oy) * ivy, tminz = (0.0f - oz) * ivz;
+        const float tmaxx = (1.0f - ox) * ivx, tmaxy = (1.0f - oy) * ivy, tmaxz = (1.0f - oz) * ivz;
+        float t0 = fmaxf(fminf(tmaxx, tminx), fmaxf(fminf(tmaxy, tminy), fminf(tmaxz, tminz)));
+        float t1 = fminf(fmaxf(tmaxx, tminx), fminf(fmaxf(tmaxy, tminy), fmaxf(tmaxz, tminz)));
+        t0 = fmaxf(0.0f, t0);
+        t1 = fminf(depth, t1);
+        const float thick = fmaxf(0.0f, t1 - t0);
+        float cx = ox + (t0 * lx), cy = oy + (t0 * ly), cz = oz + (t0 * lz);
+
+        float rx = 0.0f, ry = 0.0f;
+        if (thick > 0.0f) {
+            const tbrm_mandelbulb& mb = U.mb;
+            const float stx = lx / mb.extent, sty = ly / mb.extent, stz = lz / mb.extent;  // SDFMarcher.usf:76
+            const int max_iter = (int) mb.max_iterations;
+            float dist = 0.0f;
+            bool done = false;
+            for (int s = 0; (float) s < mb.max_steps; s++) {
+                const float apx = mb.center[0] + ((cx - 0.5f) * mb.extent), apy = mb.center[1] + ((cy - 0.5f) * mb.extent),
+                            apz = mb.center[2] + ((cz - 0.5f) * mb.extent);
+                dist = mandelbulb_sdf(apx, apy, apz, mb.bailout, mb.power, max_iter, iters);
+                if (dist < mb.high_precision_eps) {
+                    float ratio = (float) s / (float) mb.max_steps;
+                    ratio = ratio * 10.0f;
+                    rx = 1.0f - ratio, ry = 1.0f;
+                    done = true;
+                    break;
+                }
+                cx = cx + (dist * stx), cy = cy + (dist * sty), cz = cz + (dist * stz);
+                if (saturatef(cx) != cx || saturatef(cy) != cy || saturatef(cz) != cz) {
+                    rx = 0.0f, ry = 0.0f;
+                    done = true;
+                    break;
+                }
+            }
+            if (!done && dist < mb.low_precision_eps) rx = 0.0f, ry = 1.0f;
+        }
+        out[(size_t) (iy - U.row_begin) * c.width + ix] = make_float2(rx, ry);
+    }
+    if (iters_out) {
+        unsigned int s = iters;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && s) atomicAdd(iters_out, (unsigned long long) s);
+    }
+}
+
+cudaError_t mandelbulb_march(cudaStream_t stream, const tbrm_mandelbulb& mb, const host::CameraUniforms& cam, int row_begin,
+                             int row_end, float* d_out, unsigned long long* d_iters) {
+    MbUniforms U;
+    static_assert(sizeof(MbCam) == sizeof(host::CameraUniforms), "camera uniform layouts must match");
+    memcpy(&U.cam, &cam, sizeof(U.cam));
+    U.mb = mb;
+    U.row_begin = row_begin, U.row_end = row_end;
+    const dim3 grid((cam.width + 31) / 32, (row_end - row_begin + 7) / 8);
+    mandelbulb_kernel<<<grid, 256, 0, stream>>>(U, (float2*) d_out, d_iters);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace tbrm

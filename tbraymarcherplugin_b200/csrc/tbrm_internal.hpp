@@ -1,0 +1,79 @@
+// tbrm_internal.hpp — state behind the opaque tbrm_resources handle and the launcher interfaces between the
+// translation units of libtbrm.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/tbrm.h"
+#include "host_plan.hpp"
+#include "sweep_common.cuh"
+
+// FBasicRaymarchRenderingResources (RaymarchTypes.h:87-129) + the stream that plays the render-thread queue
+struct tbrm_resources {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+
+    // DataVolumeTextureRef
+    int32_t ddims[3] = {0, 0, 0};
+    tbrm_format data_fmt = TBRM_FMT_G8;
+    void* data = nullptr;
+    bool data_owned = false;
+    bool data_ready = false;
+
+    // TFTextureRef collapsed to 256 x RGBA fp32 (fp16-rounded values)
+    float4* tf = nullptr;
+    bool tf_ready = false;
+
+    // LightVolumeRenderTarget
+    int32_t ldims[3] = {0, 0, 0};
+    tbrm_format light_fmt = TBRM_FMT_R32F;
+    void* light = nullptr;
+    bool half_res = false;
+
+    tbrm_windowing windowing = {0.5f, 1.0f, 1, 1};  // VolumeInfo.h:36-46 defaults
+    tbrm_options options = {};
+
+    // XYZReadWriteBuffers[axis].Buffers[0..3] (RaymarchVolume.cpp:864-866,889-891), light pixel format
+    void* rw[3][4] = {};
+    // scratch of the fused sweep: ring of propagated slices + per-tile progress flags
+    void* ring = nullptr;
+    size_t ring_bytes = 0;
+    unsigned int* flags = nullptr;
+    size_t flags_count = 0;
+    unsigned long long* counters = nullptr;  // device scratch for step / iteration counts
+
+    size_t light_voxels() const { return (size_t) ldims[0] * ldims[1] * ldims[2]; }
+    size_t data_voxels() const { return (size_t) ddims[0] * ddims[1] * ddims[2]; }
+    size_t light_elem() const { return light_fmt == TBRM_FMT_G8 ? 1 : 4; }
+    size_t data_elem() const { return data_fmt == TBRM_FMT_G8 ? 1 : (data_fmt == TBRM_FMT_G16 ? 2 : 4); }
+};
+
+namespace tbrm {
+
+extern std::atomic<long long> g_kernel_launches;
+void set_last_error(const std::string& msg);
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// sweep.cu
+cudaError_t sweep_fill_buffer(tbrm_resources& r, void* buf, size_t count, float value);
+cudaError_t sweep_pass_per_slice(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches);
+cudaError_t sweep_pass_fused(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
+cudaError_t clear_light(tbrm_resources& r, float value);
+
+// raymarch.cu
+cudaError_t raymarch_cube_setup(tbrm_resources& r, const host::CameraUniforms& cam, float* d_out);
+cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, const float clip_center[3], const float clip_dir[3],
+                         float step_count, int row_begin, int row_end, float* d_out, unsigned long long* d_steps);
+
+// mandelbulb.cu
+cudaError_t mandelbulb_march(cudaStream_t stream, const tbrm_mandelbulb& mb, const host::CameraUniforms& cam, int row_begin,
+                             int row_end, float* d_out, unsigned long long* d_iters);
+
+// synth.cu
+cudaError_t synth_volume_u8(cudaStream_t stream, int kind, const int32_t dims[3], uint32_t seed, uint8_t* d_out);
+
+}  // namespace tbrm

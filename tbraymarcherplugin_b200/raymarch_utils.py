@@ -1,0 +1,411 @@
+"""Python mirror of the reference's operator surface, bound to libtbrm.so through the C ABI.
+
+Names, argument meaning and error behaviour follow the plugin (paths relative to the plugin root):
+
+* ``URaymarchUtils``                      Source/Raymarcher/Public/Util/RaymarchUtils.h:20-99
+* ``FBasicRaymarchRenderingResources``    Source/Raymarcher/Public/Rendering/RaymarchTypes.h:87-129
+* ``FDirLightParameters``                 RaymarchTypes.h:20-41
+* ``FClippingPlaneParameters``            RaymarchTypes.h:45-71
+* ``FRaymarchWorldParameters``            RaymarchTypes.h:136-153
+* ``FWindowingParameters``                Source/VolumeTextureToolkit/Public/VolumeAsset/VolumeInfo.h:32-53
+
+``bool& LightAdded`` out-parameters become return values. The C++ twin with the reference's exact signatures is
+``tbraymarcherplugin_b200/csrc/RaymarchUtils.hpp``. This module is host-side glue only: every computation
+happens in the CUDA library; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import FMT_G8, FMT_G16, FMT_R32F, TbrmError, check
+
+Vec3 = Tuple[float, float, float]
+
+_NP_OF_FMT = {FMT_G8: np.uint8, FMT_G16: np.uint16, FMT_R32F: np.float32}
+_FMT_OF_NP = {np.dtype(np.uint8): FMT_G8, np.dtype(np.uint16): FMT_G16, np.dtype(np.float32): FMT_R32F}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# parameter structs
+# --------------------------------------------------------------------------------------------------------------
+@dataclass
+class FDirLightParameters:
+    LightDirection: Vec3 = (0.0, 0.0, 0.0)
+    LightIntensity: float = 0.0
+
+    def to_c(self) -> _capi.DirLight:
+        return _capi.DirLight((C.c_double * 3)(*map(float, self.LightDirection)), float(self.LightIntensity))
+
+
+@dataclass
+class FClippingPlaneParameters:
+    # RaymarchVolume.cpp:640-641: "ridiculously far and facing away" when there is no clipping plane
+    Center: Vec3 = (0.0, 0.0, 100000.0)
+    Direction: Vec3 = (0.0, 0.0, -1.0)
+
+
+@dataclass
+class FTransform:
+    Translation: Vec3 = (0.0, 0.0, 0.0)
+    Rotation: Tuple[float, float, float, float] = (0.0, 0.0, 0.0, 1.0)  # quaternion x, y, z, w
+    Scale3D: Vec3 = (1.0, 1.0, 1.0)
+
+    @staticmethod
+    def from_axis_angle(axis: Vec3, degrees: float, translation: Vec3 = (0, 0, 0), scale: Vec3 = (1, 1, 1)) -> "FTransform":
+        n = math.sqrt(sum(a * a for a in axis))
+        h = math.radians(degrees) / 2.0
+        s = math.sin(h) / n
+        return FTransform(tuple(map(float, translation)), (axis[0] * s, axis[1] * s, axis[2] * s, math.cos(h)), tuple(map(float, scale)))
+
+
+@dataclass
+class FRaymarchWorldParameters:
+    VolumeTransform: FTransform = field(default_factory=FTransform)
+    ClippingPlaneParameters: FClippingPlaneParameters = field(default_factory=FClippingPlaneParameters)
+
+    def to_c(self) -> _capi.World:
+        t = self.VolumeTransform
+        c = self.ClippingPlaneParameters
+        return _capi.World(
+            (C.c_double * 3)(*map(float, t.Translation)),
+            (C.c_double * 4)(*map(float, t.Rotation)),
+            (C.c_double * 3)(*map(float, t.Scale3D)),
+            _capi.ClipPlane((C.c_double * 3)(*map(float, c.Center)), (C.c_double * 3)(*map(float, c.Direction))),
+        )
+
+
+@dataclass
+class FWindowingParameters:
+    Center: float = 0.5
+    Width: float = 1.0
+    LowCutoff: bool = True
+    HighCutoff: bool = True
+
+    def to_c(self) -> _capi.Windowing:
+        return _capi.Windowing(float(self.Center), float(self.Width), int(bool(self.LowCutoff)), int(bool(self.HighCutoff)))
+
+
+@dataclass
+class FCamera:
+    """Explicit pinhole camera standing in for the UE view the material reads."""
+
+    Eye: Vec3 = (-0.9, -0.5, 0.7)
+    LookAt: Vec3 = (0.0, 0.0, 0.0)
+    Up: Vec3 = (0.0, 0.0, 1.0)
+    HFovDeg: float = 60.0
+    Width: int = 512
+    Height: int = 512
+    SceneDepth: float = 0.0
+    FrameIndex: int = 0
+    Jitter: bool = True
+
+    def to_c(self) -> _capi.Camera:
+        return _capi.Camera(
+            (C.c_double * 3)(*map(float, self.Eye)),
+            (C.c_double * 3)(*map(float, self.LookAt)),
+            (C.c_double * 3)(*map(float, self.Up)),
+            float(self.HFovDeg),
+            int(self.Width),
+            int(self.Height),
+            float(self.SceneDepth),
+            int(self.FrameIndex),
+            int(bool(self.Jitter)),
+        )
+
+
+@dataclass
+class FMandelbulbParameters:
+    """Arguments of PerformMandelbulbRaymarchReturnDistance (SDFMarcher.usf:61-72); defaults per SURVEY.md §8(d)."""
+
+    VolumeCenter: Vec3 = (0.0, 0.0, 0.0)
+    Extent: float = 2.4
+    Power: float = 8.0
+    MaxSteps: float = 1024.0
+    MaxIterations: float = 16.0
+    Bailout: float = 2.4
+    HighPrecisionEps: float = 1e-4
+    LowPrecisionEps: float = 1e-2
+
+    def to_c(self) -> _capi.Mandelbulb:
+        return _capi.Mandelbulb(
+            (C.c_float * 3)(*map(float, self.VolumeCenter)),
+            self.Extent,
+            self.Power,
+            self.MaxSteps,
+            self.MaxIterations,
+            self.Bailout,
+            self.HighPrecisionEps,
+            self.LowPrecisionEps,
+        )
+
+
+@dataclass
+class FSweepStats:
+    passes: int = 0
+    fell_back: bool = False
+    voxels: int = 0
+    kernel_launches: int = 0
+    faces: Tuple[int, ...] = ()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# resources
+# --------------------------------------------------------------------------------------------------------------
+class FBasicRaymarchRenderingResources:
+    """Per-volume GPU resources: data volume, TF texture, light volume, windowing, propagation buffers.
+
+    Created by :meth:`URaymarchUtils.InitializeRaymarchResources` (ARaymarchVolume::InitializeRaymarchResources,
+    RaymarchVolume.cpp:821-920). A default-constructed object is *uninitialised*: ops return LightAdded = False.
+    """
+
+    def __init__(self) -> None:
+        self._h: Optional[C.c_void_p] = None
+        self.bIsInitialized = False
+        self.LightVolumeHalfResolution = False
+        self.bLightVolume32Bit = False
+        self.WindowingParameters = FWindowingParameters()
+        self.DataDims: Tuple[int, int, int] = (0, 0, 0)
+        self.LightDims: Tuple[int, int, int] = (0, 0, 0)
+        self.DataFormat = FMT_G8
+        self.LightFormat = FMT_G8
+        self.Device = 0
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def release(self) -> None:  # FreeRaymarchResources, RaymarchVolume.cpp:922-949
+        if self._h is not None:
+            _capi.load().tbrm_destroy(self._h)
+            self._h = None
+        self.bIsInitialized = False
+
+
+class URaymarchUtils:
+    """Blueprint function library of the plugin, as static methods."""
+
+    # ---- resource set-up ------------------------------------------------------------------------------------
+    @staticmethod
+    def InitializeRaymarchResources(
+        data_dims: Sequence[int],
+        data_format: int = FMT_G8,
+        bLightVolume32Bit: bool = False,
+        LightVolumeHalfResolution: bool = False,
+        device: int = 0,
+    ) -> FBasicRaymarchRenderingResources:
+        lib = _capi.load()
+        res = FBasicRaymarchRenderingResources()
+        dims = (C.c_int32 * 3)(*map(int, data_dims))
+        h = C.c_void_p()
+        light_fmt = FMT_R32F if bLightVolume32Bit else FMT_G8  # RaymarchVolume.cpp:857-861
+        check(lib.tbrm_create(device, dims, data_format, light_fmt, int(LightVolumeHalfResolution), C.byref(h)))
+        res._h = h
+        res.Device = device
+        res.DataDims = tuple(int(d) for d in data_dims)
+        ld = (C.c_int32 * 3)()
+        check(lib.tbrm_light_volume_dims(h, ld))
+        res.LightDims = (ld[0], ld[1], ld[2])
+        res.DataFormat = data_format
+        res.LightFormat = light_fmt
+        res.bLightVolume32Bit = bLightVolume32Bit
+        res.LightVolumeHalfResolution = LightVolumeHalfResolution
+        return res
+
+    @staticmethod
+    def SetDataVolume(Resources: FBasicRaymarchRenderingResources, volume: np.ndarray) -> None:
+        """Upload the data volume; ``volume`` is indexed [z, y, x] (x fastest, TextureUtilities.cpp:43-78)."""
+        v = np.ascontiguousarray(volume)
+        X, Y, Z = Resources.DataDims
+        if v.shape != (Z, Y, X) or _FMT_OF_NP.get(v.dtype) != Resources.DataFormat:
+            raise ValueError(f"volume must have shape {(Z, Y, X)} and dtype {_NP_OF_FMT[Resources.DataFormat]}")
+        check(_capi.load().tbrm_upload_volume(Resources.handle, v.ctypes.data_as(C.c_void_p), 0))
+        check(_capi.load().tbrm_flush(Resources.handle))
+        Resources.bIsInitialized = True
+
+    @staticmethod
+    def SetDataVolumeDevice(Resources: FBasicRaymarchRenderingResources, device_ptr: int, copy: bool = False) -> None:
+        lib = _capi.load()
+        if copy:
+            check(lib.tbrm_upload_volume(Resources.handle, C.c_void_p(device_ptr), 1))
+        else:
+            check(lib.tbrm_bind_volume_device(Resources.handle, C.c_void_p(device_ptr)))
+        Resources.bIsInitialized = True
+
+    @staticmethod
+    def SetWindowingParameters(Resources: FBasicRaymarchRenderingResources, w: FWindowingParameters) -> None:
+        Resources.WindowingParameters = w
+        cw = w.to_c()
+        check(_capi.load().tbrm_set_windowing(Resources.handle, C.byref(cw)))
+
+    @staticmethod
+    def SetOptions(Resources: FBasicRaymarchRenderingResources, border_exact: bool = False, data_addr_wrap: bool = False, sweep_impl: int = 0) -> None:
+        o = _capi.Options(int(border_exact), int(data_addr_wrap), int(sweep_impl))
+        check(_capi.load().tbrm_set_options(Resources.handle, C.byref(o)))
+
+    # ---- transfer functions (RaymarchUtils.h:57-64) ------------------------------------------------------------
+    @staticmethod
+    def MakeDefaultTFTexture(Resources: FBasicRaymarchRenderingResources) -> None:
+        check(_capi.load().tbrm_make_default_tf(Resources.handle))
+
+    @staticmethod
+    def ColorCurveToTexture(Resources: FBasicRaymarchRenderingResources, curve_rgba: np.ndarray, texture_height: int = 16) -> None:
+        """``curve_rgba``: (256, 4) float32 samples of the colour curve at i/255 (RaymarchUtils.cpp:153-162)."""
+        s = np.ascontiguousarray(curve_rgba, dtype=np.float32)
+        if s.shape != (256, 4):
+            raise ValueError("curve samples must be (256, 4)")
+        tex = np.ascontiguousarray(np.broadcast_to(s, (texture_height, 256, 4)))
+        check(_capi.load().tbrm_set_transfer_function(Resources.handle, tex.ctypes.data_as(C.POINTER(C.c_float)), 256, texture_height))
+
+    # ---- light volume ops (RaymarchUtils.h:31-49) ------------------------------------------------------------
+    @staticmethod
+    def ClearResourceLightVolumes(Resources: FBasicRaymarchRenderingResources, ClearValue: float) -> None:
+        if Resources is None or Resources.handle is None:
+            return  # RaymarchUtils.cpp:106-109
+        check(_capi.load().tbrm_clear_light_volume(Resources.handle, float(ClearValue)))
+
+    @staticmethod
+    def AddDirLightToSingleVolume(
+        Resources: FBasicRaymarchRenderingResources,
+        LightParameters: FDirLightParameters,
+        Added: bool,
+        WorldParameters: FRaymarchWorldParameters,
+        bGPUSync: bool = False,
+        stats: Optional[FSweepStats] = None,
+    ) -> bool:
+        """Returns LightAdded (RaymarchUtils.cpp:35-68): False iff the resources are not initialised."""
+        lib = _capi.load()
+        light, world = LightParameters.to_c(), WorldParameters.to_c()
+        added = C.c_int(0)
+        st = _capi.SweepStats()
+        status = lib.tbrm_add_dir_light_stats(Resources.handle, C.byref(light), int(Added), C.byref(world), C.byref(added), int(bGPUSync), C.byref(st))
+        if status == _capi.TBRM_ERR_NOT_INITIALIZED:
+            return False
+        check(status)
+        _fill_stats(stats, st)
+        return bool(added.value)
+
+    @staticmethod
+    def ChangeDirLightInSingleVolume(
+        Resources: FBasicRaymarchRenderingResources,
+        OldLightParameters: FDirLightParameters,
+        NewLightParameters: FDirLightParameters,
+        WorldParameters: FRaymarchWorldParameters,
+        bGPUSync: bool = False,
+        stats: Optional[FSweepStats] = None,
+    ) -> bool:
+        """Returns LightAdded (RaymarchUtils.cpp:70-92)."""
+        lib = _capi.load()
+        old, new, world = OldLightParameters.to_c(), NewLightParameters.to_c(), WorldParameters.to_c()
+        added = C.c_int(0)
+        st = _capi.SweepStats()
+        status = lib.tbrm_change_dir_light_stats(
+            Resources.handle, C.byref(old), C.byref(new), C.byref(world), C.byref(added), int(bGPUSync), C.byref(st)
+        )
+        if status == _capi.TBRM_ERR_NOT_INITIALIZED:
+            return False
+        check(status)
+        _fill_stats(stats, st)
+        return bool(added.value)
+
+    @staticmethod
+    def FlushRenderingCommands(Resources: FBasicRaymarchRenderingResources) -> None:
+        check(_capi.load().tbrm_flush(Resources.handle))
+
+    @staticmethod
+    def ReadLightVolume(Resources: FBasicRaymarchRenderingResources) -> np.ndarray:
+        X, Y, Z = Resources.LightDims
+        out = np.empty((Z, Y, X), dtype=_NP_OF_FMT[Resources.LightFormat])
+        check(_capi.load().tbrm_download_light_volume(Resources.handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @staticmethod
+    def WriteLightVolume(Resources: FBasicRaymarchRenderingResources, light: np.ndarray) -> None:
+        X, Y, Z = Resources.LightDims
+        v = np.ascontiguousarray(light, dtype=_NP_OF_FMT[Resources.LightFormat])
+        if v.shape != (Z, Y, X):
+            raise ValueError("light volume shape mismatch")
+        check(_capi.load().tbrm_upload_light_volume(Resources.handle, v.ctypes.data_as(C.c_void_p)))
+
+    # ---- material entry points ----------------------------------------------------------------------------
+    @staticmethod
+    def PerformRaymarchCubeSetup(Resources: FBasicRaymarchRenderingResources, Camera: FCamera, WorldParameters: FRaymarchWorldParameters) -> np.ndarray:
+        cam, world = Camera.to_c(), WorldParameters.to_c()
+        out = np.empty((Camera.Height, Camera.Width, 4), dtype=np.float32)
+        check(_capi.load().tbrm_raymarch_cube_setup(Resources.handle, C.byref(cam), C.byref(world), out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+    @staticmethod
+    def PerformWindowedLitRaymarch(
+        Resources: FBasicRaymarchRenderingResources,
+        Camera: FCamera,
+        WorldParameters: FRaymarchWorldParameters,
+        StepCount: float,
+        rows: Optional[Tuple[int, int]] = None,
+        out: Optional[np.ndarray] = None,
+        device_out_ptr: Optional[int] = None,
+        count_steps: bool = True,
+    ):
+        """Cube setup + lit march for image rows [rows[0], rows[1]). Returns (rgba, executed_steps)."""
+        cam, world = Camera.to_c(), WorldParameters.to_c()
+        r0, r1 = rows if rows is not None else (0, Camera.Height)
+        steps = C.c_uint64(0)
+        psteps = C.byref(steps) if count_steps else None
+        if device_out_ptr is not None:
+            check(_capi.load().tbrm_raymarch_lit(Resources.handle, C.byref(cam), C.byref(world), float(StepCount), r0, r1, C.c_void_p(device_out_ptr), 1, psteps))
+            return None, int(steps.value)
+        if out is None:
+            out = np.empty((r1 - r0, Camera.Width, 4), dtype=np.float32)
+        check(_capi.load().tbrm_raymarch_lit(Resources.handle, C.byref(cam), C.byref(world), float(StepCount), r0, r1, out.ctypes.data_as(C.c_void_p), 0, psteps))
+        return out, int(steps.value)
+
+    @staticmethod
+    def PerformMandelbulbRaymarchReturnDistance(
+        Params: FMandelbulbParameters,
+        Camera: FCamera,
+        WorldParameters: FRaymarchWorldParameters,
+        rows: Optional[Tuple[int, int]] = None,
+        device: int = 0,
+        device_out_ptr: Optional[int] = None,
+    ):
+        cam, world, mb = Camera.to_c(), WorldParameters.to_c(), Params.to_c()
+        r0, r1 = rows if rows is not None else (0, Camera.Height)
+        iters = C.c_uint64(0)
+        if device_out_ptr is not None:
+            check(_capi.load().tbrm_mandelbulb_march(device, C.byref(mb), C.byref(cam), C.byref(world), r0, r1, C.c_void_p(device_out_ptr), 1, C.byref(iters)))
+            return None, int(iters.value)
+        out = np.empty((r1 - r0, Camera.Width, 2), dtype=np.float32)
+        check(_capi.load().tbrm_mandelbulb_march(device, C.byref(mb), C.byref(cam), C.byref(world), r0, r1, out.ctypes.data_as(C.c_void_p), 0, C.byref(iters)))
+        return out, int(iters.value)
+
+
+def _fill_stats(dst: Optional[FSweepStats], st: _capi.SweepStats) -> None:
+    if dst is None:
+        return
+    dst.passes = int(st.passes)
+    dst.fell_back = bool(st.fell_back)
+    dst.voxels = int(st.voxels)
+    dst.kernel_launches = int(st.kernel_launches)
+    dst.faces = tuple(int(f) for f in st.faces if f >= 0)
+
+
+def plan_dir_light(light_dims: Sequence[int], windowing: FWindowingParameters, light: FDirLightParameters,
+                   world: FRaymarchWorldParameters, border_exact: bool = False) -> _capi.LightPlan:
+    """Host parameter math of one light (pure host code inside libtbrm.so; needs no GPU)."""
+    dims = (C.c_int32 * 3)(*map(int, light_dims))
+    w, l, wo = windowing.to_c(), light.to_c(), world.to_c()
+    o = _capi.Options(int(border_exact), 0, 0)
+    out = _capi.LightPlan()
+    check(_capi.load().tbrm_plan_dir_light(dims, C.byref(w), C.byref(o), C.byref(l), C.byref(wo), C.byref(out)))
+    return out

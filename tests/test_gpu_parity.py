@@ -1,0 +1,200 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar: the sweep and the lit ray march share the oracle's fp32 arithmetic contract, so they must agree
+BIT-FOR-BIT (which is stricter than BASELINE.json's 1e-4); the Mandelbulb march uses libm vs CUDA transcendentals and
+is compared with a tolerance plus a small budget of sphere-tracing step flips."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tbraymarcherplugin_b200 import FMT_G8, synth
+from tbraymarcherplugin_b200.raymarch_utils import (FCamera, FDirLightParameters, FMandelbulbParameters, FSweepStats, FWindowingParameters,
+                                                    URaymarchUtils)
+
+pytestmark = pytest.mark.gpu
+
+CT_WINDOW = FWindowingParameters(0.45, 0.5, True, False)
+# sweep implementations under test: 1 = per-slice launches (reference schedule), 2 = fused persistent sweep
+IMPLS = [int(x) for x in os.environ.get("TBRM_TEST_IMPLS", "1,2").split(",")]
+
+
+def make_pair(data, curve, windowing, light32=True, half_res=False, border_exact=False, sweep_impl=0, wrap=False):
+    Z, Y, X = data.shape
+    res = URaymarchUtils.InitializeRaymarchResources((X, Y, Z), FMT_G8 if data.dtype == np.uint8 else (1 if data.dtype == np.uint16 else 2),
+                                                     bLightVolume32Bit=light32, LightVolumeHalfResolution=half_res)
+    URaymarchUtils.SetDataVolume(res, data)
+    if curve is None:
+        URaymarchUtils.MakeDefaultTFTexture(res)
+        tf = oracle.default_tf()
+    else:
+        URaymarchUtils.ColorCurveToTexture(res, curve)
+        tf = oracle.prepare_tf(curve)
+    URaymarchUtils.SetWindowingParameters(res, windowing)
+    URaymarchUtils.SetOptions(res, border_exact=border_exact, data_addr_wrap=wrap, sweep_impl=sweep_impl)
+    ora = oracle.OracleVolume(data, tf, windowing, light32=light32, half_res=half_res, border_exact=border_exact, data_addr_wrap=wrap)
+    return res, ora
+
+
+def assert_same(gpu, ref, what):
+    if not np.array_equal(gpu, ref):
+        d = np.abs(gpu.astype(np.float64) - ref.astype(np.float64))
+        raise AssertionError(f"{what}: {np.count_nonzero(d)} of {d.size} elements differ, max |d| = {d.max():.3e}")
+
+
+WORLDS = {"identity": synth.identity_world, "scaled_rotated": synth.scaled_rotated_world, "clipped": synth.clipped_world}
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("world_name", list(WORLDS))
+@pytest.mark.parametrize("dims", [(32, 32, 32), (40, 24, 56)])
+def test_add_dir_light_matches_oracle(dims, world_name, impl):
+    data = synth.perlin_ct_volume(dims)
+    res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, sweep_impl=impl)
+    world = WORLDS[world_name]()
+    URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    for light in synth.LIGHTS:
+        st = FSweepStats()
+        assert URaymarchUtils.AddDirLightToSingleVolume(res, light, True, world, bGPUSync=(impl == 2), stats=st)
+        n = ora.add_dir_light(light, True, world)
+        assert st.passes == n
+        assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"after adding {light.LightDirection}")
+    # removing a light goes through the same kernel with bAdded = -1
+    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[1], False, world, bGPUSync=(impl == 2))
+    ora.add_dir_light(synth.LIGHTS[1], False, world)
+    assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "after removing L2")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_default_tf_sphere_and_nonzero_window_border(impl):
+    data = synth.sphere_volume((36, 36, 36))
+    # window whose zero point (C - W/2 = 0.3) makes the data sampler border colour non-zero (Q1)
+    res, ora = make_pair(data, None, FWindowingParameters(0.5, 0.4, False, True), sweep_impl=impl)
+    for light in synth.LIGHTS[:2]:
+        URaymarchUtils.AddDirLightToSingleVolume(res, light, True, synth.identity_world(), bGPUSync=(impl == 2))
+        ora.add_dir_light(light, True, synth.identity_world())
+    assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "sphere / default TF")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("light32,half_res", [(False, False), (True, True), (False, True)])
+def test_g8_and_half_resolution_light_volumes(light32, half_res, impl):
+    data = synth.perlin_ct_volume((33, 30, 41))  # odd sizes: ceil(dims/2) light volume
+    res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, light32=light32, half_res=half_res, sweep_impl=impl)
+    assert res.LightDims == ora.ldims
+    for light in synth.LIGHTS[:3]:
+        URaymarchUtils.AddDirLightToSingleVolume(res, light, True, synth.identity_world(), bGPUSync=(impl == 2))
+        ora.add_dir_light(light, True, synth.identity_world())
+    assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"light32={light32} half_res={half_res}")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("data_dtype", [np.uint16, np.float32])
+def test_g16_and_float_data_volumes(data_dtype, impl):
+    base = synth.perlin_ct_volume((28, 28, 28)).astype(np.float32) / 255.0
+    data = (base * 65535).astype(np.uint16) if data_dtype == np.uint16 else base.astype(np.float32)
+    res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, sweep_impl=impl)
+    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[0], True, synth.identity_world(), bGPUSync=(impl == 2))
+    ora.add_dir_light(synth.LIGHTS[0], True, synth.identity_world())
+    assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, str(data_dtype))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("world_name", ["identity", "clipped"])
+def test_change_dir_light_matches_oracle(world_name, impl):
+    data = synth.perlin_ct_volume((40, 36, 32))
+    res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, sweep_impl=impl)
+    world = WORLDS[world_name]()
+    lights = list(synth.LIGHTS)
+    for l in lights:
+        URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=(impl == 2))
+        ora.add_dir_light(l, True, world)
+    fused = fallback = 0
+    for step in range(1, 5):  # cfg 3: rotate each light 5 degrees about +Z per update
+        for i, l in enumerate(lights):
+            new = synth.rotate_about_z(synth.LIGHTS[i], 5.0 * step)
+            st = FSweepStats()
+            assert URaymarchUtils.ChangeDirLightInSingleVolume(res, l, new, world, bGPUSync=(impl == 2), stats=st)
+            code = ora.change_dir_light(l, new, world)
+            assert st.fell_back == (code >= 100)
+            fused += not st.fell_back
+            fallback += st.fell_back
+            lights[i] = new
+        assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"after update {step}")
+    # a change between lights with different major axes falls back to Remove + Add (LightingShaders.cpp:192-198)
+    st = FSweepStats()
+    URaymarchUtils.ChangeDirLightInSingleVolume(res, lights[0], synth.LIGHTS[1], world, bGPUSync=(impl == 2), stats=st)
+    ora.change_dir_light(lights[0], synth.LIGHTS[1], world)
+    assert st.fell_back and fused > 0
+    assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "after the fallback change")
+
+
+def test_zero_direction_and_clear():
+    res, ora = make_pair(synth.sphere_volume((16, 16, 16)), None, FWindowingParameters())
+    URaymarchUtils.ClearResourceLightVolumes(res, 0.25)
+    st = FSweepStats()
+    assert URaymarchUtils.AddDirLightToSingleVolume(res, FDirLightParameters((0, 0, 0), 1.0), True, synth.identity_world(), stats=st)
+    assert st.passes == 0
+    assert np.all(URaymarchUtils.ReadLightVolume(res) == np.float32(0.25))
+
+
+@pytest.mark.parametrize("world_name", list(WORLDS))
+@pytest.mark.parametrize("jitter", [True, False])
+def test_lit_raymarch_matches_oracle(world_name, jitter):
+    data = synth.perlin_ct_volume((48, 48, 48))
+    res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW)
+    world = WORLDS[world_name]()
+    for l in synth.LIGHTS[:2]:
+        URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world)
+        ora.add_dir_light(l, True, world)
+    cam = synth.benchmark_camera(112, 80, jitter=jitter, frame=3)
+    rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 96.0)
+    ref, ref_steps = ora.raymarch_lit(cam, world, 96.0)
+    assert ref[..., 3].max() > 0.5 and steps > 10000
+    assert steps == ref_steps
+    assert_same(rgba, ref, "lit raymarch")
+    assert_same(URaymarchUtils.PerformRaymarchCubeSetup(res, cam, world), oracle.cube_setup(cam, world), "cube setup")
+    # a row range renders exactly those rows
+    part, _ = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 96.0, rows=(24, 56))
+    assert_same(part, ref[24:56], "row range")
+
+
+def test_lit_raymarch_default_tf_early_out_and_g8_light():
+    data = synth.sphere_volume((40, 40, 40))
+    res, ora = make_pair(data, None, FWindowingParameters(), light32=False)
+    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[2], True, synth.identity_world())
+    ora.add_dir_light(synth.LIGHTS[2], True, synth.identity_world())
+    cam = synth.benchmark_camera(64, 64)
+    rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, synth.identity_world(), 64.0)
+    ref, ref_steps = ora.raymarch_lit(cam, synth.identity_world(), 64.0)
+    assert (ref[..., 3] == 1.0).any()  # the opaque default TF triggers the alpha > 0.95 early-out
+    assert steps == ref_steps
+    assert_same(rgba, ref, "default TF raymarch")
+
+
+def test_mandelbulb_matches_oracle_within_tolerance():
+    cam = synth.benchmark_camera(96, 64, jitter=False)
+    params = FMandelbulbParameters(MaxSteps=256.0, MaxIterations=12.0)
+    out, iters = URaymarchUtils.PerformMandelbulbRaymarchReturnDistance(params, cam, synth.identity_world())
+    ref, ref_iters = oracle.mandelbulb(params, cam, synth.identity_world())
+    assert (ref[..., 1] == 1).sum() > 200
+    # tolerance 1e-4 per channel; sphere tracing a fractal amplifies the ulp-level differences between libm and CUDA
+    # transcendentals, so a hit can land one march step earlier/later (value changes by k*10/MaxSteps): budget 2 %.
+    bad = np.abs(out - ref).max(axis=-1) > 1e-4
+    assert bad.mean() < 0.02, f"{bad.sum()} of {bad.size} pixels differ"
+    assert abs(iters - ref_iters) / ref_iters < 0.02
+
+
+@pytest.mark.parametrize("kind", ["sphere", "perlin"])
+def test_device_synth_equals_numpy_twin(kind):
+    import ctypes as C
+
+    from tbraymarcherplugin_b200 import _capi
+
+    dims = (40, 28, 36)
+    out = np.empty(dims[::-1], np.uint8)
+    _capi.check(_capi.load().tbrm_synth_volume_u8(0, 0 if kind == "sphere" else 1, (C.c_int32 * 3)(*dims), synth.PERLIN_SEED,
+                                                  out.ctypes.data_as(C.c_void_p), 0))
+    ref = synth.sphere_volume(dims) if kind == "sphere" else synth.perlin_ct_volume(dims)
+    assert_same(out, ref, kind)

@@ -1,0 +1,131 @@
+"""CPU-side tests of the product's host logic: the C-ABI library loads and exports every declared symbol, its host
+parameter math (csrc/host_plan.hpp) agrees bit-for-bit with the oracle's restatement of LightingShaderUtils.cpp, and
+argument validation / error behaviour follows the reference. No compute calls (there is no GPU here)."""
+import ctypes as C
+import math
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from tbraymarcherplugin_b200 import _capi, synth
+from tbraymarcherplugin_b200.raymarch_utils import (FBasicRaymarchRenderingResources, FClippingPlaneParameters, FDirLightParameters,
+                                                    FRaymarchWorldParameters, FTransform, FWindowingParameters, URaymarchUtils,
+                                                    plan_dir_light)
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_symbol_the_header_declares():
+    header = (ROOT / "include" / "tbrm.h").read_text()
+    declared = set(re.findall(r"\b(tbrm_[a-z0-9_]+)\s*\(", header))
+    lib = _capi.load()
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"libtbrm.so does not export {name}"
+    assert declared == set(_capi.PROTOTYPES), declared ^ set(_capi.PROTOTYPES)
+    assert lib.tbrm_abi_version() == 1
+
+
+def test_struct_layouts_match_between_binding_and_oracle():
+    assert C.sizeof(_capi.LightPlan) == C.sizeof(oracle.LightPlan)
+    assert C.sizeof(_capi.PassPlan) == C.sizeof(oracle.Pass)
+
+
+def _random_world(rng):
+    axis = rng.standard_normal(3)
+    t = FTransform.from_axis_angle(tuple(axis), float(rng.uniform(-180, 180)), tuple(rng.uniform(-50, 50, 3)), tuple(rng.uniform(0.3, 3.0, 3)))
+    c = FClippingPlaneParameters(tuple(rng.uniform(-40, 40, 3)), tuple(rng.standard_normal(3)))
+    return FRaymarchWorldParameters(t, c)
+
+
+def _plans_equal(a, b):
+    for f, _ in _capi.LightPlan._fields_:
+        va, vb = getattr(a, f), getattr(b, f)
+        if f == "passes":
+            for pa, pb in zip(va, vb):
+                for g, _ in _capi.PassPlan._fields_:
+                    xa, xb = getattr(pa, g), getattr(pb, g)
+                    xa = list(xa) if hasattr(xa, "__len__") else xa
+                    xb = list(xb) if hasattr(xb, "__len__") else xb
+                    assert xa == xb, (g, xa, xb)
+        else:
+            va = list(va) if hasattr(va, "__len__") else va
+            vb = list(vb) if hasattr(vb, "__len__") else vb
+            assert va == vb, (f, va, vb)
+
+
+def test_host_plan_matches_oracle_bit_for_bit():
+    rng = np.random.default_rng(7)
+    worlds = [synth.identity_world(), synth.scaled_rotated_world(), synth.clipped_world()] + [_random_world(rng) for _ in range(40)]
+    for i, world in enumerate(worlds):
+        dims = tuple(int(d) for d in rng.integers(5, 300, 3))
+        win = FWindowingParameters(float(rng.uniform(0, 1)), float(rng.uniform(0.05, 1.5)), bool(i & 1), bool(i & 2))
+        light = FDirLightParameters(tuple(rng.standard_normal(3) * 3), float(rng.uniform(0.1, 1.5)))
+        for exact in (False, True):
+            _plans_equal(plan_dir_light(dims, win, light, world, exact), oracle.plan_dir_light(dims, win, light, world, exact))
+    for light in synth.LIGHTS:  # the benchmark lights, identity transform
+        _plans_equal(plan_dir_light((512, 512, 512), FWindowingParameters(), light, worlds[0]),
+                     oracle.plan_dir_light((512, 512, 512), FWindowingParameters(), light, worlds[0]))
+
+
+def test_plan_semantics():
+    w = FWindowingParameters()
+    world = synth.identity_world()
+    # axis-aligned light: weight 1 on +Z, one pass, sweep from the top slice downwards (LightingShaderUtils.cpp:66-70,181-187)
+    p = plan_dir_light((32, 48, 64), w, FDirLightParameters((0, 0, -1), 0.5), world)
+    assert p.add_passes == 1 and p.passes[0].face == 4 and p.passes[0].weight == 1.0 and p.passes[1].weight == 0.0
+    assert p.passes[0].dirn == -1 and p.passes[0].start == 63 and p.passes[0].stop == -1 and list(p.passes[0].td) == [32, 48, 64]
+    assert p.passes[0].light_alpha == 0.5 and list(p.passes[0].uv_offset) == [0.0, 0.0]
+    assert p.passes[0].step_size == pytest.approx(1 / 64) and list(p.passes[0].uvw_offset) == pytest.approx([0, 0, 1 / 32])
+    # L1: faces -X then -Y, weights 0.8 / 0.2 (third axis folded into the second), transposed dims (Y,Z,X) / (X,Z,Y)
+    p = plan_dir_light((32, 48, 64), w, synth.LIGHTS[0], world)
+    assert p.add_passes == 2 and [q.face for q in p.passes] == [1, 3]
+    assert p.passes[0].weight + p.passes[1].weight == pytest.approx(1.0)
+    assert list(p.passes[0].td) == [48, 64, 32] and list(p.passes[1].td) == [32, 64, 48]
+    assert p.passes[0].dirn == 1 and p.passes[0].start == 0 and p.passes[0].stop == 32
+    # no clipping plane: "ridiculously far and facing away"
+    assert list(p.clip_center) == pytest.approx([0.5, 0.5, 100000.5]) and list(p.clip_dir) == [0.0, 0.0, -1.0]
+    # border colours: 8-bit round trip by default, exact on request
+    assert p.passes[0].border != p.passes[0].light_alpha
+    assert abs(p.passes[0].border - p.passes[0].light_alpha) < 4e-3
+    pe = plan_dir_light((32, 48, 64), w, synth.LIGHTS[0], world, border_exact=True)
+    assert pe.passes[0].border == pe.passes[0].light_alpha and pe.data_border == 0.0
+    assert plan_dir_light((8, 8, 8), w, FDirLightParameters((0, 0, 0), 1.0), world).zero_direction == 1
+
+
+def test_uninitialised_resources_report_light_not_added():
+    res = FBasicRaymarchRenderingResources()  # no handle: every pointer the reference checks is null
+    assert URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[0], True, synth.identity_world()) is False
+    assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], synth.LIGHTS[1], synth.identity_world()) is False
+    URaymarchUtils.ClearResourceLightVolumes(res, 0.0)  # silently returns
+
+
+def test_create_without_a_device_fails_loudly():
+    lib = _capi.load()
+    if lib.tbrm_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_capi.TbrmError) as e:
+        URaymarchUtils.InitializeRaymarchResources((8, 8, 8))
+    assert e.value.status == _capi.TBRM_ERR_NO_DEVICE
+
+
+def test_argument_validation():
+    lib = _capi.load()
+    h = C.c_void_p()
+    assert lib.tbrm_create(0, (C.c_int32 * 3)(0, 4, 4), 0, 2, 0, C.byref(h)) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    assert lib.tbrm_create(0, (C.c_int32 * 3)(4, 4, 4), 0, 1, 0, C.byref(h)) == _capi.TBRM_ERR_INVALID_ARGUMENT  # G16 light volume
+    assert b"light volume" in lib.tbrm_last_error()
+    assert lib.tbrm_flush(None) == _capi.TBRM_ERR_INVALID_ARGUMENT
+
+
+def test_synthetic_volumes_are_deterministic_and_shaped():
+    s = synth.sphere_volume((16, 12, 10))
+    assert s.shape == (10, 12, 16) and s.dtype == np.uint8 and s.max() > 200 and s[0, 0, 0] == 0
+    p1, p2 = synth.perlin_ct_volume((24, 24, 24)), synth.perlin_ct_volume((24, 24, 24))
+    assert np.array_equal(p1, p2) and p1[0, 0, 0] == 0 and 60 < p1[12, 12, 12] < 200
+    assert not np.array_equal(p1, synth.perlin_ct_volume((24, 24, 24), seed=1))
+    c = synth.soft_ct_curve()
+    assert c.shape == (256, 4) and c[0, 3] == 0 and c[255, 3] == pytest.approx(0.15)
