@@ -110,7 +110,8 @@ typedef struct tbrm_mandelbulb {
 typedef struct tbrm_options {
     int32_t border_exact;     /* 0: 8-bit FColor round trip of sampler border colours (Q1,Q2); 1: exact values */
     int32_t data_addr_wrap;   /* raymarch data sampler address mode: 0 clamp (default), 1 wrap (Q5) */
-    int32_t sweep_impl;       /* 0: auto, 1: per-slice launches (reference schedule), 2: fused persistent sweep */
+    int32_t sweep_impl;       /* 0: auto (gpu_sync ? fused : per-slice), 1: per-slice launches (reference schedule),
+                                 2: fused persistent sweep (TMA-staged when eligible), 3: generic fused sweep only */
     int32_t reserved[5];
 } tbrm_options;
 
@@ -121,6 +122,7 @@ typedef struct tbrm_sweep_stats {
     int64_t voxels;          /* light-volume voxels x passes */
     int32_t kernel_launches; /* CUDA kernels launched by this op */
     int32_t faces[4];        /* FCubeFace of each pass (0:+X 1:-X 2:+Y 3:-Y 4:+Z 5:-Z), -1 if unused */
+    int32_t impl[4];         /* kernel family of each pass: 1 per-slice launches, 2 fused (generic), 3 fused (TMA-staged) */
 } tbrm_sweep_stats;
 
 /* Opaque FBasicRaymarchRenderingResources (RaymarchTypes.h:87-129): data volume, TF texture, light volume,

@@ -12,13 +12,20 @@ for n,view,steps in [(256,(512,512),256.),(512,(1920,1080),512.)]:
     URaymarchUtils.ColorCurveToTexture(res,synth.soft_ct_curve())
     URaymarchUtils.SetWindowingParameters(res,FWindowingParameters(0.45,0.5,True,False))
     w=synth.identity_world()
-    for it in range(3):
+    for sync in (False, True):
+      for it in range(3):
         ms=C.c_float()
         lib.tbrm_timer_begin(res.handle)
         URaymarchUtils.ClearResourceLightVolumes(res,0.0)
-        for l in synth.LIGHTS[:2]: URaymarchUtils.AddDirLightToSingleVolume(res,l,True,w)
+        for l in synth.LIGHTS[:2]: URaymarchUtils.AddDirLightToSingleVolume(res,l,True,w,bGPUSync=sync)
         lib.tbrm_timer_end(res.handle,C.byref(ms))
-        print(n,'sweep reset 2 lights ms',ms.value, flush=True)
+        print(n,'sweep reset 2 lights gpu_sync',sync,'ms',ms.value, flush=True)
+    for li,l in enumerate(synth.LIGHTS):
+        st=FSweepStats(); ms=C.c_float()
+        lib.tbrm_timer_begin(res.handle)
+        URaymarchUtils.AddDirLightToSingleVolume(res,l,True,w,bGPUSync=True,stats=st)
+        lib.tbrm_timer_end(res.handle,C.byref(ms))
+        print(n,'light',li,'faces',st.faces,'fused ms',ms.value, flush=True)
     cam=synth.benchmark_camera(*view)
     out=torch.empty(view[0]*view[1]*4,dtype=torch.float32,device='cuda')
     for it in range(3):

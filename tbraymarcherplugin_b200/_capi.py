@@ -75,6 +75,7 @@ class SweepStats(C.Structure):
         ("voxels", C.c_int64),
         ("kernel_launches", C.c_int32),
         ("faces", C.c_int32 * 4),
+        ("impl", C.c_int32 * 4),
     ]
 
 

@@ -145,6 +145,8 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     if (r->tf) cudaFree(r->tf);
     if (r->counters) cudaFree(r->counters);
     if (r->ring) cudaFree(r->ring);
+    if (r->data_yzx) cudaFree(r->data_yzx);
+    if (r->tables) cudaFree(r->tables);
     if (r->flags) cudaFree(r->flags);
     for (auto& axis : r->rw)
         for (void* b : axis)
@@ -173,6 +175,7 @@ tbrm_status tbrm_upload_volume(tbrm_resources* r, const void* src, int src_is_de
     }
     TBRM_CUDA(cudaMemcpyAsync(r->data, src, bytes, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, r->stream));
     r->data_ready = true;
+    r->data_yzx_valid = false;
     return TBRM_OK;
 }
 
@@ -186,6 +189,7 @@ tbrm_status tbrm_bind_volume_device(tbrm_resources* r, const void* dptr) {
     r->data = const_cast<void*>(dptr);
     r->data_owned = false;
     r->data_ready = true;
+    r->data_yzx_valid = false;
     return TBRM_OK;
 }
 
@@ -274,17 +278,28 @@ static void fill_uniforms(const tbrm_resources& r, const tbrm_light_plan& plan, 
 static tbrm_status run_pass(tbrm_resources& r, const SweepUniforms& u, bool change, int gpu_sync, tbrm_sweep_stats* stats) {
     int launches = 0;
     bool handled = false;
-    const int impl = r.options.sweep_impl;  // 0 auto, 1 per-slice, 2 fused
-    if (impl == 2 || (impl == 0 && gpu_sync)) {
+    int used = 1;
+    // 0 auto (gpu_sync ? fused : per-slice), 1 per-slice, 2 fused (TMA path when eligible), 3 generic fused only
+    const int impl = r.options.sweep_impl;
+    const bool want_fused = impl == 2 || impl == 3 || (impl == 0 && gpu_sync);
+    if (want_fused && impl != 3) {
+        TBRM_CUDA(sweep_pass_tma(r, u, change, &launches, &handled));
+        if (handled) used = 3;
+    }
+    if (want_fused && !handled) {
         TBRM_CUDA(sweep_pass_fused(r, u, change, &launches, &handled));
-        if (!handled && impl == 2) {
+        if (handled) used = 2;
+        if (!handled && impl != 0) {
             set_last_error("fused sweep does not support this configuration");
             return TBRM_ERR_UNSUPPORTED;
         }
     }
     if (!handled) TBRM_CUDA(sweep_pass_per_slice(r, u, change, &launches));
     if (stats) {
-        if (stats->passes < 4) stats->faces[stats->passes] = u.axis * 2 + (u.dirn > 0 ? 1 : 0);
+        if (stats->passes < 4) {
+            stats->faces[stats->passes] = u.axis * 2 + (u.dirn > 0 ? 1 : 0);
+            stats->impl[stats->passes] = used;
+        }
         stats->passes += 1;
         stats->voxels += (int64_t) u.td[0] * u.td[1] * u.td[2];
         stats->kernel_launches += launches;

@@ -151,3 +151,4 @@ cudaError_t sweep_pass_per_slice(tbrm_resources& r, const SweepUniforms& u, bool
 }  // namespace tbrm
 
 #include "sweep_fused.cuh"
+#include "sweep_tma.cuh"

@@ -45,6 +45,11 @@ struct tbrm_resources {
     unsigned int* flags = nullptr;
     size_t flags_count = 0;
     unsigned long long* counters = nullptr;  // device scratch for step / iteration counts
+    // TMA sweep: (y,z,x)-ordered replica of the data volume for sweeps along X, and the per-pass sampler tables
+    void* data_yzx = nullptr;
+    bool data_yzx_valid = false;
+    void* tables = nullptr;
+    size_t tables_bytes = 0;
 
     size_t light_voxels() const { return (size_t) ldims[0] * ldims[1] * ldims[2]; }
     size_t data_voxels() const { return (size_t) ddims[0] * ddims[1] * ddims[2]; }
@@ -62,6 +67,7 @@ inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory
 cudaError_t sweep_fill_buffer(tbrm_resources& r, void* buf, size_t count, float value);
 cudaError_t sweep_pass_per_slice(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches);
 cudaError_t sweep_pass_fused(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
+cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
 cudaError_t clear_light(tbrm_resources& r, float value);
 
 // raymarch.cu

@@ -152,6 +152,7 @@ class FSweepStats:
     voxels: int = 0
     kernel_launches: int = 0
     faces: Tuple[int, ...] = ()
+    impl: Tuple[int, ...] = ()  # 1 per-slice launches, 2 fused (generic), 3 fused (TMA-staged)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -398,6 +399,7 @@ def _fill_stats(dst: Optional[FSweepStats], st: _capi.SweepStats) -> None:
     dst.voxels = int(st.voxels)
     dst.kernel_launches = int(st.kernel_launches)
     dst.faces = tuple(int(f) for f in st.faces if f >= 0)
+    dst.impl = tuple(int(st.impl[i]) for i in range(len(dst.faces)))
 
 
 def plan_dir_light(light_dims: Sequence[int], windowing: FWindowingParameters, light: FDirLightParameters,

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 CT_WINDOW = FWindowingParameters(0.45, 0.5, True, False)
 # sweep implementations under test: 1 = per-slice launches (reference schedule), 2 = fused persistent sweep
-IMPLS = [int(x) for x in os.environ.get("TBRM_TEST_IMPLS", "1,2").split(",")]
+IMPLS = [int(x) for x in os.environ.get("TBRM_TEST_IMPLS", "1,2,3").split(",")]
 
 
 def make_pair(data, curve, windowing, light32=True, half_res=False, border_exact=False, sweep_impl=0, wrap=False):
@@ -48,7 +48,7 @@ WORLDS = {"identity": synth.identity_world, "scaled_rotated": synth.scaled_rotat
 
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("world_name", list(WORLDS))
-@pytest.mark.parametrize("dims", [(32, 32, 32), (40, 24, 56)])
+@pytest.mark.parametrize("dims", [(32, 32, 32), (40, 24, 56), (64, 48, 80), (144, 80, 96)])
 def test_add_dir_light_matches_oracle(dims, world_name, impl):
     data = synth.perlin_ct_volume(dims)
     res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, sweep_impl=impl)
@@ -56,12 +56,14 @@ def test_add_dir_light_matches_oracle(dims, world_name, impl):
     URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
     for light in synth.LIGHTS:
         st = FSweepStats()
-        assert URaymarchUtils.AddDirLightToSingleVolume(res, light, True, world, bGPUSync=(impl == 2), stats=st)
+        assert URaymarchUtils.AddDirLightToSingleVolume(res, light, True, world, bGPUSync=(impl >= 2), stats=st)
         n = ora.add_dir_light(light, True, world)
         assert st.passes == n
-        assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"after adding {light.LightDirection}")
+        if impl == 2 and dims[0] % 16 == 0 and dims[1] % 16 == 0:
+            assert st.impl[0] == 3, f"expected the TMA-staged sweep on the primary axis, got {st.impl}"
+        assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"after adding {light.LightDirection} (faces {st.faces}, impl {st.impl})")
     # removing a light goes through the same kernel with bAdded = -1
-    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[1], False, world, bGPUSync=(impl == 2))
+    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[1], False, world, bGPUSync=(impl >= 2))
     ora.add_dir_light(synth.LIGHTS[1], False, world)
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "after removing L2")
 
@@ -72,7 +74,7 @@ def test_default_tf_sphere_and_nonzero_window_border(impl):
     # window whose zero point (C - W/2 = 0.3) makes the data sampler border colour non-zero (Q1)
     res, ora = make_pair(data, None, FWindowingParameters(0.5, 0.4, False, True), sweep_impl=impl)
     for light in synth.LIGHTS[:2]:
-        URaymarchUtils.AddDirLightToSingleVolume(res, light, True, synth.identity_world(), bGPUSync=(impl == 2))
+        URaymarchUtils.AddDirLightToSingleVolume(res, light, True, synth.identity_world(), bGPUSync=(impl >= 2))
         ora.add_dir_light(light, True, synth.identity_world())
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "sphere / default TF")
 
@@ -84,7 +86,7 @@ def test_g8_and_half_resolution_light_volumes(light32, half_res, impl):
     res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, light32=light32, half_res=half_res, sweep_impl=impl)
     assert res.LightDims == ora.ldims
     for light in synth.LIGHTS[:3]:
-        URaymarchUtils.AddDirLightToSingleVolume(res, light, True, synth.identity_world(), bGPUSync=(impl == 2))
+        URaymarchUtils.AddDirLightToSingleVolume(res, light, True, synth.identity_world(), bGPUSync=(impl >= 2))
         ora.add_dir_light(light, True, synth.identity_world())
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"light32={light32} half_res={half_res}")
 
@@ -95,7 +97,7 @@ def test_g16_and_float_data_volumes(data_dtype, impl):
     base = synth.perlin_ct_volume((28, 28, 28)).astype(np.float32) / 255.0
     data = (base * 65535).astype(np.uint16) if data_dtype == np.uint16 else base.astype(np.float32)
     res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, sweep_impl=impl)
-    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[0], True, synth.identity_world(), bGPUSync=(impl == 2))
+    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[0], True, synth.identity_world(), bGPUSync=(impl >= 2))
     ora.add_dir_light(synth.LIGHTS[0], True, synth.identity_world())
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, str(data_dtype))
 
@@ -108,14 +110,14 @@ def test_change_dir_light_matches_oracle(world_name, impl):
     world = WORLDS[world_name]()
     lights = list(synth.LIGHTS)
     for l in lights:
-        URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=(impl == 2))
+        URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=(impl >= 2))
         ora.add_dir_light(l, True, world)
     fused = fallback = 0
     for step in range(1, 5):  # cfg 3: rotate each light 5 degrees about +Z per update
         for i, l in enumerate(lights):
             new = synth.rotate_about_z(synth.LIGHTS[i], 5.0 * step)
             st = FSweepStats()
-            assert URaymarchUtils.ChangeDirLightInSingleVolume(res, l, new, world, bGPUSync=(impl == 2), stats=st)
+            assert URaymarchUtils.ChangeDirLightInSingleVolume(res, l, new, world, bGPUSync=(impl >= 2), stats=st)
             code = ora.change_dir_light(l, new, world)
             assert st.fell_back == (code >= 100)
             fused += not st.fell_back
@@ -124,7 +126,7 @@ def test_change_dir_light_matches_oracle(world_name, impl):
         assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"after update {step}")
     # a change between lights with different major axes falls back to Remove + Add (LightingShaders.cpp:192-198)
     st = FSweepStats()
-    URaymarchUtils.ChangeDirLightInSingleVolume(res, lights[0], synth.LIGHTS[1], world, bGPUSync=(impl == 2), stats=st)
+    URaymarchUtils.ChangeDirLightInSingleVolume(res, lights[0], synth.LIGHTS[1], world, bGPUSync=(impl >= 2), stats=st)
     ora.change_dir_light(lights[0], synth.LIGHTS[1], world)
     assert st.fell_back and fused > 0
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "after the fallback change")
