@@ -227,6 +227,7 @@ static cudaError_t fused_typed(tbrm_resources& r, const SweepUniforms& u, int* l
     }
     P.ring = (float*) r.ring;
     P.flags = r.flags;
+    r.ring_epoch = 0;  // plain floats go into the ring: the TMA sweep must clear it before trusting tags again
     if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
     const DataT* d = (const DataT*) r.data;
     const float4* tf = r.tf;

@@ -24,7 +24,9 @@ constexpr int kTmaThreads = 256;
 constexpr int kTW = 64, kTH = 8;  // tile: 64 x 8 pixels, 2 adjacent pixels per thread
 constexpr int kSB = 4;            // slices per pipeline stage
 constexpr int kStages = 3;
-constexpr int kRingDepth = 8;
+constexpr int kRingDepth = 16;
+constexpr int kHaloPerThread = 2;          // footprint cells owned by other tiles, fetched per thread
+constexpr int kFpW = kTW + 4, kFpH = kTH + 4;  // SMEM footprint of the previous slice
 
 struct AxisTab {  // per native coordinate c of one axis (device pointers)
     const float* S;   // GetUVW(c) + UVWOffset
@@ -49,6 +51,7 @@ struct TmaParams {
     int bmin[2], bext[2];   // footprint offset / extent in the buffer plane
     int data_dims_t[3];     // data dims in transposed (p,q,s) order
     int stage_bytes, light_bytes, data_bytes;
+    unsigned int epoch;     // distinguishes the ring tags of successive passes
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
@@ -95,291 +98,11 @@ __device__ __forceinline__ void tma_wait_all() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// correctly rounded v/255 for v in 0..255 without a division (Markstein: q = v*r; q += (v - q*255)*r)
-__device__ __forceinline__ float decode_u8(uint32_t v) {
-    const float x = (float) v;
-    const float r = 0.003921568859368563f;  // RN(1/255)
-    const float q = x * r;
-    const float e = __fmaf_rn(-q, 255.0f, x);
-    return __fmaf_rn(e, r, q);
-}
-// correctly rounded x / w given rw = RN(1/w)
-__device__ __forceinline__ float div_markstein(float x, float w, float rw) {
-    const float q = x * rw;
-    const float e = __fmaf_rn(-q, w, x);
-    return __fmaf_rn(e, rw, q);
-}
+}  // namespace tbrm
 
-// opacity toward the light of one voxel given its trilinear data value (WindowedSampling.usf:20-37), alpha only
-__device__ __forceinline__ float opacity_from_value(float v, const Windowing& win, float rwidth, const float* s_alpha, float step) {
-    const float pos = div_markstein(v - win.center + (win.width / 2.0f), win.width, rwidth);
-    if ((pos < 0.0f && win.low > 0.0f) || (pos > 1.0f && win.high > 0.0f)) return 0.0f;
-    int i0, i1;
-    float f;
-    tf_taps(pos, i0, i1, f);
-    const float a = lerpf(s_alpha[i0], s_alpha[i1], f);
-    return step_opacity(a, step);
-}
+#include "sweep_tma_kernel.cuh"
 
-// AXIS = native sweep axis. Transposed coordinates: AXIS 2 -> (p,q,s) = (x,y,z); 1 -> (x,z,y); 0 -> (y,z,x).
-template <int AXIS, bool CLIP>
-__global__ void __launch_bounds__(kTmaThreads, 4)
-    sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map, const TmaParams P,
-                     const float4* __restrict__ tf) {
-    constexpr int PA = (AXIS == 0) ? 1 : 0;                 // native axis of p
-    constexpr int QA = (AXIS == 2) ? 1 : 2;                 // native axis of q
-    constexpr int SA = AXIS;                                // native axis of s
-    const SweepUniforms& U = P.U;
-    const int tx = U.td[0], ty = U.td[1], ns = U.td[2];
-    const int tile = blockIdx.x, tid = threadIdx.x;
-    const int tix = tile % P.ntx, tiy = tile / P.ntx;
-    const int x0 = tix * kTW, y0 = tiy * kTH;
-    const size_t plane = (size_t) tx * ty;
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* stage_base = smem;
-    float* s_fp = (float*) (smem + (size_t) kStages * P.stage_bytes);  // footprint of the previous slice
-    float* s_alpha = s_fp + (kTW + 4) * (kTH + 4);
-    uint64_t* s_bar = (uint64_t*) (s_alpha + 256);
-    __shared__ int s_up[kFusedMaxDeps], s_down[kFusedMaxDeps];
-    __shared__ int s_nup, s_ndown;
-
-    const int fx0 = x0 + P.bmin[0], fy0 = y0 + P.bmin[1], FW = P.bext[0], FH = P.bext[1];
-    if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // tiles whose published slice we read (footprint) and tiles that read ours
-        int nup = 0, ndown = 0;
-        const int ax = max(fx0, 0) / kTW, bx = min(fx0 + FW - 1, tx - 1) / kTW;
-        const int ay = max(fy0, 0) / kTH, by = min(fy0 + FH - 1, ty - 1) / kTH;
-        if (fx0 + FW > 0 && fx0 < tx && fy0 + FH > 0 && fy0 < ty)
-            for (int j = ay; j <= by; ++j)
-                for (int i = ax; i <= bx; ++i)
-                    if ((i != tix || j != tiy) && nup < kFusedMaxDeps) s_up[nup++] = j * P.ntx + i;
-        // tile (i,j) reads [i*TW + bmin, i*TW + bmin + FW) : it touches us iff that interval meets [x0, x0 + TW)
-        for (int j = 0; j < P.nty; ++j) {
-            const int gy = j * kTH + P.bmin[1];
-            if (gy + FH <= y0 || gy >= y0 + kTH) continue;
-            for (int i = 0; i < P.ntx; ++i) {
-                const int gx = i * kTW + P.bmin[0];
-                if (gx + FW <= x0 || gx >= x0 + kTW) continue;
-                if ((i != tix || j != tiy) && ndown < kFusedMaxDeps) s_down[ndown++] = j * P.ntx + i;
-            }
-        }
-        s_nup = nup, s_ndown = ndown;
-    }
-    s_alpha[tid] = __ldg(&tf[tid]).w;
-
-    // ---- per-thread invariants: 2 adjacent pixels (px, px+1) of row py --------------------------------------
-    const int lx = (tid & 31) * 2, ly = tid >> 5;
-    const int px = x0 + lx, py = y0 + ly;
-    const bool v0 = px < tx && py < ty, v1 = px + 1 < tx && py < ty;
-    const int pxc = min(px, tx - 1), px1c = min(px + 1, tx - 1), pyc = min(py, ty - 1);
-    // data taps along p (3 columns shared by the two pixels) and q (2 rows)
-    const int2 mp0 = __ldg(&P.A.ax[PA].meta[pxc]), mp1 = __ldg(&P.A.ax[PA].meta[px1c]), mq = __ldg(&P.A.ax[QA].meta[pyc]);
-    const float fp0 = __ldg(&P.A.ax[PA].f[pxc]), fp1 = __ldg(&P.A.ax[PA].f[px1c]), fq = __ldg(&P.A.ax[QA].f[pyc]);
-    const int dN_p = P.data_dims_t[0], dN_q = P.data_dims_t[1], dN_s = P.data_dims_t[2];
-    const int col = mp0.x - (x0 + P.dmin[0]);  // column of the first tap inside the data box
-    const int rowq = mq.x - (y0 + P.dmin[1]);
-    const bool inP0 = (unsigned) mp0.x < (unsigned) dN_p, inP1 = (unsigned) (mp0.x + 1) < (unsigned) dN_p,
-               inP2 = (unsigned) (mp0.x + 2) < (unsigned) dN_p;
-    const bool inQ0 = (unsigned) mq.x < (unsigned) dN_q, inQ1 = (unsigned) (mq.x + 1) < (unsigned) dN_q;
-    const bool all_pq = inP0 && inP1 && inP2 && inQ0 && inQ1;
-    const bool inside_pq0 = mp0.y && mq.y, inside_pq1 = mp1.y && mq.y;
-    float Sp0 = 0.f, Sp1 = 0.f, Sq = 0.f;
-    if (CLIP) {
-        Sp0 = __ldg(&P.A.ax[PA].S[pxc]), Sp1 = __ldg(&P.A.ax[PA].S[px1c]), Sq = __ldg(&P.A.ax[QA].S[pyc]);
-    }
-    // read-buffer bilinear: 3 columns x 2 rows of the footprint
-    const int2 bxa = __ldg(&P.A.bx[pxc]), bxb = __ldg(&P.A.bx[px1c]), bya = __ldg(&P.A.by[pyc]);
-    const float bfx0 = __int_as_float(bxa.y), bfx1 = __int_as_float(bxb.y), bfy = __int_as_float(bya.y);
-    const int fcol = bxa.x - fx0, frow = bya.x - fy0;
-    const float rwidth = 1.0f / U.win.width;
-    const float step = U.a.step;
-    const int shift = (col & 3) * 8;
-    const int col4 = col & ~3;
-    __syncthreads();
-    const int nup = s_nup, ndown = s_ndown;
-
-    const int nblocks = (ns + kSB - 1) / kSB;
-    // native coordinates of block b's light box origin along s
-    // blocks are aligned to multiples of kSB in native coordinates (TMA: 16-byte aligned inner coordinate when the
-    // sweep axis is x); a descending sweep visits them last-to-first
-    auto block_s0 = [&](int b) { return (U.dirn > 0 ? b : nblocks - 1 - b) * kSB; };
-    auto issue_load = [&](int b) {
-        const int st = b % kStages;
-        unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
-        mbar_expect_tx(&s_bar[st], (uint32_t) (P.light_bytes + P.data_bytes));
-        const int s0 = block_s0(b);
-        int lc[3], dc[3];
-        lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;  // light map is over native (x,y,z)
-        tma_load_3d(sb, &light_map, lc[0], lc[1], lc[2], &s_bar[st]);
-        // data map: native dims for Z / Y sweeps, the (y,z,x) replica for X sweeps, i.e. always (p,q,s)-ordered for X
-        if (AXIS == 0) {
-            tma_load_3d(sb + P.light_bytes, &data_map, x0 + P.dmin[0], y0 + P.dmin[1], s0 + P.dmin[2], &s_bar[st]);
-        } else {
-            dc[PA] = x0 + P.dmin[0], dc[QA] = y0 + P.dmin[1], dc[SA] = s0 + P.dmin[2];
-            tma_load_3d(sb + P.light_bytes, &data_map, dc[0], dc[1], dc[2], &s_bar[st]);
-        }
-    };
-    if (tid == 0) issue_load(0);
-
-    for (int b = 0; b < nblocks; ++b) {
-        const int st = b % kStages;
-        if (tid == 0 && b + 1 < nblocks) {
-            tma_wait_read<1>();  // the store that last read stage (b+1)%3 (block b-2) has finished reading SMEM
-            issue_load(b + 1);
-        }
-        mbar_wait(&s_bar[st], (uint32_t) ((b / kStages) & 1));
-        unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
-        float* s_light = (float*) sb;
-        const unsigned char* s_data = sb + P.light_bytes;
-        const int s0 = block_s0(b);
-
-#pragma unroll 1
-        for (int sl = 0; sl < kSB; ++sl) {
-            const int loop = s0 + (U.dirn > 0 ? sl : kSB - 1 - sl);
-            if (loop >= ns) continue;
-            const int k = U.dirn > 0 ? loop : ns - 1 - loop;  // position in sweep order
-            // ---- A: opacity toward the light for this thread's two voxels (independent of the previous slice) ----
-            const int2 ms = __ldg(&P.A.ax[SA].meta[loop]);
-            const float fs = __ldg(&P.A.ax[SA].f[loop]);
-            const int rows = ms.x - (s0 + P.dmin[2]);
-            const bool inS0 = (unsigned) ms.x < (unsigned) dN_s, inS1 = (unsigned) (ms.x + 1) < (unsigned) dN_s;
-            float w0 = 1.0f, w1 = 1.0f;
-            if (CLIP) {
-                const float Ss = __ldg(&P.A.ax[SA].S[loop]);
-                float S0[3], S1[3];
-                S0[PA] = Sp0, S0[QA] = Sq, S0[SA] = Ss;
-                S1[PA] = Sp1, S1[QA] = Sq, S1[SA] = Ss;
-                const float rx = (float) U.ldims[0], ry = (float) U.ldims[1], rz = (float) U.ldims[2];
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    const float* S = v ? S1 : S0;
-                    const float dist = dot3(S[0] - U.clip_center[0], S[1] - U.clip_center[1], S[2] - U.clip_center[2], U.clip_dir[0],
-                                            U.clip_dir[1], U.clip_dir[2]);
-                    const float ox = S[0] - (S[0] + U.clip_dir[0] * dist), oy = S[1] - (S[1] + U.clip_dir[1] * dist),
-                                oz = S[2] - (S[2] + U.clip_dir[2] * dist);
-                    const float vx = ox * rx, vy = oy * ry, vz = oz * rz;
-                    const float vdist = sqrtf(dot3(vx, vy, vz, vx, vy, vz));
-                    const float sgn = dist > 0.0f ? 1.0f : (dist < 0.0f ? -1.0f : 0.0f);
-                    const float w = fminf(fmaxf(0.5f + (0.57735026919f * vdist * sgn), 0.0f), 1.0f);
-                    if (v) w1 = w; else w0 = w;
-                }
-            }
-            const bool g0 = v0 && w0 > 0.0f && inside_pq0 && ms.y, g1 = v1 && w1 > 0.0f && inside_pq1 && ms.y;
-            float cs0 = 0.0f, cs1 = 0.0f;
-            if (g0 || g1) {
-                // 4 rows (q, s) x 3 columns of taps; two aligned 32-bit loads + a funnel shift per row
-                float t[3][2][2];
-                const bool all_in = all_pq && inS0 && inS1;
-#pragma unroll
-                for (int js = 0; js < 2; ++js)
-#pragma unroll
-                    for (int jq = 0; jq < 2; ++jq) {
-                        const unsigned char* rowp = s_data + (size_t) (rowq + jq) * P.ds_q + (size_t) (rows + js) * P.ds_s + col4;
-                        const uint32_t a = *(const uint32_t*) rowp, bb = *(const uint32_t*) (rowp + 4);
-                        const uint32_t w = __funnelshift_r(a, bb, shift);
-                        t[0][jq][js] = decode_u8(w & 0xffu);
-                        t[1][jq][js] = decode_u8((w >> 8) & 0xffu);
-                        t[2][jq][js] = decode_u8((w >> 16) & 0xffu);
-                    }
-                if (!all_in) {
-                    const bool ip[3] = {inP0, inP1, inP2}, iq[2] = {inQ0, inQ1}, is[2] = {inS0, inS1};
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int jq = 0; jq < 2; ++jq)
-#pragma unroll
-                            for (int js = 0; js < 2; ++js)
-                                if (!(ip[c] && iq[jq] && is[js])) t[c][jq][js] = U.data_border;
-                }
-                float val0, val1;
-                if (AXIS == 2) {  // x = p, y = q, z = s
-                    const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
-                    const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
-                    val0 = lerpf(lerpf(a00, a10, fq), lerpf(a01, a11, fq), fs);
-                    const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
-                    const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
-                    val1 = lerpf(lerpf(b00, b10, fq), lerpf(b01, b11, fq), fs);
-                } else if (AXIS == 1) {  // x = p, y = s, z = q
-                    const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
-                    const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
-                    val0 = lerpf(lerpf(a00, a01, fs), lerpf(a10, a11, fs), fq);
-                    const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
-                    const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
-                    val1 = lerpf(lerpf(b00, b01, fs), lerpf(b10, b11, fs), fq);
-                } else {  // x = s, y = p, z = q
-                    const float d00 = lerpf(t[0][0][0], t[0][0][1], fs), d10 = lerpf(t[1][0][0], t[1][0][1], fs),
-                                d20 = lerpf(t[2][0][0], t[2][0][1], fs);
-                    const float d01 = lerpf(t[0][1][0], t[0][1][1], fs), d11 = lerpf(t[1][1][0], t[1][1][1], fs),
-                                d21 = lerpf(t[2][1][0], t[2][1][1], fs);
-                    val0 = lerpf(lerpf(d00, d10, fp0), lerpf(d01, d11, fp0), fq);
-                    val1 = lerpf(lerpf(d10, d20, fp1), lerpf(d11, d21, fp1), fq);
-                }
-                if (g0) cs0 = opacity_from_value(val0, U.win, rwidth, s_alpha, step) * w0;
-                if (g1) cs1 = opacity_from_value(val1, U.win, rwidth, s_alpha, step) * w1;
-            }
-
-            // ---- B: wait for the tiles we read (slice k-1 published) and the tiles that read the slot we overwrite ----
-            if (k > 0) {
-                if (tid < nup) {
-                    const unsigned int* f = P.flags + (size_t) s_up[tid] * kFlagStride;
-                    while (ld_acquire(f) < (unsigned) k) {
-                    }
-                } else if (tid >= 32 && tid - 32 < ndown && k >= kRingDepth) {
-                    const unsigned int* f = P.flags + (size_t) s_down[tid - 32] * kFlagStride;
-                    while (ld_acquire(f) < (unsigned) (k - kRingDepth + 2)) {
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- C: footprint of slice k-1 (L2 ring; slice -1 is the cleared buffer = LightAlpha) ----
-            {
-                const float* rd = P.ring + (size_t) ((k + kRingDepth - 1) % kRingDepth) * plane;
-                for (int c = tid; c < FW * FH; c += kTmaThreads) {
-                    const int gx = fx0 + c % FW, gy = fy0 + c / FW;
-                    const bool in = (unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty;
-                    s_fp[c] = in ? (k > 0 ? __ldcg(rd + (size_t) gx + (size_t) tx * gy) : U.a.light_alpha) : U.a.border;
-                }
-            }
-            __syncthreads();
-            // ---- D: propagate, publish to the ring, accumulate into the light brick ----
-            {
-                const float* r0 = s_fp + frow * FW + fcol;
-                const float* r1 = r0 + FW;
-                const float t00 = r0[0], t10 = r0[1], t20 = r0[2], t01 = r1[0], t11 = r1[1], t21 = r1[2];
-                const float prev0 = lerpf(lerpf(t00, t10, bfx0), lerpf(t01, t11, bfx0), bfy);
-                const float prev1 = lerpf(lerpf(t10, t20, bfx1), lerpf(t11, t21, bfx1), bfy);
-                const float cur0 = prev0 * (1.0f - cs0), cur1 = prev1 * (1.0f - cs1);
-                float* wr = P.ring + (size_t) (k % kRingDepth) * plane + (size_t) px + (size_t) tx * py;
-                if (v1)
-                    __stcg((float2*) wr, make_float2(cur0, cur1));
-                else if (v0)
-                    __stcg(wr, cur0);
-                const int sli = loop - s0;
-                float* lp = s_light + lx * P.ls_p + ly * P.ls_q + sli * P.ls_s;
-                if (v0 && fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
-                if (v1 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                st_release(P.flags + (size_t) tile * kFlagStride, (unsigned) (k + 1));
-            }
-        }
-        // ---- write the updated light brick back ----
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            int lc[3];
-            lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;
-            tma_store_3d(&light_map, lc[0], lc[1], lc[2], s_light);
-            tma_commit();
-        }
-    }
-    if (tid == 0) tma_wait_all<0>();
-}
+namespace tbrm {
 
 // ---- host side -------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -569,7 +292,14 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     P.dext[0] = (ext_p + 4 + 15) / 16 * 16, P.dext[1] = ext_q, P.dext[2] = ext_s;
     if (P.dext[0] > 256 || P.dext[1] > 256 || P.dext[2] > 256) return cudaSuccess;
     for (int d = 0; d < 2; ++d) P.bmin[d] = T.bmin[d], P.bext[d] = (d ? kTH : kTW) + (T.bmax[d] - T.bmin[d]) + 1;
-    if (P.bext[0] > kTW + 4 || P.bext[1] > kTH + 4) return cudaSuccess;
+    if (P.bext[0] > kFpW || P.bext[1] > kFpH) return cudaSuccess;
+    if (u.td[2] >= 65000) return cudaSuccess;  // slice index + 1 must fit the 16-bit tag field
+    // halo cells (footprint cells of other tiles) must fit kHaloPerThread per thread
+    {
+        const int ow = std::max(0, std::min(P.bmin[0] + P.bext[0], kTW) - std::max(P.bmin[0], 0));
+        const int oh = ow > 0 ? std::max(0, std::min(P.bmin[1] + P.bext[1], kTH) - std::max(P.bmin[1], 0)) : 0;
+        if (P.bext[0] * P.bext[1] - ow * oh > kHaloPerThread * kTmaThreads) return cudaSuccess;
+    }
     // dependency lists must fit
     {
         const long long nx = (long long) (P.bext[0] + kTW - 1) / kTW + 1, ny = (long long) (P.bext[1] + kTH - 1) / kTH + 1;
@@ -600,7 +330,7 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     P.light_bytes = kTW * kTH * kSB * 4;
     P.data_bytes = P.dext[0] * P.dext[1] * P.dext[2];
     P.stage_bytes = (P.light_bytes + P.data_bytes + 16 + 127) / 128 * 128;
-    const size_t smem = (size_t) kStages * P.stage_bytes + ((kTW + 4) * (kTH + 4) + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t) kStages * P.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
 
     const bool clip = !clip_is_inactive(u, T);
     const void* kern = nullptr;
@@ -618,13 +348,21 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     if ((long long) sms * per_sm < ntiles) return cudaSuccess;  // the plane does not fit one co-resident wave
 
     // scratch: ring, flags, tables
-    const size_t ring_bytes = (size_t) kRingDepth * tx * ty * sizeof(float);
+    const size_t ring_bytes = (size_t) kRingDepth * tx * ty * sizeof(unsigned long long);
     if (r.ring_bytes < ring_bytes) {
         if (r.ring) cudaStreamSynchronize(r.stream), cudaFree(r.ring);
         r.ring = nullptr, r.ring_bytes = 0;
         if ((e = cudaMalloc(&r.ring, ring_bytes)) != cudaSuccess) return e;
         r.ring_bytes = ring_bytes;
+        r.ring_epoch = 0;
     }
+    // ring tags are (epoch << 16 | slice + 1): a fresh epoch per pass means cells left by earlier passes never match.
+    // Clear the ring when it is new, when the generic fused kernel (plain floats) used it since, or when the epoch wraps.
+    if (r.ring_epoch == 0 || r.ring_epoch >= 0xffffu) {
+        if ((e = cudaMemsetAsync(r.ring, 0, r.ring_bytes, r.stream)) != cudaSuccess) return e;
+        r.ring_epoch = 0;
+    }
+    P.epoch = ++r.ring_epoch;
     if (r.flags_count < (size_t) ntiles * kFlagStride) {
         if (r.flags) cudaStreamSynchronize(r.stream), cudaFree(r.flags);
         r.flags = nullptr, r.flags_count = 0;

@@ -1,0 +1,377 @@
+// sweep_tma_kernel.cuh — device code of the TMA-staged fused plane-sweep (included by sweep_tma.cuh).
+#pragma once
+
+namespace tbrm {
+
+// 64-bit ring cell = (tag << 32) | float bits. One aligned 64-bit store / load is single-copy atomic, so a reader that
+// sees the expected tag also sees the matching value: no fence and no separate flag on the critical path.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// correctly rounded v/255 for v in 0..255 without a division (Markstein: q = v*r; q += (v - q*255)*r)
+__device__ __forceinline__ float decode_u8(uint32_t v) {
+    const float x = (float) v;
+    const float r = 0.003921568859368563f;  // RN(1/255)
+    const float q = x * r;
+    const float e = __fmaf_rn(-q, 255.0f, x);
+    return __fmaf_rn(e, r, q);
+}
+// correctly rounded x / w given rw = RN(1/w)
+__device__ __forceinline__ float div_markstein(float x, float w, float rw) {
+    const float q = x * rw;
+    const float e = __fmaf_rn(-q, w, x);
+    return __fmaf_rn(e, rw, q);
+}
+
+// opacity toward the light of one voxel given its trilinear data value (WindowedSampling.usf:20-37), alpha only
+__device__ __forceinline__ float opacity_from_value(float v, const Windowing& win, float rwidth, const float* s_alpha, float step) {
+    const float pos = div_markstein(v - win.center + (win.width / 2.0f), win.width, rwidth);
+    if ((pos < 0.0f && win.low > 0.0f) || (pos > 1.0f && win.high > 0.0f)) return 0.0f;
+    int i0, i1;
+    float f;
+    tf_taps(pos, i0, i1, f);
+    const float a = lerpf(s_alpha[i0], s_alpha[i1], f);
+    return step_opacity(a, step);
+}
+
+// AXIS = native sweep axis. Transposed coordinates: AXIS 2 -> (p,q,s) = (x,y,z); 1 -> (x,z,y); 0 -> (y,z,x).
+//
+// Per slice k every thread
+//  (a) issues the loads of the <= 2 halo cells it fetches from the L2 ring (slice k-1 of the upstream tiles);
+//  (b) computes the opacity toward the light of its two voxels from the TMA-staged data brick — the bulk of the work,
+//      independent of the previous slice, which hides the ring latency;
+//  (c) checks the halo tags (re-polls only while the upstream tile is not yet ahead) and parks the values in SMEM;
+//  (d) after ONE block barrier propagates: previous-slice taps from SMEM (own tile forwarded through SMEM, halo from the
+//      ring), extinction, export of the cells other tiles read, accumulation into the light brick in SMEM.
+template <int AXIS, bool CLIP>
+__global__ void __launch_bounds__(kTmaThreads, 4)
+    sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map, const TmaParams P,
+                     const float4* __restrict__ tf) {
+    constexpr int PA = (AXIS == 0) ? 1 : 0;  // native axis of p
+    constexpr int QA = (AXIS == 2) ? 1 : 2;  // native axis of q
+    constexpr int SA = AXIS;                 // native axis of s
+    const SweepUniforms& U = P.U;
+    const int tx = U.td[0], ty = U.td[1], ns = U.td[2];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int tix = tile % P.ntx, tiy = tile / P.ntx;
+    const int x0 = tix * kTW, y0 = tiy * kTH;
+    const size_t plane = (size_t) tx * ty;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* stage_base = smem;
+    float* s_fp = (float*) (smem + (size_t) kStages * P.stage_bytes);  // 2 x footprint (ping-pong over slices)
+    float* s_alpha = s_fp + 2 * kFpW * kFpH;
+    uint64_t* s_bar = (uint64_t*) (s_alpha + 256);
+    __shared__ int s_down[kFusedMaxDeps];
+    __shared__ int s_ndown;
+
+    const int fx0 = x0 + P.bmin[0], fy0 = y0 + P.bmin[1], FW = P.bext[0], FH = P.bext[1];
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) mbar_init(&s_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // tiles that read cells of ours: tile (i,j) reads [i*TW + bmin, +FW) x [j*TH + bmin, +FH)
+        int ndown = 0;
+        for (int j = 0; j < P.nty; ++j) {
+            const int gy = j * kTH + P.bmin[1];
+            if (gy + FH <= y0 || gy >= y0 + kTH) continue;
+            for (int i = 0; i < P.ntx; ++i) {
+                const int gx = i * kTW + P.bmin[0];
+                if (gx + FW <= x0 || gx >= x0 + kTW) continue;
+                if ((i != tix || j != tiy) && ndown < kFusedMaxDeps) s_down[ndown++] = j * P.ntx + i;
+            }
+        }
+        s_ndown = ndown;
+    }
+    s_alpha[tid] = __ldg(&tf[tid]).w;
+    // footprint buffers: out-of-plane cells hold the sampler border colour for good, in-plane cells start as the
+    // cleared buffer (LightAlpha) = "slice -1"
+    for (int c = tid; c < kFpW * kFpH; c += kTmaThreads) {
+        const int gx = fx0 + c % kFpW, gy = fy0 + c / kFpW;
+        const bool in = (unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty;
+        const float v = in ? U.a.light_alpha : U.a.border;
+        s_fp[c] = v;
+        s_fp[kFpW * kFpH + c] = v;
+    }
+
+    // ---- per-thread invariants: 2 adjacent pixels (px, px+1) of row py --------------------------------------
+    const int lx = (tid & 31) * 2, ly = tid >> 5;
+    const int px = x0 + lx, py = y0 + ly;
+    const bool v0 = px < tx && py < ty, v1 = px + 1 < tx && py < ty;
+    const int pxc = min(px, tx - 1), px1c = min(px + 1, tx - 1), pyc = min(py, ty - 1);
+    const int2 mp0 = __ldg(&P.A.ax[PA].meta[pxc]), mp1 = __ldg(&P.A.ax[PA].meta[px1c]), mq = __ldg(&P.A.ax[QA].meta[pyc]);
+    const float fp0 = __ldg(&P.A.ax[PA].f[pxc]), fp1 = __ldg(&P.A.ax[PA].f[px1c]), fq = __ldg(&P.A.ax[QA].f[pyc]);
+    const int dN_p = P.data_dims_t[0], dN_q = P.data_dims_t[1], dN_s = P.data_dims_t[2];
+    const int col = mp0.x - (x0 + P.dmin[0]);  // column of the first tap inside the data box
+    const int rowq = mq.x - (y0 + P.dmin[1]);
+    const bool inP0 = (unsigned) mp0.x < (unsigned) dN_p, inP1 = (unsigned) (mp0.x + 1) < (unsigned) dN_p,
+               inP2 = (unsigned) (mp0.x + 2) < (unsigned) dN_p;
+    const bool inQ0 = (unsigned) mq.x < (unsigned) dN_q, inQ1 = (unsigned) (mq.x + 1) < (unsigned) dN_q;
+    const bool all_pq = inP0 && inP1 && inP2 && inQ0 && inQ1;
+    const bool inside_pq0 = v0 && mp0.y && mq.y, inside_pq1 = v1 && mp1.y && mq.y;
+    float Sp0 = 0.f, Sp1 = 0.f, Sq = 0.f;
+    if (CLIP) {
+        Sp0 = __ldg(&P.A.ax[PA].S[pxc]), Sp1 = __ldg(&P.A.ax[PA].S[px1c]), Sq = __ldg(&P.A.ax[QA].S[pyc]);
+    }
+    const int2 bxa = __ldg(&P.A.bx[pxc]), bxb = __ldg(&P.A.bx[px1c]), bya = __ldg(&P.A.by[pyc]);
+    const float bfx0 = __int_as_float(bxa.y), bfx1 = __int_as_float(bxb.y), bfy = __int_as_float(bya.y);
+    const int tap_idx = (bya.x - fy0) * kFpW + (bxa.x - fx0);  // first of the 3 x 2 read-buffer taps
+    // where this thread's own output lives in the footprint (if the footprint covers it)
+    const bool own_in0 = v0 && px >= fx0 && px < fx0 + FW && py >= fy0 && py < fy0 + FH;
+    const bool own_in1 = v1 && px + 1 >= fx0 && px + 1 < fx0 + FW && py >= fy0 && py < fy0 + FH;
+    const int own_idx = (py - fy0) * kFpW + (px - fx0);
+    // is a pixel read by another tile? tile (i,j) reads [i*TW + bmin, +FW) x [j*TH + bmin, +FH)
+    auto exported = [&](int gx, int gy) {
+        const int rx = gx - P.bmin[0], ry = gy - P.bmin[1];  // tile origin i*TW must lie in (rx - FW, rx]
+        const int ia = max(0, (rx - FW + kTW) / kTW), ib = rx >= 0 ? min(P.ntx - 1, rx / kTW) : -1;
+        const int ja = max(0, (ry - FH + kTH) / kTH), jb = ry >= 0 ? min(P.nty - 1, ry / kTH) : -1;
+        for (int j = ja; j <= jb; ++j)
+            for (int i = ia; i <= ib; ++i) {
+                const int gx0 = i * kTW + P.bmin[0], gy0 = j * kTH + P.bmin[1];
+                if ((i != tix || j != tiy) && gx >= gx0 && gx < gx0 + FW && gy >= gy0 && gy < gy0 + FH) return true;
+            }
+        return false;
+    };
+    const bool exp0 = v0 && exported(px, py), exp1 = v1 && exported(px + 1, py);
+    // halo cells this thread fetches: footprint cells inside the plane that belong to other tiles
+    int halo_fp[kHaloPerThread], halo_ring[kHaloPerThread];
+    {
+        const int ox0 = max(fx0, x0), ox1 = min(fx0 + FW, x0 + kTW), oy0 = max(fy0, y0), oy1 = min(fy0 + FH, y0 + kTH);
+        const int ow = max(0, ox1 - ox0), oh = (ow > 0) ? max(0, oy1 - oy0) : 0;
+        const int top = (oh > 0 ? oy0 - fy0 : FH) * FW, mid = oh * (FW - ow);
+#pragma unroll
+        for (int i = 0; i < kHaloPerThread; ++i) {
+            int h = tid + i * kTmaThreads, gx = -1, gy = -1;
+            halo_fp[i] = -1, halo_ring[i] = 0;
+            if (h < top) {
+                gy = fy0 + h / FW, gx = fx0 + h % FW;
+            } else if (h - top < mid) {
+                h -= top;
+                const int r = h / (FW - ow), c = h % (FW - ow);
+                gy = oy0 + r;
+                gx = (c < ox0 - fx0) ? fx0 + c : c + ow + fx0;
+            } else if (oh > 0) {
+                h -= top + mid;
+                gy = oy1 + h / FW, gx = fx0 + h % FW;
+                if (gy >= fy0 + FH) gy = -1;
+            }
+            if ((unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty) {
+                halo_fp[i] = (gy - fy0) * kFpW + (gx - fx0);
+                halo_ring[i] = gy * tx + gx;
+            }
+        }
+    }
+    const float rwidth = 1.0f / U.win.width;
+    const float step = U.a.step;
+    const int shift = (col & 3) * 8;
+    const int thread_data = rowq * P.ds_q + (col & ~3);
+    const int light_off = lx * P.ls_p + ly * P.ls_q;
+    unsigned long long* const ring = (unsigned long long*) P.ring;
+    const unsigned int tag_base = P.epoch << 16;
+    __syncthreads();
+    const int ndown = s_ndown;
+
+    const int nblocks = (ns + kSB - 1) / kSB;
+    // blocks are aligned to multiples of kSB in native coordinates (TMA: 16-byte aligned inner coordinate when the
+    // sweep axis is x); a descending sweep visits them last-to-first
+    auto block_s0 = [&](int b) { return (U.dirn > 0 ? b : nblocks - 1 - b) * kSB; };
+    auto issue_load = [&](int b) {
+        const int st = b % kStages;
+        unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
+        mbar_expect_tx(&s_bar[st], (uint32_t) (P.light_bytes + P.data_bytes));
+        const int s0 = block_s0(b);
+        int lc[3], dc[3];
+        lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;  // light map is over native (x,y,z)
+        tma_load_3d(sb, &light_map, lc[0], lc[1], lc[2], &s_bar[st]);
+        // data map: native dims for Z / Y sweeps, the (y,z,x) replica for X sweeps, i.e. (p,q,s)-ordered for X
+        if (AXIS == 0) {
+            tma_load_3d(sb + P.light_bytes, &data_map, x0 + P.dmin[0], y0 + P.dmin[1], s0 + P.dmin[2], &s_bar[st]);
+        } else {
+            dc[PA] = x0 + P.dmin[0], dc[QA] = y0 + P.dmin[1], dc[SA] = s0 + P.dmin[2];
+            tma_load_3d(sb + P.light_bytes, &data_map, dc[0], dc[1], dc[2], &s_bar[st]);
+        }
+    };
+    if (tid == 0) issue_load(0);
+
+    for (int b = 0; b < nblocks; ++b) {
+        const int st = b % kStages;
+        if (tid == 0 && b + 1 < nblocks) {
+            tma_wait_read<1>();  // the store that last read stage (b+1)%3 (block b-2) has finished reading SMEM
+            issue_load(b + 1);
+        }
+        mbar_wait(&s_bar[st], (uint32_t) ((b / kStages) & 1));
+        unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
+        float* s_light = (float*) sb;
+        const unsigned char* s_data = sb + P.light_bytes;
+        const int s0 = block_s0(b);
+
+#pragma unroll 1
+        for (int sl = 0; sl < kSB; ++sl) {
+            const int loop = s0 + (U.dirn > 0 ? sl : kSB - 1 - sl);
+            if (loop >= ns) continue;
+            const int k = U.dirn > 0 ? loop : ns - 1 - loop;  // position in sweep order
+            float* fp_cur = s_fp + (k & 1) * (kFpW * kFpH);
+            float* fp_next = s_fp + ((k + 1) & 1) * (kFpW * kFpH);
+            // ---- (a) issue the halo loads of slice k-1 (and, every 4th slice, the back-pressure probes) ----
+            const unsigned int want_tag = tag_base + (unsigned) k;  // slice k-1 carries tag k
+            const unsigned long long* rd = ring + (size_t) ((k + kRingDepth - 1) % kRingDepth) * plane;
+            unsigned long long hv[kHaloPerThread];
+#pragma unroll
+            for (int i = 0; i < kHaloPerThread; ++i) hv[i] = 0;
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < kHaloPerThread; ++i)
+                    if (halo_fp[i] >= 0) hv[i] = ld_relaxed_u64(rd + halo_ring[i]);
+            }
+            // a ring slot is reused every kRingDepth slices: before exporting slices k..k+3 every reader must have
+            // consumed slice k+3-kRingDepth, i.e. passed the barrier of its slice k+4-kRingDepth
+            const bool probe = (k & 3) == 0 && k + 4 > kRingDepth && tid < ndown;
+            unsigned int pv = 0;
+            if (probe) pv = ld_relaxed_u32(P.flags + (size_t) s_down[tid] * kFlagStride);
+
+            // ---- (b) opacity toward the light for this thread's two voxels (independent of the previous slice) ----
+            const int2 ms = __ldg(&P.A.ax[SA].meta[loop]);
+            const float fs = __ldg(&P.A.ax[SA].f[loop]);
+            const int rows = ms.x - (s0 + P.dmin[2]);
+            const bool inS0 = (unsigned) ms.x < (unsigned) dN_s, inS1 = (unsigned) (ms.x + 1) < (unsigned) dN_s;
+            float w0 = 1.0f, w1 = 1.0f;
+            if (CLIP) {
+                const float Ss = __ldg(&P.A.ax[SA].S[loop]);
+                float S0[3], S1[3];
+                S0[PA] = Sp0, S0[QA] = Sq, S0[SA] = Ss;
+                S1[PA] = Sp1, S1[QA] = Sq, S1[SA] = Ss;
+                const float rx = (float) U.ldims[0], ry = (float) U.ldims[1], rz = (float) U.ldims[2];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const float* S = v ? S1 : S0;
+                    const float dist = dot3(S[0] - U.clip_center[0], S[1] - U.clip_center[1], S[2] - U.clip_center[2], U.clip_dir[0],
+                                            U.clip_dir[1], U.clip_dir[2]);
+                    const float ox = S[0] - (S[0] + U.clip_dir[0] * dist), oy = S[1] - (S[1] + U.clip_dir[1] * dist),
+                                oz = S[2] - (S[2] + U.clip_dir[2] * dist);
+                    const float vx = ox * rx, vy = oy * ry, vz = oz * rz;
+                    const float vdist = sqrtf(dot3(vx, vy, vz, vx, vy, vz));
+                    const float sgn = dist > 0.0f ? 1.0f : (dist < 0.0f ? -1.0f : 0.0f);
+                    const float w = fminf(fmaxf(0.5f + (0.57735026919f * vdist * sgn), 0.0f), 1.0f);
+                    if (v)
+                        w1 = w;
+                    else
+                        w0 = w;
+                }
+            }
+            const bool g0 = w0 > 0.0f && inside_pq0 && ms.y, g1 = w1 > 0.0f && inside_pq1 && ms.y;
+            float cs0 = 0.0f, cs1 = 0.0f;
+            if (g0 || g1) {
+                // 4 rows (q, s) x 3 columns of taps; two aligned 32-bit loads + a funnel shift per row
+                float t[3][2][2];
+                const unsigned char* base = s_data + thread_data + rows * P.ds_s;
+#pragma unroll
+                for (int js = 0; js < 2; ++js)
+#pragma unroll
+                    for (int jq = 0; jq < 2; ++jq) {
+                        const unsigned char* rowp = base + jq * P.ds_q + js * P.ds_s;
+                        const uint32_t a = *(const uint32_t*) rowp, bb = *(const uint32_t*) (rowp + 4);
+                        const uint32_t w = __funnelshift_r(a, bb, shift);
+                        t[0][jq][js] = decode_u8(w & 0xffu);
+                        t[1][jq][js] = decode_u8((w >> 8) & 0xffu);
+                        t[2][jq][js] = decode_u8((w >> 16) & 0xffu);
+                    }
+                if (!(all_pq && inS0 && inS1)) {
+                    const bool ip[3] = {inP0, inP1, inP2}, iq[2] = {inQ0, inQ1}, is[2] = {inS0, inS1};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int jq = 0; jq < 2; ++jq)
+#pragma unroll
+                            for (int js = 0; js < 2; ++js)
+                                if (!(ip[c] && iq[jq] && is[js])) t[c][jq][js] = U.data_border;
+                }
+                float val0, val1;
+                if (AXIS == 2) {  // x = p, y = q, z = s
+                    const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
+                    const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
+                    val0 = lerpf(lerpf(a00, a10, fq), lerpf(a01, a11, fq), fs);
+                    const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
+                    const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
+                    val1 = lerpf(lerpf(b00, b10, fq), lerpf(b01, b11, fq), fs);
+                } else if (AXIS == 1) {  // x = p, y = s, z = q
+                    const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
+                    const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
+                    val0 = lerpf(lerpf(a00, a01, fs), lerpf(a10, a11, fs), fq);
+                    const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
+                    const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
+                    val1 = lerpf(lerpf(b00, b01, fs), lerpf(b10, b11, fs), fq);
+                } else {  // x = s, y = p, z = q
+                    const float d00 = lerpf(t[0][0][0], t[0][0][1], fs), d10 = lerpf(t[1][0][0], t[1][0][1], fs),
+                                d20 = lerpf(t[2][0][0], t[2][0][1], fs);
+                    const float d01 = lerpf(t[0][1][0], t[0][1][1], fs), d11 = lerpf(t[1][1][0], t[1][1][1], fs),
+                                d21 = lerpf(t[2][1][0], t[2][1][1], fs);
+                    val0 = lerpf(lerpf(d00, d10, fp0), lerpf(d01, d11, fp0), fq);
+                    val1 = lerpf(lerpf(d10, d20, fp1), lerpf(d11, d21, fp1), fq);
+                }
+                if (g0) cs0 = opacity_from_value(val0, U.win, rwidth, s_alpha, step) * w0;
+                if (g1) cs1 = opacity_from_value(val1, U.win, rwidth, s_alpha, step) * w1;
+            }
+
+            // ---- (c) the halo of slice k-1 must have arrived; readers of the slots we overwrite must have moved on ----
+            if (k > 0) {
+#pragma unroll
+                for (int i = 0; i < kHaloPerThread; ++i)
+                    if (halo_fp[i] >= 0) {
+                        while ((unsigned int) (hv[i] >> 32) != want_tag) hv[i] = ld_relaxed_u64(rd + halo_ring[i]);
+                        fp_cur[halo_fp[i]] = __uint_as_float((unsigned int) hv[i]);
+                    }
+            }
+            if (probe) {
+                const unsigned int need = (unsigned) (k + 4 - kRingDepth);
+                while (pv < need) pv = ld_relaxed_u32(P.flags + (size_t) s_down[tid] * kFlagStride);
+            }
+            __syncthreads();
+            // progress counter for back-pressure: every read of slice k-1 by this tile is done
+            if (tid == 0) st_relaxed_u32(P.flags + (size_t) tile * kFlagStride, (unsigned) k);
+
+            // ---- (d) propagate, export, accumulate into the light brick ----
+            {
+                const float* r0 = fp_cur + tap_idx;
+                const float* r1 = r0 + kFpW;
+                const float t00 = r0[0], t10 = r0[1], t20 = r0[2], t01 = r1[0], t11 = r1[1], t21 = r1[2];
+                const float prev0 = lerpf(lerpf(t00, t10, bfx0), lerpf(t01, t11, bfx0), bfy);
+                const float prev1 = lerpf(lerpf(t10, t20, bfx1), lerpf(t11, t21, bfx1), bfy);
+                const float cur0 = prev0 * (1.0f - cs0), cur1 = prev1 * (1.0f - cs1);
+                if (own_in0) fp_next[own_idx] = cur0;
+                if (own_in1) fp_next[own_idx + 1] = cur1;
+                unsigned long long* wr = ring + (size_t) (k % kRingDepth) * plane + (size_t) px + (size_t) tx * py;
+                const unsigned long long tag = (unsigned long long) (tag_base + (unsigned) k + 1u) << 32;
+                if (exp0) st_relaxed_u64(wr, tag | __float_as_uint(cur0));
+                if (exp1) st_relaxed_u64(wr + 1, tag | __float_as_uint(cur1));
+                float* lp = s_light + light_off + (loop - s0) * P.ls_s;
+                if (v0 && fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
+                if (v1 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
+            }
+        }
+        // ---- write the updated light brick back ----
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            int lc[3];
+            lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;
+            tma_store_3d(&light_map, lc[0], lc[1], lc[2], s_light);
+            tma_commit();
+        }
+    }
+    if (tid == 0) tma_wait_all<0>();
+}
+
+}  // namespace tbrm

@@ -42,6 +42,7 @@ struct tbrm_resources {
     // scratch of the fused sweep: ring of propagated slices + per-tile progress flags
     void* ring = nullptr;
     size_t ring_bytes = 0;
+    unsigned int ring_epoch = 0;  // TMA sweep: tag epoch of the ring cells (0 = ring holds no valid tags)
     unsigned int* flags = nullptr;
     size_t flags_count = 0;
     unsigned long long* counters = nullptr;  // device scratch for step / iteration counts
