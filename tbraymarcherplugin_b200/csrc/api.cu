@@ -147,6 +147,7 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     if (r->ring) cudaFree(r->ring);
     if (r->data_yzx) cudaFree(r->data_yzx);
     if (r->tables) cudaFree(r->tables);
+    if (r->bricks) cudaFree(r->bricks);
     if (r->flags) cudaFree(r->flags);
     for (auto& axis : r->rw)
         for (void* b : axis)
@@ -176,6 +177,7 @@ tbrm_status tbrm_upload_volume(tbrm_resources* r, const void* src, int src_is_de
     TBRM_CUDA(cudaMemcpyAsync(r->data, src, bytes, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, r->stream));
     r->data_ready = true;
     r->data_yzx_valid = false;
+    r->bricks_valid = false;
     return TBRM_OK;
 }
 
@@ -190,6 +192,7 @@ tbrm_status tbrm_bind_volume_device(tbrm_resources* r, const void* dptr) {
     r->data_owned = false;
     r->data_ready = true;
     r->data_yzx_valid = false;
+    r->bricks_valid = false;
     return TBRM_OK;
 }
 

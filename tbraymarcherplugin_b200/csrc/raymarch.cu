@@ -222,6 +222,186 @@ __global__ void __launch_bounds__(256) raymarch_lit_kernel(const MarchUniforms U
     }
 }
 
+// ---- fast path: U8 data, R32F light volume ---------------------------------------------------------------------
+// Same arithmetic contract, bit-identical results; what changes is how the numbers are produced:
+//   * UNORM8 decode and the TF-position division use exact division-free sequences (see sweep_tma_kernel.cuh);
+//   * the Wrap sampler of the light volume (saturate(p) keeps the tap index in [-1, N-1]) wraps with two selects
+//     instead of two integer modulos per axis;
+//   * samples that contribute exactly nothing are not evaluated: a sample whose 8 taps all lie in a brick whose largest
+//     byte is rejected by the low cut-off returns (0,0,0,0) (WindowedSampling.usf:28) — the brick max-grid makes that
+//     test one byte load —, and a sample with zero opacity adds exactly 0 to every channel, so its light-volume fetch
+//     is skipped. The march position still advances by the same sequence of fp32 adds.
+constexpr int kBrick = 8;  // brick edge in voxels
+
+struct FastUniforms {
+    MarchUniforms M;
+    const uint8_t* bricks;  // [bz][by][bx] max over voxels [8b, 8b+8] per axis, or nullptr
+    int bdims[3];
+    int skip_byte;          // largest byte the low cut-off rejects (-1: no skipping)
+    float rwidth;
+};
+
+__device__ __forceinline__ float decode_u8_exact(uint32_t v) {
+    const float x = (float) v;
+    return __fmaf_rn(x, 0.003921568859368563f, x * -2.319175823606301e-10f);  // == RN(v / 255)
+}
+__device__ __forceinline__ float div_exact(float x, float w, float rw) {  // == RN(x / w), rw = RN(1/w)
+    const float q = x * rw;
+    return __fmaf_rn(__fmaf_rn(-q, w, x), rw, q);
+}
+
+// one march sample (AccumulateWindowedRaymarchStep); returns nothing, updates acc
+__device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t* __restrict__ data, const float* __restrict__ light,
+                                            const float4* s_tf, V3 p, float step, float4& acc) {
+    const MarchUniforms& U = F.M;
+    int i0, j0, k0;
+    float fx, fy, fz;
+    axis_taps(p.x, U.ddims[0], i0, fx);
+    axis_taps(p.y, U.ddims[1], j0, fy);
+    axis_taps(p.z, U.ddims[2], k0, fz);
+    const int xs0 = clamp_index(i0, U.ddims[0]), ys0 = clamp_index(j0, U.ddims[1]), zs0 = clamp_index(k0, U.ddims[2]);
+    if (F.bricks) {
+        const int m = __ldg(F.bricks + (xs0 >> 3) + F.bdims[0] * ((ys0 >> 3) + F.bdims[1] * (zs0 >> 3)));
+        // every tap is rejected by the low cut-off, and with weights < 1 each lerp stays between its operands, so the
+        // trilinear value is rejected too: the sample is exactly (0,0,0,0)
+        if (m <= F.skip_byte && fx < 1.0f && fy < 1.0f && fz < 1.0f) return;
+    }
+    const int xs1 = clamp_index(i0 + 1, U.ddims[0]), ys1 = clamp_index(j0 + 1, U.ddims[1]), zs1 = clamp_index(k0 + 1, U.ddims[2]);
+    const size_t X = U.ddims[0], XY = (size_t) U.ddims[0] * U.ddims[1];
+    const uint8_t* r00 = data + X * ys0 + XY * zs0;
+    const uint8_t* r01 = data + X * ys1 + XY * zs0;
+    const uint8_t* r10 = data + X * ys0 + XY * zs1;
+    const uint8_t* r11 = data + X * ys1 + XY * zs1;
+    const uint32_t b000 = __ldg(r00 + xs0), b100 = __ldg(r00 + xs1), b010 = __ldg(r01 + xs0), b110 = __ldg(r01 + xs1);
+    const uint32_t b001 = __ldg(r10 + xs0), b101 = __ldg(r10 + xs1), b011 = __ldg(r11 + xs0), b111 = __ldg(r11 + xs1);
+    const float c00 = lerpf(decode_u8_exact(b000), decode_u8_exact(b100), fx);
+    const float c01 = lerpf(decode_u8_exact(b010), decode_u8_exact(b110), fx);
+    const float c10 = lerpf(decode_u8_exact(b001), decode_u8_exact(b101), fx);
+    const float c11 = lerpf(decode_u8_exact(b011), decode_u8_exact(b111), fx);
+    const float v = lerpf(lerpf(c00, c01, fy), lerpf(c10, c11, fy), fz);
+    const float pos = div_exact(v - U.win.center + (U.win.width / 2.0f), U.win.width, F.rwidth);
+    if ((pos < 0.0f && U.win.low > 0.0f) || (pos > 1.0f && U.win.high > 0.0f)) return;
+    int t0, t1;
+    float tf;
+    tf_taps(pos, t0, t1, tf);
+    const float4 a = s_tf[t0], b = s_tf[t1];
+    const float alpha = step_opacity(lerpf(a.w, b.w, tf), step);
+    if (alpha == 0.0f) return;  // adds (rgb * l * 0) * (1 - A) = 0 and 0 * (1 - A) = 0: nothing changes
+    float sx = lerpf(a.x, b.x, tf), sy = lerpf(a.y, b.y, tf), sz = lerpf(a.z, b.z, tf);
+    // light volume: trilinear, wrap addressing, at saturate(p)
+    {
+        int li, lj, lk;
+        float gx, gy, gz;
+        axis_taps(saturatef(p.x), U.ldims[0], li, gx);
+        axis_taps(saturatef(p.y), U.ldims[1], lj, gy);
+        axis_taps(saturatef(p.z), U.ldims[2], lk, gz);
+        const int LX = U.ldims[0], LY = U.ldims[1], LZ = U.ldims[2];
+        const int x0 = li < 0 ? li + LX : li, x1 = li + 1 >= LX ? li + 1 - LX : li + 1;
+        const int y0 = lj < 0 ? lj + LY : lj, y1 = lj + 1 >= LY ? lj + 1 - LY : lj + 1;
+        const int z0 = lk < 0 ? lk + LZ : lk, z1 = lk + 1 >= LZ ? lk + 1 - LZ : lk + 1;
+        const size_t SX = LX, SXY = (size_t) LX * LY;
+        const float* q00 = light + SX * y0 + SXY * z0;
+        const float* q01 = light + SX * y1 + SXY * z0;
+        const float* q10 = light + SX * y0 + SXY * z1;
+        const float* q11 = light + SX * y1 + SXY * z1;
+        const float d00 = lerpf(__ldg(q00 + x0), __ldg(q00 + x1), gx), d01 = lerpf(__ldg(q01 + x0), __ldg(q01 + x1), gx);
+        const float d10 = lerpf(__ldg(q10 + x0), __ldg(q10 + x1), gx), d11 = lerpf(__ldg(q11 + x0), __ldg(q11 + x1), gx);
+        const float l = lerpf(lerpf(d00, d01, gy), lerpf(d10, d11, gy), gz);
+        sx = sx * l, sy = sy * l, sz = sz * l;
+    }
+    const float oma = 1.0f - acc.w;
+    acc.x = acc.x + ((sx * alpha) * oma);
+    acc.y = acc.y + ((sy * alpha) * oma);
+    acc.z = acc.z + ((sz * alpha) * oma);
+    acc.w = acc.w + (alpha * oma);
+}
+
+template <bool CLIP>
+__global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
+                                                            const float* __restrict__ light, const float4* __restrict__ tf,
+                                                            float4* __restrict__ out, unsigned long long* __restrict__ steps_out) {
+    const MarchUniforms& U = F.M;
+    __shared__ float4 s_tf[256];
+    s_tf[threadIdx.x] = __ldg(&tf[threadIdx.x]);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ix = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const int iy = U.row_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    unsigned int steps = 0;
+    if (ix < U.cam.width && iy < U.row_end) {
+        const V3 V = camera_vector(U.cam, ix, iy);
+        V3 cur, lcv;
+        float thick;
+        cube_setup(U.cam, V, cur, thick, lcv);
+        const float ss = 1 / U.step_count;
+        const float fas = U.step_count * thick;
+        const float fl = floorf(fas);
+        const int max_steps = (int) fl;
+        const float fin = fas - fl;
+        const V3 sv = v3(lcv.x * ss, lcv.y * ss, lcv.z * ss);
+        const float ssw = 100.0f * ss;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (U.cam.jitter) {
+            const float rnd = (float) pcg16_x(ix, iy, U.cam.frame_mod8) / 65535.0f;
+            cur = v3(cur.x - sv.x * rnd, cur.y - sv.y * rnd, cur.z - sv.z * rnd);
+        }
+        int i = 0;
+        for (i = 0; i < max_steps; i++) {
+            cur = v3(cur.x + sv.x, cur.y + sv.y, cur.z + sv.z);
+            if (CLIP) {
+                const float cd = dot3(cur.x - U.clip_center[0], cur.y - U.clip_center[1], cur.z - U.clip_center[2], U.clip_dir[0],
+                                      U.clip_dir[1], U.clip_dir[2]);
+                if (cd <= 0.0f) continue;
+            }
+            fast_sample(F, data, light, s_tf, cur, ssw, acc);
+            if (acc.w > 0.95f) {
+                acc.w = 1.0f;
+                break;
+            }
+        }
+        steps = (unsigned) (i < max_steps ? i + 1 : max_steps);
+        if (i == max_steps && fin > 0.0f) {
+            cur = v3(cur.x + sv.x * fin, cur.y + sv.y * fin, cur.z + sv.z * fin);
+            ++steps;
+            bool clipped = false;
+            if (CLIP) {
+                const float cd = dot3(cur.x - U.clip_center[0], cur.y - U.clip_center[1], cur.z - U.clip_center[2], U.clip_dir[0],
+                                      U.clip_dir[1], U.clip_dir[2]);
+                clipped = cd <= 0.0f;
+            }
+            if (!clipped) fast_sample(F, data, light, s_tf, cur, 100.0f * fin, acc);
+        }
+        out[(size_t) (iy - U.row_begin) * U.cam.width + ix] = acc;
+    }
+    if (steps_out) {
+        unsigned int s = steps;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && s) atomicAdd(steps_out, (unsigned long long) s);
+    }
+}
+
+// brick max-grid: bricks[b] = max data byte over voxels [8b, 8b + 8] on every axis (one voxel of apron on the far side:
+// a sample whose first tap lies in brick b has its second tap at most one voxel further)
+__global__ void brick_max_kernel(const uint8_t* __restrict__ data, int X, int Y, int Z, int BX, int BY, int BZ, uint8_t* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int bx = b % BX, by = (b / BX) % BY, bz = b / (BX * BY);
+    unsigned int m = 0;
+    for (int t = threadIdx.x; t < 9 * 9 * 9; t += blockDim.x) {
+        const int x = bx * kBrick + t % 9, y = by * kBrick + (t / 9) % 9, z = bz * kBrick + t / 81;
+        if (x < X && y < Y && z < Z) m = max(m, (unsigned int) __ldg(data + (size_t) x + (size_t) X * ((size_t) y + (size_t) Y * z)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ unsigned int s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int) (blockDim.x >> 5); ++w) m = max(m, s_m[w]);
+        out[b] = (uint8_t) m;
+    }
+}
+
 __global__ void cube_setup_kernel(const RayCam cam, float4* __restrict__ out) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
     if (ix >= cam.width || iy >= cam.height) return;
@@ -256,6 +436,43 @@ static cudaError_t launch_lit(tbrm_resources& r, const MarchUniforms& U, float* 
     return cudaGetLastError();
 }
 
+// largest byte the low cut-off rejects, with the shader's fp32 arithmetic (-1: none / cut-off disabled)
+static int low_cut_byte(const Windowing& w) {
+    if (!(w.low > 0.0f)) return -1;
+    int lo = -1;
+    for (int b = 0; b < 256; ++b) {
+        const float v = (float) b / 255.0f;
+        const float pos = (v - w.center + (w.width / 2.0f)) / w.width;
+        if (pos < 0.0f) {
+            if (lo != b - 1) return -1;  // not a prefix of the byte range: no skipping
+            lo = b;
+        }
+    }
+    return lo;
+}
+
+static cudaError_t ensure_bricks(tbrm_resources& r) {
+    if (r.bricks_valid) return cudaSuccess;
+    const int BX = (r.ddims[0] + kBrick - 1) / kBrick, BY = (r.ddims[1] + kBrick - 1) / kBrick, BZ = (r.ddims[2] + kBrick - 1) / kBrick;
+    cudaError_t e;
+    if (!r.bricks && (e = cudaMalloc(&r.bricks, (size_t) BX * BY * BZ)) != cudaSuccess) return e;
+    brick_max_kernel<<<BX * BY * BZ, 128, 0, r.stream>>>((const uint8_t*) r.data, r.ddims[0], r.ddims[1], r.ddims[2], BX, BY, BZ,
+                                                         (uint8_t*) r.bricks);
+    count_launch();
+    r.bricks_valid = true;
+    return cudaGetLastError();
+}
+
+// conservative: the clip plane never rejects a march position (positions stay within the unit cube expanded by 1)
+static bool clip_never_rejects(const float c[3], const float d[3]) {
+    double dmin = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        const double lo = (-1.0 - (double) c[a]) * d[a], hi = (2.0 - (double) c[a]) * d[a];
+        dmin += lo < hi ? lo : hi;
+    }
+    return dmin > 1.0;
+}
+
 cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, const float clip_center[3], const float clip_dir[3],
                          float step_count, int row_begin, int row_end, float* d_out, unsigned long long* d_steps) {
     MarchUniforms U;
@@ -271,6 +488,27 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
     U.row_begin = row_begin, U.row_end = row_end;
     U.data_wrap = r.options.data_addr_wrap;
     const bool l8 = r.light_fmt == TBRM_FMT_G8;
+    if (r.data_fmt == TBRM_FMT_G8 && !l8 && !U.data_wrap && r.options.reserved[1] == 0) {
+        FastUniforms F;
+        F.M = U;
+        F.rwidth = 1.0f / U.win.width;
+        F.skip_byte = low_cut_byte(U.win);
+        F.bricks = nullptr;
+        for (int k = 0; k < 3; ++k) F.bdims[k] = (r.ddims[k] + kBrick - 1) / kBrick;
+        if (F.skip_byte >= 0) {
+            cudaError_t e = ensure_bricks(r);
+            if (e != cudaSuccess) return e;
+            F.bricks = (const uint8_t*) r.bricks;
+        }
+        const int rows = row_end - row_begin;
+        const dim3 grid((cam.width + 31) / 32, (rows + 7) / 8);
+        if (clip_never_rejects(clip_center, clip_dir))
+            raymarch_fast_kernel<false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+        else
+            raymarch_fast_kernel<true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+        count_launch();
+        return cudaGetLastError();
+    }
     switch (r.data_fmt) {
         case TBRM_FMT_G8:
             return l8 ? launch_lit<uint8_t, uint8_t>(r, U, d_out, d_steps) : launch_lit<uint8_t, float>(r, U, d_out, d_steps);

@@ -49,6 +49,8 @@ struct tbrm_resources {
     // TMA sweep: (y,z,x)-ordered replica of the data volume for sweeps along X, and the per-pass sampler tables
     void* data_yzx = nullptr;
     bool data_yzx_valid = false;
+    void* bricks = nullptr;  // raymarch: per-8^3-brick max of the data volume (exact empty-space skipping)
+    bool bricks_valid = false;
     void* tables = nullptr;
     size_t tables_bytes = 0;
 
