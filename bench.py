@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of TBRaymarcherPlugin on B200, measured on BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): 512^3 CT-like Perlin R8 volume, R32F light volume, windowing {C .45, W .5, low cut-off},
+'soft_ct' transfer function, 2 directional lights, 1920x1080 view, 512 steps. One STEP is one pass of the hot path over
+that input = what ARaymarchVolume::Tick does when the lights changed (RaymarchVolume.cpp:374-378, 418-451) plus the frame
+the renderer then draws: ClearLightVolume + AddDirLightToSingleVolume x 2 (fused sweep) + PerformWindowedLitRaymarch.
+
+Metric: Mray-steps/s = executed march-loop iterations of the frame (incl. clipped ones and the final partial step,
+SURVEY.md §8d) / device time of the whole step (sweep + raymarch). The per-stage figures (raymarch Mray-steps/s on its own,
+sweep Mvoxels/s and GB/s) ride along in "stages".
+
+N > 1 (torchrun, one process per GPU): the path shards by independent volumes — every rank owns one ARaymarchVolume of the
+scene (its own data / light volume / frame), no data-path collective, weak scaling.
+
+--impl reference: the reference has no CPU implementation and cannot be built here (Unreal Engine 5.4 + HLSL), so this arm
+times the CPU oracle (oracle/, kind "port") with all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_VOL = 512
+VIEW = (1920, 1080)
+STEPS = 512.0
+LIGHT_IDS = (0, 1)
+SAMPLE_ROWS = list(range(27, 1080, 54))  # 20 evenly spaced rows for the CPU baseline's raymarch sample
+SWEEP_SAMPLE_N = 256  # the CPU sweep sample runs one axis pass over a 256^3 rendition of the same volume (1/8 of the voxels)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": f"cfg2: {N_VOL}^3 CT-like Perlin R8 volume, R32F light volume, 2 dir lights full reset (fused sweep, bGPUSync) + lit raymarch "
+                    f"{VIEW[0]}x{VIEW[1]} @ {int(STEPS)} steps, windowing C=.45 W=.5 low cut-off, TF soft_ct, jitter on",
+        "volume": [N_VOL] * 3, "view": list(VIEW), "steps": STEPS, "lights": len(LIGHT_IDS),
+        "sharding": "1 volume" if n_gpus == 1 else f"{n_gpus} independent volumes, one per GPU, no collective",
+        "cache": "inputs larger than L2 (128 MiB data + 512 MiB light volume vs 126 MB L2): no flush needed between steps",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU oracle legs (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------------------------
+def oracle_sample(data, data_small, light_after_reset, threads: int):
+    """One bounded sample of the workload on the host: one sweep axis pass over a 256^3 rendition of the volume (the per-voxel
+    work does not depend on the resolution) and the lit raymarch of 20 evenly spaced rows of the real 512^3 / 1080p frame.
+    Returns (estimated seconds for the whole step, estimated ray-steps of the whole frame, detail)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import numpy as np
+
+    import oracle
+    from tbraymarcherplugin_b200 import synth
+    from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters
+
+    oracle.lib().tbo_set_threads(threads)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    tf = oracle.prepare_tf(synth.soft_ct_curve())
+    world = synth.identity_world()
+    small = oracle.OracleVolume(data_small, tf, win)
+    t0 = time.perf_counter()
+    passes = small.add_dir_light(synth.LIGHTS[3], True, world)  # axis-aligned light: exactly one axis pass over all voxels
+    t_pass = (time.perf_counter() - t0) / max(passes, 1) * (N_VOL / SWEEP_SAMPLE_N) ** 3
+    total_passes = 4  # L1 and L2 take two axis passes each
+    vol = oracle.OracleVolume(data, tf, win)
+    if light_after_reset is not None:
+        vol.light = light_after_reset
+    else:
+        vol.light[...] = 1.0  # the cost of a march step does not depend on the light values
+    cam = synth.benchmark_camera(*VIEW)
+    t_rows, steps_rows = 0.0, 0
+    for r in SAMPLE_ROWS:
+        t0 = time.perf_counter()
+        _, st = vol.raymarch_lit(cam, world, STEPS, rows=(r, r + 1))
+        t_rows += time.perf_counter() - t0
+        steps_rows += st
+    scale = VIEW[1] / len(SAMPLE_ROWS)
+    est_seconds = total_passes * t_pass + t_rows * scale
+    est_steps = steps_rows * scale
+    detail = {"sweep_pass_s_scaled": t_pass, "raymarch_rows_s": t_rows, "rows": len(SAMPLE_ROWS), "row_steps": steps_rows}
+    return est_seconds, est_steps, detail
+
+
+SAMPLE_TEXT = ("per step: 1 sweep axis pass over a 256^3 rendition of the volume (x8 voxels, x4 passes) + lit raymarch of 20 evenly spaced "
+               "rows of the 512^3/1080p frame (x54), extrapolated linearly to the whole step")
+
+
+def run_reference(args) -> int:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle
+
+    threads = os.cpu_count() or 1
+    data = oracle.synth_volume("perlin", (N_VOL,) * 3)  # untimed set-up; bit-identical to the device generator
+    data_small = oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3)
+    times, steps = [], 0.0
+    for i in range(args.warmup + args.steps):
+        est_s, est_steps, _ = oracle_sample(data, data_small, None, threads)
+        if i >= args.warmup:
+            times.append(est_s)
+            steps = est_steps
+    ms = 1e3 * sum(times) / len(times)
+    value = steps / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": SAMPLE_TEXT},
+        "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference (UE 5.4 / HLSL) has no CPU path and cannot be built here; this is the CPU oracle port with all host threads",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args) -> int:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tbraymarcherplugin_b200 import FMT_G8, _capi, synth
+    from tbraymarcherplugin_b200.raymarch_utils import FSweepStats, FWindowingParameters, URaymarchUtils
+
+    rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    lib = _capi.load()
+    if lib.tbrm_device_count() <= 0:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, (W, H) = N_VOL, VIEW
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    world = synth.identity_world()
+    lights = [synth.LIGHTS[i] for i in LIGHT_IDS]
+    cam = synth.benchmark_camera(W, H)
+
+    # inputs: generated on the device (untimed), plus a pinned host copy for the end-to-end leg
+    res = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True, device=local)
+    d_vol = torch.empty(n * n * n, dtype=torch.uint8, device="cuda")
+    seed = synth.PERLIN_SEED + rank  # every rank owns a different volume of the scene
+    _capi.check(lib.tbrm_synth_volume_u8(local, _capi.SYNTH_PERLIN_CT, (C.c_int32 * 3)(n, n, n), seed & 0xFFFFFFFF, C.c_void_p(d_vol.data_ptr()), 1))
+    URaymarchUtils.SetDataVolumeDevice(res, d_vol.data_ptr())
+    URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
+    URaymarchUtils.SetWindowingParameters(res, win)
+    d_img = torch.empty(H * W * 4, dtype=torch.float32, device="cuda")
+    h_vol = torch.empty(n * n * n, dtype=torch.uint8).pin_memory()
+    h_vol.copy_(d_vol)
+    h_img = torch.empty(H * W * 4, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def timer_begin():
+        _capi.check(lib.tbrm_timer_begin(res.handle))
+
+    def timer_end() -> float:
+        ms = C.c_float()
+        _capi.check(lib.tbrm_timer_end(res.handle, C.byref(ms)))
+        return ms.value
+
+    sweep_stats = []
+
+    def sweep():
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        sweep_stats.clear()
+        for l in lights:
+            st = FSweepStats()
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
+            sweep_stats.append(st)
+
+    def raymarch(count=True) -> int:
+        _, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, STEPS, device_out_ptr=d_img.data_ptr(), count_steps=count)
+        return steps
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also builds the lazily created replica / brick grid / scratch) ----
+    ray_steps = 0
+    for _ in range(max(args.warmup, 3)):
+        sweep()
+        ray_steps = raymarch()
+    URaymarchUtils.FlushRenderingCommands(res)
+
+    # ---- timed region: K steps, device time on the library's stream, max over ranks ----
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    launches0 = lib.tbrm_kernel_launch_count()
+    timer_begin()
+    for _ in range(args.steps):
+        sweep()
+        raymarch(count=False)  # the step counter read-back would synchronise; steps are identical every frame
+    total_ms = timer_end()
+    launches = lib.tbrm_kernel_launch_count() - launches0
+    barrier()
+    clock_info = clocks.stop()
+    if world_size > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        s = torch.tensor([ray_steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        all_steps = float(s.item())
+        l = torch.tensor([launches], device="cuda", dtype=torch.float64)
+        dist.all_reduce(l, op=dist.ReduceOp.SUM)
+        launches = int(l.item())
+    else:
+        all_steps = float(ray_steps)
+    ms_per_step = total_ms / args.steps
+    value = all_steps / (ms_per_step * 1e-3) / 1e6
+
+    # ---- per-stage timings (same stream, CUDA events), for the roofline objects ----
+    reps = max(3, min(args.steps, 10))
+    timer_begin()
+    for _ in range(reps):
+        sweep()
+    sweep_ms = timer_end() / reps
+    timer_begin()
+    for _ in range(reps):
+        raymarch(count=False)
+    ray_ms = timer_end() / reps
+    # one axis pass of the fused sweep on its own (L4 = a single +Z pass), the sweep's dominant kernel
+    URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    st4 = FSweepStats()
+    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[3], True, world, bGPUSync=True, stats=st4)
+    timer_begin()
+    for _ in range(reps):
+        URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[3], True, world, bGPUSync=True)
+    pass_ms = timer_end() / reps
+
+    hbm_peak, peak_src = peaks()
+    vox = float(n) ** 3
+    passes = sum(s.passes for s in sweep_stats)
+    sweep_bytes = vox * (4.0 + passes * 9.0)  # clear (4 B) + per axis pass 1 B data + 4 B read + 4 B write
+    ray_bytes = vox * 1.0 + vox * 4.0 + 256 * 16 * 8 + W * H * 16.0  # compulsory bytes of the raymarch
+    roofline = {  # dominant kernel by time: the raymarch (instruction-issue bound, not HBM bound — reported honestly)
+        "kernel": "raymarch_fast_kernel", "bound": "hbm", "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": ray_bytes / (ray_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "note": "compulsory bytes / kernel time; ~200 instr per non-empty sample make this kernel issue-bound (DESIGN.md §6)",
+    }
+    roofline_sweep = {
+        "kernel": "sweep_tma_kernel (one axis pass)", "bound": "hbm", "achieved": vox * 9.0 / (pass_ms * 1e-3) / 1e9, "peak": hbm_peak,
+        "unit": "GB/s", "frac": vox * 9.0 / (pass_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "impl": list(st4.impl), "ms": pass_ms,
+    }
+    ncu = ROOT / "profiles" / "traffic.json"
+    if ncu.exists():  # dram bytes per launch from the committed `ncu --set full` captures
+        t = json.loads(ncu.read_text())
+        roofline["traffic"] = t.get("raymarch_fast_kernel")
+        roofline_sweep["traffic"] = t.get("sweep_tma_kernel")
+
+    # ---- end to end: the reference-facing API with HOST buffers, copies inside the timed region ----
+    h_np = h_vol.numpy().reshape(n, n, n)
+    img_np = h_img.numpy().reshape(H, W, 4)
+
+    def e2e_step():
+        URaymarchUtils.SetDataVolume(res, h_np)  # H2D of the step's input (pinned)
+        sweep()
+        URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, STEPS, out=img_np, count_steps=False)  # D2H of the frame (pinned)
+
+    URaymarchUtils.SetDataVolume(res, h_np)  # switch the resource set to an owned device copy before timing
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    if world_size > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": all_steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mray-steps/s", "h2d_bytes_per_step": int(h_vol.numel()) * world_size,
+           "d2h_bytes_per_step": int(h_img.numel()) * 4 * world_size, "ms_per_step": e2e_ms}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample ----
+    cpu_baseline = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        sweep()
+        light = URaymarchUtils.ReadLightVolume(res)
+        threads = os.cpu_count() or 1
+        sys.path.insert(0, str(ROOT / "tests"))
+        import oracle
+
+        est_s, est_steps, detail = oracle_sample(h_np, oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3), light, threads)
+        cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": SAMPLE_TEXT,
+                        "est_ms_per_step": est_s * 1e3, **detail}
+
+    if rank == 0:
+        line = {
+            "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world_size), "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_sweep": roofline_sweep, "cpu_baseline": cpu_baseline,
+            "stages": {
+                "ray_steps_per_frame": ray_steps,
+                "raymarch": {"ms": ray_ms, "Mray_steps_per_s": ray_steps / (ray_ms * 1e-3) / 1e6},
+                "sweep": {"ms": sweep_ms, "axis_passes": passes, "Mvoxels_per_s": vox * passes / (sweep_ms * 1e-3) / 1e6,
+                          "GB_per_s": sweep_bytes / (sweep_ms * 1e-3) / 1e9, "frac_of_hbm_peak": sweep_bytes / (sweep_ms * 1e-3) / 1e9 / hbm_peak,
+                          "impl": [list(s.impl) for s in sweep_stats]},
+            },
+        }
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 2
+        args.warmup = args.warmup if args.warmup is not None else 1
+        return run_reference(args)
+    args.steps = args.steps if args.steps is not None else 20
+    args.warmup = args.warmup if args.warmup is not None else 3
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

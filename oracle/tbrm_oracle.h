@@ -54,6 +54,7 @@ int tbo_raymarch_lit(const tbo_volume* vol, const tbrm_camera* cam, const tbrm_w
                      int row_end, float* out_rgba, uint64_t* out_steps, uint8_t* near_gate);
 int tbo_mandelbulb_march(const tbrm_mandelbulb* mb, const tbrm_camera* cam, const tbrm_world* world, int row_begin, int row_end,
                          float* out_xy, uint64_t* out_iterations);
+int tbo_synth_volume_u8(int kind, const int32_t dims[3], uint32_t seed, uint8_t* out);
 float tbo_det_pow(float x, float y);
 float tbo_round_to_half(float x);
 void tbo_sample_windowed_tf(float value, float step, const float* tf, const tbrm_windowing* w, float out[4]);

@@ -251,8 +251,11 @@ class URaymarchUtils:
         check(_capi.load().tbrm_set_windowing(Resources.handle, C.byref(cw)))
 
     @staticmethod
-    def SetOptions(Resources: FBasicRaymarchRenderingResources, border_exact: bool = False, data_addr_wrap: bool = False, sweep_impl: int = 0) -> None:
-        o = _capi.Options(int(border_exact), int(data_addr_wrap), int(sweep_impl))
+    def SetOptions(Resources: FBasicRaymarchRenderingResources, border_exact: bool = False, data_addr_wrap: bool = False, sweep_impl: int = 0,
+                   debug_flags: Sequence[int] = ()) -> None:
+        """Engine-semantics switches and kernel selection; ``debug_flags`` fills tbrm_options.reserved."""
+        r = list(debug_flags)[:5] + [0] * (5 - min(len(debug_flags), 5))
+        o = _capi.Options(int(border_exact), int(data_addr_wrap), int(sweep_impl), (C.c_int32 * 5)(*r))
         check(_capi.load().tbrm_set_options(Resources.handle, C.byref(o)))
 
     # ---- transfer functions (RaymarchUtils.h:57-64) ------------------------------------------------------------

@@ -156,6 +156,13 @@ def mandelbulb(params: FMandelbulbParameters, cam: FCamera, world: FRaymarchWorl
     return out, int(n.value)
 
 
+def synth_volume(kind: str, dims, seed: int = 0x5EED1234) -> np.ndarray:
+    """Synthetic volume generated by the oracle library (OpenMP); bit-identical to synth.py's numpy generators."""
+    out = np.empty(tuple(dims)[::-1], np.uint8)
+    lib().tbo_synth_volume_u8(0 if kind == "sphere" else 1, (C.c_int32 * 3)(*dims), C.c_uint32(seed & 0xFFFFFFFF), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def det_pow(x: float, y: float) -> float:
     return float(lib().tbo_det_pow(x, y))
 

@@ -225,3 +225,9 @@ def test_mandelbulb_far_ray_misses_and_centre_ray_hits():
     assert out[4, 4, 1] == 1.0 and 0.0 < out[4, 4, 0] <= 1.0  # centre pixel hits the bulb
     assert out[0, 0, 1] == 0.0  # corner pixel leaves the cube
     assert iters > 0
+
+
+def test_oracle_synth_generator_equals_numpy_twin():
+    for kind, fn in (("sphere", synth.sphere_volume), ("perlin", synth.perlin_ct_volume)):
+        dims = (24, 20, 28)
+        assert np.array_equal(oracle.synth_volume(kind, dims), fn(dims)), kind
