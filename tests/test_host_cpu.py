@@ -129,3 +129,45 @@ def test_synthetic_volumes_are_deterministic_and_shaped():
     assert not np.array_equal(p1, synth.perlin_ct_volume((24, 24, 24), seed=1))
     c = synth.soft_ct_curve()
     assert c.shape == (256, 4) and c[0, 3] == 0 and c[255, 3] == pytest.approx(0.15)
+
+
+def test_cpp_host_mirror_compiles_against_the_c_abi(tmp_path):
+    """csrc/RaymarchUtils.hpp (the reference's signatures over the C ABI) is plain C++17 and links against libtbrm.so."""
+    import subprocess
+
+    from tbraymarcherplugin_b200 import build
+
+    src = tmp_path / "t.cpp"
+    src.write_text('''
+        #include "tbraymarcherplugin_b200/csrc/RaymarchUtils.hpp"
+        using namespace tbrm_ue;
+        int main() {
+            FBasicRaymarchRenderingResources res;  // uninitialised: every resource pointer is null
+            bool added = true;
+            URaymarchUtils::AddDirLightToSingleVolume(res, FDirLightParameters(FVector(1, 0, 0), 1.0f), true, FRaymarchWorldParameters(), added, true);
+            if (added) return 1;  // LightAdded must be false (RaymarchUtils.cpp:39-45)
+            added = true;
+            URaymarchUtils::ChangeDirLightInSingleVolume(res, FDirLightParameters(), FDirLightParameters(), FRaymarchWorldParameters(), added);
+            URaymarchUtils::ClearResourceLightVolumes(res, 0.0f);
+            return added ? 2 : 0;
+        }''')
+    exe = tmp_path / "t"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-I", str(ROOT), str(src), "-o", str(exe), str(build.LIB_PATH), f"-Wl,-rpath,{build.PKG_DIR}"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_exact_division_free_sequences():
+    """The fast kernels replace v/255 by fma(v, c_hi, v*c_lo) and x/W by Markstein's sequence; both must equal IEEE division."""
+    v = np.arange(256, dtype=np.float32)
+    c_hi, c_lo = np.float32(0.003921568859368563), np.float32(-2.319175823606301e-10)
+    got = (v.astype(np.float64) * float(c_hi) + (v * c_lo).astype(np.float64)).astype(np.float32)  # fma: exact product, one rounding
+    assert np.array_equal(got, v / np.float32(255.0))
+    rng = np.random.default_rng(3)
+    for w in (0.5, 1.0, 0.4, 0.3, 0.9, 1.7):
+        w32 = np.float32(w)
+        rw = np.float32(1.0) / w32
+        x = np.concatenate([rng.uniform(-1.5, 2.0, 20000), (np.arange(-20, 280) / 255.0)]).astype(np.float32)
+        q = x * rw
+        e = (-(q.astype(np.float64)) * float(w32) + x.astype(np.float64)).astype(np.float32)
+        q2 = (e.astype(np.float64) * float(rw) + q.astype(np.float64)).astype(np.float32)
+        assert np.array_equal(q2, x / w32), w
