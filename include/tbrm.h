@@ -112,7 +112,8 @@ typedef struct tbrm_options {
     int32_t data_addr_wrap;   /* raymarch data sampler address mode: 0 clamp (default), 1 wrap (Q5) */
     int32_t sweep_impl;       /* 0: auto (gpu_sync ? fused : per-slice), 1: per-slice launches (reference schedule),
                                  2: fused persistent sweep (TMA-staged when eligible), 3: generic fused sweep only */
-    int32_t reserved[5];
+    int32_t reserved[5];      /* debug / test hooks: [0] bit 0 disables the sweep's exact empty-space skip; [1] = 1 forces the generic
+                                 raymarch kernel; [2] > 0 caps the tile rows of one sweep launch (forces banded passes) */
 } tbrm_options;
 
 /* Per-op counters written by the *_stats calls (for the metric definitions of SURVEY.md §8d). */
@@ -124,6 +125,12 @@ typedef struct tbrm_sweep_stats {
     int32_t faces[4];        /* FCubeFace of each pass (0:+X 1:-X 2:+Y 3:-Y 4:+Z 5:-Z), -1 if unused */
     int32_t impl[4];         /* kernel family of each pass: 1 per-slice launches, 2 fused (generic), 3 fused (TMA-staged) */
 } tbrm_sweep_stats;
+
+/* One GPU's share of a volume that is sharded over the GPUs of a box as Z-slabs. */
+typedef struct tbrm_slab {
+    int32_t rank, nranks;    /* position in the chain of slabs; nranks == 1: not sharded */
+    int32_t z_begin, z_end;  /* light-volume slices [z_begin, z_end) this GPU owns (tbrm_slab_partition) */
+} tbrm_slab;
 
 /* Opaque FBasicRaymarchRenderingResources (RaymarchTypes.h:87-129): data volume, TF texture, light volume,
  * windowing, the 3x4 propagation buffers, and the CUDA stream that plays the render-thread queue. */
@@ -203,6 +210,39 @@ tbrm_status tbrm_download_light_volume(tbrm_resources* res, void* dst_host);
 tbrm_status tbrm_upload_light_volume(tbrm_resources* res, const void* src_host);
 void* tbrm_light_volume_device_ptr(tbrm_resources* res);
 void* tbrm_data_volume_device_ptr(tbrm_resources* res);
+
+/* Use caller-owned device memory as the light volume (light_fmt texels, must outlive res): lets the host layer run
+ * collectives (NCCL all-gather of the slabs) directly on it. The previous light volume is freed. */
+tbrm_status tbrm_bind_light_volume_device(tbrm_resources* res, void* dptr);
+
+/* ---- Z-slab sharding of ONE volume over the GPUs of a box ------------------------------- */
+/* Every rank holds the whole data volume (1 B/voxel, replicated) and a full-size light volume of which it owns the slices
+ * [z_begin, z_end): after tbrm_slab_configure the sweep ops (clear / add / change) touch only the owned slab, and the
+ * propagated light crosses slab boundaries inside the sweep kernel through the neighbours' exchange arenas (NVLink peer
+ * stores for sweeps along X / Y, a plane hand-off for sweeps along Z). The result is bit-identical to the unsharded sweep.
+ * Gathering the slabs (an all-gather of the light volume, in place) is the caller's collective. Requires R8 data, an R32F
+ * full-resolution light volume, X % 16 == 0, Y % 16 == 0 and Z % 8 == 0; other configurations return TBRM_ERR_UNSUPPORTED. */
+void tbrm_slab_partition(int32_t z_slices, int32_t nranks, int32_t rank, int32_t* z_begin, int32_t* z_end);
+tbrm_status tbrm_slab_configure(tbrm_resources* res, const tbrm_slab* slab);
+/* The exchange arena of this rank: device pointer + size, and its CUDA IPC handle (64 bytes) for the neighbour processes. */
+tbrm_status tbrm_slab_arena(tbrm_resources* res, void** dptr, size_t* bytes);
+tbrm_status tbrm_slab_ipc_handle(tbrm_resources* res, void* handle64);
+/* Connect the neighbour that owns the slab below (side = -1) or above (side = +1): from its IPC handle (another process),
+ * or from a device pointer valid in this process (same-process peers, tests). */
+tbrm_status tbrm_slab_open_peer(tbrm_resources* res, int side, const void* handle64);
+tbrm_status tbrm_slab_set_peer(tbrm_resources* res, int side, void* peer_arena_dptr);
+/* Clears the exchange arena and restarts the tag sequence. Call on every rank, between two barriers, with no sweep in
+ * flight: after creating the peers' connections is not required, after TBRM_ERR_UNSUPPORTED "sequence used up" it is. */
+tbrm_status tbrm_slab_reset_comm(tbrm_resources* res);
+/* TBRM_ERR_CUDA if a slab exchange timed out since the last call (a neighbour died or ran different passes); synchronises. */
+tbrm_status tbrm_slab_check(tbrm_resources* res);
+tbrm_status tbrm_slab_set_timeout_ms(tbrm_resources* res, int timeout_ms);
+/* One axis pass of AddDirLightToSingleVolume (pass = 0 or 1), and the order in which slabs must run it when they cannot
+ * run concurrently (several slabs on one GPU): +1 lower slabs first, -1 higher slabs first, 0 any order / no such pass.
+ * Production code calls tbrm_add_dir_light on every rank; these two exist for single-GPU tests of the exchange. */
+tbrm_status tbrm_add_dir_light_pass(tbrm_resources* res, const tbrm_dir_light* light, int added, const tbrm_world* world,
+                                    int pass, int gpu_sync, tbrm_sweep_stats* stats);
+tbrm_status tbrm_slab_pass_order(tbrm_resources* res, const tbrm_dir_light* light, const tbrm_world* world, int pass, int* order);
 
 /* ---- raymarch ----------------------------------------------------------------------------------------- */
 /* PerformRaymarchCubeSetup for every pixel: out_entry_thickness[4*(iy*W+ix)] = (entry UVW, thickness). */

@@ -3,6 +3,8 @@ sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 from tbraymarcherplugin_b200 import _capi, synth, FMT_G8
 from tbraymarcherplugin_b200.raymarch_utils import *
 lib=_capi.load()
+import os
+flags=int(os.environ.get('TBRM_EXP','0'),0)
 for n,view,steps in [(256,(512,512),256.),(512,(1920,1080),512.)]:
     res=URaymarchUtils.InitializeRaymarchResources((n,n,n),FMT_G8,bLightVolume32Bit=True)
     import torch
@@ -12,6 +14,7 @@ for n,view,steps in [(256,(512,512),256.),(512,(1920,1080),512.)]:
     URaymarchUtils.ColorCurveToTexture(res,synth.soft_ct_curve())
     URaymarchUtils.SetWindowingParameters(res,FWindowingParameters(0.45,0.5,True,False))
     w=synth.identity_world()
+    URaymarchUtils.SetOptions(res,debug_flags=(flags,))
     for sync in (False, True):
       for it in range(3):
         ms=C.c_float()

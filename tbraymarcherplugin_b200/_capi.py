@@ -79,6 +79,10 @@ class SweepStats(C.Structure):
     ]
 
 
+class Slab(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("z_begin", C.c_int32), ("z_end", C.c_int32)]
+
+
 class PassPlan(C.Structure):
     _fields_ = [
         ("face", C.c_int32),
@@ -142,6 +146,18 @@ PROTOTYPES = {
     "tbrm_upload_light_volume": (_I, [_P, _P]),
     "tbrm_light_volume_device_ptr": (_P, [_P]),
     "tbrm_data_volume_device_ptr": (_P, [_P]),
+    "tbrm_bind_light_volume_device": (_I, [_P, _P]),
+    "tbrm_slab_partition": (None, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "tbrm_slab_configure": (_I, [_P, C.POINTER(Slab)]),
+    "tbrm_slab_arena": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "tbrm_slab_ipc_handle": (_I, [_P, _P]),
+    "tbrm_slab_open_peer": (_I, [_P, _I, _P]),
+    "tbrm_slab_set_peer": (_I, [_P, _I, _P]),
+    "tbrm_slab_reset_comm": (_I, [_P]),
+    "tbrm_slab_check": (_I, [_P]),
+    "tbrm_slab_set_timeout_ms": (_I, [_P, _I]),
+    "tbrm_add_dir_light_pass": (_I, [_P, C.POINTER(DirLight), _I, C.POINTER(World), _I, _I, C.POINTER(SweepStats)]),
+    "tbrm_slab_pass_order": (_I, [_P, C.POINTER(DirLight), C.POINTER(World), _I, C.POINTER(_I)]),
     "tbrm_raymarch_cube_setup": (_I, [_P, C.POINTER(Camera), C.POINTER(World), _P, _I]),
     "tbrm_raymarch_lit": (_I, [_P, C.POINTER(Camera), C.POINTER(World), C.c_float, _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
     "tbrm_mandelbulb_march": (_I, [_I, C.POINTER(Mandelbulb), C.POINTER(Camera), C.POINTER(World), _I, _I, _P, _I, C.POINTER(C.c_uint64)]),

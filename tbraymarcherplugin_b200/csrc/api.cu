@@ -141,7 +141,10 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
     if (r->data_owned && r->data) cudaFree(r->data);
-    if (r->light) cudaFree(r->light);
+    if (r->light && r->light_owned) cudaFree(r->light);
+    for (int i = 0; i < 2; ++i)
+        if (r->peer_arena[i] && r->peer_ipc[i]) cudaIpcCloseMemHandle(r->peer_arena[i]);
+    if (r->arena) cudaFree(r->arena);
     if (r->tf) cudaFree(r->tf);
     if (r->counters) cudaFree(r->counters);
     if (r->ring) cudaFree(r->ring);
@@ -244,6 +247,12 @@ tbrm_status tbrm_set_windowing(tbrm_resources* r, const tbrm_windowing* w) {
 tbrm_status tbrm_clear_light_volume(tbrm_resources* r, float clear_value) {
     if (!r || !r->light) return TBRM_OK;  // RaymarchUtils.cpp:106-109: silently returns without a render target
     TBRM_CUDA(cudaSetDevice(r->device));
+    if (r->slab.nranks > 1) {  // a sharded volume: every rank clears the slab it owns
+        const size_t plane = (size_t) r->ldims[0] * r->ldims[1];
+        TBRM_CUDA(sweep_fill_buffer(*r, (char*) r->light + plane * r->slab.z_begin * r->light_elem(),
+                                    plane * (size_t) (r->slab.z_end - r->slab.z_begin), clear_value));
+        return TBRM_OK;
+    }
     TBRM_CUDA(clear_light(*r, clear_value));
     return TBRM_OK;
 }
@@ -284,10 +293,15 @@ static tbrm_status run_pass(tbrm_resources& r, const SweepUniforms& u, bool chan
     int used = 1;
     // 0 auto (gpu_sync ? fused : per-slice), 1 per-slice, 2 fused (TMA path when eligible), 3 generic fused only
     const int impl = r.options.sweep_impl;
-    const bool want_fused = impl == 2 || impl == 3 || (impl == 0 && gpu_sync);
-    if (want_fused && impl != 3) {
+    const bool sharded = r.slab.nranks > 1;
+    const bool want_fused = impl == 2 || impl == 3 || (impl == 0 && gpu_sync) || sharded;
+    if (want_fused && (impl != 3 || sharded)) {
         TBRM_CUDA(sweep_pass_tma(r, u, change, &launches, &handled));
         if (handled) used = 3;
+    }
+    if (sharded && !handled) {  // only the TMA-staged sweep knows how to exchange light between slabs
+        set_last_error(std::string("sharded volume: only the TMA-staged sweep exchanges light between slabs; ") + tbrm_last_error());
+        return TBRM_ERR_UNSUPPORTED;
     }
     if (want_fused && !handled) {
         TBRM_CUDA(sweep_pass_fused(r, u, change, &launches, &handled));
@@ -312,11 +326,12 @@ static tbrm_status run_pass(tbrm_resources& r, const SweepUniforms& u, bool chan
 
 // AddDirLightToSingleLightVolume_RenderThread — LightingShaders.cpp:35-166
 static tbrm_status add_dir_light_impl(tbrm_resources& r, const tbrm_dir_light& light, bool added, const tbrm_world& world, int gpu_sync,
-                                      tbrm_sweep_stats* stats) {
+                                      tbrm_sweep_stats* stats, int only_pass = -1) {
     tbrm_light_plan plan;
     host::plan_dir_light(r.ldims, r.windowing, r.options.border_exact != 0, light, world, plan);
     if (plan.zero_direction) return TBRM_OK;  // :41-46
     for (int i = 0; i < plan.add_passes; ++i) {  // "break if the axis weight == 0", :65-68, :94-97
+        if (only_pass >= 0 && i != only_pass) continue;
         SweepUniforms u;
         fill_uniforms(r, plan, i, u);
         u.sign = added ? 1.0f : -1.0f;
@@ -407,6 +422,144 @@ tbrm_status tbrm_upload_light_volume(tbrm_resources* r, const void* src_host) {
     TBRM_CUDA(cudaSetDevice(r->device));
     TBRM_CUDA(cudaMemcpyAsync(r->light, src_host, r->light_voxels() * r->light_elem(), cudaMemcpyHostToDevice, r->stream));
     TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_bind_light_volume_device(tbrm_resources* r, void* dptr) {
+    TBRM_REQUIRE(r && dptr, "tbrm_bind_light_volume_device: null argument");
+    TBRM_REQUIRE(((uintptr_t) dptr & 15) == 0, "tbrm_bind_light_volume_device: the light volume must be 16-byte aligned");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->light && r->light_owned) cudaFree(r->light);
+    r->light = dptr;
+    r->light_owned = false;
+    return TBRM_OK;
+}
+
+// ---- Z-slab sharding ----------------------------------------------------------------------------------------
+void tbrm_slab_partition(int32_t z_slices, int32_t nranks, int32_t rank, int32_t* z_begin, int32_t* z_end) {
+    if (!z_begin || !z_end || nranks <= 0 || rank < 0 || rank >= nranks) return;
+    slab_partition(z_slices, nranks, rank, z_begin, z_end);
+}
+
+tbrm_status tbrm_slab_configure(tbrm_resources* r, const tbrm_slab* slab) {
+    TBRM_REQUIRE(r && slab, "tbrm_slab_configure: null argument");
+    TBRM_REQUIRE(slab->nranks >= 1 && slab->rank >= 0 && slab->rank < slab->nranks, "tbrm_slab_configure: bad rank");
+    if (slab->nranks > 1) {
+        int32_t zb, ze;
+        slab_partition(r->ldims[2], slab->nranks, slab->rank, &zb, &ze);
+        TBRM_REQUIRE(zb == slab->z_begin && ze == slab->z_end && zb < ze, "tbrm_slab_configure: the slab must follow tbrm_slab_partition and be non-empty");
+        if (r->data_fmt != TBRM_FMT_G8 || r->light_fmt != TBRM_FMT_R32F || r->half_res || r->ddims[0] % 16 || r->ddims[1] % 16 || r->ddims[2] % 8) {
+            set_last_error("tbrm_slab_configure: sharding needs R8 data, an R32F full-resolution light volume, X % 16 == 0, Y % 16 == 0, Z % 8 == 0");
+            return TBRM_ERR_UNSUPPORTED;
+        }
+    }
+    TBRM_CUDA(cudaSetDevice(r->device));
+    r->slab = *slab;
+    if (slab->nranks > 1) TBRM_CUDA(slab_ensure_arena(*r));
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_arena(tbrm_resources* r, void** dptr, size_t* bytes) {
+    TBRM_REQUIRE(r && dptr && bytes, "tbrm_slab_arena: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(slab_ensure_arena(*r));
+    *dptr = r->arena, *bytes = r->arena_bytes;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_ipc_handle(tbrm_resources* r, void* handle64) {
+    TBRM_REQUIRE(r && handle64, "tbrm_slab_ipc_handle: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(slab_ensure_arena(*r));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));  // the arena has been cleared before anybody can write to it
+    cudaIpcMemHandle_t h;
+    TBRM_CUDA(cudaIpcGetMemHandle(&h, r->arena));
+    memcpy(handle64, &h, sizeof(h));
+    return TBRM_OK;
+}
+
+static tbrm_status drop_peer(tbrm_resources* r, int i) {
+    if (r->peer_arena[i] && r->peer_ipc[i]) TBRM_CUDA(cudaIpcCloseMemHandle(r->peer_arena[i]));
+    r->peer_arena[i] = nullptr, r->peer_ipc[i] = false;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_open_peer(tbrm_resources* r, int side, const void* handle64) {
+    TBRM_REQUIRE(r && handle64 && (side == -1 || side == 1), "tbrm_slab_open_peer: bad argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    const int i = side < 0 ? 0 : 1;
+    tbrm_status s = drop_peer(r, i);
+    if (s != TBRM_OK) return s;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    TBRM_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    r->peer_arena[i] = p, r->peer_ipc[i] = true;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_set_peer(tbrm_resources* r, int side, void* peer_arena_dptr) {
+    TBRM_REQUIRE(r && (side == -1 || side == 1), "tbrm_slab_set_peer: bad argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    const int i = side < 0 ? 0 : 1;
+    tbrm_status s = drop_peer(r, i);
+    if (s != TBRM_OK) return s;
+    r->peer_arena[i] = peer_arena_dptr;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_reset_comm(tbrm_resources* r) {
+    TBRM_REQUIRE(r, "tbrm_slab_reset_comm: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->arena) TBRM_CUDA(cudaMemsetAsync(r->arena, 0, r->arena_bytes, r->stream));
+    if (r->ring) TBRM_CUDA(cudaMemsetAsync(r->ring, 0, r->ring_bytes, r->stream));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    r->pass_seq = 0;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_check(tbrm_resources* r) {
+    TBRM_REQUIRE(r, "tbrm_slab_check: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    if (!r->arena) return TBRM_OK;
+    unsigned int err = 0;
+    TBRM_CUDA(cudaMemcpy(&err, (unsigned int*) r->arena + 2, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) {
+        TBRM_CUDA(cudaMemset((unsigned int*) r->arena + 2, 0, sizeof(err)));
+        set_last_error("slab exchange timed out: a neighbouring slab did not deliver its light (results are void)");
+        return TBRM_ERR_CUDA;
+    }
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_set_timeout_ms(tbrm_resources* r, int timeout_ms) {
+    TBRM_REQUIRE(r && timeout_ms >= 0, "tbrm_slab_set_timeout_ms: bad argument");
+    r->slab_timeout_ms = timeout_ms;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_add_dir_light_pass(tbrm_resources* r, const tbrm_dir_light* light, int added, const tbrm_world* world, int pass,
+                                    int gpu_sync, tbrm_sweep_stats* stats) {
+    reset_stats(stats);
+    if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
+    TBRM_REQUIRE(light && world && (pass == 0 || pass == 1), "tbrm_add_dir_light_pass: bad argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    return add_dir_light_impl(*r, *light, added != 0, *world, gpu_sync, stats, pass);
+}
+
+tbrm_status tbrm_slab_pass_order(tbrm_resources* r, const tbrm_dir_light* light, const tbrm_world* world, int pass, int* order) {
+    TBRM_REQUIRE(r && light && world && order && (pass == 0 || pass == 1), "tbrm_slab_pass_order: bad argument");
+    *order = 0;
+    tbrm_light_plan plan;
+    host::plan_dir_light(r->ldims, r->windowing, r->options.border_exact != 0, *light, *world, plan);
+    if (plan.zero_direction || pass >= plan.add_passes) return TBRM_OK;
+    SweepUniforms u;
+    fill_uniforms(*r, plan, pass, u);
+    *order = slab_pass_order(u);
     return TBRM_OK;
 }
 

@@ -16,6 +16,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace tbrm {
@@ -27,6 +29,7 @@ constexpr int kStages = 3;
 constexpr int kRingDepth = 16;
 constexpr int kHaloPerThread = 2;          // footprint cells owned by other tiles, fetched per thread
 constexpr int kFpW = kTW + 4, kFpH = kTH + 4;  // SMEM footprint of the previous slice
+constexpr int kHaloOverflow = kFpW * kFpH - kHaloPerThread * kTmaThreads;  // halo cells beyond the per-thread registers
 
 struct AxisTab {  // per native coordinate c of one axis (device pointers)
     const float* S;   // GetUVW(c) + UVWOffset
@@ -39,8 +42,24 @@ struct LightTabs {
     const int2* by;  // per py
 };
 
+// What a launch that covers only part of a pass needs (see the SLAB notes on sweep_tma_kernel)
+struct SlabParams {
+    int tile_row0, tile_rows;        // tile rows of the buffer plane this launch walks
+    int q_lo, q_hi;                  // buffer rows it owns
+    int k_begin, k_end;              // slices (in sweep order) it walks
+    int reach_lo, reach_hi;          // rows below q_lo / at or above q_hi a band's footprints read
+    const unsigned long long* inbox; // [slice][reach_lo + reach_hi row slots][tx] LL cells: rows q_lo-reach_lo .. q_lo-1, q_hi .. q_hi+reach_hi-1
+    unsigned long long* out_lo;      // inbox of the band below (rows < q_lo): local, or the neighbour GPU's through NVLink; or null
+    unsigned long long* out_hi;      // inbox of the band above
+    const unsigned long long* zin;   // plane of LL cells holding the upstream slab's last slice (k_begin > 0), or null
+    unsigned long long* zout;        // the downstream slab's zin (k_end < slices), or null
+    unsigned int* error;             // device word set when an exchange timed out
+    unsigned long long timeout_ns;
+};
+
 struct TmaParams {
     SweepUniforms U;
+    SlabParams S;
     LightTabs A;      // the (added) light
     int ntx, nty;
     float* ring;
@@ -52,6 +71,9 @@ struct TmaParams {
     int data_dims_t[3];     // data dims in transposed (p,q,s) order
     int stage_bytes, light_bytes, data_bytes;
     unsigned int epoch;     // distinguishes the ring tags of successive passes
+    unsigned int cut_lo_mode, cut_lo_add;  // exact empty-space skip on tap bytes (see window_cut_byte); mode 0 = off
+    const int* tile_order;  // optional blockIdx -> tile permutation (load balance), else nullptr
+    int exp_flags;          // experiment switches (tbrm_options.reserved[0])
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
@@ -142,6 +164,7 @@ struct HostTabs {
     int dmin[3], dmax[3];  // min / max of (i0 - c) per native axis
     int bmin[2], bmax[2];
     bool pairs_ok = true;  // i0(c+1) == i0(c) + 1 everywhere along each axis
+    bool weights_lt_one = true;  // every trilinear weight is < 1 (needed by the exact empty-space skip)
 };
 
 static void build_tabs(const SweepUniforms& u, const LightPass& L, HostTabs& T) {
@@ -158,6 +181,7 @@ static void build_tabs(const SweepUniforms& u, const LightPass& L, HostTabs& T) 
             const int i0 = (int) fl;
             const float sat = fminf(fmaxf(s, 0.0f), 1.0f);
             T.S[a][c] = s, T.f[a][c] = fr, T.meta[a][c] = make_int2(i0, s == sat ? 1 : 0);
+            if (!(fr >= 0.0f && fr < 1.0f)) T.weights_lt_one = false;
             T.dmin[a] = std::min(T.dmin[a], i0 - c), T.dmax[a] = std::max(T.dmax[a], i0 - c);
             if (c > 0 && T.meta[a][c - 1].x + 1 != i0) T.pairs_ok = false;
         }
@@ -206,6 +230,29 @@ static bool clip_is_inactive(const SweepUniforms& u, const HostTabs& T) {
     return 0.57735026919 * dmin * scale > 4.0 && dmin < 1e30;
 }
 
+// Largest byte T the low cut-off rejects, evaluated with the shader's fp32 arithmetic (GetTransferFuncPosition +
+// cut-off, WindowedSampling.usf:14-29). A trilinear value lies between its smallest and largest tap (each lerp
+// fma(t, b-a, a) with 0 <= t < 1 stays inside [a,b]) and the window position is monotone in the value, so taps that
+// are all <= T imply a rejected sample. mode 0: no skip; 1: T < 128; 2: T >= 128; `add` is the SWAR addend.
+static void window_cut_byte(const Windowing& w, bool allow, unsigned int& mode, unsigned int& add) {
+    int lo = -1;
+    bool ok = allow && w.low > 0.0f;
+    for (int b = 0; b < 256 && ok; ++b) {
+        const float v = (float) b / 255.0f;
+        const float pos = (v - w.center + (w.width / 2.0f)) / w.width;
+        if (pos < 0.0f) {
+            if (lo != b - 1) ok = false;  // the rejected bytes must be a prefix of the byte range
+            lo = b;
+        }
+    }
+    mode = 0, add = 0;
+    if (!ok || lo < 0) return;
+    if (lo < 128)
+        mode = 1, add = (unsigned) (127 - lo) * 0x010101u;
+    else
+        mode = 2, add = (unsigned) (255 - lo) * 0x010101u;
+}
+
 static cudaError_t upload(tbrm_resources& r, const void* src, size_t bytes, size_t& off, const void** dptr) {
     off = (off + 15) & ~(size_t) 15;
     *dptr = (const char*) r.tables + off;
@@ -214,15 +261,66 @@ static cudaError_t upload(tbrm_resources& r, const void* src, size_t bytes, size
     return e;
 }
 
-template <int AXIS>
-static cudaError_t tma_launch(tbrm_resources& r, const CUtensorMap& lm, const CUtensorMap& dm, const TmaParams& P, bool clip, int ntiles,
+static const void* tma_kernel(int axis, bool clip, bool slab) {
+#define TBRM_K(A) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true> : (const void*) sweep_tma_kernel<A, false, true>) \
+                        : (clip ? (const void*) sweep_tma_kernel<A, true, false> : (const void*) sweep_tma_kernel<A, false, false>))
+    return axis == 0 ? TBRM_K(0) : (axis == 1 ? TBRM_K(1) : TBRM_K(2));
+#undef TBRM_K
+}
+
+static cudaError_t tma_launch(tbrm_resources& r, const void* kern, const CUtensorMap& lm, const CUtensorMap& dm, const TmaParams& P, int ntiles,
                               size_t smem) {
     const float4* tf = r.tf;
     void* args[] = {(void*) &lm, (void*) &dm, (void*) &P, (void*) &tf};
-    const void* k = clip ? (const void*) sweep_tma_kernel<AXIS, true> : (const void*) sweep_tma_kernel<AXIS, false>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    return cudaLaunchCooperativeKernel(kern, dim3(ntiles), dim3(kTmaThreads), args, smem, r.stream);
+}
+
+// ---- slab exchange arena: header (acks, error word) + 2 regions x (inbox + hand-off plane) of LL cells ----------------
+constexpr size_t kArenaHeader = 256;
+constexpr int kInboxSlots = 8;  // rows of a neighbouring band a launch may read (reach_lo + reach_hi)
+static size_t arena_inbox_cells(const int32_t d[3]) {
+    const size_t a0 = (size_t) d[0] * d[1], a2 = (size_t) d[2] * d[0];  // axis 0: ns = X, tx = Y; axis 1: ns = Y, tx = X; axis 2
+    return std::max(a0, a2) * kInboxSlots;
+}
+static size_t arena_region_bytes(const int32_t d[3]) { return (arena_inbox_cells(d) + (size_t) d[0] * d[1]) * sizeof(unsigned long long); }
+size_t slab_arena_bytes(const int32_t ldims[3]) { return kArenaHeader + 2 * arena_region_bytes(ldims); }
+static unsigned long long* arena_inbox(void* arena, const int32_t d[3], int region) {
+    return (unsigned long long*) ((char*) arena + kArenaHeader + (size_t) region * arena_region_bytes(d));
+}
+static unsigned long long* arena_zplane(void* arena, const int32_t d[3], int region) { return arena_inbox(arena, d, region) + arena_inbox_cells(d); }
+static unsigned int* arena_word(void* arena, int i) { return (unsigned int*) arena + i; }  // 0: ack from lo, 1: ack from hi, 2: error
+
+cudaError_t slab_ensure_arena(tbrm_resources& r) {
+    if (r.arena) return cudaSuccess;
+    const size_t bytes = slab_arena_bytes(r.ldims);
+    cudaError_t e = cudaMalloc(&r.arena, bytes);
     if (e != cudaSuccess) return e;
-    return cudaLaunchCooperativeKernel(k, dim3(ntiles), dim3(kTmaThreads), args, smem, r.stream);
+    r.arena_bytes = bytes;
+    return cudaMemsetAsync(r.arena, 0, bytes, r.stream);
+}
+
+// flow control between the passes of neighbouring slabs: a region of a neighbour's arena is rewritten every second pass, so
+// before exporting pass `seq` the neighbours must have finished pass seq - 2 (they post the last pass they completed)
+__global__ void slab_wait_kernel(const unsigned int* ack_lo, const unsigned int* ack_hi, unsigned int need, unsigned int* error,
+                                 unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_timer_ns();
+    for (int i = 0; i < 2; ++i) {
+        const unsigned int* a = i ? ack_hi : ack_lo;
+        if (!a) continue;
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+            if (v < need && global_timer_ns() - t0 > timeout_ns) {
+                atomicExch(error, 1u);
+                return;
+            }
+        } while (v < need);
+    }
+}
+__global__ void slab_signal_kernel(unsigned int* to_lo, unsigned int* to_hi, unsigned int seq) {
+    __threadfence_system();
+    if (to_lo) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(to_lo), "r"(seq) : "memory");
+    if (to_hi) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(to_hi), "r"(seq) : "memory");
 }
 
 __global__ void permute_yzx_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int X, int Y, int Z) {
@@ -253,22 +351,39 @@ static cudaError_t ensure_replica(tbrm_resources& r) {
     return cudaGetLastError();
 }
 
+// the pass is left to another sweep implementation; remember why (shown when a sharded volume has no alternative)
+static cudaError_t not_handled(const char* why) {
+    set_last_error(std::string("TMA-staged sweep not applicable: ") + why);
+    static const bool verbose = getenv("TBRM_DEBUG") != nullptr;
+    if (verbose) fprintf(stderr, "[tbrm] TMA-staged sweep not applicable: %s\n", why);
+    return cudaSuccess;
+}
+
+int slab_pass_order(const SweepUniforms& u) {
+    if (u.axis == 2) return u.dirn > 0 ? 1 : -1;  // the slabs of a sweep along Z form a chain in sweep order
+    HostTabs T;
+    build_tabs(u, u.a, T);
+    const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
+    if (reach_lo > 0 && reach_hi > 0) return 2;
+    return reach_hi > 0 ? -1 : 1;
+}
+
 cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled) {
     *handled = false;
-    if (change || r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res) return cudaSuccess;
+    if (change || r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res) return not_handled("change || r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res");
     const int X = r.ddims[0], Y = r.ddims[1], Z = r.ddims[2];
-    if (X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)) return cudaSuccess;  // TMA global strides must be multiples of 16 bytes
-    if (((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)) return cudaSuccess;
-    if (!get_encode()) return cudaSuccess;
+    if (X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)) return not_handled("X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)");  // TMA global strides must be multiples of 16 bytes
+    if (((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)) return not_handled("((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)");
+    if (!get_encode()) return not_handled("!get_encode()");
     int dev = r.device, sms = 0, coop = 0;
     cudaError_t e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev)) != cudaSuccess) return e;
-    if (!coop) return cudaSuccess;
+    if (!coop) return not_handled("!coop");
 
     HostTabs T;
     build_tabs(u, u.a, T);
-    if (!T.pairs_ok) return cudaSuccess;
+    if (!T.pairs_ok) return not_handled("!T.pairs_ok");
     const int tx = u.td[0], ty = u.td[1];
     TmaParams P;
     memset(&P, 0, sizeof(P));
@@ -290,26 +405,20 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     const int ext_p = kTW + (T.dmax[pa] - dmin_p_al) + 1, ext_q = kTH + (T.dmax[qa] - T.dmin[qa]) + 1,
               ext_s = kSB + (T.dmax[sa] - T.dmin[sa]) + 1;
     P.dext[0] = (ext_p + 4 + 15) / 16 * 16, P.dext[1] = ext_q, P.dext[2] = ext_s;
-    if (P.dext[0] > 256 || P.dext[1] > 256 || P.dext[2] > 256) return cudaSuccess;
+    if (P.dext[0] > 256 || P.dext[1] > 256 || P.dext[2] > 256) return not_handled("P.dext[0] > 256 || P.dext[1] > 256 || P.dext[2] > 256");
     for (int d = 0; d < 2; ++d) P.bmin[d] = T.bmin[d], P.bext[d] = (d ? kTH : kTW) + (T.bmax[d] - T.bmin[d]) + 1;
-    if (P.bext[0] > kFpW || P.bext[1] > kFpH) return cudaSuccess;
-    if (u.td[2] >= 65000) return cudaSuccess;  // slice index + 1 must fit the 16-bit tag field
-    // halo cells (footprint cells of other tiles) must fit kHaloPerThread per thread
-    {
-        const int ow = std::max(0, std::min(P.bmin[0] + P.bext[0], kTW) - std::max(P.bmin[0], 0));
-        const int oh = ow > 0 ? std::max(0, std::min(P.bmin[1] + P.bext[1], kTH) - std::max(P.bmin[1], 0)) : 0;
-        if (P.bext[0] * P.bext[1] - ow * oh > kHaloPerThread * kTmaThreads) return cudaSuccess;
-    }
+    if (P.bext[0] > kFpW || P.bext[1] > kFpH) return not_handled("P.bext[0] > kFpW || P.bext[1] > kFpH");
+    if (u.td[2] >= 65000) return not_handled("u.td[2] >= 65000");  // slice index + 1 must fit the 16-bit tag field
     // dependency lists must fit
     {
         const long long nx = (long long) (P.bext[0] + kTW - 1) / kTW + 1, ny = (long long) (P.bext[1] + kTH - 1) / kTH + 1;
-        if (nx * ny - 1 > kFusedMaxDeps) return cudaSuccess;
+        if (nx * ny - 1 > kFusedMaxDeps) return not_handled("nx * ny - 1 > kFusedMaxDeps");
     }
     // tensor maps. Light: native (X,Y,Z) fp32, box = tile x SB along the sweep axis.
     int lbox[3], ldims[3] = {r.ldims[0], r.ldims[1], r.ldims[2]};
     lbox[pa] = kTW, lbox[qa] = kTH, lbox[sa] = kSB;
     CUtensorMap lm, dm;
-    if (!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.light, ldims, lbox)) return cudaSuccess;
+    if (!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.light, ldims, lbox)) return not_handled("!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.light, ldims, lbox)");
     // light SMEM strides: box is stored with native x fastest, then y, then z
     {
         const int str[3] = {1, lbox[0], lbox[0] * lbox[1]};
@@ -318,12 +427,12 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     if (u.axis == 0) {
         if ((e = ensure_replica(r)) != cudaSuccess) return e;
         const int dd[3] = {Y, Z, X}, db[3] = {P.dext[0], P.dext[1], P.dext[2]};
-        if (!make_map3(&dm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.data_yzx, dd, db)) return cudaSuccess;
+        if (!make_map3(&dm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.data_yzx, dd, db)) return not_handled("!make_map3(&dm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.data_yzx, dd, db)");
         P.ds_q = P.dext[0], P.ds_s = P.dext[0] * P.dext[1];
     } else {
         int dd[3] = {X, Y, Z}, db[3];
         db[pa] = P.dext[0], db[qa] = P.dext[1], db[sa] = P.dext[2];
-        if (!make_map3(&dm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.data, dd, db)) return cudaSuccess;
+        if (!make_map3(&dm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.data, dd, db)) return not_handled("!make_map3(&dm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.data, dd, db)");
         const int str[3] = {1, db[0], db[0] * db[1]};
         P.ds_q = str[qa], P.ds_s = str[sa];
     }
@@ -333,19 +442,45 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     const size_t smem = (size_t) kStages * P.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
 
     const bool clip = !clip_is_inactive(u, T);
-    const void* kern = nullptr;
-    switch (u.axis) {
-        case 0: kern = clip ? (const void*) sweep_tma_kernel<0, true> : (const void*) sweep_tma_kernel<0, false>; break;
-        case 1: kern = clip ? (const void*) sweep_tma_kernel<1, true> : (const void*) sweep_tma_kernel<1, false>; break;
-        default: kern = clip ? (const void*) sweep_tma_kernel<2, true> : (const void*) sweep_tma_kernel<2, false>; break;
+    // ---- which part of the pass this GPU runs, and in how many co-resident waves (bands of tile rows) ----
+    const tbrm_slab& sl = r.slab;
+    const bool sharded = sl.nranks > 1;
+    const bool shard_q = sharded && u.axis != 2, shard_s = sharded && u.axis == 2;  // q = z for sweeps along X and Y
+    const int ns = u.td[2];
+    int q_begin = 0, q_end = ty, k_begin = 0, k_end = ns;
+    if (shard_q) q_begin = sl.z_begin, q_end = sl.z_end;
+    if (shard_s) {
+        k_begin = u.dirn > 0 ? sl.z_begin : ns - sl.z_end;
+        k_end = u.dirn > 0 ? sl.z_end : ns - sl.z_begin;
     }
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) {
-        cudaGetLastError();
-        return cudaSuccess;
-    }
+    const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTmaThreads, smem)) != cudaSuccess) return e;
-    if ((long long) sms * per_sm < ntiles) return cudaSuccess;  // the plane does not fit one co-resident wave
+    const void* kern_plain = tma_kernel(u.axis, clip, false);
+    const void* kern_slab = tma_kernel(u.axis, clip, true);
+    for (const void* k : {kern_plain, kern_slab})
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) {
+            cudaGetLastError();
+            return not_handled("shared memory per block");
+        }
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_slab, kTmaThreads, smem)) != cudaSuccess) return e;
+    int cap_rows = (int) std::min<long long>((long long) sms * per_sm / P.ntx, 1 << 20);  // tile rows of one co-resident wave
+    if (r.options.reserved[2] > 0) cap_rows = std::min(cap_rows, r.options.reserved[2]);      // test hook: force banding on small planes
+    if (cap_rows < 1) return not_handled("cap_rows < 1");
+    const int tr0 = q_begin / kTH, tr1 = (q_end + kTH - 1) / kTH;
+    auto bands_of = [&](int qb, int qe) { return ((qe + kTH - 1) / kTH - qb / kTH + cap_rows - 1) / cap_rows; };
+    const int nbands = bands_of(q_begin, q_end);
+    const int rows_per_band = (tr1 - tr0 + nbands - 1) / nbands;
+    const bool use_slab = sharded || nbands > 1;
+    if (use_slab) {
+        if (reach_lo + reach_hi > kInboxSlots) return not_handled("the footprints reach more than 8 rows into the neighbouring bands");
+        // a footprint must not reach past the adjacent band (bands and slabs are at least 8 rows)
+        if (std::max(reach_lo, reach_hi) > std::min(kTH, q_end - (tr0 + (nbands - 1) * rows_per_band) * kTH))
+            return not_handled("the footprints reach past the adjacent band");
+        if (nbands > 1 && reach_lo > 0 && reach_hi > 0) return not_handled("nbands > 1 && reach_lo > 0 && reach_hi > 0");  // bands run one after the other: one-way dependencies only
+        if (q_begin % kTH != 0 || (q_end % kTH != 0 && q_end != ty)) return not_handled("q_begin % kTH != 0 || (q_end % kTH != 0 && q_end != ty)");
+        if (k_begin % kSB != 0 || (k_end % kSB != 0 && k_end != ns) || (shard_s && ns % kSB != 0)) return not_handled("k_begin % kSB != 0 || (k_end % kSB != 0 && k_end != ns) || (shard_s && ns % kSB != 0)");
+        if ((e = slab_ensure_arena(r)) != cudaSuccess) return e;
+    }
 
     // scratch: ring, flags, tables
     const size_t ring_bytes = (size_t) kRingDepth * tx * ty * sizeof(unsigned long long);
@@ -356,13 +491,28 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
         r.ring_bytes = ring_bytes;
         r.ring_epoch = 0;
     }
-    // ring tags are (epoch << 16 | slice + 1): a fresh epoch per pass means cells left by earlier passes never match.
-    // Clear the ring when it is new, when the generic fused kernel (plain floats) used it since, or when the epoch wraps.
-    if (r.ring_epoch == 0 || r.ring_epoch >= 0xffffu) {
-        if ((e = cudaMemsetAsync(r.ring, 0, r.ring_bytes, r.stream)) != cudaSuccess) return e;
-        r.ring_epoch = 0;
+    // Cell tags are (pass_seq << 16 | slice + 1): a fresh sequence number per pass means cells left by earlier passes never
+    // match. pass_seq counts the TMA passes of this resource set; the slabs of a sharded volume execute the same passes, so
+    // their numbers agree. The ring is cleared when it is new or the generic fused kernel (plain floats) used it since
+    // (ring_epoch == 0); when the 16-bit sequence space is used up everything holding tags is cleared — locally in stream
+    // order, for a sharded volume by tbrm_slab_reset_comm on every rank (the exchange arenas are written by the neighbours).
+    if (r.pass_seq >= 0xfff0u) {
+        if (sharded) {
+            set_last_error("slab exchange: the tag sequence is used up, call tbrm_slab_reset_comm on every rank (between barriers)");
+            return cudaErrorNotSupported;
+        }
+        r.pass_seq = 0, r.ring_epoch = 0;
+        if (r.arena && (e = cudaMemsetAsync(r.arena, 0, r.arena_bytes, r.stream)) != cudaSuccess) return e;
     }
-    P.epoch = ++r.ring_epoch;
+    if (r.ring_epoch == 0) {
+        if ((e = cudaMemsetAsync(r.ring, 0, r.ring_bytes, r.stream)) != cudaSuccess) return e;
+        r.ring_epoch = 1;
+    }
+    P.epoch = ++r.pass_seq;
+    P.exp_flags = r.options.reserved[0];
+    P.cut_lo_mode = 0, P.cut_lo_add = 0;
+    if (!(P.exp_flags & 1)) window_cut_byte(u.win, T.weights_lt_one, P.cut_lo_mode, P.cut_lo_add);  // reserved[0] bit 0 disables the skip
+    P.tile_order = nullptr;
     if (r.flags_count < (size_t) ntiles * kFlagStride) {
         if (r.flags) cudaStreamSynchronize(r.stream), cudaFree(r.flags);
         r.flags = nullptr, r.flags_count = 0;
@@ -390,15 +540,90 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     // pageable-memory async copies return once the source has been staged, so T may go out of scope after this call
     P.ring = (float*) r.ring;
     P.flags = r.flags;
-    if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
-    switch (u.axis) {
-        case 0: e = tma_launch<0>(r, lm, dm, P, clip, ntiles, smem); break;
-        case 1: e = tma_launch<1>(r, lm, dm, P, clip, ntiles, smem); break;
-        default: e = tma_launch<2>(r, lm, dm, P, clip, ntiles, smem); break;
+    memset(&P.S, 0, sizeof(P.S));
+    if (!use_slab) {
+        if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
+        if ((e = tma_launch(r, kern_plain, lm, dm, P, ntiles, smem)) != cudaSuccess) return e;
+        count_launch();
+        *launches += 1;
+        *handled = true;
+        return cudaSuccess;
     }
-    if (e != cudaSuccess) return e;
-    count_launch();
-    *launches += 1;
+
+    // ---- partial launches: the bands of this GPU's share of the pass, upstream band first ----
+    const unsigned int seq = P.epoch;
+    void* peer_lo = shard_q ? r.peer_arena[0] : nullptr;  // neighbours along q exist only when q is the sharded axis
+    void* peer_hi = shard_q ? r.peer_arena[1] : nullptr;
+    if (shard_q && ((sl.rank > 0 && !peer_lo) || (sl.rank + 1 < sl.nranks && !peer_hi))) {
+        set_last_error("slab exchange: neighbour arenas are not connected (tbrm_slab_open_peer / tbrm_slab_set_peer)");
+        return cudaErrorNotSupported;
+    }
+    void* peer_up = nullptr;    // upstream / downstream slab of a sweep along Z
+    void* peer_down = nullptr;
+    if (shard_s) {
+        peer_up = u.dirn > 0 ? r.peer_arena[0] : r.peer_arena[1];
+        peer_down = u.dirn > 0 ? r.peer_arena[1] : r.peer_arena[0];
+        if ((k_begin > 0 && !peer_up) || (k_end < ns && !peer_down)) {
+            set_last_error("slab exchange: neighbour arenas are not connected (tbrm_slab_open_peer / tbrm_slab_set_peer)");
+            return cudaErrorNotSupported;
+        }
+    }
+    const unsigned long long timeout_ns = (unsigned long long) (r.slab_timeout_ms > 0 ? r.slab_timeout_ms : 4000) * 1000000ull;
+    unsigned int* err_word = arena_word(r.arena, 2);
+    if (sharded && seq > 2) {  // the neighbours must be done with the arena regions this pass overwrites
+        const unsigned int* a_lo = r.peer_arena[0] ? arena_word(r.arena, 0) : nullptr;
+        const unsigned int* a_hi = r.peer_arena[1] ? arena_word(r.arena, 1) : nullptr;
+        slab_wait_kernel<<<1, 1, 0, r.stream>>>(a_lo, a_hi, seq - 2, err_word, timeout_ns);
+        count_launch();
+        *launches += 1;
+    }
+    int nb_lo = nbands;  // bands of the lower neighbour's slab (same partition rule on every rank: tbrm_slab_partition)
+    if (shard_q && sl.rank > 0) {
+        int32_t zb, ze;
+        slab_partition(u.ldims[2], sl.nranks, sl.rank - 1, &zb, &ze);
+        nb_lo = bands_of(zb, ze);
+    }
+    const bool ascending = reach_lo > 0 || reach_hi == 0;  // footprints reach toward lower rows: lower bands are upstream
+    for (int i = 0; i < nbands; ++i) {
+        const int bi = ascending ? i : nbands - 1 - i;
+        SlabParams& S = P.S;
+        S.tile_row0 = tr0 + bi * rows_per_band;
+        S.tile_rows = std::min(rows_per_band, tr1 - S.tile_row0);
+        if (S.tile_rows <= 0) continue;
+        S.q_lo = S.tile_row0 * kTH, S.q_hi = std::min(q_end, (S.tile_row0 + S.tile_rows) * kTH);
+        S.k_begin = k_begin, S.k_end = k_end;
+        S.reach_lo = reach_lo, S.reach_hi = reach_hi;
+        S.inbox = arena_inbox(r.arena, r.ldims, (seq + bi) & 1);
+        S.out_lo = S.out_hi = nullptr;
+        if (reach_hi > 0) {  // the band below reads our first rows
+            if (bi > 0)
+                S.out_lo = arena_inbox(r.arena, r.ldims, (seq + bi - 1) & 1);
+            else if (peer_lo)
+                S.out_lo = arena_inbox(peer_lo, r.ldims, (seq + nb_lo - 1) & 1);  // the neighbour's last band
+        }
+        if (reach_lo > 0) {  // the band above reads our last rows
+            if (bi < nbands - 1)
+                S.out_hi = arena_inbox(r.arena, r.ldims, (seq + bi + 1) & 1);
+            else if (peer_hi)
+                S.out_hi = arena_inbox(peer_hi, r.ldims, seq & 1);  // the neighbour's first band
+        }
+        S.zin = (shard_s && k_begin > 0) ? arena_zplane(r.arena, r.ldims, seq & 1) : nullptr;
+        S.zout = (shard_s && k_end < ns) ? arena_zplane(peer_down, r.ldims, seq & 1) : nullptr;
+        S.error = err_word;
+        S.timeout_ns = timeout_ns;
+        if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
+        if ((e = tma_launch(r, kern_slab, lm, dm, P, S.tile_rows * P.ntx, smem)) != cudaSuccess) return e;
+        count_launch();
+        *launches += 1;
+    }
+    if (sharded) {  // tell the neighbours this slab is done with pass `seq` (acks live in THEIR arenas: word 1 = "from hi" for our lower neighbour)
+        unsigned int* to_lo = r.peer_arena[0] ? arena_word(r.peer_arena[0], 1) : nullptr;
+        unsigned int* to_hi = r.peer_arena[1] ? arena_word(r.peer_arena[1], 0) : nullptr;
+        slab_signal_kernel<<<1, 1, 0, r.stream>>>(to_lo, to_hi, seq);
+        count_launch();
+        *launches += 1;
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     *handled = true;
     return cudaSuccess;
 }

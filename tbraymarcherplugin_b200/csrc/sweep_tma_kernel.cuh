@@ -22,13 +22,26 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned int* p, unsigned int v) 
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// correctly rounded v/255 for v in 0..255 without a division (Markstein: q = v*r; q += (v - q*255)*r)
+// cells another GPU writes over NVLink (slab exchange) are accessed at system scope
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// correctly rounded v/255 for v in 0..255 without a division: with 1/255 = c_hi + c_lo (c_hi = RN(1/255)),
+// fma(v, c_hi, v*c_lo) == RN(v/255) for every byte (exhaustive check in tests/test_host_cpu.py)
 __device__ __forceinline__ float decode_u8(uint32_t v) {
     const float x = (float) v;
-    const float r = 0.003921568859368563f;  // RN(1/255)
-    const float q = x * r;
-    const float e = __fmaf_rn(-q, 255.0f, x);
-    return __fmaf_rn(e, r, q);
+    return __fmaf_rn(x, 0.003921568859368563f, x * -2.319175823606301e-10f);
 }
 // correctly rounded x / w given rw = RN(1/w)
 __device__ __forceinline__ float div_markstein(float x, float w, float rw) {
@@ -57,7 +70,14 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 //  (c) checks the halo tags (re-polls only while the upstream tile is not yet ahead) and parks the values in SMEM;
 //  (d) after ONE block barrier propagates: previous-slice taps from SMEM (own tile forwarded through SMEM, halo from the
 //      ring), extinction, export of the cells other tiles read, accumulation into the light brick in SMEM.
-template <int AXIS, bool CLIP>
+//
+// SLAB = true adds what a launch needs when it covers only part of the pass (SlabParams): a band of tile rows of the buffer
+// plane (the Z-slab of a GPU for sweeps along X / Y, or one co-resident wave of a plane too large for the GPU) and / or a
+// sub-range of the slices (the Z-slab of a GPU for sweeps along Z). Footprint rows owned by a neighbouring band arrive in a
+// full-depth inbox of LL cells (written by that band's launch: an earlier launch on this GPU, or the neighbour GPU's
+// concurrent launch through NVLink peer stores); the last slice of a slice sub-range is handed to the next slab as a
+// plane of LL cells. The per-voxel arithmetic is untouched, so a sharded pass is bit-identical to an unsharded one.
+template <int AXIS, bool CLIP, bool SLAB>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map, const TmaParams P,
                      const float4* __restrict__ tf) {
@@ -66,8 +86,11 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     constexpr int SA = AXIS;                 // native axis of s
     const SweepUniforms& U = P.U;
     const int tx = U.td[0], ty = U.td[1], ns = U.td[2];
-    const int tile = blockIdx.x, tid = threadIdx.x;
-    const int tix = tile % P.ntx, tiy = tile / P.ntx;
+    const int tid = threadIdx.x;
+    const int tix = (int) blockIdx.x % P.ntx, tiy = (SLAB ? P.S.tile_row0 : 0) + (int) blockIdx.x / P.ntx;
+    const int tile = tiy * P.ntx + tix;
+    const int row_lo = SLAB ? P.S.tile_row0 : 0, row_hi = SLAB ? P.S.tile_row0 + P.S.tile_rows : P.nty;  // tile rows of this launch
+    const int k_begin = SLAB ? P.S.k_begin : 0, k_end = SLAB ? P.S.k_end : ns;
     const int x0 = tix * kTW, y0 = tiy * kTH;
     const size_t plane = (size_t) tx * ty;
 
@@ -78,6 +101,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     uint64_t* s_bar = (uint64_t*) (s_alpha + 256);
     __shared__ int s_down[kFusedMaxDeps];
     __shared__ int s_ndown;
+    __shared__ volatile int s_abort;  // SLAB: an exchange with another launch timed out; stop waiting (results are void)
 
     const int fx0 = x0 + P.bmin[0], fy0 = y0 + P.bmin[1], FW = P.bext[0], FH = P.bext[1];
     if (tid == 0) {
@@ -85,7 +109,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // tiles that read cells of ours: tile (i,j) reads [i*TW + bmin, +FW) x [j*TH + bmin, +FH)
         int ndown = 0;
-        for (int j = 0; j < P.nty; ++j) {
+        s_abort = 0;
+        for (int j = row_lo; j < row_hi; ++j) {
             const int gy = j * kTH + P.bmin[1];
             if (gy + FH <= y0 || gy >= y0 + kTH) continue;
             for (int i = 0; i < P.ntx; ++i) {
@@ -137,7 +162,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     auto exported = [&](int gx, int gy) {
         const int rx = gx - P.bmin[0], ry = gy - P.bmin[1];  // tile origin i*TW must lie in (rx - FW, rx]
         const int ia = max(0, (rx - FW + kTW) / kTW), ib = rx >= 0 ? min(P.ntx - 1, rx / kTW) : -1;
-        const int ja = max(0, (ry - FH + kTH) / kTH), jb = ry >= 0 ? min(P.nty - 1, ry / kTH) : -1;
+        const int ja = max(row_lo, (ry - FH + kTH) / kTH), jb = ry >= 0 ? min(row_hi - 1, ry / kTH) : -1;
         for (int j = ja; j <= jb; ++j)
             for (int i = ia; i <= ib; ++i) {
                 const int gx0 = i * kTW + P.bmin[0], gy0 = j * kTH + P.bmin[1];
@@ -146,16 +171,19 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         return false;
     };
     const bool exp0 = v0 && exported(px, py), exp1 = v1 && exported(px + 1, py);
-    // halo cells this thread fetches: footprint cells inside the plane that belong to other tiles
+    // halo cells this thread fetches: footprint cells inside the plane that belong to other tiles. Cell h of the enumeration
+    // (rows above the own tile, left / right of it, rows below) goes to thread h % 256; the first two of a thread live in
+    // registers and are prefetched behind the occlusion work, the rest (footprints shifted far off the tile: a second-axis
+    // pass of a light close to its main axis) are described in SMEM and fetched in a plain loop.
     int halo_fp[kHaloPerThread], halo_ring[kHaloPerThread];
+    __shared__ int s_over_fp[kHaloOverflow], s_over_ring[kHaloOverflow];
     {
         const int ox0 = max(fx0, x0), ox1 = min(fx0 + FW, x0 + kTW), oy0 = max(fy0, y0), oy1 = min(fy0 + FH, y0 + kTH);
         const int ow = max(0, ox1 - ox0), oh = (ow > 0) ? max(0, oy1 - oy0) : 0;
         const int top = (oh > 0 ? oy0 - fy0 : FH) * FW, mid = oh * (FW - ow);
-#pragma unroll
-        for (int i = 0; i < kHaloPerThread; ++i) {
-            int h = tid + i * kTmaThreads, gx = -1, gy = -1;
-            halo_fp[i] = -1, halo_ring[i] = 0;
+        auto halo_cell = [&](int h, int& fp_idx, int& ring_idx) {
+            int gx = -1, gy = -1;
+            fp_idx = -1, ring_idx = 0;
             if (h < top) {
                 gy = fy0 + h / FW, gx = fx0 + h % FW;
             } else if (h - top < mid) {
@@ -169,11 +197,33 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 if (gy >= fy0 + FH) gy = -1;
             }
             if ((unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty) {
-                halo_fp[i] = (gy - fy0) * kFpW + (gx - fx0);
-                halo_ring[i] = gy * tx + gx;
+                fp_idx = (gy - fy0) * kFpW + (gx - fx0);
+                ring_idx = gy * tx + gx;
+                if (SLAB && (gy < P.S.q_lo || gy >= P.S.q_hi)) {  // owned by a neighbouring band: inbox row slot
+                    const int slot = gy < P.S.q_lo ? gy - (P.S.q_lo - P.S.reach_lo) : P.S.reach_lo + gy - P.S.q_hi;
+                    ring_idx = -1 - (slot * tx + gx);
+                }
             }
+        };
+#pragma unroll
+        for (int i = 0; i < kHaloPerThread; ++i) halo_cell(tid + i * kTmaThreads, halo_fp[i], halo_ring[i]);
+        for (int h = tid + kHaloPerThread * kTmaThreads; h < FW * FH; h += kTmaThreads) {
+            int f, g;
+            halo_cell(h, f, g);
+            s_over_fp[h - kHaloPerThread * kTmaThreads] = f, s_over_ring[h - kHaloPerThread * kTmaThreads] = g;
         }
     }
+    const int n_over = max(0, FW * FH - kHaloPerThread * kTmaThreads);
+    // SLAB: cells a neighbouring band reads go to its inbox as well (row slot in the RECEIVER's numbering)
+    bool xlo0 = false, xlo1 = false, xhi0 = false, xhi1 = false;
+    int xlo_idx = 0, xhi_idx = 0;
+    if (SLAB) {
+        const bool lo = P.S.out_lo != nullptr && py - P.S.q_lo < P.S.reach_hi, hi = P.S.out_hi != nullptr && P.S.q_hi - 1 - py < P.S.reach_lo;
+        xlo0 = lo && v0, xlo1 = lo && v1, xhi0 = hi && v0, xhi1 = hi && v1;
+        xlo_idx = (P.S.reach_lo + py - P.S.q_lo) * tx + px;      // the lower neighbour's q_hi is our q_lo
+        xhi_idx = (py - (P.S.q_hi - P.S.reach_lo)) * tx + px;    // the upper neighbour's q_lo is our q_hi
+    }
+    const size_t inbox_plane = SLAB ? (size_t) (P.S.reach_lo + P.S.reach_hi) * tx : 0;
     const float rwidth = 1.0f / U.win.width;
     const float step = U.a.step;
     const int shift = (col & 3) * 8;
@@ -183,13 +233,41 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const unsigned int tag_base = P.epoch << 16;
     __syncthreads();
     const int ndown = s_ndown;
+    // give up on an exchange that does not complete (a peer that died or was never launched): flag it, stop waiting
+    auto timed_out = [&](unsigned long long t0) {
+        if (global_timer_ns() - t0 < P.S.timeout_ns) return false;
+        s_abort = 1;
+        atomicExch(P.S.error, 1u);
+        return true;
+    };
+    if (SLAB && k_begin > 0 && P.S.zin != nullptr) {
+        // the slices before k_begin belong to the upstream slab: its last slice (tag k_begin) is our "slice k_begin - 1"
+        float* fp0 = s_fp + (k_begin & 1) * (kFpW * kFpH);
+        const unsigned int want = tag_base + (unsigned) k_begin;
+        for (int c = tid; c < kFpW * kFpH; c += kTmaThreads) {
+            const int gx = fx0 + c % kFpW, gy = fy0 + c / kFpW;
+            if ((unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty) {
+                const unsigned long long* cell = P.S.zin + (size_t) gy * tx + gx;
+                unsigned long long v = ld_relaxed_sys_u64(cell);
+                const unsigned long long t0 = global_timer_ns();
+                unsigned int polls = 0;
+                while ((unsigned int) (v >> 32) != want && !s_abort) {
+                    v = ld_relaxed_sys_u64(cell);
+                    if ((++polls & 255u) == 0 && timed_out(t0)) break;
+                }
+                fp0[c] = __uint_as_float((unsigned int) v);
+            }
+        }
+        __syncthreads();
+    }
 
     const int nblocks = (ns + kSB - 1) / kSB;
+    const int b_begin = k_begin / kSB, b_end = (k_end + kSB - 1) / kSB;  // SLAB slice ranges are multiples of kSB (host)
     // blocks are aligned to multiples of kSB in native coordinates (TMA: 16-byte aligned inner coordinate when the
     // sweep axis is x); a descending sweep visits them last-to-first
     auto block_s0 = [&](int b) { return (U.dirn > 0 ? b : nblocks - 1 - b) * kSB; };
     auto issue_load = [&](int b) {
-        const int st = b % kStages;
+        const int st = (b - b_begin) % kStages;
         unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
         mbar_expect_tx(&s_bar[st], (uint32_t) (P.light_bytes + P.data_bytes));
         const int s0 = block_s0(b);
@@ -204,15 +282,15 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             tma_load_3d(sb + P.light_bytes, &data_map, dc[0], dc[1], dc[2], &s_bar[st]);
         }
     };
-    if (tid == 0) issue_load(0);
+    if (tid == 0) issue_load(b_begin);
 
-    for (int b = 0; b < nblocks; ++b) {
-        const int st = b % kStages;
-        if (tid == 0 && b + 1 < nblocks) {
+    for (int b = b_begin; b < b_end; ++b) {
+        const int st = (b - b_begin) % kStages;
+        if (tid == 0 && b + 1 < b_end) {
             tma_wait_read<1>();  // the store that last read stage (b+1)%3 (block b-2) has finished reading SMEM
             issue_load(b + 1);
         }
-        mbar_wait(&s_bar[st], (uint32_t) ((b / kStages) & 1));
+        mbar_wait(&s_bar[st], (uint32_t) (((b - b_begin) / kStages) & 1));
         unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
         float* s_light = (float*) sb;
         const unsigned char* s_data = sb + P.light_bytes;
@@ -228,13 +306,18 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             // ---- (a) issue the halo loads of slice k-1 (and, every 4th slice, the back-pressure probes) ----
             const unsigned int want_tag = tag_base + (unsigned) k;  // slice k-1 carries tag k
             const unsigned long long* rd = ring + (size_t) ((k + kRingDepth - 1) % kRingDepth) * plane;
+            const unsigned long long* rdi = SLAB ? P.S.inbox + (size_t) max(k - 1, 0) * inbox_plane : nullptr;  // inbox is full depth
+            auto halo_load = [&](int i) {
+                if (SLAB && halo_ring[i] < 0) return ld_relaxed_sys_u64(rdi + (-1 - halo_ring[i]));
+                return ld_relaxed_u64(rd + halo_ring[i]);
+            };
             unsigned long long hv[kHaloPerThread];
 #pragma unroll
             for (int i = 0; i < kHaloPerThread; ++i) hv[i] = 0;
-            if (k > 0) {
+            if (k > k_begin) {
 #pragma unroll
                 for (int i = 0; i < kHaloPerThread; ++i)
-                    if (halo_fp[i] >= 0) hv[i] = ld_relaxed_u64(rd + halo_ring[i]);
+                    if (halo_fp[i] >= 0) hv[i] = halo_load(i);
             }
             // a ring slot is reused every kRingDepth slices: before exporting slices k..k+3 every reader must have
             // consumed slice k+3-kRingDepth, i.e. passed the barrier of its slice k+4-kRingDepth
@@ -276,6 +359,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             if (g0 || g1) {
                 // 4 rows (q, s) x 3 columns of taps; two aligned 32-bit loads + a funnel shift per row
                 float t[3][2][2];
+                uint32_t wq[2][2];
                 const unsigned char* base = s_data + thread_data + rows * P.ds_s;
 #pragma unroll
                 for (int js = 0; js < 2; ++js)
@@ -283,60 +367,101 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                     for (int jq = 0; jq < 2; ++jq) {
                         const unsigned char* rowp = base + jq * P.ds_q + js * P.ds_s;
                         const uint32_t a = *(const uint32_t*) rowp, bb = *(const uint32_t*) (rowp + 4);
-                        const uint32_t w = __funnelshift_r(a, bb, shift);
-                        t[0][jq][js] = decode_u8(w & 0xffu);
-                        t[1][jq][js] = decode_u8((w >> 8) & 0xffu);
-                        t[2][jq][js] = decode_u8((w >> 16) & 0xffu);
+                        wq[jq][js] = __funnelshift_r(a, bb, shift) & 0x00ffffffu;
                     }
-                if (!(all_pq && inS0 && inS1)) {
-                    const bool ip[3] = {inP0, inP1, inP2}, iq[2] = {inQ0, inQ1}, is[2] = {inS0, inS1};
+                const bool all_in = all_pq && inS0 && inS1;
+                // Exact empty-space skip (SWAR "some byte > T", T = largest byte the low cut-off rejects): a trilinear value
+                // lies between its smallest and largest tap and the window position is monotone in the value, so if no tap
+                // exceeds T both samples are rejected and return exactly 0 (WindowedSampling.usf:28)
+                uint32_t any_gt = 1u;
+                if (P.cut_lo_mode == 1)
+                    any_gt = (((wq[0][0] + P.cut_lo_add) | wq[0][0]) | ((wq[0][1] + P.cut_lo_add) | wq[0][1]) |
+                              ((wq[1][0] + P.cut_lo_add) | wq[1][0]) | ((wq[1][1] + P.cut_lo_add) | wq[1][1])) & 0x00808080u;
+                else if (P.cut_lo_mode == 2)
+                    any_gt = ((((wq[0][0] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[0][0]) | (((wq[0][1] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[0][1]) |
+                              (((wq[1][0] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[1][0]) | (((wq[1][1] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[1][1])) & 0x00808080u;
+                if (!(all_in && any_gt == 0u)) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
+                    for (int js = 0; js < 2; ++js)
 #pragma unroll
-                        for (int jq = 0; jq < 2; ++jq)
+                        for (int jq = 0; jq < 2; ++jq) {
+                            const uint32_t w = wq[jq][js];
+                            t[0][jq][js] = decode_u8(w & 0xffu);
+                            t[1][jq][js] = decode_u8((w >> 8) & 0xffu);
+                            t[2][jq][js] = decode_u8(w >> 16);
+                        }
+                    if (!all_in) {
+                        const bool ip[3] = {inP0, inP1, inP2}, iq[2] = {inQ0, inQ1}, is[2] = {inS0, inS1};
 #pragma unroll
-                            for (int js = 0; js < 2; ++js)
-                                if (!(ip[c] && iq[jq] && is[js])) t[c][jq][js] = U.data_border;
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int jq = 0; jq < 2; ++jq)
+#pragma unroll
+                                for (int js = 0; js < 2; ++js)
+                                    if (!(ip[c] && iq[jq] && is[js])) t[c][jq][js] = U.data_border;
+                    }
+                    float val0, val1;
+                    if (AXIS == 2) {  // x = p, y = q, z = s
+                        const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
+                        const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
+                        val0 = lerpf(lerpf(a00, a10, fq), lerpf(a01, a11, fq), fs);
+                        const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
+                        const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
+                        val1 = lerpf(lerpf(b00, b10, fq), lerpf(b01, b11, fq), fs);
+                    } else if (AXIS == 1) {  // x = p, y = s, z = q
+                        const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
+                        const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
+                        val0 = lerpf(lerpf(a00, a01, fs), lerpf(a10, a11, fs), fq);
+                        const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
+                        const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
+                        val1 = lerpf(lerpf(b00, b01, fs), lerpf(b10, b11, fs), fq);
+                    } else {  // x = s, y = p, z = q
+                        const float d00 = lerpf(t[0][0][0], t[0][0][1], fs), d10 = lerpf(t[1][0][0], t[1][0][1], fs),
+                                    d20 = lerpf(t[2][0][0], t[2][0][1], fs);
+                        const float d01 = lerpf(t[0][1][0], t[0][1][1], fs), d11 = lerpf(t[1][1][0], t[1][1][1], fs),
+                                    d21 = lerpf(t[2][1][0], t[2][1][1], fs);
+                        val0 = lerpf(lerpf(d00, d10, fp0), lerpf(d01, d11, fp0), fq);
+                        val1 = lerpf(lerpf(d10, d20, fp1), lerpf(d11, d21, fp1), fq);
+                    }
+                    if (g0) cs0 = opacity_from_value(val0, U.win, rwidth, s_alpha, step) * w0;
+                    if (g1) cs1 = opacity_from_value(val1, U.win, rwidth, s_alpha, step) * w1;
                 }
-                float val0, val1;
-                if (AXIS == 2) {  // x = p, y = q, z = s
-                    const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
-                    const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
-                    val0 = lerpf(lerpf(a00, a10, fq), lerpf(a01, a11, fq), fs);
-                    const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
-                    const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
-                    val1 = lerpf(lerpf(b00, b10, fq), lerpf(b01, b11, fq), fs);
-                } else if (AXIS == 1) {  // x = p, y = s, z = q
-                    const float a00 = lerpf(t[0][0][0], t[1][0][0], fp0), a10 = lerpf(t[0][1][0], t[1][1][0], fp0);
-                    const float a01 = lerpf(t[0][0][1], t[1][0][1], fp0), a11 = lerpf(t[0][1][1], t[1][1][1], fp0);
-                    val0 = lerpf(lerpf(a00, a01, fs), lerpf(a10, a11, fs), fq);
-                    const float b00 = lerpf(t[1][0][0], t[2][0][0], fp1), b10 = lerpf(t[1][1][0], t[2][1][0], fp1);
-                    const float b01 = lerpf(t[1][0][1], t[2][0][1], fp1), b11 = lerpf(t[1][1][1], t[2][1][1], fp1);
-                    val1 = lerpf(lerpf(b00, b01, fs), lerpf(b10, b11, fs), fq);
-                } else {  // x = s, y = p, z = q
-                    const float d00 = lerpf(t[0][0][0], t[0][0][1], fs), d10 = lerpf(t[1][0][0], t[1][0][1], fs),
-                                d20 = lerpf(t[2][0][0], t[2][0][1], fs);
-                    const float d01 = lerpf(t[0][1][0], t[0][1][1], fs), d11 = lerpf(t[1][1][0], t[1][1][1], fs),
-                                d21 = lerpf(t[2][1][0], t[2][1][1], fs);
-                    val0 = lerpf(lerpf(d00, d10, fp0), lerpf(d01, d11, fp0), fq);
-                    val1 = lerpf(lerpf(d10, d20, fp1), lerpf(d11, d21, fp1), fq);
-                }
-                if (g0) cs0 = opacity_from_value(val0, U.win, rwidth, s_alpha, step) * w0;
-                if (g1) cs1 = opacity_from_value(val1, U.win, rwidth, s_alpha, step) * w1;
             }
 
             // ---- (c) the halo of slice k-1 must have arrived; readers of the slots we overwrite must have moved on ----
-            if (k > 0) {
+            if (k > k_begin) {
 #pragma unroll
                 for (int i = 0; i < kHaloPerThread; ++i)
                     if (halo_fp[i] >= 0) {
-                        while ((unsigned int) (hv[i] >> 32) != want_tag) hv[i] = ld_relaxed_u64(rd + halo_ring[i]);
+                        if (!SLAB) {
+                            while ((unsigned int) (hv[i] >> 32) != want_tag) hv[i] = ld_relaxed_u64(rd + halo_ring[i]);
+                        } else if ((unsigned int) (hv[i] >> 32) != want_tag) {
+                            const unsigned long long t0 = global_timer_ns();
+                            unsigned int polls = 0;
+                            while ((unsigned int) (hv[i] >> 32) != want_tag && !s_abort) {
+                                hv[i] = halo_load(i);
+                                if ((++polls & 255u) == 0 && timed_out(t0)) break;
+                            }
+                        }
                         fp_cur[halo_fp[i]] = __uint_as_float((unsigned int) hv[i]);
                     }
+                for (int h = tid; h < n_over; h += kTmaThreads) {
+                    const int f = s_over_fp[h], g = s_over_ring[h];
+                    if (f < 0) continue;
+                    const unsigned long long* cell = (SLAB && g < 0) ? rdi + (-1 - g) : rd + g;
+                    unsigned long long v = SLAB ? ld_relaxed_sys_u64(cell) : ld_relaxed_u64(cell);
+                    const unsigned long long t0 = SLAB ? global_timer_ns() : 0ull;
+                    unsigned int polls = 0;
+                    while ((unsigned int) (v >> 32) != want_tag && !(SLAB && s_abort)) {
+                        v = SLAB ? ld_relaxed_sys_u64(cell) : ld_relaxed_u64(cell);
+                        if (SLAB && (++polls & 255u) == 0 && timed_out(t0)) break;
+                    }
+                    fp_cur[f] = __uint_as_float((unsigned int) v);
+                }
             }
             if (probe) {
                 const unsigned int need = (unsigned) (k + 4 - kRingDepth);
-                while (pv < need) pv = ld_relaxed_u32(P.flags + (size_t) s_down[tid] * kFlagStride);
+                while (pv < need && !(SLAB && s_abort)) pv = ld_relaxed_u32(P.flags + (size_t) s_down[tid] * kFlagStride);
             }
             __syncthreads();
             // progress counter for back-pressure: every read of slice k-1 by this tile is done
@@ -356,6 +481,18 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 const unsigned long long tag = (unsigned long long) (tag_base + (unsigned) k + 1u) << 32;
                 if (exp0) st_relaxed_u64(wr, tag | __float_as_uint(cur0));
                 if (exp1) st_relaxed_u64(wr + 1, tag | __float_as_uint(cur1));
+                if (SLAB) {
+                    const size_t ko = (size_t) k * inbox_plane;
+                    if (xlo0) st_relaxed_sys_u64(P.S.out_lo + ko + xlo_idx, tag | __float_as_uint(cur0));
+                    if (xlo1) st_relaxed_sys_u64(P.S.out_lo + ko + xlo_idx + 1, tag | __float_as_uint(cur1));
+                    if (xhi0) st_relaxed_sys_u64(P.S.out_hi + ko + xhi_idx, tag | __float_as_uint(cur0));
+                    if (xhi1) st_relaxed_sys_u64(P.S.out_hi + ko + xhi_idx + 1, tag | __float_as_uint(cur1));
+                    if (P.S.zout != nullptr && k == k_end - 1) {  // hand the last slice of this slab to the next one
+                        unsigned long long* zo = P.S.zout + (size_t) px + (size_t) tx * py;
+                        if (v0) st_relaxed_sys_u64(zo, tag | __float_as_uint(cur0));
+                        if (v1) st_relaxed_sys_u64(zo + 1, tag | __float_as_uint(cur1));
+                    }
+                }
                 float* lp = s_light + light_off + (loop - s0) * P.ls_s;
                 if (v0 && fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
                 if (v1 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);

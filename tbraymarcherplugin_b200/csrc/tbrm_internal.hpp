@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 
@@ -53,6 +54,16 @@ struct tbrm_resources {
     bool bricks_valid = false;
     void* tables = nullptr;
     size_t tables_bytes = 0;
+    bool light_owned = true;
+
+    // Z-slab sharding of this volume over several GPUs and the exchange arena of partial sweep launches
+    tbrm_slab slab = {0, 1, 0, 0};
+    unsigned int pass_seq = 0;     // TMA passes executed: the tag sequence of ring / arena cells
+    void* arena = nullptr;         // header + 2 regions x (inbox + hand-off plane) of LL cells, written by the neighbours
+    size_t arena_bytes = 0;
+    void* peer_arena[2] = {nullptr, nullptr};  // arenas of the slabs below / above (peer-mapped or same-process pointers)
+    bool peer_ipc[2] = {false, false};
+    int slab_timeout_ms = 0;       // 0 = default (4 s)
 
     size_t light_voxels() const { return (size_t) ldims[0] * ldims[1] * ldims[2]; }
     size_t data_voxels() const { return (size_t) ddims[0] * ddims[1] * ddims[2]; }
@@ -72,6 +83,15 @@ cudaError_t sweep_pass_per_slice(tbrm_resources& r, const SweepUniforms& u, bool
 cudaError_t sweep_pass_fused(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
 cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
 cudaError_t clear_light(tbrm_resources& r, float value);
+int slab_pass_order(const SweepUniforms& u);  // +1 lower slabs first, -1 higher slabs first, 2 only concurrently
+size_t slab_arena_bytes(const int32_t ldims[3]);
+cudaError_t slab_ensure_arena(tbrm_resources& r);
+// the partition rule every rank applies: slabs are multiples of 8 slices, the last rank takes the remainder
+inline void slab_partition(int Z, int nranks, int rank, int32_t* z_begin, int32_t* z_end) {
+    const int per = std::max(8, (Z / nranks + 7) / 8 * 8);
+    *z_begin = std::min(Z, rank * per);
+    *z_end = rank + 1 == nranks ? Z : std::min(Z, (rank + 1) * per);
+}
 
 // raymarch.cu
 cudaError_t raymarch_cube_setup(tbrm_resources& r, const host::CameraUniforms& cam, float* d_out);
