@@ -255,6 +255,15 @@ tbrm_status tbrm_raymarch_cube_setup(tbrm_resources* res, const tbrm_camera* cam
 tbrm_status tbrm_raymarch_lit(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world, float step_count,
                               int row_begin, int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps);
 
+/* The same for the image rows one GPU renders when a frame is dealt to `block_stride` GPUs in interleaved blocks of
+ * `block_rows` rows (a multiple of 8): blocks first_block, first_block + block_stride, ... The rows land compacted in
+ * out_rgba (tbrm_raymarch_interleaved_rows(...) rows of W float4), in image order. Interleaving balances early ray
+ * termination and ray length between the GPUs ("per-GPU tile compositing"). */
+tbrm_status tbrm_raymarch_lit_interleaved(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world, float step_count,
+                                          int block_rows, int first_block, int block_stride, float* out_rgba, int out_is_device,
+                                          uint64_t* out_steps);
+int tbrm_raymarch_interleaved_rows(int height, int block_rows, int first_block, int block_stride);
+
 /* PerformMandelbulbRaymarchReturnDistance over the image rows [row_begin,row_end): out[2*pixel] = (x, y).
  * out_iterations (optional): total Mandelbulb_SDF inner-loop iterations executed. Needs no resources. */
 tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, const tbrm_camera* cam,

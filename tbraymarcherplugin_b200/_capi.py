@@ -160,6 +160,8 @@ PROTOTYPES = {
     "tbrm_slab_pass_order": (_I, [_P, C.POINTER(DirLight), C.POINTER(World), _I, C.POINTER(_I)]),
     "tbrm_raymarch_cube_setup": (_I, [_P, C.POINTER(Camera), C.POINTER(World), _P, _I]),
     "tbrm_raymarch_lit": (_I, [_P, C.POINTER(Camera), C.POINTER(World), C.c_float, _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
+    "tbrm_raymarch_lit_interleaved": (_I, [_P, C.POINTER(Camera), C.POINTER(World), C.c_float, _I, _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
+    "tbrm_raymarch_interleaved_rows": (_I, [_I, _I, _I, _I]),
     "tbrm_mandelbulb_march": (_I, [_I, C.POINTER(Mandelbulb), C.POINTER(Camera), C.POINTER(World), _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
     "tbrm_flush": (_I, [_P]),
     "tbrm_stream": (_P, [_P]),

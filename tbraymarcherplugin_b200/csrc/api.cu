@@ -580,14 +580,15 @@ tbrm_status tbrm_raymarch_cube_setup(tbrm_resources* r, const tbrm_camera* cam, 
                        [&](void* d) { return raymarch_cube_setup(*r, cu, (float*) d); });
 }
 
-tbrm_status tbrm_raymarch_lit(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
-                              int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+static tbrm_status raymarch_lit_impl(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                                     int row_end, int row_block, int block_stride, float* out_rgba, int out_is_device, uint64_t* out_steps) {
     if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
     TBRM_REQUIRE(world && out_rgba, "tbrm_raymarch_lit: null argument");
     TBRM_REQUIRE(camera_valid(cam), "tbrm_raymarch_lit: invalid camera");
     TBRM_REQUIRE(step_count > 0.0f, "tbrm_raymarch_lit: step count must be positive");
     TBRM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= cam->height, "tbrm_raymarch_lit: bad row range");
-    if (row_begin == row_end) {
+    const int rows = raymarch_local_rows(row_begin, row_end, row_block, block_stride);
+    if (rows == 0) {
         if (out_steps) *out_steps = 0;
         return TBRM_OK;
     }
@@ -598,9 +599,9 @@ tbrm_status tbrm_raymarch_lit(tbrm_resources* r, const tbrm_camera* cam, const t
     host::plan_clip(*world, cc, cd);  // SetMaterialClippingParameters, RaymarchVolume.cpp:705-728
     unsigned long long* d_steps = out_steps ? r->counters : nullptr;
     if (d_steps) TBRM_CUDA(cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), r->stream));
-    const size_t bytes = (size_t) cam->width * (row_end - row_begin) * 4 * sizeof(float);
+    const size_t bytes = (size_t) cam->width * rows * 4 * sizeof(float);
     tbrm_status s = with_output(r->device, r->stream, out_rgba, bytes, out_is_device, [&](void* d) {
-        return raymarch_lit(*r, cu, cc, cd, step_count, row_begin, row_end, (float*) d, d_steps);
+        return raymarch_lit(*r, cu, cc, cd, step_count, row_begin, row_end, row_block, block_stride, (float*) d, d_steps);
     });
     if (s != TBRM_OK) return s;
     if (out_steps) {
@@ -610,6 +611,25 @@ tbrm_status tbrm_raymarch_lit(tbrm_resources* r, const tbrm_camera* cam, const t
         *out_steps = h;
     }
     return TBRM_OK;
+}
+
+tbrm_status tbrm_raymarch_lit(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                              int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    return raymarch_lit_impl(r, cam, world, step_count, row_begin, row_end, 8, 1, out_rgba, out_is_device, out_steps);
+}
+
+tbrm_status tbrm_raymarch_lit_interleaved(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count,
+                                          int block_rows, int first_block, int block_stride, float* out_rgba, int out_is_device,
+                                          uint64_t* out_steps) {
+    TBRM_REQUIRE(cam && block_rows > 0 && block_rows % 8 == 0 && first_block >= 0 && block_stride >= 1 && first_block < block_stride,
+                 "tbrm_raymarch_lit_interleaved: block_rows must be a positive multiple of 8, 0 <= first_block < block_stride");
+    const int row_begin = std::min(first_block * block_rows, cam->height);
+    return raymarch_lit_impl(r, cam, world, step_count, row_begin, cam->height, block_rows, block_stride, out_rgba, out_is_device, out_steps);
+}
+
+int tbrm_raymarch_interleaved_rows(int height, int block_rows, int first_block, int block_stride) {
+    if (height <= 0 || block_rows <= 0 || block_stride < 1 || first_block < 0) return 0;
+    return raymarch_local_rows(std::min(first_block * block_rows, height), height, block_rows, block_stride);
 }
 
 tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, const tbrm_camera* cam, const tbrm_world* world,

@@ -20,6 +20,7 @@ struct MarchUniforms {
     float clip_center[3], clip_dir[3];
     float step_count;
     int row_begin, row_end;
+    int row_block, block_stride;  // local row lr renders image row row_begin + (lr / row_block) * row_block * block_stride + lr % row_block
     int data_wrap;
 };
 
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(256) raymarch_lit_kernel(const MarchUniforms U
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ix = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int iy = U.row_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    const int lr = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);  // row of the output buffer
+    const int iy = U.row_begin + (lr / U.row_block) * U.row_block * U.block_stride + lr % U.row_block;
     unsigned int steps = 0;
     if (ix < U.cam.width && iy < U.row_end) {
         const V3 V = camera_vector(U.cam, ix, iy);
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(256) raymarch_lit_kernel(const MarchUniforms U
                                   U.clip_dir[1], U.clip_dir[2]);
             if (!(cd <= 0.0f)) accumulate_step<DataT, LightT>(U, data, light, s_tf, cur, 100.0f * fin, acc);
         }
-        out[(size_t) (iy - U.row_begin) * U.cam.width + ix] = acc;
+        out[(size_t) lr * U.cam.width + ix] = acc;
     }
     if (steps_out) {
         unsigned int s = steps;
@@ -326,7 +328,8 @@ __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ix = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int iy = U.row_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    const int lr = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);  // row of the output buffer
+    const int iy = U.row_begin + (lr / U.row_block) * U.row_block * U.block_stride + lr % U.row_block;
     unsigned int steps = 0;
     if (ix < U.cam.width && iy < U.row_end) {
         const V3 V = camera_vector(U.cam, ix, iy);
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F
             }
             if (!clipped) fast_sample(F, data, light, s_tf, cur, 100.0f * fin, acc);
         }
-        out[(size_t) (iy - U.row_begin) * U.cam.width + ix] = acc;
+        out[(size_t) lr * U.cam.width + ix] = acc;
     }
     if (steps_out) {
         unsigned int s = steps;
@@ -428,7 +431,7 @@ cudaError_t raymarch_cube_setup(tbrm_resources& r, const host::CameraUniforms& c
 
 template <typename DataT, typename LightT>
 static cudaError_t launch_lit(tbrm_resources& r, const MarchUniforms& U, float* d_out, unsigned long long* d_steps) {
-    const int rows = U.row_end - U.row_begin;
+    const int rows = raymarch_local_rows(U.row_begin, U.row_end, U.row_block, U.block_stride);
     const dim3 grid((U.cam.width + 31) / 32, (rows + 7) / 8);
     raymarch_lit_kernel<DataT, LightT><<<grid, 256, 0, r.stream>>>(U, (const DataT*) r.data, (const LightT*) r.light, r.tf,
                                                                    (float4*) d_out, d_steps);
@@ -473,8 +476,16 @@ static bool clip_never_rejects(const float c[3], const float d[3]) {
     return dmin > 1.0;
 }
 
+// rows of the output buffer when blocks of `row_block` rows, every `block_stride`-th one starting at row_begin, are rendered
+int raymarch_local_rows(int row_begin, int row_end, int row_block, int block_stride) {
+    int rows = 0;
+    for (int b = row_begin; b < row_end; b += row_block * block_stride) rows += std::min(row_block, row_end - b);
+    return rows;
+}
+
 cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, const float clip_center[3], const float clip_dir[3],
-                         float step_count, int row_begin, int row_end, float* d_out, unsigned long long* d_steps) {
+                         float step_count, int row_begin, int row_end, int row_block, int block_stride, float* d_out,
+                         unsigned long long* d_steps) {
     MarchUniforms U;
     U.cam = to_raycam(cam);
     for (int k = 0; k < 3; ++k) {
@@ -486,6 +497,7 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
     U.win = Windowing{r.windowing.center, r.windowing.width, r.windowing.low_cutoff ? 1.0f : 0.0f, r.windowing.high_cutoff ? 1.0f : 0.0f};
     U.step_count = step_count;
     U.row_begin = row_begin, U.row_end = row_end;
+    U.row_block = row_block, U.block_stride = block_stride;
     U.data_wrap = r.options.data_addr_wrap;
     const bool l8 = r.light_fmt == TBRM_FMT_G8;
     if (r.data_fmt == TBRM_FMT_G8 && !l8 && !U.data_wrap && r.options.reserved[1] == 0) {
@@ -500,7 +512,7 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
             if (e != cudaSuccess) return e;
             F.bricks = (const uint8_t*) r.bricks;
         }
-        const int rows = row_end - row_begin;
+        const int rows = raymarch_local_rows(row_begin, row_end, row_block, block_stride);
         const dim3 grid((cam.width + 31) / 32, (rows + 7) / 8);
         if (clip_never_rejects(clip_center, clip_dir))
             raymarch_fast_kernel<false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);

@@ -96,7 +96,9 @@ inline void slab_partition(int Z, int nranks, int rank, int32_t* z_begin, int32_
 // raymarch.cu
 cudaError_t raymarch_cube_setup(tbrm_resources& r, const host::CameraUniforms& cam, float* d_out);
 cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, const float clip_center[3], const float clip_dir[3],
-                         float step_count, int row_begin, int row_end, float* d_out, unsigned long long* d_steps);
+                         float step_count, int row_begin, int row_end, int row_block, int block_stride, float* d_out,
+                         unsigned long long* d_steps);
+int raymarch_local_rows(int row_begin, int row_end, int row_block, int block_stride);
 
 // mandelbulb.cu
 cudaError_t mandelbulb_march(cudaStream_t stream, const tbrm_mandelbulb& mb, const host::CameraUniforms& cam, int row_begin,

@@ -1,16 +1,31 @@
-"""Host-side sharding logic for multi-GPU runs (one process per GPU, launched by torchrun).
+"""Host-side sharding logic for multi-GPU runs (one process per GPU, launched by torchrun) — SURVEY.md §8(e), DESIGN.md §8.
 
-Round 1 shards the path by independent units with no data-path collective:
-  * volumes of a scene (each ARaymarchVolume owns its resources) are dealt round-robin to ranks;
-  * the rows of one frame can be dealt to ranks in interleaved blocks (the unit tbrm_raymarch_lit renders), which balances
-    early ray termination across ranks; gathering the blocks back is plain concatenation.
-torch.distributed is used only for barriers, max-over-ranks timing and (optionally) gathering rendered rows.
+Two ways to spread the hot path over the GPUs of a box:
+
+* **independent volumes** (a scene holds several ARaymarchVolumes, each with its own resources): volumes are dealt to
+  ranks, no data-path collective (``volumes_of_rank``);
+* **one volume, Z-slab sharded** (``FShardedRaymarchVolume``): every rank holds the whole R8 data volume (1 B/voxel,
+  replicated by an NCCL all-gather of the uploaded slabs) and a full-size light volume of which it owns the slices
+  ``tbrm_slab_partition`` assigns to it. ``AddDirLight`` runs on every rank; the propagated light crosses slab boundaries
+  *inside the sweep kernel* through NVLink peer stores into the neighbours' exchange arenas (libtbrm.so, CUDA IPC), so a
+  sharded sweep is bit-identical to an unsharded one. ``GatherLightVolume`` is an in-place NCCL all-gather of the slabs;
+  ``Render`` deals the frame to the ranks in interleaved 8-row blocks and gathers them on rank 0.
+
+torch / torch.distributed are plumbing here: device memory the collectives can address, the NCCL calls and their stream.
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
 
 
+# --------------------------------------------------------------------------------------------------------------
+# pure host logic (no GPU needed; covered by the gloo tests)
+# --------------------------------------------------------------------------------------------------------------
 def volumes_of_rank(n_volumes: int, rank: int, world_size: int) -> List[int]:
     """Volume indices owned by `rank`: round-robin, every volume owned exactly once."""
     if not (0 <= rank < world_size):
@@ -26,15 +41,28 @@ def row_blocks_of_rank(height: int, rank: int, world_size: int, block_rows: int 
     return blocks[rank::world_size]
 
 
+def rows_of_rank(height: int, rank: int, world_size: int, block_rows: int = 8) -> np.ndarray:
+    """Image rows rank `rank` renders, in the order they appear in its compacted output (tbrm_raymarch_lit_interleaved)."""
+    blocks = row_blocks_of_rank(height, rank, world_size, block_rows)
+    if not blocks:
+        return np.zeros(0, np.int64)
+    return np.concatenate([np.arange(b, e, dtype=np.int64) for b, e in blocks])
+
+
 def assemble_rows(height: int, world_size: int, per_rank_rows: Sequence[Sequence], block_rows: int = 8):
     """Inverse of row_blocks_of_rank: per_rank_rows[r] is the list of row-block arrays rank r rendered, in order."""
-    import numpy as np
-
     out = [None] * len(range(0, height, block_rows))
     for r in range(world_size):
         for i, blk in enumerate(per_rank_rows[r]):
             out[r + i * world_size] = blk
     return np.concatenate(out, axis=0)
+
+
+def slab_of_rank(z_slices: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """The Z-slab [z_begin, z_end) of `rank` — the partition rule of the library (multiples of 8 slices)."""
+    z0, z1 = C.c_int32(), C.c_int32()
+    _capi.load().tbrm_slab_partition(int(z_slices), int(world_size), int(rank), C.byref(z0), C.byref(z1))
+    return z0.value, z1.value
 
 
 def max_over_ranks(value: float, device=None) -> float:
@@ -47,3 +75,152 @@ def max_over_ranks(value: float, device=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def gather_interleaved_rows(local_rows, height: int, block_rows: int, dst: int = 0, group=None):
+    """Gather the compacted row blocks every rank rendered into the full frame on rank `dst` (None elsewhere).
+
+    `local_rows`: tensor (rows_of_rank, W, C) on the backend's device (CUDA for nccl, CPU for gloo). Ranks own different
+    numbers of rows, so blocks are padded to the largest share for the fixed-size gather and scattered by row index."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = [len(rows_of_rank(height, r, world, block_rows)) for r in range(world)]
+    if local_rows.shape[0] != counts[rank]:
+        raise ValueError(f"rank {rank} holds {local_rows.shape[0]} rows, expected {counts[rank]}")
+    pad = max(counts)
+    send = local_rows
+    if send.shape[0] < pad:
+        send = torch.cat([send, send.new_zeros((pad - send.shape[0],) + tuple(send.shape[1:]))], 0)
+    send = send.contiguous()
+    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = send.new_empty((height,) + tuple(send.shape[1:]))
+    for r in range(world):
+        idx = torch.as_tensor(rows_of_rank(height, r, world, block_rows), device=send.device)
+        out.index_copy_(0, idx, bufs[r][: counts[r]])
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# one volume sharded over the ranks of a process group
+# --------------------------------------------------------------------------------------------------------------
+class FShardedRaymarchVolume:
+    """FBasicRaymarchRenderingResources of ONE ARaymarchVolume, Z-slab sharded over a torch.distributed group.
+
+    Every method is collective: all ranks call it with the same arguments (like the render commands of one volume)."""
+
+    BLOCK_ROWS = 8
+
+    def __init__(self, data_dims: Sequence[int], device: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from .raymarch_utils import FMT_G8, URaymarchUtils
+
+        self.lib = _capi.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        X, Y, Z = (int(d) for d in data_dims)
+        self.dims = (X, Y, Z)
+        self.z0, self.z1 = slab_of_rank(Z, self.rank, self.world)
+        slabs = [slab_of_rank(Z, r, self.world) for r in range(self.world)]
+        if any(b - a != self.z1 - self.z0 or b <= a for a, b in slabs):
+            raise ValueError(f"{Z} slices do not split into {self.world} equal slabs of a multiple of 8 slices")
+        self.res = URaymarchUtils.InitializeRaymarchResources(self.dims, FMT_G8, bLightVolume32Bit=True, device=device)
+        dev = torch.device("cuda", device)
+        # collectives run on these tensors, the library computes on them: caller-owned, bound into the resource set
+        self.data = torch.empty((Z, Y, X), dtype=torch.uint8, device=dev)
+        self.light = torch.zeros((Z, Y, X), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        _capi.check(self.lib.tbrm_bind_volume_device(self.res.handle, C.c_void_p(self.data.data_ptr())))
+        _capi.check(self.lib.tbrm_bind_light_volume_device(self.res.handle, C.c_void_p(self.light.data_ptr())))
+        self.res.bIsInitialized = True
+        slab = _capi.Slab(self.rank, self.world, self.z0, self.z1)
+        _capi.check(self.lib.tbrm_slab_configure(self.res.handle, C.byref(slab)))
+        # exchange arenas: CUDA IPC handles travel through the process group, neighbours map each other's arena
+        handle = (C.c_ubyte * 64)()
+        _capi.check(self.lib.tbrm_slab_ipc_handle(self.res.handle, handle))
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        for side, peer in ((-1, self.rank - 1), (+1, self.rank + 1)):
+            if 0 <= peer < self.world:
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
+                _capi.check(self.lib.tbrm_slab_open_peer(self.res.handle, side, buf))
+        dist.barrier(group=group)
+        # NCCL ops are issued under the library's stream so that sweep -> all-gather -> raymarch stay stream-ordered
+        self.stream = torch.cuda.ExternalStream(self.lib.tbrm_stream(self.res.handle), device=dev)
+        self._frame = None
+
+    # ---- inputs -------------------------------------------------------------------------------------------
+    def SetDataVolumeSlab(self, slab) -> None:
+        """Upload this rank's slab of the data volume ([z0:z1] of the (Z,Y,X) array; numpy, or a torch tensor on any device)
+        and replicate the volume on every GPU with an all-gather over NVLink."""
+        import torch
+        import torch.distributed as dist
+
+        t = torch.as_tensor(slab) if not isinstance(slab, torch.Tensor) else slab
+        if tuple(t.shape) != (self.z1 - self.z0, self.dims[1], self.dims[0]) or t.dtype != torch.uint8:
+            raise ValueError("slab must be uint8 with shape (z1 - z0, Y, X)")
+        with torch.cuda.stream(self.stream):
+            self.data[self.z0:self.z1].copy_(t, non_blocking=True)
+            dist.all_gather_into_tensor(self.data.view(-1), self.data[self.z0:self.z1].reshape(-1), group=self.group)
+        # the replica / brick grid derived from the data volume are rebuilt lazily
+        _capi.check(self.lib.tbrm_bind_volume_device(self.res.handle, C.c_void_p(self.data.data_ptr())))
+
+    # ---- sweep (collective; same arguments on every rank) ---------------------------------------------------
+    def ClearLightVolume(self, value: float = 0.0) -> None:
+        from .raymarch_utils import URaymarchUtils
+
+        URaymarchUtils.ClearResourceLightVolumes(self.res, value)
+
+    def AddDirLight(self, light, added: bool, world, stats=None) -> bool:
+        from .raymarch_utils import URaymarchUtils
+
+        return URaymarchUtils.AddDirLightToSingleVolume(self.res, light, added, world, bGPUSync=True, stats=stats)
+
+    def GatherLightVolume(self) -> None:
+        """In-place all-gather of the slabs: afterwards every rank holds the whole light volume (the raymarch reads it)."""
+        import torch
+        import torch.distributed as dist
+
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(self.light.view(-1), self.light[self.z0:self.z1].reshape(-1), group=self.group)
+
+    # ---- frame ------------------------------------------------------------------------------------------
+    def local_rows(self, height: int) -> int:
+        return int(self.lib.tbrm_raymarch_interleaved_rows(height, self.BLOCK_ROWS, self.rank, self.world))
+
+    def Render(self, cam, world, step_count: float, gather: bool = True, count_steps: bool = False):
+        """Lit raymarch of this rank's interleaved row blocks; the frame is assembled on rank 0 (returned there as a
+        (H, W, 4) CUDA tensor, None elsewhere). Returns (frame, executed march steps of this rank or 0)."""
+        import torch
+
+        rows = self.local_rows(cam.Height)
+        if self._frame is None or self._frame.shape != (rows, cam.Width, 4):
+            self._frame = torch.empty((rows, cam.Width, 4), dtype=torch.float32, device=self.light.device)
+        c, w = cam.to_c(), world.to_c()
+        steps = C.c_uint64(0)
+        _capi.check(self.lib.tbrm_raymarch_lit_interleaved(self.res.handle, C.byref(c), C.byref(w), float(step_count), self.BLOCK_ROWS,
+                                                           self.rank, self.world, C.c_void_p(self._frame.data_ptr()), 1,
+                                                           C.byref(steps) if count_steps else None))
+        frame = None
+        if gather:
+            with torch.cuda.stream(self.stream):
+                frame = gather_interleaved_rows(self._frame, cam.Height, self.BLOCK_ROWS, dst=0, group=self.group)
+        return frame, int(steps.value)
+
+    # ---- queue control --------------------------------------------------------------------------------------
+    def Flush(self) -> None:
+        _capi.check(self.lib.tbrm_flush(self.res.handle))
+
+    def Check(self) -> None:
+        """Raises if a slab exchange timed out since the last call (synchronises)."""
+        _capi.check(self.lib.tbrm_slab_check(self.res.handle))
+
+    def release(self) -> None:
+        self.res.release()

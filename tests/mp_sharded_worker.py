@@ -1,0 +1,77 @@
+"""Worker of tests/test_gpu_multi.py (one process per GPU, launched by torchrun): ONE volume Z-slab sharded over the ranks.
+Checks, bit for bit, against the unsharded sweep / raymarch that rank 0 also runs on its own GPU:
+the gathered light volume after a full reset with all four lights and after removing one, and the gathered frame."""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from tbraymarcherplugin_b200 import FMT_G8, _capi, sharding, synth
+from tbraymarcherplugin_b200.raymarch_utils import FSweepStats, FWindowingParameters, URaymarchUtils
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    rank, world_size, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _capi.load()
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    world = synth.identity_world()
+    cam = synth.benchmark_camera(320, 200)
+
+    d_vol = torch.empty((n, n, n), dtype=torch.uint8, device="cuda")
+    _capi.check(lib.tbrm_synth_volume_u8(local, _capi.SYNTH_PERLIN_CT, (C.c_int32 * 3)(n, n, n), synth.PERLIN_SEED, C.c_void_p(d_vol.data_ptr()), 1))
+
+    vol = sharding.FShardedRaymarchVolume((n, n, n), local)
+    URaymarchUtils.ColorCurveToTexture(vol.res, synth.soft_ct_curve())
+    URaymarchUtils.SetWindowingParameters(vol.res, win)
+    vol.SetDataVolumeSlab(d_vol[vol.z0:vol.z1])
+    vol.Flush()
+    assert torch.equal(vol.data, d_vol), "all-gather of the data slabs"
+
+    for rep in range(2):  # twice: the second round reuses both arena regions
+        vol.ClearLightVolume(0.0)
+        for l in synth.LIGHTS:
+            st = FSweepStats()
+            assert vol.AddDirLight(l, True, world, stats=st)
+            assert set(st.impl) == {3}, st.impl
+    vol.AddDirLight(synth.LIGHTS[1], False, world)
+    vol.GatherLightVolume()
+    frame, _ = vol.Render(cam, world, 200.0)
+    vol.Check()
+
+    if rank == 0:
+        ref = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True, device=local)
+        URaymarchUtils.SetDataVolumeDevice(ref, d_vol.data_ptr())
+        URaymarchUtils.ColorCurveToTexture(ref, synth.soft_ct_curve())
+        URaymarchUtils.SetWindowingParameters(ref, win)
+        URaymarchUtils.ClearResourceLightVolumes(ref, 0.0)
+        for l in synth.LIGHTS:
+            URaymarchUtils.AddDirLightToSingleVolume(ref, l, True, world, bGPUSync=True)
+        URaymarchUtils.AddDirLightToSingleVolume(ref, synth.LIGHTS[1], False, world, bGPUSync=True)
+        L_ref = URaymarchUtils.ReadLightVolume(ref)
+        L = vol.light.cpu().numpy()
+        d = np.abs(L - L_ref)
+        assert np.array_equal(L, L_ref), f"light volume: {np.count_nonzero(d)} voxels differ, max {d.max():.3e}, first {np.argwhere(d > 0)[:3].tolist()}"
+        img_ref, _ = URaymarchUtils.PerformWindowedLitRaymarch(ref, cam, world, 200.0)
+        img = frame.cpu().numpy()
+        assert img_ref[..., 3].max() > 0.5
+        assert np.array_equal(img, img_ref), f"frame: max diff {np.abs(img - img_ref).max():.3e}"
+    else:
+        assert frame is None
+    dist.barrier()
+    vol.release()
+    dist.destroy_process_group()
+    print(f"sharded ok rank {rank}/{world_size} n={n}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,20 @@ WORKER = textwrap.dedent("""
     gathered = [None, None]
     dist.all_gather_object(gathered, mine)
     assert np.array_equal(sharding.assemble_rows(H, 2, gathered, 8), frame)
+    # 2b. the collective used by FShardedRaymarchVolume.Render: ranks hold their compacted interleaved rows (unequal shares),
+    #     rank 0 receives the whole frame
+    for H2 in (45, 64, 7):
+        f2 = torch.arange(H2 * W * 4, dtype=torch.float32).reshape(H2, W, 4)
+        local = f2[torch.as_tensor(sharding.rows_of_rank(H2, rank, 2, 8))]
+        got = sharding.gather_interleaved_rows(local, H2, 8, dst=0)
+        assert (got is None) == (rank != 0)
+        if rank == 0:
+            assert torch.equal(got, f2)
+    # 2c. the Z-slab partition rule (library code, needs no GPU): slabs tile [0, Z) and are multiples of 8 slices
+    for Z, n in ((512, 2), (512, 8), (1024, 8), (96, 3), (64, 4)):
+        slabs = [sharding.slab_of_rank(Z, r, n) for r in range(n)]
+        assert slabs[0][0] == 0 and slabs[-1][1] == Z and all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+        assert all((b - a) % 8 == 0 and b > a for a, b in slabs)
     # 3. volumes are partitioned, whole-job throughput = sum of per-rank units / max time
     vols = sharding.volumes_of_rank(5, rank, 2)
     n = torch.tensor([len(vols)], dtype=torch.float64)
