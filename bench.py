@@ -87,12 +87,20 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_config(n_gpus: int) -> dict:
+def workload_config(n_gpus: int, slabs: bool = True) -> dict:
+    if n_gpus == 1:
+        shard = "1 volume, 1 GPU"
+    elif slabs:
+        shard = (f"ONE volume Z-slab sharded over {n_gpus} GPUs: data volume replicated (NCCL all-gather of the uploaded slabs), light sweep per "
+                 "slab with in-kernel NVLink peer-store halo exchange, NCCL all-gather of the light slabs, frame rendered in interleaved 8-row "
+                 "blocks and gathered on rank 0")
+    else:
+        shard = f"{n_gpus} independent volumes, one per GPU, no collective"
     return {
-        "workload": f"cfg2: {N_VOL}^3 CT-like Perlin R8 volume, R32F light volume, 2 dir lights full reset (fused sweep, bGPUSync) + lit raymarch "
+        "workload": f"{'cfg2' if N_VOL == 512 else 'cfg4'}: {N_VOL}^3 CT-like Perlin R8 volume, R32F light volume, {len(LIGHT_IDS)} dir lights full reset (fused sweep, bGPUSync) + lit raymarch "
                     f"{VIEW[0]}x{VIEW[1]} @ {int(STEPS)} steps, windowing C=.45 W=.5 low cut-off, TF soft_ct, jitter on",
         "volume": [N_VOL] * 3, "view": list(VIEW), "steps": STEPS, "lights": len(LIGHT_IDS),
-        "sharding": "1 volume" if n_gpus == 1 else f"{n_gpus} independent volumes, one per GPU, no collective",
+        "sharding": shard,
         "cache": "inputs larger than L2 (128 MiB data + 512 MiB light volume vs 126 MB L2): no flush needed between steps",
     }
 
@@ -119,7 +127,7 @@ def oracle_sample(data, data_small, light_after_reset, threads: int):
     t0 = time.perf_counter()
     passes = small.add_dir_light(synth.LIGHTS[3], True, world)  # axis-aligned light: exactly one axis pass over all voxels
     t_pass = (time.perf_counter() - t0) / max(passes, 1) * (N_VOL / SWEEP_SAMPLE_N) ** 3
-    total_passes = 4  # L1 and L2 take two axis passes each
+    total_passes = 2 * len(LIGHT_IDS)  # L1, L2 (and L3) take two axis passes each
     vol = oracle.OracleVolume(data, tf, win)
     if light_after_reset is not None:
         vol.light = light_after_reset
@@ -139,8 +147,10 @@ def oracle_sample(data, data_small, light_after_reset, threads: int):
     return est_seconds, est_steps, detail
 
 
-SAMPLE_TEXT = ("per step: 1 sweep axis pass over a 256^3 rendition of the volume (x8 voxels, x4 passes) + lit raymarch of 20 evenly spaced "
-               "rows of the 512^3/1080p frame (x54), extrapolated linearly to the whole step")
+def sample_text() -> str:
+    return (f"per step: 1 sweep axis pass over a {SWEEP_SAMPLE_N}^3 rendition of the volume (x{(N_VOL // SWEEP_SAMPLE_N) ** 3} voxels, "
+            f"x{2 * len(LIGHT_IDS)} passes) + lit raymarch of {len(SAMPLE_ROWS)} evenly spaced rows of the {N_VOL}^3/{VIEW[1]}p frame "
+            f"(x{VIEW[1] // len(SAMPLE_ROWS)}), extrapolated linearly to the whole step")
 
 
 def run_reference(args) -> int:
@@ -165,7 +175,7 @@ def run_reference(args) -> int:
         "impl": "reference", "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": SAMPLE_TEXT},
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": sample_text()},
         "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference (UE 5.4 / HLSL) has no CPU path and cannot be built here; this is the CPU oracle port with all host threads",
     }
@@ -181,7 +191,7 @@ def run_ours(args) -> int:
     import torch
     import torch.distributed as dist
 
-    from tbraymarcherplugin_b200 import FMT_G8, _capi, synth
+    from tbraymarcherplugin_b200 import FMT_G8, _capi, sharding, synth
     from tbraymarcherplugin_b200.raymarch_utils import FSweepStats, FWindowingParameters, URaymarchUtils
 
     rank, world_size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,6 +203,7 @@ def run_ours(args) -> int:
     if world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    slabs = world_size > 1 and args.sharding == "slabs"  # ONE volume, Z-slab sharded (strong scaling); else one volume per rank
 
     n, (W, H) = N_VOL, VIEW
     win = FWindowingParameters(0.45, 0.5, True, False)
@@ -201,17 +212,29 @@ def run_ours(args) -> int:
     cam = synth.benchmark_camera(W, H)
 
     # inputs: generated on the device (untimed), plus a pinned host copy for the end-to-end leg
-    res = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True, device=local)
-    d_vol = torch.empty(n * n * n, dtype=torch.uint8, device="cuda")
-    seed = synth.PERLIN_SEED + rank  # every rank owns a different volume of the scene
+    d_vol = torch.empty((n, n, n), dtype=torch.uint8, device="cuda")
+    seed = synth.PERLIN_SEED + (0 if slabs else rank)  # independent volumes: every rank owns a different volume of the scene
     _capi.check(lib.tbrm_synth_volume_u8(local, _capi.SYNTH_PERLIN_CT, (C.c_int32 * 3)(n, n, n), seed & 0xFFFFFFFF, C.c_void_p(d_vol.data_ptr()), 1))
-    URaymarchUtils.SetDataVolumeDevice(res, d_vol.data_ptr())
+    if slabs:
+        vol = sharding.FShardedRaymarchVolume((n, n, n), local)
+        res = vol.res
+        z0, z1 = vol.z0, vol.z1
+        vol.SetDataVolumeSlab(d_vol[z0:z1])
+        my_rows = vol.local_rows(H)
+    else:
+        vol = None
+        res = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True, device=local)
+        URaymarchUtils.SetDataVolumeDevice(res, d_vol.data_ptr())
+        z0, z1 = 0, n
+        my_rows = H
     URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
     URaymarchUtils.SetWindowingParameters(res, win)
     d_img = torch.empty(H * W * 4, dtype=torch.float32, device="cuda")
-    h_vol = torch.empty(n * n * n, dtype=torch.uint8).pin_memory()
-    h_vol.copy_(d_vol)
-    h_img = torch.empty(H * W * 4, dtype=torch.float32).pin_memory()
+    h_vol = torch.empty((z1 - z0, n, n), dtype=torch.uint8).pin_memory()  # this rank's share of the step's input
+    h_vol.copy_(d_vol[z0:z1])
+    h_img = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    if slabs:
+        del d_vol  # the sharded volume holds the replicated copy
     torch.cuda.synchronize()
 
     def timer_begin():
@@ -225,16 +248,24 @@ def run_ours(args) -> int:
     sweep_stats = []
 
     def sweep():
-        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)  # a sharded volume clears the slab it owns
         sweep_stats.clear()
         for l in lights:
             st = FSweepStats()
             assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
             sweep_stats.append(st)
 
-    def raymarch(count=True) -> int:
+    def gather_light():
+        if slabs:
+            vol.GatherLightVolume()  # NCCL all-gather of the light slabs, in place, ordered on the library's stream
+
+    def raymarch(count=True, gather=True):
+        """Returns (executed steps of this rank, frame tensor on rank 0 when sharded)."""
+        if slabs:
+            frame, steps = vol.Render(cam, world, STEPS, gather=gather, count_steps=count)
+            return steps, frame
         _, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, STEPS, device_out_ptr=d_img.data_ptr(), count_steps=count)
-        return steps
+        return steps, None
 
     def barrier():
         torch.cuda.synchronize()
@@ -242,12 +273,24 @@ def run_ours(args) -> int:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allreduce(x, op):
+        if world_size == 1:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world_size > 1 else (None, None)
+
     # ---- warm-up (also builds the lazily created replica / brick grid / scratch) ----
     ray_steps = 0
     for _ in range(max(args.warmup, 3)):
         sweep()
-        ray_steps = raymarch()
+        gather_light()
+        ray_steps, _ = raymarch()
     URaymarchUtils.FlushRenderingCommands(res)
+    if slabs:
+        vol.Check()
 
     # ---- timed region: K steps, device time on the library's stream, max over ranks ----
     clocks = ClockSampler(local)
@@ -257,44 +300,38 @@ def run_ours(args) -> int:
     timer_begin()
     for _ in range(args.steps):
         sweep()
+        gather_light()
         raymarch(count=False)  # the step counter read-back would synchronise; steps are identical every frame
     total_ms = timer_end()
     launches = lib.tbrm_kernel_launch_count() - launches0
     barrier()
     clock_info = clocks.stop()
-    if world_size > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        s = torch.tensor([ray_steps], device="cuda", dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        all_steps = float(s.item())
-        l = torch.tensor([launches], device="cuda", dtype=torch.float64)
-        dist.all_reduce(l, op=dist.ReduceOp.SUM)
-        launches = int(l.item())
-    else:
-        all_steps = float(ray_steps)
+    total_ms = allreduce(total_ms, MAX)
+    all_steps = allreduce(ray_steps, SUM)  # slabs: the ranks' shares of ONE frame; volumes: one frame per rank
+    launches = int(allreduce(launches, SUM))
     ms_per_step = total_ms / args.steps
     value = all_steps / (ms_per_step * 1e-3) / 1e6
 
-    # ---- per-stage timings (same stream, CUDA events), for the roofline objects ----
+    # ---- per-stage timings (same stream, CUDA events; max over ranks), for the roofline objects ----
     reps = max(3, min(args.steps, 10))
-    timer_begin()
-    for _ in range(reps):
-        sweep()
-    sweep_ms = timer_end() / reps
-    timer_begin()
-    for _ in range(reps):
-        raymarch(count=False)
-    ray_ms = timer_end() / reps
-    # one axis pass of the fused sweep on its own (L4 = a single +Z pass), the sweep's dominant kernel
+
+    def stage(fn):
+        barrier()
+        timer_begin()
+        for _ in range(reps):
+            fn()
+        return allreduce(timer_end() / reps, MAX)
+
+    sweep_ms = stage(sweep)
+    gather_ms = stage(gather_light) if slabs else 0.0
+    ray_ms = stage(lambda: raymarch(count=False, gather=False))
+    frame_gather_ms = (stage(lambda: raymarch(count=False, gather=True)) - ray_ms) if slabs else 0.0
+    # one axis pass of the fused sweep on its own (L4 = a single Z pass), the sweep's dominant kernel. On a sharded volume the
+    # slabs of a sweep along Z form a chain, so the roofline pass is timed with an X-major single pass... L4 is what N=1 times.
     URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
     st4 = FSweepStats()
     URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[3], True, world, bGPUSync=True, stats=st4)
-    timer_begin()
-    for _ in range(reps):
-        URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[3], True, world, bGPUSync=True)
-    pass_ms = timer_end() / reps
+    pass_ms = stage(lambda: URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[3], True, world, bGPUSync=True))
 
     hbm_peak, peak_src = peaks()
     vox = float(n) ** 3
@@ -302,44 +339,49 @@ def run_ours(args) -> int:
     sweep_bytes = vox * (4.0 + passes * 9.0)  # clear (4 B) + per axis pass 1 B data + 4 B read + 4 B write
     ray_bytes = vox * 1.0 + vox * 4.0 + 256 * 16 * 8 + W * H * 16.0  # compulsory bytes of the raymarch
     roofline = {  # dominant kernel by time: the raymarch (instruction-issue bound, not HBM bound — reported honestly)
-        "kernel": "raymarch_fast_kernel", "bound": "hbm", "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": ray_bytes / (ray_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "kernel": "raymarch_fast_kernel", "bound": "hbm", "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9, "peak": hbm_peak * world_size, "unit": "GB/s",
+        "frac": ray_bytes / (ray_ms * 1e-3) / 1e9 / (hbm_peak * world_size), "traffic": None, "peak_source": peak_src,
         "note": "compulsory bytes / kernel time; ~200 instr per non-empty sample make this kernel issue-bound (DESIGN.md §6)",
     }
     roofline_sweep = {
-        "kernel": "sweep_tma_kernel (one axis pass)", "bound": "hbm", "achieved": vox * 9.0 / (pass_ms * 1e-3) / 1e9, "peak": hbm_peak,
-        "unit": "GB/s", "frac": vox * 9.0 / (pass_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
-        "impl": list(st4.impl), "ms": pass_ms,
+        "kernel": "sweep_tma_kernel (one axis pass along Z; on a sharded volume its slabs run as a chain)", "bound": "hbm",
+        "achieved": vox * 9.0 / (pass_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": vox * 9.0 / (pass_ms * 1e-3) / 1e9 / hbm_peak,
+        "traffic": None, "peak_source": peak_src, "impl": list(st4.impl), "ms": pass_ms,
     }
     ncu = ROOT / "profiles" / "traffic.json"
-    if ncu.exists():  # dram bytes per launch from the committed `ncu --set full` captures
+    if ncu.exists() and world_size == 1:  # dram bytes per launch from the committed `ncu --set full` captures (N_VOL = 512, one GPU)
         t = json.loads(ncu.read_text())
         roofline["traffic"] = t.get("raymarch_fast_kernel")
         roofline_sweep["traffic"] = t.get("sweep_tma_kernel")
 
     # ---- end to end: the reference-facing API with HOST buffers, copies inside the timed region ----
-    h_np = h_vol.numpy().reshape(n, n, n)
-    img_np = h_img.numpy().reshape(H, W, 4)
-
     def e2e_step():
-        URaymarchUtils.SetDataVolume(res, h_np)  # H2D of the step's input (pinned)
+        if slabs:
+            vol.SetDataVolumeSlab(h_vol)  # H2D of this rank's slab (pinned) + all-gather over NVLink
+        else:
+            URaymarchUtils.SetDataVolume(res, h_vol.numpy())  # H2D of the step's input (pinned)
         sweep()
-        URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, STEPS, out=img_np, count_steps=False)  # D2H of the frame (pinned)
+        gather_light()
+        if slabs:
+            _, frame = raymarch(count=False)
+            if rank == 0:
+                with torch.cuda.stream(vol.stream):
+                    h_img.copy_(frame, non_blocking=True)  # D2H of the assembled frame (pinned)
+            vol.Flush()
+        else:
+            URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, STEPS, out=h_img.numpy(), count_steps=False)  # D2H of the frame (pinned)
 
-    URaymarchUtils.SetDataVolume(res, h_np)  # switch the resource set to an owned device copy before timing
+    e2e_step()  # also switches an unsharded resource set to an owned device copy before timing
     e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    if world_size > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e = {"value": all_steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mray-steps/s", "h2d_bytes_per_step": int(h_vol.numel()) * world_size,
-           "d2h_bytes_per_step": int(h_img.numel()) * 4 * world_size, "ms_per_step": e2e_ms}
+    e2e_ms = allreduce(1e3 * (time.perf_counter() - t0) / args.steps, MAX)
+    frames = 1 if slabs else world_size
+    e2e = {"value": all_steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mray-steps/s", "h2d_bytes_per_step": int(n) ** 3 * frames,
+           "d2h_bytes_per_step": H * W * 16 * frames, "ms_per_step": e2e_ms}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample ----
     cpu_baseline = None
@@ -350,26 +392,34 @@ def run_ours(args) -> int:
         sys.path.insert(0, str(ROOT / "tests"))
         import oracle
 
-        est_s, est_steps, detail = oracle_sample(h_np, oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3), light, threads)
-        cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": SAMPLE_TEXT,
+        est_s, est_steps, detail = oracle_sample(h_vol.numpy(), oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3), light, threads)
+        cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": sample_text(),
                         "est_ms_per_step": est_s * 1e3, **detail}
 
+    if slabs:
+        vol.Check()
     if rank == 0:
+        frame_steps = all_steps if slabs else ray_steps
         line = {
             "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world_size), "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world_size, slabs), "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_sweep": roofline_sweep, "cpu_baseline": cpu_baseline,
             "stages": {
-                "ray_steps_per_frame": ray_steps,
-                "raymarch": {"ms": ray_ms, "Mray_steps_per_s": ray_steps / (ray_ms * 1e-3) / 1e6},
-                "sweep": {"ms": sweep_ms, "axis_passes": passes, "Mvoxels_per_s": vox * passes / (sweep_ms * 1e-3) / 1e6,
-                          "GB_per_s": sweep_bytes / (sweep_ms * 1e-3) / 1e9, "frac_of_hbm_peak": sweep_bytes / (sweep_ms * 1e-3) / 1e9 / hbm_peak,
+                "ray_steps_per_frame": frame_steps,
+                "raymarch": {"ms": ray_ms, "Mray_steps_per_s": all_steps / (ray_ms * 1e-3) / 1e6},
+                "sweep": {"ms": sweep_ms, "axis_passes": passes, "Mvoxels_per_s": vox * passes * frames / (sweep_ms * 1e-3) / 1e6,
+                          "GB_per_s": sweep_bytes * frames / (sweep_ms * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": sweep_bytes * frames / (sweep_ms * 1e-3) / 1e9 / (hbm_peak * world_size),
                           "impl": [list(s.impl) for s in sweep_stats]},
+                "light_all_gather_ms": gather_ms, "frame_gather_ms": frame_gather_ms,
             },
         }
         print(json.dumps(line), flush=True)
     if world_size > 1:
+        dist.barrier()
+        if slabs:
+            vol.release()
         dist.destroy_process_group()
     return 0
 
@@ -381,7 +431,15 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="slabs", choices=["slabs", "volumes"],
+                    help="N > 1: 'slabs' = ONE volume Z-slab sharded over the GPUs (strong scaling, default); 'volumes' = one volume per GPU (weak)")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
+                    help="cfg2 = 512^3 / 1080p / 512 steps / 2 lights (BASELINE.json configs[1], default); cfg4 = 1024^3 / 2160p / 768 steps / 3 lights")
     args = ap.parse_args()
+    if args.workload == "cfg4":
+        global N_VOL, VIEW, STEPS, LIGHT_IDS, SAMPLE_ROWS
+        N_VOL, VIEW, STEPS, LIGHT_IDS = 1024, (3840, 2160), 768.0, (0, 1, 2)
+        SAMPLE_ROWS = list(range(54, 2160, 108))
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 2
         args.warmup = args.warmup if args.warmup is not None else 1

@@ -273,6 +273,9 @@ tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, con
 /* ---- queue control ------------------------------------------------------------------------------------ */
 tbrm_status tbrm_flush(tbrm_resources* res); /* FlushRenderingCommands(): wait for the resource set's stream */
 void* tbrm_stream(tbrm_resources* res);      /* the cudaStream_t ops are enqueued on */
+/* Enqueue on a caller-owned cudaStream_t from now on (the engine owns the command list): waits for the work already
+ * enqueued, the previous stream is destroyed if the library created it. The stream must outlive res. */
+tbrm_status tbrm_set_stream(tbrm_resources* res, void* cuda_stream);
 /* Device time in ms between two points of the resource set's stream: call begin, enqueue ops, call end
  * (end synchronises). Used by bench.py so kernels launched on this stream are timed on this stream. */
 tbrm_status tbrm_timer_begin(tbrm_resources* res);

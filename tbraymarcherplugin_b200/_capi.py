@@ -165,6 +165,7 @@ PROTOTYPES = {
     "tbrm_mandelbulb_march": (_I, [_I, C.POINTER(Mandelbulb), C.POINTER(Camera), C.POINTER(World), _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
     "tbrm_flush": (_I, [_P]),
     "tbrm_stream": (_P, [_P]),
+    "tbrm_set_stream": (_I, [_P, _P]),
     "tbrm_timer_begin": (_I, [_P]),
     "tbrm_timer_end": (_I, [_P, C.POINTER(C.c_float)]),
     "tbrm_synth_volume_u8": (_I, [_I, _I, C.POINTER(C.c_int32), C.c_uint32, _P, _I]),

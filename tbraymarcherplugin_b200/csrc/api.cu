@@ -151,13 +151,14 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     if (r->data_yzx) cudaFree(r->data_yzx);
     if (r->tables) cudaFree(r->tables);
     if (r->bricks) cudaFree(r->bricks);
+
     if (r->flags) cudaFree(r->flags);
     for (auto& axis : r->rw)
         for (void* b : axis)
             if (b) cudaFree(b);
     if (r->ev_begin) cudaEventDestroy(r->ev_begin);
     if (r->ev_end) cudaEventDestroy(r->ev_end);
-    if (r->stream) cudaStreamDestroy(r->stream);
+    if (r->stream && r->stream_owned) cudaStreamDestroy(r->stream);
     delete r;
     return TBRM_OK;
 }
@@ -681,6 +682,16 @@ tbrm_status tbrm_flush(tbrm_resources* r) {
 }
 
 void* tbrm_stream(tbrm_resources* r) { return r ? (void*) r->stream : nullptr; }
+
+tbrm_status tbrm_set_stream(tbrm_resources* r, void* cuda_stream) {
+    TBRM_REQUIRE(r, "tbrm_set_stream: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->stream_owned && r->stream) cudaStreamDestroy(r->stream);
+    r->stream = (cudaStream_t) cuda_stream;
+    r->stream_owned = false;
+    return TBRM_OK;
+}
 
 tbrm_status tbrm_timer_begin(tbrm_resources* r) {
     TBRM_REQUIRE(r, "tbrm_timer_begin: null argument");

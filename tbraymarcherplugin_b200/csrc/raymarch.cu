@@ -454,7 +454,7 @@ static int low_cut_byte(const Windowing& w) {
     return lo;
 }
 
-static cudaError_t ensure_bricks(tbrm_resources& r) {
+cudaError_t ensure_bricks(tbrm_resources& r) {
     if (r.bricks_valid) return cudaSuccess;
     const int BX = (r.ddims[0] + kBrick - 1) / kBrick, BY = (r.ddims[1] + kBrick - 1) / kBrick, BZ = (r.ddims[2] + kBrick - 1) / kBrick;
     cudaError_t e;

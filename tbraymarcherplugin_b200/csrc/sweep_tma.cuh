@@ -72,7 +72,6 @@ struct TmaParams {
     int stage_bytes, light_bytes, data_bytes;
     unsigned int epoch;     // distinguishes the ring tags of successive passes
     unsigned int cut_lo_mode, cut_lo_add;  // exact empty-space skip on tap bytes (see window_cut_byte); mode 0 = off
-    const int* tile_order;  // optional blockIdx -> tile permutation (load balance), else nullptr
     int exp_flags;          // experiment switches (tbrm_options.reserved[0])
 };
 
@@ -234,7 +233,7 @@ static bool clip_is_inactive(const SweepUniforms& u, const HostTabs& T) {
 // cut-off, WindowedSampling.usf:14-29). A trilinear value lies between its smallest and largest tap (each lerp
 // fma(t, b-a, a) with 0 <= t < 1 stays inside [a,b]) and the window position is monotone in the value, so taps that
 // are all <= T imply a rejected sample. mode 0: no skip; 1: T < 128; 2: T >= 128; `add` is the SWAR addend.
-static void window_cut_byte(const Windowing& w, bool allow, unsigned int& mode, unsigned int& add) {
+static void window_cut_byte(const Windowing& w, bool allow, unsigned int& mode, unsigned int& add, int* cut = nullptr) {
     int lo = -1;
     bool ok = allow && w.low > 0.0f;
     for (int b = 0; b < 256 && ok; ++b) {
@@ -246,6 +245,7 @@ static void window_cut_byte(const Windowing& w, bool allow, unsigned int& mode, 
         }
     }
     mode = 0, add = 0;
+    if (cut) *cut = (ok && lo >= 0) ? lo : -1;
     if (!ok || lo < 0) return;
     if (lo < 128)
         mode = 1, add = (unsigned) (127 - lo) * 0x010101u;
@@ -511,13 +511,14 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     P.epoch = ++r.pass_seq;
     P.exp_flags = r.options.reserved[0];
     P.cut_lo_mode = 0, P.cut_lo_add = 0;
-    if (!(P.exp_flags & 1)) window_cut_byte(u.win, T.weights_lt_one, P.cut_lo_mode, P.cut_lo_add);  // reserved[0] bit 0 disables the skip
-    P.tile_order = nullptr;
-    if (r.flags_count < (size_t) ntiles * kFlagStride) {
+    int cut = -1;
+    if (!(P.exp_flags & 1)) window_cut_byte(u.win, T.weights_lt_one, P.cut_lo_mode, P.cut_lo_add, &cut);  // reserved[0] bit 0 disables the skip
+    const size_t flag_words = (size_t) ntiles * kFlagStride;  // one progress word (its own 32-byte sector) per tile
+    if (r.flags_count < flag_words) {
         if (r.flags) cudaStreamSynchronize(r.stream), cudaFree(r.flags);
         r.flags = nullptr, r.flags_count = 0;
-        if ((e = cudaMalloc((void**) &r.flags, (size_t) ntiles * kFlagStride * sizeof(unsigned int))) != cudaSuccess) return e;
-        r.flags_count = (size_t) ntiles * kFlagStride;
+        if ((e = cudaMalloc((void**) &r.flags, flag_words * sizeof(unsigned int))) != cudaSuccess) return e;
+        r.flags_count = flag_words;
     }
     size_t need = 256;
     for (int a = 0; a < 3; ++a) need += (size_t) u.ldims[a] * 16 + 48;
@@ -542,7 +543,7 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     P.flags = r.flags;
     memset(&P.S, 0, sizeof(P.S));
     if (!use_slab) {
-        if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(r.flags, 0, flag_words * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
         if ((e = tma_launch(r, kern_plain, lm, dm, P, ntiles, smem)) != cudaSuccess) return e;
         count_launch();
         *launches += 1;

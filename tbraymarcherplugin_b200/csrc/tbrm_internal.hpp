@@ -16,6 +16,7 @@
 struct tbrm_resources {
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool stream_owned = true;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 
     // DataVolumeTextureRef
@@ -54,6 +55,7 @@ struct tbrm_resources {
     bool bricks_valid = false;
     void* tables = nullptr;
     size_t tables_bytes = 0;
+
     bool light_owned = true;
 
     // Z-slab sharding of this volume over several GPUs and the exchange arena of partial sweep launches
@@ -98,6 +100,7 @@ cudaError_t raymarch_cube_setup(tbrm_resources& r, const host::CameraUniforms& c
 cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, const float clip_center[3], const float clip_dir[3],
                          float step_count, int row_begin, int row_end, int row_block, int block_stride, float* d_out,
                          unsigned long long* d_steps);
+cudaError_t ensure_bricks(tbrm_resources& r);  // brick max-grid: 1 byte per 8^3 brick (max over [8b, 8b+8] per axis)
 int raymarch_local_rows(int row_begin, int row_end, int row_block, int block_stride);
 
 // mandelbulb.cu

@@ -152,8 +152,10 @@ class FShardedRaymarchVolume:
                 buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
                 _capi.check(self.lib.tbrm_slab_open_peer(self.res.handle, side, buf))
         dist.barrier(group=group)
-        # NCCL ops are issued under the library's stream so that sweep -> all-gather -> raymarch stay stream-ordered
-        self.stream = torch.cuda.ExternalStream(self.lib.tbrm_stream(self.res.handle), device=dev)
+        # the library enqueues on a torch-owned stream, and the NCCL ops are issued under the same stream, so that
+        # sweep -> all-gather -> raymarch -> gather stay stream-ordered without host synchronisation
+        self.stream = torch.cuda.Stream(device=dev)
+        _capi.check(self.lib.tbrm_set_stream(self.res.handle, C.c_void_p(self.stream.cuda_stream)))
         self._frame = None
 
     # ---- inputs -------------------------------------------------------------------------------------------
@@ -223,4 +225,5 @@ class FShardedRaymarchVolume:
         _capi.check(self.lib.tbrm_slab_check(self.res.handle))
 
     def release(self) -> None:
+        self.Flush()
         self.res.release()
