@@ -145,6 +145,7 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     for (int i = 0; i < 2; ++i)
         if (r->peer_arena[i] && r->peer_ipc[i]) cudaIpcCloseMemHandle(r->peer_arena[i]);
     if (r->arena) cudaFree(r->arena);
+    if (r->change_scratch) cudaFree(r->change_scratch);
     if (r->tf) cudaFree(r->tf);
     if (r->counters) cudaFree(r->counters);
     if (r->ring) cudaFree(r->ring);

@@ -57,9 +57,16 @@ struct SlabParams {
     unsigned long long timeout_ns;
 };
 
+// what a launch does with the light it propagates
+enum { kModeAdd = 0,      // LightVolume += light * sign where |light| > 1e-3 (AddDirLight)
+       kModeStore = 1,    // scratch volume = light (the removed light of a ChangeDirLight; light_map is the scratch volume's map)
+       kModeCombine = 2 };// LightVolume += light - scratch where |light - scratch| > 1e-3 (the added light of a ChangeDirLight)
+
 struct TmaParams {
     SweepUniforms U;
     SlabParams S;
+    int mode;
+    int data_off;           // offset of the data brick inside a stage (after the light brick and, when combining, the scratch brick)
     LightTabs A;      // the (added) light
     int ntx, nty;
     float* ring;
@@ -268,11 +275,11 @@ static const void* tma_kernel(int axis, bool clip, bool slab) {
 #undef TBRM_K
 }
 
-static cudaError_t tma_launch(tbrm_resources& r, const void* kern, const CUtensorMap& lm, const CUtensorMap& dm, const TmaParams& P, int ntiles,
-                              size_t smem) {
+static cudaError_t tma_launch(tbrm_resources& r, const void* kern, int threads, const CUtensorMap& lm, const CUtensorMap& dm, const CUtensorMap& sm,
+                              const TmaParams& P, int ntiles, size_t smem) {
     const float4* tf = r.tf;
-    void* args[] = {(void*) &lm, (void*) &dm, (void*) &P, (void*) &tf};
-    return cudaLaunchCooperativeKernel(kern, dim3(ntiles), dim3(kTmaThreads), args, smem, r.stream);
+    void* args[] = {(void*) &lm, (void*) &dm, (void*) &sm, (void*) &P, (void*) &tf};
+    return cudaLaunchCooperativeKernel(kern, dim3(ntiles), dim3(threads), args, smem, r.stream);
 }
 
 // ---- slab exchange arena: header (acks, error word) + 2 regions x (inbox + hand-off plane) of LL cells ----------------
@@ -368,9 +375,42 @@ int slab_pass_order(const SweepUniforms& u) {
     return reach_hi > 0 ? -1 : 1;
 }
 
+static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u, int mode, int* launches, bool* handled);
+
+// One axis pass. ChangeDirLight (LightingShaders.cpp:168-326) runs as two launches that share the exchange machinery of the
+// Add sweep: the removed light's sweep leaves its propagated light in a scratch volume, the added light's sweep combines
+// LightVolume += added - removed under the reference's threshold on the difference — the same values, voxel by voxel, as
+// the fused shader.
 cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled) {
+    if (!change) return sweep_pass_tma_mode(r, u, kModeAdd, launches, handled);
     *handled = false;
-    if (change || r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res) return not_handled("change || r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res");
+    if (r.light_fmt != TBRM_FMT_R32F) return not_handled("ChangeDirLight on a G8 light volume");
+    cudaError_t e;
+    if (!r.change_scratch && (e = cudaMalloc(&r.change_scratch, r.light_voxels() * sizeof(float))) != cudaSuccess) return e;
+    SweepUniforms ur = u;
+    ur.a = u.r;  // the removed light drives the first launch
+    bool h1 = false, h2 = false;
+    const unsigned int seq0 = r.pass_seq;
+    if ((e = sweep_pass_tma_mode(r, ur, kModeStore, launches, &h1)) != cudaSuccess) return e;
+    if (!h1) return cudaSuccess;
+    if ((e = sweep_pass_tma_mode(r, u, kModeCombine, launches, &h2)) != cudaSuccess) return e;
+    if (!h2) {
+        // the first launch only wrote the scratch volume, so another implementation can still take the whole pass; a sharded
+        // volume has none (and its neighbours have consumed a sequence number): report it
+        if (r.slab.nranks > 1) {
+            set_last_error("ChangeDirLight: the added light's sweep is not supported by the TMA-staged sweep although the removed light's is");
+            return cudaErrorNotSupported;
+        }
+        (void) seq0;
+        return cudaSuccess;
+    }
+    *handled = true;
+    return cudaSuccess;
+}
+
+static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u, int mode, int* launches, bool* handled) {
+    *handled = false;
+    if (r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res) return not_handled("r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res");
     const int X = r.ddims[0], Y = r.ddims[1], Z = r.ddims[2];
     if (X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)) return not_handled("X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)");  // TMA global strides must be multiples of 16 bytes
     if (((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)) return not_handled("((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)");
@@ -417,8 +457,13 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     // tensor maps. Light: native (X,Y,Z) fp32, box = tile x SB along the sweep axis.
     int lbox[3], ldims[3] = {r.ldims[0], r.ldims[1], r.ldims[2]};
     lbox[pa] = kTW, lbox[qa] = kTH, lbox[sa] = kSB;
-    CUtensorMap lm, dm;
-    if (!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.light, ldims, lbox)) return not_handled("!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.light, ldims, lbox)");
+    CUtensorMap lm, dm, sm;
+    // the brick that is loaded, updated and stored: the light volume, or the scratch volume when the light is only stored
+    if (!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeStore ? r.change_scratch : r.light, ldims, lbox))
+        return not_handled("tensor map of the light volume");
+    if (!make_map3(&sm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeCombine ? r.change_scratch : r.light, ldims, lbox))
+        return not_handled("tensor map of the scratch volume");
+    P.mode = mode;
     // light SMEM strides: box is stored with native x fastest, then y, then z
     {
         const int str[3] = {1, lbox[0], lbox[0] * lbox[1]};
@@ -437,8 +482,9 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
         P.ds_q = str[qa], P.ds_s = str[sa];
     }
     P.light_bytes = kTW * kTH * kSB * 4;
+    P.data_off = mode == kModeCombine ? 2 * P.light_bytes : P.light_bytes;
     P.data_bytes = P.dext[0] * P.dext[1] * P.dext[2];
-    P.stage_bytes = (P.light_bytes + P.data_bytes + 16 + 127) / 128 * 128;
+    P.stage_bytes = (P.data_off + P.data_bytes + 16 + 127) / 128 * 128;
     const size_t smem = (size_t) kStages * P.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
 
     const bool clip = !clip_is_inactive(u, T);
@@ -455,6 +501,7 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     }
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
+    const int threads = kTmaThreads;
     const void* kern_plain = tma_kernel(u.axis, clip, false);
     const void* kern_slab = tma_kernel(u.axis, clip, true);
     for (const void* k : {kern_plain, kern_slab})
@@ -462,7 +509,7 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
             cudaGetLastError();
             return not_handled("shared memory per block");
         }
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_slab, kTmaThreads, smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_slab, threads, smem)) != cudaSuccess) return e;
     int cap_rows = (int) std::min<long long>((long long) sms * per_sm / P.ntx, 1 << 20);  // tile rows of one co-resident wave
     if (r.options.reserved[2] > 0) cap_rows = std::min(cap_rows, r.options.reserved[2]);      // test hook: force banding on small planes
     if (cap_rows < 1) return not_handled("cap_rows < 1");
@@ -544,7 +591,7 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
     memset(&P.S, 0, sizeof(P.S));
     if (!use_slab) {
         if ((e = cudaMemsetAsync(r.flags, 0, flag_words * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
-        if ((e = tma_launch(r, kern_plain, lm, dm, P, ntiles, smem)) != cudaSuccess) return e;
+        if ((e = tma_launch(r, kern_plain, threads, lm, dm, sm, P, ntiles, smem)) != cudaSuccess) return e;
         count_launch();
         *launches += 1;
         *handled = true;
@@ -613,7 +660,7 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
         S.error = err_word;
         S.timeout_ns = timeout_ns;
         if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
-        if ((e = tma_launch(r, kern_slab, lm, dm, P, S.tile_rows * P.ntx, smem)) != cudaSuccess) return e;
+        if ((e = tma_launch(r, kern_slab, threads, lm, dm, sm, P, S.tile_rows * P.ntx, smem)) != cudaSuccess) return e;
         count_launch();
         *launches += 1;
     }

@@ -79,8 +79,8 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 // plane of LL cells. The per-voxel arithmetic is untouched, so a sharded pass is bit-identical to an unsharded one.
 template <int AXIS, bool CLIP, bool SLAB>
 __global__ void __launch_bounds__(kTmaThreads, 4)
-    sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map, const TmaParams P,
-                     const float4* __restrict__ tf) {
+    sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
+                     const __grid_constant__ CUtensorMap scratch_map, const TmaParams P, const float4* __restrict__ tf) {
     constexpr int PA = (AXIS == 0) ? 1 : 0;  // native axis of p
     constexpr int QA = (AXIS == 2) ? 1 : 2;  // native axis of q
     constexpr int SA = AXIS;                 // native axis of s
@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                inP2 = (unsigned) (mp0.x + 2) < (unsigned) dN_p;
     const bool inQ0 = (unsigned) mq.x < (unsigned) dN_q, inQ1 = (unsigned) (mq.x + 1) < (unsigned) dN_q;
     const bool all_pq = inP0 && inP1 && inP2 && inQ0 && inQ1;
-    const bool inside_pq0 = v0 && mp0.y && mq.y, inside_pq1 = v1 && mp1.y && mq.y;
+    // AddDirLight samples only where GetUVW + UVWOffset is inside [0,1]^3 (AddDirLightShader.usf:110); ChangeDirLight has no such
+    // gate and relies on the border sampler (ChangeDirLightShader.usf:130,136)
+    const bool gate = U.gate_saturate != 0;
+    const bool inside_pq0 = v0 && (!gate || (mp0.y && mq.y)), inside_pq1 = v1 && (!gate || (mp1.y && mq.y));
     float Sp0 = 0.f, Sp1 = 0.f, Sq = 0.f;
     if (CLIP) {
         Sp0 = __ldg(&P.A.ax[PA].S[pxc]), Sp1 = __ldg(&P.A.ax[PA].S[px1c]), Sq = __ldg(&P.A.ax[QA].S[pyc]);
@@ -177,10 +180,12 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     // pass of a light close to its main axis) are described in SMEM and fetched in a plain loop.
     int halo_fp[kHaloPerThread], halo_ring[kHaloPerThread];
     __shared__ int s_over_fp[kHaloOverflow], s_over_ring[kHaloOverflow];
+    int n_halo;  // footprint cells outside the own tile
     {
         const int ox0 = max(fx0, x0), ox1 = min(fx0 + FW, x0 + kTW), oy0 = max(fy0, y0), oy1 = min(fy0 + FH, y0 + kTH);
         const int ow = max(0, ox1 - ox0), oh = (ow > 0) ? max(0, oy1 - oy0) : 0;
         const int top = (oh > 0 ? oy0 - fy0 : FH) * FW, mid = oh * (FW - ow);
+        n_halo = FW * FH - ow * oh;
         auto halo_cell = [&](int h, int& fp_idx, int& ring_idx) {
             int gx = -1, gy = -1;
             fp_idx = -1, ring_idx = 0;
@@ -207,13 +212,13 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         };
 #pragma unroll
         for (int i = 0; i < kHaloPerThread; ++i) halo_cell(tid + i * kTmaThreads, halo_fp[i], halo_ring[i]);
-        for (int h = tid + kHaloPerThread * kTmaThreads; h < FW * FH; h += kTmaThreads) {
+        for (int h = tid + kHaloPerThread * kTmaThreads; h < n_halo; h += kTmaThreads) {
             int f, g;
             halo_cell(h, f, g);
             s_over_fp[h - kHaloPerThread * kTmaThreads] = f, s_over_ring[h - kHaloPerThread * kTmaThreads] = g;
         }
     }
-    const int n_over = max(0, FW * FH - kHaloPerThread * kTmaThreads);
+    const int n_over = max(0, n_halo - kHaloPerThread * kTmaThreads);
     // SLAB: cells a neighbouring band reads go to its inbox as well (row slot in the RECEIVER's numbering)
     bool xlo0 = false, xlo1 = false, xhi0 = false, xhi1 = false;
     int xlo_idx = 0, xhi_idx = 0;
@@ -269,17 +274,18 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     auto issue_load = [&](int b) {
         const int st = (b - b_begin) % kStages;
         unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
-        mbar_expect_tx(&s_bar[st], (uint32_t) (P.light_bytes + P.data_bytes));
+        mbar_expect_tx(&s_bar[st], (uint32_t) (P.data_off + P.data_bytes));
         const int s0 = block_s0(b);
         int lc[3], dc[3];
         lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;  // light map is over native (x,y,z)
         tma_load_3d(sb, &light_map, lc[0], lc[1], lc[2], &s_bar[st]);
+        if (P.mode == kModeCombine) tma_load_3d(sb + P.light_bytes, &scratch_map, lc[0], lc[1], lc[2], &s_bar[st]);
         // data map: native dims for Z / Y sweeps, the (y,z,x) replica for X sweeps, i.e. (p,q,s)-ordered for X
         if (AXIS == 0) {
-            tma_load_3d(sb + P.light_bytes, &data_map, x0 + P.dmin[0], y0 + P.dmin[1], s0 + P.dmin[2], &s_bar[st]);
+            tma_load_3d(sb + P.data_off, &data_map, x0 + P.dmin[0], y0 + P.dmin[1], s0 + P.dmin[2], &s_bar[st]);
         } else {
             dc[PA] = x0 + P.dmin[0], dc[QA] = y0 + P.dmin[1], dc[SA] = s0 + P.dmin[2];
-            tma_load_3d(sb + P.light_bytes, &data_map, dc[0], dc[1], dc[2], &s_bar[st]);
+            tma_load_3d(sb + P.data_off, &data_map, dc[0], dc[1], dc[2], &s_bar[st]);
         }
     };
     if (tid == 0) issue_load(b_begin);
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         mbar_wait(&s_bar[st], (uint32_t) (((b - b_begin) / kStages) & 1));
         unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
         float* s_light = (float*) sb;
-        const unsigned char* s_data = sb + P.light_bytes;
+        const unsigned char* s_data = sb + P.data_off;
         const int s0 = block_s0(b);
 
 #pragma unroll 1
@@ -354,7 +360,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                         w0 = w;
                 }
             }
-            const bool g0 = w0 > 0.0f && inside_pq0 && ms.y, g1 = w1 > 0.0f && inside_pq1 && ms.y;
+            const bool gs = !gate || ms.y;
+            const bool g0 = w0 > 0.0f && inside_pq0 && gs, g1 = w1 > 0.0f && inside_pq1 && gs;
             float cs0 = 0.0f, cs1 = 0.0f;
             if (g0 || g1) {
                 // 4 rows (q, s) x 3 columns of taps; two aligned 32-bit loads + a funnel shift per row
@@ -494,8 +501,18 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                     }
                 }
                 float* lp = s_light + light_off + (loop - s0) * P.ls_s;
-                if (v0 && fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
-                if (v1 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
+                if (P.mode == kModeAdd) {  // AddDirLightShader.usf:121-126
+                    if (v0 && fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
+                    if (v1 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
+                } else if (P.mode == kModeStore) {  // the removed light of a ChangeDirLight: its light goes to the scratch volume
+                    if (v0) lp[0] = cur0;
+                    if (v1) lp[P.ls_p] = cur1;
+                } else {  // the added light of a ChangeDirLight: LightVolume += added - removed (ChangeDirLightShader.usf:146-153)
+                    const float* rp = lp + P.light_bytes / 4;
+                    const float r0c = rp[0], r1c = rp[P.ls_p];
+                    if (v0 && fabsf(cur0 - r0c) > 1e-3f) lp[0] = lp[0] + cur0 - r0c;
+                    if (v1 && fabsf(cur1 - r1c) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + cur1 - r1c;
+                }
             }
         }
         // ---- write the updated light brick back ----

@@ -57,6 +57,7 @@ struct tbrm_resources {
     size_t tables_bytes = 0;
 
     bool light_owned = true;
+    void* change_scratch = nullptr;  // TMA sweep: the removed light's propagated light of a ChangeDirLight (R32F, light volume dims)
 
     // Z-slab sharding of this volume over several GPUs and the exchange arena of partial sweep launches
     tbrm_slab slab = {0, 1, 0, 0};

@@ -185,6 +185,11 @@ class FShardedRaymarchVolume:
 
         return URaymarchUtils.AddDirLightToSingleVolume(self.res, light, added, world, bGPUSync=True, stats=stats)
 
+    def ChangeDirLight(self, old_light, new_light, world, stats=None) -> bool:
+        from .raymarch_utils import URaymarchUtils
+
+        return URaymarchUtils.ChangeDirLightInSingleVolume(self.res, old_light, new_light, world, bGPUSync=True, stats=stats)
+
     def GatherLightVolume(self) -> None:
         """In-place all-gather of the slabs: afterwards every rank holds the whole light volume (the raymarch reads it)."""
         import torch

@@ -44,6 +44,13 @@ def main():
             assert vol.AddDirLight(l, True, world, stats=st)
             assert set(st.impl) == {3}, st.impl
     vol.AddDirLight(synth.LIGHTS[1], False, world)
+    # incremental updates (cfg 3): every remaining light is rotated 5 degrees about +Z per update, as ONE ChangeDirLight each
+    current = [synth.LIGHTS[0], synth.LIGHTS[2], synth.LIGHTS[3]]
+    for step in (1, 2):
+        for i, base in enumerate((synth.LIGHTS[0], synth.LIGHTS[2], synth.LIGHTS[3])):
+            new = synth.rotate_about_z(base, 5.0 * step)
+            assert vol.ChangeDirLight(current[i], new, world)
+            current[i] = new
     vol.GatherLightVolume()
     frame, _ = vol.Render(cam, world, 200.0)
     vol.Check()
@@ -57,6 +64,12 @@ def main():
         for l in synth.LIGHTS:
             URaymarchUtils.AddDirLightToSingleVolume(ref, l, True, world, bGPUSync=True)
         URaymarchUtils.AddDirLightToSingleVolume(ref, synth.LIGHTS[1], False, world, bGPUSync=True)
+        cur = [synth.LIGHTS[0], synth.LIGHTS[2], synth.LIGHTS[3]]
+        for step in (1, 2):
+            for i, base in enumerate((synth.LIGHTS[0], synth.LIGHTS[2], synth.LIGHTS[3])):
+                new = synth.rotate_about_z(base, 5.0 * step)
+                URaymarchUtils.ChangeDirLightInSingleVolume(ref, cur[i], new, world, bGPUSync=True)
+                cur[i] = new
         L_ref = URaymarchUtils.ReadLightVolume(ref)
         L = vol.light.cpu().numpy()
         d = np.abs(L - L_ref)

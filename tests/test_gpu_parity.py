@@ -104,8 +104,9 @@ def test_g16_and_float_data_volumes(data_dtype, impl):
 
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("world_name", ["identity", "clipped"])
-def test_change_dir_light_matches_oracle(world_name, impl):
-    data = synth.perlin_ct_volume((40, 36, 32))
+@pytest.mark.parametrize("dims", [(40, 36, 32), (64, 64, 64)])  # the second one is covered by the TMA-staged sweep
+def test_change_dir_light_matches_oracle(dims, world_name, impl):
+    data = synth.perlin_ct_volume(dims)
     res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, sweep_impl=impl)
     world = WORLDS[world_name]()
     lights = list(synth.LIGHTS)
@@ -120,6 +121,8 @@ def test_change_dir_light_matches_oracle(world_name, impl):
             assert URaymarchUtils.ChangeDirLightInSingleVolume(res, l, new, world, bGPUSync=(impl >= 2), stats=st)
             code = ora.change_dir_light(l, new, world)
             assert st.fell_back == (code >= 100)
+            if impl == 2 and dims[0] % 16 == 0 and not st.fell_back:
+                assert 3 in st.impl, f"expected the TMA-staged sweep for ChangeDirLight, got {st.impl}"
             fused += not st.fell_back
             fallback += st.fell_back
             lights[i] = new
