@@ -204,6 +204,11 @@ def run_ours(args) -> int:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     slabs = world_size > 1 and args.sharding == "slabs"  # ONE volume, Z-slab sharded (strong scaling); else one volume per rank
+    t_start = time.perf_counter()
+
+    def trace(what):
+        if args.trace:
+            print(f"[bench rank {rank} +{time.perf_counter() - t_start:7.2f}s] {what}", file=sys.stderr, flush=True)
 
     n, (W, H) = N_VOL, VIEW
     win = FWindowingParameters(0.45, 0.5, True, False)
@@ -283,14 +288,22 @@ def run_ours(args) -> int:
     MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world_size > 1 else (None, None)
 
     # ---- warm-up (also builds the lazily created replica / brick grid / scratch) ----
+    trace("inputs ready")
     ray_steps = 0
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         sweep()
+        if args.trace:
+            URaymarchUtils.FlushRenderingCommands(res)
+            trace(f"warm-up {i}: sweep done")
         gather_light()
         ray_steps, _ = raymarch()
+        if slabs:
+            vol.Check()  # fail fast if a slab exchange timed out
+        trace(f"warm-up {i}: frame done")
     URaymarchUtils.FlushRenderingCommands(res)
     if slabs:
         vol.Check()
+    trace("warm-up checked")
 
     # ---- timed region: K steps, device time on the library's stream, max over ranks ----
     clocks = ClockSampler(local)
@@ -306,6 +319,7 @@ def run_ours(args) -> int:
     launches = lib.tbrm_kernel_launch_count() - launches0
     barrier()
     clock_info = clocks.stop()
+    trace("timed region done")
     total_ms = allreduce(total_ms, MAX)
     all_steps = allreduce(ray_steps, SUM)  # slabs: the ranks' shares of ONE frame; volumes: one frame per rank
     launches = int(allreduce(launches, SUM))
@@ -333,6 +347,7 @@ def run_ours(args) -> int:
     URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[3], True, world, bGPUSync=True, stats=st4)
     pass_ms = stage(lambda: URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[3], True, world, bGPUSync=True))
 
+    trace("stage timings done")
     hbm_peak, peak_src = peaks()
     vox = float(n) ** 3
     passes = sum(s.passes for s in sweep_stats)
@@ -379,6 +394,7 @@ def run_ours(args) -> int:
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = allreduce(1e3 * (time.perf_counter() - t0) / args.steps, MAX)
+    trace("end-to-end done")
     frames = 1 if slabs else world_size
     e2e = {"value": all_steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mray-steps/s", "h2d_bytes_per_step": int(n) ** 3 * frames,
            "d2h_bytes_per_step": H * W * 16 * frames, "ms_per_step": e2e_ms}
@@ -431,6 +447,7 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="print progress lines to stderr (debugging multi-GPU runs)")
     ap.add_argument("--sharding", default="slabs", choices=["slabs", "volumes"],
                     help="N > 1: 'slabs' = ONE volume Z-slab sharded over the GPUs (strong scaling, default); 'volumes' = one volume per GPU (weak)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],

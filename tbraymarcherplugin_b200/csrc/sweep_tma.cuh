@@ -282,7 +282,11 @@ static cudaError_t tma_launch(tbrm_resources& r, const void* kern, int threads, 
     return cudaLaunchCooperativeKernel(kern, dim3(ntiles), dim3(threads), args, smem, r.stream);
 }
 
-// ---- slab exchange arena: header (acks, error word) + 2 regions x (inbox + hand-off plane) of LL cells ----------------
+// ---- slab exchange arena: header (acks, error word) + 4 regions x (inbox + hand-off plane) of LL cells ----------------
+// A launch reads the region (pass parity, band parity): neighbouring bands of one pass use different regions, and a region
+// comes up again two passes later — which is what the ack protocol below protects (a neighbour that runs ahead writes
+// pass seq + 1 into the other pair of regions while this GPU still reads pass seq).
+static int arena_region(unsigned int seq, int band) { return (int) ((seq & 1u) << 1) | (band & 1); }
 constexpr size_t kArenaHeader = 256;
 constexpr int kInboxSlots = 8;  // rows of a neighbouring band a launch may read (reach_lo + reach_hi)
 static size_t arena_inbox_cells(const int32_t d[3]) {
@@ -290,7 +294,7 @@ static size_t arena_inbox_cells(const int32_t d[3]) {
     return std::max(a0, a2) * kInboxSlots;
 }
 static size_t arena_region_bytes(const int32_t d[3]) { return (arena_inbox_cells(d) + (size_t) d[0] * d[1]) * sizeof(unsigned long long); }
-size_t slab_arena_bytes(const int32_t ldims[3]) { return kArenaHeader + 2 * arena_region_bytes(ldims); }
+size_t slab_arena_bytes(const int32_t ldims[3]) { return kArenaHeader + 4 * arena_region_bytes(ldims); }
 static unsigned long long* arena_inbox(void* arena, const int32_t d[3], int region) {
     return (unsigned long long*) ((char*) arena + kArenaHeader + (size_t) region * arena_region_bytes(d));
 }
@@ -641,22 +645,22 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         S.q_lo = S.tile_row0 * kTH, S.q_hi = std::min(q_end, (S.tile_row0 + S.tile_rows) * kTH);
         S.k_begin = k_begin, S.k_end = k_end;
         S.reach_lo = reach_lo, S.reach_hi = reach_hi;
-        S.inbox = arena_inbox(r.arena, r.ldims, (seq + bi) & 1);
+        S.inbox = arena_inbox(r.arena, r.ldims, arena_region(seq, bi));
         S.out_lo = S.out_hi = nullptr;
         if (reach_hi > 0) {  // the band below reads our first rows
             if (bi > 0)
-                S.out_lo = arena_inbox(r.arena, r.ldims, (seq + bi - 1) & 1);
+                S.out_lo = arena_inbox(r.arena, r.ldims, arena_region(seq, bi - 1));
             else if (peer_lo)
-                S.out_lo = arena_inbox(peer_lo, r.ldims, (seq + nb_lo - 1) & 1);  // the neighbour's last band
+                S.out_lo = arena_inbox(peer_lo, r.ldims, arena_region(seq, nb_lo - 1));  // the neighbour's last band
         }
         if (reach_lo > 0) {  // the band above reads our last rows
             if (bi < nbands - 1)
-                S.out_hi = arena_inbox(r.arena, r.ldims, (seq + bi + 1) & 1);
+                S.out_hi = arena_inbox(r.arena, r.ldims, arena_region(seq, bi + 1));
             else if (peer_hi)
-                S.out_hi = arena_inbox(peer_hi, r.ldims, seq & 1);  // the neighbour's first band
+                S.out_hi = arena_inbox(peer_hi, r.ldims, arena_region(seq, 0));  // the neighbour's first band
         }
-        S.zin = (shard_s && k_begin > 0) ? arena_zplane(r.arena, r.ldims, seq & 1) : nullptr;
-        S.zout = (shard_s && k_end < ns) ? arena_zplane(peer_down, r.ldims, seq & 1) : nullptr;
+        S.zin = (shard_s && k_begin > 0) ? arena_zplane(r.arena, r.ldims, arena_region(seq, 0)) : nullptr;
+        S.zout = (shard_s && k_end < ns) ? arena_zplane(peer_down, r.ldims, arena_region(seq, 0)) : nullptr;
         S.error = err_word;
         S.timeout_ns = timeout_ns;
         if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;

@@ -62,7 +62,7 @@ struct tbrm_resources {
     // Z-slab sharding of this volume over several GPUs and the exchange arena of partial sweep launches
     tbrm_slab slab = {0, 1, 0, 0};
     unsigned int pass_seq = 0;     // TMA passes executed: the tag sequence of ring / arena cells
-    void* arena = nullptr;         // header + 2 regions x (inbox + hand-off plane) of LL cells, written by the neighbours
+    void* arena = nullptr;         // header + 4 regions x (inbox + hand-off plane) of LL cells, written by the neighbours
     size_t arena_bytes = 0;
     void* peer_arena[2] = {nullptr, nullptr};  // arenas of the slabs below / above (peer-mapped or same-process pointers)
     bool peer_ipc[2] = {false, false};
