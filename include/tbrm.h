@@ -157,6 +157,14 @@ tbrm_status tbrm_upload_volume(tbrm_resources* res, const void* src, int src_is_
 /* Use caller-owned device memory as the data volume without copying (must outlive res). */
 tbrm_status tbrm_bind_volume_device(tbrm_resources* res, const void* dptr);
 
+/* Streaming (double-buffered) upload for time-varying volumes: copies the NEXT data volume (host memory, pinned for a true
+ * overlap) into a back buffer on a dedicated upload stream while the render queue keeps working on the current one, the way
+ * the engine streams texture updates; tbrm_present_volume makes the render queue wait for that copy and swaps the buffers.
+ * Both return immediately. src_host must stay valid until the copy has run (tbrm_present_volume + tbrm_flush, or the next
+ * tbrm_upload_volume_async). */
+tbrm_status tbrm_upload_volume_async(tbrm_resources* res, const void* src_host);
+tbrm_status tbrm_present_volume(tbrm_resources* res);
+
 /* Transfer function: RGBA float32, `width` x `height` texels, rounded to fp16 like PF_FloatRGBA
  * (ColorCurveToTexture, RaymarchUtils.cpp:143-174). width must be 256. */
 tbrm_status tbrm_set_transfer_function(tbrm_resources* res, const float* rgba, int width, int height);
@@ -254,6 +262,13 @@ tbrm_status tbrm_raymarch_cube_setup(tbrm_resources* res, const tbrm_camera* cam
  * the final partial step) — the numerator of Mray-steps/s. */
 tbrm_status tbrm_raymarch_lit(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world, float step_count,
                               int row_begin, int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps);
+
+/* Whole-frame lit raymarch into a device frame owned by the resource set, followed by its copy to out_host (pinned) on a
+ * dedicated download stream: returns immediately, the next ops of the render queue overlap the copy. tbrm_download_wait blocks
+ * until every such copy has finished (two frames may be in flight). */
+tbrm_status tbrm_raymarch_lit_to_host_async(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world, float step_count,
+                                            float* out_host);
+tbrm_status tbrm_download_wait(tbrm_resources* res);
 
 /* The same for the image rows one GPU renders when a frame is dealt to `block_stride` GPUs in interleaved blocks of
  * `block_rows` rows (a multiple of 8): blocks first_block, first_block + block_stride, ... The rows land compacted in

@@ -126,6 +126,10 @@ PROTOTYPES = {
     "tbrm_set_options": (_I, [_P, C.POINTER(Options)]),
     "tbrm_upload_volume": (_I, [_P, _P, _I]),
     "tbrm_bind_volume_device": (_I, [_P, _P]),
+    "tbrm_upload_volume_async": (_I, [_P, _P]),
+    "tbrm_present_volume": (_I, [_P]),
+    "tbrm_raymarch_lit_to_host_async": (_I, [_P, C.POINTER(Camera), C.POINTER(World), C.c_float, _P]),
+    "tbrm_download_wait": (_I, [_P]),
     "tbrm_set_transfer_function": (_I, [_P, C.POINTER(C.c_float), _I, _I]),
     "tbrm_make_default_tf": (_I, [_P]),
     "tbrm_set_windowing": (_I, [_P, C.POINTER(Windowing)]),

@@ -140,7 +140,19 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     if (!r) return TBRM_OK;
     cudaSetDevice(r->device);
     if (r->stream) cudaStreamSynchronize(r->stream);
+    if (r->upload_stream) cudaStreamSynchronize(r->upload_stream);
+    if (r->download_stream) cudaStreamSynchronize(r->download_stream);
     if (r->data_owned && r->data) cudaFree(r->data);
+    if (r->data_back) cudaFree(r->data_back);
+    for (int i = 0; i < 2; ++i) {
+        if (r->frame_dev[i]) cudaFree(r->frame_dev[i]);
+        if (r->ev_frame_done[i]) cudaEventDestroy(r->ev_frame_done[i]);
+        if (r->ev_frame_copied[i]) cudaEventDestroy(r->ev_frame_copied[i]);
+    }
+    if (r->ev_uploaded) cudaEventDestroy(r->ev_uploaded);
+    if (r->ev_back_free) cudaEventDestroy(r->ev_back_free);
+    if (r->upload_stream) cudaStreamDestroy(r->upload_stream);
+    if (r->download_stream) cudaStreamDestroy(r->download_stream);
     if (r->light && r->light_owned) cudaFree(r->light);
     for (int i = 0; i < 2; ++i)
         if (r->peer_arena[i] && r->peer_ipc[i]) cudaIpcCloseMemHandle(r->peer_arena[i]);
@@ -180,6 +192,55 @@ tbrm_status tbrm_upload_volume(tbrm_resources* r, const void* src, int src_is_de
         r->data_owned = true;
     }
     TBRM_CUDA(cudaMemcpyAsync(r->data, src, bytes, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, r->stream));
+    r->data_ready = true;
+    r->data_yzx_valid = false;
+    r->bricks_valid = false;
+    return TBRM_OK;
+}
+
+// ---- streaming upload: back buffer + upload stream ------------------------------------------------------------
+static tbrm_status ensure_streaming(tbrm_resources* r) {
+    if (!r->upload_stream) TBRM_CUDA(cudaStreamCreateWithFlags(&r->upload_stream, cudaStreamNonBlocking));
+    if (!r->download_stream) TBRM_CUDA(cudaStreamCreateWithFlags(&r->download_stream, cudaStreamNonBlocking));
+    if (!r->ev_uploaded) TBRM_CUDA(cudaEventCreateWithFlags(&r->ev_uploaded, cudaEventDisableTiming));
+    if (!r->ev_back_free) TBRM_CUDA(cudaEventCreateWithFlags(&r->ev_back_free, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        if (!r->ev_frame_done[i]) TBRM_CUDA(cudaEventCreateWithFlags(&r->ev_frame_done[i], cudaEventDisableTiming));
+        if (!r->ev_frame_copied[i]) TBRM_CUDA(cudaEventCreateWithFlags(&r->ev_frame_copied[i], cudaEventDisableTiming));
+    }
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_upload_volume_async(tbrm_resources* r, const void* src_host) {
+    TBRM_REQUIRE(r && src_host, "tbrm_upload_volume_async: null argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    tbrm_status s = ensure_streaming(r);
+    if (s != TBRM_OK) return s;
+    const size_t bytes = r->data_voxels() * r->data_elem();
+    if (!r->data_back) {
+        TBRM_CUDA(cudaMalloc(&r->data_back, bytes));
+        TBRM_CUDA(cudaEventRecord(r->ev_back_free, r->stream));  // nothing reads a fresh buffer
+    }
+    // the back buffer was the front buffer until the last swap: wait until the render queue is done with it
+    TBRM_CUDA(cudaStreamWaitEvent(r->upload_stream, r->ev_back_free, 0));
+    TBRM_CUDA(cudaMemcpyAsync(r->data_back, src_host, bytes, cudaMemcpyHostToDevice, r->upload_stream));
+    TBRM_CUDA(cudaEventRecord(r->ev_uploaded, r->upload_stream));
+    r->upload_pending = true;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_present_volume(tbrm_resources* r) {
+    TBRM_REQUIRE(r, "tbrm_present_volume: null argument");
+    TBRM_REQUIRE(r->upload_pending && r->data_back, "tbrm_present_volume: no tbrm_upload_volume_async since the last present");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaStreamWaitEvent(r->stream, r->ev_uploaded, 0));  // the render queue continues once the copy has landed
+    void* old_front = r->data_owned ? r->data : nullptr;
+    r->data = r->data_back;
+    r->data_owned = true;
+    r->data_back = old_front;  // a caller-bound front buffer is not ours to reuse: the next upload allocates a back buffer
+    // everything enqueued so far may still read the old front buffer; later ops read the new one
+    TBRM_CUDA(cudaEventRecord(r->ev_back_free, r->stream));
+    r->upload_pending = false;
     r->data_ready = true;
     r->data_yzx_valid = false;
     r->bricks_valid = false;
@@ -627,6 +688,46 @@ tbrm_status tbrm_raymarch_lit_interleaved(tbrm_resources* r, const tbrm_camera* 
                  "tbrm_raymarch_lit_interleaved: block_rows must be a positive multiple of 8, 0 <= first_block < block_stride");
     const int row_begin = std::min(first_block * block_rows, cam->height);
     return raymarch_lit_impl(r, cam, world, step_count, row_begin, cam->height, block_rows, block_stride, out_rgba, out_is_device, out_steps);
+}
+
+tbrm_status tbrm_raymarch_lit_to_host_async(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count,
+                                            float* out_host) {
+    if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
+    TBRM_REQUIRE(world && out_host && camera_valid(cam), "tbrm_raymarch_lit_to_host_async: bad argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    tbrm_status s = ensure_streaming(r);
+    if (s != TBRM_OK) return s;
+    const size_t bytes = (size_t) cam->width * cam->height * 4 * sizeof(float);
+    if (r->frame_bytes < bytes) {
+        TBRM_CUDA(cudaStreamSynchronize(r->download_stream));
+        TBRM_CUDA(cudaStreamSynchronize(r->stream));
+        for (int i = 0; i < 2; ++i) {
+            if (r->frame_dev[i]) cudaFree(r->frame_dev[i]);
+            r->frame_dev[i] = nullptr, r->frame_in_flight[i] = false;
+            TBRM_CUDA(cudaMalloc(&r->frame_dev[i], bytes));
+        }
+        r->frame_bytes = bytes;
+    }
+    const int f = r->frame_next;
+    r->frame_next ^= 1;
+    // the device frame is reused every second call: its previous copy to the host must have finished
+    if (r->frame_in_flight[f]) TBRM_CUDA(cudaStreamWaitEvent(r->stream, r->ev_frame_copied[f], 0));
+    s = raymarch_lit_impl(r, cam, world, step_count, 0, cam->height, 8, 1, (float*) r->frame_dev[f], 1, nullptr);
+    if (s != TBRM_OK) return s;
+    TBRM_CUDA(cudaEventRecord(r->ev_frame_done[f], r->stream));
+    TBRM_CUDA(cudaStreamWaitEvent(r->download_stream, r->ev_frame_done[f], 0));
+    TBRM_CUDA(cudaMemcpyAsync(out_host, r->frame_dev[f], bytes, cudaMemcpyDeviceToHost, r->download_stream));
+    TBRM_CUDA(cudaEventRecord(r->ev_frame_copied[f], r->download_stream));
+    r->frame_in_flight[f] = true;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_download_wait(tbrm_resources* r) {
+    TBRM_REQUIRE(r, "tbrm_download_wait: null argument");
+    if (!r->download_stream) return TBRM_OK;
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(cudaStreamSynchronize(r->download_stream));
+    return TBRM_OK;
 }
 
 int tbrm_raymarch_interleaved_rows(int height, int block_rows, int first_block, int block_stride) {

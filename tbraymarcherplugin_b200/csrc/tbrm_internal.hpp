@@ -26,6 +26,19 @@ struct tbrm_resources {
     bool data_owned = false;
     bool data_ready = false;
 
+    // streaming upload / download (tbrm_upload_volume_async, tbrm_raymarch_lit_to_host_async)
+    void* data_back = nullptr;               // back buffer of the data volume
+    cudaStream_t upload_stream = nullptr, download_stream = nullptr;
+    cudaEvent_t ev_uploaded = nullptr;       // the copy into data_back has finished
+    cudaEvent_t ev_back_free = nullptr;      // the render queue no longer reads data_back (recorded when it was swapped out)
+    bool upload_pending = false;
+    void* frame_dev[2] = {nullptr, nullptr}; // device frames, used alternately
+    size_t frame_bytes = 0;
+    cudaEvent_t ev_frame_done[2] = {nullptr, nullptr};   // the raymarch into frame_dev[i] has finished
+    cudaEvent_t ev_frame_copied[2] = {nullptr, nullptr}; // its copy to the host has finished
+    bool frame_in_flight[2] = {false, false};
+    int frame_next = 0;
+
     // TFTextureRef collapsed to 256 x RGBA fp32 (fp16-rounded values)
     float4* tf = nullptr;
     bool tf_ready = false;

@@ -236,6 +236,21 @@ class URaymarchUtils:
         Resources.bIsInitialized = True
 
     @staticmethod
+    def SetDataVolumeAsync(Resources: FBasicRaymarchRenderingResources, volume: np.ndarray) -> None:
+        """Streaming upload of the NEXT data volume into the back buffer (returns immediately; pinned memory overlaps with the
+        render queue). ``volume`` must stay alive until PresentDataVolume + FlushRenderingCommands (or the next call)."""
+        X, Y, Z = Resources.DataDims
+        if volume.shape != (Z, Y, X) or _FMT_OF_NP.get(volume.dtype) != Resources.DataFormat or not volume.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"volume must be C-contiguous with shape {(Z, Y, X)} and dtype {_NP_OF_FMT[Resources.DataFormat]}")
+        check(_capi.load().tbrm_upload_volume_async(Resources.handle, volume.ctypes.data_as(C.c_void_p)))
+
+    @staticmethod
+    def PresentDataVolume(Resources: FBasicRaymarchRenderingResources) -> None:
+        """The render queue waits for the last SetDataVolumeAsync and switches to that volume."""
+        check(_capi.load().tbrm_present_volume(Resources.handle))
+        Resources.bIsInitialized = True
+
+    @staticmethod
     def SetDataVolumeDevice(Resources: FBasicRaymarchRenderingResources, device_ptr: int, copy: bool = False) -> None:
         lib = _capi.load()
         if copy:
@@ -373,6 +388,20 @@ class URaymarchUtils:
             out = np.empty((r1 - r0, Camera.Width, 4), dtype=np.float32)
         check(_capi.load().tbrm_raymarch_lit(Resources.handle, C.byref(cam), C.byref(world), float(StepCount), r0, r1, out.ctypes.data_as(C.c_void_p), 0, psteps))
         return out, int(steps.value)
+
+    @staticmethod
+    def PerformWindowedLitRaymarchAsync(Resources: FBasicRaymarchRenderingResources, Camera: FCamera, WorldParameters: FRaymarchWorldParameters,
+                                        StepCount: float, out: np.ndarray) -> None:
+        """Whole frame into ``out`` ((H, W, 4) float32, pinned for a true overlap) through the download stream; returns
+        immediately. Read ``out`` after WaitForDownloads."""
+        if out.shape != (Camera.Height, Camera.Width, 4) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous (H, W, 4) float32 array")
+        cam, world = Camera.to_c(), WorldParameters.to_c()
+        check(_capi.load().tbrm_raymarch_lit_to_host_async(Resources.handle, C.byref(cam), C.byref(world), float(StepCount), out.ctypes.data_as(C.c_void_p)))
+
+    @staticmethod
+    def WaitForDownloads(Resources: FBasicRaymarchRenderingResources) -> None:
+        check(_capi.load().tbrm_download_wait(Resources.handle))
 
     @staticmethod
     def PerformMandelbulbRaymarchReturnDistance(
