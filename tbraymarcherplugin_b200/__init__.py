@@ -5,9 +5,11 @@ from ._capi import FMT_G8, FMT_G16, FMT_R32F, TbrmError
 from .raymarch_utils import (FBasicRaymarchRenderingResources, FCamera, FClippingPlaneParameters, FDirLightParameters,
                              FMandelbulbParameters, FRaymarchWorldParameters, FSweepStats, FTransform, FWindowingParameters,
                              URaymarchUtils, plan_dir_light)
+from .raymarch_volume import ARaymarchClipPlane, ARaymarchLight, ARaymarchVolume, ERaymarchMaterial
 
 __all__ = [
     "FMT_G8", "FMT_G16", "FMT_R32F", "TbrmError", "FBasicRaymarchRenderingResources", "FCamera", "FClippingPlaneParameters",
     "FDirLightParameters", "FMandelbulbParameters", "FRaymarchWorldParameters", "FSweepStats", "FTransform",
-    "FWindowingParameters", "URaymarchUtils", "plan_dir_light",
+    "FWindowingParameters", "URaymarchUtils", "plan_dir_light", "ARaymarchVolume", "ARaymarchLight", "ARaymarchClipPlane",
+    "ERaymarchMaterial",
 ]

@@ -147,6 +147,43 @@ public:
         Resources.Handle = nullptr;
         Resources.bIsInitialized = false;
     }
+
+    // ---- material entry points (Custom nodes of M_Raymarch) -------------------------------------------------------
+    /** PerformRaymarchCubeSetup + PerformWindowedLitRaymarch (WindowedRaymarchMaterials.usf:36-96) for the whole frame;
+        OutRGBA receives premultiplied RGBA float32, W*H*4 floats, host memory. Returns false if the resources are not ready. */
+    static bool PerformWindowedLitRaymarch(const FBasicRaymarchRenderingResources& Resources, const tbrm_camera& Camera,
+                                           const FRaymarchWorldParameters& WorldParameters, float StepCount, float* OutRGBA,
+                                           uint64_t* OutSteps = nullptr) {
+        const tbrm_world w = ToC(WorldParameters);
+        return tbrm_raymarch_lit(Resources.Handle, &Camera, &w, StepCount, 0, Camera.height, OutRGBA, 0, OutSteps) == TBRM_OK;
+    }
+
+    // ---- streaming (time-varying volumes): the engine streams texture updates while the render thread keeps drawing ------
+    static bool SetDataVolumeAsync(FBasicRaymarchRenderingResources& Resources, const void* PinnedHostVolume) {
+        return tbrm_upload_volume_async(Resources.Handle, PinnedHostVolume) == TBRM_OK;
+    }
+    static bool PresentDataVolume(FBasicRaymarchRenderingResources& Resources) {
+        const bool ok = tbrm_present_volume(Resources.Handle) == TBRM_OK;
+        Resources.bIsInitialized = Resources.bIsInitialized || ok;
+        return ok;
+    }
+    static bool PerformWindowedLitRaymarchAsync(const FBasicRaymarchRenderingResources& Resources, const tbrm_camera& Camera,
+                                                const FRaymarchWorldParameters& WorldParameters, float StepCount, float* PinnedOutRGBA) {
+        const tbrm_world w = ToC(WorldParameters);
+        return tbrm_raymarch_lit_to_host_async(Resources.Handle, &Camera, &w, StepCount, PinnedOutRGBA) == TBRM_OK;
+    }
+    static void WaitForDownloads(const FBasicRaymarchRenderingResources& Resources) { tbrm_download_wait(Resources.Handle); }
+
+    // ---- one volume sharded over the GPUs of a box as Z-slabs (the caller runs one process / context per GPU) ------------
+    /** Configure this GPU's slab (rank of nranks) following the library's partition rule. Neighbours are then connected with
+        tbrm_slab_ipc_handle / tbrm_slab_open_peer (handles travel through the host's own IPC). */
+    static bool ConfigureSlab(FBasicRaymarchRenderingResources& Resources, int Rank, int NumRanks) {
+        int32_t dims[3];
+        if (tbrm_light_volume_dims(Resources.Handle, dims) != TBRM_OK) return false;
+        tbrm_slab s{Rank, NumRanks, 0, 0};
+        tbrm_slab_partition(dims[2], NumRanks, Rank, &s.z_begin, &s.z_end);
+        return tbrm_slab_configure(Resources.Handle, &s) == TBRM_OK;
+    }
 };
 
 }  // namespace tbrm_ue

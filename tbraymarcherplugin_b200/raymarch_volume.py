@@ -1,0 +1,181 @@
+"""Host-side mirror of the caller of the hot path: ARaymarchVolume's light bookkeeping and per-tick update policy.
+
+Reference (paths relative to the plugin root):
+  ARaymarchVolume::OnConstruction    Source/Raymarcher/Private/Actor/RaymarchVolume.cpp:161-173   (LightParametersMap seeding)
+  ARaymarchVolume::Tick              RaymarchVolume.cpp:326-416   (world change => full reset; reset-vs-incremental rule)
+  ARaymarchVolume::ResetAllLights    RaymarchVolume.cpp:418-451
+  ARaymarchVolume::UpdateSingleLight RaymarchVolume.cpp:453-465
+  ARaymarchVolume::GetWorldParameters RaymarchVolume.cpp:632-648
+  ARaymarchLight::GetCurrentParameters Source/Raymarcher/Private/Actor/RaymarchLight.cpp:28-31
+
+This is SURVEY.md §8(f) row 1's host part (the scheduler that decides WHICH operator of the boundary runs each frame); the
+actors' engine plumbing (components, materials, editor hooks) is out of scope. Everything that touches the GPU goes through an
+"operator surface" object with URaymarchUtils' methods (the real one by default), so the policy is testable without a device.
+
+Faithfulness notes:
+* The reference compares world parameters with FTransform::Equals (tolerance 1e-4 per component, RaymarchTypes.h:145-148) and
+  light parameters exactly (RaymarchTypes.h:31-34); so does this mirror.
+* ResetAllLights does NOT refresh LightParametersMap (RaymarchVolume.cpp:418-451): after a reset triggered while lights had
+  moved, the next tick still sees them as changed and either resets again or issues ChangeDirLight from the stale "old"
+  parameters. ``bRefreshLightMapOnReset=False`` (default) reproduces that; ``True`` records the parameters a reset used.
+"""
+from __future__ import annotations
+
+import enum
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+from .raymarch_utils import (FBasicRaymarchRenderingResources, FClippingPlaneParameters, FDirLightParameters, FRaymarchWorldParameters,
+                             FTransform, URaymarchUtils)
+
+KINDA_SMALL_NUMBER = 1e-4  # FTransform::Equals default tolerance
+
+
+class ERaymarchMaterial(enum.Enum):  # RaymarchVolume.h: ERaymarchMaterial
+    Lit = 0
+    Intensity = 1
+    Octree = 2
+
+
+@dataclass(eq=False)
+class ARaymarchLight:
+    """Directional light actor: forward vector + intensity (RaymarchLight.cpp:28-31). Identity (not value) keys the map."""
+
+    ForwardVector: tuple = (0.0, 0.0, -1.0)
+    LightIntensity: float = 1.0
+    Name: str = "RaymarchLight"
+
+    def GetCurrentParameters(self) -> FDirLightParameters:
+        return FDirLightParameters(tuple(float(c) for c in self.ForwardVector), float(self.LightIntensity))
+
+
+@dataclass(eq=False)
+class ARaymarchClipPlane:
+    Center: tuple = (0.0, 0.0, 0.0)
+    Direction: tuple = (0.0, 0.0, 1.0)
+
+    def GetCurrentParameters(self) -> FClippingPlaneParameters:
+        return FClippingPlaneParameters(tuple(map(float, self.Center)), tuple(map(float, self.Direction)))
+
+
+def _light_params_equal(a: FDirLightParameters, b: FDirLightParameters) -> bool:  # RaymarchTypes.h:31-34: exact
+    return tuple(a.LightDirection) == tuple(b.LightDirection) and a.LightIntensity == b.LightIntensity
+
+
+def _transform_equals(a: FTransform, b: FTransform, tol: float = KINDA_SMALL_NUMBER) -> bool:
+    """FTransform::Equals: translation, rotation (q or -q) and scale within the tolerance."""
+    close = lambda u, v: all(abs(x - y) <= tol for x, y in zip(u, v))  # noqa: E731
+    rot = close(a.Rotation, b.Rotation) or close(a.Rotation, tuple(-c for c in b.Rotation))
+    return close(a.Translation, b.Translation) and rot and close(a.Scale3D, b.Scale3D)
+
+
+def _world_params_equal(a: FRaymarchWorldParameters, b: FRaymarchWorldParameters) -> bool:  # RaymarchTypes.h:145-148
+    ca, cb = a.ClippingPlaneParameters, b.ClippingPlaneParameters
+    return _transform_equals(a.VolumeTransform, b.VolumeTransform) and tuple(ca.Center) == tuple(cb.Center) and tuple(ca.Direction) == tuple(cb.Direction)
+
+
+@dataclass
+class FTickReport:
+    """What one Tick did (for logs, tests and benchmarks)."""
+
+    action: str = "none"  # "none" | "not_initialized" | "reset" | "incremental"
+    lights_updated: int = 0
+    errors: List[str] = field(default_factory=list)
+
+
+class ARaymarchVolume:
+    def __init__(self, RaymarchResources: FBasicRaymarchRenderingResources, LightsArray: Optional[List[Optional[ARaymarchLight]]] = None,
+                 ClippingPlane: Optional[ARaymarchClipPlane] = None, VolumeTransform: Optional[FTransform] = None, ops=URaymarchUtils,
+                 bRefreshLightMapOnReset: bool = False):
+        self.RaymarchResources = RaymarchResources
+        self.LightsArray: List[Optional[ARaymarchLight]] = list(LightsArray or [])
+        self.ClippingPlane = ClippingPlane
+        self.ComponentTransform = VolumeTransform or FTransform()
+        self.SelectRaymarchMaterial = ERaymarchMaterial.Lit
+        self.bFastShader = True  # RaymarchVolume.h:64-65
+        self.bVisible = True
+        self.bRequestedRecompute = False
+        self.bRefreshLightMapOnReset = bRefreshLightMapOnReset
+        self.ops = ops
+        self.WorldParameters = self.GetWorldParameters()
+        self.LightParametersMap: Dict[ARaymarchLight, FDirLightParameters] = {}
+        self.OnConstruction()
+
+    # RaymarchVolume.cpp:161-173
+    def OnConstruction(self) -> None:
+        self.LightParametersMap.clear()
+        for light in self.LightsArray:
+            if light is not None and light.LightIntensity > 0.0:
+                self.LightParametersMap[light] = light.GetCurrentParameters()
+
+    # RaymarchVolume.cpp:632-648
+    def GetWorldParameters(self) -> FRaymarchWorldParameters:
+        clip = self.ClippingPlane.GetCurrentParameters() if self.ClippingPlane else FClippingPlaneParameters((0.0, 0.0, 100000.0), (0.0, 0.0, -1.0))
+        return FRaymarchWorldParameters(self.ComponentTransform, clip)
+
+    def UpdateWorldParameters(self) -> None:
+        self.WorldParameters = self.GetWorldParameters()
+
+    # RaymarchVolume.cpp:326-416
+    def Tick(self, DeltaTime: float = 0.0) -> FTickReport:
+        rep = FTickReport()
+        if not self.RaymarchResources.bIsInitialized or not self.bVisible:
+            rep.action = "not_initialized"
+            return rep
+        # Volume transform changed or clipping plane moved -> need full recompute.
+        if not _world_params_equal(self.WorldParameters, self.GetWorldParameters()):
+            self.bRequestedRecompute = True
+            self.UpdateWorldParameters()
+        # Only check if we need to update lights if we're using the Lit raymarch material.
+        if self.SelectRaymarchMaterial != ERaymarchMaterial.Lit:
+            return rep
+        if self.bRequestedRecompute:
+            self.ResetAllLights(rep)
+            return rep
+        lights_to_update: List[ARaymarchLight] = []
+        for light in self.LightsArray:
+            if light is None:
+                continue
+            if light not in self.LightParametersMap:
+                self.LightParametersMap[light] = light.GetCurrentParameters()
+                lights_to_update.append(light)
+            elif not _light_params_equal(light.GetCurrentParameters(), self.LightParametersMap[light]):
+                lights_to_update.append(light)
+        # More than half lights need update -> full reset is quicker (integer division as in the reference)
+        if len(lights_to_update) > 1 and len(lights_to_update) >= len(self.LightsArray) // 2:
+            self.ResetAllLights(rep)
+        else:
+            for light in lights_to_update:
+                self.UpdateSingleLight(light, rep)
+                self.LightParametersMap[light] = light.GetCurrentParameters()
+            if lights_to_update:
+                rep.action = "incremental"
+                rep.lights_updated = len(lights_to_update)
+        return rep
+
+    # RaymarchVolume.cpp:418-451
+    def ResetAllLights(self, rep: Optional[FTickReport] = None) -> None:
+        rep = rep if rep is not None else FTickReport()
+        if not self.RaymarchResources.bIsInitialized:
+            return
+        self.ops.ClearResourceLightVolumes(self.RaymarchResources, 0.0)
+        rep.action = "reset"
+        for light in self.LightsArray:
+            if light is None:
+                continue
+            ok = self.ops.AddDirLightToSingleVolume(self.RaymarchResources, light.GetCurrentParameters(), True, self.WorldParameters,
+                                                    bGPUSync=self.bFastShader)
+            if not ok:
+                rep.errors.append(f"Error. Could not add/remove light {light.Name} in volume.")
+                return  # bRequestedRecompute stays set: the reset is retried next tick
+            rep.lights_updated += 1
+            if self.bRefreshLightMapOnReset:
+                self.LightParametersMap[light] = light.GetCurrentParameters()
+        self.bRequestedRecompute = False
+
+    # RaymarchVolume.cpp:453-465
+    def UpdateSingleLight(self, UpdatedLight: ARaymarchLight, rep: Optional[FTickReport] = None) -> None:
+        ok = self.ops.ChangeDirLightInSingleVolume(self.RaymarchResources, self.LightParametersMap[UpdatedLight], UpdatedLight.GetCurrentParameters(),
+                                                   self.WorldParameters, bGPUSync=self.bFastShader)
+        if not ok and rep is not None:
+            rep.errors.append(f"Error. Could not change light {UpdatedLight.Name} in volume.")

@@ -156,6 +156,61 @@ def test_cpp_host_mirror_compiles_against_the_c_abi(tmp_path):
     assert subprocess.run([str(exe)]).returncode == 0
 
 
+def test_cpp_volume_policy_mirror(tmp_path):
+    """csrc/RaymarchVolume.hpp (ARaymarchVolume::Tick policy in C++) with a recording operator surface: the same decisions as
+    tests/test_volume_policy_cpu.py checks for the Python twin."""
+    import subprocess
+
+    src = tmp_path / "p.cpp"
+    src.write_text('''
+        #include <cstdio>
+        #include "tbraymarcherplugin_b200/csrc/RaymarchVolume.hpp"
+        using namespace tbrm_ue;
+        static std::vector<std::string> calls;
+        struct Rec {
+            static void ClearResourceLightVolumes(FBasicRaymarchRenderingResources, float) { calls.push_back("clear"); }
+            static void AddDirLightToSingleVolume(const FBasicRaymarchRenderingResources&, const FDirLightParameters&, bool, FRaymarchWorldParameters, bool& ok, bool) { calls.push_back("add"); ok = true; }
+            static void ChangeDirLightInSingleVolume(FBasicRaymarchRenderingResources&, FDirLightParameters o, FDirLightParameters n, FRaymarchWorldParameters, bool& ok, bool) {
+                calls.push_back(o.LightIntensity == 1.0f && n.LightIntensity != 1.0f ? "change" : "change?"); ok = true; }
+        };
+        #define CHECK(c) do { if (!(c)) { std::printf("failed: %s (line %d)\\n", #c, __LINE__); return 1; } } while (0)
+        int main() {
+            ARaymarchLight L[4];
+            for (int i = 0; i < 4; ++i) L[i].ForwardVector = FVector(1, 0.1 * i, -0.3);
+            ARaymarchVolume<Rec> vol;
+            vol.RaymarchResources.bIsInitialized = true;
+            for (auto& l : L) vol.LightsArray.push_back(&l);
+            vol.OnConstruction();
+            CHECK(vol.Tick().action == FTickReport::None && calls.empty());
+            L[2].LightIntensity = 0.5f;                       // one light changed: incremental, old parameters from the map
+            CHECK(vol.Tick().action == FTickReport::Incremental && calls.size() == 1 && calls[0] == "change");
+            CHECK(vol.Tick().action == FTickReport::None);
+            calls.clear();
+            L[0].LightIntensity = 0.2f; L[1].LightIntensity = 0.3f;   // 2 of 4 changed: "> 1 && >= half" -> full reset
+            CHECK(vol.Tick().action == FTickReport::Reset && calls.size() == 5 && calls[0] == "clear" && calls[4] == "add");
+            calls.clear();
+            CHECK(vol.Tick().action == FTickReport::Reset);  // reference quirk: the map is stale after a reset, the rule fires again
+            vol.bRefreshLightMapOnReset = true;
+            CHECK(vol.Tick().action == FTickReport::Reset && vol.Tick().action == FTickReport::None);
+            calls.clear();
+            vol.ComponentTransform.Translation = FVector(5, 0, 0);  // world change: full reset
+            CHECK(vol.Tick().action == FTickReport::Reset && !vol.bRequestedRecompute);
+            vol.ComponentTransform.Translation = FVector(5 + 5e-5, 0, 0);  // within FTransform::Equals' tolerance
+            CHECK(vol.Tick().action == FTickReport::None);
+            vol.SelectRaymarchMaterial = ERaymarchMaterial::Intensity;
+            L[3].LightIntensity = 0.1f;
+            calls.clear();
+            CHECK(vol.Tick().action == FTickReport::None && calls.empty());
+            vol.RaymarchResources.bIsInitialized = false;
+            CHECK(vol.Tick().action == FTickReport::NotInitialized);
+            return 0;
+        }''')
+    exe = tmp_path / "p"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-I", str(ROOT), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+
+
 def test_exact_division_free_sequences():
     """The fast kernels replace v/255 by fma(v, c_hi, v*c_lo) and x/W by Markstein's sequence; both must equal IEEE division."""
     v = np.arange(256, dtype=np.float32)

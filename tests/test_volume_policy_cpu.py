@@ -1,0 +1,108 @@
+"""ARaymarchVolume's per-tick update policy (RaymarchVolume.cpp:326-465) mirrored in raymarch_volume.py, checked on the CPU
+with a recording stand-in for the operator surface: which of Clear / AddDirLight / ChangeDirLight runs, with which arguments."""
+import pytest
+
+from tbraymarcherplugin_b200.raymarch_utils import FBasicRaymarchRenderingResources, FTransform
+from tbraymarcherplugin_b200.raymarch_volume import ARaymarchClipPlane, ARaymarchLight, ARaymarchVolume, ERaymarchMaterial
+
+
+class RecordingOps:
+    def __init__(self, fail_on=None):
+        self.calls, self.fail_on = [], fail_on
+
+    def ClearResourceLightVolumes(self, res, value):
+        self.calls.append(("clear", value))
+
+    def AddDirLightToSingleVolume(self, res, light, added, world, bGPUSync=False, stats=None):
+        self.calls.append(("add", tuple(light.LightDirection), light.LightIntensity, added, bGPUSync))
+        return self.fail_on != "add"
+
+    def ChangeDirLightInSingleVolume(self, res, old, new, world, bGPUSync=False, stats=None):
+        self.calls.append(("change", tuple(old.LightDirection), tuple(new.LightDirection), old.LightIntensity, new.LightIntensity))
+        return self.fail_on != "change"
+
+
+def make(n_lights=4, **kw):
+    res = FBasicRaymarchRenderingResources()
+    res.bIsInitialized = True
+    lights = [ARaymarchLight((1.0, 0.1 * i, -0.3), 1.0, f"L{i}") for i in range(n_lights)]
+    ops = RecordingOps(kw.pop("fail_on", None))
+    return ARaymarchVolume(res, lights, ops=ops, **kw), lights, ops
+
+
+def test_nothing_changed_means_no_gpu_work_and_uninitialised_volumes_do_not_tick():
+    vol, lights, ops = make()
+    assert vol.Tick().action == "none" and ops.calls == []
+    vol.RaymarchResources.bIsInitialized = False
+    lights[0].LightIntensity = 0.5
+    assert vol.Tick().action == "not_initialized" and ops.calls == []
+
+
+def test_one_changed_light_is_an_incremental_change_with_the_remembered_old_parameters():
+    vol, lights, ops = make()
+    lights[2].ForwardVector = (0.0, 1.0, 0.0)
+    rep = vol.Tick()
+    assert rep.action == "incremental" and rep.lights_updated == 1
+    assert ops.calls == [("change", (1.0, 0.2, -0.3), (0.0, 1.0, 0.0), 1.0, 1.0)]
+    assert vol.Tick().action == "none"  # the map was refreshed (RaymarchVolume.cpp:411)
+
+
+def test_reset_rule_more_than_one_and_at_least_half_of_the_lights():
+    vol, lights, ops = make(4)
+    lights[0].LightIntensity = 0.2
+    lights[1].LightIntensity = 0.3
+    rep = vol.Tick()  # 2 changed, 2 >= 4 // 2 -> full reset
+    assert rep.action == "reset" and [c[0] for c in ops.calls] == ["clear", "add", "add", "add", "add"]
+    assert all(c[4] is True for c in ops.calls[1:]), "bFastShader selects the fused sweep"
+    # with 6 lights, 2 changed lights are below half: two incremental changes
+    vol, lights, ops = make(6)
+    lights[0].LightIntensity = 0.2
+    lights[5].LightIntensity = 0.3
+    assert vol.Tick().action == "incremental" and [c[0] for c in ops.calls] == ["change", "change"]
+    # a single light never triggers the rule ("Num() > 1"), even if it is the only one
+    vol, lights, ops = make(1)
+    lights[0].LightIntensity = 0.2
+    assert vol.Tick().action == "incremental"
+
+
+def test_world_or_clip_plane_change_forces_a_full_reset_with_the_new_world():
+    plane = ARaymarchClipPlane((0, 0, 0), (0, 0, 1))
+    vol, lights, ops = make(3, ClippingPlane=plane)
+    vol.ComponentTransform = FTransform((5.0, 0.0, 0.0))
+    assert vol.Tick().action == "reset" and vol.bRequestedRecompute is False
+    ops.calls.clear()
+    vol.ComponentTransform = FTransform((5.0 + 5e-5, 0.0, 0.0))  # within FTransform::Equals' tolerance: no change
+    assert vol.Tick().action == "none"
+    plane.Center = (0.0, 0.0, 0.1)  # clip planes compare exactly
+    assert vol.Tick().action == "reset"
+    # only the Lit material keeps the light volume up to date (RaymarchVolume.cpp:366-368)
+    vol.SelectRaymarchMaterial = ERaymarchMaterial.Intensity
+    ops.calls.clear()
+    lights[0].LightIntensity = 0.1
+    assert vol.Tick().action == "none" and ops.calls == []
+
+
+def test_new_lights_enter_the_map_and_a_failed_reset_is_retried():
+    vol, lights, ops = make(4)
+    extra = ARaymarchLight((0.0, 0.0, -1.0), 0.7, "late")
+    vol.LightsArray.append(extra)
+    rep = vol.Tick()  # unknown light: recorded, then "changed" from its own current parameters
+    assert rep.action == "incremental" and ops.calls[0][0] == "change" and ops.calls[0][1] == ops.calls[0][2]
+    vol2, _, ops2 = make(2, fail_on="add")
+    vol2.bRequestedRecompute = True
+    rep = vol2.Tick()
+    assert rep.errors and vol2.bRequestedRecompute is True  # RaymarchVolume.cpp:441-446 returns before clearing the flag
+
+
+def test_reference_quirk_stale_light_map_after_a_reset_and_the_opt_in_fix():
+    for refresh in (False, True):
+        vol, lights, ops = make(4, bRefreshLightMapOnReset=refresh)
+        lights[0].LightIntensity = 0.2
+        vol.bRequestedRecompute = True
+        assert vol.Tick().action == "reset"
+        ops.calls.clear()
+        rep = vol.Tick()
+        if refresh:
+            assert rep.action == "none"
+        else:  # the reference re-issues a change from parameters the light volume no longer holds
+            assert rep.action == "incremental" and ops.calls[0][:1] == ("change",) and ops.calls[0][3:] == (1.0, 0.2)
