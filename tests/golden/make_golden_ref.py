@@ -1,0 +1,72 @@
+"""Writes tests/golden/ref_*.npz from the REFERENCE'S OWN host code (oracle/_ref/libtbrm_ref.so = LightingShaderUtils.cpp,
+VolumeInfo.cpp and the TextureUtilities.h templates of /root/reference, compiled against the engine-type shim of
+oracle/ue_shim by oracle/ref.mk). Unlike make_golden.py these vectors ARE reference output: they pin the oracle (and the
+product's host math) to the reference for SURVEY.md §8 rows a15-a21 and the volume normalisation of row (f)3, and they
+travel to machines where /root/reference does not exist.
+
+    python tests/golden/make_golden_ref.py        (needs /root/reference or a prebuilt oracle/_ref/libtbrm_ref.so)
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE.parents[1]))
+sys.path.insert(0, str(HERE.parent))
+
+import refpin  # noqa: E402
+from tbraymarcherplugin_b200 import synth  # noqa: E402
+from tbraymarcherplugin_b200.raymarch_utils import (FClippingPlaneParameters, FDirLightParameters, FRaymarchWorldParameters,  # noqa: E402
+                                                    FTransform)
+
+SPECIAL_DIRS = [(0, 0, -1), (1, 0, 0), (0, -1, 0), (1, 1, 0), (1, -1, 0), (-1, 1, 1), (1, 1, 1), (0, 1, -1), (-1, 0, -1), (1, 1e-4, 0),
+                (0, 0, 0), (0.05, 0.02, -1), (-3, 0.4, 0.3)]
+
+
+def world_to_row(w: FRaymarchWorldParameters) -> np.ndarray:
+    c = w.to_c()
+    return np.array([*c.translation, *c.rotation, *c.scale, *c.clip.center, *c.clip.direction], np.float64)
+
+
+def world_from_row(r: np.ndarray) -> FRaymarchWorldParameters:
+    t = FTransform(tuple(r[0:3]), tuple(r[3:7]), tuple(r[7:10]))
+    return FRaymarchWorldParameters(t, FClippingPlaneParameters(tuple(r[10:13]), tuple(r[13:16])))
+
+
+def hostmath_inputs():
+    rng = np.random.default_rng(20261017)
+    dims, dirs, inten, worlds = [], [], [], []
+    fixed = [synth.identity_world(), synth.scaled_rotated_world(), synth.clipped_world()]
+    for i, d in enumerate(SPECIAL_DIRS):
+        for w in fixed[: 1 + (i % 3)]:
+            dims.append((32, 48, 64) if i % 2 else (512, 512, 512)), dirs.append(d), inten.append(0.7), worlds.append(world_to_row(w))
+    for l in synth.LIGHTS:
+        for w in fixed:
+            dims.append((512, 512, 512)), dirs.append(tuple(l.LightDirection)), inten.append(l.LightIntensity), worlds.append(world_to_row(w))
+    for i in range(300):
+        axis = rng.standard_normal(3)
+        t = FTransform.from_axis_angle(tuple(axis), float(rng.uniform(-180, 180)), tuple(rng.uniform(-50, 50, 3)), tuple(rng.uniform(0.3, 3.0, 3)))
+        w = FRaymarchWorldParameters(t, FClippingPlaneParameters(tuple(rng.uniform(-40, 40, 3)), tuple(rng.standard_normal(3))))
+        dims.append(tuple(int(x) for x in rng.integers(5, 1100, 3))), dirs.append(tuple(rng.standard_normal(3) * 3))
+        inten.append(float(rng.uniform(0.05, 1.5))), worlds.append(world_to_row(w if i % 5 else fixed[0]))
+    return np.array(dims, np.int32), np.array(dirs, np.float64), np.array(inten, np.float32), np.array(worlds, np.float64)
+
+
+def hostmath_case():
+    dims, dirs, inten, worlds = hostmath_inputs()
+    plans = []
+    for d, l, i, w in zip(dims, dirs, inten, worlds):
+        p = refpin.plan_dir_light(tuple(int(x) for x in d), FDirLightParameters(tuple(l), float(i)), world_from_row(w))
+        plans.append(refpin.plan_to_vector(p))
+    perms = np.stack([refpin.permutation_rows(f) for f in range(6)])
+    return {"dims": dims, "dirs": dirs, "intensity": inten, "worlds": worlds, "plans": np.stack(plans), "permutation_rows": perms}
+
+
+CASES = {"ref_hostmath": hostmath_case}
+
+if __name__ == "__main__":
+    for name, fn in CASES.items():
+        arrays = fn()
+        np.savez_compressed(HERE / f"{name}.npz", **arrays)
+        print(name, {k: v.shape for k, v in arrays.items()})

@@ -1,0 +1,92 @@
+"""ctypes binding of oracle/_ref/libtbrm_ref.so: the reference's OWN host code (LightingShaderUtils.cpp, VolumeInfo.cpp, the
+TextureUtilities.h templates) compiled from /root/reference against the engine-type shim of oracle/ue_shim (oracle/ref.mk).
+Test infrastructure. The library is prebuilt in the development container (build() of __graft_entry__.py) and travels to the GPU
+box as a file; where it is absent the tests that need it skip and the committed vectors of tests/golden/ref_*.npz stand in."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+import oracle
+from tbraymarcherplugin_b200 import _capi
+
+ROOT = Path(__file__).resolve().parents[1]
+LIB = ROOT / "oracle" / "_ref" / "libtbrm_ref.so"
+REFERENCE = Path("/root/reference")
+
+# EVolumeVoxelFormat (Source/VolumeTextureToolkit/Public/VolumeAsset/VolumeInfo.h:12-27)
+VOXEL_DTYPES = {0: np.uint8, 1: np.int8, 2: np.uint16, 3: np.int16, 4: np.uint32, 5: np.int32, 6: np.float32}
+
+_lib = None
+
+
+def available() -> bool:
+    return LIB.exists() or REFERENCE.exists()
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            if not REFERENCE.exists():
+                raise FileNotFoundError(f"{LIB} is not built and {REFERENCE} is not present")
+            subprocess.run(["make", "-C", str(ROOT / "oracle"), "-f", "ref.mk"], check=True)
+        L = C.CDLL(str(LIB))
+        L.tbref_plan_dir_light.argtypes = [C.POINTER(C.c_int32), C.POINTER(_capi.DirLight), C.POINTER(_capi.World), C.POINTER(oracle.LightPlan)]
+        L.tbref_permutation_rows.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.tbref_normalize_array.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.tbref_convert_to_float.argtypes = [C.c_int, C.c_void_p, C.c_int32, C.c_void_p]
+        L.tbref_volume_info_map.restype = C.c_float
+        L.tbref_volume_info_map.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        _lib = L
+    return _lib
+
+
+def plan_dir_light(ldims, light, world) -> oracle.LightPlan:
+    out = oracle.LightPlan()
+    l, w = light.to_c(), world.to_c()
+    lib().tbref_plan_dir_light((C.c_int32 * 3)(*ldims), C.byref(l), C.byref(w), C.byref(out))
+    return out
+
+
+def permutation_rows(face: int) -> np.ndarray:
+    rows = (C.c_double * 9)()
+    lib().tbref_permutation_rows(face, rows)
+    return np.array(rows).reshape(3, 3)
+
+
+def normalize_array(fmt: int, arr: np.ndarray):
+    """UVolumeTextureToolkit::NormalizeArrayByFormat: returns (normalised array, original min, original max)."""
+    a = np.ascontiguousarray(arr, VOXEL_DTYPES[fmt])
+    out = np.empty(a.size, np.uint8 if a.itemsize == 1 else np.uint16)
+    lo, hi = C.c_float(), C.c_float()
+    nb = lib().tbref_normalize_array(fmt, a.ctypes.data, a.nbytes, out.ctypes.data, C.byref(lo), C.byref(hi))
+    assert nb == out.itemsize
+    return out.reshape(a.shape), lo.value, hi.value
+
+
+def convert_to_float(fmt: int, arr: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(arr, VOXEL_DTYPES[fmt])
+    out = np.empty(a.size, np.float32)
+    assert lib().tbref_convert_to_float(fmt, a.ctypes.data, a.size, out.ctypes.data) == 0
+    return out.reshape(a.shape)
+
+
+def volume_info_map(what: int, is_normalized: bool, lo: float, hi: float, v: float) -> float:
+    return float(lib().tbref_volume_info_map(what, int(is_normalized), lo, hi, v))
+
+
+PLAN_PASS_FIELDS = ["face", "axis", "dirn", "td", "start", "stop", "weight", "light_alpha", "border", "uv_offset", "uvw_offset", "step_size"]
+
+
+def plan_to_vector(p: oracle.LightPlan) -> np.ndarray:
+    """Every field the reference computes, as float64 (exact for the int32 / float32 / float64 members)."""
+    v = [p.zero_direction, p.add_passes, *p.clip_center, *p.clip_dir, *p.local_dir]
+    for ps in p.passes:
+        for f in PLAN_PASS_FIELDS:
+            x = getattr(ps, f)
+            v.extend(list(x) if hasattr(x, "__len__") else [x])
+    return np.array(v, np.float64)
