@@ -92,6 +92,29 @@ extern "C" int tbref_plan_dir_light(const int32_t ldims[3], const tbrm_dir_light
     return 0;
 }
 
+// GetLocalClippingParameters (LightingShaderUtils.cpp:205-220), as ARaymarchVolume feeds it to the materials (RaymarchVolume.cpp:705-728)
+extern "C" void tbref_local_clipping(const tbrm_world* world, float center[3], float dir[3]) {
+    FRaymarchWorldParameters WorldParameters;
+    WorldParameters.VolumeTransform = to_transform(*world);
+    WorldParameters.ClippingPlaneParameters = FClippingPlaneParameters(FVector(world->clip.center[0], world->clip.center[1], world->clip.center[2]),
+                                                                      FVector(world->clip.direction[0], world->clip.direction[1], world->clip.direction[2]));
+    const FClippingPlaneParameters L = GetLocalClippingParameters(WorldParameters);
+    center[0] = (float) L.Center.X, center[1] = (float) L.Center.Y, center[2] = (float) L.Center.Z;
+    dir[0] = (float) L.Direction.X, dir[1] = (float) L.Direction.Y, dir[2] = (float) L.Direction.Z;
+}
+
+// Border colour of the data-volume sampler: the statements of FAddDirLightShader::SetRaymarchResources (LightingShaders.h:76-94; the class
+// itself is RHI code) on the shim's FLinearColor, then what the RHI makes of the packed colour (policy Q1: byte / 255, sRGB -> linear).
+extern "C" float tbref_data_border(const tbrm_windowing* win, int exact) {
+    FWindowingParameters WindowingParams;
+    WindowingParams.Center = win->center, WindowingParams.Width = win->width;
+    float ZeroTFValue = WindowingParams.Center - 0.5 * WindowingParams.Width;
+    if (exact) return ZeroTFValue;
+    FLinearColor VolumeClearColor = FLinearColor(ZeroTFValue, 0.0, 0.0, 0.0);
+    const uint32 BorderColorInt = VolumeClearColor.ToFColor(false).ToPackedARGB();
+    return border_from_packed(BorderColorInt);
+}
+
 // rows of GetPermutationMatrix(LocalMajorAxes, index) for a face: pos = px*row0 + py*row1 + Loop*row2 (AddDirLightShader.usf)
 extern "C" void tbref_permutation_rows(int face, double rows[9]) {
     FMajorAxes axes;

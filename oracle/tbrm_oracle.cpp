@@ -55,51 +55,10 @@ inline F3 normalize3(F3 a) {
 inline float saturatef(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }  // saturate(NaN) = 0 like HLSL
 inline float signf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
-const float kLog2P[10] = {1.4426950216293335f,  -0.7213473320007324f, 0.4808982014656067f,  -0.3606966435909271f,
-                          0.2885688841342926f,  -0.23961904644966125f, 0.2045752853155136f, -0.19102497398853302f,
-                          0.18631209433078766f, -0.11020159721374512f};
-const float kExp2Q[7] = {1.0f,
-                         0.6931471824645996f,
-                         0.24022650718688965f,
-                         0.05550327152013779f,
-                         0.009618035517632961f,
-                         0.0013400432653725147f,
-                         0.00015467364573851228f};
-
-inline float det_log2(float x) {  // x normal, > 0
-    int32_t bits;
-    std::memcpy(&bits, &x, 4);
-    int32_t e = ((bits >> 23) & 0xff) - 127;
-    int32_t mb = (bits & 0x007fffff) | 0x3f800000;
-    float m;
-    std::memcpy(&m, &mb, 4);
-    if (m > 1.41421356f) {
-        m = m * 0.5f;
-        e += 1;
-    }
-    float t = m - 1.0f;
-    float p = kLog2P[9];
-    for (int i = 8; i >= 0; --i) p = fmaf(p, t, kLog2P[i]);
-    return fmaf(t, p, (float) e);
-}
-inline float det_exp2(float z) {
-    float n = floorf(z + 0.5f);
-    if (n < -125.0f) return 0.0f;
-    float f = z - n;
-    float q = kExp2Q[6];
-    for (int i = 5; i >= 0; --i) q = fmaf(q, f, kExp2Q[i]);
-    int32_t qb;
-    std::memcpy(&qb, &q, 4);
-    qb += ((int32_t) n) << 23;
-    float r;
-    std::memcpy(&r, &qb, 4);
-    return r;
-}
-// pow(x, y) for y > 0, x <= 1 (the only use: 1 - pow(1 - a, StepSize), WindowedSampling.usf:35)
-inline float det_pow(float x, float y) {
-    if (!(x >= 1.17549435e-38f)) return 0.0f;
-    return det_exp2(y * det_log2(x));
-}
+}  // namespace
+#include "tbrm_contract.h"
+namespace {
+using namespace tbrm_contract;
 
 // fp32 -> fp16 -> fp32 round trip, round-to-nearest-even (FFloat16 / PF_FloatRGBA texels, Q9)
 inline float round_to_half(float f) {
@@ -767,6 +726,18 @@ inline void accumulate_step(const MarchCtx& c, F3 p, float step, float acc[4]) {
 }
 
 }  // namespace
+
+extern "C" void tbo_make_camera_uniforms(const tbrm_camera* cam, const tbrm_world* world, tbo_camera_uniforms* out) {
+    CamF c;
+    make_cam(cam, world, c);
+    const F3 v[4] = {c.eye, c.fwd, c.rt, c.ut};
+    float* dst[4] = {out->eye, out->fwd, out->rt, out->ut};
+    for (int i = 0; i < 4; ++i) dst[i][0] = v[i].x, dst[i][1] = v[i].y, dst[i][2] = v[i].z;
+    out->inv_w2 = c.inv_w2, out->inv_h2 = c.inv_h2;
+    std::memcpy(out->m, c.m, sizeof(c.m));
+    out->depth = c.depth;
+    out->width = cam->width, out->height = cam->height, out->frame_mod8 = cam->frame_index % 8, out->jitter = cam->jitter;
+}
 
 extern "C" int tbo_raymarch_cube_setup(const tbrm_camera* cam, const tbrm_world* world, float* out) {
     CamF c;

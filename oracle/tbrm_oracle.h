@@ -41,6 +41,18 @@ typedef struct tbo_volume {
     int32_t data_addr_wrap;
 } tbo_volume;
 
+/* The fp32 uniforms the stand-in camera (tbrm_camera, include/tbrm.h) hands to the pixel shader: ResolvedView.WorldCameraOrigin,
+ * the camera basis that yields MaterialParameters.CameraVector per pixel, GetPrimitiveData().WorldToLocal, scene depth.
+ * Same layout as the kernels' RayCam (csrc/raymarch.cu). */
+typedef struct tbo_camera_uniforms {
+    float eye[3], fwd[3], rt[3], ut[3]; /* rt = right * tan(hfov/2), ut = up * tan(hfov/2) * H/W */
+    float inv_w2, inv_h2;               /* 2/W, 2/H */
+    float m[4][3];                      /* WorldToLocal, row-vector convention: local = [w,1] * M */
+    float depth;
+    int32_t width, height, frame_mod8, jitter;
+} tbo_camera_uniforms;
+void tbo_make_camera_uniforms(const tbrm_camera* cam, const tbrm_world* world, tbo_camera_uniforms* out);
+
 void tbo_prepare_tf(const float* rgba, int width, int height, float* out_256x4);
 void tbo_default_tf(float* out_256x4);
 int tbo_plan_dir_light(const int32_t ldims[3], const tbrm_windowing* win, int border_exact, const tbrm_dir_light* light,

@@ -63,7 +63,51 @@ def hostmath_case():
     return {"dims": dims, "dirs": dirs, "intensity": inten, "worlds": worlds, "plans": np.stack(plans), "permutation_rows": perms}
 
 
-CASES = {"ref_hostmath": hostmath_case}
+SHADER_DIMS = (24, 20, 16)
+
+
+def shader_inputs():
+    import oracle
+    from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters
+    data = synth.perlin_ct_volume(SHADER_DIMS)
+    return data, oracle.prepare_tf(synth.soft_ct_curve()), FWindowingParameters(0.45, 0.5, True, False)
+
+
+def shader_sequence(vol, world, out, tag):
+    """Full reset with the four benchmark lights, removal of L2, an in-place ChangeDirLight (same major axes), one that falls back to
+    Remove + Add (different axes), then a lit frame — the states tests/test_ref_shaders_cpu.py replays through the oracle."""
+    for l in synth.LIGHTS:
+        vol.add_dir_light(l, True, world)
+    out[f"{tag}_reset"] = vol.light.copy()
+    vol.add_dir_light(synth.LIGHTS[1], False, world)
+    out[f"{tag}_removed"] = vol.light.copy()
+    vol.change_dir_light(synth.LIGHTS[0], synth.rotate_about_z(synth.LIGHTS[0], 5.0), world)
+    out[f"{tag}_changed"] = vol.light.copy()
+    vol.change_dir_light(synth.LIGHTS[2], synth.rotate_about_z(synth.LIGHTS[2], 80.0), world)
+    out[f"{tag}_changed_fallback"] = vol.light.copy()
+
+
+SHADER_WORLDS = {"identity": synth.identity_world, "scaled_rotated": synth.scaled_rotated_world, "clipped": synth.clipped_world}
+
+
+def shaders_case():
+    """Outputs of the reference's OWN shaders (AddDirLightShader.usf, ChangeDirLightShader.usf, WindowedRaymarchMaterials.usf, compiled
+    for the CPU by oracle/ref.mk) driven by the reference's own host math."""
+    data, tf, win = shader_inputs()
+    out = {}
+    for name, mk in SHADER_WORLDS.items():
+        for light32 in (True, False):
+            vol = refpin.RefVolume(data, tf, win, light32=light32)
+            tag = f"{name}_{'r32f' if light32 else 'g8'}"
+            shader_sequence(vol, mk(), out, tag)
+            if light32:
+                cam = synth.benchmark_camera(40, 24, jitter=True, frame=3)
+                out[f"{tag}_setup"] = vol.raymarch(-1, cam, mk(), 48.0)
+                out[f"{tag}_lit"] = vol.raymarch(0, cam, mk(), 48.0)
+    return out
+
+
+CASES = {"ref_hostmath": hostmath_case, "ref_shaders": shaders_case}
 
 if __name__ == "__main__":
     for name, fn in CASES.items():

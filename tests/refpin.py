@@ -90,3 +90,51 @@ def plan_to_vector(p: oracle.LightPlan) -> np.ndarray:
             x = getattr(ps, f)
             v.extend(list(x) if hasattr(x, "__len__") else [x])
     return np.array(v, np.float64)
+
+
+# ---- the reference's shaders run on the CPU (oracle/ref_shaders.cpp) ----------------------------------------------------------
+class CameraUniforms(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("fwd", C.c_float * 3), ("rt", C.c_float * 3), ("ut", C.c_float * 3), ("inv_w2", C.c_float),
+                ("inv_h2", C.c_float), ("m", C.c_float * 12), ("depth", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("frame_mod8", C.c_int32), ("jitter", C.c_int32)]
+
+
+def camera_uniforms(cam, world) -> CameraUniforms:
+    """The fp32 uniforms of the stand-in camera, computed by the oracle library (an INPUT of the pixel shaders, not part of them)."""
+    out = CameraUniforms()
+    c, w = cam.to_c(), world.to_c()
+    f = oracle.lib().tbo_make_camera_uniforms
+    f.argtypes = [C.POINTER(_capi.Camera), C.POINTER(_capi.World), C.POINTER(CameraUniforms)]
+    f.restype = None
+    f(C.byref(c), C.byref(w), C.byref(out))
+    return out
+
+
+class RefVolume(oracle.OracleVolume):
+    """OracleVolume whose ops run the reference's own shaders (AddDirLightShader.usf, ChangeDirLightShader.usf,
+    WindowedRaymarchMaterials.usf ... compiled for the CPU) driven by the reference's own host math."""
+
+    def add_dir_light(self, light, added, world, near_gate=None) -> int:
+        v, l, w = self.c(), light.to_c(), world.to_c()
+        f = lib().tbref_add_dir_light
+        f.argtypes = [C.POINTER(oracle.Volume), C.POINTER(_capi.DirLight), C.c_int, C.POINTER(_capi.World)]
+        return f(C.byref(v), C.byref(l), int(added), C.byref(w))
+
+    def change_dir_light(self, old, new, world, near_gate=None) -> int:
+        v, o, n, w = self.c(), old.to_c(), new.to_c(), world.to_c()
+        f = lib().tbref_change_dir_light
+        f.argtypes = [C.POINTER(oracle.Volume), C.POINTER(_capi.DirLight), C.POINTER(_capi.DirLight), C.POINTER(_capi.World)]
+        return f(C.byref(v), C.byref(o), C.byref(n), C.byref(w))
+
+    def raymarch(self, material: int, cam, world, steps: float, rows=None, octree=None, octree_mip: int = 0) -> np.ndarray:
+        """material: -1 cube setup, 0 lit, 1 intensity, 2 octree (octree = list of 4 uint16 mip arrays, z-y-x ordered)."""
+        r0, r1 = rows if rows else (0, cam.Height)
+        out = np.empty((r1 - r0, cam.Width, 4), np.float32)
+        v, w, cu = self.c(), world.to_c(), camera_uniforms(cam, world)
+        mips = (C.c_void_p * 4)(*[m.ctypes.data for m in octree]) if octree else None
+        odims = (C.c_int32 * 3)(*octree[0].shape[::-1]) if octree else None
+        f = lib().tbref_raymarch
+        f.argtypes = [C.c_int, C.POINTER(oracle.Volume), C.POINTER(CameraUniforms), C.POINTER(_capi.World), C.c_float, C.c_int, C.c_int,
+                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        f(material, C.byref(v), C.byref(cu), C.byref(w), float(steps), r0, r1, mips, odims, int(octree_mip), out.ctypes.data)
+        return out

@@ -72,3 +72,4 @@ def test_mandelbulb_close_to_golden():
     bad = np.abs(out - want["out"]).max(axis=-1) > 1e-4
     assert bad.mean() <= 0.02, f"{bad.sum()} of {bad.size} pixels differ"
     assert abs(iters - int(want["iterations"][0])) / int(want["iterations"][0]) < 0.02
+

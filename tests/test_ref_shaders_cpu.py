@@ -1,0 +1,92 @@
+"""Pins the oracle to the REFERENCE'S OWN SHADER CODE. oracle/ref.mk streams AddDirLightShader.usf, ChangeDirLightShader.usf,
+WindowedRaymarchMaterials.usf (+ RaymarchMaterialCommon / WindowedSampling / RaymarcherCommon), GenerateOctreeShader.usf, SDFMarcher.usf and
+CalculateMandelbulbSDF.usf from /root/reference through syntactic rewrites (oracle/hlsl2cpp.py) and compiles them for the CPU against
+oracle/hlsl_shim; oracle/ref_shaders.cpp dispatches them with the uniforms the reference's own host code computes.
+
+  * tests/golden/ref_shaders.npz holds outputs of that build (tests/golden/make_golden_ref.py): the oracle must reproduce them
+    bit for bit — this part runs everywhere;
+  * with oracle/_ref/libtbrm_ref.so present the comparison also runs live over more formats, sizes and random lights.
+
+A match proves that the oracle restates the shaders' logic (gating, thresholds, operation order, addressing, the schedule of the
+host drivers). The engine semantics under the shaders (samplers, UNORM conversions, pow) are the shim's — the same policies the
+oracle states — and stay unpinned."""
+import importlib.util
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+import refpin
+from tbraymarcherplugin_b200 import synth
+from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FWindowingParameters
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+_spec = importlib.util.spec_from_file_location("make_golden_ref", GOLDEN / "make_golden_ref.py")
+mk = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mk)
+
+needs_ref = pytest.mark.skipif(not refpin.available(), reason="oracle/_ref/libtbrm_ref.so not built and /root/reference absent")
+
+
+@pytest.mark.parametrize("world", list(mk.SHADER_WORLDS))
+@pytest.mark.parametrize("light32", [True, False])
+def test_oracle_reproduces_the_reference_shaders_golden_outputs(world, light32):
+    want = np.load(GOLDEN / "ref_shaders.npz")
+    data, tf, win = mk.shader_inputs()
+    vol = oracle.OracleVolume(data, tf, win, light32=light32)
+    got = {}
+    tag = f"{world}_{'r32f' if light32 else 'g8'}"
+    mk.shader_sequence(vol, mk.SHADER_WORLDS[world](), got, tag)
+    for k, v in got.items():
+        assert v.dtype == want[k].dtype and np.array_equal(v, want[k]), f"{k}: oracle differs from the reference shader"
+    if light32:
+        cam = synth.benchmark_camera(40, 24, jitter=True, frame=3)
+        w = mk.SHADER_WORLDS[world]()
+        assert np.array_equal(oracle.cube_setup(cam, w), want[f"{tag}_setup"])
+        rgba, _ = vol.raymarch_lit(cam, w, 48.0)
+        assert np.array_equal(rgba, want[f"{tag}_lit"])
+
+
+def test_reference_shader_golden_outputs_are_not_trivial():
+    g = np.load(GOLDEN / "ref_shaders.npz")
+    assert g["identity_r32f_reset"].max() > 1.5 and g["identity_g8_reset"].max() == 255
+    for a, b in (("reset", "removed"), ("removed", "changed"), ("changed", "changed_fallback")):
+        assert not np.array_equal(g[f"identity_r32f_{a}"], g[f"identity_r32f_{b}"])
+    assert not np.array_equal(g["identity_r32f_reset"], g["clipped_r32f_reset"])
+    assert g["identity_r32f_lit"][..., 3].max() > 0.3 and (g["identity_r32f_setup"][..., 3] > 0).mean() > 0.3
+
+
+@needs_ref
+def test_golden_outputs_are_what_the_reference_build_produces_today():
+    want = np.load(GOLDEN / "ref_shaders.npz")
+    got = mk.shaders_case()
+    assert set(want.files) == set(got)
+    for k in want.files:
+        assert np.array_equal(want[k], got[k]), k
+
+
+@needs_ref
+@pytest.mark.parametrize("dtype,half_res,border_exact", [(np.uint8, False, False), (np.uint16, False, False), (np.float32, False, True),
+                                                         (np.uint8, True, False)])
+def test_oracle_equals_live_reference_shaders(dtype, half_res, border_exact):
+    rng = np.random.default_rng(11)
+    base = synth.perlin_ct_volume((20, 28, 36))
+    data = base if dtype == np.uint8 else (base.astype(np.uint16) * 257 if dtype == np.uint16 else (base / np.float32(255)).astype(np.float32))
+    tf = oracle.prepare_tf(synth.soft_ct_curve())
+    for win, world in ((FWindowingParameters(0.45, 0.5, True, False), synth.scaled_rotated_world()),
+                       (FWindowingParameters(0.5, 1.0, True, True), synth.clipped_world())):
+        kw = dict(light32=True, half_res=half_res, border_exact=border_exact)
+        a, b = oracle.OracleVolume(data, tf, win, **kw), refpin.RefVolume(data, tf, win, **kw)
+        lights = [FDirLightParameters(tuple(rng.standard_normal(3)), float(rng.uniform(0.3, 1.2))) for _ in range(3)]
+        lights.append(FDirLightParameters((0, 0, -1), 0.5))  # axis-aligned: a single pass
+        for l in lights:
+            a.add_dir_light(l, True, world), b.add_dir_light(l, True, world)
+            assert np.array_equal(a.light, b.light)
+        for l in lights[:3]:
+            n = synth.rotate_about_z(l, 7.0)
+            a.change_dir_light(l, n, world), b.change_dir_light(l, n, world)
+            assert np.array_equal(a.light, b.light)
+        cam = synth.benchmark_camera(36, 28, jitter=True, frame=5)
+        rgba, _ = a.raymarch_lit(cam, world, 40.0)
+        assert np.array_equal(rgba, b.raymarch(0, cam, world, 40.0))
