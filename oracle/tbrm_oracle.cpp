@@ -823,6 +823,219 @@ extern "C" int tbo_raymarch_lit(const tbo_volume* vol, const tbrm_camera* cam, c
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// the other two materials and the octree they read — SURVEY.md §8(f) row 2
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+// per-pixel preamble shared by the three marches (WindowedRaymarchMaterials.usf:46-62, 113-130, 196-208)
+struct MarchSetup {
+    F3 cur, sv;
+    int max_steps;
+    float fin, ss;
+};
+inline MarchSetup march_setup(const CamF& c, const tbrm_camera* cam, float step_count, int ix, int iy) {
+    F3 V = camera_vector(c, ix, iy), cur, lcv;
+    float thick;
+    cube_setup(c, V, cur, thick, lcv);
+    MarchSetup m;
+    m.ss = 1 / step_count;
+    float fas = step_count * thick;
+    float fl = floorf(fas);
+    m.max_steps = (int) fl;
+    m.fin = fas - fl;
+    m.sv = f3(lcv.x * m.ss, lcv.y * m.ss, lcv.z * m.ss);
+    if (cam->jitter) {
+        float rnd = (float) pcg16_x(ix, iy, cam->frame_index % 8) / 65535.0f;
+        cur = f3(cur.x - m.sv.x * rnd, cur.y - m.sv.y * rnd, cur.z - m.sv.z * rnd);
+    }
+    m.cur = cur;
+    return m;
+}
+inline bool clipped(F3 p, F3 cc, F3 cd) {  // IsCurPosClipped — RaymarcherCommon.usf:22-25
+    return dot3(f3(p.x - cc.x, p.y - cc.y, p.z - cc.z), cd) <= 0.0f;
+}
+inline void local_clip(const tbo_volume* vol, const tbrm_world* world, F3& cc, F3& cd) {
+    tbo_light_plan plan;
+    tbrm_dir_light dummy{{0, 0, 1}, 0.0f};
+    const int32_t one[3] = {1, 1, 1};
+    const tbrm_windowing w0{0.5f, 1.0f, 1, 1};
+    tbo_plan_dir_light(vol ? vol->ldims : one, vol ? &vol->win : &w0, 1, &dummy, world, &plan);
+    cc = f3(plan.clip_center[0], plan.clip_center[1], plan.clip_center[2]);
+    cd = f3(plan.clip_dir[0], plan.clip_dir[1], plan.clip_dir[2]);
+}
+// UNORM16 UAV store (A.1)
+inline uint16_t quant16(float v) { return (uint16_t) floorf(saturatef(v) * 65535.0f + 0.5f); }
+struct OctreeTex {
+    const uint16_t* mip[4];
+    int X[4], Y[4], Z[4];
+    inline float load(int m, int x, int y, int z) const {  // Texture3D.Load: out-of-bounds -> 0
+        if (x < 0 || y < 0 || z < 0 || x >= X[m] || y >= Y[m] || z >= Z[m]) return 0.0f;
+        return (float) mip[m][(size_t) x + (size_t) X[m] * ((size_t) y + (size_t) Y[m] * (size_t) z)] / 65535.0f;
+    }
+};
+inline void octree_dims(const int32_t odims[3], OctreeTex& t) {
+    for (int m = 0; m < 4; ++m) t.X[m] = std::max(1, odims[0] >> m), t.Y[m] = std::max(1, odims[1] >> m), t.Z[m] = std::max(1, odims[2] >> m);
+}
+}  // namespace
+
+// PerformWindowedIntensityRaymarch — WindowedRaymarchMaterials.usf:187-242: the first unclipped sample, windowed to grey, alpha 1
+extern "C" int tbo_raymarch_intensity(const tbo_volume* vol, const tbrm_camera* cam, const tbrm_world* world, float step_count,
+                                      int row_begin, int row_end, float* out_rgba, uint64_t* out_steps) {
+    CamF c;
+    make_cam(cam, world, c);
+    F3 cc, cd;
+    local_clip(vol, world, cc, cd);
+    DataTex data{vol->data, vol->data_fmt, vol->ddims[0], vol->ddims[1], vol->ddims[2]};
+    const int W = cam->width;
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : total)
+    for (int iy = row_begin; iy < row_end; ++iy)
+        for (int ix = 0; ix < W; ++ix) {
+            MarchSetup m = march_setup(c, cam, step_count, ix, iy);
+            F3 cur = m.cur;
+            float o[4] = {0, 0, 0, 0};  // :241 "didn't hit anything"
+            uint64_t steps = 0;
+            bool hit = false;
+            for (int i = 0; i < m.max_steps; i++) {  // :211
+                cur = f3(cur.x + m.sv.x, cur.y + m.sv.y, cur.z + m.sv.z);
+                ++steps;
+                F3 sp = f3(saturatef(cur.x), saturatef(cur.y), saturatef(cur.z));
+                if (!clipped(sp, cc, cd)) {           // :215 tests the SATURATED position
+                    float v = sample_data(data, sp, ADDR_CLAMP, 0.0f);  // :217
+                    float pos = saturatef(tf_position(v, vol->win.center, vol->win.width));  // :220 clamp(..., 0, 1)
+                    o[0] = o[1] = o[2] = pos, o[3] = 1.0f;
+                    hit = true;
+                    break;                            // :222 return
+                }
+            }
+            if (!hit && m.fin > 0.0f) {               // :227
+                cur = f3(cur.x + m.sv.x * m.fin, cur.y + m.sv.y * m.fin, cur.z + m.sv.z * m.fin);
+                ++steps;
+                if (!clipped(cur, cc, cd)) {          // :231 tests the raw position
+                    float v = sample_data(data, cur, ADDR_CLAMP, 0.0f);
+                    float pos = saturatef(tf_position(v, vol->win.center, vol->win.width));
+                    o[0] = o[1] = o[2] = pos, o[3] = 1.0f;
+                }
+            }
+            size_t p = 4 * ((size_t) (iy - row_begin) * W + ix);
+            out_rgba[p] = o[0], out_rgba[p + 1] = o[1], out_rgba[p + 2] = o[2], out_rgba[p + 3] = o[3];
+            total += steps;
+        }
+    if (out_steps) *out_steps = total;
+    return 0;
+}
+
+// GenerateOctreeShader.usf:28-107 dispatched by GenerateOctreeForVolume_RenderThread (OctreeShaders.cpp:28-54): one thread per 8^3 leaf
+// of a render target whose sides are the data volume's rounded up to powers of two (RaymarchVolume.cpp:873-877), 4 mips, PF_G16.
+// mips[m]: (odims >> m, at least 1) UNORM16 texels. Mip 0 = data value * MinMaxValues.y (= 1), 0 outside the data volume; mip m =
+// max over 2x2x2 texels of mip m-1 (read back through the UNORM16 UAV, i.e. after quantisation).
+extern "C" int tbo_generate_octree(const void* data, const int32_t ddims[3], int data_fmt, const int32_t odims[3], void* const* mips) {
+    DataTex vol{data, data_fmt, ddims[0], ddims[1], ddims[2]};
+    OctreeTex t;
+    octree_dims(odims, t);
+    uint16_t* w[4];
+    for (int m = 0; m < 4; ++m) w[m] = (uint16_t*) mips[m], t.mip[m] = w[m];
+    auto store = [&](int m, int x, int y, int z, float v) {  // out-of-bounds UAV stores are dropped
+        if (x < t.X[m] && y < t.Y[m] && z < t.Z[m]) w[m][(size_t) x + (size_t) t.X[m] * ((size_t) y + (size_t) t.Y[m] * (size_t) z)] = quant16(v);
+    };
+    const int gx = (odims[0] + 7) / 8, gy = (odims[1] + 7) / 8, gz = (odims[2] + 7) / 8;
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int lz = 0; lz < gz; ++lz)
+        for (int ly = 0; ly < gy; ++ly)
+            for (int lx = 0; lx < gx; ++lx) {
+                const int ox = lx * 8, oy = ly * 8, oz = lz * 8;  // ThreadOffset :33
+                for (int x = 0; x < 8; x++)                       // :36-49
+                    for (int y = 0; y < 8; y++)
+                        for (int z = 0; z < 8; z++) {
+                            const int ax = ox + x, ay = oy + y, az = oz + z;
+                            const bool in = ax < vol.X && ay < vol.Y && az < vol.Z;
+                            store(0, ax, ay, az, (in ? vol.texel(ax, ay, az) : 0.0f) * 1.0f);
+                        }
+                for (int mip = 1; mip < 4; mip++) {               // :60-105
+                    const int div = 1 << mip;
+                    const int lox = (2 * ox) / div, loy = (2 * oy) / div, loz = (2 * oz) / div;  // LowerMipOffset :72
+                    for (int x = 0; x < 8 / div; x++)
+                        for (int y = 0; y < 8 / div; y++)
+                            for (int z = 0; z < 8 / div; z++) {
+                                float mx = 0;
+                                for (int a = 0; a < 2; a++)
+                                    for (int b = 0; b < 2; b++)
+                                        for (int cc = 0; cc < 2; cc++) {
+                                            float nv = t.load(mip - 1, lox + x * 2 + a, loy + y * 2 + b, loz + z * 2 + cc);
+                                            if (mx < nv) mx = nv;
+                                        }
+                                store(mip, ox / div + x, oy / div + y, oz / div + z, mx);
+                            }
+                }
+            }
+    return 0;
+}
+
+// PerformWindowedRaymarchOctree — WindowedRaymarchMaterials.usf:99-183: the lit march's loop with a point Load from one octree mip
+// instead of the trilinear data sample, and no light volume.
+extern "C" int tbo_raymarch_octree(const tbo_volume* vol, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                                   int row_end, const void* const* mips, const int32_t odims[3], int octree_mip, float* out_rgba,
+                                   uint64_t* out_steps) {
+    CamF c;
+    make_cam(cam, world, c);
+    F3 cc, cd;
+    local_clip(vol, world, cc, cd);
+    OctreeTex t;
+    octree_dims(odims, t);
+    for (int m = 0; m < 4; ++m) t.mip[m] = (const uint16_t*) mips[m];
+    const int mip = octree_mip;
+    const bool mip_ok = mip >= 0 && mip < 4;
+    const int mq = mip_ok ? mip : 3;  // GetDimensions of a missing mip: nothing to march (Load returns 0 everywhere)
+    const float ow = (float) t.X[mq], oh = (float) t.Y[mq], od = (float) t.Z[mq];  // :135
+    const float od0 = (float) t.Z[0];                                              // OctreeDepthConst :132
+    const float dd = (float) vol->ddims[2];                                        // DataVolumeDepth :126
+    const int W = cam->width;
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : total)
+    for (int iy = row_begin; iy < row_end; ++iy)
+        for (int ix = 0; ix < W; ++ix) {
+            MarchSetup m = march_setup(c, cam, step_count, ix, iy);
+            F3 cur = m.cur;
+            const float ssw = 100.0f * m.ss;  // :119
+            float acc[4] = {0, 0, 0, 0};
+            uint64_t steps = 0;
+            auto sample = [&](F3 p) {
+                // :148 int3 VoxelPos = float3(...): truncation towards zero
+                int vx = (int) (p.x * ow), vy = (int) (p.y * oh), vz = (int) (((p.z * dd) / od0) * od);
+                float v = mip_ok ? t.load(mip, vx, vy, vz) : 0.0f;  // SampleWindowedVolumeOctreeStep, WindowedSampling.usf:47-52
+                float s[4];
+                sample_windowed_tf(v, ssw, vol->tf, vol->win, s);
+                float oma = 1.0f - acc[3];  // AccumulateLightEnergy
+                acc[0] = acc[0] + ((s[0] * s[3]) * oma);
+                acc[1] = acc[1] + ((s[1] * s[3]) * oma);
+                acc[2] = acc[2] + ((s[2] * s[3]) * oma);
+                acc[3] = acc[3] + (s[3] * oma);
+            };
+            int i = 0;
+            for (i = 0; i < m.max_steps; i++) {  // :138
+                cur = f3(cur.x + m.sv.x, cur.y + m.sv.y, cur.z + m.sv.z);
+                ++steps;
+                if (!clipped(cur, cc, cd)) {
+                    sample(cur);
+                    if (acc[3] > 0.95f) {  // :156-160
+                        acc[3] = 1.0f;
+                        break;
+                    }
+                }
+            }
+            if (i == m.max_steps && m.fin > 0.0f) {  // :165 — note: the opacity step stays StepSizeWorld here (:173), unlike the lit march
+                cur = f3(cur.x + m.sv.x * m.fin, cur.y + m.sv.y * m.fin, cur.z + m.sv.z * m.fin);
+                ++steps;
+                if (!clipped(cur, cc, cd)) sample(cur);
+            }
+            size_t p = 4 * ((size_t) (iy - row_begin) * W + ix);
+            out_rgba[p] = acc[0], out_rgba[p + 1] = acc[1], out_rgba[p + 2] = acc[2], out_rgba[p + 3] = acc[3];
+            total += steps;
+        }
+    if (out_steps) *out_steps = total;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Mandelbulb — SDFMarcher.usf
 // ------------------------------------------------------------------------------------------------------------
 namespace {
@@ -892,6 +1105,143 @@ extern "C" int tbo_mandelbulb_march(const tbrm_mandelbulb* mb, const tbrm_camera
         }
     if (out_iterations) *out_iterations = total;
     return 0;
+}
+
+// PerformMandelbulbRaymarchReturnNormal — SDFMarcher.usf:117-188: the same sphere tracing; a hit returns the normalised vector of three
+// SDF evaluations at positions offset BACKWARDS by DerivationDistance / Extent along each axis (:156-165 — not a true gradient), alpha 1.
+extern "C" int tbo_mandelbulb_march_normal(const tbrm_mandelbulb* mb, float derivation_distance, const tbrm_camera* cam, const tbrm_world* world,
+                                           int row_begin, int row_end, float* out_rgba, uint64_t* out_iterations) {
+    CamF c;
+    make_cam(cam, world, c);
+    const int W = cam->width;
+    uint64_t total = 0;
+    const float dd = derivation_distance / mb->extent;  // :138
+    auto actual = [&](F3 p) {                           // GetActualPosition :54-58
+        return f3(mb->center[0] + ((p.x - 0.5f) * mb->extent), mb->center[1] + ((p.y - 0.5f) * mb->extent), mb->center[2] + ((p.z - 0.5f) * mb->extent));
+    };
+#pragma omp parallel for schedule(dynamic, 2) reduction(+ : total)
+    for (int iy = row_begin; iy < row_end; ++iy)
+        for (int ix = 0; ix < W; ++ix) {
+            F3 V = camera_vector(c, ix, iy), cur, lcv;
+            float thick;
+            cube_setup(c, V, cur, thick, lcv);
+            float o[4] = {0, 0, 0, 0};
+            uint64_t iters = 0;
+            if (thick > 0.0f) {
+                F3 step = f3(lcv.x / mb->extent, lcv.y / mb->extent, lcv.z / mb->extent);  // :134
+                float dist = 0.0f;
+                bool done = false;
+                for (int s = 0; (float) s < mb->max_steps; s++) {  // :142
+                    dist = mandelbulb_sdf(actual(cur), mb->bailout, mb->power, (int) mb->max_iterations, iters);
+                    if (dist < mb->high_precision_eps) {  // :147
+                        F3 n;
+                        n.x = mandelbulb_sdf(actual(f3(cur.x - dd, cur.y - 0.0f, cur.z - 0.0f)), mb->bailout, mb->power, (int) mb->max_iterations, iters);
+                        n.y = mandelbulb_sdf(actual(f3(cur.x - 0.0f, cur.y - dd, cur.z - 0.0f)), mb->bailout, mb->power, (int) mb->max_iterations, iters);
+                        n.z = mandelbulb_sdf(actual(f3(cur.x - 0.0f, cur.y - 0.0f, cur.z - dd)), mb->bailout, mb->power, (int) mb->max_iterations, iters);
+                        n = normalize3(n);  // :166
+                        o[0] = n.x, o[1] = n.y, o[2] = n.z, o[3] = 1.0f;
+                        done = true;
+                        break;
+                    }
+                    cur = f3(cur.x + (dist * step.x), cur.y + (dist * step.y), cur.z + (dist * step.z));  // :171
+                    if (saturatef(cur.x) != cur.x || saturatef(cur.y) != cur.y || saturatef(cur.z) != cur.z) {  // :174-177
+                        done = true;
+                        break;
+                    }
+                }
+                if (!done && dist < mb->low_precision_eps) o[3] = 1.0f;  // :182-186 "return black normal"
+            }
+            size_t p = 4 * ((size_t) (iy - row_begin) * W + ix);
+            out_rgba[p] = o[0], out_rgba[p + 1] = o[1], out_rgba[p + 2] = o[2], out_rgba[p + 3] = o[3];
+            total += iters;
+        }
+    if (out_iterations) *out_iterations = total;
+    return 0;
+}
+
+// CalculateMandelbulbSDF.usf:24-65 dispatched by CalculateMandelbulbSDF_RenderThread (FractalShaders.cpp:41-70): per voxel of the volume
+// texture (PF_G16 in the reference, FractalVolume.cpp:166) the distance estimate with 50 iterations and Bailout = Extent, divided by Extent.
+// out_fmt: TBRM_FMT_G16 (UNORM16 store, as the reference) or TBRM_FMT_R32F (the unquantised value).
+extern "C" int tbo_mandelbulb_sdf(const int32_t dims[3], const float center[3], float extent, float power, int out_fmt, void* out,
+                                  uint64_t* out_iterations) {
+    if (!(extent > 0.0f)) return 0;  // EnqueueRenderCommand_CalculateMandelbulbSDF :28-31
+    uint64_t total = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total)
+    for (int z = 0; z < dims[2]; ++z)
+        for (int y = 0; y < dims[1]; ++y)
+            for (int x = 0; x < dims[0]; ++x) {
+                F3 uvw = f3((float) x / (float) dims[0], (float) y / (float) dims[1], (float) z / (float) dims[2]);  // :58 (no +0.5)
+                F3 n = f3(uvw.x - 0.5f, uvw.y - 0.5f, uvw.z - 0.5f);
+                F3 co = f3(center[0] + (n.x * extent), center[1] + (n.y * extent), center[2] + (n.z * extent));
+                uint64_t iters = 0;
+                float v = mandelbulb_sdf(co, extent, power, 50, iters) / extent;  // :26-27, :63
+                size_t i = (size_t) x + (size_t) dims[0] * ((size_t) y + (size_t) dims[1] * (size_t) z);
+                if (out_fmt == TBRM_FMT_G16)
+                    ((uint16_t*) out)[i] = quant16(v);
+                else
+                    ((float*) out)[i] = v;
+                total += iters;
+            }
+    if (out_iterations) *out_iterations = total;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// volume ingest — SURVEY.md §8(f) row 3
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+// UVolumeTextureToolkit::ConvertArrayToNormalizedArray<InType, OutType> — TextureUtilities.h:103-149. Notes that follow the reference:
+// InMax starts at numeric_limits<InType>::min(), which for float is the smallest POSITIVE normal (:111); the float -> OutType
+// conversion truncates (:142); a constant volume divides 0 by 0 — the NaN converts to 0 on x86 (policy; undefined in C++).
+template <typename In, typename Out>
+void normalize_array(const In* in, size_t n, Out* out, float& omin, float& omax) {
+    In mn = std::numeric_limits<In>::max(), mx = std::numeric_limits<In>::min();
+    for (size_t i = 0; i < n; i++) {
+        if (in[i] < mn) mn = in[i];
+        if (in[i] > mx) mx = in[i];
+    }
+    const float fmn = (float) mn, fmx = (float) mx;
+    const float range = fmx - fmn;
+    const float omaxf = (float) std::numeric_limits<Out>::max();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        float nrm = ((float) in[i] - fmn) / range;
+        float v = 0.0f + (nrm * omaxf);
+        out[i] = (v >= 0.0f && v < omaxf + 1.0f) ? (Out) v : (Out) 0;
+    }
+    omin = fmn, omax = fmx;
+}
+template <typename In>
+void to_float_array(const In* in, size_t n, float* out) {  // ConvertArrayToFloatTemplated — TextureUtilities.h:153-178
+    for (size_t i = 0; i < n; i++) out[i] = static_cast<float>(in[i]);
+}
+}  // namespace
+
+// UVolumeTextureToolkit::NormalizeArrayByFormat — TextureUtilities.cpp:304-327. fmt = EVolumeVoxelFormat (VolumeInfo.h:12-27):
+// 0 u8, 1 i8, 2 u16, 3 i16, 4 u32, 5 i32, 6 f32. 1-byte inputs normalise to u8, everything else to u16. Returns bytes per output voxel.
+extern "C" int tbo_normalize_array(int fmt, const void* in, uint64_t count, void* out, float* out_min, float* out_max) {
+    switch (fmt) {
+        case 0: normalize_array((const uint8_t*) in, count, (uint8_t*) out, *out_min, *out_max); return 1;
+        case 1: normalize_array((const int8_t*) in, count, (uint8_t*) out, *out_min, *out_max); return 1;
+        case 2: normalize_array((const uint16_t*) in, count, (uint16_t*) out, *out_min, *out_max); return 2;
+        case 3: normalize_array((const int16_t*) in, count, (uint16_t*) out, *out_min, *out_max); return 2;
+        case 4: normalize_array((const uint32_t*) in, count, (uint16_t*) out, *out_min, *out_max); return 2;
+        case 5: normalize_array((const int32_t*) in, count, (uint16_t*) out, *out_min, *out_max); return 2;
+        case 6: normalize_array((const float*) in, count, (uint16_t*) out, *out_min, *out_max); return 2;
+        default: return 0;
+    }
+}
+// UVolumeTextureToolkit::ConvertArrayToFloat — TextureUtilities.cpp:329-350 (a float input is not converted: returns 1)
+extern "C" int tbo_convert_to_float(int fmt, const void* in, uint64_t count, float* out) {
+    switch (fmt) {
+        case 0: to_float_array((const uint8_t*) in, count, out); return 0;
+        case 1: to_float_array((const int8_t*) in, count, out); return 0;
+        case 2: to_float_array((const uint16_t*) in, count, out); return 0;
+        case 3: to_float_array((const int16_t*) in, count, out); return 0;
+        case 4: to_float_array((const uint32_t*) in, count, out); return 0;
+        case 5: to_float_array((const int32_t*) in, count, out); return 0;
+        default: return 1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -66,6 +66,18 @@ int tbo_raymarch_lit(const tbo_volume* vol, const tbrm_camera* cam, const tbrm_w
                      int row_end, float* out_rgba, uint64_t* out_steps, uint8_t* near_gate);
 int tbo_mandelbulb_march(const tbrm_mandelbulb* mb, const tbrm_camera* cam, const tbrm_world* world, int row_begin, int row_end,
                          float* out_xy, uint64_t* out_iterations);
+/* the other materials, the octree, the Mandelbulb variants, volume ingest */
+int tbo_raymarch_intensity(const tbo_volume* vol, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                           int row_end, float* out_rgba, uint64_t* out_steps);
+int tbo_generate_octree(const void* data, const int32_t ddims[3], int data_fmt, const int32_t odims[3], void* const* mips);
+int tbo_raymarch_octree(const tbo_volume* vol, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                        int row_end, const void* const* mips, const int32_t odims[3], int octree_mip, float* out_rgba, uint64_t* out_steps);
+int tbo_mandelbulb_march_normal(const tbrm_mandelbulb* mb, float derivation_distance, const tbrm_camera* cam, const tbrm_world* world,
+                                int row_begin, int row_end, float* out_rgba, uint64_t* out_iterations);
+int tbo_mandelbulb_sdf(const int32_t dims[3], const float center[3], float extent, float power, int out_fmt, void* out,
+                       uint64_t* out_iterations);
+int tbo_normalize_array(int fmt, const void* in, uint64_t count, void* out, float* out_min, float* out_max);
+int tbo_convert_to_float(int fmt, const void* in, uint64_t count, float* out);
 int tbo_synth_volume_u8(int kind, const int32_t dims[3], uint32_t seed, uint8_t* out);
 float tbo_det_pow(float x, float y);
 float tbo_round_to_half(float x);

@@ -107,7 +107,83 @@ def shaders_case():
     return out
 
 
-CASES = {"ref_hostmath": hostmath_case, "ref_shaders": shaders_case}
+MATERIAL_DIMS = [(20, 9, 5), (32, 40, 24)]
+MATERIAL_WINDOWS = {"ct": (0.45, 0.5, True, False), "full": (0.5, 1.0, True, True)}
+MATERIAL_WORLDS = {"identity": synth.identity_world, "clipped": synth.clipped_world}
+MANDELBULB_VIEW = (32, 24)
+SDF_CASE = dict(dims=(20, 16, 12), center=(0.1, 0.0, -0.05), extent=2.4, power=8.0)
+
+
+def material_camera():
+    return synth.benchmark_camera(40, 24, jitter=True, frame=2)
+
+
+def mandelbulb_params():
+    from tbraymarcherplugin_b200.raymarch_utils import FMandelbulbParameters
+    return FMandelbulbParameters(MaxSteps=64.0, MaxIterations=8.0)
+
+
+def materials_case():
+    """The reference's GenerateOctreeShader.usf, PerformWindowedIntensityRaymarch, PerformWindowedRaymarchOctree, SDFMarcher.usf (distance and
+    normal variants) and CalculateMandelbulbSDF.usf, compiled for the CPU."""
+    import oracle
+    from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters
+    tf = oracle.prepare_tf(synth.soft_ct_curve())
+    out = {}
+    for dims in MATERIAL_DIMS:
+        tag = "x".join(map(str, dims))
+        data = synth.perlin_ct_volume(dims)
+        mips = refpin.generate_octree(data)
+        for m, a in enumerate(mips):
+            out[f"octree_{tag}_mip{m}"] = a
+        for wname, wv in MATERIAL_WINDOWS.items():
+            for world_name, mkw in MATERIAL_WORLDS.items():
+                vol = refpin.RefVolume(data, tf, FWindowingParameters(*wv))
+                out[f"intensity_{tag}_{wname}_{world_name}"] = vol.raymarch(1, material_camera(), mkw(), 40.0)
+                for mip in (0, 2):
+                    out[f"octree_march_{tag}_{wname}_{world_name}_mip{mip}"] = vol.raymarch(2, material_camera(), mkw(), 40.0, octree=mips, octree_mip=mip)
+    cam = synth.benchmark_camera(*MANDELBULB_VIEW, jitter=False)
+    out["mandelbulb_distance"] = refpin.mandelbulb_march(0, mandelbulb_params(), cam, synth.identity_world())
+    out["mandelbulb_normal"] = refpin.mandelbulb_march(1, mandelbulb_params(), cam, synth.identity_world(), 0.01)
+    out["mandelbulb_sdf_g16"] = refpin.mandelbulb_sdf(g16=True, **SDF_CASE)
+    out["mandelbulb_sdf_r32f"] = refpin.mandelbulb_sdf(g16=False, **SDF_CASE)
+    return out
+
+
+def ingest_inputs():
+    """One array per EVolumeVoxelFormat: random values plus the type's extremes for the narrow types."""
+    rng = np.random.default_rng(77)
+    arrays = {}
+    for fmt, dt in refpin.VOXEL_DTYPES.items():
+        if fmt == 6:
+            a = (rng.standard_normal(600) * 1500.0).astype(np.float32)
+        else:
+            info = np.iinfo(dt)
+            a = rng.integers(max(info.min, -40000), min(info.max, 90000), 600, endpoint=True).astype(dt)
+            if np.dtype(dt).itemsize == 1:
+                a[:2] = (info.min, info.max)
+        arrays[fmt] = a
+    arrays[16] = (-np.abs(rng.standard_normal(300)) - 1.0).astype(np.float32)  # all-negative floats: InMax stays FLT_MIN (TextureUtilities.h:111)
+    return arrays
+
+
+def ingest_case():
+    """UVolumeTextureToolkit::NormalizeArrayByFormat / ConvertArrayToFloat and FVolumeInfo::Normalize* of the reference (SURVEY.md §8(f) row 3)."""
+    out = {}
+    for key, a in ingest_inputs().items():
+        fmt = key % 10
+        n, lo, hi = refpin.normalize_array(fmt, a)
+        out[f"in_{key}"], out[f"normalized_{key}"], out[f"minmax_{key}"] = a, n, np.array([lo, hi], np.float32)
+        if fmt != 6:
+            out[f"float_{key}"] = refpin.convert_to_float(fmt, a)
+    vals = np.array([-1000.0, 0.0, 37.5, 3000.0, 1e-3], np.float32)
+    out["info_values"] = vals
+    out["info_maps"] = np.array([[refpin.volume_info_map(w, True, -1000.0, 3000.0, float(v)) for v in vals] for w in range(4)], np.float32)
+    out["info_maps_raw"] = np.array([[refpin.volume_info_map(w, False, -1000.0, 3000.0, float(v)) for v in vals] for w in range(4)], np.float32)
+    return out
+
+
+CASES = {"ref_hostmath": hostmath_case, "ref_shaders": shaders_case, "ref_materials": materials_case, "ref_ingest": ingest_case}
 
 if __name__ == "__main__":
     for name, fn in CASES.items():

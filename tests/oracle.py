@@ -179,3 +179,95 @@ def sample_windowed_tf(value, step, tf, windowing: FWindowingParameters) -> np.n
     w = windowing.to_c()
     lib().tbo_sample_windowed_tf(value, step, t.ctypes.data_as(C.POINTER(C.c_float)), C.byref(w), out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
+
+
+# ---- SURVEY.md §8(f) rows 2-4 -------------------------------------------------------------------------------------------------------
+def _octree_args(mips):
+    return (C.c_void_p * 4)(*[m.ctypes.data for m in mips]), (C.c_int32 * 3)(*mips[0].shape[::-1])
+
+
+def octree_dims(ddims):
+    """FMath::RoundUpToPowerOfTwo per side (RaymarchVolume.cpp:876-877)."""
+    return tuple(1 << max(0, int(d) - 1).bit_length() for d in ddims)
+
+
+def generate_octree(data: np.ndarray):
+    """GenerateOctreeShader.usf: returns the 4 UNORM16 mips (z, y, x ordered arrays)."""
+    d = np.ascontiguousarray(data)
+    Z, Y, X = d.shape
+    od = octree_dims((X, Y, Z))
+    mips = [np.zeros(tuple(max(1, s >> m) for s in od[::-1]), np.uint16) for m in range(4)]
+    ptrs, odims = _octree_args(mips)
+    f = lib().tbo_generate_octree
+    f.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_void_p]
+    f(d.ctypes.data, (C.c_int32 * 3)(X, Y, Z), _FMT[d.dtype], odims, ptrs)
+    return mips
+
+
+def raymarch_intensity(vol: OracleVolume, cam: FCamera, world: FRaymarchWorldParameters, steps: float, rows=None):
+    r0, r1 = rows if rows else (0, cam.Height)
+    out = np.empty((r1 - r0, cam.Width, 4), np.float32)
+    n = C.c_uint64(0)
+    v, c, w = vol.c(), cam.to_c(), world.to_c()
+    f = lib().tbo_raymarch_intensity
+    f.argtypes = [C.POINTER(Volume), C.POINTER(_capi.Camera), C.POINTER(_capi.World), C.c_float, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    f(C.byref(v), C.byref(c), C.byref(w), float(steps), r0, r1, out.ctypes.data, C.byref(n))
+    return out, int(n.value)
+
+
+def raymarch_octree(vol: OracleVolume, cam: FCamera, world: FRaymarchWorldParameters, steps: float, mips, octree_mip: int = 0, rows=None):
+    r0, r1 = rows if rows else (0, cam.Height)
+    out = np.empty((r1 - r0, cam.Width, 4), np.float32)
+    n = C.c_uint64(0)
+    v, c, w = vol.c(), cam.to_c(), world.to_c()
+    ptrs, odims = _octree_args(mips)
+    f = lib().tbo_raymarch_octree
+    f.argtypes = [C.POINTER(Volume), C.POINTER(_capi.Camera), C.POINTER(_capi.World), C.c_float, C.c_int, C.c_int, C.c_void_p,
+                  C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    f(C.byref(v), C.byref(c), C.byref(w), float(steps), r0, r1, ptrs, odims, int(octree_mip), out.ctypes.data, C.byref(n))
+    return out, int(n.value)
+
+
+def mandelbulb_normal(params: FMandelbulbParameters, derivation_distance: float, cam: FCamera, world: FRaymarchWorldParameters, rows=None):
+    r0, r1 = rows if rows else (0, cam.Height)
+    out = np.empty((r1 - r0, cam.Width, 4), np.float32)
+    n = C.c_uint64(0)
+    m, c, w = params.to_c(), cam.to_c(), world.to_c()
+    f = lib().tbo_mandelbulb_march_normal
+    f.argtypes = [C.POINTER(_capi.Mandelbulb), C.c_float, C.POINTER(_capi.Camera), C.POINTER(_capi.World), C.c_int, C.c_int, C.c_void_p,
+                  C.POINTER(C.c_uint64)]
+    f(C.byref(m), float(derivation_distance), C.byref(c), C.byref(w), r0, r1, out.ctypes.data, C.byref(n))
+    return out, int(n.value)
+
+
+def mandelbulb_sdf(dims, center=(0.0, 0.0, 0.0), extent: float = 2.0, power: float = 8.0, g16: bool = True):
+    """CalculateMandelbulbSDF.usf over a dims = (X, Y, Z) volume: UNORM16 like the reference's PF_G16 texture, or raw float32."""
+    out = np.zeros(tuple(dims)[::-1], np.uint16 if g16 else np.float32)
+    n = C.c_uint64(0)
+    f = lib().tbo_mandelbulb_sdf
+    f.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    f((C.c_int32 * 3)(*dims), (C.c_float * 3)(*center), float(extent), float(power), 1 if g16 else 2, out.ctypes.data, C.byref(n))
+    return out, int(n.value)
+
+
+# EVolumeVoxelFormat (VolumeInfo.h:12-27) -> numpy
+VOXEL_DTYPES = {0: np.uint8, 1: np.int8, 2: np.uint16, 3: np.int16, 4: np.uint32, 5: np.int32, 6: np.float32}
+
+
+def normalize_array(fmt: int, arr: np.ndarray):
+    a = np.ascontiguousarray(arr, VOXEL_DTYPES[fmt])
+    out = np.empty(a.shape, np.uint8 if a.itemsize == 1 else np.uint16)
+    lo, hi = C.c_float(), C.c_float()
+    f = lib().tbo_normalize_array
+    f.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    assert f(fmt, a.ctypes.data, a.size, out.ctypes.data, C.byref(lo), C.byref(hi)) == out.itemsize
+    return out, lo.value, hi.value
+
+
+def convert_to_float(fmt: int, arr: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(arr, VOXEL_DTYPES[fmt])
+    out = np.empty(a.shape, np.float32)
+    f = lib().tbo_convert_to_float
+    f.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+    assert f(fmt, a.ctypes.data, a.size, out.ctypes.data) == 0
+    return out

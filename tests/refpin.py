@@ -138,3 +138,34 @@ class RefVolume(oracle.OracleVolume):
                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         f(material, C.byref(v), C.byref(cu), C.byref(w), float(steps), r0, r1, mips, odims, int(octree_mip), out.ctypes.data)
         return out
+
+
+def generate_octree(data: np.ndarray):
+    """The reference's GenerateOctreeShader.usf: returns the 4 UNORM16 mips."""
+    d = np.ascontiguousarray(data)
+    Z, Y, X = d.shape
+    od = oracle.octree_dims((X, Y, Z))
+    mips = [np.zeros(tuple(max(1, s >> m) for s in od[::-1]), np.uint16) for m in range(4)]
+    f = lib().tbref_generate_octree
+    f.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_void_p]
+    f(d.ctypes.data, (C.c_int32 * 3)(X, Y, Z), oracle._FMT[d.dtype], (C.c_int32 * 3)(*od), (C.c_void_p * 4)(*[m.ctypes.data for m in mips]))
+    return mips
+
+
+def mandelbulb_march(variant: int, params, cam, world, derivation_distance: float = 0.0, rows=None) -> np.ndarray:
+    """variant 0: PerformMandelbulbRaymarchReturnDistance (2 floats / pixel), 1: ...ReturnNormal (4 floats / pixel)."""
+    r0, r1 = rows if rows else (0, cam.Height)
+    out = np.empty((r1 - r0, cam.Width, 2 if variant == 0 else 4), np.float32)
+    m, cu = params.to_c(), camera_uniforms(cam, world)
+    f = lib().tbref_mandelbulb_march
+    f.argtypes = [C.c_int, C.POINTER(_capi.Mandelbulb), C.c_float, C.POINTER(CameraUniforms), C.c_int, C.c_int, C.c_void_p]
+    f(variant, C.byref(m), float(derivation_distance), C.byref(cu), r0, r1, out.ctypes.data)
+    return out
+
+
+def mandelbulb_sdf(dims, center=(0.0, 0.0, 0.0), extent: float = 2.0, power: float = 8.0, g16: bool = True) -> np.ndarray:
+    out = np.zeros(tuple(dims)[::-1], np.uint16 if g16 else np.float32)
+    f = lib().tbref_mandelbulb_sdf
+    f.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_void_p]
+    f((C.c_int32 * 3)(*dims), (C.c_float * 3)(*center), float(extent), float(power), 1 if g16 else 2, out.ctypes.data)
+    return out
