@@ -12,6 +12,12 @@
  *   PerformRaymarchCubeSetup                       Source/Raymarcher/Shaders/Private/RaymarchMaterialCommon.usf:23-69
  *   PerformWindowedLitRaymarch                     Source/Raymarcher/Shaders/Private/WindowedRaymarchMaterials.usf:36-96
  *   PerformMandelbulbRaymarchReturnDistance        Source/FractalMarcher/Shaders/Private/SDFMarcher.usf:61-112
+ * and, next to the path:
+ *   URaymarchUtils::GenerateOctree                 Source/Raymarcher/Public/Util/RaymarchUtils.h:45
+ *   PerformWindowedIntensityRaymarch / ...Octree   Source/Raymarcher/Shaders/Private/WindowedRaymarchMaterials.usf:99-242
+ *   PerformMandelbulbRaymarchReturnNormal          Source/FractalMarcher/Shaders/Private/SDFMarcher.usf:117-188
+ *   EnqueueRenderCommand_CalculateMandelbulbSDF    Source/FractalMarcher/Public/Rendering/FractalShaders.h
+ *   UMHDLoader / IVolumeLoader / UVolumeTextureToolkit::NormalizeArrayByFormat   Source/VolumeTextureToolkit
  *
  * Conventions
  *   - plain C, no torch / CUDA types in any signature; device pointers are passed as void*.
@@ -284,6 +290,86 @@ int tbrm_raymarch_interleaved_rows(int height, int block_rows, int first_block, 
 tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, const tbrm_camera* cam,
                                   const tbrm_world* world, int row_begin, int row_end, float* out_xy,
                                   int out_is_device, uint64_t* out_iterations);
+
+/* ---- the other materials and the octree -------------------------------------------- */
+/* URaymarchUtils::GenerateOctree (RaymarchUtils.cpp:94-102 -> GenerateOctreeForVolume_RenderThread, OctreeShaders.cpp:28-54): fills the
+ * octree volume of the resource set — sides = the data volume's rounded up to powers of two, 4 mips, UNORM16 (RaymarchVolume.cpp:873-877);
+ * mip 0 = data value (0 outside the data volume), mip m = max over 2x2x2 texels of mip m-1. Uploading a new data volume invalidates it. */
+tbrm_status tbrm_generate_octree(tbrm_resources* res);
+tbrm_status tbrm_octree_mip_dims(const tbrm_resources* res, int mip, int32_t dims[3]);
+tbrm_status tbrm_download_octree_mip(tbrm_resources* res, int mip, void* dst_host); /* uint16 texels, x fastest */
+/* PerformWindowedIntensityRaymarch (WindowedRaymarchMaterials.usf:187-242): the first unclipped sample of every ray, windowed to grey,
+ * alpha 1; (0,0,0,0) where nothing is hit. Same camera / row / output conventions as tbrm_raymarch_lit. */
+tbrm_status tbrm_raymarch_intensity(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                                    int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps);
+/* PerformWindowedRaymarchOctree (WindowedRaymarchMaterials.usf:99-183): the lit march's loop with a point load from octree mip
+ * `octree_mip` (0..3, ARaymarchVolume::OctreeVolumeMip) instead of the trilinear data sample, no light volume. Needs
+ * tbrm_generate_octree (TBRM_ERR_NOT_INITIALIZED otherwise). */
+tbrm_status tbrm_raymarch_octree(tbrm_resources* res, const tbrm_camera* cam, const tbrm_world* world, float step_count, int octree_mip,
+                                 int row_begin, int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps);
+
+/* ---- Mandelbulb variants -------------------------------------------------------------- */
+/* PerformMandelbulbRaymarchReturnNormal (SDFMarcher.usf:117-188): out[4*pixel] = (normal, 1) on a hit — the normalised vector of three
+ * SDF evaluations offset backwards by derivation_distance / extent per axis —, (0,0,0,1) for a low-precision hit, (0,0,0,0) for a miss. */
+tbrm_status tbrm_mandelbulb_march_normal(int device, const tbrm_mandelbulb* params, float derivation_distance, const tbrm_camera* cam,
+                                         const tbrm_world* world, int row_begin, int row_end, float* out_rgba, int out_is_device,
+                                         uint64_t* out_iterations);
+/* CalculateMandelbulbSDF (CalculateMandelbulbSDF.usf:24-65, FractalShaders.cpp:26-70): the distance estimate (50 iterations, bailout =
+ * extent) / extent for every voxel of a dims[0] x dims[1] x dims[2] volume whose voxel (x,y,z) sits at center + ((x,y,z)/dims - 0.5) *
+ * extent. out_fmt: TBRM_FMT_G16 (UNORM16, the reference's PF_G16 volume texture) or TBRM_FMT_R32F. extent <= 0: nothing happens. */
+tbrm_status tbrm_mandelbulb_sdf(int device, const int32_t dims[3], const float center[3], float extent, float power, tbrm_format out_fmt,
+                                void* dst, int dst_is_device, uint64_t* out_iterations);
+
+/* ---- volume ingest ------------------------------------------------------------------ */
+/* EVolumeVoxelFormat — Source/VolumeTextureToolkit/Public/VolumeAsset/VolumeInfo.h:12-27 */
+typedef enum tbrm_voxel_format {
+    TBRM_VOXEL_U8 = 0,
+    TBRM_VOXEL_I8 = 1,
+    TBRM_VOXEL_U16 = 2,
+    TBRM_VOXEL_I16 = 3,
+    TBRM_VOXEL_U32 = 4,
+    TBRM_VOXEL_I32 = 5,
+    TBRM_VOXEL_F32 = 6
+} tbrm_voxel_format;
+/* FVolumeInfo — VolumeInfo.h:56-141 */
+typedef struct tbrm_volume_info {
+    int32_t parse_ok;          /* bParseWasSuccessful */
+    int32_t dims[3];           /* Dimensions */
+    double spacing[3];         /* Spacing (mm) */
+    double world_dims[3];      /* WorldDimensions = Spacing * Dimensions */
+    int32_t original_format;   /* tbrm_voxel_format of the file */
+    int32_t actual_format;     /* after normalisation / float conversion (ConvertData, VolumeLoader.cpp:97-128) */
+    int32_t bytes_per_voxel;   /* of the file */
+    int32_t is_signed;
+    int32_t is_normalized;     /* bIsNormalized */
+    float min_value, max_value; /* MinValue / MaxValue of the original data (defaults -1000 / 3000) */
+    int32_t is_compressed;     /* a CompressedDataSize tag was present: the data file is zlib-compressed */
+    int64_t compressed_bytes;
+    char data_file[512];       /* DataFileName (relative to the header) */
+} tbrm_volume_info;
+/* UMHDLoader::ParseVolumeInfoFromHeader (MHDLoader.cpp:18-181) on the header's text. TBRM_ERR_INVALID_ARGUMENT + parse_ok = 0 when a
+ * required key (DimSize, ElementSpacing | ElementSize, ElementType, ElementDataFile) is missing or the element type is unknown. Host only. */
+tbrm_status tbrm_mhd_parse_header(const char* header_text, tbrm_volume_info* out);
+/* FVolumeInfo::NormalizeValue / DenormalizeValue / NormalizeRange / DenormalizeRange (VolumeInfo.cpp:18-55): window centre / width
+ * between the original value range and the normalised [0,1] texture. Host only. */
+float tbrm_volume_info_normalize_value(const tbrm_volume_info* info, float value);
+float tbrm_volume_info_denormalize_value(const tbrm_volume_info* info, float value);
+float tbrm_volume_info_normalize_range(const tbrm_volume_info* info, float range);
+float tbrm_volume_info_denormalize_range(const tbrm_volume_info* info, float range);
+/* UVolumeTextureToolkit::NormalizeArrayByFormat (TextureUtilities.cpp:304-327) on the GPU: min / max of `count` voxels of
+ * voxel_format, then every voxel mapped to the full range of uint8 (1-byte inputs) or uint16 (all others), truncating like the
+ * reference. src / dst: host or device memory. out_min / out_max: the original extremes (as floats). */
+tbrm_status tbrm_normalize_volume(int device, int voxel_format, const void* src, int src_is_device, uint64_t count, void* dst,
+                                  int dst_is_device, float* out_min, float* out_max);
+/* UVolumeTextureToolkit::ConvertArrayToFloat (TextureUtilities.cpp:329-350); TBRM_VOXEL_F32 input is rejected like there. */
+tbrm_status tbrm_convert_volume_to_float(int device, int voxel_format, const void* src, int src_is_device, uint64_t count, float* dst,
+                                         int dst_is_device);
+/* UMHDLoader::CreateVolumeFromFile (MHDLoader.cpp:183-227) up to the texture: parses `mhd_path`, loads the raw or zlib data file next
+ * to it, converts on the GPU (normalize: to G8 / G16 with min / max recorded in info; else convert_to_float: to R32F; else as stored)
+ * and creates a resource set whose data volume it is. Voxel formats with no texture format of the path (unnormalised 32-bit integers)
+ * return TBRM_ERR_UNSUPPORTED. */
+tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
+                                 tbrm_volume_info* info, tbrm_resources** out);
 
 /* ---- queue control ------------------------------------------------------------------------------------ */
 tbrm_status tbrm_flush(tbrm_resources* res); /* FlushRenderingCommands(): wait for the resource set's stream */

@@ -112,6 +112,25 @@ class LightPlan(C.Structure):
     ]
 
 
+class VolumeInfo(C.Structure):  # tbrm_volume_info = FVolumeInfo
+    _fields_ = [
+        ("parse_ok", C.c_int32),
+        ("dims", C.c_int32 * 3),
+        ("spacing", C.c_double * 3),
+        ("world_dims", C.c_double * 3),
+        ("original_format", C.c_int32),
+        ("actual_format", C.c_int32),
+        ("bytes_per_voxel", C.c_int32),
+        ("is_signed", C.c_int32),
+        ("is_normalized", C.c_int32),
+        ("min_value", C.c_float),
+        ("max_value", C.c_float),
+        ("is_compressed", C.c_int32),
+        ("compressed_bytes", C.c_int64),
+        ("data_file", C.c_char * 512),
+    ]
+
+
 # every symbol include/tbrm.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _I = C.c_int
@@ -167,6 +186,24 @@ PROTOTYPES = {
     "tbrm_raymarch_lit_interleaved": (_I, [_P, C.POINTER(Camera), C.POINTER(World), C.c_float, _I, _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
     "tbrm_raymarch_interleaved_rows": (_I, [_I, _I, _I, _I]),
     "tbrm_mandelbulb_march": (_I, [_I, C.POINTER(Mandelbulb), C.POINTER(Camera), C.POINTER(World), _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
+    "tbrm_generate_octree": (_I, [_P]),
+    "tbrm_octree_mip_dims": (_I, [_P, _I, C.POINTER(C.c_int32)]),
+    "tbrm_download_octree_mip": (_I, [_P, _I, _P]),
+    "tbrm_raymarch_intensity": (_I, [_P, C.POINTER(Camera), C.POINTER(World), C.c_float, _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
+    "tbrm_raymarch_octree": (_I, [_P, C.POINTER(Camera), C.POINTER(World), C.c_float, _I, _I, _I, _P, _I, C.POINTER(C.c_uint64)]),
+    "tbrm_mandelbulb_march_normal": (
+        _I,
+        [_I, C.POINTER(Mandelbulb), C.c_float, C.POINTER(Camera), C.POINTER(World), _I, _I, _P, _I, C.POINTER(C.c_uint64)],
+    ),
+    "tbrm_mandelbulb_sdf": (_I, [_I, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, C.c_float, _I, _P, _I, C.POINTER(C.c_uint64)]),
+    "tbrm_mhd_parse_header": (_I, [C.c_char_p, C.POINTER(VolumeInfo)]),
+    "tbrm_volume_info_normalize_value": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),
+    "tbrm_volume_info_denormalize_value": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),
+    "tbrm_volume_info_normalize_range": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),
+    "tbrm_volume_info_denormalize_range": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),
+    "tbrm_normalize_volume": (_I, [_I, _I, _P, _I, C.c_uint64, _P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "tbrm_convert_volume_to_float": (_I, [_I, _I, _P, _I, C.c_uint64, _P, _I]),
+    "tbrm_load_mhd_volume": (_I, [_I, C.c_char_p, _I, _I, _I, _I, C.POINTER(VolumeInfo), C.POINTER(_P)]),
     "tbrm_flush": (_I, [_P]),
     "tbrm_stream": (_P, [_P]),
     "tbrm_set_stream": (_I, [_P, _P]),

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtbrm.so"
-SOURCES = ["api.cu", "sweep.cu", "raymarch.cu", "mandelbulb.cu", "synth.cu"]
+SOURCES = ["api.cu", "sweep.cu", "raymarch.cu", "mandelbulb.cu", "synth.cu", "ingest.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [_nvcc(), "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    link = [_nvcc(), "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lz"]
     subprocess.run(link, check=True)
     return LIB_PATH
 

@@ -158,6 +158,40 @@ public:
         return tbrm_raymarch_lit(Resources.Handle, &Camera, &w, StepCount, 0, Camera.height, OutRGBA, 0, OutSteps) == TBRM_OK;
     }
 
+    // ---- the other materials, the octree, volume ingest ---------------------------------------------
+    /** Generates the octree acceleration volume of the resources. (RaymarchUtils.h:43-45) */
+    static void GenerateOctree(FBasicRaymarchRenderingResources& Resources) { tbrm_generate_octree(Resources.Handle); }
+
+    /** PerformWindowedIntensityRaymarch (WindowedRaymarchMaterials.usf:187-242), whole frame into host memory. */
+    static bool PerformWindowedIntensityRaymarch(const FBasicRaymarchRenderingResources& Resources, const tbrm_camera& Camera,
+                                                 const FRaymarchWorldParameters& WorldParameters, float StepCount, float* OutRGBA,
+                                                 uint64_t* OutSteps = nullptr) {
+        const tbrm_world w = ToC(WorldParameters);
+        return tbrm_raymarch_intensity(Resources.Handle, &Camera, &w, StepCount, 0, Camera.height, OutRGBA, 0, OutSteps) == TBRM_OK;
+    }
+
+    /** PerformWindowedRaymarchOctree (WindowedRaymarchMaterials.usf:99-183) on mip OctreeMip (ARaymarchVolume::OctreeVolumeMip). */
+    static bool PerformWindowedRaymarchOctree(const FBasicRaymarchRenderingResources& Resources, const tbrm_camera& Camera,
+                                              const FRaymarchWorldParameters& WorldParameters, float StepCount, uint32_t OctreeMip, float* OutRGBA,
+                                              uint64_t* OutSteps = nullptr) {
+        const tbrm_world w = ToC(WorldParameters);
+        return tbrm_raymarch_octree(Resources.Handle, &Camera, &w, StepCount, (int) OctreeMip, 0, Camera.height, OutRGBA, 0, OutSteps) == TBRM_OK;
+    }
+
+    /** UMHDLoader::CreateVolumeFromFile (MHDLoader.cpp:183-227) + InitializeRaymarchResources: header, raw / zlib data file, normalisation
+        or float conversion on the GPU, resources whose data volume it is. */
+    static bool CreateVolumeFromFile(FBasicRaymarchRenderingResources& Resources, const char* FileName, tbrm_volume_info& OutInfo,
+                                     bool bNormalize = true, bool bConvertToFloat = true, bool bLightVolume32Bit = false, int Device = 0) {
+        if (Resources.bIsInitialized) FreeRaymarchResources(Resources);
+        tbrm_resources* h = nullptr;
+        if (tbrm_load_mhd_volume(Device, FileName, bNormalize ? 1 : 0, bConvertToFloat ? 1 : 0, bLightVolume32Bit ? TBRM_FMT_R32F : TBRM_FMT_G8,
+                                 Resources.LightVolumeHalfResolution, &OutInfo, &h) != TBRM_OK)
+            return false;
+        Resources.Handle = h;
+        Resources.bIsInitialized = true;
+        return true;
+    }
+
     // ---- streaming (time-varying volumes): the engine streams texture updates while the render thread keeps drawing ------
     static bool SetDataVolumeAsync(FBasicRaymarchRenderingResources& Resources, const void* PinnedHostVolume) {
         return tbrm_upload_volume_async(Resources.Handle, PinnedHostVolume) == TBRM_OK;

@@ -54,6 +54,65 @@ static tbrm_status with_output(int device, cudaStream_t stream, void* dst, size_
     return TBRM_OK;
 }
 
+// runs `enqueue(d_out, d_counter)` on the per-thread stream, delivers `bytes` of output and the optional iteration count
+template <typename F>
+static tbrm_status mandelbulb_op(int device, void* dst, size_t bytes, int dst_is_device, uint64_t* out_iterations, F enqueue) {
+    if (tbrm_device_count() <= 0) {
+        set_last_error("no CUDA device visible");
+        return TBRM_ERR_NO_DEVICE;
+    }
+    TBRM_CUDA(cudaSetDevice(device));
+    unsigned long long* d_iters = nullptr;
+    if (out_iterations) {
+        TBRM_CUDA(cudaMalloc((void**) &d_iters, sizeof(unsigned long long)));
+        TBRM_CUDA(cudaMemsetAsync(d_iters, 0, sizeof(unsigned long long), cudaStreamPerThread));
+    }
+    tbrm_status s = with_output(device, cudaStreamPerThread, dst, bytes, dst_is_device, [&](void* d) { return enqueue(d, d_iters); });
+    if (s == TBRM_OK && out_iterations) {
+        unsigned long long h = 0;
+        cudaError_t e = cudaMemcpyAsync(&h, d_iters, sizeof(h), cudaMemcpyDeviceToHost, cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+        *out_iterations = h;
+        if (e != cudaSuccess) s = TBRM_ERR_CUDA;
+    }
+    if (s == TBRM_OK && dst_is_device && cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) s = TBRM_ERR_CUDA;
+    if (d_iters) cudaFree(d_iters);
+    return s;
+}
+
+// the conversions share: staging of a host source, the two scratch buffers, delivery to a host or device destination
+struct IngestBuffers {
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    void* d_partials = nullptr;
+    float* d_minmax = nullptr;
+    bool own_in = false, own_out = false;
+    ~IngestBuffers() {
+        if (own_in && d_in) cudaFree(d_in);
+        if (own_out && d_out) cudaFree(d_out);
+        if (d_partials) cudaFree(d_partials);
+        if (d_minmax) cudaFree(d_minmax);
+    }
+};
+
+static tbrm_status ingest_stage(IngestBuffers& b, const void* src, int src_is_device, size_t in_bytes, void* dst, int dst_is_device,
+                                size_t out_bytes) {
+    if (src_is_device) {
+        b.d_in = const_cast<void*>(src);
+    } else {
+        TBRM_CUDA(cudaMalloc(&b.d_in, in_bytes));
+        b.own_in = true;
+        TBRM_CUDA(cudaMemcpyAsync(b.d_in, src, in_bytes, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    }
+    if (dst_is_device) {
+        b.d_out = dst;
+    } else {
+        TBRM_CUDA(cudaMalloc(&b.d_out, out_bytes));
+        b.own_out = true;
+    }
+    return TBRM_OK;
+}
+
 extern "C" {
 
 int tbrm_abi_version(void) { return TBRM_ABI_VERSION; }
@@ -164,6 +223,8 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     if (r->data_yzx) cudaFree(r->data_yzx);
     if (r->tables) cudaFree(r->tables);
     if (r->bricks) cudaFree(r->bricks);
+    for (int m = 0; m < 4; ++m)
+        if (r->octree[m]) cudaFree(r->octree[m]);
 
     if (r->flags) cudaFree(r->flags);
     for (auto& axis : r->rw)
@@ -195,6 +256,7 @@ tbrm_status tbrm_upload_volume(tbrm_resources* r, const void* src, int src_is_de
     r->data_ready = true;
     r->data_yzx_valid = false;
     r->bricks_valid = false;
+    r->octree_valid = false;  // bRequestedOctreeRebuild (RaymarchVolume.cpp:553-554)
     return TBRM_OK;
 }
 
@@ -244,6 +306,7 @@ tbrm_status tbrm_present_volume(tbrm_resources* r) {
     r->data_ready = true;
     r->data_yzx_valid = false;
     r->bricks_valid = false;
+    r->octree_valid = false;  // bRequestedOctreeRebuild (RaymarchVolume.cpp:553-554)
     return TBRM_OK;
 }
 
@@ -259,6 +322,7 @@ tbrm_status tbrm_bind_volume_device(tbrm_resources* r, const void* dptr) {
     r->data_ready = true;
     r->data_yzx_valid = false;
     r->bricks_valid = false;
+    r->octree_valid = false;  // bRequestedOctreeRebuild (RaymarchVolume.cpp:553-554)
     return TBRM_OK;
 }
 
@@ -773,6 +837,248 @@ tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, con
     }
     if (d_iters) cudaFree(d_iters);
     return s;
+}
+
+// ---- the other materials and the octree ----------------------------------------------
+tbrm_status tbrm_generate_octree(tbrm_resources* r) {
+    // URaymarchUtils::GenerateOctree enqueues without checks (RaymarchUtils.cpp:94-102); the shader needs the data volume
+    if (!r || !r->data || !r->data_ready) return TBRM_ERR_NOT_INITIALIZED;
+    TBRM_CUDA(cudaSetDevice(r->device));
+    TBRM_CUDA(generate_octree(*r));
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_octree_mip_dims(const tbrm_resources* r, int mip, int32_t dims[3]) {
+    TBRM_REQUIRE(r && dims && mip >= 0 && mip < 4, "tbrm_octree_mip_dims: bad argument (4 mips)");
+    octree_mip_dims(*r, mip, dims);
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_download_octree_mip(tbrm_resources* r, int mip, void* dst_host) {
+    TBRM_REQUIRE(r && dst_host && mip >= 0 && mip < 4, "tbrm_download_octree_mip: bad argument (4 mips)");
+    if (!r->octree_valid) return TBRM_ERR_NOT_INITIALIZED;
+    TBRM_CUDA(cudaSetDevice(r->device));
+    int32_t d[3];
+    octree_mip_dims(*r, mip, d);
+    TBRM_CUDA(cudaMemcpyAsync(dst_host, r->octree[mip], (size_t) d[0] * d[1] * d[2] * sizeof(uint16_t), cudaMemcpyDeviceToHost, r->stream));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    return TBRM_OK;
+}
+
+// material: 1 intensity, 2 octree
+static tbrm_status raymarch_material_impl(tbrm_resources* r, int material, const tbrm_camera* cam, const tbrm_world* world, float step_count,
+                                          int octree_mip, int row_begin, int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    if (!r || !r->data || !r->data_ready) return TBRM_ERR_NOT_INITIALIZED;
+    if (material == 2 && (!r->tf_ready || !r->octree_valid)) return TBRM_ERR_NOT_INITIALIZED;
+    TBRM_REQUIRE(world && out_rgba, "raymarch: null argument");
+    TBRM_REQUIRE(camera_valid(cam), "raymarch: invalid camera");
+    TBRM_REQUIRE(step_count > 0.0f, "raymarch: step count must be positive");
+    TBRM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= cam->height, "raymarch: bad row range");
+    TBRM_REQUIRE(material != 2 || (octree_mip >= 0 && octree_mip < 4), "tbrm_raymarch_octree: the octree has mips 0..3");
+    if (row_begin == row_end) {
+        if (out_steps) *out_steps = 0;
+        return TBRM_OK;
+    }
+    TBRM_CUDA(cudaSetDevice(r->device));
+    host::CameraUniforms cu;
+    host::plan_camera(*cam, *world, cu);
+    float cc[3], cd[3];
+    host::plan_clip(*world, cc, cd);
+    unsigned long long* d_steps = out_steps ? r->counters : nullptr;
+    if (d_steps) TBRM_CUDA(cudaMemsetAsync(d_steps, 0, sizeof(unsigned long long), r->stream));
+    const size_t bytes = (size_t) cam->width * (row_end - row_begin) * 4 * sizeof(float);
+    tbrm_status s = with_output(r->device, r->stream, out_rgba, bytes, out_is_device, [&](void* d) {
+        return material == 1 ? raymarch_intensity(*r, cu, cc, cd, step_count, row_begin, row_end, (float*) d, d_steps)
+                             : raymarch_octree(*r, cu, cc, cd, step_count, octree_mip, row_begin, row_end, (float*) d, d_steps);
+    });
+    if (s != TBRM_OK) return s;
+    if (out_steps) {
+        unsigned long long h = 0;
+        TBRM_CUDA(cudaMemcpyAsync(&h, d_steps, sizeof(h), cudaMemcpyDeviceToHost, r->stream));
+        TBRM_CUDA(cudaStreamSynchronize(r->stream));
+        *out_steps = h;
+    }
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_raymarch_intensity(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
+                                    int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    return raymarch_material_impl(r, 1, cam, world, step_count, 0, row_begin, row_end, out_rgba, out_is_device, out_steps);
+}
+
+tbrm_status tbrm_raymarch_octree(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int octree_mip,
+                                 int row_begin, int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    return raymarch_material_impl(r, 2, cam, world, step_count, octree_mip, row_begin, row_end, out_rgba, out_is_device, out_steps);
+}
+
+// ---- Mandelbulb variants ---------------------------------------------------------------
+tbrm_status tbrm_mandelbulb_march_normal(int device, const tbrm_mandelbulb* params, float derivation_distance, const tbrm_camera* cam,
+                                         const tbrm_world* world, int row_begin, int row_end, float* out_rgba, int out_is_device,
+                                         uint64_t* out_iterations) {
+    TBRM_REQUIRE(params && world && out_rgba, "tbrm_mandelbulb_march_normal: null argument");
+    TBRM_REQUIRE(camera_valid(cam), "tbrm_mandelbulb_march_normal: invalid camera");
+    TBRM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= cam->height, "tbrm_mandelbulb_march_normal: bad row range");
+    TBRM_REQUIRE(params->extent != 0.0f, "tbrm_mandelbulb_march_normal: extent must be non-zero");
+    if (row_begin == row_end) {
+        if (out_iterations) *out_iterations = 0;
+        return TBRM_OK;
+    }
+    host::CameraUniforms cu;
+    host::plan_camera(*cam, *world, cu);
+    const size_t bytes = (size_t) cam->width * (row_end - row_begin) * 4 * sizeof(float);
+    return mandelbulb_op(device, out_rgba, bytes, out_is_device, out_iterations, [&](void* d, unsigned long long* it) {
+        return mandelbulb_march_normal(cudaStreamPerThread, *params, derivation_distance, cu, row_begin, row_end, (float*) d, it);
+    });
+}
+
+tbrm_status tbrm_mandelbulb_sdf(int device, const int32_t dims[3], const float center[3], float extent, float power, tbrm_format out_fmt,
+                                void* dst, int dst_is_device, uint64_t* out_iterations) {
+    TBRM_REQUIRE(dims && center && dst, "tbrm_mandelbulb_sdf: null argument");
+    TBRM_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && dims[2] <= 65535, "tbrm_mandelbulb_sdf: bad dimensions");
+    TBRM_REQUIRE(out_fmt == TBRM_FMT_G16 || out_fmt == TBRM_FMT_R32F, "tbrm_mandelbulb_sdf: output is G16 (the reference's texture) or R32F");
+    if (out_iterations) *out_iterations = 0;
+    if (!(extent > 0.0f)) return TBRM_OK;  // EnqueueRenderCommand_CalculateMandelbulbSDF: Extent <= 0 -> return (FractalShaders.cpp:28-31)
+    const size_t bytes = (size_t) dims[0] * dims[1] * dims[2] * (out_fmt == TBRM_FMT_G16 ? 2 : 4);
+    return mandelbulb_op(device, dst, bytes, dst_is_device, out_iterations, [&](void* d, unsigned long long* it) {
+        return mandelbulb_sdf_bake(cudaStreamPerThread, dims, center, extent, power, out_fmt == TBRM_FMT_G16, d, it);
+    });
+}
+
+// ---- volume ingest -------------------------------------------------------------------
+tbrm_status tbrm_mhd_parse_header(const char* header_text, tbrm_volume_info* out) {
+    TBRM_REQUIRE(header_text && out, "tbrm_mhd_parse_header: null argument");
+    if (!mhd_parse_header(header_text, *out)) {
+        set_last_error("tbrm_mhd_parse_header: DimSize, ElementSpacing | ElementSize, ElementType (MET_*) and ElementDataFile are required");
+        return TBRM_ERR_INVALID_ARGUMENT;
+    }
+    return TBRM_OK;
+}
+
+// FVolumeInfo::NormalizeValue ... DenormalizeRange — VolumeInfo.cpp:18-55
+float tbrm_volume_info_normalize_value(const tbrm_volume_info* i, float v) {
+    return (!i || !i->is_normalized) ? v : ((v - i->min_value) / (i->max_value - i->min_value));
+}
+float tbrm_volume_info_denormalize_value(const tbrm_volume_info* i, float v) {
+    return (!i || !i->is_normalized) ? v : ((v * (i->max_value - i->min_value)) + i->min_value);
+}
+float tbrm_volume_info_normalize_range(const tbrm_volume_info* i, float v) {
+    return (!i || !i->is_normalized) ? v : (v / (i->max_value - i->min_value));
+}
+float tbrm_volume_info_denormalize_range(const tbrm_volume_info* i, float v) {
+    return (!i || !i->is_normalized) ? v : (v * (i->max_value - i->min_value));
+}
+
+tbrm_status tbrm_normalize_volume(int device, int voxel_format, const void* src, int src_is_device, uint64_t count, void* dst,
+                                  int dst_is_device, float* out_min, float* out_max) {
+    TBRM_REQUIRE(src && dst && count > 0, "tbrm_normalize_volume: null argument or empty volume");
+    const int ib = voxel_format_bytes(voxel_format);
+    TBRM_REQUIRE(ib > 0, "tbrm_normalize_volume: unknown voxel format");
+    if (tbrm_device_count() <= 0) {
+        set_last_error("tbrm_normalize_volume: no CUDA device visible");
+        return TBRM_ERR_NO_DEVICE;
+    }
+    TBRM_CUDA(cudaSetDevice(device));
+    const size_t ob = ib == 1 ? 1 : 2;
+    IngestBuffers b;
+    tbrm_status s = ingest_stage(b, src, src_is_device, (size_t) count * ib, dst, dst_is_device, (size_t) count * ob);
+    if (s != TBRM_OK) return s;
+    TBRM_CUDA(cudaMalloc(&b.d_partials, ingest_partials_bytes()));
+    TBRM_CUDA(cudaMalloc((void**) &b.d_minmax, 2 * sizeof(float)));
+    TBRM_CUDA(ingest_normalize(cudaStreamPerThread, voxel_format, b.d_in, (size_t) count, b.d_out, b.d_partials, b.d_minmax));
+    float mm[2] = {0.0f, 0.0f};
+    TBRM_CUDA(cudaMemcpyAsync(mm, b.d_minmax, sizeof(mm), cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    if (!dst_is_device) TBRM_CUDA(cudaMemcpyAsync(dst, b.d_out, (size_t) count * ob, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    TBRM_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    if (out_min) *out_min = mm[0];
+    if (out_max) *out_max = mm[1];
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_convert_volume_to_float(int device, int voxel_format, const void* src, int src_is_device, uint64_t count, float* dst,
+                                         int dst_is_device) {
+    TBRM_REQUIRE(src && dst && count > 0, "tbrm_convert_volume_to_float: null argument or empty volume");
+    const int ib = voxel_format_bytes(voxel_format);
+    TBRM_REQUIRE(ib > 0 && voxel_format != TBRM_VOXEL_F32, "tbrm_convert_volume_to_float: integer voxel formats only (ConvertArrayToFloat)");
+    if (tbrm_device_count() <= 0) {
+        set_last_error("tbrm_convert_volume_to_float: no CUDA device visible");
+        return TBRM_ERR_NO_DEVICE;
+    }
+    TBRM_CUDA(cudaSetDevice(device));
+    IngestBuffers b;
+    tbrm_status s = ingest_stage(b, src, src_is_device, (size_t) count * ib, dst, dst_is_device, (size_t) count * sizeof(float));
+    if (s != TBRM_OK) return s;
+    TBRM_CUDA(ingest_to_float(cudaStreamPerThread, voxel_format, b.d_in, (size_t) count, (float*) b.d_out));
+    if (!dst_is_device) TBRM_CUDA(cudaMemcpyAsync(dst, b.d_out, (size_t) count * sizeof(float), cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    TBRM_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
+                                 tbrm_volume_info* info, tbrm_resources** out) {
+    TBRM_REQUIRE(mhd_path && info && out, "tbrm_load_mhd_volume: null argument");
+    *out = nullptr;
+    std::string text;
+    {
+        FILE* f = std::fopen(mhd_path, "rb");
+        if (!f) {
+            set_last_error(std::string("tbrm_load_mhd_volume: cannot read ") + mhd_path);
+            return TBRM_ERR_INVALID_ARGUMENT;
+        }
+        char buf[4096];
+        size_t n;
+        while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+        std::fclose(f);
+    }
+    tbrm_status s = tbrm_mhd_parse_header(text.c_str(), info);
+    if (s != TBRM_OK) return s;
+    TBRM_REQUIRE(info->dims[0] > 0 && info->dims[1] > 0 && info->dims[2] > 0, "tbrm_load_mhd_volume: DimSize has a zero dimension");
+    // ConvertData (VolumeLoader.cpp:97-128) decides the texture format
+    const int of = info->original_format;
+    tbrm_format data_fmt;
+    if (normalize)
+        data_fmt = info->bytes_per_voxel > 1 ? TBRM_FMT_G16 : TBRM_FMT_G8;
+    else if (convert_to_float || of == TBRM_VOXEL_F32)
+        data_fmt = TBRM_FMT_R32F;
+    else if (info->bytes_per_voxel == 1)
+        data_fmt = TBRM_FMT_G8;   // VoxelFormatToPixelFormat: UnsignedChar / SignedChar -> PF_G8 (bits as stored)
+    else if (info->bytes_per_voxel == 2)
+        data_fmt = TBRM_FMT_G16;  // UnsignedShort / SignedShort -> PF_G16
+    else {
+        set_last_error("tbrm_load_mhd_volume: unnormalised 32-bit integer voxels map to PF_R32_SINT, which the path does not sample");
+        return TBRM_ERR_UNSUPPORTED;
+    }
+    std::string dir(mhd_path);
+    const size_t slash = dir.find_last_of("/\\");
+    dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+    std::vector<uint8_t> voxels;
+    std::string err;
+    if (!load_voxel_file(dir + "/" + info->data_file, *info, voxels, err)) {  // LoadRawDataFileFromInfo: FilePath + "/" + DataFileName
+        set_last_error("tbrm_load_mhd_volume: " + err);
+        return TBRM_ERR_INVALID_ARGUMENT;
+    }
+    s = tbrm_create(device, info->dims, data_fmt, light_fmt, half_res, out);
+    if (s != TBRM_OK) return s;
+    tbrm_resources* r = *out;
+    const uint64_t count = (uint64_t) r->data_voxels();
+    TBRM_CUDA(cudaMalloc(&r->data, (size_t) count * r->data_elem()));
+    r->data_owned = true;
+    if (normalize) {
+        s = tbrm_normalize_volume(device, of, voxels.data(), 0, count, r->data, 1, &info->min_value, &info->max_value);
+        info->is_normalized = 1;
+        info->actual_format = info->bytes_per_voxel > 1 ? TBRM_VOXEL_U16 : TBRM_VOXEL_U8;
+    } else if (convert_to_float && of != TBRM_VOXEL_F32) {
+        s = tbrm_convert_volume_to_float(device, of, voxels.data(), 0, count, (float*) r->data, 1);
+        info->actual_format = TBRM_VOXEL_F32;
+    } else {
+        s = cudaMemcpy(r->data, voxels.data(), voxels.size(), cudaMemcpyHostToDevice) == cudaSuccess ? TBRM_OK : TBRM_ERR_CUDA;
+    }
+    if (s != TBRM_OK) {
+        tbrm_destroy(r);
+        *out = nullptr;
+        return s;
+    }
+    r->data_ready = true;
+    return TBRM_OK;
 }
 
 // ---- queue control ----------------------------------------------------------------------------------------

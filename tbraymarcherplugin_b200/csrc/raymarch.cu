@@ -692,3 +692,5 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
 }
 
 }  // namespace tbrm
+
+#include "materials.cuh"

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/tbrm.h"
 #include "host_plan.hpp"
@@ -66,6 +67,9 @@ struct tbrm_resources {
     bool data_yzx_valid = false;
     void* bricks = nullptr;  // raymarch: per-8^3-brick max of the data volume (exact empty-space skipping)
     bool bricks_valid = false;
+    // OctreeVolumeRenderTarget (RaymarchTypes.h:104-106): 4 UNORM16 mips, sides rounded up to powers of two (RaymarchVolume.cpp:873-877)
+    void* octree[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool octree_valid = false;
     void* tables = nullptr;
     size_t tables_bytes = 0;
 
@@ -116,10 +120,30 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
                          unsigned long long* d_steps);
 cudaError_t ensure_bricks(tbrm_resources& r);  // brick max-grid: 1 byte per 8^3 brick (max over [8b, 8b+8] per axis)
 int raymarch_local_rows(int row_begin, int row_end, int row_block, int block_stride);
+// materials.cuh (part of raymarch.cu): octree generation, intensity and octree marches
+void octree_mip_dims(const tbrm_resources& r, int mip, int32_t dims[3]);
+cudaError_t generate_octree(tbrm_resources& r);
+cudaError_t raymarch_intensity(tbrm_resources& r, const host::CameraUniforms& cam, const float clip_center[3], const float clip_dir[3],
+                               float step_count, int row_begin, int row_end, float* d_out, unsigned long long* d_steps);
+cudaError_t raymarch_octree(tbrm_resources& r, const host::CameraUniforms& cam, const float clip_center[3], const float clip_dir[3],
+                            float step_count, int octree_mip, int row_begin, int row_end, float* d_out, unsigned long long* d_steps);
 
 // mandelbulb.cu
 cudaError_t mandelbulb_march(cudaStream_t stream, const tbrm_mandelbulb& mb, const host::CameraUniforms& cam, int row_begin,
                              int row_end, float* d_out, unsigned long long* d_iters);
+
+cudaError_t mandelbulb_march_normal(cudaStream_t stream, const tbrm_mandelbulb& mb, float derivation_distance, const host::CameraUniforms& cam,
+                                    int row_begin, int row_end, float* d_out, unsigned long long* d_iters);
+cudaError_t mandelbulb_sdf_bake(cudaStream_t stream, const int32_t dims[3], const float center[3], float extent, float power, int g16, void* d_out,
+                                unsigned long long* d_iters);
+
+// ingest.cu
+int voxel_format_bytes(int fmt);
+size_t ingest_partials_bytes();
+cudaError_t ingest_normalize(cudaStream_t stream, int fmt, const void* d_in, size_t n, void* d_out, void* d_partials, float* d_minmax);
+cudaError_t ingest_to_float(cudaStream_t stream, int fmt, const void* d_in, size_t n, float* d_out);
+bool mhd_parse_header(const std::string& text, tbrm_volume_info& out);
+bool load_voxel_file(const std::string& path, const tbrm_volume_info& info, std::vector<uint8_t>& voxels, std::string& err);
 
 // synth.cu
 cudaError_t synth_volume_u8(cudaStream_t stream, int kind, const int32_t dims[3], uint32_t seed, uint8_t* d_out);

@@ -423,6 +423,165 @@ class URaymarchUtils:
         return out, int(iters.value)
 
 
+    # ---- the other materials and the octree ----------------------------------------------
+    @staticmethod
+    def GenerateOctree(Resources: FBasicRaymarchRenderingResources) -> None:
+        """URaymarchUtils::GenerateOctree (RaymarchUtils.h:45): fills the 4-mip UNORM16 octree volume of the resource set."""
+        check(_capi.load().tbrm_generate_octree(Resources.handle))
+
+    @staticmethod
+    def ReadOctreeMip(Resources: FBasicRaymarchRenderingResources, Mip: int) -> np.ndarray:
+        d = (C.c_int32 * 3)()
+        check(_capi.load().tbrm_octree_mip_dims(Resources.handle, int(Mip), d))
+        out = np.empty((d[2], d[1], d[0]), dtype=np.uint16)
+        check(_capi.load().tbrm_download_octree_mip(Resources.handle, int(Mip), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    @staticmethod
+    def PerformWindowedIntensityRaymarch(Resources: FBasicRaymarchRenderingResources, Camera: FCamera, WorldParameters: FRaymarchWorldParameters,
+                                         StepCount: float, rows: Optional[Tuple[int, int]] = None):
+        """WindowedRaymarchMaterials.usf:187-242. Returns (rgba, executed_steps)."""
+        cam, world = Camera.to_c(), WorldParameters.to_c()
+        r0, r1 = rows if rows is not None else (0, Camera.Height)
+        steps = C.c_uint64(0)
+        out = np.empty((r1 - r0, Camera.Width, 4), dtype=np.float32)
+        check(_capi.load().tbrm_raymarch_intensity(Resources.handle, C.byref(cam), C.byref(world), float(StepCount), r0, r1,
+                                                   out.ctypes.data_as(C.c_void_p), 0, C.byref(steps)))
+        return out, int(steps.value)
+
+    @staticmethod
+    def PerformWindowedRaymarchOctree(Resources: FBasicRaymarchRenderingResources, Camera: FCamera, WorldParameters: FRaymarchWorldParameters,
+                                      StepCount: float, OctreeMip: int = 0, rows: Optional[Tuple[int, int]] = None):
+        """WindowedRaymarchMaterials.usf:99-183 (needs GenerateOctree). Returns (rgba, executed_steps)."""
+        cam, world = Camera.to_c(), WorldParameters.to_c()
+        r0, r1 = rows if rows is not None else (0, Camera.Height)
+        steps = C.c_uint64(0)
+        out = np.empty((r1 - r0, Camera.Width, 4), dtype=np.float32)
+        check(_capi.load().tbrm_raymarch_octree(Resources.handle, C.byref(cam), C.byref(world), float(StepCount), int(OctreeMip), r0, r1,
+                                                out.ctypes.data_as(C.c_void_p), 0, C.byref(steps)))
+        return out, int(steps.value)
+
+    # ---- Mandelbulb variants (SURVEY.md §8(f) row 4) ---------------------------------------------------------------
+    @staticmethod
+    def PerformMandelbulbRaymarchReturnNormal(Params: FMandelbulbParameters, DerivationDistance: float, Camera: FCamera,
+                                              WorldParameters: FRaymarchWorldParameters, rows: Optional[Tuple[int, int]] = None, device: int = 0):
+        """SDFMarcher.usf:117-188. Returns ((rows, W, 4) normal + alpha, SDF iterations)."""
+        cam, world, mb = Camera.to_c(), WorldParameters.to_c(), Params.to_c()
+        r0, r1 = rows if rows is not None else (0, Camera.Height)
+        iters = C.c_uint64(0)
+        out = np.empty((r1 - r0, Camera.Width, 4), dtype=np.float32)
+        check(_capi.load().tbrm_mandelbulb_march_normal(device, C.byref(mb), float(DerivationDistance), C.byref(cam), C.byref(world), r0, r1,
+                                                        out.ctypes.data_as(C.c_void_p), 0, C.byref(iters)))
+        return out, int(iters.value)
+
+    @staticmethod
+    def CalculateMandelbulbSDF(Dimensions: Sequence[int], Center: Vec3 = (0.0, 0.0, 0.0), Extent: float = 2.0, Power: float = 8.0,
+                               g16: bool = True, device: int = 0):
+        """EnqueueRenderCommand_CalculateMandelbulbSDF (FractalShaders.cpp:26-70). Returns ((Z, Y, X) volume, SDF iterations); the volume is
+        UNORM16 like the reference's PF_G16 texture, or float32."""
+        out = np.zeros(tuple(int(d) for d in Dimensions)[::-1], dtype=np.uint16 if g16 else np.float32)
+        iters = C.c_uint64(0)
+        check(_capi.load().tbrm_mandelbulb_sdf(device, (C.c_int32 * 3)(*map(int, Dimensions)), (C.c_float * 3)(*map(float, Center)), float(Extent),
+                                               float(Power), FMT_G16 if g16 else FMT_R32F, out.ctypes.data_as(C.c_void_p), 0, C.byref(iters)))
+        return out, int(iters.value)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# volume ingest (SURVEY.md §8(f) row 3): UMHDLoader / IVolumeLoader / UVolumeTextureToolkit of the VolumeTextureToolkit module
+# --------------------------------------------------------------------------------------------------------------
+# EVolumeVoxelFormat (VolumeInfo.h:12-27) <-> numpy
+VOXEL_DTYPES = {0: np.uint8, 1: np.int8, 2: np.uint16, 3: np.int16, 4: np.uint32, 5: np.int32, 6: np.float32}
+_VOXEL_OF_NP = {np.dtype(v): k for k, v in VOXEL_DTYPES.items()}
+
+
+class FVolumeInfo:
+    """FVolumeInfo (VolumeInfo.h:56-141) over the C struct."""
+
+    def __init__(self, c: Optional[_capi.VolumeInfo] = None):
+        self.c = c if c is not None else _capi.VolumeInfo()
+
+    bParseWasSuccessful = property(lambda self: bool(self.c.parse_ok))
+    Dimensions = property(lambda self: tuple(self.c.dims))
+    Spacing = property(lambda self: tuple(self.c.spacing))
+    WorldDimensions = property(lambda self: tuple(self.c.world_dims))
+    OriginalFormat = property(lambda self: int(self.c.original_format))
+    ActualFormat = property(lambda self: int(self.c.actual_format))
+    BytesPerVoxel = property(lambda self: int(self.c.bytes_per_voxel))
+    bIsSigned = property(lambda self: bool(self.c.is_signed))
+    bIsNormalized = property(lambda self: bool(self.c.is_normalized))
+    MinValue = property(lambda self: float(self.c.min_value))
+    MaxValue = property(lambda self: float(self.c.max_value))
+    bIsCompressed = property(lambda self: bool(self.c.is_compressed))
+    CompressedByteSize = property(lambda self: int(self.c.compressed_bytes))
+    DataFileName = property(lambda self: self.c.data_file.decode())
+
+    def NormalizeValue(self, v: float) -> float:
+        return float(_capi.load().tbrm_volume_info_normalize_value(C.byref(self.c), float(v)))
+
+    def DenormalizeValue(self, v: float) -> float:
+        return float(_capi.load().tbrm_volume_info_denormalize_value(C.byref(self.c), float(v)))
+
+    def NormalizeRange(self, v: float) -> float:
+        return float(_capi.load().tbrm_volume_info_normalize_range(C.byref(self.c), float(v)))
+
+    def DenormalizeRange(self, v: float) -> float:
+        return float(_capi.load().tbrm_volume_info_denormalize_range(C.byref(self.c), float(v)))
+
+
+class UMHDLoader:
+    @staticmethod
+    def ParseVolumeInfoFromHeaderText(text: str) -> FVolumeInfo:
+        """UMHDLoader::ParseVolumeInfoFromHeader (MHDLoader.cpp:18-181) on the header's text; bParseWasSuccessful tells the outcome."""
+        info = FVolumeInfo()
+        _capi.load().tbrm_mhd_parse_header(text.encode(), C.byref(info.c))
+        return info
+
+    @staticmethod
+    def CreateVolumeFromFile(FileName: str, bNormalize: bool = True, bConvertToFloat: bool = True, bLightVolume32Bit: bool = False,
+                             LightVolumeHalfResolution: bool = False, device: int = 0):
+        """UMHDLoader::CreateVolumeFromFile (MHDLoader.cpp:183-227) + InitializeRaymarchResources: returns (resources, FVolumeInfo)."""
+        lib = _capi.load()
+        info = FVolumeInfo()
+        h = C.c_void_p()
+        light_fmt = FMT_R32F if bLightVolume32Bit else FMT_G8
+        check(lib.tbrm_load_mhd_volume(device, str(FileName).encode(), int(bNormalize), int(bConvertToFloat), light_fmt, int(LightVolumeHalfResolution),
+                                       C.byref(info.c), C.byref(h)))
+        res = FBasicRaymarchRenderingResources()
+        res._h = h
+        res.Device = device
+        res.DataDims = info.Dimensions
+        ld = (C.c_int32 * 3)()
+        check(lib.tbrm_light_volume_dims(h, ld))
+        res.LightDims = (ld[0], ld[1], ld[2])
+        res.DataFormat = {0: FMT_G8, 2: FMT_G16, 6: FMT_R32F}.get(info.ActualFormat, FMT_G8 if info.BytesPerVoxel == 1 else FMT_G16)
+        res.LightFormat = light_fmt
+        res.bLightVolume32Bit = bLightVolume32Bit
+        res.LightVolumeHalfResolution = LightVolumeHalfResolution
+        return res, info
+
+
+class UVolumeTextureToolkit:
+    @staticmethod
+    def NormalizeArrayByFormat(array: np.ndarray, device: int = 0):
+        """TextureUtilities.cpp:304-327 on the GPU. Returns (normalised uint8 / uint16 array, original min, original max)."""
+        a = np.ascontiguousarray(array)
+        fmt = _VOXEL_OF_NP[a.dtype]
+        out = np.empty(a.shape, np.uint8 if a.itemsize == 1 else np.uint16)
+        lo, hi = C.c_float(), C.c_float()
+        check(_capi.load().tbrm_normalize_volume(device, fmt, a.ctypes.data_as(C.c_void_p), 0, a.size, out.ctypes.data_as(C.c_void_p), 0,
+                                                 C.byref(lo), C.byref(hi)))
+        return out, lo.value, hi.value
+
+    @staticmethod
+    def ConvertArrayToFloat(array: np.ndarray, device: int = 0) -> np.ndarray:
+        """TextureUtilities.cpp:329-350 on the GPU."""
+        a = np.ascontiguousarray(array)
+        out = np.empty(a.shape, np.float32)
+        check(_capi.load().tbrm_convert_volume_to_float(device, _VOXEL_OF_NP[a.dtype], a.ctypes.data_as(C.c_void_p), 0, a.size,
+                                                        out.ctypes.data_as(C.c_void_p), 0))
+        return out
+
+
 def _fill_stats(dst: Optional[FSweepStats], st: _capi.SweepStats) -> None:
     if dst is None:
         return

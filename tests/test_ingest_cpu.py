@@ -1,0 +1,98 @@
+"""Host side of volume ingest in the PRODUCT library — no GPU needed: the MetaImage header parser that mirrors
+UMHDLoader::ParseVolumeInfoFromHeader (MHDLoader.cpp:18-181), FVolumeInfo's value / range mappings against the reference's own
+VolumeInfo.cpp (tests/golden/ref_ingest.npz), and the error behaviour of the GPU entry points on a machine without a device."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tbraymarcherplugin_b200 import _capi
+from tbraymarcherplugin_b200.raymarch_utils import FVolumeInfo, UMHDLoader, UVolumeTextureToolkit
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+HEADER = """ObjectType = Image
+NDims = 3
+BinaryData = True
+BinaryDataByteOrderMSB = False
+CompressedData = False
+TransformMatrix = 1 0 0 0 1 0 0 0 1
+Offset = 0 0 0
+CenterOfRotation = 0 0 0
+ElementSpacing = 0.5 0.5 1.25
+DimSize = 64 48 20
+AnatomicalOrientation = ???
+ElementType = MET_SHORT
+ElementDataFile = ct_head.raw
+"""
+
+
+def test_mhd_header_fields():
+    info = UMHDLoader.ParseVolumeInfoFromHeaderText(HEADER)
+    assert info.bParseWasSuccessful and info.Dimensions == (64, 48, 20) and info.Spacing == (0.5, 0.5, 1.25)
+    assert info.WorldDimensions == (32.0, 24.0, 25.0)  # Spacing * Dimensions (MHDLoader.cpp:74)
+    assert info.OriginalFormat == 3 and info.BytesPerVoxel == 2 and info.bIsSigned and not info.bIsCompressed
+    assert info.DataFileName == "ct_head.raw" and not info.bIsNormalized
+    assert (info.MinValue, info.MaxValue) == (-1000.0, 3000.0)  # FVolumeInfo defaults until the data has been scanned
+
+
+@pytest.mark.parametrize("name,fmt,nbytes,signed", [("MET_UCHAR", 0, 1, False), ("MET_CHAR", 1, 1, True), ("MET_USHORT", 2, 2, False),
+                                                    ("MET_SHORT", 3, 2, True), ("MET_UINT", 4, 4, False), ("MET_INT", 5, 4, True),
+                                                    ("MET_FLOAT", 6, 4, True)])
+def test_mhd_element_types(name, fmt, nbytes, signed):
+    info = UMHDLoader.ParseVolumeInfoFromHeaderText(HEADER.replace("MET_SHORT", name))
+    assert info.bParseWasSuccessful and (info.OriginalFormat, info.BytesPerVoxel, info.bIsSigned) == (fmt, nbytes, signed)
+
+
+def test_mhd_variants_and_failures():
+    # ElementSize is accepted in place of ElementSpacing; CompressedDataSize switches zlib loading on (MHDLoader.cpp:59,140-153)
+    info = UMHDLoader.ParseVolumeInfoFromHeaderText(HEADER.replace("ElementSpacing", "ElementSize") + "CompressedDataSize = 12345\n")
+    assert info.bParseWasSuccessful and info.bIsCompressed and info.CompressedByteSize == 12345
+    for missing in ("DimSize", "ElementSpacing", "ElementType", "ElementDataFile"):
+        bad = "\n".join(l for l in HEADER.splitlines() if not l.startswith(missing))
+        assert not UMHDLoader.ParseVolumeInfoFromHeaderText(bad).bParseWasSuccessful, missing
+    assert not UMHDLoader.ParseVolumeInfoFromHeaderText(HEADER.replace("MET_SHORT", "MET_DOUBLE")).bParseWasSuccessful
+    assert not UMHDLoader.ParseVolumeInfoFromHeaderText("").bParseWasSuccessful
+    # keys are matched as whole words anywhere in the file, in any order
+    shuffled = "ElementDataFile = a.raw\nElementType = MET_UCHAR\nDimSize = 1 2 3\nElementSpacing = 1 1 1\n"
+    assert UMHDLoader.ParseVolumeInfoFromHeaderText(shuffled).Dimensions == (1, 2, 3)
+    lib = _capi.load()
+    assert lib.tbrm_mhd_parse_header(None, None) == _capi.TBRM_ERR_INVALID_ARGUMENT
+
+
+def test_volume_info_mappings_equal_the_reference():
+    g = np.load(GOLDEN / "ref_ingest.npz")  # FVolumeInfo::{Normalize,Denormalize}{Value,Range} of the reference on [-1000, 3000]
+    info = FVolumeInfo()
+    info.c.min_value, info.c.max_value = -1000.0, 3000.0
+    for normalized, key in ((1, "info_maps"), (0, "info_maps_raw")):
+        info.c.is_normalized = normalized
+        fns = (info.NormalizeValue, info.DenormalizeValue, info.NormalizeRange, info.DenormalizeRange)
+        got = np.array([[f(float(v)) for v in g["info_values"]] for f in fns], np.float32)
+        assert np.array_equal(got, g[key]), key
+
+
+def test_gpu_entry_points_validate_and_fail_loudly_without_a_device():
+    lib = _capi.load()
+    a = np.arange(16, dtype=np.int16)
+    out = np.empty(16, np.uint16)
+    lo, hi = C.c_float(), C.c_float()
+    args = (a.ctypes.data_as(C.c_void_p), 0, 16, out.ctypes.data_as(C.c_void_p), 0, C.byref(lo), C.byref(hi))
+    assert lib.tbrm_normalize_volume(0, 99, *args) == _capi.TBRM_ERR_INVALID_ARGUMENT  # unknown voxel format
+    assert lib.tbrm_normalize_volume(0, 3, None, 0, 16, out.ctypes.data_as(C.c_void_p), 0, None, None) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    assert lib.tbrm_convert_volume_to_float(0, 6, a.ctypes.data_as(C.c_void_p), 0, 16, out.ctypes.data_as(C.c_void_p), 0) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    if lib.tbrm_device_count() > 0:
+        pytest.skip("a GPU is present: the no-device behaviour cannot be observed")
+    assert lib.tbrm_normalize_volume(0, 3, *args) == _capi.TBRM_ERR_NO_DEVICE  # no CPU fallback
+    with pytest.raises(_capi.TbrmError):
+        UVolumeTextureToolkit.NormalizeArrayByFormat(a)
+    h = C.c_void_p()
+    info = _capi.VolumeInfo()
+    assert lib.tbrm_load_mhd_volume(0, b"/nonexistent/x.mhd", 1, 0, 0, 0, C.byref(info), C.byref(h)) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    assert lib.tbrm_generate_octree(None) == _capi.TBRM_ERR_NOT_INITIALIZED
+    d = (C.c_int32 * 3)(8, 8, 8)
+    c = (C.c_float * 3)(0, 0, 0)
+    buf = np.zeros(512, np.uint16)
+    assert lib.tbrm_mandelbulb_sdf(0, d, c, 2.0, 8.0, 0, buf.ctypes.data_as(C.c_void_p), 0, None) == _capi.TBRM_ERR_INVALID_ARGUMENT  # G8 output
+    assert lib.tbrm_mandelbulb_sdf(0, d, c, 0.0, 8.0, 1, buf.ctypes.data_as(C.c_void_p), 0, None) == _capi.TBRM_OK  # Extent <= 0: no-op
+    assert lib.tbrm_mandelbulb_sdf(0, d, c, 2.0, 8.0, 1, buf.ctypes.data_as(C.c_void_p), 0, None) == _capi.TBRM_ERR_NO_DEVICE
