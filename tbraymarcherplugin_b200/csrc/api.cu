@@ -84,16 +84,20 @@ static tbrm_status mandelbulb_op(int device, void* dst, size_t bytes, int dst_is
 struct IngestBuffers {
     void* d_in = nullptr;
     void* d_out = nullptr;
-    void* d_partials = nullptr;
-    float* d_minmax = nullptr;
     bool own_in = false, own_out = false;
     ~IngestBuffers() {
         if (own_in && d_in) cudaFree(d_in);
         if (own_out && d_out) cudaFree(d_out);
-        if (d_partials) cudaFree(d_partials);
-        if (d_minmax) cudaFree(d_minmax);
     }
 };
+// per host thread and device: the (min, max) partials of the reduction + the final pair (ops run on the per-thread stream, so the
+// scratch is per thread too; ~10 KB, kept for the life of the process: a device-to-device conversion allocates nothing)
+static void* ingest_scratch(int device) {
+    static thread_local void* cache[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    if (!cache[device] && cudaMalloc(&cache[device], ingest_partials_bytes() + 64) != cudaSuccess) cache[device] = nullptr;
+    return cache[device];
+}
 
 static tbrm_status ingest_stage(IngestBuffers& b, const void* src, int src_is_device, size_t in_bytes, void* dst, int dst_is_device,
                                 size_t out_bytes) {
@@ -982,11 +986,15 @@ tbrm_status tbrm_normalize_volume(int device, int voxel_format, const void* src,
     IngestBuffers b;
     tbrm_status s = ingest_stage(b, src, src_is_device, (size_t) count * ib, dst, dst_is_device, (size_t) count * ob);
     if (s != TBRM_OK) return s;
-    TBRM_CUDA(cudaMalloc(&b.d_partials, ingest_partials_bytes()));
-    TBRM_CUDA(cudaMalloc((void**) &b.d_minmax, 2 * sizeof(float)));
-    TBRM_CUDA(ingest_normalize(cudaStreamPerThread, voxel_format, b.d_in, (size_t) count, b.d_out, b.d_partials, b.d_minmax));
+    void* scratch = ingest_scratch(device);
+    if (!scratch) {
+        set_last_error("tbrm_normalize_volume: cannot allocate the reduction scratch");
+        return TBRM_ERR_CUDA;
+    }
+    float* d_minmax = (float*) ((char*) scratch + ingest_partials_bytes());
+    TBRM_CUDA(ingest_normalize(cudaStreamPerThread, voxel_format, b.d_in, (size_t) count, b.d_out, scratch, d_minmax));
     float mm[2] = {0.0f, 0.0f};
-    TBRM_CUDA(cudaMemcpyAsync(mm, b.d_minmax, sizeof(mm), cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    TBRM_CUDA(cudaMemcpyAsync(mm, d_minmax, sizeof(mm), cudaMemcpyDeviceToHost, cudaStreamPerThread));
     if (!dst_is_device) TBRM_CUDA(cudaMemcpyAsync(dst, b.d_out, (size_t) count * ob, cudaMemcpyDeviceToHost, cudaStreamPerThread));
     TBRM_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
     if (out_min) *out_min = mm[0];

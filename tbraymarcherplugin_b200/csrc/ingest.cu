@@ -119,15 +119,34 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_normalize_kernel(const 
     if (blockIdx.x == 0 && threadIdx.x == 0) out_minmax[0] = fmn, out_minmax[1] = fmx;  // OutOriginalMin / OutOriginalMax
     const size_t nvec = n / VEC;
     const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const Pack<In, VEC> p = *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC);
-        Pack<Out, VEC> q;
+    if constexpr (sizeof(In) == 1) {
+        // 1-byte voxels: the map has 256 entries — each thread evaluates the reference's expression for one input value, the voxels
+        // then go through the table (same function on the same inputs: identical results, no division per voxel)
+        static_assert(kIngestThreads == 256, "one table entry per thread");
+        __shared__ Out lut[256];
+        constexpr int kLo = (int) std::numeric_limits<In>::min();
+        lut[threadIdx.x] = normalize_one<In, Out>((In) ((int) threadIdx.x + kLo), fmn, range, omaxf);
+        __syncthreads();
+        for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+            const Pack<In, VEC> p = *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC);
+            Pack<Out, VEC> q;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) q.v[k] = normalize_one<In, Out>(p.v[k], fmn, range, omaxf);
-        *reinterpret_cast<Pack<Out, VEC>*>(out + i * VEC) = q;
+            for (int k = 0; k < VEC; ++k) q.v[k] = lut[(int) p.v[k] - kLo];
+            *reinterpret_cast<Pack<Out, VEC>*>(out + i * VEC) = q;
+        }
+        if (blockIdx.x == 0)
+            for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) out[i] = lut[(int) in[i] - kLo];
+    } else {
+        for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+            const Pack<In, VEC> p = *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC);
+            Pack<Out, VEC> q;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) q.v[k] = normalize_one<In, Out>(p.v[k], fmn, range, omaxf);
+            *reinterpret_cast<Pack<Out, VEC>*>(out + i * VEC) = q;
+        }
+        if (blockIdx.x == 0)
+            for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) out[i] = normalize_one<In, Out>(in[i], fmn, range, omaxf);
     }
-    if (blockIdx.x == 0)
-        for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) out[i] = normalize_one<In, Out>(in[i], fmn, range, omaxf);
 }
 
 // ConvertArrayToFloatTemplated: NewData[i] = static_cast<float>(TypedData[i])

@@ -11,8 +11,8 @@ namespace tbrm {
 
 // ---- octree: 4-level max pyramid of the data volume in a pow-2 sized UNORM16 volume ---------------------------------------------------
 // The reference runs ONE thread per 8^3 leaf ([numthreads(1,1,1)]) which copies 512 voxels and reduces them three times through the UAV.
-// Here one 256-thread CTA owns a 32 x 8 x 8 strip (4 leaves along x): mip 0 is written with coalesced 64-byte rows and kept in shared
-// memory, mips 1-3 are reduced from shared memory — the data volume is read once, every octree texel is written once:
+// Here one 256-thread CTA owns a 128 x 8 x 8 strip (16 leaves along x): a warp reads one 128-voxel row segment with 4-voxel loads and
+// writes its 256 bytes of mip 0 with 8-byte stores; mip 0 stays in 16 KiB of shared memory, mips 1-3 are reduced from shared memory — the data volume is read once, every octree texel is written once:
 // algorithmic bytes = B_d per data voxel + 2 * (1 + 1/8 + 1/64 + 1/512) per octree voxel. UNORM16 values round-trip exactly through
 // the float load / store of the shader (v/65535 -> floor(v'*65535 + .5) is the identity on 0..65535), so the reductions are integer maxima.
 struct OctreeUniforms {
@@ -22,28 +22,63 @@ struct OctreeUniforms {
 
 __device__ __forceinline__ unsigned int quant16(float v) { return (unsigned int) floorf(saturatef(v) * 65535.0f + 0.5f); }
 
-template <typename DataT>
+template <typename T, int N>
+struct alignas(sizeof(T) * N) OctPack {
+    T v[N];
+};
+
+// VEC4: the data rows can be read 4 voxels at a time (X % 4 == 0 and an aligned base pointer)
+template <typename DataT, bool VEC4>
 __global__ void __launch_bounds__(256) octree_build_kernel(const OctreeUniforms U, const DataT* __restrict__ data, uint16_t* __restrict__ mip0,
                                                            uint16_t* __restrict__ mip1, uint16_t* __restrict__ mip2, uint16_t* __restrict__ mip3) {
-    __shared__ uint16_t s0[8][8][32];
-    __shared__ uint16_t s1[4][4][16];
-    __shared__ uint16_t s2[2][2][8];
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, z0 = blockIdx.z * 8;
-    const int t = threadIdx.x, lx = t & 31, ly = t >> 5;
+    __shared__ __align__(8) uint16_t s0[8][8][128];
+    __shared__ uint16_t s1[4][4][64];
+    __shared__ uint16_t s2[2][2][32];
+    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8, z0 = blockIdx.z * 8;
+    const int t = threadIdx.x, tx = t & 31, ly = t >> 5;
     const int X = U.ddims[0], Y = U.ddims[1], Z = U.ddims[2];
     const int OX = U.odims[0][0], OY = U.odims[0][1], OZ = U.odims[0][2];
-    // mip 0: OctreeVolumeMip0[p] = Volume.Load(p).r * MinMaxValues.y (= 1); Load outside the data volume returns 0 (:36-49)
+    // mip 0: OctreeVolumeMip0[p] = Volume.Load(p).r * MinMaxValues.y (= 1); Load outside the data volume returns 0 (:36-49).
+    // A thread owns 4 voxels along x: a warp reads one 128-voxel row segment and writes 256 bytes of it.
+    const int x = x0 + 4 * tx, y = y0 + ly;
 #pragma unroll
     for (int lz = 0; lz < 8; ++lz) {
-        const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
-        unsigned int q = 0;
-        if (x < X && y < Y && z < Z) q = quant16(Texel<DataT>::decode(__ldg(data + (size_t) x + (size_t) X * ((size_t) y + (size_t) Y * z))) * 1.0f);
-        s0[lz][ly][lx] = (uint16_t) q;
-        if (x < OX && y < OY && z < OZ) mip0[(size_t) x + (size_t) OX * ((size_t) y + (size_t) OY * z)] = (uint16_t) q;  // out-of-bounds UAV stores are dropped
+        const int z = z0 + lz;
+        unsigned int q[4] = {0, 0, 0, 0};
+        if (y < Y && z < Z) {
+            const size_t row = (size_t) X * ((size_t) y + (size_t) Y * z);
+            if (VEC4 && x + 3 < X) {
+                const OctPack<DataT, 4> p = *reinterpret_cast<const OctPack<DataT, 4>*>(data + row + x);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[k] = quant16(Texel<DataT>::decode(p.v[k]) * 1.0f);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (x + k < X) q[k] = quant16(Texel<DataT>::decode(__ldg(data + row + x + k)) * 1.0f);
+            }
+        }
+        OctPack<uint16_t, 4> o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o.v[k] = (uint16_t) q[k];
+        *reinterpret_cast<OctPack<uint16_t, 4>*>(&s0[lz][ly][4 * tx]) = o;
+        if (y < OY && z < OZ) {  // out-of-bounds UAV stores are dropped
+            uint16_t* dst = mip0 + (size_t) x + (size_t) OX * ((size_t) y + (size_t) OY * z);
+            if (x + 3 < OX && (OX & 3) == 0) {
+                *reinterpret_cast<OctPack<uint16_t, 4>*>(dst) = o;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (x + k < OX) dst[k] = o.v[k];
+            }
+        }
     }
     __syncthreads();
-    {  // mip 1: 16 x 4 x 4 texels of this strip, one per thread
-        const int mx = t & 15, my = (t >> 4) & 3, mz = t >> 6;
+    // strip texels beyond the octree's bounds hold 0 in shared memory (they lie outside the data volume: octree sides >= data sides),
+    // which is what the shader's Load returns for them
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // mip 1: 64 x 4 x 4 texels of this strip, four per thread
+        const int e = t + 256 * k;
+        const int mx = e & 63, my = (e >> 6) & 3, mz = e >> 8;
         unsigned int m = 0;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -51,16 +86,14 @@ __global__ void __launch_bounds__(256) octree_build_kernel(const OctreeUniforms 
             for (int b = 0; b < 2; ++b)
 #pragma unroll
                 for (int a = 0; a < 2; ++a) m = max(m, (unsigned int) s0[2 * mz + c][2 * my + b][2 * mx + a]);
-        // strip texels beyond the octree's bounds hold 0 in shared memory (they lie outside the data volume: octree sides >= data
-        // sides), which is what the shader's Load returns for them
         s1[mz][my][mx] = (uint16_t) m;
         const int gx = x0 / 2 + mx, gy = y0 / 2 + my, gz = z0 / 2 + mz;
         if (gx < U.odims[1][0] && gy < U.odims[1][1] && gz < U.odims[1][2])
             mip1[(size_t) gx + (size_t) U.odims[1][0] * ((size_t) gy + (size_t) U.odims[1][1] * gz)] = (uint16_t) m;
     }
     __syncthreads();
-    if (t < 32) {  // mip 2: 8 x 2 x 2
-        const int mx = t & 7, my = (t >> 3) & 1, mz = t >> 4;
+    if (t < 128) {  // mip 2: 32 x 2 x 2
+        const int mx = t & 31, my = (t >> 5) & 1, mz = t >> 6;
         unsigned int m = 0;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -74,7 +107,7 @@ __global__ void __launch_bounds__(256) octree_build_kernel(const OctreeUniforms 
             mip2[(size_t) gx + (size_t) U.odims[2][0] * ((size_t) gy + (size_t) U.odims[2][1] * gz)] = (uint16_t) m;
     }
     __syncthreads();
-    if (t < 4) {  // mip 3: 4 x 1 x 1
+    if (t < 16) {  // mip 3: 16 x 1 x 1
         unsigned int m = 0;
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -250,9 +283,14 @@ void octree_mip_dims(const tbrm_resources& r, int mip, int32_t dims[3]) {  // Ra
 
 template <typename DataT>
 static cudaError_t launch_octree(tbrm_resources& r, const OctreeUniforms& U) {
-    const dim3 grid((U.odims[0][0] + 31) / 32, (U.odims[0][1] + 7) / 8, (U.odims[0][2] + 7) / 8);
-    octree_build_kernel<DataT><<<grid, 256, 0, r.stream>>>(U, (const DataT*) r.data, (uint16_t*) r.octree[0], (uint16_t*) r.octree[1],
-                                                          (uint16_t*) r.octree[2], (uint16_t*) r.octree[3]);
+    const dim3 grid((U.odims[0][0] + 127) / 128, (U.odims[0][1] + 7) / 8, (U.odims[0][2] + 7) / 8);
+    const bool vec4 = (U.ddims[0] & 3) == 0 && (reinterpret_cast<uintptr_t>(r.data) % (4 * sizeof(DataT))) == 0;
+    if (vec4)
+        octree_build_kernel<DataT, true><<<grid, 256, 0, r.stream>>>(U, (const DataT*) r.data, (uint16_t*) r.octree[0], (uint16_t*) r.octree[1],
+                                                                    (uint16_t*) r.octree[2], (uint16_t*) r.octree[3]);
+    else
+        octree_build_kernel<DataT, false><<<grid, 256, 0, r.stream>>>(U, (const DataT*) r.data, (uint16_t*) r.octree[0], (uint16_t*) r.octree[1],
+                                                                     (uint16_t*) r.octree[2], (uint16_t*) r.octree[3]);
     count_launch();
     return cudaGetLastError();
 }
