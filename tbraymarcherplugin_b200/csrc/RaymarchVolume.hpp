@@ -53,6 +53,7 @@ inline bool WorldParametersEqual(const FRaymarchWorldParameters& a, const FRayma
 struct FTickReport {
     enum Action { None, NotInitialized, Reset, Incremental } action = None;
     int lights_updated = 0;
+    bool octree_rebuilt = false;
     std::vector<std::string> errors;
 };
 
@@ -69,6 +70,8 @@ public:
     bool bFastShader = true;  // RaymarchVolume.h:64-65
     bool bVisible = true;
     bool bRequestedRecompute = false;
+    bool bRequestedOctreeRebuild = false;  // RaymarchVolume.h:168-169; requested by SetVolumeAsset (RaymarchVolume.cpp:553-554)
+    uint32_t OctreeVolumeMip = 0;          // RaymarchVolume.h:191-193
     // The reference's ResetAllLights does not refresh LightParametersMap (RaymarchVolume.cpp:418-451): lights that had moved
     // when a reset ran are seen as changed again next tick. false reproduces that, true records what the reset used.
     bool bRefreshLightMapOnReset = false;
@@ -96,6 +99,11 @@ public:
         if (!WorldParametersEqual(WorldParameters, GetWorldParameters())) {
             bRequestedRecompute = true;
             WorldParameters = GetWorldParameters();
+        }
+        if (bRequestedOctreeRebuild && SelectRaymarchMaterial == ERaymarchMaterial::Octree) {  // RaymarchVolume.cpp:358-363
+            Ops::GenerateOctree(RaymarchResources);
+            bRequestedOctreeRebuild = false;
+            rep.octree_rebuilt = true;
         }
         if (SelectRaymarchMaterial != ERaymarchMaterial::Lit) return rep;
         if (bRequestedRecompute) {

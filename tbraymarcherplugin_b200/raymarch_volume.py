@@ -80,6 +80,7 @@ class FTickReport:
 
     action: str = "none"  # "none" | "not_initialized" | "reset" | "incremental"
     lights_updated: int = 0
+    octree_rebuilt: bool = False
     errors: List[str] = field(default_factory=list)
 
 
@@ -95,6 +96,9 @@ class ARaymarchVolume:
         self.bFastShader = True  # RaymarchVolume.h:64-65
         self.bVisible = True
         self.bRequestedRecompute = False
+        self.bRequestedOctreeRebuild = False  # RaymarchVolume.h:168-169; set by SetVolumeAsset (RaymarchVolume.cpp:553-554)
+        self.OctreeVolumeMip = 0              # RaymarchVolume.h:191-193
+        self.RaymarchingSteps = 150.0         # RaymarchVolume.h:188-189
         self.bRefreshLightMapOnReset = bRefreshLightMapOnReset
         self.ops = ops
         self.WorldParameters = self.GetWorldParameters()
@@ -126,6 +130,11 @@ class ARaymarchVolume:
         if not _world_params_equal(self.WorldParameters, self.GetWorldParameters()):
             self.bRequestedRecompute = True
             self.UpdateWorldParameters()
+        # RaymarchVolume.cpp:358-363
+        if self.bRequestedOctreeRebuild and self.SelectRaymarchMaterial == ERaymarchMaterial.Octree:
+            self.ops.GenerateOctree(self.RaymarchResources)
+            self.bRequestedOctreeRebuild = False
+            rep.octree_rebuilt = True
         # Only check if we need to update lights if we're using the Lit raymarch material.
         if self.SelectRaymarchMaterial != ERaymarchMaterial.Lit:
             return rep
@@ -179,3 +188,19 @@ class ARaymarchVolume:
                                                    self.WorldParameters, bGPUSync=self.bFastShader)
         if not ok and rep is not None:
             rep.errors.append(f"Error. Could not change light {UpdatedLight.Name} in volume.")
+
+    # ARaymarchVolume::SetVolumeAsset, RaymarchVolume.cpp:467-560 (the part that concerns the path): new data => everything is stale
+    def OnVolumeLoaded(self) -> None:
+        self.UpdateWorldParameters()
+        self.bRequestedRecompute = True
+        self.bRequestedOctreeRebuild = True
+
+    def Render(self, Camera, rows=None):
+        """What UE's renderer does with the selected material (RaymarchVolume.cpp:144-152, 789-800): the entry point of M_Raymarch,
+        M_Intensity_Raymarch or M_Octree_Raymarch for every covered pixel. Returns (rgba, executed_steps)."""
+        if self.SelectRaymarchMaterial == ERaymarchMaterial.Lit:
+            return self.ops.PerformWindowedLitRaymarch(self.RaymarchResources, Camera, self.WorldParameters, self.RaymarchingSteps, rows=rows)
+        if self.SelectRaymarchMaterial == ERaymarchMaterial.Intensity:
+            return self.ops.PerformWindowedIntensityRaymarch(self.RaymarchResources, Camera, self.WorldParameters, self.RaymarchingSteps, rows=rows)
+        return self.ops.PerformWindowedRaymarchOctree(self.RaymarchResources, Camera, self.WorldParameters, self.RaymarchingSteps,
+                                                      self.OctreeVolumeMip, rows=rows)

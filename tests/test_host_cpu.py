@@ -172,6 +172,7 @@ def test_cpp_volume_policy_mirror(tmp_path):
             static void AddDirLightToSingleVolume(const FBasicRaymarchRenderingResources&, const FDirLightParameters&, bool, FRaymarchWorldParameters, bool& ok, bool) { calls.push_back("add"); ok = true; }
             static void ChangeDirLightInSingleVolume(FBasicRaymarchRenderingResources&, FDirLightParameters o, FDirLightParameters n, FRaymarchWorldParameters, bool& ok, bool) {
                 calls.push_back(o.LightIntensity == 1.0f && n.LightIntensity != 1.0f ? "change" : "change?"); ok = true; }
+            static void GenerateOctree(FBasicRaymarchRenderingResources&) { calls.push_back("octree"); }
         };
         #define CHECK(c) do { if (!(c)) { std::printf("failed: %s (line %d)\\n", #c, __LINE__); return 1; } } while (0)
         int main() {
@@ -201,6 +202,11 @@ def test_cpp_volume_policy_mirror(tmp_path):
             L[3].LightIntensity = 0.1f;
             calls.clear();
             CHECK(vol.Tick().action == FTickReport::None && calls.empty());
+            vol.bRequestedOctreeRebuild = true;                  // a new volume was loaded (RaymarchVolume.cpp:553-554)
+            CHECK(!vol.Tick().octree_rebuilt && calls.empty());  // not under the intensity material
+            vol.SelectRaymarchMaterial = ERaymarchMaterial::Octree;
+            CHECK(vol.Tick().octree_rebuilt && calls.size() == 1 && calls[0] == "octree" && !vol.bRequestedOctreeRebuild);
+            CHECK(!vol.Tick().octree_rebuilt && calls.size() == 1);
             vol.RaymarchResources.bIsInitialized = false;
             CHECK(vol.Tick().action == FTickReport::NotInitialized);
             return 0;

@@ -106,3 +106,47 @@ def test_reference_quirk_stale_light_map_after_a_reset_and_the_opt_in_fix():
             assert rep.action == "none"
         else:  # the reference re-issues a change from parameters the light volume no longer holds
             assert rep.action == "incremental" and ops.calls[0][:1] == ("change",) and ops.calls[0][3:] == (1.0, 0.2)
+
+
+class RecordingMaterialOps(RecordingOps):
+    def GenerateOctree(self, res):
+        self.calls.append(("octree",))
+
+    def PerformWindowedLitRaymarch(self, res, cam, world, steps, rows=None):
+        self.calls.append(("lit", steps))
+        return None, 0
+
+    def PerformWindowedIntensityRaymarch(self, res, cam, world, steps, rows=None):
+        self.calls.append(("intensity", steps))
+        return None, 0
+
+    def PerformWindowedRaymarchOctree(self, res, cam, world, steps, mip, rows=None):
+        self.calls.append(("octree_march", steps, mip))
+        return None, 0
+
+
+def test_octree_is_rebuilt_once_and_only_while_the_octree_material_is_selected():
+    """RaymarchVolume.cpp:358-363 + :553-554: a new volume requests the rebuild; the tick performs it only under the octree material,
+    and lights are only maintained under the lit material (:365-368)."""
+    res = FBasicRaymarchRenderingResources()
+    res.bIsInitialized = True
+    ops = RecordingMaterialOps()
+    lights = [ARaymarchLight((1.0, 0.0, -0.3), 1.0, "L0")]
+    vol = ARaymarchVolume(res, lights, ops=ops)
+    vol.OnVolumeLoaded()
+    rep = vol.Tick()  # lit material: full reset (bRequestedRecompute), the octree request stays pending
+    assert rep.action == "reset" and not rep.octree_rebuilt and ("octree",) not in ops.calls and vol.bRequestedOctreeRebuild
+    ops.calls.clear()
+    vol.SelectRaymarchMaterial = ERaymarchMaterial.Octree
+    lights[0].ForwardVector = (0.0, 1.0, 0.0)
+    rep = vol.Tick()
+    assert rep.octree_rebuilt and ops.calls == [("octree",)] and not vol.bRequestedOctreeRebuild  # no light work under this material
+    assert vol.Tick().octree_rebuilt is False and ops.calls == [("octree",)]
+    vol.OctreeVolumeMip, vol.RaymarchingSteps = 2, 200.0
+    vol.Render(camera := object())
+    vol.SelectRaymarchMaterial = ERaymarchMaterial.Intensity
+    vol.Render(camera)
+    vol.SelectRaymarchMaterial = ERaymarchMaterial.Lit
+    vol.Render(camera)
+    assert ops.calls[1:] == [("octree_march", 200.0, 2), ("intensity", 200.0), ("lit", 200.0)]
+    assert vol.Tick().action == "incremental"  # back under the lit material the moved light is finally updated
