@@ -12,11 +12,13 @@ Metric: Mray-steps/s = executed march-loop iterations of the frame (incl. clippe
 SURVEY.md §8d) / device time of the whole step (sweep + raymarch). The per-stage figures (raymarch Mray-steps/s on its own,
 sweep Mvoxels/s and GB/s) ride along in "stages".
 
-N > 1 (torchrun, one process per GPU): the path shards by independent volumes — every rank owns one ARaymarchVolume of the
-scene (its own data / light volume / frame), no data-path collective, weak scaling.
+N > 1 (torchrun, one process per GPU): ONE volume is sharded over the GPUs as Z-slabs — in-kernel NVLink halo exchange for the sweep,
+NCCL all-gathers of the data / light slabs, interleaved row blocks of the frame gathered on rank 0; strong scaling.
+--sharding volumes gives every rank its own independent volume instead (no data-path collective, weak scaling).
 
 --impl reference: the reference has no CPU implementation and cannot be built here (Unreal Engine 5.4 + HLSL), so this arm
-times the CPU oracle (oracle/, kind "port") with all host threads on a bounded sample of the same workload.
+times the reference's own shaders compiled for the CPU (oracle/_ref, kind "reference"; the CPU oracle, kind "port", where that build is
+absent) with all host threads on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -108,9 +110,17 @@ def workload_config(n_gpus: int, slabs: bool = True) -> dict:
 # ------------------------------------------------------------------------------------------------------------------
 # CPU oracle legs (cpu_baseline and --impl reference)
 # ------------------------------------------------------------------------------------------------------------------
-def oracle_sample(data, data_small, light_after_reset, threads: int):
+def reference_build_available() -> bool:
+    """oracle/_ref/libtbrm_ref.so: the reference's own shaders and host math compiled for the CPU (oracle/ref.mk). It is built where
+    /root/reference exists and travels to the GPU box as a file."""
+    return (ROOT / "oracle" / "_ref" / "libtbrm_ref.so").exists()
+
+
+def oracle_sample(data, data_small, light_after_reset, threads: int, kind: str = "port"):
     """One bounded sample of the workload on the host: one sweep axis pass over a 256^3 rendition of the volume (the per-voxel
     work does not depend on the resolution) and the lit raymarch of 20 evenly spaced rows of the real 512^3 / 1080p frame.
+    kind "reference": the reference's own AddDirLightShader.usf / WindowedRaymarchMaterials.usf + LightingShaderUtils.cpp compiled for the
+    CPU (oracle/_ref, OpenMP over the pixels of a slice / the pixels of a row block); kind "port": the oracle's restatement.
     Returns (estimated seconds for the whole step, estimated ray-steps of the whole frame, detail)."""
     sys.path.insert(0, str(ROOT / "tests"))
     import numpy as np
@@ -120,15 +130,22 @@ def oracle_sample(data, data_small, light_after_reset, threads: int):
     from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters
 
     oracle.lib().tbo_set_threads(threads)
+    if kind == "reference":
+        import refpin
+        Volume = refpin.RefVolume
+    else:
+        Volume = oracle.OracleVolume
     win = FWindowingParameters(0.45, 0.5, True, False)
     tf = oracle.prepare_tf(synth.soft_ct_curve())
     world = synth.identity_world()
-    small = oracle.OracleVolume(data_small, tf, win)
+    warm = Volume(np.ascontiguousarray(data_small[:16, :16, :16]), tf, win)  # untimed: spins up the OpenMP team, pages the library in
+    warm.add_dir_light(synth.LIGHTS[3], True, world)
+    small = Volume(data_small, tf, win)
     t0 = time.perf_counter()
-    passes = small.add_dir_light(synth.LIGHTS[3], True, world)  # axis-aligned light: exactly one axis pass over all voxels
-    t_pass = (time.perf_counter() - t0) / max(passes, 1) * (N_VOL / SWEEP_SAMPLE_N) ** 3
+    small.add_dir_light(synth.LIGHTS[3], True, world)  # axis-aligned light: exactly one axis pass over all voxels
+    t_pass = (time.perf_counter() - t0) * (N_VOL / SWEEP_SAMPLE_N) ** 3
     total_passes = 2 * len(LIGHT_IDS)  # L1, L2 (and L3) take two axis passes each
-    vol = oracle.OracleVolume(data, tf, win)
+    vol = Volume(data, tf, win)
     if light_after_reset is not None:
         vol.light = light_after_reset
     else:
@@ -137,8 +154,13 @@ def oracle_sample(data, data_small, light_after_reset, threads: int):
     t_rows, steps_rows = 0.0, 0
     for r in SAMPLE_ROWS:
         t0 = time.perf_counter()
-        _, st = vol.raymarch_lit(cam, world, STEPS, rows=(r, r + 1))
+        if kind == "reference":
+            vol.raymarch(0, cam, world, STEPS, rows=(r, r + 1))
+        else:
+            _, st = vol.raymarch_lit(cam, world, STEPS, rows=(r, r + 1))
         t_rows += time.perf_counter() - t0
+        if kind == "reference":  # the shader does not count its steps: the (bit-identical) oracle does, untimed
+            _, st = oracle.OracleVolume.raymarch_lit(vol, cam, world, STEPS, rows=(r, r + 1))
         steps_rows += st
     scale = VIEW[1] / len(SAMPLE_ROWS)
     est_seconds = total_passes * t_pass + t_rows * scale
@@ -153,6 +175,15 @@ def sample_text() -> str:
             f"(x{VIEW[1] // len(SAMPLE_ROWS)}), extrapolated linearly to the whole step")
 
 
+REFERENCE_NOTE = {
+    "reference": "the reference is a UE 5.4 / HLSL plugin with no CPU path; this runs ITS OWN shader sources (AddDirLightShader.usf, "
+                 "WindowedRaymarchMaterials.usf) and host math (LightingShaderUtils.cpp) compiled for the CPU against an HLSL / engine-type shim "
+                 "(oracle/ref.mk -> oracle/_ref/libtbrm_ref.so), OpenMP over all host threads",
+    "port": "the reference (UE 5.4 / HLSL) has no CPU path; oracle/_ref is not present on this machine, so this is the CPU oracle port "
+            "(bit-identical to the reference build) with all host threads",
+}
+
+
 def run_reference(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -161,11 +192,12 @@ def run_reference(args) -> int:
     import oracle
 
     threads = os.cpu_count() or 1
+    kind = "reference" if reference_build_available() else "port"
     data = oracle.synth_volume("perlin", (N_VOL,) * 3)  # untimed set-up; bit-identical to the device generator
     data_small = oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3)
     times, steps = [], 0.0
     for i in range(args.warmup + args.steps):
-        est_s, est_steps, _ = oracle_sample(data, data_small, None, threads)
+        est_s, est_steps, _ = oracle_sample(data, data_small, None, threads, kind)
         if i >= args.warmup:
             times.append(est_s)
             steps = est_steps
@@ -175,9 +207,9 @@ def run_reference(args) -> int:
         "impl": "reference", "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": sample_text()},
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": threads, "kind": kind, "sample": sample_text()},
         "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference (UE 5.4 / HLSL) has no CPU path and cannot be built here; this is the CPU oracle port with all host threads",
+        "note": REFERENCE_NOTE[kind],
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -436,9 +468,10 @@ def run_ours(args) -> int:
         sys.path.insert(0, str(ROOT / "tests"))
         import oracle
 
-        est_s, est_steps, detail = oracle_sample(h_vol.numpy(), oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3), light, threads)
-        cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": "port", "sample": sample_text(),
-                        "est_ms_per_step": est_s * 1e3, **detail}
+        kind = "reference" if reference_build_available() else "port"
+        est_s, est_steps, detail = oracle_sample(h_vol.numpy(), oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3), light, threads, kind)
+        cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": kind, "sample": sample_text(),
+                        "est_ms_per_step": est_s * 1e3, "note": REFERENCE_NOTE[kind], **detail}
 
     if slabs:
         vol.Check()
