@@ -1068,7 +1068,13 @@ tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize
     if (s != TBRM_OK) return s;
     tbrm_resources* r = *out;
     const uint64_t count = (uint64_t) r->data_voxels();
-    TBRM_CUDA(cudaMalloc(&r->data, (size_t) count * r->data_elem()));
+    if (cudaMalloc(&r->data, (size_t) count * r->data_elem()) != cudaSuccess) {
+        set_last_error("tbrm_load_mhd_volume: cudaMalloc(data volume) failed");
+        r->data = nullptr;
+        tbrm_destroy(r);
+        *out = nullptr;
+        return TBRM_ERR_CUDA;
+    }
     r->data_owned = true;
     if (normalize) {
         s = tbrm_normalize_volume(device, of, voxels.data(), 0, count, r->data, 1, &info->min_value, &info->max_value);

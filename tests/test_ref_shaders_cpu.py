@@ -90,3 +90,32 @@ def test_oracle_equals_live_reference_shaders(dtype, half_res, border_exact):
         cam = synth.benchmark_camera(36, 28, jitter=True, frame=5)
         rgba, _ = a.raymarch_lit(cam, world, 40.0)
         assert np.array_equal(rgba, b.raymarch(0, cam, world, 40.0))
+
+
+@needs_ref
+def test_the_oracle_written_goldens_of_the_gpu_tests_are_reference_shader_output_too():
+    """tests/golden/sweep_32.npz and raymarch_32.npz were written by the oracle (make_golden.py); tests/test_gpu_golden.py holds the
+    TMA-staged sweep (the dominant kernel; 32^3 is eligible) and the fast lit march to them. The reference's own shaders produce the
+    same arrays — so those GPU tests compare the CUDA path with reference output."""
+    spec = importlib.util.spec_from_file_location("make_golden", GOLDEN / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = np.load(GOLDEN / "sweep_32.npz")
+    data = synth.perlin_ct_volume(mg.SWEEP_DIMS)
+    tf = oracle.prepare_tf(synth.soft_ct_curve())
+    for name, mkw in mg.WORLDS.items():
+        vol, world = refpin.RefVolume(data, tf, mg.CT_WINDOW), mkw()
+        for l in synth.LIGHTS:
+            vol.add_dir_light(l, True, world)
+        assert np.array_equal(vol.light, want[f"{name}_reset"])
+        vol.add_dir_light(synth.LIGHTS[1], False, world)
+        assert np.array_equal(vol.light, want[f"{name}_removed"])
+        vol.change_dir_light(synth.LIGHTS[0], synth.rotate_about_z(synth.LIGHTS[0], 5.0), world)
+        assert np.array_equal(vol.light, want[f"{name}_changed"])
+    frames = np.load(GOLDEN / "raymarch_32.npz")
+    vol, world = refpin.RefVolume(data, tf, mg.CT_WINDOW), synth.identity_world()
+    for l in synth.LIGHTS[:2]:
+        vol.add_dir_light(l, True, world)
+    cam = synth.benchmark_camera(48, 32, jitter=True, frame=3)  # the shader always jitters: only the jitter = 1 frame has a counterpart
+    assert np.array_equal(vol.raymarch(0, cam, world, 64.0), frames["rgba_jitter1"])
+    assert np.array_equal(vol.raymarch(-1, cam, world, 64.0), frames["setup_jitter1"])
