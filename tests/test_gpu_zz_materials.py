@@ -220,3 +220,20 @@ def test_mandelbulb_sdf_bake_close_to_oracle(g16):
     # Extent <= 0: the reference enqueues nothing
     untouched, n = URaymarchUtils.CalculateMandelbulbSDF((8, 8, 8), Extent=0.0, g16=g16)
     assert n == 0 and not untouched.any()
+
+
+def test_cpp_example_runs_end_to_end(tmp_path):
+    """examples/mhd_to_frame.cpp (plain C++ over the C ABI): MetaImage file -> resources -> sweep -> octree -> the three materials."""
+    import subprocess
+
+    from test_ingest_cpu import _build_example
+
+    dims = (48, 40, 32)
+    raw = (synth.perlin_ct_volume(dims).astype(np.int16) * 12 - 1000)
+    (tmp_path / "v.raw").write_bytes(raw.tobytes())
+    (tmp_path / "v.mhd").write_text(f"NDims = 3\nDimSize = {dims[0]} {dims[1]} {dims[2]}\nElementSpacing = 1 1 1\nElementType = MET_SHORT\nElementDataFile = v.raw\n")
+    out = subprocess.run([str(_build_example(tmp_path)), str(tmp_path / "v.mhd")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "48 x 40 x 32 voxels" in out.stdout and "normalised to G16" in out.stdout
+    steps = [int(l.split(":")[1].split()[0]) for l in out.stdout.splitlines() if "march:" in l]
+    assert len(steps) == 3 and all(s > 0 for s in steps) and steps[1] < steps[0]  # the intensity march stops at its first sample

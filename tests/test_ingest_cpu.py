@@ -96,3 +96,25 @@ def test_gpu_entry_points_validate_and_fail_loudly_without_a_device():
     assert lib.tbrm_mandelbulb_sdf(0, d, c, 2.0, 8.0, 0, buf.ctypes.data_as(C.c_void_p), 0, None) == _capi.TBRM_ERR_INVALID_ARGUMENT  # G8 output
     assert lib.tbrm_mandelbulb_sdf(0, d, c, 0.0, 8.0, 1, buf.ctypes.data_as(C.c_void_p), 0, None) == _capi.TBRM_OK  # Extent <= 0: no-op
     assert lib.tbrm_mandelbulb_sdf(0, d, c, 2.0, 8.0, 1, buf.ctypes.data_as(C.c_void_p), 0, None) == _capi.TBRM_ERR_NO_DEVICE
+
+
+def _build_example(tmp_path):
+    import subprocess
+
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "mhd_to_frame"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I", str(root), str(root / "examples" / "mhd_to_frame.cpp"),
+                    "-L", str(root / "tbraymarcherplugin_b200"), "-ltbrm", f"-Wl,-rpath,{root / 'tbraymarcherplugin_b200'}", "-o", str(exe)], check=True)
+    return exe
+
+
+def test_cpp_example_builds_against_the_c_abi_and_fails_loudly(tmp_path):
+    """examples/mhd_to_frame.cpp: plain C++17 over include/tbrm.h, no CUDA headers. Without a readable header it reports the library's error."""
+    import subprocess
+
+    exe = _build_example(tmp_path)
+    out = subprocess.run([str(exe), str(tmp_path / "missing.mhd")], capture_output=True, text=True)
+    assert out.returncode == 1 and "cannot read" in out.stderr
+    (tmp_path / "bad.mhd").write_text("DimSize = 4 4 4\nElementType = MET_UCHAR\nElementDataFile = x.raw\n")  # no ElementSpacing
+    out = subprocess.run([str(exe), str(tmp_path / "bad.mhd")], capture_output=True, text=True)
+    assert out.returncode == 1 and "required" in out.stderr
