@@ -56,10 +56,46 @@ def run(cfg, Volume, march):
     return vol.light, march(vol, cam, world, cfg["steps"])
 
 
+# BASELINE.json configs[2]: 512^3, 4 lights, incremental ChangeDirLight updates. Update k turns light k % 4 by a further 5 degrees about +Z
+#  through ChangeDirLightInSingleVolume; checkpoints after the reset and after updates 4, 8 and 16.
+CFG3 = dict(volume="perlin", n=512, window=(0.45, 0.5, True, False), updates=16, checkpoints=(0, 4, 8, 16))
+
+
+def run_cfg3(Volume, on_checkpoint):
+    data, tf, win = inputs(CFG3)
+    vol = Volume(data, tf, win)
+    world = synth.identity_world()
+    lights = list(synth.LIGHTS)
+    for l in lights:
+        vol.add_dir_light(l, True, world)
+    on_checkpoint(0, vol.light)
+    for k in range(1, CFG3["updates"] + 1):
+        i = (k - 1) % 4
+        new = synth.rotate_about_z(lights[i], 5.0)
+        vol.change_dir_light(lights[i], new, world)
+        lights[i] = new
+        if k in CFG3["checkpoints"]:
+            on_checkpoint(k, vol.light)
+
+
 if __name__ == "__main__":
     import refpin
 
-    out = {}
+    path = HERE / "ref_fullsize_hashes.json"
+    if "--cfg3" in sys.argv:  # adds / refreshes the cfg3 entry only (about 7 minutes on 8 cores)
+        out = json.loads(path.read_text())
+        entry = {"config": {k: (list(v) if isinstance(v, tuple) else v) for k, v in CFG3.items()}, "light": {}}
+        t0 = time.time()
+
+        def keep(k, light):
+            entry["light"][str(k)] = digests(light)
+            print("cfg3 checkpoint", k, "%.0f s" % (time.time() - t0), entry["light"][str(k)]["all"][:16], float(light.max()), flush=True)
+
+        run_cfg3(refpin.RefVolume, keep)
+        out["cfg3"] = entry
+        path.write_text(json.dumps(out, indent=1) + "\n")
+        sys.exit(0)
+    out = json.loads(path.read_text()) if path.exists() else {}
     for name, cfg in CONFIGS.items():
         t0 = time.time()
         light, frame = run(cfg, refpin.RefVolume, lambda v, cam, w, s: v.raymarch(0, cam, w, s))
@@ -71,4 +107,4 @@ if __name__ == "__main__":
             light_o, frame_o = run(cfg, oracle.OracleVolume, lambda v, cam, w, s: v.raymarch_lit(cam, w, s)[0])
             print(name, "oracle: %.0f s" % (time.time() - t0), "light equal", digests(light_o) == out[name]["light"], "frame equal",
                   digests(frame_o) == out[name]["frame"], flush=True)
-    (HERE / "ref_fullsize_hashes.json").write_text(json.dumps(out, indent=1) + "\n")
+    path.write_text(json.dumps(out, indent=1) + "\n")

@@ -63,3 +63,42 @@ def test_cuda_path_equals_the_reference_shaders_at_full_size(name):
     assert_digests(frame, WANT[name]["frame"], f"{name} frame")
     assert steps > 1e7
     res.release()
+
+
+@pytest.mark.gpu
+def test_cuda_change_dir_light_sequence_equals_the_reference_shaders_at_full_size():
+    """BASELINE.json configs[2]: 512^3, 4 lights, 16 incremental ChangeDirLight updates (update k turns light k % 4 by a further 5 degrees
+    about +Z): the light volume after the reset and after updates 4, 8 and 16 against the reference's ChangeDirLightShader.usf output."""
+    if "cfg3" not in WANT:
+        pytest.skip("ref_fullsize_hashes.json has no cfg3 entry")
+    cfg = mk.CFG3
+    n = cfg["n"]
+    res = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True)
+    URaymarchUtils.SetDataVolume(res, oracle.synth_volume(cfg["volume"], (n, n, n)))
+    URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
+    URaymarchUtils.SetWindowingParameters(res, FWindowingParameters(*cfg["window"]))
+    URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+
+    class Gpu:  # the volume interface mk.run_cfg3 drives
+        def __init__(self, *a):
+            pass
+
+        @property
+        def light(self):
+            return URaymarchUtils.ReadLightVolume(res)
+
+        def add_dir_light(self, light, added, world):
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, light, added, world, bGPUSync=True)
+
+        def change_dir_light(self, old, new, world):
+            assert URaymarchUtils.ChangeDirLightInSingleVolume(res, old, new, world, bGPUSync=True)
+
+    seen = []
+    real_inputs = mk.inputs
+    mk.inputs = lambda cfg: (None, None, None)  # the data volume already sits on the GPU
+    try:
+        mk.run_cfg3(Gpu, lambda k, light: (seen.append(k), assert_digests(light, WANT["cfg3"]["light"][str(k)], f"cfg3 after update {k}")))
+    finally:
+        mk.inputs = real_inputs
+    assert tuple(seen) == tuple(cfg["checkpoints"])
+    res.release()
