@@ -24,6 +24,10 @@ from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters  # noqa:
 
 BLOCK = 64
 
+# BASELINE.json configs[3] on ONE GPU's worth of work: 1024^3, 3 lights, 3840 x 2160, 768 steps (about 20 minutes of CPU for the reference build:
+# generated only with --cfg4). The 8-GPU slab-sharded run must give the same bits (tests/test_gpu_multi.py checks N GPUs against 1).
+CFG4 = dict(volume="perlin", n=1024, lights=[0, 1, 2], view=(3840, 2160), steps=768.0, window=(0.45, 0.5, True, False))
+
 CONFIGS = {
     # BASELINE.json configs[0]; TF soft_ct so that rays do not saturate in one step, default windowing
     "cfg1": dict(volume="sphere", n=256, lights=[0], view=(512, 512), steps=256.0, window=(0.5, 1.0, True, True)),
@@ -96,7 +100,8 @@ if __name__ == "__main__":
         path.write_text(json.dumps(out, indent=1) + "\n")
         sys.exit(0)
     out = json.loads(path.read_text()) if path.exists() else {}
-    for name, cfg in CONFIGS.items():
+    todo = {"cfg4": CFG4} if "--cfg4" in sys.argv else CONFIGS
+    for name, cfg in todo.items():
         t0 = time.time()
         light, frame = run(cfg, refpin.RefVolume, lambda v, cam, w, s: v.raymarch(0, cam, w, s))
         out[name] = {"config": {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}, "light": digests(light), "frame": digests(frame),

@@ -2,7 +2,9 @@
 (per block of 64 Z-slices / image rows, and the checksum of the checksums) of the light volume and the frame that the REFERENCE'S OWN
 shaders produce (compiled for the CPU, oracle/ref.mk; tests/golden/make_golden_ref_fullsize.py) for
   cfg1 = configs[0]: 256^3 sphere R8, 1 light, 512 x 512, 256 steps;
-  cfg2 = configs[1]: 512^3 CT-like Perlin R8, 2 lights, 1920 x 1080, 512 steps, windowing on — the bench.py workload.
+  cfg2 = configs[1]: 512^3 CT-like Perlin R8, 2 lights, 1920 x 1080, 512 steps, windowing on — the bench.py workload;
+  cfg3 = configs[2]: 512^3, 4 lights, 16 incremental ChangeDirLight updates (light volume after the reset and after updates 4, 8, 16);
+  cfg4 = configs[3]: 1024^3, 3 lights, 3840 x 2160, 768 steps (GPU only; one GPU — N GPUs give the same bits, tests/test_gpu_multi.py).
 CPU: the oracle reproduces them (bit-exact). GPU: the CUDA path (TMA-staged fused sweep + fast lit march, through the C ABI) reproduces
 them — at the size the benchmark runs."""
 import ctypes as C
@@ -41,9 +43,11 @@ def test_oracle_equals_the_reference_shaders_at_full_size(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg4"])
 def test_cuda_path_equals_the_reference_shaders_at_full_size(name):
-    cfg = mk.CONFIGS[name]
+    if name not in WANT:
+        pytest.skip(f"ref_fullsize_hashes.json has no {name} entry")
+    cfg = mk.CFG4 if name == "cfg4" else mk.CONFIGS[name]
     n = cfg["n"]
     res = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True)
     data = oracle.synth_volume(cfg["volume"], (n, n, n))  # bit-identical to the device generator (test_gpu_parity.py)
