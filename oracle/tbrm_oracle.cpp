@@ -1042,8 +1042,10 @@ extern "C" int tbo_raymarch_octree(const tbo_volume* vol, const tbrm_camera* cam
 // Mandelbulb — SDFMarcher.usf
 // ------------------------------------------------------------------------------------------------------------
 namespace {
+int g_mandelbulb_variant = 0;  // 0: the reference's formulation; 1: the transcendental-free power-8 twin of csrc/mandelbulb.cu
+
 // Mandelbulb_SDF — SDFMarcher.usf:24-52
-inline float mandelbulb_sdf(F3 pos, float bailout, float power, int iterations, uint64_t& iters) {
+inline float mandelbulb_sdf_reference(F3 pos, float bailout, float power, int iterations, uint64_t& iters) {
     F3 z = pos;
     float dr = 1.0f, r = 0.0f;
     for (int i = 0; i < iterations; i++) {
@@ -1060,6 +1062,42 @@ inline float mandelbulb_sdf(F3 pos, float bailout, float power, int iterations, 
         z = f3(z.x + pos.x, z.y + pos.y, z.z + pos.z);
     }
     return 0.5f * logf(r) * r / dr;
+}
+
+// NOT the reference's code: the CPU twin of the kernels' Power == 8 fast path (mandelbulb_sdf_p8 in csrc/mandelbulb.cu). The same
+// iteration with cos(theta) = z/r, sin(theta) = rho/r, cos(phi) = x/rho, sin(phi) = y/rho, three angle doublings and r^8 by squaring:
+// only +, -, *, /, sqrt — the same bits on the CPU and on the GPU up to the final log. Selected by tbo_set_mandelbulb_variant(1); the
+// tests use it to check the kernels tightly, and variant 0 to bound how far the fast path strays from the reference's formulation.
+inline float mandelbulb_sdf_p8(F3 pos, float bailout, int iterations, uint64_t& iters) {
+    float zx = pos.x, zy = pos.y, zz = pos.z;
+    float dr = 1.0f, r = 0.0f;
+    for (int i = 0; i < iterations; i++) {
+        const float r2 = ((zx * zx) + (zy * zy)) + (zz * zz);
+        r = sqrtf(r2);
+        if (r > bailout) break;
+        ++iters;
+        const float r4 = r2 * r2, r8 = r4 * r4;
+        const float r7 = (r4 * r2) * r;
+        dr = r7 * 8.0f * dr + 1.0f;
+        const float rho2 = (zx * zx) + (zy * zy);
+        const float rho = sqrtf(rho2);
+        float ct = zz / r, st = rho / r;
+        float cp = rho > 0.0f ? zx / rho : 1.0f, sp = rho > 0.0f ? zy / rho : 0.0f;
+        for (int d = 0; d < 3; ++d) {
+            const float c2 = (ct * ct) - (st * st), s2 = 2.0f * (ct * st);
+            ct = c2, st = s2;
+            const float c3 = (cp * cp) - (sp * sp), s3 = 2.0f * (cp * sp);
+            cp = c3, sp = s3;
+        }
+        zx = r8 * (st * cp) + pos.x;
+        zy = r8 * (sp * st) + pos.y;
+        zz = r8 * ct + pos.z;
+    }
+    return 0.5f * logf(r) * r / dr;
+}
+inline float mandelbulb_sdf(F3 pos, float bailout, float power, int iterations, uint64_t& iters) {
+    if (g_mandelbulb_variant == 1 && power == 8.0f) return mandelbulb_sdf_p8(pos, bailout, iterations, iters);
+    return mandelbulb_sdf_reference(pos, bailout, power, iterations, iters);
 }
 }  // namespace
 
@@ -1311,6 +1349,7 @@ extern "C" int tbo_synth_volume_u8(int kind, const int32_t dims[3], uint32_t see
 // ------------------------------------------------------------------------------------------------------------
 // exported helpers for the known-answer tests
 // ------------------------------------------------------------------------------------------------------------
+extern "C" void tbo_set_mandelbulb_variant(int v) { g_mandelbulb_variant = v; }
 extern "C" float tbo_det_pow(float x, float y) { return det_pow(x, y); }
 extern "C" float tbo_round_to_half(float x) { return round_to_half(x); }
 extern "C" void tbo_sample_windowed_tf(float value, float step, const float* tf, const tbrm_windowing* w, float out[4]) {

@@ -237,3 +237,32 @@ def test_cpp_example_runs_end_to_end(tmp_path):
     assert "48 x 40 x 32 voxels" in out.stdout and "normalised to G16" in out.stdout
     steps = [int(l.split(":")[1].split()[0]) for l in out.stdout.splitlines() if "march:" in l]
     assert len(steps) == 3 and all(s > 0 for s in steps) and steps[1] < steps[0]  # the intensity march stops at its first sample
+
+
+def test_mandelbulb_power8_kernels_match_their_cpu_twin():
+    """Power == 8 runs the transcendental-free iteration (mandelbulb_sdf_p8): only +, -, *, /, sqrt and one log, so the oracle's variant 1
+    (the same arithmetic on the CPU) must agree far more tightly than the reference formulation does; another power takes the
+    transcendental path and is compared with the usual budget."""
+    from tbraymarcherplugin_b200.raymarch_utils import FMandelbulbParameters
+
+    L = oracle.lib()
+    world, cam = synth.identity_world(), synth.benchmark_camera(240, 135, jitter=False)
+    mb = FMandelbulbParameters(MaxSteps=256.0, MaxIterations=16.0)
+    got, iters = URaymarchUtils.PerformMandelbulbRaymarchReturnDistance(mb, cam, world)
+    gsdf, _ = URaymarchUtils.CalculateMandelbulbSDF((40, 36, 32), (0.1, 0.0, -0.05), 2.4, 8.0, g16=False)
+    try:
+        L.tbo_set_mandelbulb_variant(1)
+        twin, twin_iters = oracle.mandelbulb(mb, cam, world)
+        tsdf, _ = oracle.mandelbulb_sdf((40, 36, 32), (0.1, 0.0, -0.05), 2.4, 8.0, False)
+    finally:
+        L.tbo_set_mandelbulb_variant(0)
+    ref, _ = oracle.mandelbulb(mb, cam, world)
+    bad_twin = (np.abs(got - twin).max(-1) > 1e-4).mean()
+    bad_ref = (np.abs(got - ref).max(-1) > 1e-4).mean()
+    assert bad_twin <= 0.005 and bad_ref <= 0.02, (bad_twin, bad_ref)
+    assert abs(iters - twin_iters) / twin_iters < 5e-3
+    assert (np.abs(gsdf - tsdf) > 1e-5).mean() <= 0.01
+    mb6 = FMandelbulbParameters(MaxSteps=64.0, MaxIterations=8.0, Power=6.0)
+    got6, _ = URaymarchUtils.PerformMandelbulbRaymarchReturnDistance(mb6, cam, world)
+    ref6, _ = oracle.mandelbulb(mb6, cam, world)
+    assert (np.abs(got6 - ref6).max(-1) > 1e-4).mean() <= 0.02

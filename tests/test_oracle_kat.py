@@ -231,3 +231,34 @@ def test_oracle_synth_generator_equals_numpy_twin():
     for kind, fn in (("sphere", synth.sphere_volume), ("perlin", synth.perlin_ct_volume)):
         dims = (24, 20, 28)
         assert np.array_equal(oracle.synth_volume(kind, dims), fn(dims)), kind
+
+
+def test_mandelbulb_power8_twin_stays_close_to_the_reference_formulation():
+    """The kernels iterate Power == 8 without transcendentals (angle doubling, r^8 by squaring: csrc/mandelbulb.cu); the oracle carries the
+    same arithmetic as variant 1. Against the reference's formulation (variant 0, bit-identical to SDFMarcher.usf compiled for the CPU) it
+    differs by rounding only, which the iteration amplifies next to the surface: well under 1 % of the pixels / voxels move by more than
+    1e-4 — the same order as libm-vs-CUDA transcendentals, and far inside the 2 % budget of the GPU tests."""
+    from tbraymarcherplugin_b200.raymarch_utils import FMandelbulbParameters
+
+    L = oracle.lib()
+    world, cam = synth.identity_world(), synth.benchmark_camera(240, 135, jitter=False)
+    mb = FMandelbulbParameters(MaxSteps=256.0, MaxIterations=16.0)
+    try:
+        L.tbo_set_mandelbulb_variant(0)
+        d0, i0 = oracle.mandelbulb(mb, cam, world)
+        n0, _ = oracle.mandelbulb_normal(mb, 0.01, cam, world)
+        s0, _ = oracle.mandelbulb_sdf((40, 36, 32), (0.1, 0.0, -0.05), 2.4, 8.0, False)
+        L.tbo_set_mandelbulb_variant(1)
+        d1, i1 = oracle.mandelbulb(mb, cam, world)
+        n1, _ = oracle.mandelbulb_normal(mb, 0.01, cam, world)
+        s1, _ = oracle.mandelbulb_sdf((40, 36, 32), (0.1, 0.0, -0.05), 2.4, 8.0, False)
+        other, _ = oracle.mandelbulb(FMandelbulbParameters(MaxSteps=64.0, MaxIterations=8.0, Power=6.0), cam, world)
+        L.tbo_set_mandelbulb_variant(0)
+        other0, _ = oracle.mandelbulb(FMandelbulbParameters(MaxSteps=64.0, MaxIterations=8.0, Power=6.0), cam, world)
+    finally:
+        L.tbo_set_mandelbulb_variant(0)
+    assert (d0[..., 1] == 1).mean() > 0.3 and not np.array_equal(d0, d1)
+    assert (np.abs(d0 - d1).max(-1) > 1e-4).mean() < 0.005 and abs(i0 - i1) / i0 < 1e-3
+    assert (n0[..., 3] != n1[..., 3]).mean() < 0.005
+    assert (np.abs(s0 - s1) > 1e-4).mean() < 0.01
+    assert np.array_equal(other, other0)  # any other power takes the reference's formulation in both variants
