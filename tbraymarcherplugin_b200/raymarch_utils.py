@@ -423,6 +423,37 @@ class URaymarchUtils:
         return out, int(iters.value)
 
 
+    # ---- the small helpers of the function library (RaymarchUtils.cpp:219-252) ----------------------------------------
+    @staticmethod
+    def GetVolumeTextureDimensions(Resources: Optional[FBasicRaymarchRenderingResources]) -> Tuple[int, int, int]:
+        """(0, 0, 0) for a missing texture (RaymarchUtils.cpp:219-230)."""
+        return tuple(Resources.DataDims) if Resources is not None and Resources.handle is not None else (0, 0, 0)
+
+    @staticmethod
+    def LocalToTextureCoords(LocalCoords: Vec3) -> Vec3:  # RaymarchUtils.cpp:244-247: the mesh is [-1,1]^3 there
+        return tuple(c / 2.0 + 0.5 for c in LocalCoords)
+
+    @staticmethod
+    def TextureToLocalCoords(TextureCoords: Vec3) -> Vec3:  # RaymarchUtils.cpp:249-252
+        return tuple((c - 0.5) * 2.0 for c in TextureCoords)
+
+    @staticmethod
+    def TransformToMatrix(Transform: FTransform, WithScaling: bool = True) -> np.ndarray:
+        """FTransform::ToMatrixWithScale / ToMatrixNoScale (RaymarchUtils.cpp:232-242): 4x4, row-vector convention (rows = axes, row 3 =
+        translation)."""
+        x, y, z, w = (float(c) for c in Transform.Rotation)
+        sx, sy, sz = (float(c) for c in Transform.Scale3D) if WithScaling else (1.0, 1.0, 1.0)
+        x2, y2, z2 = x + x, y + y, z + z
+        xx2, yy2, zz2 = x * x2, y * y2, z * z2
+        yz2, wx2, xy2, wz2, xz2, wy2 = y * z2, w * x2, x * y2, w * z2, x * z2, w * y2
+        m = np.zeros((4, 4))
+        m[0, :3] = ((1.0 - (yy2 + zz2)) * sx, (xy2 + wz2) * sx, (xz2 - wy2) * sx)
+        m[1, :3] = ((xy2 - wz2) * sy, (1.0 - (xx2 + zz2)) * sy, (yz2 + wx2) * sy)
+        m[2, :3] = ((xz2 + wy2) * sz, (yz2 - wx2) * sz, (1.0 - (xx2 + yy2)) * sz)
+        m[3, :3] = tuple(float(c) for c in Transform.Translation)
+        m[3, 3] = 1.0
+        return m
+
     # ---- the other materials and the octree (SURVEY.md §8(f) row 2) ----------------------------------------------
     @staticmethod
     def GenerateOctree(Resources: FBasicRaymarchRenderingResources) -> None:

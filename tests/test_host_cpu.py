@@ -232,3 +232,20 @@ def test_exact_division_free_sequences():
         e = (-(q.astype(np.float64)) * float(w32) + x.astype(np.float64)).astype(np.float32)
         q2 = (e.astype(np.float64) * float(rw) + q.astype(np.float64)).astype(np.float32)
         assert np.array_equal(q2, x / w32), w
+
+
+def test_small_helpers_of_the_function_library():
+    """RaymarchUtils.cpp:219-252: coordinate helpers and TransformToMatrix (FTransform::ToMatrixWithScale: row-vector convention)."""
+    assert URaymarchUtils.LocalToTextureCoords((-1.0, 0.0, 1.0)) == (0.0, 0.5, 1.0)
+    assert URaymarchUtils.TextureToLocalCoords((0.0, 0.5, 1.0)) == (-1.0, 0.0, 1.0)
+    assert URaymarchUtils.GetVolumeTextureDimensions(None) == (0, 0, 0)
+    assert URaymarchUtils.GetVolumeTextureDimensions(FBasicRaymarchRenderingResources()) == (0, 0, 0)
+    t = FTransform.from_axis_angle((0, 0, 1), 90.0, (5.0, 6.0, 7.0), (2.0, 3.0, 4.0))
+    m = URaymarchUtils.TransformToMatrix(t)
+    p = np.array([1.0, 0.0, 0.0, 1.0]) @ m  # scale, rotate +90 degrees about Z, translate
+    assert np.allclose(p[:3], (5.0, 8.0, 7.0)) and np.allclose(m[3], (5, 6, 7, 1))
+    r = URaymarchUtils.TransformToMatrix(t, WithScaling=False)
+    assert np.allclose(r[:3, :3] @ r[:3, :3].T, np.eye(3)) and np.allclose(np.linalg.det(r[:3, :3]), 1.0)
+    # consistent with the library's InverseTransformPosition (the WorldToLocal the kernels use): world -> local -> world
+    lp = np.linalg.inv(m)
+    assert np.allclose((np.array([5.0, 8.0, 7.0, 1.0]) @ lp)[:3], (1.0, 0.0, 0.0))
