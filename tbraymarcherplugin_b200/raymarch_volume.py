@@ -195,6 +195,29 @@ class ARaymarchVolume:
         self.bRequestedRecompute = True
         self.bRequestedOctreeRebuild = True
 
+    def SetVolumeAsset(self, RaymarchResources: FBasicRaymarchRenderingResources, ImageInfo=None, TransferFuncCurve=None,
+                       DefaultWindowingParameters=None) -> bool:
+        """SetVolumeAsset with the asset taken apart: resources whose data volume is the asset's texture (e.g. from
+        UMHDLoader.CreateVolumeFromFile), its FVolumeInfo, TF curve (256 x RGBA; None: MakeDefaultTFTexture, :511-514) and default
+        windowing. The mesh scale becomes WorldDimensions / 10 — "Unreal units are in cm, MHD and Dicoms both have sizes in mm" (:545-546) —
+        and a full light recompute plus an octree rebuild are requested (:549-554)."""
+        if RaymarchResources is None or RaymarchResources.handle is None:
+            return False
+        self.RaymarchResources = RaymarchResources
+        if TransferFuncCurve is not None:
+            self.ops.ColorCurveToTexture(RaymarchResources, TransferFuncCurve)
+        else:
+            self.ops.MakeDefaultTFTexture(RaymarchResources)
+        RaymarchResources.bIsInitialized = True
+        if DefaultWindowingParameters is not None:
+            RaymarchResources.WindowingParameters = DefaultWindowingParameters
+            self.ops.SetWindowingParameters(RaymarchResources, DefaultWindowingParameters)
+        if ImageInfo is not None:
+            t = self.ComponentTransform
+            self.ComponentTransform = FTransform(t.Translation, t.Rotation, tuple(float(d) / 10.0 for d in ImageInfo.WorldDimensions))
+        self.OnVolumeLoaded()
+        return True
+
     def Render(self, Camera, rows=None):
         """What UE's renderer does with the selected material (RaymarchVolume.cpp:144-152, 789-800): the entry point of M_Raymarch,
         M_Intensity_Raymarch or M_Octree_Raymarch for every covered pixel. Returns (rgba, executed_steps)."""

@@ -150,3 +150,35 @@ def test_octree_is_rebuilt_once_and_only_while_the_octree_material_is_selected()
     vol.Render(camera)
     assert ops.calls[1:] == [("octree_march", 200.0, 2), ("intensity", 200.0), ("lit", 200.0)]
     assert vol.Tick().action == "incremental"  # back under the lit material the moved light is finally updated
+
+
+def test_set_volume_asset_scales_the_mesh_and_requests_recompute_and_octree_rebuild():
+    """RaymarchVolume.cpp:467-560: TF (default ramp without a curve), windowing, mesh scale = WorldDimensions / 10 (mm -> cm), full light
+    recompute and octree rebuild requested."""
+    class Ops(RecordingMaterialOps):
+        def MakeDefaultTFTexture(self, res):
+            self.calls.append(("default_tf",))
+
+        def ColorCurveToTexture(self, res, curve):
+            self.calls.append(("curve_tf",))
+
+        def SetWindowingParameters(self, res, w):
+            self.calls.append(("window", w.Center, w.Width))
+
+    class Info:
+        WorldDimensions = (320.0, 240.0, 125.0)
+
+    from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters
+
+    ops = Ops()
+    vol = ARaymarchVolume(FBasicRaymarchRenderingResources(), [ARaymarchLight((1.0, 0.0, -0.3), 1.0, "L0")], ops=ops)
+    assert vol.SetVolumeAsset(FBasicRaymarchRenderingResources()) is False  # no texture: nothing happens (:469-472)
+    res = FBasicRaymarchRenderingResources()
+    res._h = object()  # stands for a created resource set
+    assert vol.SetVolumeAsset(res, Info(), None, FWindowingParameters(0.4, 0.3, True, False))
+    assert ops.calls == [("default_tf",), ("window", 0.4, 0.3)]
+    assert vol.ComponentTransform.Scale3D == (32.0, 24.0, 12.5) and vol.WorldParameters.VolumeTransform.Scale3D == (32.0, 24.0, 12.5)
+    assert vol.bRequestedRecompute and vol.bRequestedOctreeRebuild and res.bIsInitialized
+    ops.calls.clear()
+    assert vol.Tick().action == "reset" and ops.calls[0] == ("clear", 0.0)
+    res._h = None  # do not let __del__ hand the stand-in to the library
