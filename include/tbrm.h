@@ -370,6 +370,11 @@ tbrm_status tbrm_convert_volume_to_float(int device, int voxel_format, const voi
  * return TBRM_ERR_UNSUPPORTED. */
 tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
                                  tbrm_volume_info* info, tbrm_resources** out);
+/* UVolumeTextureToolkit::LoadRawIntoNewVolumeTextureAsset / LoadRawFileIntoArray / LoadZLibCompressedFileIntoArray (TextureUtilities.h:67-75,
+ * 85-101; TextureUtilities.cpp:262-302): the same without a header — dims[0] x dims[1] x dims[2] voxels of `voxel_format` read from
+ * `raw_path` (zlib-compressed when compressed_bytes > 0), converted like above; `info` is filled in as if a header had described the file. */
+tbrm_status tbrm_load_raw_volume(int device, const char* raw_path, const int32_t dims[3], int voxel_format, int64_t compressed_bytes, int normalize,
+                                 int convert_to_float, tbrm_format light_fmt, int half_res, tbrm_volume_info* info, tbrm_resources** out);
 
 /* ---- queue control ------------------------------------------------------------------------------------ */
 tbrm_status tbrm_flush(tbrm_resources* res); /* FlushRenderingCommands(): wait for the resource set's stream */

@@ -204,6 +204,7 @@ PROTOTYPES = {
     "tbrm_normalize_volume": (_I, [_I, _I, _P, _I, C.c_uint64, _P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tbrm_convert_volume_to_float": (_I, [_I, _I, _P, _I, C.c_uint64, _P, _I]),
     "tbrm_load_mhd_volume": (_I, [_I, C.c_char_p, _I, _I, _I, _I, C.POINTER(VolumeInfo), C.POINTER(_P)]),
+    "tbrm_load_raw_volume": (_I, [_I, C.c_char_p, C.POINTER(C.c_int32), _I, C.c_int64, _I, _I, _I, _I, C.POINTER(VolumeInfo), C.POINTER(_P)]),
     "tbrm_flush": (_I, [_P]),
     "tbrm_stream": (_P, [_P]),
     "tbrm_set_stream": (_I, [_P, _P]),

@@ -1021,25 +1021,11 @@ tbrm_status tbrm_convert_volume_to_float(int device, int voxel_format, const voi
     return TBRM_OK;
 }
 
-tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
-                                 tbrm_volume_info* info, tbrm_resources** out) {
-    TBRM_REQUIRE(mhd_path && info && out, "tbrm_load_mhd_volume: null argument");
-    *out = nullptr;
-    std::string text;
-    {
-        FILE* f = std::fopen(mhd_path, "rb");
-        if (!f) {
-            set_last_error(std::string("tbrm_load_mhd_volume: cannot read ") + mhd_path);
-            return TBRM_ERR_INVALID_ARGUMENT;
-        }
-        char buf[4096];
-        size_t n;
-        while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
-        std::fclose(f);
-    }
-    tbrm_status s = tbrm_mhd_parse_header(text.c_str(), info);
-    if (s != TBRM_OK) return s;
-    TBRM_REQUIRE(info->dims[0] > 0 && info->dims[1] > 0 && info->dims[2] > 0, "tbrm_load_mhd_volume: DimSize has a zero dimension");
+// IVolumeLoader::LoadAndConvertData (VolumeLoader.cpp:88-128) + CreateVolumeTextureTransient + InitializeRaymarchResources: the voxels of
+// `data_path` described by `info`, converted on the GPU, as the data volume of a new resource set
+static tbrm_status load_volume_from_info(int device, const std::string& data_path, int normalize, int convert_to_float, tbrm_format light_fmt,
+                                         int half_res, tbrm_volume_info* info, tbrm_resources** out, const char* who) {
+    TBRM_REQUIRE(info->dims[0] > 0 && info->dims[1] > 0 && info->dims[2] > 0, std::string(who) + ": the volume has a zero dimension");
     // ConvertData (VolumeLoader.cpp:97-128) decides the texture format
     const int of = info->original_format;
     tbrm_format data_fmt;
@@ -1052,24 +1038,21 @@ tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize
     else if (info->bytes_per_voxel == 2)
         data_fmt = TBRM_FMT_G16;  // UnsignedShort / SignedShort -> PF_G16
     else {
-        set_last_error("tbrm_load_mhd_volume: unnormalised 32-bit integer voxels map to PF_R32_SINT, which the path does not sample");
+        set_last_error(std::string(who) + ": unnormalised 32-bit integer voxels map to PF_R32_SINT, which the path does not sample");
         return TBRM_ERR_UNSUPPORTED;
     }
-    std::string dir(mhd_path);
-    const size_t slash = dir.find_last_of("/\\");
-    dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
     std::vector<uint8_t> voxels;
     std::string err;
-    if (!load_voxel_file(dir + "/" + info->data_file, *info, voxels, err)) {  // LoadRawDataFileFromInfo: FilePath + "/" + DataFileName
-        set_last_error("tbrm_load_mhd_volume: " + err);
+    if (!load_voxel_file(data_path, *info, voxels, err)) {
+        set_last_error(std::string(who) + ": " + err);
         return TBRM_ERR_INVALID_ARGUMENT;
     }
-    s = tbrm_create(device, info->dims, data_fmt, light_fmt, half_res, out);
+    tbrm_status s = tbrm_create(device, info->dims, data_fmt, light_fmt, half_res, out);
     if (s != TBRM_OK) return s;
     tbrm_resources* r = *out;
     const uint64_t count = (uint64_t) r->data_voxels();
     if (cudaMalloc(&r->data, (size_t) count * r->data_elem()) != cudaSuccess) {
-        set_last_error("tbrm_load_mhd_volume: cudaMalloc(data volume) failed");
+        set_last_error(std::string(who) + ": cudaMalloc(data volume) failed");
         r->data = nullptr;
         tbrm_destroy(r);
         *out = nullptr;
@@ -1093,6 +1076,48 @@ tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize
     }
     r->data_ready = true;
     return TBRM_OK;
+}
+
+tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
+                                 tbrm_volume_info* info, tbrm_resources** out) {
+    TBRM_REQUIRE(mhd_path && info && out, "tbrm_load_mhd_volume: null argument");
+    *out = nullptr;
+    std::string text;
+    {
+        FILE* f = std::fopen(mhd_path, "rb");
+        if (!f) {
+            set_last_error(std::string("tbrm_load_mhd_volume: cannot read ") + mhd_path);
+            return TBRM_ERR_INVALID_ARGUMENT;
+        }
+        char buf[4096];
+        size_t n;
+        while ((n = std::fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, n);
+        std::fclose(f);
+    }
+    tbrm_status s = tbrm_mhd_parse_header(text.c_str(), info);
+    if (s != TBRM_OK) return s;
+    std::string dir(mhd_path);
+    const size_t slash = dir.find_last_of("/\\");
+    dir = slash == std::string::npos ? std::string(".") : dir.substr(0, slash);
+    // LoadRawDataFileFromInfo: FilePath + "/" + DataFileName
+    return load_volume_from_info(device, dir + "/" + info->data_file, normalize, convert_to_float, light_fmt, half_res, info, out, "tbrm_load_mhd_volume");
+}
+
+tbrm_status tbrm_load_raw_volume(int device, const char* raw_path, const int32_t dims[3], int voxel_format, int64_t compressed_bytes, int normalize,
+                                 int convert_to_float, tbrm_format light_fmt, int half_res, tbrm_volume_info* info, tbrm_resources** out) {
+    TBRM_REQUIRE(raw_path && dims && info && out, "tbrm_load_raw_volume: null argument");
+    *out = nullptr;
+    TBRM_REQUIRE(voxel_format_bytes(voxel_format) > 0, "tbrm_load_raw_volume: unknown voxel format");
+    std::memset(info, 0, sizeof(*info));
+    info->parse_ok = 1;
+    for (int k = 0; k < 3; ++k) info->dims[k] = dims[k], info->spacing[k] = 1.0, info->world_dims[k] = (double) dims[k];
+    info->original_format = info->actual_format = voxel_format;
+    info->bytes_per_voxel = voxel_format_bytes(voxel_format);
+    info->is_signed = (voxel_format == TBRM_VOXEL_I8 || voxel_format == TBRM_VOXEL_I16 || voxel_format == TBRM_VOXEL_I32 || voxel_format == TBRM_VOXEL_F32);
+    info->min_value = -1000.0f, info->max_value = 3000.0f;
+    info->is_compressed = compressed_bytes > 0, info->compressed_bytes = compressed_bytes > 0 ? compressed_bytes : 0;
+    std::snprintf(info->data_file, sizeof(info->data_file), "%s", raw_path);
+    return load_volume_from_info(device, raw_path, normalize, convert_to_float, light_fmt, half_res, info, out, "tbrm_load_raw_volume");
 }
 
 // ---- queue control ----------------------------------------------------------------------------------------

@@ -577,21 +577,39 @@ class UMHDLoader:
         light_fmt = FMT_R32F if bLightVolume32Bit else FMT_G8
         check(lib.tbrm_load_mhd_volume(device, str(FileName).encode(), int(bNormalize), int(bConvertToFloat), light_fmt, int(LightVolumeHalfResolution),
                                        C.byref(info.c), C.byref(h)))
-        res = FBasicRaymarchRenderingResources()
-        res._h = h
-        res.Device = device
-        res.DataDims = info.Dimensions
-        ld = (C.c_int32 * 3)()
-        check(lib.tbrm_light_volume_dims(h, ld))
-        res.LightDims = (ld[0], ld[1], ld[2])
-        res.DataFormat = {0: FMT_G8, 2: FMT_G16, 6: FMT_R32F}.get(info.ActualFormat, FMT_G8 if info.BytesPerVoxel == 1 else FMT_G16)
-        res.LightFormat = light_fmt
-        res.bLightVolume32Bit = bLightVolume32Bit
-        res.LightVolumeHalfResolution = LightVolumeHalfResolution
-        return res, info
+        return _wrap_loaded_resources(h, info, light_fmt, bLightVolume32Bit, LightVolumeHalfResolution, device), info
+
+
+def _wrap_loaded_resources(h, info: "FVolumeInfo", light_fmt: int, bLightVolume32Bit: bool, LightVolumeHalfResolution: bool,
+                           device: int) -> FBasicRaymarchRenderingResources:
+    res = FBasicRaymarchRenderingResources()
+    res._h = h
+    res.Device = device
+    res.DataDims = info.Dimensions
+    ld = (C.c_int32 * 3)()
+    check(_capi.load().tbrm_light_volume_dims(h, ld))
+    res.LightDims = (ld[0], ld[1], ld[2])
+    res.DataFormat = {0: FMT_G8, 2: FMT_G16, 6: FMT_R32F}.get(info.ActualFormat, FMT_G8 if info.BytesPerVoxel == 1 else FMT_G16)
+    res.LightFormat = light_fmt
+    res.bLightVolume32Bit = bLightVolume32Bit
+    res.LightVolumeHalfResolution = LightVolumeHalfResolution
+    return res
 
 
 class UVolumeTextureToolkit:
+    @staticmethod
+    def LoadRawIntoNewVolume(RawFileName: str, Dimensions: Sequence[int], dtype, bNormalize: bool = True, bConvertToFloat: bool = False,
+                             CompressedByteSize: int = 0, bLightVolume32Bit: bool = False, LightVolumeHalfResolution: bool = False, device: int = 0):
+        """UVolumeTextureToolkit::LoadRawIntoNewVolumeTextureAsset (TextureUtilities.h:85-101) + InitializeRaymarchResources: a headerless raw
+        (or zlib, CompressedByteSize > 0) file of Dimensions voxels of numpy type dtype. Returns (resources, FVolumeInfo)."""
+        info = FVolumeInfo()
+        h = C.c_void_p()
+        light_fmt = FMT_R32F if bLightVolume32Bit else FMT_G8
+        check(_capi.load().tbrm_load_raw_volume(device, str(RawFileName).encode(), (C.c_int32 * 3)(*map(int, Dimensions)), _VOXEL_OF_NP[np.dtype(dtype)],
+                                                int(CompressedByteSize), int(bNormalize), int(bConvertToFloat), light_fmt,
+                                                int(LightVolumeHalfResolution), C.byref(info.c), C.byref(h)))
+        return _wrap_loaded_resources(h, info, light_fmt, bLightVolume32Bit, LightVolumeHalfResolution, device), info
+
     @staticmethod
     def NormalizeArrayByFormat(array: np.ndarray, device: int = 0):
         """TextureUtilities.cpp:304-327 on the GPU. Returns (normalised uint8 / uint16 array, original min, original max)."""

@@ -266,3 +266,19 @@ def test_mandelbulb_power8_kernels_match_their_cpu_twin():
     got6, _ = URaymarchUtils.PerformMandelbulbRaymarchReturnDistance(mb6, cam, world)
     ref6, _ = oracle.mandelbulb(mb6, cam, world)
     assert (np.abs(got6 - ref6).max(-1) > 1e-4).mean() <= 0.02
+
+
+def test_headerless_raw_file_loads_like_the_mhd_path(tmp_path):
+    from tbraymarcherplugin_b200.raymarch_utils import UVolumeTextureToolkit as T
+
+    dims = (40, 24, 16)
+    raw = (synth.perlin_ct_volume(dims).astype(np.int16) * 9 - 700)
+    (tmp_path / "v.raw").write_bytes(raw.tobytes())
+    (tmp_path / "v.zraw").write_bytes(zlib.compress(raw.tobytes(), 6))
+    want, lo, hi = oracle.normalize_array(3, raw)
+    for name, packed in (("v.raw", 0), ("v.zraw", (tmp_path / "v.zraw").stat().st_size)):
+        res, info = T.LoadRawIntoNewVolume(str(tmp_path / name), dims, np.int16, CompressedByteSize=packed, bLightVolume32Bit=True)
+        assert info.Dimensions == dims and (info.MinValue, info.MaxValue) == (lo, hi) and info.bIsNormalized and res.DataFormat == 1
+        URaymarchUtils.GenerateOctree(res)  # mip 0 of the octree is the (G16) data volume itself
+        assert np.array_equal(URaymarchUtils.ReadOctreeMip(res, 0)[:dims[2], :dims[1], :dims[0]], want)
+        res.release()

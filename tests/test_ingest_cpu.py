@@ -118,3 +118,19 @@ def test_cpp_example_builds_against_the_c_abi_and_fails_loudly(tmp_path):
     (tmp_path / "bad.mhd").write_text("DimSize = 4 4 4\nElementType = MET_UCHAR\nElementDataFile = x.raw\n")  # no ElementSpacing
     out = subprocess.run([str(exe), str(tmp_path / "bad.mhd")], capture_output=True, text=True)
     assert out.returncode == 1 and "required" in out.stderr
+
+
+def test_raw_loader_validates_before_touching_a_device(tmp_path):
+    lib = _capi.load()
+    h, info = C.c_void_p(), _capi.VolumeInfo()
+    dims = (C.c_int32 * 3)(4, 4, 4)
+    args = (1, 0, 0, 0, C.byref(info), C.byref(h))
+    assert lib.tbrm_load_raw_volume(0, str(tmp_path / "missing.raw").encode(), dims, 0, 0, *args) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    assert b"cannot open" in lib.tbrm_last_error()
+    assert lib.tbrm_load_raw_volume(0, b"x.raw", dims, 42, 0, *args) == _capi.TBRM_ERR_INVALID_ARGUMENT  # unknown voxel format
+    (tmp_path / "short.raw").write_bytes(b"\\0" * 10)
+    assert lib.tbrm_load_raw_volume(0, str(tmp_path / "short.raw").encode(), dims, 0, 0, *args) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    assert b"fewer bytes" in lib.tbrm_last_error()
+    # unnormalised 32-bit integers have no texture format the path samples (PF_R32_SINT in the reference: "experimental")
+    (tmp_path / "i32.raw").write_bytes(b"\\0" * 256)
+    assert lib.tbrm_load_raw_volume(0, str(tmp_path / "i32.raw").encode(), dims, 5, 0, 0, 0, 0, 0, C.byref(info), C.byref(h)) == _capi.TBRM_ERR_UNSUPPORTED
