@@ -339,7 +339,7 @@ typedef struct tbrm_volume_info {
     double world_dims[3];      /* WorldDimensions = Spacing * Dimensions */
     int32_t original_format;   /* tbrm_voxel_format of the file */
     int32_t actual_format;     /* after normalisation / float conversion (ConvertData, VolumeLoader.cpp:97-128) */
-    int32_t bytes_per_voxel;   /* of the file */
+    int32_t bytes_per_voxel;   /* of the file; 2 once a multi-byte volume has been normalised (ConvertData, VolumeLoader.cpp:106-110) */
     int32_t is_signed;
     int32_t is_normalized;     /* bIsNormalized */
     float min_value, max_value; /* MinValue / MaxValue of the original data (defaults -1000 / 3000) */
@@ -356,6 +356,11 @@ float tbrm_volume_info_normalize_value(const tbrm_volume_info* info, float value
 float tbrm_volume_info_denormalize_value(const tbrm_volume_info* info, float value);
 float tbrm_volume_info_normalize_range(const tbrm_volume_info* info, float range);
 float tbrm_volume_info_denormalize_range(const tbrm_volume_info* info, float range);
+/* IVolumeLoader::ConvertData's decision (VolumeLoader.cpp:97-128) + FVolumeInfo::VoxelFormatToPixelFormat (VolumeInfo.cpp:99-122): which voxel
+ * format the loaded volume ends up in (*out_actual_format, a tbrm_voxel_format) and which texture format that is (*out_texture_format, a
+ * tbrm_format; -1 for PF_R32_SINT — unnormalised 32-bit integers —, which the path does not sample). Host only. */
+tbrm_status tbrm_converted_format(const tbrm_volume_info* info, int normalize, int convert_to_float, int* out_texture_format,
+                                  int* out_actual_format);
 /* UVolumeTextureToolkit::NormalizeArrayByFormat (TextureUtilities.cpp:304-327) on the GPU: min / max of `count` voxels of
  * voxel_format, then every voxel mapped to the full range of uint8 (1-byte inputs) or uint16 (all others), truncating like the
  * reference. src / dst: host or device memory. out_min / out_max: the original extremes (as floats). */

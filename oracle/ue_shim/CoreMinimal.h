@@ -20,7 +20,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
+#include <utility>
+#include <vector>
 
 using std::abs;  // the reference calls unqualified abs() on doubles (MSVC resolves it to the double overload)
 
@@ -50,13 +53,31 @@ typedef char TCHAR;
 #define DECLARE_MULTICAST_DELEGATE_OneParam(...)
 #define WITH_EDITOR 0
 #define UE_SMALL_NUMBER (1.e-8)
+#define UINTERFACE(...)
+#define UE_LOG(...) ((void) 0)
+#define DEFINE_LOG_CATEGORY(x)
+#define TCHAR_TO_UTF8(x) (x)
+#define MoveTemp(x) std::move(x)
 
+enum class ESearchCase { CaseSensitive, IgnoreCase };
+enum class ESearchDir { FromStart, FromEnd };
 struct FString {
     std::string s;
     FString() {}
     FString(const char* c) : s(c) {}
     FString(const std::string& c) : s(c) {}
     static FString SanitizeFloat(double v) { return FString(std::to_string(v)); }
+    const TCHAR* operator*() const { return s.c_str(); }
+    int32 Find(const FString& sub, ESearchCase = ESearchCase::IgnoreCase, ESearchDir dir = ESearchDir::FromStart) const {
+        const size_t p = dir == ESearchDir::FromEnd ? s.rfind(sub.s) : s.find(sub.s);
+        return p == std::string::npos ? -1 : (int32) p;
+    }
+    void RightChopInline(int32 n) { s = n <= 0 ? s : (n >= (int32) s.size() ? std::string() : s.substr((size_t) n)); }
+    void ReplaceCharInline(char from, char to) {
+        for (char& c : s)
+            if (c == from) c = to;
+    }
+    bool operator==(const FString& o) const { return s == o.s; }
 };
 inline FString operator+(const FString& a, const FString& b) { return FString(a.s + b.s); }
 inline FString operator+(const char* a, const FString& b) { return FString(std::string(a) + b.s); }
@@ -200,11 +221,73 @@ enum EPixelFormat { PF_Unknown = 0, PF_G8, PF_G16, PF_R32_FLOAT, PF_R32_SINT, PF
 enum ETextureSourceFormat { TSF_Invalid = 0, TSF_G8, TSF_G16, TSF_RGBA16F };
 enum TextureAddress { TA_Wrap = 0, TA_Clamp, TA_Mirror };
 
-class UObject {};
+class UObject {
+public:
+    virtual ~UObject() {}
+};
+class UInterface : public UObject {};
 class UDataAsset : public UObject {};
-class UTexture;
+class UTexture : public UObject {};
 class UTexture2D;
-class UVolumeTexture;
+// what the loaders' texture-creation calls leave behind (ref_wrap.cpp fills it in): format, size and a copy of the bulk data
+class UVolumeTexture : public UTexture {
+public:
+    int PixelFormat = 0;
+    int32 SizeX = 0, SizeY = 0, SizeZ = 0;
+    std::vector<uint8> Bulk;
+};
+struct FName {
+    FString Name;
+    FName() {}
+    FName(const FString& n) : Name(n) {}
+};
+enum EObjectFlags { RF_NoFlags = 0, RF_Public = 1, RF_Standalone = 2 };
+inline EObjectFlags operator|(EObjectFlags a, EObjectFlags b) { return (EObjectFlags) ((int) a | (int) b); }
+template <typename T>
+T* NewObject(UObject* = nullptr, FName = FName(), EObjectFlags = RF_NoFlags) { return new T(); }  // never freed: test process
+
+template <typename T>
+class TUniquePtr;
+template <typename T>
+class TUniquePtr<T[]> {
+    std::unique_ptr<T[]> P;
+
+public:
+    TUniquePtr() {}
+    explicit TUniquePtr(T* p) : P(p) {}
+    TUniquePtr(TUniquePtr&&) = default;
+    TUniquePtr& operator=(TUniquePtr&&) = default;
+    T* Get() const { return P.get(); }
+};
+template <typename T>
+struct TArray : std::vector<T> {
+    void Empty() { this->clear(); }
+};
+
+// file-system stand-ins used by VolumeLoader.cpp (plain stdio; project-relative lookups resolve to nothing)
+struct FFileHelper {
+    static bool LoadFileToString(FString& out, const TCHAR* path);
+};
+struct FPaths {
+    static void Split(const FString& full, FString& path, FString& name, FString& ext);
+    static FString MakeValidFileName(const FString& n) { return n; }
+    static FString ProjectContentDir() { return FString(""); }
+    static bool DirectoryExists(const FString&) { return false; }
+};
+struct IFileManager {
+    static IFileManager& Get() {
+        static IFileManager m;
+        return m;
+    }
+    FString ConvertToAbsolutePathForExternalAppForRead(const TCHAR* p) const { return FString(p); }
+};
+struct FFileManagerGeneric {
+    static FFileManagerGeneric& Get() {
+        static FFileManagerGeneric m;
+        return m;
+    }
+    void FindFiles(TArray<FString>&, const TCHAR*, const TCHAR*) const {}
+};
 class UTextureRenderTargetVolume;
 class UCurveLinearColor;
 class URenderTargetVolumeMipped;

@@ -1,0 +1,3 @@
+// SHIM (see CoreMinimal.h in this directory): intentionally empty
+#pragma once
+#include "CoreMinimal.h"

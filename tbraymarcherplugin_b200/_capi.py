@@ -201,6 +201,7 @@ PROTOTYPES = {
     "tbrm_volume_info_denormalize_value": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),
     "tbrm_volume_info_normalize_range": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),
     "tbrm_volume_info_denormalize_range": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),
+    "tbrm_converted_format": (_I, [C.POINTER(VolumeInfo), _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "tbrm_normalize_volume": (_I, [_I, _I, _P, _I, C.c_uint64, _P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tbrm_convert_volume_to_float": (_I, [_I, _I, _P, _I, C.c_uint64, _P, _I]),
     "tbrm_load_mhd_volume": (_I, [_I, C.c_char_p, _I, _I, _I, _I, C.POINTER(VolumeInfo), C.POINTER(_P)]),

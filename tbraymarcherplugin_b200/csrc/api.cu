@@ -80,6 +80,25 @@ static tbrm_status mandelbulb_op(int device, void* dst, size_t bytes, int dst_is
     return s;
 }
 
+// ConvertData (VolumeLoader.cpp:97-128) + VoxelFormatToPixelFormat (VolumeInfo.cpp:99-122)
+static void converted_format(const tbrm_volume_info& info, int normalize, int convert_to_float, int& texture_format, int& actual_format) {
+    const int of = info.original_format;
+    if (normalize)
+        actual_format = info.bytes_per_voxel > 1 ? TBRM_VOXEL_U16 : TBRM_VOXEL_U8;  // "normalize and cap at G16"
+    else if (convert_to_float && of != TBRM_VOXEL_F32)
+        actual_format = TBRM_VOXEL_F32;
+    else
+        actual_format = of;
+    switch (actual_format) {
+        case TBRM_VOXEL_U8:
+        case TBRM_VOXEL_I8: texture_format = TBRM_FMT_G8; break;    // bits as stored
+        case TBRM_VOXEL_U16:
+        case TBRM_VOXEL_I16: texture_format = TBRM_FMT_G16; break;
+        case TBRM_VOXEL_F32: texture_format = TBRM_FMT_R32F; break;
+        default: texture_format = -1; break;                        // PF_R32_SINT: "experimental" in the reference, not sampled by the path
+    }
+}
+
 // the conversions share: staging of a host source, the two scratch buffers, delivery to a host or device destination
 struct IngestBuffers {
     void* d_in = nullptr;
@@ -972,6 +991,14 @@ float tbrm_volume_info_denormalize_range(const tbrm_volume_info* i, float v) {
     return (!i || !i->is_normalized) ? v : (v * (i->max_value - i->min_value));
 }
 
+tbrm_status tbrm_converted_format(const tbrm_volume_info* info, int normalize, int convert_to_float, int* out_texture_format,
+                                  int* out_actual_format) {
+    TBRM_REQUIRE(info && out_texture_format && out_actual_format, "tbrm_converted_format: null argument");
+    TBRM_REQUIRE(voxel_format_bytes(info->original_format) > 0, "tbrm_converted_format: unknown voxel format");
+    converted_format(*info, normalize, convert_to_float, *out_texture_format, *out_actual_format);
+    return TBRM_OK;
+}
+
 tbrm_status tbrm_normalize_volume(int device, int voxel_format, const void* src, int src_is_device, uint64_t count, void* dst,
                                   int dst_is_device, float* out_min, float* out_max) {
     TBRM_REQUIRE(src && dst && count > 0, "tbrm_normalize_volume: null argument or empty volume");
@@ -1026,21 +1053,14 @@ tbrm_status tbrm_convert_volume_to_float(int device, int voxel_format, const voi
 static tbrm_status load_volume_from_info(int device, const std::string& data_path, int normalize, int convert_to_float, tbrm_format light_fmt,
                                          int half_res, tbrm_volume_info* info, tbrm_resources** out, const char* who) {
     TBRM_REQUIRE(info->dims[0] > 0 && info->dims[1] > 0 && info->dims[2] > 0, std::string(who) + ": the volume has a zero dimension");
-    // ConvertData (VolumeLoader.cpp:97-128) decides the texture format
     const int of = info->original_format;
-    tbrm_format data_fmt;
-    if (normalize)
-        data_fmt = info->bytes_per_voxel > 1 ? TBRM_FMT_G16 : TBRM_FMT_G8;
-    else if (convert_to_float || of == TBRM_VOXEL_F32)
-        data_fmt = TBRM_FMT_R32F;
-    else if (info->bytes_per_voxel == 1)
-        data_fmt = TBRM_FMT_G8;   // VoxelFormatToPixelFormat: UnsignedChar / SignedChar -> PF_G8 (bits as stored)
-    else if (info->bytes_per_voxel == 2)
-        data_fmt = TBRM_FMT_G16;  // UnsignedShort / SignedShort -> PF_G16
-    else {
+    int tex = -1, actual = of;
+    converted_format(*info, normalize, convert_to_float, tex, actual);
+    if (tex < 0) {
         set_last_error(std::string(who) + ": unnormalised 32-bit integer voxels map to PF_R32_SINT, which the path does not sample");
         return TBRM_ERR_UNSUPPORTED;
     }
+    const tbrm_format data_fmt = (tbrm_format) tex;
     std::vector<uint8_t> voxels;
     std::string err;
     if (!load_voxel_file(data_path, *info, voxels, err)) {
@@ -1062,10 +1082,9 @@ static tbrm_status load_volume_from_info(int device, const std::string& data_pat
     if (normalize) {
         s = tbrm_normalize_volume(device, of, voxels.data(), 0, count, r->data, 1, &info->min_value, &info->max_value);
         info->is_normalized = 1;
-        info->actual_format = info->bytes_per_voxel > 1 ? TBRM_VOXEL_U16 : TBRM_VOXEL_U8;
+        if (info->bytes_per_voxel > 1) info->bytes_per_voxel = 2;  // VolumeLoader.cpp:106-110; the float conversion leaves it alone (:116-121)
     } else if (convert_to_float && of != TBRM_VOXEL_F32) {
         s = tbrm_convert_volume_to_float(device, of, voxels.data(), 0, count, (float*) r->data, 1);
-        info->actual_format = TBRM_VOXEL_F32;
     } else {
         s = cudaMemcpy(r->data, voxels.data(), voxels.size(), cudaMemcpyHostToDevice) == cudaSuccess ? TBRM_OK : TBRM_ERR_CUDA;
     }
@@ -1074,6 +1093,7 @@ static tbrm_status load_volume_from_info(int device, const std::string& data_pat
         *out = nullptr;
         return s;
     }
+    info->actual_format = actual;
     r->data_ready = true;
     return TBRM_OK;
 }

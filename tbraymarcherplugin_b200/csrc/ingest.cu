@@ -274,7 +274,8 @@ bool mhd_parse_header(const std::string& text, tbrm_volume_info& out) {
     for (const auto& t : kTypes)
         if (type == t.name) fmt = t.fmt;
     if (fmt < 0) return false;
-    out.original_format = out.actual_format = fmt;
+    out.original_format = fmt;
+    out.actual_format = TBRM_VOXEL_U8;  // FVolumeInfo's default (VolumeInfo.h:72-74): ConvertData sets it once the data has been loaded
     out.bytes_per_voxel = voxel_format_bytes(fmt);
     out.is_signed = (fmt == TBRM_VOXEL_I8 || fmt == TBRM_VOXEL_I16 || fmt == TBRM_VOXEL_I32 || fmt == TBRM_VOXEL_F32) ? 1 : 0;  // IsVoxelFormatSigned
     if (words_after(text, "CompressedDataSize", nullptr, in)) {

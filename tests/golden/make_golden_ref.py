@@ -183,10 +183,69 @@ def ingest_case():
     return out
 
 
-CASES = {"ref_hostmath": hostmath_case, "ref_shaders": shaders_case, "ref_materials": materials_case, "ref_ingest": ingest_case}
+LOADER_HEADERS = [
+    "ObjectType = Image\nNDims = 3\nDimSize = 64 48 20\nElementSpacing = 0.5 0.5 1.25\nElementType = MET_SHORT\nElementDataFile = ct_head.raw\n",
+    "NDims = 3\r\nDimSize = 7 8 9\r\nElementSize = 1 2 3\r\nElementType = MET_UCHAR\r\nElementDataFile = a.raw\r\n",
+    "ElementDataFile = a.raw\nElementType = MET_FLOAT\nDimSize = 1 2 3\nElementSpacing = 1e-1 .5 2\n",
+    "DimSize = 10 10 10\nElementSpacing = 1 1 1\nElementType = MET_USHORT\nCompressedData = True\nCompressedDataSize = 12345\nElementDataFile = z.zraw\n",
+    "DimSize\t=\t3   4\n5\nElementSpacing = 1 1 1\nElementType = MET_INT\nElementDataFile = x.raw",
+    "DimSize = 4 4 4\nElementType = MET_UCHAR\nElementDataFile = x.raw\n",                        # no spacing
+    "ElementSpacing = 1 1 1\nElementType = MET_UCHAR\nElementDataFile = x.raw\n",                  # no DimSize
+    "DimSize = 4 4 4\nElementSpacing = 1 1 1\nElementType = MET_DOUBLE\nElementDataFile = x.raw\n",  # unknown element type
+    "DimSize = 4 4 4\nElementSpacing = 1 1 1\nElementType = MET_CHAR\n",                            # no data file
+    "",
+    "DimSize = 4 4 4\nElementSpacing = 1 1 1\nElementType = MET_UINT\nElementDataFile = with space.raw\n",  # a name is ONE word
+]
+INFO_FIELDS = ["parse_ok", "dims", "spacing", "world_dims", "original_format", "actual_format", "bytes_per_voxel", "is_signed", "is_normalized",
+               "min_value", "max_value", "is_compressed", "compressed_bytes"]
+
+
+def info_to_vector(i) -> np.ndarray:
+    v = []
+    for f in INFO_FIELDS:
+        x = getattr(i, f)
+        v.extend(list(x) if hasattr(x, "__len__") else [x])
+    return np.array(v, np.float64)
+
+
+def loaders_case():
+    """The reference's own UMHDLoader::ParseVolumeInfoFromHeader on a set of headers, and the outcome of IVolumeLoader::ConvertData +
+    FVolumeInfo::VoxelFormatToPixelFormat (through UMHDLoader::CreateVolumeFromFile) for every element type and flag combination."""
+    import tempfile
+
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        d = Path(d)
+        parsed, names = [], []
+        for h in LOADER_HEADERS:
+            (d / "h.mhd").write_text(h, newline="")
+            i = refpin.mhd_parse_file(d / "h.mhd")
+            parsed.append(info_to_vector(i))
+            names.append(i.data_file.decode())
+        out["parsed"] = np.stack(parsed)
+        out["data_files"] = np.array(names)
+        table = []
+        for fmt, dt in refpin.VOXEL_DTYPES.items():
+            met = ["MET_UCHAR", "MET_CHAR", "MET_USHORT", "MET_SHORT", "MET_UINT", "MET_INT", "MET_FLOAT"][fmt]
+            raw = (np.arange(2 * 3 * 4) % 7).astype(dt)
+            (d / "v.raw").write_bytes(raw.tobytes())
+            (d / "v.mhd").write_text(f"DimSize = 4 3 2\nElementSpacing = 1 1 1\nElementType = {met}\nElementDataFile = v.raw\n")
+            for nrm in (0, 1):
+                for flt in (0, 1):
+                    info, tex, bulk = refpin.mhd_create_volume(d / "v.mhd", nrm, flt)
+                    table.append([fmt, nrm, flt, tex, info.actual_format, info.bytes_per_voxel, info.is_normalized, len(bulk)])
+        out["conversion_table"] = np.array(table, np.int64)
+    return out
+
+
+CASES = {"ref_hostmath": hostmath_case, "ref_shaders": shaders_case, "ref_materials": materials_case, "ref_ingest": ingest_case,
+         "ref_loaders": loaders_case}
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
     for name, fn in CASES.items():
+        if only and name not in only:
+            continue
         arrays = fn()
         np.savez_compressed(HERE / f"{name}.npz", **arrays)
         print(name, {k: v.shape for k, v in arrays.items()})

@@ -169,3 +169,26 @@ def mandelbulb_sdf(dims, center=(0.0, 0.0, 0.0), extent: float = 2.0, power: flo
     f.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_void_p]
     f((C.c_int32 * 3)(*dims), (C.c_float * 3)(*center), float(extent), float(power), 1 if g16 else 2, out.ctypes.data)
     return out
+
+
+# ---- the reference's own volume loaders (oracle/ref_loaders.cpp: MHDLoader.cpp + VolumeLoader.cpp compiled from /root/reference) -----------------
+def mhd_parse_file(path) -> _capi.VolumeInfo:
+    """UMHDLoader::ParseVolumeInfoFromHeader of the reference on a header file."""
+    out = _capi.VolumeInfo()
+    f = lib().tbref_mhd_parse_file
+    f.argtypes = [C.c_char_p, C.POINTER(_capi.VolumeInfo)]
+    f(str(path).encode(), C.byref(out))
+    return out
+
+
+def mhd_create_volume(path, normalize: bool, convert_to_float: bool):
+    """UMHDLoader::CreateVolumeFromFile of the reference: (FVolumeInfo of the asset, texture format as tbrm_format or -1, bulk data bytes),
+    or None when the reference produces no asset."""
+    info, fmt, nbytes = _capi.VolumeInfo(), C.c_int(), C.c_uint64()
+    buf = np.empty(1 << 24, np.uint8)
+    f = lib().tbref_mhd_create_volume
+    f.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(_capi.VolumeInfo), C.POINTER(C.c_int), C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    if f(str(path).encode(), int(normalize), int(convert_to_float), C.byref(info), C.byref(fmt), buf.ctypes.data, buf.nbytes, C.byref(nbytes)) != 0:
+        return None
+    assert nbytes.value <= buf.nbytes
+    return info, fmt.value, buf[: nbytes.value].copy()
