@@ -112,8 +112,19 @@ def workload_config(n_gpus: int, slabs: bool = True) -> dict:
 # ------------------------------------------------------------------------------------------------------------------
 def reference_build_available() -> bool:
     """oracle/_ref/libtbrm_ref.so: the reference's own shaders and host math compiled for the CPU (oracle/ref.mk). It is built where
-    /root/reference exists and travels to the GPU box as a file."""
-    return (ROOT / "oracle" / "_ref" / "libtbrm_ref.so").exists()
+    /root/reference exists and travels to the GPU box as a file. True only if it is there AND loads (a file built for another machine
+    must not take the bench line down: the oracle port stands in)."""
+    if not (ROOT / "oracle" / "_ref" / "libtbrm_ref.so").exists():
+        return False
+    try:
+        sys.path.insert(0, str(ROOT / "tests"))
+        import refpin
+
+        refpin.lib()
+        return True
+    except Exception as e:  # noqa: BLE001
+        print(f"bench.py: oracle/_ref/libtbrm_ref.so does not load ({e!r}); falling back to the oracle port", file=sys.stderr)
+        return False
 
 
 def oracle_sample(data, data_small, light_after_reset, threads: int, kind: str = "port"):
