@@ -119,3 +119,35 @@ def test_the_oracle_written_goldens_of_the_gpu_tests_are_reference_shader_output
     cam = synth.benchmark_camera(48, 32, jitter=True, frame=3)  # the shader always jitters: only the jitter = 1 frame has a counterpart
     assert np.array_equal(vol.raymarch(0, cam, world, 64.0), frames["rgba_jitter1"])
     assert np.array_equal(vol.raymarch(-1, cam, world, 64.0), frames["setup_jitter1"])
+
+
+@needs_ref
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 3), (1, 7, 1), (16, 1, 1), (7, 3, 1), (5, 4, 6)])
+def test_degenerate_and_ragged_sizes_equal_the_reference_shaders(dims):
+    """Edge cases: one-voxel and one-voxel-thick volumes, odd sizes — random data, three windows, G8 / R32F and half-resolution light volumes,
+    axis-aligned lights, a ChangeDirLight, all three materials and the octree."""
+    rng = np.random.default_rng(sum(dims))
+    data = rng.integers(0, 256, dims[::-1]).astype(np.uint8)
+    tf = oracle.prepare_tf(synth.soft_ct_curve())
+    lights = synth.LIGHTS + [FDirLightParameters((1, 0, 0), 0.7), FDirLightParameters((0, 1, 0), 0.3)]
+    cam = synth.benchmark_camera(24, 16, jitter=True, frame=1)
+    for win in (FWindowingParameters(0.45, 0.5, True, False), FWindowingParameters(0.5, 1.0, True, True), FWindowingParameters(0.2, 0.1, False, False)):
+        for world in (synth.identity_world(), synth.clipped_world()):
+            for light32, half in ((True, False), (False, False), (True, True)):
+                a = oracle.OracleVolume(data, tf, win, light32=light32, half_res=half)
+                b = refpin.RefVolume(data, tf, win, light32=light32, half_res=half)
+                for l in lights:
+                    a.add_dir_light(l, True, world), b.add_dir_light(l, True, world)
+                    assert np.array_equal(a.light, b.light)
+                n = synth.rotate_about_z(synth.LIGHTS[0], 20.0)
+                a.change_dir_light(synth.LIGHTS[0], n, world), b.change_dir_light(synth.LIGHTS[0], n, world)
+                assert np.array_equal(a.light, b.light)
+                if light32:
+                    assert np.array_equal(a.raymarch_lit(cam, world, 17.0)[0], b.raymarch(0, cam, world, 17.0))
+                    assert np.array_equal(oracle.raymarch_intensity(a, cam, world, 17.0)[0], b.raymarch(1, cam, world, 17.0))
+    ma, mb = oracle.generate_octree(data), refpin.generate_octree(data)
+    assert all(np.array_equal(x, y) for x, y in zip(ma, mb))
+    a, b = oracle.OracleVolume(data, tf, FWindowingParameters()), refpin.RefVolume(data, tf, FWindowingParameters())
+    for mip in range(4):
+        assert np.array_equal(oracle.raymarch_octree(a, cam, synth.identity_world(), 17.0, ma, mip)[0],
+                              b.raymarch(2, cam, synth.identity_world(), 17.0, octree=mb, octree_mip=mip))
