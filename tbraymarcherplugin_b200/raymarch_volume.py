@@ -218,6 +218,68 @@ class ARaymarchVolume:
         self.OnVolumeLoaded()
         return True
 
+    # ---- setters: what changes the light volume requests a recompute (RaymarchVolume.cpp:562-577, 746-818) -------------------------
+    def _set_windowing(self, **kw) -> None:
+        w = self.RaymarchResources.WindowingParameters
+        if all(getattr(w, k) == v for k, v in kw.items()):
+            return  # unchanged: nothing happens (:748-749 ...)
+        for k, v in kw.items():
+            setattr(w, k, v)
+        self.ops.SetWindowingParameters(self.RaymarchResources, w)  # SetMaterialWindowingParameters + the compute shaders' uniform
+        self.bRequestedRecompute = True
+
+    def SetWindowCenter(self, Center: float) -> None:
+        self._set_windowing(Center=Center)
+
+    def SetWindowWidth(self, Width: float) -> None:
+        self._set_windowing(Width=Width)
+
+    def SetLowCutoff(self, LowCutoff: bool) -> None:
+        self._set_windowing(LowCutoff=LowCutoff)
+
+    def SetHighCutoff(self, HighCutoff: bool) -> None:
+        self._set_windowing(HighCutoff=HighCutoff)
+
+    def GetWindowCenter(self) -> float:
+        return self.RaymarchResources.WindowingParameters.Center
+
+    def GetWindowWidth(self) -> float:
+        return self.RaymarchResources.WindowingParameters.Width
+
+    def SetTFCurve(self, InTFCurve) -> None:
+        if InTFCurve is None:
+            return
+        self.ops.ColorCurveToTexture(self.RaymarchResources, InTFCurve)
+        self.ops.FlushRenderingCommands(self.RaymarchResources)
+        self.bRequestedRecompute = True
+
+    def SwitchRenderer(self, InSelectRaymarchMaterial: ERaymarchMaterial) -> None:
+        self.SelectRaymarchMaterial = InSelectRaymarchMaterial
+
+    def SetRaymarchSteps(self, InRaymarchingSteps: float) -> None:
+        self.RaymarchingSteps = float(InRaymarchingSteps)
+
+    def LoadMHDFileIntoVolumeNormalized(self, FileName: str, loader=None, **kw) -> bool:
+        """CreateVolumeFromFile(FileName, bNormalize = true, bConvertToFloat = false) + SetVolumeAsset (:613-628)."""
+        return self._load_mhd(FileName, True, False, loader, **kw)
+
+    def LoadMHDFileIntoVolumeTransientR32F(self, FileName: str, loader=None, **kw) -> bool:
+        """CreateVolumeFromFile(FileName, false, true) + SetVolumeAsset (:596-611)."""
+        return self._load_mhd(FileName, False, True, loader, **kw)
+
+    def _load_mhd(self, FileName, normalize, to_float, loader, **kw) -> bool:
+        if loader is None:
+            from .raymarch_utils import UMHDLoader as loader
+        try:
+            res, info = loader.CreateVolumeFromFile(FileName, bNormalize=normalize, bConvertToFloat=to_float, **kw)
+        except Exception:  # the reference returns false when no asset could be created
+            return False
+        old = self.RaymarchResources
+        ok = self.SetVolumeAsset(res, info)
+        if ok and old is not None and old is not res:
+            old.release()
+        return ok
+
     def Render(self, Camera, rows=None):
         """What UE's renderer does with the selected material (RaymarchVolume.cpp:144-152, 789-800): the entry point of M_Raymarch,
         M_Intensity_Raymarch or M_Octree_Raymarch for every covered pixel. Returns (rgba, executed_steps)."""

@@ -182,3 +182,47 @@ def test_set_volume_asset_scales_the_mesh_and_requests_recompute_and_octree_rebu
     ops.calls.clear()
     assert vol.Tick().action == "reset" and ops.calls[0] == ("clear", 0.0)
     res._h = None  # do not let __del__ hand the stand-in to the library
+
+
+def test_setters_request_a_recompute_only_when_something_changed():
+    """RaymarchVolume.cpp:562-577, 746-818: window centre / width / cut-offs and the TF curve invalidate the light volume; unchanged values
+    do nothing; steps and renderer switches do not touch the lights."""
+    class Ops(RecordingMaterialOps):
+        def SetWindowingParameters(self, res, w):
+            self.calls.append(("window", w.Center, w.Width, w.LowCutoff, w.HighCutoff))
+
+        def ColorCurveToTexture(self, res, curve):
+            self.calls.append(("curve_tf",))
+
+        def FlushRenderingCommands(self, res):
+            self.calls.append(("flush",))
+
+    res = FBasicRaymarchRenderingResources()
+    res.bIsInitialized = True
+    ops = Ops()
+    vol = ARaymarchVolume(res, [ARaymarchLight((1.0, 0.0, -0.3), 1.0, "L0")], ops=ops)
+    vol.SetWindowCenter(vol.GetWindowCenter())
+    vol.SetLowCutoff(True)
+    assert ops.calls == [] and not vol.bRequestedRecompute
+    vol.SetWindowCenter(0.4)
+    assert ops.calls == [("window", 0.4, 1.0, True, True)] and vol.bRequestedRecompute
+    assert vol.Tick().action == "reset" and not vol.bRequestedRecompute
+    ops.calls.clear()
+    vol.SetWindowWidth(0.5), vol.SetHighCutoff(False)
+    assert [c[0] for c in ops.calls] == ["window", "window"] and ops.calls[-1] == ("window", 0.4, 0.5, True, False) and vol.bRequestedRecompute
+    vol.Tick()
+    ops.calls.clear()
+    vol.SetTFCurve(None)
+    assert ops.calls == [] and not vol.bRequestedRecompute
+    vol.SetTFCurve(object())
+    assert ops.calls == [("curve_tf",), ("flush",)] and vol.bRequestedRecompute
+    vol.Tick()
+    vol.SetRaymarchSteps(300), vol.SwitchRenderer(ERaymarchMaterial.Intensity)
+    assert vol.RaymarchingSteps == 300.0 and vol.SelectRaymarchMaterial == ERaymarchMaterial.Intensity and not vol.bRequestedRecompute
+
+    class Loader:  # a loader that cannot produce an asset: the reference returns false and keeps the old volume
+        @staticmethod
+        def CreateVolumeFromFile(*a, **k):
+            raise RuntimeError("no such file")
+
+    assert vol.LoadMHDFileIntoVolumeNormalized("missing.mhd", loader=Loader) is False and vol.RaymarchResources is res
