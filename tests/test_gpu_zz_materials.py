@@ -319,3 +319,44 @@ def test_degenerate_and_ragged_sizes_match_oracle(dims, gpu_sync):
             assert np.array_equal(URaymarchUtils.PerformWindowedRaymarchOctree(res, cam, world, 17.0, mip)[0],
                                   oracle.raymarch_octree(vol, cam, world, 17.0, mips, mip)[0])
         res.release()
+
+
+def test_raymarch_volume_actor_from_mhd_file_ticks_and_renders_every_material(tmp_path):
+    """The caller of the boundary end to end: ARaymarchVolume.LoadMHDFileIntoVolumeNormalized -> Tick (full reset; octree rebuild under the
+    octree material) -> Render with each material; the lit frame equals the oracle's for the same normalised voxels and world."""
+    from tbraymarcherplugin_b200 import ARaymarchLight, ARaymarchVolume, ERaymarchMaterial
+    from tbraymarcherplugin_b200.raymarch_utils import FBasicRaymarchRenderingResources
+
+    dims = (32, 32, 16)
+    raw = (synth.perlin_ct_volume(dims).astype(np.int16) * 7 - 500)
+    (tmp_path / "v.raw").write_bytes(raw.tobytes())
+    (tmp_path / "v.mhd").write_text(f"DimSize = {dims[0]} {dims[1]} {dims[2]}\nElementSpacing = 1 1 2\nElementType = MET_SHORT\nElementDataFile = v.raw\n")
+    lights = [ARaymarchLight(tuple(l.LightDirection), l.LightIntensity, f"L{i}") for i, l in enumerate(synth.LIGHTS[:2])]
+    vol = ARaymarchVolume(FBasicRaymarchRenderingResources(), lights)
+    assert vol.Tick().action == "not_initialized"
+    assert vol.LoadMHDFileIntoVolumeNormalized(str(tmp_path / "v.mhd"), bLightVolume32Bit=True)
+    assert vol.ComponentTransform.Scale3D == (3.2, 3.2, 3.2)  # WorldDimensions / 10
+    vol.SetWindowCenter(0.45), vol.SetWindowWidth(0.5), vol.SetHighCutoff(False), vol.SetRaymarchSteps(48)
+    rep = vol.Tick()
+    assert rep.action == "reset" and rep.lights_updated == 2 and not rep.errors
+    cam = synth.benchmark_camera(48, 32)
+    cam.Eye = tuple(3.2 * c for c in cam.Eye)  # the mesh is 3.2 units wide now
+    lit, steps = vol.Render(cam)
+    want, _, _ = oracle.normalize_array(3, raw)
+    ora = oracle.OracleVolume(want, oracle.default_tf(), vol.RaymarchResources.WindowingParameters)
+    for l in lights:
+        ora.add_dir_light(l.GetCurrentParameters(), True, vol.WorldParameters)
+    assert np.array_equal(URaymarchUtils.ReadLightVolume(vol.RaymarchResources), ora.light)
+    ref, ref_steps = ora.raymarch_lit(cam, vol.WorldParameters, 48.0)
+    assert steps == ref_steps and np.array_equal(lit, ref)
+    vol.SwitchRenderer(ERaymarchMaterial.Octree)
+    assert vol.Tick().octree_rebuilt
+    assert np.array_equal(vol.Render(cam)[0], oracle.raymarch_octree(ora, cam, vol.WorldParameters, 48.0, oracle.generate_octree(want), 0)[0])
+    vol.SwitchRenderer(ERaymarchMaterial.Intensity)
+    assert np.array_equal(vol.Render(cam)[0], oracle.raymarch_intensity(ora, cam, vol.WorldParameters, 48.0)[0])
+    lights[0].ForwardVector = tuple(synth.rotate_about_z(synth.LIGHTS[0], 5.0).LightDirection)
+    vol.SwitchRenderer(ERaymarchMaterial.Lit)
+    assert vol.Tick().action == "incremental"
+    ora.change_dir_light(synth.LIGHTS[0], lights[0].GetCurrentParameters(), vol.WorldParameters)
+    assert np.array_equal(URaymarchUtils.ReadLightVolume(vol.RaymarchResources), ora.light)
+    vol.RaymarchResources.release()
