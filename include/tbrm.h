@@ -129,7 +129,8 @@ typedef struct tbrm_sweep_stats {
     int64_t voxels;          /* light-volume voxels x passes */
     int32_t kernel_launches; /* CUDA kernels launched by this op */
     int32_t faces[4];        /* FCubeFace of each pass (0:+X 1:-X 2:+Y 3:-Y 4:+Z 5:-Z), -1 if unused */
-    int32_t impl[4];         /* kernel family of each pass: 1 per-slice launches, 2 fused (generic), 3 fused (TMA-staged) */
+    int32_t impl[4];         /* kernel family of each pass: 1 per-slice launches, 2 fused (generic), 3 fused (TMA-staged),
+                                4 joined per-slice launches (tbrm_add_dir_lights_joined) */
 } tbrm_sweep_stats;
 
 /* One GPU's share of a volume that is sharded over the GPUs of a box as Z-slabs. */
@@ -193,6 +194,16 @@ tbrm_status tbrm_add_dir_light_stats(tbrm_resources* res, const tbrm_dir_light* 
 tbrm_status tbrm_change_dir_light_stats(tbrm_resources* res, const tbrm_dir_light* old_light,
                                         const tbrm_dir_light* new_light, const tbrm_world* world, int* light_added,
                                         int gpu_sync, tbrm_sweep_stats* stats);
+
+/* Same-axis light joining (the reference's Readme.md:165-166, 186-187 names it as the optimisation of the paper it
+ * does not implement): AddDirLight for n_lights lights at once, the passes of all lights that propagate from the same cube face joined into
+ * ONE sweep of the reference's per-slice schedule (one launch per slice for the whole group instead of one per light; at most 8 members per
+ * sweep). Per voxel the members are evaluated in light order, each with its own propagation buffers and the arithmetic of
+ * AddDirLightShader.usf; a single light gives the bits of tbrm_add_dir_light(gpu_sync = 0), several lights differ from consecutive calls
+ * only in the order in which a voxel's contributions are summed (<= a few ulp). *lights_added: lights with a non-zero direction, 0 when a
+ * resource is missing. stats: passes = sweeps run, impl = 4. Not available on a slab-sharded volume (TBRM_ERR_UNSUPPORTED). */
+tbrm_status tbrm_add_dir_lights_joined(tbrm_resources* res, const tbrm_dir_light* lights, int n_lights, int added, const tbrm_world* world,
+                                       int* lights_added, tbrm_sweep_stats* stats);
 
 /* Host parameter math of one light (LightingShaderUtils.cpp:29-265, LightingShaders.cpp:100-130): what the
  * render-thread functions compute on the CPU before dispatching. Pure host function, needs no GPU. */

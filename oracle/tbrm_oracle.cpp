@@ -548,6 +548,69 @@ extern "C" int tbo_add_dir_light(const tbo_volume* vol, const tbrm_dir_light* li
     return passes;
 }
 
+// NOT in the reference (its Readme.md:165-166, 186-187 names it as the missing optimisation of the paper): the passes of several lights
+// that propagate from the SAME cube face joined into one sweep — SURVEY.md §8(f) row 1. The CPU twin of tbrm_add_dir_lights_joined:
+//   * every light is planned like AddDirLight (zero directions skipped, passes with weight 0 dropped);
+//   * passes are grouped by face in order of first appearance (light order, then pass order), at most 8 per group;
+//   * a group is swept once: per slice and voxel the members are evaluated in group order, each with its own propagation buffers and exactly
+//     the arithmetic of AddDirLightShader.usf, and each adds to the light volume in turn (through the volume's pixel format).
+// A group of one is bit-identical to tbo_add_dir_light's pass. With several members the result differs from consecutive AddDirLight calls
+// only in the ORDER in which a voxel's contributions are summed (tests bound it).
+extern "C" int tbo_add_dir_lights_joined(const tbo_volume* vol, const tbrm_dir_light* lights, int n_lights, int added, const tbrm_world* world) {
+    struct Group {
+        int face;
+        std::vector<tbo_pass> members;
+    };
+    std::vector<Group> groups;
+    tbo_light_plan first;
+    bool have_plan = false;
+    for (int i = 0; i < n_lights; ++i) {
+        tbo_light_plan plan;
+        tbo_plan_dir_light(vol->ldims, &vol->win, vol->border_exact, &lights[i], world, &plan);
+        if (plan.zero_direction) continue;
+        if (!have_plan) first = plan, have_plan = true;
+        for (int p = 0; p < plan.add_passes; ++p) {
+            size_t g = 0;
+            while (g < groups.size() && !(groups[g].face == plan.pass[p].face && groups[g].members.size() < 8)) ++g;
+            if (g == groups.size()) groups.push_back(Group{plan.pass[p].face, {}});
+            groups[g].members.push_back(plan.pass[p]);
+        }
+    }
+    if (!have_plan) return 0;
+    SweepCtx c;
+    make_ctx(vol, first, c);  // clip plane and data border depend on the world and the window only
+    const float sign = added ? 1.0f : -1.0f;
+    for (const Group& G : groups) {
+        const tbo_pass& P0 = G.members[0];
+        const int tx = P0.td[0], ty = P0.td[1], K = (int) G.members.size();
+        std::vector<Buf2D> buf(2 * K);
+        for (int m = 0; m < K; ++m) {
+            buf[2 * m].init(tx, ty, vol->light_fmt, G.members[m].light_alpha);
+            buf[2 * m + 1].init(tx, ty, vol->light_fmt, G.members[m].light_alpha);
+        }
+        for (int j = P0.start; j != P0.stop; j += P0.dirn) {
+            const int par = (j % 2 == 0) ? 0 : 1;
+#pragma omp parallel for schedule(static)
+            for (int py = 0; py < ty; ++py)
+                for (int px = 0; px < tx; ++px) {
+                    int x, y, z;
+                    permute(P0.axis, px, py, j, x, y, z);
+                    for (int m = 0; m < K; ++m) {
+                        const tbo_pass& P = G.members[m];
+                        float u = ((float) px + 0.5f) / (float) tx + P.uv_offset[0];
+                        float v = ((float) py + 0.5f) / (float) ty + P.uv_offset[1];
+                        float prev = buf[2 * m + par].sample_border(u, v, P.border);
+                        float cs = occlusion_sample(c, x, y, z, P.uvw_offset, P.step_size, true);
+                        float cur = prev * (1.0f - cs);
+                        buf[2 * m + (par ^ 1)].store(px, py, cur);
+                        if (fabsf(cur) > 1e-3f) c.light.store(x, y, z, c.light.load(x, y, z) + (cur * sign));
+                    }
+                }
+        }
+    }
+    return (int) groups.size();
+}
+
 // ChangeDirLightInSingleLightVolume_RenderThread — LightingShaders.cpp:168-326, kernel ChangeDirLightShader.usf:75-156
 extern "C" int tbo_change_dir_light(const tbo_volume* vol, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
                                     const tbrm_world* world, uint8_t* near_gate) {

@@ -59,6 +59,8 @@ int tbo_plan_dir_light(const int32_t ldims[3], const tbrm_windowing* win, int bo
                        const tbrm_world* world, tbo_light_plan* out);
 int tbo_clear_light_volume(void* light, const int32_t ldims[3], int light_fmt, float value);
 int tbo_add_dir_light(const tbo_volume* vol, const tbrm_dir_light* light, int added, const tbrm_world* world, uint8_t* near_gate);
+/* the CPU twin of tbrm_add_dir_lights_joined (same-face passes of several lights in one sweep; not in the reference); returns the sweeps run */
+int tbo_add_dir_lights_joined(const tbo_volume* vol, const tbrm_dir_light* lights, int n_lights, int added, const tbrm_world* world);
 int tbo_change_dir_light(const tbo_volume* vol, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
                          const tbrm_world* world, uint8_t* near_gate);
 int tbo_raymarch_cube_setup(const tbrm_camera* cam, const tbrm_world* world, float* out);

@@ -160,6 +160,7 @@ PROTOTYPES = {
         _I,
         [_P, C.POINTER(DirLight), C.POINTER(DirLight), C.POINTER(World), C.POINTER(_I), _I, C.POINTER(SweepStats)],
     ),
+    "tbrm_add_dir_lights_joined": (_I, [_P, C.POINTER(DirLight), _I, _I, C.POINTER(World), C.POINTER(_I), C.POINTER(SweepStats)]),
     "tbrm_plan_dir_light": (
         _I,
         [C.POINTER(C.c_int32), C.POINTER(Windowing), C.POINTER(Options), C.POINTER(DirLight), C.POINTER(World), C.POINTER(LightPlan)],

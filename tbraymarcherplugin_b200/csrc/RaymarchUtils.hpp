@@ -9,6 +9,7 @@
 // Scale3D}); UObject texture pointers become the opaque tbrm_resources handle that owns the device memory.
 #pragma once
 #include <array>
+#include <vector>
 #include <cstdint>
 
 #include "../../include/tbrm.h"
@@ -106,6 +107,18 @@ public:
         int added = 0;
         tbrm_change_dir_light(Resources.Handle, &o, &n, &w, &added, bGPUSync ? 1 : 0);
         LightAdded = added != 0;
+    }
+
+    /** Not in the reference (its Readme.md:165-166, 186-187 names it as the missing optimisation): adds all lights at once, the passes that
+        propagate from the same cube face joined into one per-slice sweep. */
+    static void AddDirLightsToSingleVolumeJoined(const FBasicRaymarchRenderingResources& Resources, const std::vector<FDirLightParameters>& Lights,
+                                                 const bool Added, const FRaymarchWorldParameters WorldParameters, bool& LightAdded) {
+        std::vector<tbrm_dir_light> l;
+        for (const FDirLightParameters& L : Lights) l.push_back(ToC(L));
+        const tbrm_world w = ToC(WorldParameters);
+        int added = 0;
+        const tbrm_status s = tbrm_add_dir_lights_joined(Resources.Handle, l.data(), (int) l.size(), Added ? 1 : 0, &w, &added, nullptr);
+        LightAdded = s == TBRM_OK;
     }
 
     /** Clears a light volume in provided raymarch resources. (RaymarchUtils.h:47-49) */

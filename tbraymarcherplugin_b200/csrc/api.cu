@@ -246,6 +246,7 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     if (r->data_yzx) cudaFree(r->data_yzx);
     if (r->tables) cudaFree(r->tables);
     if (r->bricks) cudaFree(r->bricks);
+    if (r->joined_buf) cudaFree(r->joined_buf);
     for (int m = 0; m < 4; ++m)
         if (r->octree[m]) cudaFree(r->octree[m]);
 
@@ -491,6 +492,54 @@ static tbrm_status add_dir_light_impl(tbrm_resources& r, const tbrm_dir_light& l
     return TBRM_OK;
 }
 
+// Same-face passes of several lights in one sweep (not in the reference — Readme.md:165-166, 186-187). Lights are
+// planned like AddDirLight; passes are grouped by cube face in order of first appearance (at most kMaxJoined per group).
+static tbrm_status add_dir_lights_joined_impl(tbrm_resources& r, const tbrm_dir_light* lights, int n_lights, bool added, const tbrm_world& world,
+                                              int* lights_added, tbrm_sweep_stats* stats) {
+    struct Group {
+        SweepUniforms u;
+        int face;
+        std::vector<LightPass> members;
+    };
+    std::vector<Group> groups;
+    int n_added = 0;
+    for (int i = 0; i < n_lights; ++i) {
+        tbrm_light_plan plan;
+        host::plan_dir_light(r.ldims, r.windowing, r.options.border_exact != 0, lights[i], world, plan);
+        if (plan.zero_direction) continue;  // LightingShaders.cpp:41-46
+        ++n_added;
+        for (int p = 0; p < plan.add_passes; ++p) {
+            size_t g = 0;
+            while (g < groups.size() && !(groups[g].face == plan.pass[p].face && (int) groups[g].members.size() < kMaxJoined)) ++g;
+            if (g == groups.size()) {
+                Group G;
+                fill_uniforms(r, plan, p, G.u);
+                G.u.sign = added ? 1.0f : -1.0f;
+                G.face = plan.pass[p].face;
+                groups.push_back(G);
+            }
+            LightPass lp;
+            fill_pass(lp, plan.pass[p]);
+            groups[g].members.push_back(lp);
+        }
+    }
+    if (lights_added) *lights_added = n_added;
+    for (Group& G : groups) {
+        int launches = 0;
+        TBRM_CUDA(sweep_pass_joined(r, G.u, G.members.data(), (int) G.members.size(), &launches));
+        if (stats) {
+            if (stats->passes < 4) {
+                stats->faces[stats->passes] = G.face;
+                stats->impl[stats->passes] = 4;
+            }
+            stats->passes += 1;
+            stats->voxels += (int64_t) G.u.td[0] * G.u.td[1] * G.u.td[2] * (int64_t) G.members.size();
+            stats->kernel_launches += launches;
+        }
+    }
+    return TBRM_OK;
+}
+
 static void reset_stats(tbrm_sweep_stats* s) {
     if (!s) return;
     memset(s, 0, sizeof(*s));
@@ -516,6 +565,20 @@ tbrm_status tbrm_add_dir_light(tbrm_resources* r, const tbrm_dir_light* light, i
 }
 
 // ChangeDirLightInSingleLightVolume_RenderThread — LightingShaders.cpp:168-326
+tbrm_status tbrm_add_dir_lights_joined(tbrm_resources* r, const tbrm_dir_light* lights, int n_lights, int added, const tbrm_world* world,
+                                       int* lights_added, tbrm_sweep_stats* stats) {
+    reset_stats(stats);
+    if (lights_added) *lights_added = 0;
+    if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
+    TBRM_REQUIRE((lights || n_lights == 0) && n_lights >= 0 && world, "tbrm_add_dir_lights_joined: null argument");
+    if (r->slab.nranks > 1) {
+        set_last_error("tbrm_add_dir_lights_joined: joined sweeps run the per-slice schedule, which does not exchange light between slabs");
+        return TBRM_ERR_UNSUPPORTED;
+    }
+    TBRM_CUDA(cudaSetDevice(r->device));
+    return add_dir_lights_joined_impl(*r, lights, n_lights, added != 0, *world, lights_added, stats);
+}
+
 tbrm_status tbrm_change_dir_light_stats(tbrm_resources* r, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
                                         const tbrm_world* world, int* light_added, int gpu_sync, tbrm_sweep_stats* stats) {
     reset_stats(stats);

@@ -54,6 +54,50 @@ __global__ void __launch_bounds__(256) sweep_slice_kernel(const SweepUniforms U,
     }
 }
 
+// ---- same-face passes of several lights joined into one sweep ------------------------------------------------
+// The reference's Readme (:165-166, 186-187) names this as the optimisation of the paper it does not implement. In the per-slice
+// schedule — one launch per slice, launch-latency bound — a group of K lights that propagate from the same cube face costs the launches
+// of one: every thread evaluates the K members in turn (own propagation buffers, the arithmetic of AddDirLightShader.usf unchanged) and
+// adds each to the light volume through the volume's pixel format, exactly as K consecutive dispatches would at that voxel. A group of
+// one is bit-identical to sweep_slice_kernel; several members differ from consecutive AddDirLight calls only in summation order.
+struct JoinedPasses {
+    int n;
+    LightPass p[kMaxJoined];
+};
+__device__ __forceinline__ float light_roundtrip(const float*, float v) { return v; }
+__device__ __forceinline__ float light_roundtrip(const uint8_t*, float v) { return (float) quant8(v) / 255.0f; }
+
+template <typename DataT, typename LightT>
+__global__ void __launch_bounds__(256) sweep_slice_joined_kernel(const SweepUniforms U, const JoinedPasses J, const int loop, const int parity,
+                                                                 const DataT* __restrict__ data, const float4* __restrict__ tf,
+                                                                 LightT* __restrict__ light, LightT* __restrict__ bufs, const size_t plane) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int py = blockIdx.y * blockDim.y + threadIdx.y;
+    const int tx = U.td[0], ty = U.td[1];
+    if (px >= tx || py >= ty) return;
+    int x, y, z;
+    permute(U.axis, px, py, loop, x, y, z);
+    const float ub = ((float) px + 0.5f) / (float) tx, vb = ((float) py + 0.5f) / (float) ty;
+    const size_t bi = (size_t) px + (size_t) tx * py;
+    const size_t li = (size_t) x + (size_t) U.ldims[0] * ((size_t) y + (size_t) U.ldims[1] * (size_t) z);
+    float lv = light_load(light, li);
+    bool changed = false;
+    for (int m = 0; m < J.n; ++m) {
+        const LightPass& L = J.p[m];
+        const LightT* rd = bufs + (size_t) (2 * m + parity) * plane;
+        LightT* wr = bufs + (size_t) (2 * m + (parity ^ 1)) * plane;
+        const float prev = sample_buffer_border(rd, tx, ty, ub + L.uv_off[0], vb + L.uv_off[1], L.border);
+        const float cs = occlusion_sample<DataT>(U, L, data, tf, x, y, z);
+        const float cur = prev * (1.0f - cs);
+        light_store(wr, bi, cur);
+        if (fabsf(cur) > 1e-3f) {
+            lv = light_roundtrip(light, lv + (cur * U.sign));
+            changed = true;
+        }
+    }
+    if (changed) light_store(light, li, lv);
+}
+
 template <typename T>
 __global__ void fill_kernel(T* p, size_t n, T v) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,6 +177,50 @@ static cudaError_t per_slice_typed(tbrm_resources& r, const SweepUniforms& u, bo
     count_launch(n);
     *launches += n;
     return cudaGetLastError();
+}
+
+template <typename DataT, typename LightT>
+static cudaError_t joined_typed(tbrm_resources& r, const SweepUniforms& u, const JoinedPasses& J, int* launches) {
+    const int tx = u.td[0], ty = u.td[1], n = u.td[2];
+    const size_t plane = (size_t) tx * ty;
+    const size_t need = 2 * (size_t) kMaxJoined * plane * r.light_elem();
+    cudaError_t e;
+    if (r.joined_bytes < need) {
+        if (r.joined_buf) {
+            cudaStreamSynchronize(r.stream);
+            cudaFree(r.joined_buf);
+            r.joined_buf = nullptr, r.joined_bytes = 0;
+        }
+        if ((e = cudaMalloc(&r.joined_buf, need)) != cudaSuccess) return e;
+        r.joined_bytes = need;
+    }
+    LightT* bufs = (LightT*) r.joined_buf;
+    for (int m = 0; m < J.n; ++m) {  // both buffers of a member start as its LightAlpha (LightingShaders.cpp:74-79)
+        if ((e = sweep_fill_buffer(r, bufs + (size_t) 2 * m * plane, 2 * plane, J.p[m].light_alpha)) != cudaSuccess) return e;
+    }
+    *launches += J.n;
+    const dim3 block(32, 8);
+    const dim3 grid((tx + block.x - 1) / block.x, (ty + block.y - 1) / block.y);
+    for (int k = 0; k < n; ++k) {
+        const int j = u.start + u.dirn * k;
+        sweep_slice_joined_kernel<DataT, LightT><<<grid, block, 0, r.stream>>>(u, J, j, (j % 2 == 0) ? 0 : 1, (const DataT*) r.data, r.tf,
+                                                                                (LightT*) r.light, bufs, plane);
+    }
+    count_launch(n);
+    *launches += n;
+    return cudaGetLastError();
+}
+
+cudaError_t sweep_pass_joined(tbrm_resources& r, const SweepUniforms& u, const LightPass* members, int n_members, int* launches) {
+    JoinedPasses J;
+    J.n = std::min(n_members, kMaxJoined);
+    for (int m = 0; m < J.n; ++m) J.p[m] = members[m];
+    const bool l8 = r.light_fmt == TBRM_FMT_G8;
+    switch (r.data_fmt) {
+        case TBRM_FMT_G8: return l8 ? joined_typed<uint8_t, uint8_t>(r, u, J, launches) : joined_typed<uint8_t, float>(r, u, J, launches);
+        case TBRM_FMT_G16: return l8 ? joined_typed<uint16_t, uint8_t>(r, u, J, launches) : joined_typed<uint16_t, float>(r, u, J, launches);
+        default: return l8 ? joined_typed<float, uint8_t>(r, u, J, launches) : joined_typed<float, float>(r, u, J, launches);
+    }
 }
 
 cudaError_t sweep_pass_per_slice(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches) {

@@ -73,6 +73,9 @@ struct tbrm_resources {
     void* tables = nullptr;
     size_t tables_bytes = 0;
 
+    void* joined_buf = nullptr;  // joined sweeps: 2 propagation buffers per member pass (light pixel format)
+    size_t joined_bytes = 0;
+
     bool light_owned = true;
     void* change_scratch = nullptr;  // TMA sweep: the removed light's propagated light of a ChangeDirLight (R32F, light volume dims)
 
@@ -100,6 +103,8 @@ inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory
 // sweep.cu
 cudaError_t sweep_fill_buffer(tbrm_resources& r, void* buf, size_t count, float value);
 cudaError_t sweep_pass_per_slice(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches);
+constexpr int kMaxJoined = 8;  // member passes of one joined sweep
+cudaError_t sweep_pass_joined(tbrm_resources& r, const SweepUniforms& u, const LightPass* members, int n_members, int* launches);
 cudaError_t sweep_pass_fused(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
 cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
 cudaError_t clear_light(tbrm_resources& r, float value);

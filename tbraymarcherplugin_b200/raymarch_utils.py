@@ -339,6 +339,21 @@ class URaymarchUtils:
         return bool(added.value)
 
     @staticmethod
+    def AddDirLightsToSingleVolumeJoined(Resources: FBasicRaymarchRenderingResources, Lights: Sequence[FDirLightParameters], Added: bool,
+                                         WorldParameters: FRaymarchWorldParameters, stats: Optional[FSweepStats] = None) -> bool:
+        """Same-axis light joining (the optimisation the reference's Readme says it lacks): AddDirLight for all of
+        ``Lights`` with the passes that propagate from the same cube face joined into one per-slice sweep. Returns LightAdded."""
+        arr = (_capi.DirLight * max(len(Lights), 1))(*[l.to_c() for l in Lights])
+        world = WorldParameters.to_c()
+        n, st = C.c_int(0), _capi.SweepStats()
+        status = _capi.load().tbrm_add_dir_lights_joined(Resources.handle, arr, len(Lights), int(Added), C.byref(world), C.byref(n), C.byref(st))
+        if status == _capi.TBRM_ERR_NOT_INITIALIZED:
+            return False
+        check(status)
+        _fill_stats(stats, st)
+        return True
+
+    @staticmethod
     def FlushRenderingCommands(Resources: FBasicRaymarchRenderingResources) -> None:
         check(_capi.load().tbrm_flush(Resources.handle))
 

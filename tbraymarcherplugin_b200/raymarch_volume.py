@@ -94,6 +94,9 @@ class ARaymarchVolume:
         self.ComponentTransform = VolumeTransform or FTransform()
         self.SelectRaymarchMaterial = ERaymarchMaterial.Lit
         self.bFastShader = True  # RaymarchVolume.h:64-65
+        # a full reset adds all lights at once, same-face passes joined into one per-slice sweep (not in the
+        # reference; pays where the sweep is launch-bound, i.e. with bFastShader off and several lights per face)
+        self.bJoinSameAxisLights = False
         self.bVisible = True
         self.bRequestedRecompute = False
         self.bRequestedOctreeRebuild = False  # RaymarchVolume.h:168-169; set by SetVolumeAsset (RaymarchVolume.cpp:553-554)
@@ -169,6 +172,18 @@ class ARaymarchVolume:
             return
         self.ops.ClearResourceLightVolumes(self.RaymarchResources, 0.0)
         rep.action = "reset"
+        if self.bJoinSameAxisLights:
+            lights = [l for l in self.LightsArray if l is not None]
+            if not self.ops.AddDirLightsToSingleVolumeJoined(self.RaymarchResources, [l.GetCurrentParameters() for l in lights], True,
+                                                             self.WorldParameters):
+                rep.errors.append("Error. Could not add/remove lights in volume.")
+                return
+            rep.lights_updated = len(lights)
+            if self.bRefreshLightMapOnReset:
+                for l in lights:
+                    self.LightParametersMap[l] = l.GetCurrentParameters()
+            self.bRequestedRecompute = False
+            return
         for light in self.LightsArray:
             if light is None:
                 continue

@@ -57,9 +57,16 @@ class FakeRaymarchUtils:
 
     @staticmethod
     def AddDirLightToSingleVolume(r, light, added, world, bGPUSync=False, stats=None):
-        r.v().add_dir_light(light, added, world)
+        n = r.v().add_dir_light(light, added, world)
         if stats is not None:
-            stats.impl = (3, 3)
+            stats.impl, stats.passes, stats.kernel_launches = (3, 3), n, 100 * n  # launch counts: only their order matters to the tests
+        return True
+
+    @staticmethod
+    def AddDirLightsToSingleVolumeJoined(r, lights, added, world, stats=None):
+        n = oracle.add_dir_lights_joined(r.v(), list(lights), added, world)
+        if stats is not None:
+            stats.passes, stats.impl, stats.kernel_launches = n, (4,) * min(n, 4), 10 * n
         return True
 
     @staticmethod

@@ -271,3 +271,12 @@ def convert_to_float(fmt: int, arr: np.ndarray) -> np.ndarray:
     f.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
     assert f(fmt, a.ctypes.data, a.size, out.ctypes.data) == 0
     return out
+
+
+def add_dir_lights_joined(vol: OracleVolume, lights, added: bool, world: FRaymarchWorldParameters) -> int:
+    """CPU twin of tbrm_add_dir_lights_joined: same-face passes of several lights in one sweep. Returns the number of sweeps."""
+    arr = (_capi.DirLight * len(lights))(*[l.to_c() for l in lights])
+    v, w = vol.c(), world.to_c()
+    f = lib().tbo_add_dir_lights_joined
+    f.argtypes = [C.POINTER(Volume), C.POINTER(_capi.DirLight), C.c_int, C.c_int, C.POINTER(_capi.World)]
+    return f(C.byref(v), arr, len(lights), int(added), C.byref(w))

@@ -360,3 +360,39 @@ def test_raymarch_volume_actor_from_mhd_file_ticks_and_renders_every_material(tm
     ora.change_dir_light(synth.LIGHTS[0], lights[0].GetCurrentParameters(), vol.WorldParameters)
     assert np.array_equal(URaymarchUtils.ReadLightVolume(vol.RaymarchResources), ora.light)
     vol.RaymarchResources.release()
+
+
+@pytest.mark.parametrize("light32", [True, False])
+@pytest.mark.parametrize("dims", [(40, 32, 24), (64, 64, 64), (33, 17, 9)])
+def test_joined_same_axis_sweeps_match_their_cpu_twin(dims, light32):
+    """tbrm_add_dir_lights_joined against the oracle's twin (bit-exact), against consecutive AddDirLight calls (equal up
+    to summation order), and the launch count it saves in the per-slice schedule."""
+    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats
+
+    data = synth.perlin_ct_volume(dims)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    lights = synth.LIGHTS + [synth.rotate_about_z(synth.LIGHTS[0], 7.0), synth.rotate_about_z(synth.LIGHTS[2], -9.0), FDirLightParameters((0, 0, 0), 1.0)]
+    for world in (synth.identity_world(), synth.clipped_world()):
+        Z, Y, X = data.shape
+        res = URaymarchUtils.InitializeRaymarchResources((X, Y, Z), FMT_G8, bLightVolume32Bit=light32)
+        URaymarchUtils.SetDataVolume(res, data)
+        URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
+        URaymarchUtils.SetWindowingParameters(res, win)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        st = FSweepStats()
+        assert URaymarchUtils.AddDirLightsToSingleVolumeJoined(res, lights, True, world, stats=st)
+        twin = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win, light32=light32)
+        n_twin = oracle.add_dir_lights_joined(twin, lights, True, world)
+        assert st.passes == n_twin and np.array_equal(URaymarchUtils.ReadLightVolume(res), twin.light)
+        # consecutive per-light adds (the reference's schedule): same volume up to summation order, more launches
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        launches = 0
+        for l in lights:
+            s1 = FSweepStats()
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=False, stats=s1)
+            launches += s1.kernel_launches
+        seq = URaymarchUtils.ReadLightVolume(res)
+        d = np.abs(seq.astype(np.float64) - twin.light.astype(np.float64))
+        assert d.max() <= (4e-6 if light32 else 1.0)
+        assert st.kernel_launches < launches
+        res.release()

@@ -249,3 +249,15 @@ def test_small_helpers_of_the_function_library():
     # consistent with the library's InverseTransformPosition (the WorldToLocal the kernels use): world -> local -> world
     lp = np.linalg.inv(m)
     assert np.allclose((np.array([5.0, 8.0, 7.0, 1.0]) @ lp)[:3], (1.0, 0.0, 0.0))
+
+
+def test_joined_lights_entry_point_validates_like_add_dir_light():
+    lib = _capi.load()
+    n = C.c_int(7)
+    st = _capi.SweepStats()
+    w = synth.identity_world().to_c()
+    arr = (_capi.DirLight * 2)(synth.LIGHTS[0].to_c(), synth.LIGHTS[1].to_c())
+    # a missing resource set: status NOT_INITIALIZED and *lights_added = 0 (the reference's `LightAdded = false`, RaymarchUtils.cpp:39-49)
+    assert lib.tbrm_add_dir_lights_joined(None, arr, 2, 1, C.byref(w), C.byref(n), C.byref(st)) == _capi.TBRM_ERR_NOT_INITIALIZED
+    assert n.value == 0 and st.passes == 0
+    assert URaymarchUtils.AddDirLightsToSingleVolumeJoined(FBasicRaymarchRenderingResources(), synth.LIGHTS, True, synth.identity_world()) is False

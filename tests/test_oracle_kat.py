@@ -262,3 +262,34 @@ def test_mandelbulb_power8_twin_stays_close_to_the_reference_formulation():
     assert (n0[..., 3] != n1[..., 3]).mean() < 0.005
     assert (np.abs(s0 - s1) > 1e-4).mean() < 0.01
     assert np.array_equal(other, other0)  # any other power takes the reference's formulation in both variants
+
+
+def test_joined_same_axis_sweeps_equal_consecutive_adds_up_to_summation_order():
+    """SURVEY.md §8(f) row 1 (not in the reference): tbo_add_dir_lights_joined sweeps the passes of all lights that propagate from the same
+    cube face once. One light: bit-identical to AddDirLight. Several: fewer sweeps, and a light volume that differs from consecutive
+    AddDirLight calls only by the order in which a voxel's contributions are added."""
+    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters
+
+    data = synth.perlin_ct_volume((40, 32, 24))
+    tf = oracle.prepare_tf(synth.soft_ct_curve())
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    lights = synth.LIGHTS + [synth.rotate_about_z(synth.LIGHTS[0], 7.0), synth.rotate_about_z(synth.LIGHTS[2], -9.0), FDirLightParameters((0, 0, 0), 1.0)]
+    for world in (synth.identity_world(), synth.clipped_world()):
+        for light32 in (True, False):
+            seq = oracle.OracleVolume(data, tf, win, light32=light32)
+            joined = oracle.OracleVolume(data, tf, win, light32=light32)
+            n_seq = sum(seq.add_dir_light(l, True, world) for l in lights)
+            n_joined = oracle.add_dir_lights_joined(joined, lights, True, world)
+            assert n_seq == 11 and n_joined < n_seq  # a zero direction adds nothing; same-face passes share a sweep
+            d = np.abs(seq.light.astype(np.float64) - joined.light.astype(np.float64))
+            assert d.max() <= (4e-6 if light32 else 1.0) and seq.light.max() > (3.0 if light32 else 200)
+            one_a, one_b = oracle.OracleVolume(data, tf, win, light32=light32), oracle.OracleVolume(data, tf, win, light32=light32)
+            one_a.add_dir_light(lights[0], True, world)
+            assert oracle.add_dir_lights_joined(one_b, [lights[0]], True, world) == 2 and np.array_equal(one_a.light, one_b.light)
+            # removing what was added restores the volume (the signs mirror AddDirLight's)
+            oracle.add_dir_lights_joined(joined, lights, False, world)
+            assert np.abs(joined.light.astype(np.float64)).max() <= (1e-5 if light32 else 2.0)
+    # more than 8 passes on one face split into two sweeps
+    many = [synth.rotate_about_z(synth.LIGHTS[2], 2.0 * i) for i in range(10)]  # L3 is dominated by +Z: all first passes share a face
+    v = oracle.OracleVolume(data, tf, win)
+    assert oracle.add_dir_lights_joined(v, many, True, synth.identity_world()) >= 3

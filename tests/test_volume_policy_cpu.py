@@ -226,3 +226,23 @@ def test_setters_request_a_recompute_only_when_something_changed():
             raise RuntimeError("no such file")
 
     assert vol.LoadMHDFileIntoVolumeNormalized("missing.mhd", loader=Loader) is False and vol.RaymarchResources is res
+
+
+def test_joined_reset_adds_all_lights_in_one_call():
+    class Ops(RecordingOps):
+        def AddDirLightsToSingleVolumeJoined(self, res, lights, added, world, stats=None):
+            self.calls.append(("joined", len(lights), added))
+            return self.fail_on != "joined"
+
+    res = FBasicRaymarchRenderingResources()
+    res.bIsInitialized = True
+    lights = [ARaymarchLight((1.0, 0.1 * i, -0.3), 1.0, f"L{i}") for i in range(3)] + [None]
+    ops = Ops()
+    vol = ARaymarchVolume(res, lights, ops=ops)
+    vol.bJoinSameAxisLights, vol.bRequestedRecompute = True, True
+    rep = vol.Tick()
+    assert rep.action == "reset" and rep.lights_updated == 3 and ops.calls == [("clear", 0.0), ("joined", 3, True)] and not vol.bRequestedRecompute
+    ops.calls.clear()
+    ops.fail_on, vol.bRequestedRecompute = "joined", True
+    rep = vol.Tick()
+    assert rep.errors and vol.bRequestedRecompute  # retried next tick, like the per-light path
