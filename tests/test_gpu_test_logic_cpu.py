@@ -4,7 +4,8 @@ about the kernels — the same functions run against the CUDA path under `-m gpu
 import pytest
 
 import fake_ops
-import test_gpu_zz_materials as M
+import test_gpu_zz_materials as M0
+import test_gpu_zzz_more as M
 import test_ref_fullsize as F
 from tbraymarcherplugin_b200 import raymarch_utils as RU
 from tbraymarcherplugin_b200 import raymarch_volume as RV
@@ -12,7 +13,7 @@ from tbraymarcherplugin_b200 import raymarch_volume as RV
 
 @pytest.fixture
 def fake_surface(monkeypatch):
-    for mod in (M, F):
+    for mod in (M0, M, F):
         monkeypatch.setattr(mod, "URaymarchUtils", fake_ops.FakeRaymarchUtils)
     monkeypatch.setattr(RU, "UMHDLoader", fake_ops.FakeMHDLoader)
     monkeypatch.setattr(RU, "UVolumeTextureToolkit", fake_ops.FakeVolumeTextureToolkit)
