@@ -164,7 +164,26 @@ def mandelbulb():
     report("mandelbulb_distance_1080p", ms, None, sdf_iterations=int(it.value), Giter_per_s=it.value / min(ms) / 1e6)
 
 
-for s in (octree, marches, ingest, mandelbulb):
+def joined_lights():
+    """Same-face passes of 4 lights joined into one per-slice sweep vs the same lights added one after the other (per-slice and fused)."""
+    from tbraymarcherplugin_b200.raymarch_utils import FSweepStats
+
+    w = synth.identity_world()
+    lights = [synth.rotate_about_z(synth.LIGHTS[0], 3.0 * i) for i in range(4)]  # the same two faces for all four
+    URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    st = FSweepStats()
+    URaymarchUtils.AddDirLightsToSingleVolumeJoined(res, lights, True, w, stats=st)
+    ms = timed_resource(res, lambda: URaymarchUtils.AddDirLightsToSingleVolumeJoined(res, lights, True, w), 3)
+    report("add_4_lights_joined_per_slice", ms, None, sweeps=st.passes, launches=st.kernel_launches)
+    for sync, name in ((False, "per_slice"), (True, "fused")):
+        def seq():
+            for l in lights:
+                URaymarchUtils.AddDirLightToSingleVolume(res, l, True, w, bGPUSync=sync)
+        ms = timed_resource(res, seq, 3)
+        report(f"add_4_lights_one_by_one_{name}", ms, None)
+
+
+for s in (octree, marches, ingest, mandelbulb, joined_lights):
     section(s)
 results["wall_s"] = time.time() - t_start
 out = ROOT / "gpurun_out"
