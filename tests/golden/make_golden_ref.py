@@ -241,8 +241,35 @@ def loaders_case():
 CASES = {"ref_hostmath": hostmath_case, "ref_shaders": shaders_case, "ref_materials": materials_case, "ref_ingest": ingest_case,
          "ref_loaders": loaders_case}
 
+# the reference files the build compiles (oracle/ref.mk), relative to the reference checkout: their digests tie the golden vectors to the sources
+REFERENCE_SOURCES = [
+    "Source/Raymarcher/Private/Rendering/LightingShaderUtils.cpp", "Source/Raymarcher/Public/Rendering/LightingShaderUtils.h",
+    "Source/Raymarcher/Public/Rendering/RaymarchTypes.h",
+    "Source/Raymarcher/Shaders/Private/AddDirLightShader.usf", "Source/Raymarcher/Shaders/Private/ChangeDirLightShader.usf",
+    "Source/Raymarcher/Shaders/Private/RaymarcherCommon.usf", "Source/Raymarcher/Shaders/Private/WindowedSampling.usf",
+    "Source/Raymarcher/Shaders/Private/RaymarchMaterialCommon.usf", "Source/Raymarcher/Shaders/Private/WindowedRaymarchMaterials.usf",
+    "Source/Raymarcher/Shaders/Private/GenerateOctreeShader.usf", "Source/Raymarcher/Shaders/Private/OctreeCommon.usf",
+    "Source/FractalMarcher/Shaders/Private/SDFMarcher.usf", "Source/FractalMarcher/Shaders/Private/CalculateMandelbulbSDF.usf",
+    "Source/VolumeTextureToolkit/Public/TextureUtilities.h", "Source/VolumeTextureToolkit/Public/VolumeAsset/VolumeInfo.h",
+    "Source/VolumeTextureToolkit/Private/VolumeAsset/VolumeInfo.cpp",
+    "Source/VolumeTextureToolkit/Private/VolumeAsset/Loaders/MHDLoader.cpp", "Source/VolumeTextureToolkit/Private/VolumeAsset/Loaders/VolumeLoader.cpp",
+]
+
+
+def reference_source_digests(root="/root/reference") -> dict:
+    import hashlib
+
+    return {rel: hashlib.sha256((Path(root) / rel).read_bytes()).hexdigest() for rel in REFERENCE_SOURCES}
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
+    if not only or "sources" in only:
+        import json
+
+        (HERE / "ref_sources.json").write_text(json.dumps({"reference": "tommybazar/TBRaymarcherPlugin @ e06b824 (SURVEY.md)",
+                                                           "sha256": reference_source_digests()}, indent=1) + "\n")
+        print("ref_sources.json written")
     for name, fn in CASES.items():
         if only and name not in only:
             continue

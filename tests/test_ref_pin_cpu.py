@@ -92,3 +92,13 @@ def test_oracle_equals_live_reference_on_fresh_random_inputs():
         ref = refpin.plan_to_vector(refpin.plan_dir_light(dims, light, world))
         _assert_plan_matches_reference(refpin.plan_to_vector(oracle.plan_dir_light(dims, FWindowingParameters(), light, world)), ref,
                                        f"seed {seed}, case {i}")
+
+
+@pytest.mark.skipif(not refpin.REFERENCE.exists(), reason="/root/reference absent")
+def test_reference_sources_are_the_ones_the_golden_vectors_were_made_from():
+    """tests/golden/ref_sources.json records the SHA-256 of every reference file oracle/ref.mk compiles; the checkout here must still match
+    (otherwise the committed ref_*.npz / ref_fullsize_hashes.json describe another revision and have to be regenerated)."""
+    import json
+
+    want = json.loads((GOLDEN / "ref_sources.json").read_text())["sha256"]
+    assert want == mk.reference_source_digests(), "reference sources changed: re-run tests/golden/make_golden_ref.py and make_golden_ref_fullsize.py"
