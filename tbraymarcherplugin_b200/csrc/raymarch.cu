@@ -401,6 +401,16 @@ __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F
 //     would have returned (0,0,0,0) exactly, so colour, alpha, early-out and the executed-step count are unchanged.
 constexpr int kMaxLeap = 64;
 
+// axis_taps without the clamp that keeps the float -> int conversion defined for wild inputs. CUDA's conversion saturates (NaN -> 0), and a
+// clamp that would have acted (floor outside [-4, N + 4]) leaves the raw index outside [1, N - 2]: raymarch_fast2_kernel then sends the
+// sample to the general sampler, which recomputes its taps WITH the clamp. For interior samples index and weight are the same numbers.
+__device__ __forceinline__ void axis_taps_raw(float u, int N, int& i0, float& f) {
+    const float x = u * (float) N - 0.5f;
+    const float fl = floorf(x);
+    f = x - fl;
+    i0 = (int) fl;
+}
+
 template <bool CLIP>
 __global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
                                                              const float* __restrict__ light, const float4* __restrict__ tf,
@@ -448,9 +458,9 @@ __global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms 
             }
             int i0, j0, k0;
             float fx, fy, fz;
-            axis_taps(cur.x, X, i0, fx);
-            axis_taps(cur.y, Y, j0, fy);
-            axis_taps(cur.z, Z, k0, fz);
+            axis_taps_raw(cur.x, X, i0, fx);
+            axis_taps_raw(cur.y, Y, j0, fy);
+            axis_taps_raw(cur.z, Z, k0, fz);
             const bool interior = (unsigned) (i0 - 1) < (unsigned) (X - 2) && (unsigned) (j0 - 1) < (unsigned) (Y - 2) &&
                                   (unsigned) (k0 - 1) < (unsigned) (Z - 2);
             if (!interior || !F.same_dims) {  // the one-voxel shell, half-resolution light volumes: the general sampler
