@@ -461,8 +461,9 @@ __global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms 
             axis_taps_raw(cur.x, X, i0, fx);
             axis_taps_raw(cur.y, Y, j0, fy);
             axis_taps_raw(cur.z, Z, k0, fz);
-            const bool interior = ((unsigned) i0 - 1u) < (unsigned) (X - 2) && ((unsigned) j0 - 1u) < (unsigned) (Y - 2) &&
-                                  ((unsigned) k0 - 1u) < (unsigned) (Z - 2);  // unsigned arithmetic: a saturated index must not overflow
+            // unsigned arithmetic: a saturated index must not overflow; a side of 1 or 2 voxels has no interior
+            const bool interior = ((unsigned) i0 - 1u) < (unsigned) max(X - 2, 0) && ((unsigned) j0 - 1u) < (unsigned) max(Y - 2, 0) &&
+                                  ((unsigned) k0 - 1u) < (unsigned) max(Z - 2, 0);
             if (!interior || !F.same_dims) {  // the one-voxel shell, half-resolution light volumes: the general sampler
                 fast_sample(F, data, light, s_tf, cur, ssw, acc);
             } else {
