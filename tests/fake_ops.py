@@ -52,6 +52,10 @@ class FakeRaymarchUtils:
         r.win = FWindowingParameters(w.Center, w.Width, w.LowCutoff, w.HighCutoff)
 
     @staticmethod
+    def SetOptions(r, **_):
+        pass
+
+    @staticmethod
     def ClearResourceLightVolumes(r, value):
         r.v().clear(value)
 

@@ -36,6 +36,10 @@ def test_logic_of_the_raw_loader_and_actor_tests(fake_surface, tmp_path):
     M.test_raymarch_volume_actor_from_mhd_file_ticks_and_renders_every_material(tmp_path / "b")
 
 
+def test_logic_of_the_small_volume_raymarch_v2_test(fake_surface):
+    M.test_second_generation_raymarch_on_small_and_degenerate_volumes((1, 7, 1))
+
+
 def test_logic_of_the_joined_lights_test(fake_surface):
     M.test_joined_same_axis_sweeps_match_their_cpu_twin((33, 17, 9), True)
     M.test_joined_same_axis_sweeps_match_their_cpu_twin((33, 17, 9), False)

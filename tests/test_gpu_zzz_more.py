@@ -189,3 +189,25 @@ def test_cpp_example_runs_end_to_end(tmp_path):
     assert "48 x 40 x 32 voxels" in out.stdout and "normalised to G16" in out.stdout
     steps = [int(l.split(":")[1].split()[0]) for l in out.stdout.splitlines() if "march:" in l]
     assert len(steps) == 3 and all(s > 0 for s in steps) and steps[1] < steps[0]  # the intensity march stops at its first sample
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (1, 7, 1), (16, 1, 1), (2, 2, 2), (5, 4, 6), (40, 24, 56)])
+def test_second_generation_raymarch_on_small_and_degenerate_volumes(dims):
+    """raymarch_fast2_kernel (opt-in, reserved[1] = 3) against the oracle on sizes where a side has no interior (1 or 2 voxels) — its interior
+    test once accepted tap index -1 for a one-voxel side — and on an ordinary small volume, with and without a clip plane."""
+    rng = np.random.default_rng(sum(dims))
+    data = rng.integers(0, 256, dims[::-1]).astype(np.uint8)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    for world in (synth.identity_world(), synth.clipped_world(), synth.scaled_rotated_world()):
+        res = make_res(data, win)
+        vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win)
+        for l in synth.LIGHTS[:2]:
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world)
+            vol.add_dir_light(l, True, world)
+        URaymarchUtils.SetOptions(res, debug_flags=(0, 3))
+        for jitter in (False, True):
+            cam = synth.benchmark_camera(40, 24, jitter=jitter, frame=2)
+            rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 33.0)
+            ref, ref_steps = vol.raymarch_lit(cam, world, 33.0)
+            assert steps == ref_steps and np.array_equal(rgba, ref), (dims, jitter)
+        res.release()
