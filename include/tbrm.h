@@ -331,6 +331,10 @@ tbrm_status tbrm_mandelbulb_march_normal(int device, const tbrm_mandelbulb* para
 tbrm_status tbrm_mandelbulb_sdf(int device, const int32_t dims[3], const float center[3], float extent, float power, tbrm_format out_fmt,
                                 void* dst, int dst_is_device, uint64_t* out_iterations);
 
+/* Test hook, host only: the kernels' transcendental-free Power == 8 iteration (csrc/mandelbulb.cu, one __host__ __device__ function) evaluated
+ * on the HOST for one position — the value Mandelbulb_SDF returns (not divided by anything) and the iterations it ran. */
+float tbrm_debug_mandelbulb_sdf_p8(const float position[3], float bailout, int iterations, uint32_t* out_iterations);
+
 /* ---- volume ingest ------------------------------------------------------------------ */
 /* EVolumeVoxelFormat — Source/VolumeTextureToolkit/Public/VolumeAsset/VolumeInfo.h:12-27 */
 typedef enum tbrm_voxel_format {

@@ -1413,6 +1413,14 @@ extern "C" int tbo_synth_volume_u8(int kind, const int32_t dims[3], uint32_t see
 // exported helpers for the known-answer tests
 // ------------------------------------------------------------------------------------------------------------
 extern "C" void tbo_set_mandelbulb_variant(int v) { g_mandelbulb_variant = v; }
+// Mandelbulb_SDF at one position: variant 0 = the reference's formulation, 1 = the power-8 twin (whatever the global switch says)
+extern "C" float tbo_mandelbulb_sdf_at(const float pos[3], float bailout, float power, int iterations, int variant, uint64_t* out_iterations) {
+    uint64_t it = 0;
+    const F3 p = f3(pos[0], pos[1], pos[2]);
+    const float d = (variant == 1 && power == 8.0f) ? mandelbulb_sdf_p8(p, bailout, iterations, it) : mandelbulb_sdf_reference(p, bailout, power, iterations, it);
+    if (out_iterations) *out_iterations = it;
+    return d;
+}
 extern "C" float tbo_det_pow(float x, float y) { return det_pow(x, y); }
 extern "C" float tbo_round_to_half(float x) { return round_to_half(x); }
 extern "C" void tbo_sample_windowed_tf(float value, float step, const float* tf, const tbrm_windowing* w, float out[4]) {

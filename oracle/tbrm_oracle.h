@@ -83,6 +83,7 @@ int tbo_convert_to_float(int fmt, const void* in, uint64_t count, float* out);
 int tbo_synth_volume_u8(int kind, const int32_t dims[3], uint32_t seed, uint8_t* out);
 /* 0 (default): Mandelbulb_SDF as the reference writes it; 1: the CPU twin of the kernels' transcendental-free Power == 8 iteration */
 void tbo_set_mandelbulb_variant(int variant);
+float tbo_mandelbulb_sdf_at(const float pos[3], float bailout, float power, int iterations, int variant, uint64_t* out_iterations);
 float tbo_det_pow(float x, float y);
 float tbo_round_to_half(float x);
 void tbo_sample_windowed_tf(float value, float step, const float* tf, const tbrm_windowing* w, float out[4]);

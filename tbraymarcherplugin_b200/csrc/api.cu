@@ -1017,6 +1017,13 @@ tbrm_status tbrm_mandelbulb_march_normal(int device, const tbrm_mandelbulb* para
     });
 }
 
+float tbrm_debug_mandelbulb_sdf_p8(const float position[3], float bailout, int iterations, uint32_t* out_iterations) {
+    unsigned int it = 0;
+    const float d = position ? mandelbulb_sdf_p8_host(position[0], position[1], position[2], bailout, iterations, &it) : 0.0f;
+    if (out_iterations) *out_iterations = it;
+    return d;
+}
+
 tbrm_status tbrm_mandelbulb_sdf(int device, const int32_t dims[3], const float center[3], float extent, float power, tbrm_format out_fmt,
                                 void* dst, int dst_is_device, uint64_t* out_iterations) {
     TBRM_REQUIRE(dims && center && dst, "tbrm_mandelbulb_sdf: null argument");

@@ -70,7 +70,7 @@ __device__ __forceinline__ float mandelbulb_sdf_trig(float px, float py, float p
 // rounded, --fmad=false) and the final log: the CPU oracle's twin (tbo_set_mandelbulb_variant(1)) produces the same bits up to
 // that log. Against the reference's formulation the two differ by rounding only, which the iteration amplifies next to the surface
 // exactly as libm-vs-CUDA transcendentals do: 0.12 % of the pixels of the 1080p frame differ by more than 1e-4 (measured on the CPU).
-__device__ __forceinline__ float mandelbulb_sdf_p8(float px, float py, float pz, float bailout, int iterations, unsigned int& iters) {
+__host__ __device__ __forceinline__ float mandelbulb_sdf_p8(float px, float py, float pz, float bailout, int iterations, unsigned int& iters) {
     float zx = px, zy = py, zz = pz;
     float dr = 1.0f, r = 0.0f;
     for (int i = 0; i < iterations; i++) {
@@ -97,6 +97,15 @@ __device__ __forceinline__ float mandelbulb_sdf_p8(float px, float py, float pz,
         zz = r8 * ct + pz;
     }
     return 0.5f * logf(r) * r / dr;
+}
+
+// the same source compiled for the host (the function is __host__ __device__; the host side is built with -ffp-contract=off): lets a machine
+// without a GPU check this iteration against the oracle's twin (tbrm_debug_mandelbulb_sdf_p8, tests/test_host_cpu.py)
+float mandelbulb_sdf_p8_host(float px, float py, float pz, float bailout, int iterations, unsigned int* iters) {
+    unsigned int it = 0;
+    const float d = mandelbulb_sdf_p8(px, py, pz, bailout, iterations, it);
+    if (iters) *iters = it;
+    return d;
 }
 
 // p8: Power == 8 and the doubling variant is enabled (uniform over the launch)

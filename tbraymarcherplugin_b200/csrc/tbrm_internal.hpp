@@ -139,6 +139,7 @@ cudaError_t mandelbulb_march(cudaStream_t stream, const tbrm_mandelbulb& mb, con
 
 cudaError_t mandelbulb_march_normal(cudaStream_t stream, const tbrm_mandelbulb& mb, float derivation_distance, const host::CameraUniforms& cam,
                                     int row_begin, int row_end, float* d_out, unsigned long long* d_iters);
+float mandelbulb_sdf_p8_host(float px, float py, float pz, float bailout, int iterations, unsigned int* iters);
 cudaError_t mandelbulb_sdf_bake(cudaStream_t stream, const int32_t dims[3], const float center[3], float extent, float power, int g16, void* d_out,
                                 unsigned long long* d_iters);
 

@@ -261,3 +261,27 @@ def test_joined_lights_entry_point_validates_like_add_dir_light():
     assert lib.tbrm_add_dir_lights_joined(None, arr, 2, 1, C.byref(w), C.byref(n), C.byref(st)) == _capi.TBRM_ERR_NOT_INITIALIZED
     assert n.value == 0 and st.passes == 0
     assert URaymarchUtils.AddDirLightsToSingleVolumeJoined(FBasicRaymarchRenderingResources(), synth.LIGHTS, True, synth.identity_world()) is False
+
+
+def test_kernel_source_of_the_power8_mandelbulb_iteration_equals_the_oracle_twin_on_the_host():
+    """csrc/mandelbulb.cu's mandelbulb_sdf_p8 is one __host__ __device__ function: its HOST compilation (tbrm_debug_mandelbulb_sdf_p8) must give
+    the oracle twin's bits (same +, -, *, /, sqrt, and here even the same libm log) — on a lattice through the bulb, next to its surface,
+    at the origin (NaN either way) and far outside. What runs on the GPU is this source compiled for sm_100a with --fmad=false."""
+    lib, ora = _capi.load(), oracle.lib()
+    ora.tbo_mandelbulb_sdf_at.restype = C.c_float
+    ora.tbo_mandelbulb_sdf_at.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    rng = np.random.default_rng(8)
+    g = np.linspace(-1.3, 1.3, 14, dtype=np.float32)
+    pts = [np.array(p, np.float32) for p in np.stack(np.meshgrid(g, g, g), -1).reshape(-1, 3)]
+    pts += [v / np.linalg.norm(v) * np.float32(r) for v, r in zip(rng.standard_normal((400, 3)).astype(np.float32), rng.uniform(0.7, 1.25, 400))]
+    pts += [np.zeros(3, np.float32), np.array([0, 0, 1.0], np.float32), np.array([5, -7, 3], np.float32), np.array([1e-30, 0, 0], np.float32)]
+    n_inside = 0
+    for iterations, bailout in ((16, 2.4), (50, 2.0)):
+        for p in pts:
+            pos = (C.c_float * 3)(*p)
+            a_it, b_it = C.c_uint32(), C.c_uint64()
+            a = lib.tbrm_debug_mandelbulb_sdf_p8(pos, bailout, iterations, C.byref(a_it))
+            b = ora.tbo_mandelbulb_sdf_at(pos, bailout, 8.0, iterations, 1, C.byref(b_it))
+            assert a_it.value == b_it.value and (np.float32(a).tobytes() == np.float32(b).tobytes() or (np.isnan(a) and np.isnan(b))), (p, a, b)
+            n_inside += a_it.value == iterations
+    assert n_inside > 50  # the lattice does reach the inside of the bulb
