@@ -5,7 +5,7 @@ import pytest
 
 import fake_ops
 import test_gpu_zz_materials as M0
-import test_gpu_zzz_more as M
+import test_zzz_gpu_more as M
 import test_ref_fullsize as F
 from tbraymarcherplugin_b200 import raymarch_utils as RU
 from tbraymarcherplugin_b200 import raymarch_volume as RV

@@ -1,7 +1,7 @@
 """GPU tests written after round 1's GPU budget was spent — they have run against an oracle-backed stand-in only (tests/test_gpu_test_logic_cpu.py)
-and sort after every test that has already passed on a B200: the Power == 8 Mandelbulb fast path against its CPU twin, the C++ example end to
-end, the headerless raw loader, the ARaymarchVolume mirror from an MHD file, degenerate / ragged volume sizes, and same-axis light joining
-(SURVEY.md §8(f) rows 1-4). Same bars as tests/test_gpu_zz_materials.py."""
+and sort after every test that has already passed on a B200 (file name) and, within the file, from the everyday paths to the edge cases: the
+Power == 8 Mandelbulb fast path against its CPU twin, the headerless raw loader, the ARaymarchVolume mirror from an MHD file, same-axis light
+joining, the C++ example end to end, and degenerate / ragged volume sizes. Same bars as tests/test_gpu_zz_materials.py."""
 import zlib
 
 import numpy as np
@@ -13,7 +13,6 @@ from tbraymarcherplugin_b200 import FMT_G8, synth
 from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters, URaymarchUtils
 
 pytestmark = pytest.mark.gpu
-
 
 def test_mandelbulb_power8_kernels_match_their_cpu_twin():
     """Power == 8 runs the transcendental-free iteration (mandelbulb_sdf_p8): only +, -, *, /, sqrt and one log, so the oracle's variant 1
@@ -57,43 +56,6 @@ def test_headerless_raw_file_loads_like_the_mhd_path(tmp_path):
         assert info.Dimensions == dims and (info.MinValue, info.MaxValue) == (lo, hi) and info.bIsNormalized and res.DataFormat == 1
         URaymarchUtils.GenerateOctree(res)  # mip 0 of the octree is the (G16) data volume itself
         assert np.array_equal(URaymarchUtils.ReadOctreeMip(res, 0)[:dims[2], :dims[1], :dims[0]], want)
-        res.release()
-
-
-@pytest.mark.parametrize("gpu_sync", [False, True])
-@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 3), (1, 7, 1), (16, 1, 1), (7, 3, 1), (5, 4, 6)])
-def test_degenerate_and_ragged_sizes_match_oracle(dims, gpu_sync):
-    """Edge cases through the C ABI: one-voxel and one-voxel-thick volumes, odd sizes (the oracle equals the reference's shaders on the same
-    cases, tests/test_ref_shaders_cpu.py): sweep incl. axis-aligned lights and a ChangeDirLight, the three materials, the octree."""
-    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters
-
-    rng = np.random.default_rng(sum(dims))
-    data = rng.integers(0, 256, dims[::-1]).astype(np.uint8)
-    win = FWindowingParameters(0.45, 0.5, True, False)
-    cam = synth.benchmark_camera(24, 16, jitter=True, frame=1)
-    lights = synth.LIGHTS + [FDirLightParameters((1, 0, 0), 0.7), FDirLightParameters((0, 1, 0), 0.3)]
-    for world in (synth.identity_world(), synth.clipped_world()):
-        res = make_res(data, win)
-        vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win)
-        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
-        for l in lights:
-            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=gpu_sync)
-            vol.add_dir_light(l, True, world)
-        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light)
-        n = synth.rotate_about_z(synth.LIGHTS[0], 20.0)
-        assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], n, world, bGPUSync=gpu_sync)
-        vol.change_dir_light(synth.LIGHTS[0], n, world)
-        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light)
-        rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 17.0)
-        ref, ref_steps = vol.raymarch_lit(cam, world, 17.0)
-        assert steps == ref_steps and np.array_equal(rgba, ref)
-        assert np.array_equal(URaymarchUtils.PerformWindowedIntensityRaymarch(res, cam, world, 17.0)[0], oracle.raymarch_intensity(vol, cam, world, 17.0)[0])
-        URaymarchUtils.GenerateOctree(res)
-        mips = oracle.generate_octree(data)
-        for mip in range(4):
-            assert np.array_equal(URaymarchUtils.ReadOctreeMip(res, mip), mips[mip])
-            assert np.array_equal(URaymarchUtils.PerformWindowedRaymarchOctree(res, cam, world, 17.0, mip)[0],
-                                  oracle.raymarch_octree(vol, cam, world, 17.0, mips, mip)[0])
         res.release()
 
 
@@ -210,4 +172,41 @@ def test_second_generation_raymarch_on_small_and_degenerate_volumes(dims):
             rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 33.0)
             ref, ref_steps = vol.raymarch_lit(cam, world, 33.0)
             assert steps == ref_steps and np.array_equal(rgba, ref), (dims, jitter)
+        res.release()
+
+
+@pytest.mark.parametrize("gpu_sync", [False, True])
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 3), (1, 7, 1), (16, 1, 1), (7, 3, 1), (5, 4, 6)])
+def test_degenerate_and_ragged_sizes_match_oracle(dims, gpu_sync):
+    """Edge cases through the C ABI: one-voxel and one-voxel-thick volumes, odd sizes (the oracle equals the reference's shaders on the same
+    cases, tests/test_ref_shaders_cpu.py): sweep incl. axis-aligned lights and a ChangeDirLight, the three materials, the octree."""
+    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters
+
+    rng = np.random.default_rng(sum(dims))
+    data = rng.integers(0, 256, dims[::-1]).astype(np.uint8)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    cam = synth.benchmark_camera(24, 16, jitter=True, frame=1)
+    lights = synth.LIGHTS + [FDirLightParameters((1, 0, 0), 0.7), FDirLightParameters((0, 1, 0), 0.3)]
+    for world in (synth.identity_world(), synth.clipped_world()):
+        res = make_res(data, win)
+        vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        for l in lights:
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=gpu_sync)
+            vol.add_dir_light(l, True, world)
+        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light)
+        n = synth.rotate_about_z(synth.LIGHTS[0], 20.0)
+        assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], n, world, bGPUSync=gpu_sync)
+        vol.change_dir_light(synth.LIGHTS[0], n, world)
+        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light)
+        rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 17.0)
+        ref, ref_steps = vol.raymarch_lit(cam, world, 17.0)
+        assert steps == ref_steps and np.array_equal(rgba, ref)
+        assert np.array_equal(URaymarchUtils.PerformWindowedIntensityRaymarch(res, cam, world, 17.0)[0], oracle.raymarch_intensity(vol, cam, world, 17.0)[0])
+        URaymarchUtils.GenerateOctree(res)
+        mips = oracle.generate_octree(data)
+        for mip in range(4):
+            assert np.array_equal(URaymarchUtils.ReadOctreeMip(res, mip), mips[mip])
+            assert np.array_equal(URaymarchUtils.PerformWindowedRaymarchOctree(res, cam, world, 17.0, mip)[0],
+                                  oracle.raymarch_octree(vol, cam, world, 17.0, mips, mip)[0])
         res.release()
