@@ -10,8 +10,19 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+def pytest_addoption(parser):
+    parser.addoption("--emulate-kernels", action="store_true", default=False,
+                     help="run against tests/emu (the CUDA sources compiled for the CPU, SIMT emulator) instead of libtbrm.so: lets the "
+                          "-m gpu tests of the non-cooperative kernels execute on a machine without a GPU")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if config.getoption("--emulate-kernels"):
+        import emu_lib
+        from tbraymarcherplugin_b200 import _capi
+
+        _capi._lib = emu_lib.load()
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE: builds tests/emu/_build/libtbrm_emu.so — the product's CUDA sources (tbraymarcherplugin_b200/csrc) compiled by g++
+against the SIMT emulator of tests/emu/cuda_on_host.h, so that the kernels' own source runs on a machine without a GPU.
+
+The only edit the sources get is syntactic: `kernel<<<grid, block, smem, stream>>>(args)` becomes
+`tbrm_emu::launch(grid, block, smem, stream, [&] { kernel(args); })`; inline PTX does not exist on the host, so the two headers that consist
+of it (the cooperative fused sweeps: sweep_fused.cuh, sweep_tma.cuh) are replaced by tests/emu/emu_sweep_stubs.h, which reports "not
+handled" exactly like a device without cooperative launch, and the per-slice schedule takes every pass.
+
+    python tests/emu/build_emu.py            (rebuilds only when a source is newer than the library)
+"""
+import re
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+CSRC = ROOT / "tbraymarcherplugin_b200" / "csrc"
+BUILD = HERE / "_build"
+LIB = BUILD / "libtbrm_emu.so"
+UNITS = ["api.cu", "sweep.cu", "raymarch.cu", "mandelbulb.cu", "synth.cu", "ingest.cu"]
+STUBBED = {"sweep_fused.cuh", "sweep_tma.cuh", "sweep_tma_kernel.cuh"}
+CXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mavx2", "-mfma", "-w", "-pthread"]
+
+
+def _match_back(text: str, end: int) -> int:
+    """start of the kernel expression that ends at `end`: identifier (with namespaces) plus an optional template argument list"""
+    i = end
+    while i > 0 and text[i - 1].isspace():
+        i -= 1
+    if text[i - 1] == ">":
+        depth = 0
+        while True:
+            i -= 1
+            if text[i] == ">":
+                depth += 1
+            elif text[i] == "<":
+                depth -= 1
+                if depth == 0:
+                    break
+    while i > 0 and (text[i - 1].isalnum() or text[i - 1] in "_:"):
+        i -= 1
+    return i
+
+
+def rewrite_launches(text: str) -> str:
+    out, pos = [], 0
+    while True:
+        k = text.find("<<<", pos)
+        if k < 0:
+            break
+        start = _match_back(text, k)
+        close = text.index(">>>", k)
+        paren = text.index("(", close)
+        assert text[close + 3:paren].strip() == "", text[k:paren + 1]
+        depth, j = 0, paren
+        while True:
+            if text[j] == "(":
+                depth += 1
+            elif text[j] == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        kernel, cfg, args = text[start:k].strip(), text[k + 3:close], text[paren + 1:j]
+        ncfg = len(re.findall(r",", re.sub(r"\([^()]*\)", "", cfg))) + 1
+        cfg_full = cfg + ", 0" * (4 - ncfg)
+        out.append(text[pos:start])
+        out.append(f"tbrm_emu::launch({cfg_full}, [&] {{ {kernel}({args}); }})")
+        pos = j + 1
+    out.append(text[pos:])
+    return "".join(out)
+
+
+def generate() -> Path:
+    gen = BUILD / "gen" / "pkg" / "csrc"
+    gen.mkdir(parents=True, exist_ok=True)
+    (BUILD / "gen" / "include").mkdir(exist_ok=True)
+    shutil.copy(ROOT / "include" / "tbrm.h", BUILD / "gen" / "include" / "tbrm.h")
+    for src in sorted(CSRC.iterdir()):
+        if src.suffix not in (".cu", ".cuh", ".hpp", ".h") or src.name in STUBBED:
+            continue
+        text = rewrite_launches(src.read_text())
+        if src.name == "sweep.cu":
+            text = text.replace('#include "sweep_fused.cuh"', '#include "emu_sweep_stubs.h"').replace('#include "sweep_tma.cuh"', "")
+        (gen / (src.name + ".cpp" if src.suffix == ".cu" else src.name)).write_text(text)
+    return gen
+
+
+def newest_source() -> float:
+    files = [p for p in CSRC.iterdir()] + [p for p in HERE.iterdir() if p.is_file()] + [ROOT / "include" / "tbrm.h"]
+    return max(p.stat().st_mtime for p in files)
+
+
+def build(force: bool = False) -> Path:
+    if LIB.exists() and not force and LIB.stat().st_mtime > newest_source():
+        return LIB
+    gen = generate()
+    inc = ["-I", str(HERE / "include"), "-I", str(HERE), "-I", str(gen), "-include", str(HERE / "cuda_on_host.h")]
+    objs, procs = [], []
+    for unit in UNITS + ["simt_engine"]:
+        src = HERE / "simt_engine.cpp" if unit == "simt_engine" else gen / (unit + ".cpp")
+        obj = BUILD / (unit + ".o")
+        objs.append(str(obj))
+        procs.append((unit, subprocess.Popen([CXX, *FLAGS, *inc, "-c", str(src), "-o", str(obj)], stderr=subprocess.PIPE, text=True)))
+    failed = False
+    for unit, p in procs:
+        _, err = p.communicate()
+        if p.returncode:
+            failed = True
+            sys.stderr.write(f"---- {unit}\n{err[:6000]}\n")
+    if failed:
+        raise RuntimeError("emulator build failed")
+    subprocess.run([CXX, "-shared", "-pthread", "-o", str(LIB), *objs, "-lz"], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))
