@@ -2,9 +2,10 @@
 against the SIMT emulator of tests/emu/cuda_on_host.h, so that the kernels' own source runs on a machine without a GPU.
 
 The only edit the sources get is syntactic: `kernel<<<grid, block, smem, stream>>>(args)` becomes
-`tbrm_emu::launch(grid, block, smem, stream, [&] { kernel(args); })`; inline PTX does not exist on the host, so the two headers that consist
-of it (the cooperative fused sweeps: sweep_fused.cuh, sweep_tma.cuh) are replaced by tests/emu/emu_sweep_stubs.h, which reports "not
-handled" exactly like a device without cooperative launch, and the per-slice schedule takes every pass.
+`tbrm_emu::launch(grid, block, smem, stream, [&] { kernel(args); })`; the acquire / release / relaxed global accesses written as inline PTX become atomic accesses
+(tbrm_emu::ld_global / st_global), and the cooperative launch of the generic fused sweep becomes tbrm_emu::launch_cooperative (all blocks
+co-resident). The TMA-staged sweep (sweep_tma.cuh: TMA, mbarriers, driver tensor maps) is replaced by tests/emu/emu_sweep_stubs.h, which
+reports "not handled" exactly like a machine whose driver lacks the tensor-map entry point.
 
     python tests/emu/build_emu.py            (rebuilds only when a source is newer than the library)
 """
@@ -20,7 +21,7 @@ CSRC = ROOT / "tbraymarcherplugin_b200" / "csrc"
 BUILD = HERE / "_build"
 LIB = BUILD / "libtbrm_emu.so"
 UNITS = ["api.cu", "sweep.cu", "raymarch.cu", "mandelbulb.cu", "synth.cu", "ingest.cu"]
-STUBBED = {"sweep_fused.cuh", "sweep_tma.cuh", "sweep_tma_kernel.cuh"}
+STUBBED = {"sweep_tma.cuh", "sweep_tma_kernel.cuh"}
 CXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mavx2", "-mfma", "-w", "-pthread"]
 
@@ -74,6 +75,23 @@ def rewrite_launches(text: str) -> str:
     return "".join(out)
 
 
+_PTX = [
+    # relaxed / acquire loads of a flag or ring cell: an atomic load that also lets the other fibers run (every spin loop goes through one)
+    (re.compile(r'asm volatile\("ld\.(?:relaxed|acquire)\.(?:gpu|sys)\.global\.u(?:32|64) %0, \[%1\];"\s*:\s*"=[rl]"\((\w+)\)\s*:\s*"l"\((\w+)\)\s*:\s*"memory"\);'),
+     r'\1 = tbrm_emu::ld_global(\2);'),
+    (re.compile(r'asm volatile\("st\.(?:relaxed|release)\.(?:gpu|sys)\.global\.u(?:32|64) \[%0\], %1;"\s*::\s*"l"\((\w+)\),\s*"[rl]"\((\w+)\)\s*:\s*"memory"\);'),
+     r'tbrm_emu::st_global(\1, \2);'),
+    (re.compile(r'asm volatile\("mov\.u64 %0, %globaltimer;"\s*:\s*"=l"\((\w+)\)\);'), r'\1 = tbrm_emu::globaltimer_ns();'),
+]
+
+
+def rewrite_ptx(text: str) -> str:
+    for rx, repl in _PTX:
+        text = rx.sub(repl, text)
+    # type-erased cooperative launch -> typed (the kernel variable keeps its function-pointer type)
+    return text.replace("cudaLaunchCooperativeKernel((const void*) kernel,", "tbrm_emu::launch_cooperative(kernel,")
+
+
 def generate() -> Path:
     gen = BUILD / "gen" / "pkg" / "csrc"
     gen.mkdir(parents=True, exist_ok=True)
@@ -82,9 +100,9 @@ def generate() -> Path:
     for src in sorted(CSRC.iterdir()):
         if src.suffix not in (".cu", ".cuh", ".hpp", ".h") or src.name in STUBBED:
             continue
-        text = rewrite_launches(src.read_text())
+        text = rewrite_ptx(rewrite_launches(src.read_text()))
         if src.name == "sweep.cu":
-            text = text.replace('#include "sweep_fused.cuh"', '#include "emu_sweep_stubs.h"').replace('#include "sweep_tma.cuh"', "")
+            text = text.replace('#include "sweep_tma.cuh"', '#include "emu_sweep_stubs.h"')
         (gen / (src.name + ".cpp" if src.suffix == ".cu" else src.name)).write_text(text)
     return gen
 

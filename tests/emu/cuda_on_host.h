@@ -192,9 +192,33 @@ void spin_hint();                    // inside a spin loop: let the other fibers
 unsigned char* dynamic_smem();       // the calling block's dynamic shared memory (zero-length launches get a valid pointer too)
 [[noreturn]] void fail(const char* what);
 
+unsigned long long globaltimer_ns();
+
 template <class F>
 inline void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F&& body) {
     run_grid(grid, block, smem, false, std::function<void()>(body));
+}
+// cudaLaunchCooperativeKernel with the kernel's function-pointer type kept: all blocks co-resident
+template <class... A, size_t... I>
+inline void call_with(void (*kernel)(A...), void** args, std::index_sequence<I...>) {
+    kernel(*(typename std::remove_cv<typename std::remove_reference<A>::type>::type*) args[I]...);
+}
+template <class... A>
+inline cudaError_t launch_cooperative(void (*kernel)(A...), dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t) {
+    run_grid(grid, block, smem, true, std::function<void()>([=] { call_with(kernel, args, std::index_sequence_for<A...>()); }));
+    return cudaSuccess;
+}
+// the inline-PTX global accesses of the flag / ring protocols (ld.acquire / ld.relaxed, st.release / st.relaxed at gpu or sys scope):
+// acquire / release atomics; a load also yields, because every spin loop of the sources polls through one
+template <class T>
+inline T ld_global(const T* p) {
+    const T v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+    spin_hint();
+    return v;
+}
+template <class T, class V>
+inline void st_global(T* p, V v) {
+    __atomic_store_n(p, (T) v, __ATOMIC_RELEASE);
 }
 }  // namespace tbrm_emu
 

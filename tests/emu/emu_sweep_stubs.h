@@ -1,15 +1,11 @@
-// emu_sweep_stubs.h — TEST INFRASTRUCTURE (tests/emu): stands in for sweep_fused.cuh / sweep_tma.cuh, whose kernels are inline PTX
-// (relaxed / system-scope accesses, mbarriers, TMA) and cooperative launches, when the product sources are compiled for the CPU. Both
-// fused schedules report "not handled", exactly what they report on a device without cooperative launch, so the per-slice schedule
-// (sweep_slice_kernel, the reference's own schedule) takes every pass; sharding a volume over GPUs is refused.
+// emu_sweep_stubs.h — TEST INFRASTRUCTURE (tests/emu): stands in for sweep_tma.cuh (TMA, mbarriers, tensor maps from the driver) when the
+// product sources are compiled for the CPU. The TMA-staged sweep reports "not handled", exactly what it reports where the driver entry
+// point for tensor maps is missing, so the generic fused sweep (cooperative; emulated) or the per-slice schedule takes every pass;
+// sharding a volume over GPUs is refused.
 #pragma once
 
 namespace tbrm {
 
-cudaError_t sweep_pass_fused(tbrm_resources&, const SweepUniforms&, bool, int*, bool* handled) {
-    *handled = false;
-    return cudaSuccess;
-}
 cudaError_t sweep_pass_tma(tbrm_resources&, const SweepUniforms&, bool, int*, bool* handled) {
     *handled = false;
     return cudaSuccess;

@@ -19,7 +19,7 @@ namespace tbrm_emu {
 }
 
 int cooperative_supported() {
-    const char* e = getenv("TBRM_EMU_COOPERATIVE");
+    const char* e = getenv("TBRM_EMU_COOPERATIVE");  // 0: behave like a device without cooperative launch (per-slice schedule everywhere)
     return (e && e[0] == '0') ? 0 : 1;
 }
 
@@ -191,6 +191,10 @@ void spin_hint() {
     if (!t_block) return;
     std::atomic_thread_fence(std::memory_order_seq_cst);
     yield_to_scheduler();
+}
+
+unsigned long long globaltimer_ns() {
+    return (unsigned long long) std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 void run_grid(dim3 grid, dim3 block, size_t smem_bytes, bool cooperative, const std::function<void()>& thread_body) {
