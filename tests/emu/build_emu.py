@@ -4,8 +4,10 @@ against the SIMT emulator of tests/emu/cuda_on_host.h, so that the kernels' own 
 The only edit the sources get is syntactic: `kernel<<<grid, block, smem, stream>>>(args)` becomes
 `tbrm_emu::launch(grid, block, smem, stream, [&] { kernel(args); })`; the acquire / release / relaxed global accesses written as inline PTX become atomic accesses
 (tbrm_emu::ld_global / st_global), and the cooperative launch of the generic fused sweep becomes tbrm_emu::launch_cooperative (all blocks
-co-resident). The TMA-staged sweep (sweep_tma.cuh: TMA, mbarriers, driver tensor maps) is replaced by tests/emu/emu_sweep_stubs.h, which
-reports "not handled" exactly like a machine whose driver lacks the tensor-map entry point.
+co-resident). The PTX helper block of the TMA-staged sweep (mbarriers, cp.async.bulk.tensor loads / stores, bulk-group waits) is replaced
+by tests/emu/emu_tma_helpers.h — synchronous copies through an emulated tensor map with the device's bounds handling and
+transaction-byte accounting — and its dynamic shared memory comes from the emulator. TBRM_EMU_TMA=0 / TBRM_EMU_COOPERATIVE=0 make the
+emulated machine report no tensor-map driver entry point / no cooperative launch, so the fallbacks of those paths can be exercised too.
 
     python tests/emu/build_emu.py            (rebuilds only when a source is newer than the library)
 """
@@ -21,7 +23,6 @@ CSRC = ROOT / "tbraymarcherplugin_b200" / "csrc"
 BUILD = HERE / "_build"
 LIB = BUILD / "libtbrm_emu.so"
 UNITS = ["api.cu", "sweep.cu", "raymarch.cu", "mandelbulb.cu", "synth.cu", "ingest.cu"]
-STUBBED = {"sweep_tma.cuh", "sweep_tma_kernel.cuh"}
 CXX = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
 FLAGS = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-mavx2", "-mfma", "-w", "-pthread"]
 
@@ -92,17 +93,38 @@ def rewrite_ptx(text: str) -> str:
     return text.replace("cudaLaunchCooperativeKernel((const void*) kernel,", "tbrm_emu::launch_cooperative(kernel,")
 
 
+def must_replace(text: str, old: str, new: str) -> str:
+    assert text.count(old) == 1, f"expected exactly one occurrence of {old!r}"
+    return text.replace(old, new)
+
+
+TMA_KERNEL_TYPE = "void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaParams, const float4*)"
+
+
+def splice_tma_helpers(text: str) -> str:
+    """sweep_tma.cuh: the PTX helper block (mbarrier / TMA / bulk-group waits) -> tests/emu/emu_tma_helpers.h; the type-erased cooperative
+    launch of the sweep_tma_kernel instantiations (one signature) -> typed."""
+    a = text.index("// ---- PTX helpers")
+    b = text.index('}  // namespace tbrm', a)
+    text = text[:a] + '}  // namespace tbrm\n#include "emu_tma_helpers.h"\nnamespace tbrm {\n' + text[b:]
+    return must_replace(text, "return cudaLaunchCooperativeKernel(kern,", f"return tbrm_emu::launch_cooperative(({TMA_KERNEL_TYPE}) kern,")
+
+
 def generate() -> Path:
     gen = BUILD / "gen" / "pkg" / "csrc"
     gen.mkdir(parents=True, exist_ok=True)
     (BUILD / "gen" / "include").mkdir(exist_ok=True)
     shutil.copy(ROOT / "include" / "tbrm.h", BUILD / "gen" / "include" / "tbrm.h")
     for src in sorted(CSRC.iterdir()):
-        if src.suffix not in (".cu", ".cuh", ".hpp", ".h") or src.name in STUBBED:
+        if src.suffix not in (".cu", ".cuh", ".hpp", ".h"):
             continue
         text = rewrite_ptx(rewrite_launches(src.read_text()))
-        if src.name == "sweep.cu":
-            text = text.replace('#include "sweep_tma.cuh"', '#include "emu_sweep_stubs.h"')
+        if src.name == "sweep_tma.cuh":
+            text = splice_tma_helpers(text)
+        if src.name == "sweep_tma_kernel.cuh":
+            text = must_replace(text, "extern __shared__ __align__(128) unsigned char smem[];", "unsigned char* smem = tbrm_emu::dynamic_smem();")
+            text = must_replace(text, 'asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', "")
+        assert "asm volatile" not in text, f"{src.name}: inline PTX the emulator build does not know:\n" + text[text.index("asm volatile"):][:300]
         (gen / (src.name + ".cpp" if src.suffix == ".cu" else src.name)).write_text(text)
     return gen
 

@@ -171,11 +171,36 @@ static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, 
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
 static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q = nullptr) {
-    *fn = nullptr;  // no driver: the TMA-staged sweep reports "not handled"
-    if (q) *q = cudaDriverEntryPointSymbolNotFound;
-    return cudaSuccess;
-}
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long flags, cudaDriverEntryPointQueryResult* q = nullptr);
+
+// ---- driver types of the tensor-map API (cuda.h) -----------------------------------------------------------------------------------------------
+typedef uint32_t cuuint32_t;
+typedef uint64_t cuuint64_t;
+enum CUresult { CUDA_SUCCESS = 0, CUDA_ERROR_INVALID_VALUE = 1 };
+struct alignas(64) CUtensorMap {
+    cuuint64_t opaque[16];
+};
+enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_UINT8 = 0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32 = 7 };
+enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
+enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0 };
+enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_NONE = 0, CU_TENSOR_MAP_L2_PROMOTION_L2_128B = 2 };
+enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
+namespace tbrm_emu {
+constexpr uint64_t kTensorMapMagic = 0x74626d7470616d31ull;
+struct TensorMap {  // what the emulated cuTensorMapEncodeTiled keeps in the 128 opaque bytes (rank 3, tiled, no interleave / swizzle)
+    uint64_t magic;
+    void* base;
+    uint64_t dims[3];
+    uint64_t strides[2];  // bytes, of dimensions 1 and 2
+    uint32_t box[3];
+    uint32_t elem;
+};
+static_assert(sizeof(TensorMap) <= sizeof(CUtensorMap), "the emulated tensor map must fit the opaque one");
+// the driver's argument checks that matter to the sources: 16-byte aligned base and strides, box sides 1..256, inner box extent a multiple of 16 bytes
+CUresult encode_tiled(CUtensorMap* out, CUtensorMapDataType type, cuuint32_t rank, void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, const cuuint32_t* elem_strides, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                      CUtensorMapFloatOOBfill);
+}  // namespace tbrm_emu
 
 // ---- SIMT engine -------------------------------------------------------------------------------------------------------------------------
 extern thread_local uint3 threadIdx, blockIdx;

@@ -54,6 +54,27 @@ void device_free(void* p) {
     g_heap.erase(it);
 }
 
+// ---- tensor maps ---------------------------------------------------------------------------------------------------------------------------
+CUresult encode_tiled(CUtensorMap* out, CUtensorMapDataType type, cuuint32_t rank, void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                      const cuuint32_t* box, const cuuint32_t* elem_strides, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                      CUtensorMapFloatOOBfill) {
+    const uint32_t elem = type == CU_TENSOR_MAP_DATA_TYPE_UINT8 ? 1u : 4u;
+    if (!out || rank != 3 || ((uintptr_t) base & 15u)) return CUDA_ERROR_INVALID_VALUE;
+    for (int d = 0; d < 3; ++d)
+        if (dims[d] == 0 || dims[d] > (1ull << 32) || box[d] == 0 || box[d] > 256 || elem_strides[d] != 1) return CUDA_ERROR_INVALID_VALUE;
+    for (int d = 0; d < 2; ++d)
+        if ((strides[d] & 15u) || strides[d] >= (1ull << 40)) return CUDA_ERROR_INVALID_VALUE;
+    if ((box[0] * elem) & 15u) return CUDA_ERROR_INVALID_VALUE;
+    TensorMap m;
+    memset(&m, 0, sizeof(m));
+    m.magic = kTensorMapMagic, m.base = base, m.elem = elem;
+    for (int d = 0; d < 3; ++d) m.dims[d] = dims[d], m.box[d] = box[d];
+    m.strides[0] = strides[0], m.strides[1] = strides[1];
+    memset(out, 0, sizeof(*out));
+    memcpy(out, &m, sizeof(m));
+    return CUDA_SUCCESS;
+}
+
 // ---- fibers ----------------------------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr size_t kStackBytes = 256 << 10;
@@ -185,7 +206,7 @@ void sync_warp() {
 unsigned long long* warp_slot(int lane) { return &t_block->warps[t_block->cur->linear / 32].slots[lane]; }
 int lane_id() { return t_block->cur->linear % 32; }
 bool lane_alive(int lane) { return t_block->warps[t_block->cur->linear / 32].lane_alive[lane]; }
-unsigned char* dynamic_smem() { return t_block->smem.data(); }
+unsigned char* dynamic_smem() { return (unsigned char*) (((uintptr_t) t_block->smem.data() + 127u) & ~(uintptr_t) 127u); }
 
 void spin_hint() {
     if (!t_block) return;
@@ -230,3 +251,11 @@ void run_grid(dim3 grid, dim3 block, size_t smem_bytes, bool cooperative, const 
 }
 
 }  // namespace tbrm_emu
+
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, cudaDriverEntryPointQueryResult* q) {
+    const char* e = getenv("TBRM_EMU_TMA");  // 0: behave like a driver without tensor maps (the TMA-staged sweep reports "not handled")
+    const bool have = !strcmp(symbol, "cuTensorMapEncodeTiled") && !(e && e[0] == '0');
+    *fn = have ? (void*) &tbrm_emu::encode_tiled : nullptr;
+    if (q) *q = have ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+    return cudaSuccess;
+}
