@@ -77,3 +77,65 @@ def test_emulated_second_generation_raymarch(emulated):
 
 def test_emulated_loader_and_ingest_kernels(emulated, tmp_path):
     M.test_headerless_raw_file_loads_like_the_mhd_path(tmp_path)
+
+
+@pytest.mark.parametrize("dims,nranks", [((64, 48, 64), 4), ((64, 64, 96), 3), ((64, 64, 64), 8)])
+def test_emulated_concurrent_slabs_equal_the_unsharded_sweep(emulated, dims, nranks):
+    """Z-slab sharding with the ranks running CONCURRENTLY, one thread per virtual rank — what N GPUs do, and what one GPU
+    cannot (co-resident cooperative kernels of several ranks would starve each other): every rank issues its passes on its own and waits for its neighbours in the kernels, middle ranks have two neighbours, a
+    rank may run a pass ahead of its neighbour (the ack protocol keeps it from overwriting exchange cells), slabs are swept in both orders;
+    AddDirLight and its removal."""
+    import ctypes as C
+    import threading
+
+    import test_gpu_slab as S
+    from tbraymarcherplugin_b200 import _capi
+
+    data = synth.perlin_ct_volume(dims)
+    world = synth.identity_world()
+    # both sweep orders over the slabs (higher first for -z lights, lower first for +z) and a light in the slab plane
+    lights = synth.LIGHTS[:2] + [FDirLightParameters((0.3, -0.2, 0.93), 0.6), FDirLightParameters((0.9, 0.35, 0.0), 0.8)]
+    ref_res = S.make_res(data)
+    URaymarchUtils.ClearResourceLightVolumes(ref_res, 0.0)
+    for l in lights:
+        st = FSweepStats()
+        assert URaymarchUtils.AddDirLightToSingleVolume(ref_res, l, True, world, bGPUSync=True, stats=st)
+        assert set(st.impl) == {3}
+    ref = URaymarchUtils.ReadLightVolume(ref_res)
+    ranks = S.virtual_ranks(data, nranks)
+    orders = set()
+    for l in lights:
+        for p in (0, 1):
+            o = C.c_int(0)
+            _capi.check(emulated.tbrm_slab_pass_order(ranks[0][0].handle, C.byref(l.to_c()), C.byref(world.to_c()), p, C.byref(o)))
+            orders.add(o.value)
+    assert {-1, 1} <= orders, orders
+    errors = []
+
+    def run(rank, added, which):
+        try:
+            res = ranks[rank][0]
+            _capi.check(emulated.tbrm_slab_set_timeout_ms(res.handle, 120000))
+            for l in which:
+                st = FSweepStats()
+                assert URaymarchUtils.AddDirLightToSingleVolume(res, l, added, world, bGPUSync=True, stats=st)
+                assert set(st.impl) == {3}
+            _capi.check(emulated.tbrm_slab_check(res.handle))
+        except BaseException as e:  # noqa: BLE001 - reported by the main thread
+            errors.append((rank, repr(e)))
+
+    def all_ranks(added, which):
+        threads = [threading.Thread(target=run, args=(r, added, which)) for r in range(nranks)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+
+    for res, _, _ in ranks:
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    all_ranks(True, lights)
+    assert ref.max() > 1.0 and np.array_equal(S.merged(ranks), ref)
+    all_ranks(False, lights[:1])
+    URaymarchUtils.AddDirLightToSingleVolume(ref_res, lights[0], False, world, bGPUSync=True)
+    assert np.array_equal(S.merged(ranks), URaymarchUtils.ReadLightVolume(ref_res))
