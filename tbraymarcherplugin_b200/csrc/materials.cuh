@@ -27,51 +27,10 @@ struct alignas(sizeof(T) * N) OctPack {
     T v[N];
 };
 
-// VEC4: the data rows can be read 4 voxels at a time (X % 4 == 0 and an aligned base pointer)
-template <typename DataT, bool VEC4>
-__global__ void __launch_bounds__(256) octree_build_kernel(const OctreeUniforms U, const DataT* __restrict__ data, uint16_t* __restrict__ mip0,
-                                                           uint16_t* __restrict__ mip1, uint16_t* __restrict__ mip2, uint16_t* __restrict__ mip3) {
-    __shared__ __align__(8) uint16_t s0[8][8][128];
-    __shared__ uint16_t s1[4][4][64];
-    __shared__ uint16_t s2[2][2][32];
-    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8, z0 = blockIdx.z * 8;
-    const int t = threadIdx.x, tx = t & 31, ly = t >> 5;
-    const int X = U.ddims[0], Y = U.ddims[1], Z = U.ddims[2];
-    const int OX = U.odims[0][0], OY = U.odims[0][1], OZ = U.odims[0][2];
-    // mip 0: OctreeVolumeMip0[p] = Volume.Load(p).r * MinMaxValues.y (= 1); Load outside the data volume returns 0 (:36-49).
-    // A thread owns 4 voxels along x: a warp reads one 128-voxel row segment and writes 256 bytes of it.
-    const int x = x0 + 4 * tx, y = y0 + ly;
-#pragma unroll
-    for (int lz = 0; lz < 8; ++lz) {
-        const int z = z0 + lz;
-        unsigned int q[4] = {0, 0, 0, 0};
-        if (y < Y && z < Z) {
-            const size_t row = (size_t) X * ((size_t) y + (size_t) Y * z);
-            if (VEC4 && x + 3 < X) {
-                const OctPack<DataT, 4> p = *reinterpret_cast<const OctPack<DataT, 4>*>(data + row + x);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) q[k] = quant16(Texel<DataT>::decode(p.v[k]) * 1.0f);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (x + k < X) q[k] = quant16(Texel<DataT>::decode(__ldg(data + row + x + k)) * 1.0f);
-            }
-        }
-        OctPack<uint16_t, 4> o;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o.v[k] = (uint16_t) q[k];
-        *reinterpret_cast<OctPack<uint16_t, 4>*>(&s0[lz][ly][4 * tx]) = o;
-        if (y < OY && z < OZ) {  // out-of-bounds UAV stores are dropped
-            uint16_t* dst = mip0 + (size_t) x + (size_t) OX * ((size_t) y + (size_t) OY * z);
-            if (x + 3 < OX && (OX & 3) == 0) {
-                *reinterpret_cast<OctPack<uint16_t, 4>*>(dst) = o;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (x + k < OX) dst[k] = o.v[k];
-            }
-        }
-    }
+// mips 1-3 of one 128 x 8 x 8 strip whose mip 0 sits in shared memory (s0); called by all 256 threads of the CTA
+__device__ __forceinline__ void octree_reduce_strip(const OctreeUniforms& U, const uint16_t (*s0)[8][128], uint16_t (*s1)[4][64], uint16_t (*s2)[2][32],
+                                                    uint16_t* __restrict__ mip1, uint16_t* __restrict__ mip2, uint16_t* __restrict__ mip3, int x0,
+                                                    int y0, int z0, int t) {
     __syncthreads();
     // strip texels beyond the octree's bounds hold 0 in shared memory (they lie outside the data volume: octree sides >= data sides),
     // which is what the shader's Load returns for them
@@ -119,6 +78,91 @@ __global__ void __launch_bounds__(256) octree_build_kernel(const OctreeUniforms 
         if (gx < U.odims[3][0] && gy < U.odims[3][1] && gz < U.odims[3][2])
             mip3[(size_t) gx + (size_t) U.odims[3][0] * ((size_t) gy + (size_t) U.odims[3][1] * gz)] = (uint16_t) m;
     }
+}
+
+// R8 data with X % 16 == 0 (and a 16-byte aligned base): a thread owns 16 voxels along x — one 16-byte load, two 16-byte stores of mip 0.
+// UNORM8 -> UNORM16 through the shader's float round trip, floor(saturate(b / 255) * 65535 + .5), equals b * 257 for every byte
+// (tests/test_host_cpu.py checks all 256), i.e. the byte replicated into both halves: one PRMT per two voxels.
+__global__ void __launch_bounds__(256) octree_build_u8x16_kernel(const OctreeUniforms U, const uint8_t* __restrict__ data, uint16_t* __restrict__ mip0,
+                                                                 uint16_t* __restrict__ mip1, uint16_t* __restrict__ mip2, uint16_t* __restrict__ mip3) {
+    __shared__ __align__(16) uint16_t s0[8][8][128];
+    __shared__ uint16_t s1[4][4][64];
+    __shared__ uint16_t s2[2][2][32];
+    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8, z0 = blockIdx.z * 8;
+    const int t = threadIdx.x, seg = t & 7, ly = (t >> 3) & 7, lzq = t >> 6;  // 8 segments x 8 rows x 4 slices per round
+    const int X = U.ddims[0], Y = U.ddims[1], Z = U.ddims[2];
+    const int OX = U.odims[0][0], OY = U.odims[0][1], OZ = U.odims[0][2];
+    const int x = x0 + 16 * seg, y = y0 + ly;
+    uint4 w[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {  // both loads in flight before the first store
+        const int z = z0 + 4 * it + lzq;
+        w[it] = make_uint4(0u, 0u, 0u, 0u);  // Load outside the data volume returns 0 (GenerateOctreeShader.usf:36-49)
+        if (x < X && y < Y && z < Z) w[it] = __ldg(reinterpret_cast<const uint4*>(data + (size_t) x + (size_t) X * ((size_t) y + (size_t) Y * z)));
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int lz = 4 * it + lzq, z = z0 + lz;
+        const unsigned int in[4] = {w[it].x, w[it].y, w[it].z, w[it].w};
+        uint4 o[2];
+        o[0] = make_uint4(__byte_perm(in[0], 0u, 0x1100u), __byte_perm(in[0], 0u, 0x3322u), __byte_perm(in[1], 0u, 0x1100u), __byte_perm(in[1], 0u, 0x3322u));
+        o[1] = make_uint4(__byte_perm(in[2], 0u, 0x1100u), __byte_perm(in[2], 0u, 0x3322u), __byte_perm(in[3], 0u, 0x1100u), __byte_perm(in[3], 0u, 0x3322u));
+        uint4* sdst = reinterpret_cast<uint4*>(&s0[lz][ly][16 * seg]);
+        sdst[0] = o[0], sdst[1] = o[1];
+        if (x < OX && y < OY && z < OZ) {  // OX is a power of two >= X >= 16: whole segments only
+            uint4* dst = reinterpret_cast<uint4*>(mip0 + (size_t) x + (size_t) OX * ((size_t) y + (size_t) OY * z));
+            dst[0] = o[0], dst[1] = o[1];
+        }
+    }
+    octree_reduce_strip(U, s0, s1, s2, mip1, mip2, mip3, x0, y0, z0, t);
+}
+
+// VEC4: the data rows can be read 4 voxels at a time (X % 4 == 0 and an aligned base pointer)
+template <typename DataT, bool VEC4>
+__global__ void __launch_bounds__(256) octree_build_kernel(const OctreeUniforms U, const DataT* __restrict__ data, uint16_t* __restrict__ mip0,
+                                                           uint16_t* __restrict__ mip1, uint16_t* __restrict__ mip2, uint16_t* __restrict__ mip3) {
+    __shared__ __align__(8) uint16_t s0[8][8][128];
+    __shared__ uint16_t s1[4][4][64];
+    __shared__ uint16_t s2[2][2][32];
+    const int x0 = blockIdx.x * 128, y0 = blockIdx.y * 8, z0 = blockIdx.z * 8;
+    const int t = threadIdx.x, tx = t & 31, ly = t >> 5;
+    const int X = U.ddims[0], Y = U.ddims[1], Z = U.ddims[2];
+    const int OX = U.odims[0][0], OY = U.odims[0][1], OZ = U.odims[0][2];
+    // mip 0: OctreeVolumeMip0[p] = Volume.Load(p).r * MinMaxValues.y (= 1); Load outside the data volume returns 0 (:36-49).
+    // A thread owns 4 voxels along x: a warp reads one 128-voxel row segment and writes 256 bytes of it.
+    const int x = x0 + 4 * tx, y = y0 + ly;
+#pragma unroll
+    for (int lz = 0; lz < 8; ++lz) {
+        const int z = z0 + lz;
+        unsigned int q[4] = {0, 0, 0, 0};
+        if (y < Y && z < Z) {
+            const size_t row = (size_t) X * ((size_t) y + (size_t) Y * z);
+            if (VEC4 && x + 3 < X) {
+                const OctPack<DataT, 4> p = *reinterpret_cast<const OctPack<DataT, 4>*>(data + row + x);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) q[k] = quant16(Texel<DataT>::decode(p.v[k]) * 1.0f);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (x + k < X) q[k] = quant16(Texel<DataT>::decode(__ldg(data + row + x + k)) * 1.0f);
+            }
+        }
+        OctPack<uint16_t, 4> o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o.v[k] = (uint16_t) q[k];
+        *reinterpret_cast<OctPack<uint16_t, 4>*>(&s0[lz][ly][4 * tx]) = o;
+        if (y < OY && z < OZ) {  // out-of-bounds UAV stores are dropped
+            uint16_t* dst = mip0 + (size_t) x + (size_t) OX * ((size_t) y + (size_t) OY * z);
+            if (x + 3 < OX && (OX & 3) == 0) {
+                *reinterpret_cast<OctPack<uint16_t, 4>*>(dst) = o;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (x + k < OX) dst[k] = o.v[k];
+            }
+        }
+    }
+    octree_reduce_strip(U, s0, s1, s2, mip1, mip2, mip3, x0, y0, z0, t);
 }
 
 // ---- per-pixel preamble shared by the two marches (WindowedRaymarchMaterials.usf:113-130, 196-208) -------------------------------------
@@ -285,7 +329,10 @@ template <typename DataT>
 static cudaError_t launch_octree(tbrm_resources& r, const OctreeUniforms& U) {
     const dim3 grid((U.odims[0][0] + 127) / 128, (U.odims[0][1] + 7) / 8, (U.odims[0][2] + 7) / 8);
     const bool vec4 = (U.ddims[0] & 3) == 0 && (reinterpret_cast<uintptr_t>(r.data) % (4 * sizeof(DataT))) == 0;
-    if (vec4)
+    if (std::is_same<DataT, uint8_t>::value && (U.ddims[0] & 15) == 0 && (reinterpret_cast<uintptr_t>(r.data) & 15) == 0)
+        octree_build_u8x16_kernel<<<grid, 256, 0, r.stream>>>(U, (const uint8_t*) r.data, (uint16_t*) r.octree[0], (uint16_t*) r.octree[1],
+                                                             (uint16_t*) r.octree[2], (uint16_t*) r.octree[3]);
+    else if (vec4)
         octree_build_kernel<DataT, true><<<grid, 256, 0, r.stream>>>(U, (const DataT*) r.data, (uint16_t*) r.octree[0], (uint16_t*) r.octree[1],
                                                                     (uint16_t*) r.octree[2], (uint16_t*) r.octree[3]);
     else

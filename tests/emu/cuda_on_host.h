@@ -307,6 +307,12 @@ static inline float __uint_as_float(unsigned int i) {
 static inline unsigned int __funnelshift_r(unsigned int lo, unsigned int hi, unsigned int shift) {
     return (unsigned int) ((((unsigned long long) hi << 32) | lo) >> (shift & 31u));
 }
+static inline unsigned int __byte_perm(unsigned int a, unsigned int b, unsigned int sel) {  // PRMT, default mode (no sign replication)
+    const unsigned long long v = ((unsigned long long) b << 32) | a;
+    unsigned int r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned int) ((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffull) << (8 * i);
+    return r;
+}
 // binary16 (round to nearest even), through the compiler's _Float16
 struct __half {
     _Float16 v;

@@ -285,3 +285,11 @@ def test_kernel_source_of_the_power8_mandelbulb_iteration_equals_the_oracle_twin
             assert a_it.value == b_it.value and (np.float32(a).tobytes() == np.float32(b).tobytes() or (np.isnan(a) and np.isnan(b))), (p, a, b)
             n_inside += a_it.value == iterations
     assert n_inside > 50  # the lattice does reach the inside of the bulb
+
+
+def test_unorm8_to_unorm16_through_the_float_round_trip_is_byte_replication():
+    """GenerateOctreeShader.usf:36-49 stores Volume.Load(p).r into a UNORM16 UAV: floor(saturate(b / 255) * 65535 + .5) in fp32. For every byte
+    that is b * 257 — what octree_build_u8x16_kernel computes with one byte permute (csrc/materials.cuh)."""
+    b = np.arange(256, dtype=np.float32)
+    v = np.clip(b / np.float32(255.0), np.float32(0), np.float32(1)) * np.float32(65535.0) + np.float32(0.5)
+    assert v.dtype == np.float32 and np.array_equal(np.floor(v).astype(np.int64), np.arange(256) * 257)

@@ -139,3 +139,15 @@ def test_emulated_concurrent_slabs_equal_the_unsharded_sweep(emulated, dims, nra
     all_ranks(False, lights[:1])
     URaymarchUtils.AddDirLightToSingleVolume(ref_res, lights[0], False, world, bGPUSync=True)
     assert np.array_equal(S.merged(ranks), URaymarchUtils.ReadLightVolume(ref_res))
+
+
+@pytest.mark.parametrize("dims", [(16, 1, 1), (48, 20, 9), (144, 16, 24), (40, 12, 8)])
+def test_emulated_octree_build_kernels(emulated, dims):
+    """octree_build_u8x16_kernel (R8 data, X % 16 == 0: 16-byte loads, byte replication instead of the float round trip) and the generic
+    kernel ((40, 12, 8)) against the oracle, all four mips."""
+    data = np.random.default_rng(sum(dims)).integers(0, 256, dims[::-1]).astype(np.uint8)
+    res = M0.make_res(data, FWindowingParameters(0.45, 0.5, True, False))
+    URaymarchUtils.GenerateOctree(res)
+    for m, want in enumerate(oracle.generate_octree(data)):
+        assert np.array_equal(URaymarchUtils.ReadOctreeMip(res, m), want), m
+    res.release()
