@@ -33,6 +33,23 @@ struct MinMax {
     In mn, mx;
 };
 
+// Grid-stride walk over the 16-byte packs of an array with kInFlight loads of a thread issued before the first is consumed: 8 CTAs x 256
+// threads x 16 bytes per SM keep 4.8 MB in flight with one load per thread — short of what 6.5 TB/s x the HBM latency needs; four do.
+constexpr int kInFlight = 4;
+template <typename In, int VEC, typename F>
+__device__ __forceinline__ void for_each_pack(const In* __restrict__ in, size_t nvec, F&& body) {
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kInFlight - 1) * stride < nvec; i += kInFlight * stride) {
+        Pack<In, VEC> p[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) p[u] = *reinterpret_cast<const Pack<In, VEC>*>(in + (i + u * stride) * VEC);
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) body(i + u * stride, p[u]);
+    }
+    for (; i < nvec; i += stride) body(i, *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC));
+}
+
 // InMin = numeric_limits<InType>::max(), InMax = numeric_limits<InType>::min() (TextureUtilities.h:110-111): for float, min() is the
 // smallest POSITIVE normal — an all-negative float volume reports FLT_MIN as its maximum. Kept: parity with the reference.
 template <typename In>
@@ -80,12 +97,10 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_minmax_kernel(const In*
     __shared__ MinMax<In> s_part[kIngestThreads / 32];
     MinMax<In> m = minmax_init<In>();
     const size_t nvec = n / VEC;
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const Pack<In, VEC> p = *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC);
+    for_each_pack<In, VEC>(in, nvec, [&](size_t, const Pack<In, VEC>& p) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) minmax_add(m, p.v[k]);
-    }
+    });
     if (blockIdx.x == 0)
         for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) minmax_add(m, in[i]);  // tail
     m = minmax_block_reduce(m, s_part);
@@ -118,7 +133,6 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_normalize_kernel(const 
     const float omaxf = (float) std::numeric_limits<Out>::max();
     if (blockIdx.x == 0 && threadIdx.x == 0) out_minmax[0] = fmn, out_minmax[1] = fmx;  // OutOriginalMin / OutOriginalMax
     const size_t nvec = n / VEC;
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
     if constexpr (sizeof(In) == 1) {
         // 1-byte voxels: the map has 256 entries — each thread evaluates the reference's expression for one input value, the voxels
         // then go through the table (same function on the same inputs: identical results, no division per voxel)
@@ -127,23 +141,21 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_normalize_kernel(const 
         constexpr int kLo = (int) std::numeric_limits<In>::min();
         lut[threadIdx.x] = normalize_one<In, Out>((In) ((int) threadIdx.x + kLo), fmn, range, omaxf);
         __syncthreads();
-        for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-            const Pack<In, VEC> p = *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC);
+        for_each_pack<In, VEC>(in, nvec, [&](size_t i, const Pack<In, VEC>& p) {
             Pack<Out, VEC> q;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) q.v[k] = lut[(int) p.v[k] - kLo];
             *reinterpret_cast<Pack<Out, VEC>*>(out + i * VEC) = q;
-        }
+        });
         if (blockIdx.x == 0)
             for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) out[i] = lut[(int) in[i] - kLo];
     } else {
-        for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-            const Pack<In, VEC> p = *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC);
+        for_each_pack<In, VEC>(in, nvec, [&](size_t i, const Pack<In, VEC>& p) {
             Pack<Out, VEC> q;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) q.v[k] = normalize_one<In, Out>(p.v[k], fmn, range, omaxf);
             *reinterpret_cast<Pack<Out, VEC>*>(out + i * VEC) = q;
-        }
+        });
         if (blockIdx.x == 0)
             for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) out[i] = normalize_one<In, Out>(in[i], fmn, range, omaxf);
     }
@@ -153,14 +165,12 @@ __global__ void __launch_bounds__(kIngestThreads) ingest_normalize_kernel(const 
 template <typename In, int VEC>
 __global__ void __launch_bounds__(kIngestThreads) ingest_to_float_kernel(const In* __restrict__ in, size_t n, float* __restrict__ out) {
     const size_t nvec = n / VEC;
-    const size_t stride = (size_t) gridDim.x * blockDim.x;
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const Pack<In, VEC> p = *reinterpret_cast<const Pack<In, VEC>*>(in + i * VEC);
+    for_each_pack<In, VEC>(in, nvec, [&](size_t i, const Pack<In, VEC>& p) {
         Pack<float, VEC> q;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) q.v[k] = static_cast<float>(p.v[k]);
         *reinterpret_cast<Pack<float, VEC>*>(out + i * VEC) = q;
-    }
+    });
     if (blockIdx.x == 0)
         for (size_t i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) out[i] = static_cast<float>(in[i]);
 }
