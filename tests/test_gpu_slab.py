@@ -4,6 +4,7 @@ after the other in dependency order (the exchange cells are full depth, so a fin
 its neighbour needs). The merged slabs must equal the unsharded sweep BIT FOR BIT. Banded passes (a buffer plane split
 into several co-resident waves, what a 1024^2 plane needs on one GPU) are forced on small planes through a test hook."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,7 @@ from tbraymarcherplugin_b200.raymarch_utils import FSweepStats, FWindowingParame
 
 pytestmark = pytest.mark.gpu
 CT_WINDOW = FWindowingParameters(0.45, 0.5, True, False)
+SLAB_TIMEOUT_MS = int(os.environ.get("TBRM_TEST_SLAB_TIMEOUT_MS", "1500"))  # the CPU emulator (--emulate-kernels) needs minutes at 256^3
 WORLDS = {"identity": synth.identity_world, "scaled_rotated": synth.scaled_rotated_world, "clipped": synth.clipped_world}
 
 
@@ -49,7 +51,7 @@ def virtual_ranks(data, nranks, band_rows=0):
         lib.tbrm_slab_partition(Z, nranks, r, C.byref(z0), C.byref(z1))
         slab = _capi.Slab(r, nranks, z0.value, z1.value)
         _capi.check(lib.tbrm_slab_configure(res.handle, C.byref(slab)))
-        _capi.check(lib.tbrm_slab_set_timeout_ms(res.handle, 1500))
+        _capi.check(lib.tbrm_slab_set_timeout_ms(res.handle, SLAB_TIMEOUT_MS))
         ranks.append((res, z0.value, z1.value))
     arenas = []
     for res, _, _ in ranks:
