@@ -453,6 +453,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     for (int d = 0; d < 2; ++d) P.bmin[d] = T.bmin[d], P.bext[d] = (d ? kTH : kTW) + (T.bmax[d] - T.bmin[d]) + 1;
     if (P.bext[0] > kFpW || P.bext[1] > kFpH) return not_handled("P.bext[0] > kFpW || P.bext[1] > kFpH");
     if (u.td[2] >= 65000) return not_handled("u.td[2] >= 65000");  // slice index + 1 must fit the 16-bit tag field
+    if ((long long) tx * ty * kRingDepth >= (1ll << 31)) return not_handled("ring cells do not fit 32-bit indices");
     // dependency lists must fit
     {
         const long long nx = (long long) (P.bext[0] + kTW - 1) / kTW + 1, ny = (long long) (P.bext[1] + kTH - 1) / kTH + 1;

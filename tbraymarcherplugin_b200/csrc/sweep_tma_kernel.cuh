@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const int k_begin = SLAB ? P.S.k_begin : 0, k_end = SLAB ? P.S.k_end : ns;
     const int x0 = tix * kTW, y0 = tiy * kTH;
     const size_t plane = (size_t) tx * ty;
+    const unsigned int plane32 = (unsigned int) (tx * ty);  // ring cells are indexed in 32 bits (the host checks kRingDepth * plane < 2^31)
 
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const bool own_in0 = v0 && px >= fx0 && px < fx0 + FW && py >= fy0 && py < fy0 + FH;
     const bool own_in1 = v1 && px + 1 >= fx0 && px + 1 < fx0 + FW && py >= fy0 && py < fy0 + FH;
     const int own_idx = (py - fy0) * kFpW + (px - fx0);
+    const unsigned int own_cell = (unsigned int) (px + tx * py);  // this thread's first pixel in a ring slice (used where v0 / v1 hold)
     // is a pixel read by another tile? tile (i,j) reads [i*TW + bmin, +FW) x [j*TH + bmin, +FH)
     auto exported = [&](int gx, int gy) {
         const int rx = gx - P.bmin[0], ry = gy - P.bmin[1];  // tile origin i*TW must lie in (rx - FW, rx]
@@ -307,15 +309,16 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             const int loop = s0 + (U.dirn > 0 ? sl : kSB - 1 - sl);
             if (loop >= ns) continue;
             const int k = U.dirn > 0 ? loop : ns - 1 - loop;  // position in sweep order
-            float* fp_cur = s_fp + (k & 1) * (kFpW * kFpH);
-            float* fp_next = s_fp + ((k + 1) & 1) * (kFpW * kFpH);
+            const int fp_par = (k & 1) * (kFpW * kFpH);
+            float* fp_cur = s_fp + fp_par;
+            float* fp_next = s_fp + (kFpW * kFpH - fp_par);
             // ---- (a) issue the halo loads of slice k-1 (and, every 4th slice, the back-pressure probes) ----
             const unsigned int want_tag = tag_base + (unsigned) k;  // slice k-1 carries tag k
-            const unsigned long long* rd = ring + (size_t) ((k + kRingDepth - 1) % kRingDepth) * plane;
+            const unsigned int rd_slot = (((unsigned int) k + kRingDepth - 1u) % kRingDepth) * plane32;  // first cell of slice k-1 in the ring
             const unsigned long long* rdi = SLAB ? P.S.inbox + (size_t) max(k - 1, 0) * inbox_plane : nullptr;  // inbox is full depth
             auto halo_load = [&](int i) {
                 if (SLAB && halo_ring[i] < 0) return ld_relaxed_sys_u64(rdi + (-1 - halo_ring[i]));
-                return ld_relaxed_u64(rd + halo_ring[i]);
+                return ld_relaxed_u64(ring + (rd_slot + (unsigned int) halo_ring[i]));
             };
             unsigned long long hv[kHaloPerThread];
 #pragma unroll
@@ -397,8 +400,10 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                             t[1][jq][js] = decode_u8((w >> 8) & 0xffu);
                             t[2][jq][js] = decode_u8(w >> 16);
                         }
-                    if (!all_in) {
-                        const bool ip[3] = {inP0, inP1, inP2}, iq[2] = {inQ0, inQ1}, is[2] = {inS0, inS1};
+                    if (!all_in) {  // cold (volume faces only): the per-tap bounds are recomputed here rather than kept live through the loop
+                        const bool ip[3] = {(unsigned) mp0.x < (unsigned) dN_p, (unsigned) (mp0.x + 1) < (unsigned) dN_p,
+                                            (unsigned) (mp0.x + 2) < (unsigned) dN_p};
+                        const bool iq[2] = {(unsigned) mq.x < (unsigned) dN_q, (unsigned) (mq.x + 1) < (unsigned) dN_q}, is[2] = {inS0, inS1};
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 for (int i = 0; i < kHaloPerThread; ++i)
                     if (halo_fp[i] >= 0) {
                         if (!SLAB) {
-                            while ((unsigned int) (hv[i] >> 32) != want_tag) hv[i] = ld_relaxed_u64(rd + halo_ring[i]);
+                            while ((unsigned int) (hv[i] >> 32) != want_tag) hv[i] = ld_relaxed_u64(ring + (rd_slot + (unsigned int) halo_ring[i]));
                         } else if ((unsigned int) (hv[i] >> 32) != want_tag) {
                             const unsigned long long t0 = global_timer_ns();
                             unsigned int polls = 0;
@@ -455,7 +460,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 for (int h = tid; h < n_over; h += kTmaThreads) {
                     const int f = s_over_fp[h], g = s_over_ring[h];
                     if (f < 0) continue;
-                    const unsigned long long* cell = (SLAB && g < 0) ? rdi + (-1 - g) : rd + g;
+                    const unsigned long long* cell = (SLAB && g < 0) ? rdi + (-1 - g) : ring + (rd_slot + (unsigned int) g);
                     unsigned long long v = SLAB ? ld_relaxed_sys_u64(cell) : ld_relaxed_u64(cell);
                     const unsigned long long t0 = SLAB ? global_timer_ns() : 0ull;
                     unsigned int polls = 0;
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 const float cur0 = prev0 * (1.0f - cs0), cur1 = prev1 * (1.0f - cs1);
                 if (own_in0) fp_next[own_idx] = cur0;
                 if (own_in1) fp_next[own_idx + 1] = cur1;
-                unsigned long long* wr = ring + (size_t) (k % kRingDepth) * plane + (size_t) px + (size_t) tx * py;
+                unsigned long long* wr = ring + (((unsigned int) k % kRingDepth) * plane32 + own_cell);
                 const unsigned long long tag = (unsigned long long) (tag_base + (unsigned) k + 1u) << 32;
                 if (exp0) st_relaxed_u64(wr, tag | __float_as_uint(cur0));
                 if (exp1) st_relaxed_u64(wr + 1, tag | __float_as_uint(cur1));
