@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             const int2 ms = __ldg(&P.A.ax[SA].meta[loop]);
             const float fs = __ldg(&P.A.ax[SA].f[loop]);
             const int rows = ms.x - (s0 + P.dmin[2]);
-            const bool inS0 = (unsigned) ms.x < (unsigned) dN_s, inS1 = (unsigned) (ms.x + 1) < (unsigned) dN_s;
+            const bool inS01 = (unsigned) ms.x < (unsigned) (dN_s - 1);  // taps ms.x and ms.x + 1 both inside (dN_s >= 1)
             float w0 = 1.0f, w1 = 1.0f;
             if (CLIP) {
                 const float Ss = __ldg(&P.A.ax[SA].S[loop]);
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                         const uint32_t a = *(const uint32_t*) rowp, bb = *(const uint32_t*) (rowp + 4);
                         wq[jq][js] = __funnelshift_r(a, bb, shift) & 0x00ffffffu;
                     }
-                const bool all_in = all_pq && inS0 && inS1;
+                const bool all_in = all_pq && inS01;
                 // Exact empty-space skip (SWAR "some byte > T", T = largest byte the low cut-off rejects): a trilinear value
                 // lies between its smallest and largest tap and the window position is monotone in the value, so if no tap
                 // exceeds T both samples are rejected and return exactly 0 (WindowedSampling.usf:28)
@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                     if (!all_in) {  // cold (volume faces only): the per-tap bounds are recomputed here rather than kept live through the loop
                         const bool ip[3] = {(unsigned) mp0.x < (unsigned) dN_p, (unsigned) (mp0.x + 1) < (unsigned) dN_p,
                                             (unsigned) (mp0.x + 2) < (unsigned) dN_p};
-                        const bool iq[2] = {(unsigned) mq.x < (unsigned) dN_q, (unsigned) (mq.x + 1) < (unsigned) dN_q}, is[2] = {inS0, inS1};
+                        const bool iq[2] = {(unsigned) mq.x < (unsigned) dN_q, (unsigned) (mq.x + 1) < (unsigned) dN_q};
+                        const bool is[2] = {(unsigned) ms.x < (unsigned) dN_s, (unsigned) (ms.x + 1) < (unsigned) dN_s};
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -505,18 +506,20 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                         if (v1) st_relaxed_sys_u64(zo + 1, tag | __float_as_uint(cur1));
                     }
                 }
+                // pixels beyond a ragged plane edge (v0 / v1 false) update their cell of the SMEM brick too: the TMA store clips the brick
+                // to the light volume, so those cells never reach memory — no validity test per slice
                 float* lp = s_light + light_off + (loop - s0) * P.ls_s;
                 if (P.mode == kModeAdd) {  // AddDirLightShader.usf:121-126
-                    if (v0 && fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
-                    if (v1 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
+                    if (fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
+                    if (fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
                 } else if (P.mode == kModeStore) {  // the removed light of a ChangeDirLight: its light goes to the scratch volume
-                    if (v0) lp[0] = cur0;
-                    if (v1) lp[P.ls_p] = cur1;
+                    lp[0] = cur0;
+                    lp[P.ls_p] = cur1;
                 } else {  // the added light of a ChangeDirLight: LightVolume += added - removed (ChangeDirLightShader.usf:146-153)
                     const float* rp = lp + P.light_bytes / 4;
                     const float r0c = rp[0], r1c = rp[P.ls_p];
-                    if (v0 && fabsf(cur0 - r0c) > 1e-3f) lp[0] = lp[0] + cur0 - r0c;
-                    if (v1 && fabsf(cur1 - r1c) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + cur1 - r1c;
+                    if (fabsf(cur0 - r0c) > 1e-3f) lp[0] = lp[0] + cur0 - r0c;
+                    if (fabsf(cur1 - r1c) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + cur1 - r1c;
                 }
             }
         }
