@@ -377,12 +377,13 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                     for (int jq = 0; jq < 2; ++jq) {
                         const unsigned char* rowp = base + jq * P.ds_q + js * P.ds_s;
                         const uint32_t a = *(const uint32_t*) rowp, bb = *(const uint32_t*) (rowp + 4);
-                        wq[jq][js] = __funnelshift_r(a, bb, shift) & 0x00ffffffu;
+                        wq[jq][js] = __funnelshift_r(a, bb, shift);  // bytes 0..2 = the three taps; byte 3 is not a tap and is never looked at
                     }
                 const bool all_in = all_pq && inS01;
                 // Exact empty-space skip (SWAR "some byte > T", T = largest byte the low cut-off rejects): a trilinear value
                 // lies between its smallest and largest tap and the window position is monotone in the value, so if no tap
-                // exceeds T both samples are rejected and return exactly 0 (WindowedSampling.usf:28)
+                // exceeds T both samples are rejected and return exactly 0 (WindowedSampling.usf:28). Carries only travel upward, so the
+                // stray byte 3 cannot disturb the three tap bytes, and the final mask drops its own flag.
                 uint32_t any_gt = 1u;
                 if (P.cut_lo_mode == 1)
                     any_gt = (((wq[0][0] + P.cut_lo_add) | wq[0][0]) | ((wq[0][1] + P.cut_lo_add) | wq[0][1]) |
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                             const uint32_t w = wq[jq][js];
                             t[0][jq][js] = decode_u8(w & 0xffu);
                             t[1][jq][js] = decode_u8((w >> 8) & 0xffu);
-                            t[2][jq][js] = decode_u8(w >> 16);
+                            t[2][jq][js] = decode_u8((w >> 16) & 0xffu);
                         }
                     if (!all_in) {  // cold (volume faces only): the per-tap bounds are recomputed here rather than kept live through the loop
                         const bool ip[3] = {(unsigned) mp0.x < (unsigned) dN_p, (unsigned) (mp0.x + 1) < (unsigned) dN_p,

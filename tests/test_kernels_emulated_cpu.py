@@ -38,9 +38,10 @@ def test_emulated_lit_raymarch_and_cube_setup_equal_golden(emulated):
 def test_emulated_tma_and_fused_sweeps_on_thin_volumes(emulated):
     """X % 16 == 0 volumes one or a few voxels thick: the TMA-staged and the generic fused sweep (which one takes a pass depends on the
     light) against the oracle, AddDirLight with axis-aligned lights and a ChangeDirLight, with and without a clip plane."""
-    win = FWindowingParameters(0.45, 0.5, True, False)
     impls = set()
-    for dims in [(16, 1, 1), (16, 16, 1), (32, 3, 5), (64, 8, 4)]:
+    # the second window rejects bytes up to 178: the other form of the exact empty-space test on tap bytes (threshold >= 128)
+    for dims, win in [((16, 1, 1), FWindowingParameters(0.45, 0.5, True, False)), ((16, 16, 1), FWindowingParameters(0.8, 0.2, True, True)),
+                      ((32, 3, 5), FWindowingParameters(0.45, 0.5, True, False)), ((64, 8, 4), FWindowingParameters(0.8, 0.2, True, False))]:
         data = np.random.default_rng(sum(dims)).integers(0, 256, dims[::-1]).astype(np.uint8)
         for world in (synth.identity_world(), synth.clipped_world()):
             res = M0.make_res(data, win)
