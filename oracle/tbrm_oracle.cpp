@@ -1128,7 +1128,7 @@ inline float mandelbulb_sdf_reference(F3 pos, float bailout, float power, int it
 }
 
 // NOT the reference's code: the CPU twin of the kernels' Power == 8 fast path (mandelbulb_sdf_p8 in csrc/mandelbulb.cu). The same
-// iteration with cos(theta) = z/r, sin(theta) = rho/r, cos(phi) = x/rho, sin(phi) = y/rho, three angle doublings and r^8 by squaring:
+// iteration with cos(theta) = z * (1/r), sin(theta) = rho * (1/r), cos(phi) = x * (1/rho), sin(phi) = y * (1/rho), three angle doublings and r^8 by squaring:
 // only +, -, *, /, sqrt — the same bits on the CPU and on the GPU up to the final log. Selected by tbo_set_mandelbulb_variant(1); the
 // tests use it to check the kernels tightly, and variant 0 to bound how far the fast path strays from the reference's formulation.
 inline float mandelbulb_sdf_p8(F3 pos, float bailout, int iterations, uint64_t& iters) {
@@ -1144,8 +1144,9 @@ inline float mandelbulb_sdf_p8(F3 pos, float bailout, int iterations, uint64_t& 
         dr = r7 * 8.0f * dr + 1.0f;
         const float rho2 = (zx * zx) + (zy * zy);
         const float rho = sqrtf(rho2);
-        float ct = zz / r, st = rho / r;
-        float cp = rho > 0.0f ? zx / rho : 1.0f, sp = rho > 0.0f ? zy / rho : 0.0f;
+        const float ir = 1.0f / r, irho = 1.0f / rho;  // two reciprocals and four products instead of four quotients
+        float ct = zz * ir, st = rho * ir;
+        float cp = rho > 0.0f ? zx * irho : 1.0f, sp = rho > 0.0f ? zy * irho : 0.0f;
         for (int d = 0; d < 3; ++d) {
             const float c2 = (ct * ct) - (st * st), s2 = 2.0f * (ct * st);
             ct = c2, st = s2;

@@ -83,8 +83,9 @@ __host__ __device__ __forceinline__ float mandelbulb_sdf_p8(float px, float py, 
         dr = r7 * 8.0f * dr + 1.0f;
         const float rho2 = (zx * zx) + (zy * zy);
         const float rho = sqrtf(rho2);
-        float ct = zz / r, st = rho / r;
-        float cp = rho > 0.0f ? zx / rho : 1.0f, sp = rho > 0.0f ? zy / rho : 0.0f;
+        const float ir = 1.0f / r, irho = 1.0f / rho;  // two reciprocals and four products instead of four quotients
+        float ct = zz * ir, st = rho * ir;
+        float cp = rho > 0.0f ? zx * irho : 1.0f, sp = rho > 0.0f ? zy * irho : 0.0f;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {  // 8 * angle
             const float c2 = (ct * ct) - (st * st), s2 = 2.0f * (ct * st);
