@@ -197,6 +197,7 @@ PROTOTYPES = {
         [_I, C.POINTER(Mandelbulb), C.c_float, C.POINTER(Camera), C.POINTER(World), _I, _I, _P, _I, C.POINTER(C.c_uint64)],
     ),
     "tbrm_debug_mandelbulb_sdf_p8": (C.c_float, [C.POINTER(C.c_float), C.c_float, _I, C.POINTER(C.c_uint32)]),
+    "tbrm_debug_download_derived": (_I, [_P, _I, _P, C.c_size_t]),
     "tbrm_mandelbulb_sdf": (_I, [_I, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_float, C.c_float, _I, _P, _I, C.POINTER(C.c_uint64)]),
     "tbrm_mhd_parse_header": (_I, [C.c_char_p, C.POINTER(VolumeInfo)]),
     "tbrm_volume_info_normalize_value": (C.c_float, [C.POINTER(VolumeInfo), C.c_float]),

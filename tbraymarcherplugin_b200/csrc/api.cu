@@ -1024,6 +1024,31 @@ float tbrm_debug_mandelbulb_sdf_p8(const float position[3], float bailout, int i
     return d;
 }
 
+tbrm_status tbrm_debug_download_derived(tbrm_resources* res, int which, void* dst, size_t capacity) {
+    TBRM_REQUIRE(res && dst, "tbrm_debug_download_derived: null argument");
+    TBRM_REQUIRE(which == 0 || which == 1, "tbrm_debug_download_derived: which must be 0 (brick grid) or 1 (yzx replica)");
+    tbrm_resources* r = res;
+    if (r->data_fmt != TBRM_FMT_G8 || !r->data_ready) {
+        set_last_error("tbrm_debug_download_derived: needs an uploaded R8 data volume");
+        return TBRM_ERR_NOT_INITIALIZED;
+    }
+    TBRM_CUDA(cudaSetDevice(r->device));
+    size_t bytes = r->data_voxels();
+    const void* src = nullptr;
+    if (which == 0) {
+        TBRM_CUDA(ensure_bricks(*r));
+        bytes = (size_t) ((r->ddims[0] + 7) / 8) * ((r->ddims[1] + 7) / 8) * ((r->ddims[2] + 7) / 8);
+        src = r->bricks;
+    } else {
+        TBRM_CUDA(build_replica_for_tests(*r));
+        src = r->data_yzx;
+    }
+    TBRM_REQUIRE(capacity >= bytes, "tbrm_debug_download_derived: destination too small");
+    TBRM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, r->stream));
+    TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    return TBRM_OK;
+}
+
 tbrm_status tbrm_mandelbulb_sdf(int device, const int32_t dims[3], const float center[3], float extent, float power, tbrm_format out_fmt,
                                 void* dst, int dst_is_device, uint64_t* out_iterations) {
     TBRM_REQUIRE(dims && center && dst, "tbrm_mandelbulb_sdf: null argument");

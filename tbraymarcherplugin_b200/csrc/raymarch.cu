@@ -564,6 +564,74 @@ __global__ void brick_max_kernel(const uint8_t* __restrict__ data, int X, int Y,
     }
 }
 
+// The same grid for R8 volumes with X % 16 == 0 in two launches that read the volume once with 16-byte loads (the kernel above issues 729
+// byte loads per brick): a 256-thread CTA owns a 128 x 8 x 8 strip = 16 bricks along x; a thread reduces its 16 voxels of one row to the
+// maxima of the two bricks they belong to and folds them into eight partial maxima per brick in shared memory — the whole brick (C), its
+// x = 0 / y = 0 / z = 0 faces (Fx, Fy, Fz), the three edges at the origin corner (Exy, Exz, Eyz) and the corner voxel (K). The apron of
+// brick b is the near face / edge / corner of its seven neighbours on the far side, so a second, tiny launch combines
+// out[b] = max(C[b], Fx[b+x], Fy[b+y], Fz[b+z], Exy[b+x+y], Exz[b+x+z], Eyz[b+y+z], K[b+x+y+z]).
+enum { kPartC = 0, kPartFx, kPartFy, kPartFz, kPartExy, kPartExz, kPartEyz, kPartK, kBrickParts };
+
+__device__ __forceinline__ unsigned int max_byte_of(unsigned int a, unsigned int b) {  // max over the 8 bytes of two words
+    const unsigned int m = __vmaxu4(a, b);
+    const unsigned int h = __vmaxu4(m, m >> 16);
+    return max(h & 0xffu, (h >> 8) & 0xffu);
+}
+
+__global__ void __launch_bounds__(256) brick_parts_kernel(const uint8_t* __restrict__ data, int X, int Y, int Z, int BX, int BY, int BZ,
+                                                          uint8_t* __restrict__ parts) {
+    __shared__ unsigned int s_part[kBrickParts][16];
+    const int t = threadIdx.x, seg = t & 7, ly = (t >> 3) & 7, lzq = t >> 6;
+    if (t < kBrickParts * 16) s_part[t >> 4][t & 15] = 0u;
+    __syncthreads();
+    const int x = blockIdx.x * 128 + 16 * seg, y = blockIdx.y * 8 + ly;
+    uint4 w[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int z = blockIdx.z * 8 + 4 * it + lzq;
+        w[it] = make_uint4(0u, 0u, 0u, 0u);  // voxels beyond the volume do not exist: 0 never raises a maximum
+        if (x < X && y < Y && z < Z) w[it] = __ldg(reinterpret_cast<const uint4*>(data + (size_t) x + (size_t) X * ((size_t) y + (size_t) Y * z)));
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int lz = 4 * it + lzq;
+        const unsigned int row[2] = {max_byte_of(w[it].x, w[it].y), max_byte_of(w[it].z, w[it].w)};  // the two bricks of this segment
+        const unsigned int first[2] = {w[it].x & 0xffu, w[it].z & 0xffu};                            // their x = 0 voxels
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b = 2 * seg + h;
+            atomicMax(&s_part[kPartC][b], row[h]);
+            atomicMax(&s_part[kPartFx][b], first[h]);
+            if (ly == 0) atomicMax(&s_part[kPartFy][b], row[h]), atomicMax(&s_part[kPartExy][b], first[h]);
+            if (lz == 0) atomicMax(&s_part[kPartFz][b], row[h]), atomicMax(&s_part[kPartExz][b], first[h]);
+            if (ly == 0 && lz == 0) atomicMax(&s_part[kPartEyz][b], row[h]), atomicMax(&s_part[kPartK][b], first[h]);
+        }
+    }
+    __syncthreads();
+    if (t < kBrickParts * 16) {
+        const int part = t >> 4, bx = blockIdx.x * 16 + (t & 15);
+        if (bx < BX) parts[(size_t) part * BX * BY * BZ + (size_t) bx + (size_t) BX * (blockIdx.y + (size_t) BY * blockIdx.z)] = (uint8_t) s_part[part][t & 15];
+    }
+}
+
+__global__ void __launch_bounds__(256) brick_combine_kernel(const uint8_t* __restrict__ parts, int BX, int BY, int BZ, uint8_t* __restrict__ out) {
+    const size_t n = (size_t) BX * BY * BZ;
+    const size_t b = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int bx = (int) (b % BX), by = (int) ((b / BX) % BY), bz = (int) (b / ((size_t) BX * BY));
+    const bool hx = bx + 1 < BX, hy = by + 1 < BY, hz = bz + 1 < BZ;  // a neighbour on the far side exists
+    const size_t sx = 1, sy = (size_t) BX, sz = (size_t) BX * BY;
+    unsigned int m = parts[kPartC * n + b];
+    if (hx) m = max(m, (unsigned int) parts[kPartFx * n + b + sx]);
+    if (hy) m = max(m, (unsigned int) parts[kPartFy * n + b + sy]);
+    if (hz) m = max(m, (unsigned int) parts[kPartFz * n + b + sz]);
+    if (hx && hy) m = max(m, (unsigned int) parts[kPartExy * n + b + sx + sy]);
+    if (hx && hz) m = max(m, (unsigned int) parts[kPartExz * n + b + sx + sz]);
+    if (hy && hz) m = max(m, (unsigned int) parts[kPartEyz * n + b + sy + sz]);
+    if (hx && hy && hz) m = max(m, (unsigned int) parts[kPartK * n + b + sx + sy + sz]);
+    out[b] = (uint8_t) m;
+}
+
 __global__ void cube_setup_kernel(const RayCam cam, float4* __restrict__ out) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
     if (ix >= cam.width || iy >= cam.height) return;
@@ -617,10 +685,19 @@ cudaError_t ensure_bricks(tbrm_resources& r) {
     if (r.bricks_valid) return cudaSuccess;
     const int BX = (r.ddims[0] + kBrick - 1) / kBrick, BY = (r.ddims[1] + kBrick - 1) / kBrick, BZ = (r.ddims[2] + kBrick - 1) / kBrick;
     cudaError_t e;
-    if (!r.bricks && (e = cudaMalloc(&r.bricks, (size_t) BX * BY * BZ)) != cudaSuccess) return e;
-    brick_max_kernel<<<BX * BY * BZ, 128, 0, r.stream>>>((const uint8_t*) r.data, r.ddims[0], r.ddims[1], r.ddims[2], BX, BY, BZ,
-                                                         (uint8_t*) r.bricks);
-    count_launch();
+    const size_t nb = (size_t) BX * BY * BZ;
+    if (!r.bricks && (e = cudaMalloc(&r.bricks, nb * (1 + kBrickParts))) != cudaSuccess) return e;  // the grid, then the 8 partial grids
+    if ((r.ddims[0] & 15) == 0 && (reinterpret_cast<uintptr_t>(r.data) & 15) == 0) {
+        uint8_t* parts = (uint8_t*) r.bricks + nb;
+        brick_parts_kernel<<<dim3((r.ddims[0] + 127) / 128, BY, BZ), 256, 0, r.stream>>>((const uint8_t*) r.data, r.ddims[0], r.ddims[1], r.ddims[2], BX,
+                                                                                       BY, BZ, parts);
+        brick_combine_kernel<<<(unsigned int) ((nb + 255) / 256), 256, 0, r.stream>>>(parts, BX, BY, BZ, (uint8_t*) r.bricks);
+        count_launch(2);
+    } else {
+        brick_max_kernel<<<BX * BY * BZ, 128, 0, r.stream>>>((const uint8_t*) r.data, r.ddims[0], r.ddims[1], r.ddims[2], BX, BY, BZ,
+                                                             (uint8_t*) r.bricks);
+        count_launch();
+    }
     r.bricks_valid = true;
     return cudaGetLastError();
 }

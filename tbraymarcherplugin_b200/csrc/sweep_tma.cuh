@@ -349,18 +349,55 @@ __global__ void permute_yzx_kernel(const uint8_t* __restrict__ src, uint8_t* __r
     }
 }
 
+// The same permutation for X % 16 == 0 and Y % 16 == 0 with 16-byte global accesses on both sides (the kernel above moves single bytes):
+// a 256-thread CTA transposes a 64 (x) x 64 (y) tile of one z plane through shared memory. In: one 16-byte load per thread, rows of the
+// tile stored as words (pitch 17: a warp's column reads below fall into one row, no bank conflict). Out: a thread gathers the 16 bytes
+// y0 .. y0 + 15 of one column x and writes them with one 16-byte store.
+__global__ void __launch_bounds__(256) permute_yzx_vec_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int X, int Y, int Z) {
+    __shared__ uint32_t tile[64][17];
+    const int t = threadIdx.x, z = blockIdx.z, bx = blockIdx.x * 64, by = blockIdx.y * 64;
+    {
+        const int row = t >> 2, vec = t & 3;
+        const int x = bx + 16 * vec, y = by + row;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (x < X && y < Y) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t) x + (size_t) X * ((size_t) y + (size_t) Y * z)));
+        tile[row][4 * vec + 0] = v.x, tile[row][4 * vec + 1] = v.y, tile[row][4 * vec + 2] = v.z, tile[row][4 * vec + 3] = v.w;
+    }
+    __syncthreads();
+    const int col = t & 63, seg = t >> 6;  // column x of the tile, 16 consecutive y
+    const int x = bx + col, y = by + 16 * seg;
+    if (x >= X || y >= Y) return;
+    const int word = col >> 2, shift = 8 * (col & 3);
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc |= ((tile[16 * seg + 4 * q + i][word] >> shift) & 0xffu) << (8 * i);
+        o[q] = acc;
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t) y + (size_t) Y * ((size_t) z + (size_t) Z * x)) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // the (y,z,x)-ordered replica of the data volume used by sweeps along X; rebuilt lazily after an upload
 static cudaError_t ensure_replica(tbrm_resources& r) {
     if (r.data_yzx_valid) return cudaSuccess;
     const size_t bytes = r.data_voxels();
     cudaError_t e;
     if (!r.data_yzx && (e = cudaMalloc(&r.data_yzx, bytes)) != cudaSuccess) return e;
-    const dim3 block(32, 8), grid((r.ddims[0] + 31) / 32, (r.ddims[1] + 31) / 32, r.ddims[2]);
-    permute_yzx_kernel<<<grid, block, 0, r.stream>>>((const uint8_t*) r.data, (uint8_t*) r.data_yzx, r.ddims[0], r.ddims[1], r.ddims[2]);
+    if ((r.ddims[0] & 15) == 0 && (r.ddims[1] & 15) == 0 && ((reinterpret_cast<uintptr_t>(r.data) | reinterpret_cast<uintptr_t>(r.data_yzx)) & 15) == 0) {
+        const dim3 grid((r.ddims[0] + 63) / 64, (r.ddims[1] + 63) / 64, r.ddims[2]);
+        permute_yzx_vec_kernel<<<grid, 256, 0, r.stream>>>((const uint8_t*) r.data, (uint8_t*) r.data_yzx, r.ddims[0], r.ddims[1], r.ddims[2]);
+    } else {
+        const dim3 block(32, 8), grid((r.ddims[0] + 31) / 32, (r.ddims[1] + 31) / 32, r.ddims[2]);
+        permute_yzx_kernel<<<grid, block, 0, r.stream>>>((const uint8_t*) r.data, (uint8_t*) r.data_yzx, r.ddims[0], r.ddims[1], r.ddims[2]);
+    }
     count_launch();
     r.data_yzx_valid = true;
     return cudaGetLastError();
 }
+
+cudaError_t build_replica_for_tests(tbrm_resources& r) { return ensure_replica(r); }
 
 // the pass is left to another sweep implementation; remember why (shown when a sharded volume has no alternative)
 static cudaError_t not_handled(const char* why) {

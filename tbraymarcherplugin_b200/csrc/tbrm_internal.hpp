@@ -108,6 +108,7 @@ cudaError_t sweep_pass_joined(tbrm_resources& r, const SweepUniforms& u, const L
 cudaError_t sweep_pass_fused(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
 cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled);
 cudaError_t clear_light(tbrm_resources& r, float value);
+cudaError_t build_replica_for_tests(tbrm_resources& r);  // the (y,z,x)-ordered replica of an R8 data volume (tbrm_debug_download_derived)
 int slab_pass_order(const SweepUniforms& u);  // +1 lower slabs first, -1 higher slabs first, 2 only concurrently
 size_t slab_arena_bytes(const int32_t ldims[3]);
 cudaError_t slab_ensure_arena(tbrm_resources& r);

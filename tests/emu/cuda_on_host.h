@@ -313,6 +313,14 @@ static inline unsigned int __byte_perm(unsigned int a, unsigned int b, unsigned 
     for (int i = 0; i < 4; ++i) r |= (unsigned int) ((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffull) << (8 * i);
     return r;
 }
+static inline unsigned int __vmaxu4(unsigned int a, unsigned int b) {  // per-byte unsigned maximum
+    unsigned int r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned int x = (a >> (8 * i)) & 0xffu, y = (b >> (8 * i)) & 0xffu;
+        r |= (x > y ? x : y) << (8 * i);
+    }
+    return r;
+}
 // binary16 (round to nearest even), through the compiler's _Float16
 struct __half {
     _Float16 v;

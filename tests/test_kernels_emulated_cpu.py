@@ -152,3 +152,10 @@ def test_emulated_octree_build_kernels(emulated, dims):
     for m, want in enumerate(oracle.generate_octree(data)):
         assert np.array_equal(URaymarchUtils.ReadOctreeMip(res, m), want), m
     res.release()
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 8), (144, 80, 40), (48, 33, 17), (40, 24, 16)])
+def test_emulated_brick_grid_and_axis_replica(emulated, dims):
+    """the structures derived from every uploaded volume (two-launch brick grid, 16-byte (y,z,x) transpose; byte-wise kernels on other
+    sizes) against their definitions in numpy"""
+    M.derived_structures_match_numpy(dims)

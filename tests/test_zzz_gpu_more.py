@@ -210,3 +210,38 @@ def test_degenerate_and_ragged_sizes_match_oracle(dims, gpu_sync):
             assert np.array_equal(URaymarchUtils.PerformWindowedRaymarchOctree(res, cam, world, 17.0, mip)[0],
                                   oracle.raymarch_octree(vol, cam, world, 17.0, mips, mip)[0])
         res.release()
+
+
+def derived_structures_match_numpy(dims):
+    """brick grid and (y,z,x) replica through tbrm_debug_download_derived against their definitions in numpy"""
+    import ctypes as C
+
+    from tbraymarcherplugin_b200 import _capi
+
+    X, Y, Z = dims
+    data = np.random.default_rng(sum(dims)).integers(0, 256, (Z, Y, X)).astype(np.uint8)
+    data[data < 200] //= 4  # mostly small values with rare large ones: maxima that depend on single voxels
+    res = make_res(data, FWindowingParameters(0.45, 0.5, True, False))
+    lib = _capi.load()
+    B = [(d + 7) // 8 for d in dims]
+    bricks = np.zeros((B[2], B[1], B[0]), np.uint8)
+    _capi.check(lib.tbrm_debug_download_derived(res.handle, 0, bricks.ctypes.data_as(C.c_void_p), bricks.size))
+    padded = np.zeros((8 * B[2] + 1, 8 * B[1] + 1, 8 * B[0] + 1), np.uint8)
+    padded[:Z, :Y, :X] = data
+    want = np.zeros_like(bricks)
+    for dz in range(9):
+        for dy in range(9):
+            for dx in range(9):
+                want = np.maximum(want, padded[dz:dz + 8 * B[2]:8, dy:dy + 8 * B[1]:8, dx:dx + 8 * B[0]:8])
+    assert np.array_equal(bricks, want), dims
+    replica = np.zeros((X, Z, Y), np.uint8)
+    _capi.check(lib.tbrm_debug_download_derived(res.handle, 1, replica.ctypes.data_as(C.c_void_p), replica.size))
+    assert np.array_equal(replica, data.transpose(2, 0, 1)), dims
+    res.release()
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 8), (144, 80, 40), (64, 64, 64), (48, 33, 17), (40, 24, 16), (256, 128, 72)])
+def test_brick_grid_and_axis_replica_match_their_definitions(dims):
+    """brick_parts_kernel + brick_combine_kernel / permute_yzx_vec_kernel (X % 16 == 0 [and Y % 16 == 0]) and the byte-wise kernels they
+    replace on other sizes."""
+    derived_structures_match_numpy(dims)
