@@ -580,10 +580,10 @@ __device__ __forceinline__ unsigned int max_byte_of(unsigned int a, unsigned int
 
 __global__ void __launch_bounds__(256) brick_parts_kernel(const uint8_t* __restrict__ data, int X, int Y, int Z, int BX, int BY, int BZ,
                                                           uint8_t* __restrict__ parts) {
-    __shared__ unsigned int s_part[kBrickParts][16];
-    const int t = threadIdx.x, seg = t & 7, ly = (t >> 3) & 7, lzq = t >> 6;
-    if (t < kBrickParts * 16) s_part[t >> 4][t & 15] = 0u;
-    __syncthreads();
+    // per round (4 z slices), warp (4 rows of one slice) and 16-voxel segment: the packed maxima {brick 2seg, brick 2seg+1, their x = 0
+    // voxels} over the warp's 4 rows (s_rows) and of its first row alone (s_row0) — no atomics
+    __shared__ unsigned int s_rows[2][8][8], s_row0[2][8][8];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, seg = t & 7, ly = (t >> 3) & 7, lzq = t >> 6;
     const int x = blockIdx.x * 128 + 16 * seg, y = blockIdx.y * 8 + ly;
     uint4 w[2];
 #pragma unroll
@@ -594,23 +594,28 @@ __global__ void __launch_bounds__(256) brick_parts_kernel(const uint8_t* __restr
     }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-        const int lz = 4 * it + lzq;
-        const unsigned int row[2] = {max_byte_of(w[it].x, w[it].y), max_byte_of(w[it].z, w[it].w)};  // the two bricks of this segment
-        const unsigned int first[2] = {w[it].x & 0xffu, w[it].z & 0xffu};                            // their x = 0 voxels
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int b = 2 * seg + h;
-            atomicMax(&s_part[kPartC][b], row[h]);
-            atomicMax(&s_part[kPartFx][b], first[h]);
-            if (ly == 0) atomicMax(&s_part[kPartFy][b], row[h]), atomicMax(&s_part[kPartExy][b], first[h]);
-            if (lz == 0) atomicMax(&s_part[kPartFz][b], row[h]), atomicMax(&s_part[kPartExz][b], first[h]);
-            if (ly == 0 && lz == 0) atomicMax(&s_part[kPartEyz][b], row[h]), atomicMax(&s_part[kPartK][b], first[h]);
-        }
+        unsigned int p = max_byte_of(w[it].x, w[it].y) | (max_byte_of(w[it].z, w[it].w) << 8) | ((w[it].x & 0xffu) << 16) | ((w[it].z & 0xffu) << 24);
+        if (lane < 8) s_row0[it][warp][seg] = p;  // lanes 0..7 hold the warp's first row (ly = 0 or 4)
+        p = __vmaxu4(p, __shfl_xor_sync(0xffffffffu, p, 8));
+        p = __vmaxu4(p, __shfl_xor_sync(0xffffffffu, p, 16));
+        if (lane < 8) s_rows[it][warp][seg] = p;
     }
     __syncthreads();
     if (t < kBrickParts * 16) {
-        const int part = t >> 4, bx = blockIdx.x * 16 + (t & 15);
-        if (bx < BX) parts[(size_t) part * BX * BY * BZ + (size_t) bx + (size_t) BX * (blockIdx.y + (size_t) BY * blockIdx.z)] = (uint8_t) s_part[part][t & 15];
+        const int part = t >> 4, b = t & 15, sg = b >> 1;
+        // which byte of the packed word, which warps (bit 0 of the warp: rows 0-3 / 4-7; bits 1-2: slice within the round), which rounds
+        const bool first = part == kPartFx || part == kPartExy || part == kPartExz || part == kPartK;
+        const bool y0 = part == kPartFy || part == kPartExy || part == kPartEyz || part == kPartK;   // only the row ly = 0
+        const bool z0 = part == kPartFz || part == kPartExz || part == kPartEyz || part == kPartK;   // only the slice lz = 0
+        const int shift = 8 * ((b & 1) + (first ? 2 : 0));
+        unsigned int m = 0;
+        for (int it = 0; it < (z0 ? 1 : 2); ++it)
+            for (int wp = 0; wp < (z0 ? 2 : 8); ++wp) {
+                if (y0 && (wp & 1)) continue;
+                m = max(m, ((y0 ? s_row0[it][wp][sg] : s_rows[it][wp][sg]) >> shift) & 0xffu);
+            }
+        const int bx = blockIdx.x * 16 + b;
+        if (bx < BX) parts[(size_t) part * BX * BY * BZ + (size_t) bx + (size_t) BX * (blockIdx.y + (size_t) BY * blockIdx.z)] = (uint8_t) m;
     }
 }
 
