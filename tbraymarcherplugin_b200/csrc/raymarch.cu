@@ -245,6 +245,7 @@ struct FastUniforms {
     int skip_byte;          // largest byte the low cut-off rejects (-1: no skipping)
     float rwidth;
     int same_dims;          // the light volume has the data volume's dimensions (raymarch_fast2_kernel)
+    float fddims[3], fldims[3];  // the dimensions as floats (axis_taps_bounded)
     float leap_margin;      // voxels kept clear of a brick face when leaping (> drift of the accumulated position)
 };
 
@@ -257,15 +258,39 @@ __device__ __forceinline__ float div_exact(float x, float w, float rw) {  // == 
     return __fmaf_rn(__fmaf_rn(-q, w, x), rw, q);
 }
 
+// ---- pipe-balanced addressing of the sample (ADDR32) --------------------------------------------------------------------------------
+// The profile of the lit march (profiles/r1_raymarch_fast_kernel_ncu.txt) has the ALU pipe as the busiest unit (62 %) with the FMA pipes
+// at 28 %: of the ~195 ALU-pipe instructions of a full sample about 90 form addresses (64-bit IADD3 / LEA / SHF pairs per tap), 12 clamp
+// the tap index in float before it is clamped again as an integer, 6 convert the dimensions to float. ADDR32 moves that work to the
+// FMA pipe or drops it: tap offsets are 32-bit integer multiply-adds (IMAD), a light tap's address is ONE widening multiply-add from the
+// volume's base (IMAD.WIDE index * 4 + base) and a data tap's one 64-bit add of the uniform base (ptxas splits a widening multiply-add by
+// 1 into exactly that, whatever is done to hide the 1), the float clamp is dropped where the integer clamp / wrap follows (march
+// positions stay within [-1, 2], so the conversion cannot overflow), and the float dimensions come from the uniforms. Same taps, same
+// weights, same arithmetic on the values: bit-identical to the 64-bit form (the host uses ADDR32 for volumes below 2^31 voxels).
+// axis_taps without the float clamp of the tap index: for callers that clamp or wrap the integer index and whose u is bounded
+__device__ __forceinline__ void axis_taps_bounded(float u, float fN, int& i0, float& f) {
+    const float x = u * fN - 0.5f;
+    const float fl = floorf(x);
+    f = x - fl;
+    i0 = (int) fl;
+}
+
 // one march sample (AccumulateWindowedRaymarchStep); returns nothing, updates acc
+template <bool ADDR32>
 __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t* __restrict__ data, const float* __restrict__ light,
                                             const float4* s_tf, V3 p, float step, float4& acc) {
     const MarchUniforms& U = F.M;
     int i0, j0, k0;
     float fx, fy, fz;
-    axis_taps(p.x, U.ddims[0], i0, fx);
-    axis_taps(p.y, U.ddims[1], j0, fy);
-    axis_taps(p.z, U.ddims[2], k0, fz);
+    if (ADDR32) {
+        axis_taps_bounded(p.x, F.fddims[0], i0, fx);
+        axis_taps_bounded(p.y, F.fddims[1], j0, fy);
+        axis_taps_bounded(p.z, F.fddims[2], k0, fz);
+    } else {
+        axis_taps(p.x, U.ddims[0], i0, fx);
+        axis_taps(p.y, U.ddims[1], j0, fy);
+        axis_taps(p.z, U.ddims[2], k0, fz);
+    }
     const int xs0 = clamp_index(i0, U.ddims[0]), ys0 = clamp_index(j0, U.ddims[1]), zs0 = clamp_index(k0, U.ddims[2]);
     if (F.bricks) {
         const int m = __ldg(F.bricks + (xs0 >> 3) + F.bdims[0] * ((ys0 >> 3) + F.bdims[1] * (zs0 >> 3)));
@@ -274,13 +299,25 @@ __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t
         if (m <= F.skip_byte && fx < 1.0f && fy < 1.0f && fz < 1.0f) return;
     }
     const int xs1 = clamp_index(i0 + 1, U.ddims[0]), ys1 = clamp_index(j0 + 1, U.ddims[1]), zs1 = clamp_index(k0 + 1, U.ddims[2]);
-    const size_t X = U.ddims[0], XY = (size_t) U.ddims[0] * U.ddims[1];
-    const uint8_t* r00 = data + X * ys0 + XY * zs0;
-    const uint8_t* r01 = data + X * ys1 + XY * zs0;
-    const uint8_t* r10 = data + X * ys0 + XY * zs1;
-    const uint8_t* r11 = data + X * ys1 + XY * zs1;
-    const uint32_t b000 = __ldg(r00 + xs0), b100 = __ldg(r00 + xs1), b010 = __ldg(r01 + xs0), b110 = __ldg(r01 + xs1);
-    const uint32_t b001 = __ldg(r10 + xs0), b101 = __ldg(r10 + xs1), b011 = __ldg(r11 + xs0), b111 = __ldg(r11 + xs1);
+    uint32_t b000, b100, b010, b110, b001, b101, b011, b111;
+    if (ADDR32) {
+        const unsigned int X = (unsigned int) U.ddims[0], XY = X * (unsigned int) U.ddims[1];
+        const unsigned int zx00 = (unsigned int) zs0 * XY + (unsigned int) xs0, zx01 = (unsigned int) zs0 * XY + (unsigned int) xs1;
+        const unsigned int zx10 = (unsigned int) zs1 * XY + (unsigned int) xs0, zx11 = (unsigned int) zs1 * XY + (unsigned int) xs1;
+        const unsigned int ya = (unsigned int) ys0 * X, yb = (unsigned int) ys1 * X;
+        b000 = __ldg(data + (ya + zx00)), b100 = __ldg(data + (ya + zx01));
+        b010 = __ldg(data + (yb + zx00)), b110 = __ldg(data + (yb + zx01));
+        b001 = __ldg(data + (ya + zx10)), b101 = __ldg(data + (ya + zx11));
+        b011 = __ldg(data + (yb + zx10)), b111 = __ldg(data + (yb + zx11));
+    } else {
+        const size_t X = U.ddims[0], XY = (size_t) U.ddims[0] * U.ddims[1];
+        const uint8_t* r00 = data + X * ys0 + XY * zs0;
+        const uint8_t* r01 = data + X * ys1 + XY * zs0;
+        const uint8_t* r10 = data + X * ys0 + XY * zs1;
+        const uint8_t* r11 = data + X * ys1 + XY * zs1;
+        b000 = __ldg(r00 + xs0), b100 = __ldg(r00 + xs1), b010 = __ldg(r01 + xs0), b110 = __ldg(r01 + xs1);
+        b001 = __ldg(r10 + xs0), b101 = __ldg(r10 + xs1), b011 = __ldg(r11 + xs0), b111 = __ldg(r11 + xs1);
+    }
     const float c00 = lerpf(decode_u8_exact(b000), decode_u8_exact(b100), fx);
     const float c01 = lerpf(decode_u8_exact(b010), decode_u8_exact(b110), fx);
     const float c10 = lerpf(decode_u8_exact(b001), decode_u8_exact(b101), fx);
@@ -299,20 +336,36 @@ __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t
     {
         int li, lj, lk;
         float gx, gy, gz;
-        axis_taps(saturatef(p.x), U.ldims[0], li, gx);
-        axis_taps(saturatef(p.y), U.ldims[1], lj, gy);
-        axis_taps(saturatef(p.z), U.ldims[2], lk, gz);
+        if (ADDR32) {
+            axis_taps_bounded(saturatef(p.x), F.fldims[0], li, gx);
+            axis_taps_bounded(saturatef(p.y), F.fldims[1], lj, gy);
+            axis_taps_bounded(saturatef(p.z), F.fldims[2], lk, gz);
+        } else {
+            axis_taps(saturatef(p.x), U.ldims[0], li, gx);
+            axis_taps(saturatef(p.y), U.ldims[1], lj, gy);
+            axis_taps(saturatef(p.z), U.ldims[2], lk, gz);
+        }
         const int LX = U.ldims[0], LY = U.ldims[1], LZ = U.ldims[2];
         const int x0 = li < 0 ? li + LX : li, x1 = li + 1 >= LX ? li + 1 - LX : li + 1;
         const int y0 = lj < 0 ? lj + LY : lj, y1 = lj + 1 >= LY ? lj + 1 - LY : lj + 1;
         const int z0 = lk < 0 ? lk + LZ : lk, z1 = lk + 1 >= LZ ? lk + 1 - LZ : lk + 1;
-        const size_t SX = LX, SXY = (size_t) LX * LY;
-        const float* q00 = light + SX * y0 + SXY * z0;
-        const float* q01 = light + SX * y1 + SXY * z0;
-        const float* q10 = light + SX * y0 + SXY * z1;
-        const float* q11 = light + SX * y1 + SXY * z1;
-        const float d00 = lerpf(__ldg(q00 + x0), __ldg(q00 + x1), gx), d01 = lerpf(__ldg(q01 + x0), __ldg(q01 + x1), gx);
-        const float d10 = lerpf(__ldg(q10 + x0), __ldg(q10 + x1), gx), d11 = lerpf(__ldg(q11 + x0), __ldg(q11 + x1), gx);
+        float d00, d01, d10, d11;
+        if (ADDR32) {
+            const unsigned int SX = (unsigned int) LX, SXY = SX * (unsigned int) LY;
+            const unsigned int zx00 = (unsigned int) z0 * SXY + (unsigned int) x0, zx01 = (unsigned int) z0 * SXY + (unsigned int) x1;
+            const unsigned int zx10 = (unsigned int) z1 * SXY + (unsigned int) x0, zx11 = (unsigned int) z1 * SXY + (unsigned int) x1;
+            const unsigned int ya = (unsigned int) y0 * SX, yb = (unsigned int) y1 * SX;
+            d00 = lerpf(__ldg(light + (ya + zx00)), __ldg(light + (ya + zx01)), gx), d01 = lerpf(__ldg(light + (yb + zx00)), __ldg(light + (yb + zx01)), gx);
+            d10 = lerpf(__ldg(light + (ya + zx10)), __ldg(light + (ya + zx11)), gx), d11 = lerpf(__ldg(light + (yb + zx10)), __ldg(light + (yb + zx11)), gx);
+        } else {
+            const size_t SX = LX, SXY = (size_t) LX * LY;
+            const float* q00 = light + SX * y0 + SXY * z0;
+            const float* q01 = light + SX * y1 + SXY * z0;
+            const float* q10 = light + SX * y0 + SXY * z1;
+            const float* q11 = light + SX * y1 + SXY * z1;
+            d00 = lerpf(__ldg(q00 + x0), __ldg(q00 + x1), gx), d01 = lerpf(__ldg(q01 + x0), __ldg(q01 + x1), gx);
+            d10 = lerpf(__ldg(q10 + x0), __ldg(q10 + x1), gx), d11 = lerpf(__ldg(q11 + x0), __ldg(q11 + x1), gx);
+        }
         const float l = lerpf(lerpf(d00, d01, gy), lerpf(d10, d11, gy), gz);
         sx = sx * l, sy = sy * l, sz = sz * l;
     }
@@ -323,7 +376,7 @@ __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t
     acc.w = acc.w + (alpha * oma);
 }
 
-template <bool CLIP>
+template <bool CLIP, bool ADDR32>
 __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
                                                             const float* __restrict__ light, const float4* __restrict__ tf,
                                                             float4* __restrict__ out, unsigned long long* __restrict__ steps_out) {
@@ -361,7 +414,7 @@ __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F
                                       U.clip_dir[1], U.clip_dir[2]);
                 if (cd <= 0.0f) continue;
             }
-            fast_sample(F, data, light, s_tf, cur, ssw, acc);
+            fast_sample<ADDR32>(F, data, light, s_tf, cur, ssw, acc);
             if (acc.w > 0.95f) {
                 acc.w = 1.0f;
                 break;
@@ -377,7 +430,7 @@ __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F
                                       U.clip_dir[1], U.clip_dir[2]);
                 clipped = cd <= 0.0f;
             }
-            if (!clipped) fast_sample(F, data, light, s_tf, cur, 100.0f * fin, acc);
+            if (!clipped) fast_sample<ADDR32>(F, data, light, s_tf, cur, 100.0f * fin, acc);
         }
         out[(size_t) lr * U.cam.width + ix] = acc;
     }
@@ -465,7 +518,7 @@ __global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms 
             const bool interior = ((unsigned) i0 - 1u) < (unsigned) max(X - 2, 0) && ((unsigned) j0 - 1u) < (unsigned) max(Y - 2, 0) &&
                                   ((unsigned) k0 - 1u) < (unsigned) max(Z - 2, 0);
             if (!interior || !F.same_dims) {  // the one-voxel shell, half-resolution light volumes: the general sampler
-                fast_sample(F, data, light, s_tf, cur, ssw, acc);
+                fast_sample<false>(F, data, light, s_tf, cur, ssw, acc);
             } else {
                 if (F.bricks) {
                     const int m = __ldg(F.bricks + (i0 >> 3) + F.bdims[0] * ((j0 >> 3) + F.bdims[1] * (k0 >> 3)));
@@ -531,7 +584,7 @@ __global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms 
                                       U.clip_dir[1], U.clip_dir[2]);
                 clipped = cd <= 0.0f;
             }
-            if (!clipped) fast_sample(F, data, light, s_tf, cur, 100.0f * fin, acc);
+            if (!clipped) fast_sample<false>(F, data, light, s_tf, cur, 100.0f * fin, acc);
         }
         out[(size_t) lr * U.cam.width + ix] = acc;
     }
@@ -759,7 +812,10 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
         const int nmax = std::max(r.ddims[0], std::max(r.ddims[1], r.ddims[2]));
         // accumulated positions drift by < kMaxLeap half-ulps of values in [-1, 2] (1.2e-7 each) = 7.7e-6 UVW = 7.7e-6 * N voxels
         F.leap_margin = std::max(0.01f, 1.0e-5f * (float) nmax);
-        // reserved[1]: 0 default, 1 generic kernel, 2 first-generation fast kernel, 3 second-generation fast kernel
+        // reserved[1]: 0 default, 1 generic kernel, 2 fast kernel with the 64-bit tap addressing round 1 measured, 3 second-generation fast kernel
+        for (int k = 0; k < 3; ++k) F.fddims[k] = (float) r.ddims[k], F.fldims[k] = (float) r.ldims[k];
+        static const bool addr64_forced = [] { const char* e = getenv("TBRM_RAYMARCH_ADDR64"); return e && e[0] == '1'; }();
+        const bool addr32 = r.options.reserved[1] != 2 && !addr64_forced && r.data_voxels() < (1ull << 31) && r.light_voxels() < (1ull << 31);
         static const bool v2_default = [] { const char* e = getenv("TBRM_RAYMARCH_V2"); return e ? e[0] == '1' : kRaymarchV2Default; }();
         const bool v2 = (r.options.reserved[1] == 3 || (r.options.reserved[1] == 0 && v2_default)) && r.data_voxels() < (1ull << 31);
         const bool noclip = clip_never_rejects(clip_center, clip_dir);
@@ -767,10 +823,14 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
             raymarch_fast2_kernel<false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
         else if (v2)
             raymarch_fast2_kernel<true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+        else if (noclip && addr32)
+            raymarch_fast_kernel<false, true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+        else if (addr32)
+            raymarch_fast_kernel<true, true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
         else if (noclip)
-            raymarch_fast_kernel<false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+            raymarch_fast_kernel<false, false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
         else
-            raymarch_fast_kernel<true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+            raymarch_fast_kernel<true, false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
         count_launch();
         return cudaGetLastError();
     }

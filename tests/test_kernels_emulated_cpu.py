@@ -159,3 +159,8 @@ def test_emulated_brick_grid_and_axis_replica(emulated, dims):
     """the structures derived from every uploaded volume (two-launch brick grid, 16-byte (y,z,x) transpose; byte-wise kernels on other
     sizes) against their definitions in numpy"""
     M.derived_structures_match_numpy(dims)
+
+
+def test_emulated_lit_march_in_both_addressing_forms(emulated):
+    M.test_lit_march_with_64_bit_tap_addressing_still_matches_oracle((40, 24, 56))
+    M.test_lit_march_with_64_bit_tap_addressing_still_matches_oracle((1, 7, 1))

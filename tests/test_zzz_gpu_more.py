@@ -245,3 +245,24 @@ def test_brick_grid_and_axis_replica_match_their_definitions(dims):
     """brick_parts_kernel + brick_combine_kernel / permute_yzx_vec_kernel (X % 16 == 0 [and Y % 16 == 0]) and the byte-wise kernels they
     replace on other sizes."""
     derived_structures_match_numpy(dims)
+
+
+@pytest.mark.parametrize("dims", [(40, 24, 56), (1, 7, 1)])
+def test_lit_march_with_64_bit_tap_addressing_still_matches_oracle(dims):
+    """The default lit march forms tap addresses from 32-bit offsets (ADDR32, csrc/raymarch.cu); reserved[1] = 2 selects the 64-bit pointer
+    form that round 1 measured. Both must give the oracle's frame."""
+    data = np.random.default_rng(sum(dims)).integers(0, 256, dims[::-1]).astype(np.uint8)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    for world in (synth.identity_world(), synth.clipped_world()):
+        res = make_res(data, win)
+        vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win)
+        for l in synth.LIGHTS[:2]:
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world)
+            vol.add_dir_light(l, True, world)
+        cam = synth.benchmark_camera(40, 24, jitter=True, frame=2)
+        ref, ref_steps = vol.raymarch_lit(cam, world, 33.0)
+        for flag in (0, 2):
+            URaymarchUtils.SetOptions(res, debug_flags=(0, flag))
+            rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 33.0)
+            assert steps == ref_steps and np.array_equal(rgba, ref), (dims, flag)
+        res.release()
