@@ -1,5 +1,6 @@
-"""One-shot validation of raymarch_fast2_kernel (second-generation lit ray march) against the first-generation fast kernel and
-the generic kernel: frames and executed-step counts must be bit-identical; prints timings. Exit code 0 = identical."""
+"""One-shot validation of raymarch_fast2_kernel (second-generation lit ray march) and of the default kernel's 32-bit tap addressing (ADDR32)
+against the first-generation fast kernel with 64-bit addressing and the generic kernel: frames and executed-step counts must be
+bit-identical; prints timings. Exit code 0 = identical."""
 import ctypes as C
 import sys
 
@@ -12,6 +13,7 @@ from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters, URaymar
 
 lib = _capi.load()
 ok = True
+LOG = []
 
 
 def frame(res, cam, world, steps, kernel):
@@ -39,10 +41,11 @@ for n, view, steps, world_name, half in [(512, (1920, 1080), 512.0, "identity", 
     for l in synth.LIGHTS[:2]:
         URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=not half)
     cam = synth.benchmark_camera(*view)
-    f1, s1, t1 = frame(res, cam, world, steps, 2)
+    f1, s1, t1 = frame(res, cam, world, steps, 2)   # first-generation fast kernel, 64-bit tap addressing (what round 1 measured)
     f2, s2, t2 = frame(res, cam, world, steps, 3)
-    same = np.array_equal(f1, f2) and s1 == s2
-    msg = f"n={n} {view} {world_name} half={half}: v1 {t1:.3f} ms, v2 {t2:.3f} ms, steps {s1} / {s2}, identical={same}"
+    f0, s0, t0 = frame(res, cam, world, steps, 0)   # the default: the same kernel with 32-bit / IMAD tap addressing (ADDR32)
+    same = np.array_equal(f1, f2) and s1 == s2 and np.array_equal(f1, f0) and s1 == s0
+    msg = f"n={n} {view} {world_name} half={half}: v1 {t1:.3f} ms, v2 {t2:.3f} ms, default (ADDR32) {t0:.3f} ms, steps {s1} / {s2} / {s0}, identical={same}"
     if n <= 256:
         fg, sg, tg = frame(res, cam, world, steps, 1)
         same_g = np.array_equal(fg, f2) and sg == s2
@@ -52,7 +55,15 @@ for n, view, steps, world_name, half in [(512, (1920, 1080), 512.0, "identity", 
         dd = np.abs(f1 - f2)
         msg += f" MAXDIFF {dd.max():.3e} at {np.argwhere(dd > 0)[:3].tolist()}"
     print(msg, flush=True)
+    LOG.append(msg)
     ok = ok and same
     res.release()
 print("V2 OK" if ok else "V2 MISMATCH", flush=True)
+try:  # keep the timings where a gpurun call brings them back
+    import os
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/raymarch_ab.txt", "w") as fh:
+            fh.write("\n".join(LOG) + "\n")
+except OSError:
+    pass
 sys.exit(0 if ok else 1)
