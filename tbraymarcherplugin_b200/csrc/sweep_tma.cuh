@@ -268,10 +268,11 @@ static cudaError_t upload(tbrm_resources& r, const void* src, size_t bytes, size
     return e;
 }
 
-static const void* tma_kernel(int axis, bool clip, bool slab) {
-#define TBRM_K(A) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true> : (const void*) sweep_tma_kernel<A, false, true>) \
-                        : (clip ? (const void*) sweep_tma_kernel<A, true, false> : (const void*) sweep_tma_kernel<A, false, false>))
-    return axis == 0 ? TBRM_K(0) : (axis == 1 ? TBRM_K(1) : TBRM_K(2));
+static const void* tma_kernel(int axis, bool clip, bool slab, int px) {
+#define TBRM_K(A, PX) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true, PX> : (const void*) sweep_tma_kernel<A, false, true, PX>) \
+                            : (clip ? (const void*) sweep_tma_kernel<A, true, false, PX> : (const void*) sweep_tma_kernel<A, false, false, PX>))
+    if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
+    return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
 #undef TBRM_K
 }
 
@@ -469,6 +470,21 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     TmaParams P;
     memset(&P, 0, sizeof(P));
     P.U = u;
+    // pixels per thread: two (tile 64 x 8) while the launch has enough tiles to fill the SMs, one (tile 32 x 8) below that — there a pass
+    // costs slices x one tile's per-slice chain, which one pixel per thread shortens (bits 4-5 of reserved[0]: 1 / 2 force the choice)
+    int px = 2;
+    {
+        const int rows = (r.slab.nranks > 1 && u.axis != 2) ? r.slab.z_end - r.slab.z_begin : ty;  // buffer rows this GPU sweeps
+        const long long tiles64 = (long long) ((tx + 63) / 64) * ((rows + kTH - 1) / kTH);
+        // round 1's numbers: a tile alone on an SM needs L = 3 400 cycles per slice, an SM with 4 resident tiles 4 875 (T = 1 220 per tile and
+        // slice); one pixel per thread scales both by 446 / 611 (SASS of the slice loop) and doubles the tiles, so it wins while the
+        // doubled tiles still fit three to an SM: max(0.73 L, ceil(2 t / SMs) * 0.73 T) < max(L, ceil(t / SMs) * T)
+        if (2 * tiles64 <= 3ll * sms) px = 1;
+        static const int env_px = [] { const char* e = getenv("TBRM_SWEEP_PX"); return e ? atoi(e) : 0; }();  // A/B timing, tests
+        const int forced = ((r.options.reserved[0] >> 4) & 3) ? ((r.options.reserved[0] >> 4) & 3) : env_px;
+        if (forced == 1 || forced == 2) px = forced;
+    }
+    const int kTW = 32 * px, kFpW = kTW + 4;  // shadow the two-pixel constants below
     P.ntx = (tx + kTW - 1) / kTW, P.nty = (ty + kTH - 1) / kTH;
     const int ntiles = P.ntx * P.nty;
     // transposed axis order (p,q,s) in native axes
@@ -544,8 +560,8 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
     const int threads = kTmaThreads;
-    const void* kern_plain = tma_kernel(u.axis, clip, false);
-    const void* kern_slab = tma_kernel(u.axis, clip, true);
+    const void* kern_plain = tma_kernel(u.axis, clip, false, px);
+    const void* kern_slab = tma_kernel(u.axis, clip, true, px);
     for (const void* k : {kern_plain, kern_slab})
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) {
             cudaGetLastError();

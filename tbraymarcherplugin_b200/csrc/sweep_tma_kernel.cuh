@@ -77,13 +77,19 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 // full-depth inbox of LL cells (written by that band's launch: an earlier launch on this GPU, or the neighbour GPU's
 // concurrent launch through NVLink peer stores); the last slice of a slice sub-range is handed to the next slab as a
 // plane of LL cells. The per-voxel arithmetic is untouched, so a sharded pass is bit-identical to an unsharded one.
-template <int AXIS, bool CLIP, bool SLAB>
+//
+// PX = pixels per thread along p: 2 (tile 64 x 8, the two pixels share their middle tap column) or 1 (tile 32 x 8). A pass costs
+// slices x the per-slice instruction chain of ONE tile once its tiles no longer fill the SMs (256^3, the slab of a sharded volume):
+// one pixel per thread shortens that chain by the second pixel's work and doubles the tiles; the host picks it for such launches.
+template <int AXIS, bool CLIP, bool SLAB, int PX>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
                      const __grid_constant__ CUtensorMap scratch_map, const TmaParams P, const float4* __restrict__ tf) {
     constexpr int PA = (AXIS == 0) ? 1 : 0;  // native axis of p
     constexpr int QA = (AXIS == 2) ? 1 : 2;  // native axis of q
     constexpr int SA = AXIS;                 // native axis of s
+    constexpr int TW = 32 * PX, FPW = TW + 4;  // tile width, width of the SMEM footprint of the previous slice
+    static_assert(PX == 1 || PX == 2, "one or two pixels per thread");
     const SweepUniforms& U = P.U;
     const int tx = U.td[0], ty = U.td[1], ns = U.td[2];
     const int tid = threadIdx.x;
@@ -91,14 +97,14 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const int tile = tiy * P.ntx + tix;
     const int row_lo = SLAB ? P.S.tile_row0 : 0, row_hi = SLAB ? P.S.tile_row0 + P.S.tile_rows : P.nty;  // tile rows of this launch
     const int k_begin = SLAB ? P.S.k_begin : 0, k_end = SLAB ? P.S.k_end : ns;
-    const int x0 = tix * kTW, y0 = tiy * kTH;
+    const int x0 = tix * TW, y0 = tiy * kTH;
     const size_t plane = (size_t) tx * ty;
     const unsigned int plane32 = (unsigned int) (tx * ty);  // ring cells are indexed in 32 bits (the host checks kRingDepth * plane < 2^31)
 
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* stage_base = smem;
     float* s_fp = (float*) (smem + (size_t) kStages * P.stage_bytes);  // 2 x footprint (ping-pong over slices)
-    float* s_alpha = s_fp + 2 * kFpW * kFpH;
+    float* s_alpha = s_fp + 2 * FPW * kFpH;
     uint64_t* s_bar = (uint64_t*) (s_alpha + 256);
     __shared__ int s_down[kFusedMaxDeps];
     __shared__ int s_ndown;
@@ -115,8 +121,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             const int gy = j * kTH + P.bmin[1];
             if (gy + FH <= y0 || gy >= y0 + kTH) continue;
             for (int i = 0; i < P.ntx; ++i) {
-                const int gx = i * kTW + P.bmin[0];
-                if (gx + FW <= x0 || gx >= x0 + kTW) continue;
+                const int gx = i * TW + P.bmin[0];
+                if (gx + FW <= x0 || gx >= x0 + TW) continue;
                 if ((i != tix || j != tiy) && ndown < kFusedMaxDeps) s_down[ndown++] = j * P.ntx + i;
             }
         }
@@ -125,18 +131,18 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     s_alpha[tid] = __ldg(&tf[tid]).w;
     // footprint buffers: out-of-plane cells hold the sampler border colour for good, in-plane cells start as the
     // cleared buffer (LightAlpha) = "slice -1"
-    for (int c = tid; c < kFpW * kFpH; c += kTmaThreads) {
-        const int gx = fx0 + c % kFpW, gy = fy0 + c / kFpW;
+    for (int c = tid; c < FPW * kFpH; c += kTmaThreads) {
+        const int gx = fx0 + c % FPW, gy = fy0 + c / FPW;
         const bool in = (unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty;
         const float v = in ? U.a.light_alpha : U.a.border;
         s_fp[c] = v;
-        s_fp[kFpW * kFpH + c] = v;
+        s_fp[FPW * kFpH + c] = v;
     }
 
     // ---- per-thread invariants: 2 adjacent pixels (px, px+1) of row py --------------------------------------
-    const int lx = (tid & 31) * 2, ly = tid >> 5;
+    const int lx = (tid & 31) * PX, ly = tid >> 5;
     const int px = x0 + lx, py = y0 + ly;
-    const bool v0 = px < tx && py < ty, v1 = px + 1 < tx && py < ty;
+    const bool v0 = px < tx && py < ty, v1 = PX == 2 && px + 1 < tx && py < ty;  // PX == 1: every use of the second pixel folds away
     const int pxc = min(px, tx - 1), px1c = min(px + 1, tx - 1), pyc = min(py, ty - 1);
     const int2 mp0 = __ldg(&P.A.ax[PA].meta[pxc]), mp1 = __ldg(&P.A.ax[PA].meta[px1c]), mq = __ldg(&P.A.ax[QA].meta[pyc]);
     const float fp0 = __ldg(&P.A.ax[PA].f[pxc]), fp1 = __ldg(&P.A.ax[PA].f[px1c]), fq = __ldg(&P.A.ax[QA].f[pyc]);
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const int col = mp0.x - (x0 + P.dmin[0]);  // column of the first tap inside the data box
     const int rowq = mq.x - (y0 + P.dmin[1]);
     const bool inP0 = (unsigned) mp0.x < (unsigned) dN_p, inP1 = (unsigned) (mp0.x + 1) < (unsigned) dN_p,
-               inP2 = (unsigned) (mp0.x + 2) < (unsigned) dN_p;
+               inP2 = PX == 1 || (unsigned) (mp0.x + 2) < (unsigned) dN_p;  // the third tap column belongs to the second pixel
     const bool inQ0 = (unsigned) mq.x < (unsigned) dN_q, inQ1 = (unsigned) (mq.x + 1) < (unsigned) dN_q;
     const bool all_pq = inP0 && inP1 && inP2 && inQ0 && inQ1;
     // AddDirLight samples only where GetUVW + UVWOffset is inside [0,1]^3 (AddDirLightShader.usf:110); ChangeDirLight has no such
@@ -157,20 +163,20 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     }
     const int2 bxa = __ldg(&P.A.bx[pxc]), bxb = __ldg(&P.A.bx[px1c]), bya = __ldg(&P.A.by[pyc]);
     const float bfx0 = __int_as_float(bxa.y), bfx1 = __int_as_float(bxb.y), bfy = __int_as_float(bya.y);
-    const int tap_idx = (bya.x - fy0) * kFpW + (bxa.x - fx0);  // first of the 3 x 2 read-buffer taps
+    const int tap_idx = (bya.x - fy0) * FPW + (bxa.x - fx0);  // first of the 3 x 2 read-buffer taps
     // where this thread's own output lives in the footprint (if the footprint covers it)
     const bool own_in0 = v0 && px >= fx0 && px < fx0 + FW && py >= fy0 && py < fy0 + FH;
     const bool own_in1 = v1 && px + 1 >= fx0 && px + 1 < fx0 + FW && py >= fy0 && py < fy0 + FH;
-    const int own_idx = (py - fy0) * kFpW + (px - fx0);
+    const int own_idx = (py - fy0) * FPW + (px - fx0);
     const unsigned int own_cell = (unsigned int) (px + tx * py);  // this thread's first pixel in a ring slice (used where v0 / v1 hold)
     // is a pixel read by another tile? tile (i,j) reads [i*TW + bmin, +FW) x [j*TH + bmin, +FH)
     auto exported = [&](int gx, int gy) {
         const int rx = gx - P.bmin[0], ry = gy - P.bmin[1];  // tile origin i*TW must lie in (rx - FW, rx]
-        const int ia = max(0, (rx - FW + kTW) / kTW), ib = rx >= 0 ? min(P.ntx - 1, rx / kTW) : -1;
+        const int ia = max(0, (rx - FW + TW) / TW), ib = rx >= 0 ? min(P.ntx - 1, rx / TW) : -1;
         const int ja = max(row_lo, (ry - FH + kTH) / kTH), jb = ry >= 0 ? min(row_hi - 1, ry / kTH) : -1;
         for (int j = ja; j <= jb; ++j)
             for (int i = ia; i <= ib; ++i) {
-                const int gx0 = i * kTW + P.bmin[0], gy0 = j * kTH + P.bmin[1];
+                const int gx0 = i * TW + P.bmin[0], gy0 = j * kTH + P.bmin[1];
                 if ((i != tix || j != tiy) && gx >= gx0 && gx < gx0 + FW && gy >= gy0 && gy < gy0 + FH) return true;
             }
         return false;
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     __shared__ int s_over_fp[kHaloOverflow], s_over_ring[kHaloOverflow];
     int n_halo;  // footprint cells outside the own tile
     {
-        const int ox0 = max(fx0, x0), ox1 = min(fx0 + FW, x0 + kTW), oy0 = max(fy0, y0), oy1 = min(fy0 + FH, y0 + kTH);
+        const int ox0 = max(fx0, x0), ox1 = min(fx0 + FW, x0 + TW), oy0 = max(fy0, y0), oy1 = min(fy0 + FH, y0 + kTH);
         const int ow = max(0, ox1 - ox0), oh = (ow > 0) ? max(0, oy1 - oy0) : 0;
         const int top = (oh > 0 ? oy0 - fy0 : FH) * FW, mid = oh * (FW - ow);
         n_halo = FW * FH - ow * oh;
@@ -204,7 +210,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 if (gy >= fy0 + FH) gy = -1;
             }
             if ((unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty) {
-                fp_idx = (gy - fy0) * kFpW + (gx - fx0);
+                fp_idx = (gy - fy0) * FPW + (gx - fx0);
                 ring_idx = gy * tx + gx;
                 if (SLAB && (gy < P.S.q_lo || gy >= P.S.q_hi)) {  // owned by a neighbouring band: inbox row slot
                     const int slot = gy < P.S.q_lo ? gy - (P.S.q_lo - P.S.reach_lo) : P.S.reach_lo + gy - P.S.q_hi;
@@ -249,10 +255,10 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     };
     if (SLAB && k_begin > 0 && P.S.zin != nullptr) {
         // the slices before k_begin belong to the upstream slab: its last slice (tag k_begin) is our "slice k_begin - 1"
-        float* fp0 = s_fp + (k_begin & 1) * (kFpW * kFpH);
+        float* fp0 = s_fp + (k_begin & 1) * (FPW * kFpH);
         const unsigned int want = tag_base + (unsigned) k_begin;
-        for (int c = tid; c < kFpW * kFpH; c += kTmaThreads) {
-            const int gx = fx0 + c % kFpW, gy = fy0 + c / kFpW;
+        for (int c = tid; c < FPW * kFpH; c += kTmaThreads) {
+            const int gx = fx0 + c % FPW, gy = fy0 + c / FPW;
             if ((unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty) {
                 const unsigned long long* cell = P.S.zin + (size_t) gy * tx + gx;
                 unsigned long long v = ld_relaxed_sys_u64(cell);
@@ -309,9 +315,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             const int loop = s0 + (U.dirn > 0 ? sl : kSB - 1 - sl);
             if (loop >= ns) continue;
             const int k = U.dirn > 0 ? loop : ns - 1 - loop;  // position in sweep order
-            const int fp_par = (k & 1) * (kFpW * kFpH);
+            const int fp_par = (k & 1) * (FPW * kFpH);
             float* fp_cur = s_fp + fp_par;
-            float* fp_next = s_fp + (kFpW * kFpH - fp_par);
+            float* fp_next = s_fp + (FPW * kFpH - fp_par);
             // ---- (a) issue the halo loads of slice k-1 (and, every 4th slice, the back-pressure probes) ----
             const unsigned int want_tag = tag_base + (unsigned) k;  // slice k-1 carries tag k
             const unsigned int rd_slot = (((unsigned int) k + kRingDepth - 1u) % kRingDepth) * plane32;  // first cell of slice k-1 in the ring
@@ -384,13 +390,14 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 // lies between its smallest and largest tap and the window position is monotone in the value, so if no tap
                 // exceeds T both samples are rejected and return exactly 0 (WindowedSampling.usf:28). Carries only travel upward, so the
                 // stray byte 3 cannot disturb the three tap bytes, and the final mask drops its own flag.
+                constexpr uint32_t kTapFlags = PX == 2 ? 0x00808080u : 0x00008080u;  // the flag bits of the tap bytes in use
                 uint32_t any_gt = 1u;
                 if (P.cut_lo_mode == 1)
                     any_gt = (((wq[0][0] + P.cut_lo_add) | wq[0][0]) | ((wq[0][1] + P.cut_lo_add) | wq[0][1]) |
-                              ((wq[1][0] + P.cut_lo_add) | wq[1][0]) | ((wq[1][1] + P.cut_lo_add) | wq[1][1])) & 0x00808080u;
+                              ((wq[1][0] + P.cut_lo_add) | wq[1][0]) | ((wq[1][1] + P.cut_lo_add) | wq[1][1])) & kTapFlags;
                 else if (P.cut_lo_mode == 2)
                     any_gt = ((((wq[0][0] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[0][0]) | (((wq[0][1] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[0][1]) |
-                              (((wq[1][0] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[1][0]) | (((wq[1][1] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[1][1])) & 0x00808080u;
+                              (((wq[1][0] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[1][0]) | (((wq[1][1] & 0x7f7f7f7fu) + P.cut_lo_add) & wq[1][1])) & kTapFlags;
                 if (!(all_in && any_gt == 0u)) {
 #pragma unroll
                     for (int js = 0; js < 2; ++js)
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                         }
                     if (!all_in) {  // cold (volume faces only): the per-tap bounds are recomputed here rather than kept live through the loop
                         const bool ip[3] = {(unsigned) mp0.x < (unsigned) dN_p, (unsigned) (mp0.x + 1) < (unsigned) dN_p,
-                                            (unsigned) (mp0.x + 2) < (unsigned) dN_p};
+                                            PX == 1 || (unsigned) (mp0.x + 2) < (unsigned) dN_p};
                         const bool iq[2] = {(unsigned) mq.x < (unsigned) dN_q, (unsigned) (mq.x + 1) < (unsigned) dN_q};
                         const bool is[2] = {(unsigned) ms.x < (unsigned) dN_s, (unsigned) (ms.x + 1) < (unsigned) dN_s};
 #pragma unroll
@@ -484,7 +491,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             // ---- (d) propagate, export, accumulate into the light brick ----
             {
                 const float* r0 = fp_cur + tap_idx;
-                const float* r1 = r0 + kFpW;
+                const float* r1 = r0 + FPW;
                 const float t00 = r0[0], t10 = r0[1], t20 = r0[2], t01 = r1[0], t11 = r1[1], t21 = r1[2];
                 const float prev0 = lerpf(lerpf(t00, t10, bfx0), lerpf(t01, t11, bfx0), bfy);
                 const float prev1 = lerpf(lerpf(t10, t20, bfx1), lerpf(t11, t21, bfx1), bfy);
@@ -512,15 +519,15 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 float* lp = s_light + light_off + (loop - s0) * P.ls_s;
                 if (P.mode == kModeAdd) {  // AddDirLightShader.usf:121-126
                     if (fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
-                    if (fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
+                    if (PX == 2 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
                 } else if (P.mode == kModeStore) {  // the removed light of a ChangeDirLight: its light goes to the scratch volume
                     lp[0] = cur0;
-                    lp[P.ls_p] = cur1;
+                    if (PX == 2) lp[P.ls_p] = cur1;
                 } else {  // the added light of a ChangeDirLight: LightVolume += added - removed (ChangeDirLightShader.usf:146-153)
                     const float* rp = lp + P.light_bytes / 4;
-                    const float r0c = rp[0], r1c = rp[P.ls_p];
+                    const float r0c = rp[0], r1c = PX == 2 ? rp[P.ls_p] : 0.0f;
                     if (fabsf(cur0 - r0c) > 1e-3f) lp[0] = lp[0] + cur0 - r0c;
-                    if (fabsf(cur1 - r1c) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + cur1 - r1c;
+                    if (PX == 2 && fabsf(cur1 - r1c) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + cur1 - r1c;
                 }
             }
         }

@@ -266,3 +266,33 @@ def test_lit_march_with_64_bit_tap_addressing_still_matches_oracle(dims):
             rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 33.0)
             assert steps == ref_steps and np.array_equal(rgba, ref), (dims, flag)
         res.release()
+
+
+@pytest.mark.parametrize("px_flag", [16, 32])  # bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread in sweep_tma_kernel
+@pytest.mark.parametrize("dims", [(64, 48, 40), (80, 24, 16), (128, 16, 8)])
+def test_tma_sweep_with_one_and_two_pixels_per_thread(dims, px_flag):
+    """The TMA-staged sweep picks one pixel per thread (tile 32 x 8) for launches that cannot fill the SMs and two (tile 64 x 8) otherwise;
+    both forced here on the same volumes, incl. planes that end inside a tile: AddDirLight (oblique and axis-aligned lights),
+    ChangeDirLight, with and without a clip plane — bit-exact against the oracle."""
+    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats
+
+    data = np.random.default_rng(sum(dims)).integers(0, 256, dims[::-1]).astype(np.uint8)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    used = set()
+    for world in (synth.identity_world(), synth.clipped_world()):
+        res = make_res(data, win)
+        URaymarchUtils.SetOptions(res, sweep_impl=2, debug_flags=(px_flag, 0))
+        vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        for l in synth.LIGHTS + [FDirLightParameters((1, 0, 0), 0.7), FDirLightParameters((0, -1, 0), 0.3)]:
+            st = FSweepStats()
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
+            vol.add_dir_light(l, True, world)
+            used |= set(st.impl)
+        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), (dims, px_flag)
+        n = synth.rotate_about_z(synth.LIGHTS[0], 20.0)
+        assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], n, world, bGPUSync=True)
+        vol.change_dir_light(synth.LIGHTS[0], n, world)
+        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), (dims, px_flag)
+        res.release()
+    assert 3 in used  # the TMA-staged sweep took passes
