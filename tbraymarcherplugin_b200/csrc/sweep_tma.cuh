@@ -470,19 +470,26 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     TmaParams P;
     memset(&P, 0, sizeof(P));
     P.U = u;
-    // pixels per thread: two (tile 64 x 8) while the launch has enough tiles to fill the SMs, one (tile 32 x 8) below that — there a pass
-    // costs slices x one tile's per-slice chain, which one pixel per thread shortens (bits 4-5 of reserved[0]: 1 / 2 force the choice)
+    // pixels per thread: two (tile 64 x 8), or one (tile 32 x 8) for launches that cannot fill the SMs — there a pass costs slices x one
+    // tile's per-slice chain, which one pixel per thread shortens. The one-pixel form has not run on a GPU yet (round 1's GPU budget was
+    // spent): it is opt-in until it has — TBRM_SWEEP_PX=auto (or bits 4-5 of reserved[0] = 3) enables the choice below, 1 / 2 force a form.
     int px = 2;
     {
-        const int rows = (r.slab.nranks > 1 && u.axis != 2) ? r.slab.z_end - r.slab.z_begin : ty;  // buffer rows this GPU sweeps
-        const long long tiles64 = (long long) ((tx + 63) / 64) * ((rows + kTH - 1) / kTH);
-        // round 1's numbers: a tile alone on an SM needs L = 3 400 cycles per slice, an SM with 4 resident tiles 4 875 (T = 1 220 per tile and
-        // slice); one pixel per thread scales both by 446 / 611 (SASS of the slice loop) and doubles the tiles, so it wins while the
-        // doubled tiles still fit three to an SM: max(0.73 L, ceil(2 t / SMs) * 0.73 T) < max(L, ceil(t / SMs) * T)
-        if (2 * tiles64 <= 3ll * sms) px = 1;
-        static const int env_px = [] { const char* e = getenv("TBRM_SWEEP_PX"); return e ? atoi(e) : 0; }();  // A/B timing, tests
-        const int forced = ((r.options.reserved[0] >> 4) & 3) ? ((r.options.reserved[0] >> 4) & 3) : env_px;
-        if (forced == 1 || forced == 2) px = forced;
+        static const int env_px = [] {  // 0 unset, 1 / 2 forced, 3 automatic
+            const char* e = getenv("TBRM_SWEEP_PX");
+            return !e ? 0 : (e[0] == 'a' ? 3 : atoi(e));
+        }();
+        const int opt = (r.options.reserved[0] >> 4) & 3;
+        const int want = opt ? opt : env_px;
+        if (want == 1 || want == 2) px = want;
+        if (want == 3) {
+            const int rows = (r.slab.nranks > 1 && u.axis != 2) ? r.slab.z_end - r.slab.z_begin : ty;  // buffer rows this GPU sweeps
+            const long long tiles64 = (long long) ((tx + 63) / 64) * ((rows + kTH - 1) / kTH);
+            // round 1's numbers: a tile alone on an SM needs L = 3 400 cycles per slice, an SM with 4 resident tiles 4 875 (T = 1 220 per tile
+            // and slice); one pixel per thread scales both by 446 / 611 (SASS of the slice loop) and doubles the tiles, so it wins while the
+            // doubled tiles still fit three to an SM: max(0.73 L, ceil(2 t / SMs) * 0.73 T) < max(L, ceil(t / SMs) * T)
+            px = (2 * tiles64 <= 3ll * sms) ? 1 : 2;
+        }
     }
     const int kTW = 32 * px, kFpW = kTW + 4;  // shadow the two-pixel constants below
     P.ntx = (tx + kTW - 1) / kTW, P.nty = (ty + kTH - 1) / kTH;

@@ -80,12 +80,12 @@ def test_emulated_loader_and_ingest_kernels(emulated, tmp_path):
     M.test_headerless_raw_file_loads_like_the_mhd_path(tmp_path)
 
 
-@pytest.mark.parametrize("dims,nranks", [((64, 48, 64), 4), ((64, 64, 96), 3), ((64, 64, 64), 8)])
-def test_emulated_concurrent_slabs_equal_the_unsharded_sweep(emulated, dims, nranks):
+@pytest.mark.parametrize("dims,nranks,px_flag", [((64, 48, 64), 4, 0), ((64, 48, 64), 4, 48), ((64, 64, 96), 3, 0), ((64, 64, 64), 8, 48)])
+def test_emulated_concurrent_slabs_equal_the_unsharded_sweep(emulated, dims, nranks, px_flag):
     """Z-slab sharding with the ranks running CONCURRENTLY, one thread per virtual rank — what N GPUs do, and what one GPU
     cannot (co-resident cooperative kernels of several ranks would starve each other): every rank issues its passes on its own and waits for its neighbours in the kernels, middle ranks have two neighbours, a
     rank may run a pass ahead of its neighbour (the ack protocol keeps it from overwriting exchange cells), slabs are swept in both orders;
-    AddDirLight and its removal."""
+    AddDirLight and its removal; with two pixels per thread and with the automatic choice (one pixel per thread for slabs this small)."""
     import ctypes as C
     import threading
 
@@ -104,6 +104,8 @@ def test_emulated_concurrent_slabs_equal_the_unsharded_sweep(emulated, dims, nra
         assert set(st.impl) == {3}
     ref = URaymarchUtils.ReadLightVolume(ref_res)
     ranks = S.virtual_ranks(data, nranks)
+    for res, _, _ in ranks:  # px_flag 48: the automatic choice of pixels per thread (one, at these sizes); 0: two
+        URaymarchUtils.SetOptions(res, sweep_impl=2, debug_flags=(px_flag, 0, 0))
     orders = set()
     for l in lights:
         for p in (0, 1):
@@ -166,7 +168,7 @@ def test_emulated_lit_march_in_both_addressing_forms(emulated):
     M.test_lit_march_with_64_bit_tap_addressing_still_matches_oracle((1, 7, 1))
 
 
-@pytest.mark.parametrize("px_flag", [16, 32])
+@pytest.mark.parametrize("px_flag", [16, 32, 48])
 def test_emulated_tma_sweep_with_one_and_two_pixels_per_thread(emulated, px_flag):
     M.test_tma_sweep_with_one_and_two_pixels_per_thread((80, 24, 16), px_flag)
     M.test_tma_sweep_with_one_and_two_pixels_per_thread((64, 48, 40), px_flag)

@@ -268,11 +268,11 @@ def test_lit_march_with_64_bit_tap_addressing_still_matches_oracle(dims):
         res.release()
 
 
-@pytest.mark.parametrize("px_flag", [16, 32])  # bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread in sweep_tma_kernel
+@pytest.mark.parametrize("px_flag", [16, 32, 48])  # bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread in sweep_tma_kernel, automatic
 @pytest.mark.parametrize("dims", [(64, 48, 40), (80, 24, 16), (128, 16, 8)])
 def test_tma_sweep_with_one_and_two_pixels_per_thread(dims, px_flag):
-    """The TMA-staged sweep picks one pixel per thread (tile 32 x 8) for launches that cannot fill the SMs and two (tile 64 x 8) otherwise;
-    both forced here on the same volumes, incl. planes that end inside a tile: AddDirLight (oblique and axis-aligned lights),
+    """The TMA-staged sweep has a one-pixel-per-thread form (tile 32 x 8) for launches that cannot fill the SMs next to the two-pixel form
+    (tile 64 x 8; the default until the other has run on a GPU); both forced here on the same volumes, and the automatic choice, incl. planes that end inside a tile: AddDirLight (oblique and axis-aligned lights),
     ChangeDirLight, with and without a clip plane — bit-exact against the oracle."""
     from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats
 
