@@ -171,6 +171,7 @@ struct MaterialUniforms {
     const uint16_t* mip;  // octree march: the mip that is sampled
     int mdims[3];         // its dimensions
     float octree_depth0;  // OctreeDepthConst: depth of octree mip 0
+    float rwidth;         // RN(1 / window width), for the division-free window position (div_exact)
 };
 
 struct PixelMarch {
@@ -252,16 +253,25 @@ __global__ void __launch_bounds__(256) raymarch_intensity_kernel(const MarchUnif
 }
 
 // one sample of PerformWindowedRaymarchOctree: point Load from the octree mip -> windowed TF -> AccumulateLightEnergy (no light volume)
+// v / 65535 for v in 0..65535 without a division: with 1/65535 = c_hi + c_lo (c_hi = RN(1/65535)), fma(v, c_hi, v * c_lo) == RN(v / 65535)
+// for every 16-bit value (exhaustive check in tests/test_host_cpu.py), like decode_u8_exact
+__device__ __forceinline__ float decode_u16_exact(uint32_t v) {
+    const float x = (float) v;
+    return __fmaf_rn(x, 1.5259021893143654e-05f, x * 3.5527678889091252e-15f);
+}
+
 __device__ __forceinline__ void octree_sample(const MaterialUniforms& F, const float4* s_tf, V3 p, float step, float ow, float oh, float od, float dd,
                                               float4& acc) {
     // int3 VoxelPos = float3(CurPos.x * OctreeWidth, CurPos.y * OctreeHeight, (CurPos.z * DataVolumeDepth / OctreeDepthConst) * OctreeDepth) — :148
     const int vx = (int) (p.x * ow), vy = (int) (p.y * oh), vz = (int) (((p.z * dd) / F.octree_depth0) * od);
     float v = 0.0f;  // Texture3D.Load out of bounds returns 0
     if ((unsigned) vx < (unsigned) F.mdims[0] && (unsigned) vy < (unsigned) F.mdims[1] && (unsigned) vz < (unsigned) F.mdims[2])
-        v = (float) __ldg(F.mip + (size_t) vx + (size_t) F.mdims[0] * ((size_t) vy + (size_t) F.mdims[1] * vz)) / 65535.0f;
-    float pos;
+        v = decode_u16_exact(__ldg(F.mip + (size_t) vx + (size_t) F.mdims[0] * ((size_t) vy + (size_t) F.mdims[1] * vz)));
+    // GetTransferFuncPosition + cut-offs (tf_position) with the lit march's correctly rounded division-free quotient
+    const Windowing& w = F.M.win;
+    const float pos = div_exact(v - w.center + (w.width / 2.0f), w.width, F.rwidth);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tf_position(v, F.M.win, pos)) {
+    if (!((pos < 0.0f && w.low > 0.0f) || (pos > 1.0f && w.high > 0.0f))) {
         int i0, i1;
         float f;
         tf_taps(pos, i0, i1, f);
@@ -399,6 +409,7 @@ cudaError_t raymarch_octree(tbrm_resources& r, const host::CameraUniforms& cam, 
     int32_t d0[3];
     octree_mip_dims(r, 0, d0);
     F.octree_depth0 = (float) d0[2];
+    F.rwidth = 1.0f / F.M.win.width;
     int32_t dm[3];
     octree_mip_dims(r, octree_mip, dm);  // 0 <= octree_mip < 4: checked by the C entry point
     for (int k = 0; k < 3; ++k) F.mdims[k] = dm[k];

@@ -223,6 +223,10 @@ def test_exact_division_free_sequences():
     c_hi, c_lo = np.float32(0.003921568859368563), np.float32(-2.319175823606301e-10)
     got = (v.astype(np.float64) * float(c_hi) + (v * c_lo).astype(np.float64)).astype(np.float32)  # fma: exact product, one rounding
     assert np.array_equal(got, v / np.float32(255.0))
+    v = np.arange(65536, dtype=np.float32)  # UNORM16 texels of the octree march (decode_u16_exact, csrc/materials.cuh)
+    c_hi, c_lo = np.float32(1.5259021893143654e-05), np.float32(3.5527678889091252e-15)
+    got = (v.astype(np.float64) * float(c_hi) + (v * c_lo).astype(np.float64)).astype(np.float32)
+    assert np.array_equal(got, v / np.float32(65535.0))
     rng = np.random.default_rng(3)
     for w in (0.5, 1.0, 0.4, 0.3, 0.9, 1.7):
         w32 = np.float32(w)
