@@ -6,6 +6,7 @@
 // URaymarchUtils::MakeDefaultTFTexture / ClearResourceLightVolumes / AddDirLightToSingleVolume / GenerateOctree, and the Custom nodes of
 // M_Raymarch / M_Intensity_Raymarch / M_Octree_Raymarch.
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "include/tbrm.h"
@@ -21,7 +22,7 @@
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        std::fprintf(stderr, "usage: %s volume.mhd\n", argv[0]);
+        std::fprintf(stderr, "usage: %s volume.mhd [width height steps]   (default 1280 720 256)\n", argv[0]);
         return 2;
     }
     tbrm_volume_info info;
@@ -54,15 +55,16 @@ int main(int argc, char** argv) {
     cam.eye[0] = -0.9, cam.eye[1] = -0.5, cam.eye[2] = 0.7;  // the unit cube sits at the origin, [-0.5, 0.5]^3
     cam.up[2] = 1.0;
     cam.hfov_deg = 60.0;
-    cam.width = 1280, cam.height = 720;
+    cam.width = argc > 3 ? std::atoi(argv[2]) : 1280, cam.height = argc > 3 ? std::atoi(argv[3]) : 720;
+    const float march_steps = argc > 4 ? (float) std::atof(argv[4]) : 256.0f;
     cam.jitter = 1;
     std::vector<float> frame((size_t) cam.width * cam.height * 4);
     uint64_t steps = 0;
-    CHECK(tbrm_raymarch_lit(res, &cam, &world, 256.0f, 0, cam.height, frame.data(), 0, &steps));
+    CHECK(tbrm_raymarch_lit(res, &cam, &world, march_steps, 0, cam.height, frame.data(), 0, &steps));
     std::printf("lit march:       %llu ray-steps\n", (unsigned long long) steps);
-    CHECK(tbrm_raymarch_intensity(res, &cam, &world, 256.0f, 0, cam.height, frame.data(), 0, &steps));
+    CHECK(tbrm_raymarch_intensity(res, &cam, &world, march_steps, 0, cam.height, frame.data(), 0, &steps));
     std::printf("intensity march: %llu ray-steps\n", (unsigned long long) steps);
-    CHECK(tbrm_raymarch_octree(res, &cam, &world, 256.0f, /*OctreeVolumeMip*/ 1, 0, cam.height, frame.data(), 0, &steps));
+    CHECK(tbrm_raymarch_octree(res, &cam, &world, march_steps, /*OctreeVolumeMip*/ 1, 0, cam.height, frame.data(), 0, &steps));
     std::printf("octree march:    %llu ray-steps\n", (unsigned long long) steps);
     CHECK(tbrm_flush(res));
     CHECK(tbrm_destroy(res));

@@ -98,13 +98,15 @@ def test_gpu_entry_points_validate_and_fail_loudly_without_a_device():
     assert lib.tbrm_mandelbulb_sdf(0, d, c, 2.0, 8.0, 1, buf.ctypes.data_as(C.c_void_p), 0, None) == _capi.TBRM_ERR_NO_DEVICE
 
 
-def _build_example(tmp_path):
+def _build_example(tmp_path, libdir=None, libname="tbrm"):
+    """examples/mhd_to_frame.cpp against libtbrm.so — or, for tests/test_kernels_emulated_cpu.py, against the emulated build of the same ABI"""
     import subprocess
 
     root = Path(__file__).resolve().parents[1]
+    libdir = libdir or root / "tbraymarcherplugin_b200"
     exe = tmp_path / "mhd_to_frame"
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I", str(root), str(root / "examples" / "mhd_to_frame.cpp"),
-                    "-L", str(root / "tbraymarcherplugin_b200"), "-ltbrm", f"-Wl,-rpath,{root / 'tbraymarcherplugin_b200'}", "-o", str(exe)], check=True)
+                    "-L", str(libdir), f"-l{libname}", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
     return exe
 
 

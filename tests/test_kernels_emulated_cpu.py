@@ -172,3 +172,10 @@ def test_emulated_lit_march_in_both_addressing_forms(emulated):
 def test_emulated_tma_sweep_with_one_and_two_pixels_per_thread(emulated, px_flag):
     M.test_tma_sweep_with_one_and_two_pixels_per_thread((80, 24, 16), px_flag)
     M.test_tma_sweep_with_one_and_two_pixels_per_thread((64, 48, 40), px_flag)
+
+
+def test_emulated_cpp_example_end_to_end(emulated, tmp_path):
+    """examples/mhd_to_frame.cpp linked against the emulated build of the C ABI: file -> resources -> sweep -> octree -> three materials, from C++"""
+    from pathlib import Path
+
+    M.test_cpp_example_runs_end_to_end(tmp_path, Path(emulated._name).parent, "tbrm_emu", view=("96", "54", "40"))

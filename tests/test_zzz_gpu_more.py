@@ -136,7 +136,7 @@ def test_joined_same_axis_sweeps_match_their_cpu_twin(dims, light32):
         res.release()
 
 
-def test_cpp_example_runs_end_to_end(tmp_path):
+def test_cpp_example_runs_end_to_end(tmp_path, libdir=None, libname="tbrm", view=()):
     """examples/mhd_to_frame.cpp (plain C++ over the C ABI): MetaImage file -> resources -> sweep -> octree -> the three materials."""
     import subprocess
 
@@ -146,7 +146,7 @@ def test_cpp_example_runs_end_to_end(tmp_path):
     raw = (synth.perlin_ct_volume(dims).astype(np.int16) * 12 - 1000)
     (tmp_path / "v.raw").write_bytes(raw.tobytes())
     (tmp_path / "v.mhd").write_text(f"NDims = 3\nDimSize = {dims[0]} {dims[1]} {dims[2]}\nElementSpacing = 1 1 1\nElementType = MET_SHORT\nElementDataFile = v.raw\n")
-    out = subprocess.run([str(_build_example(tmp_path)), str(tmp_path / "v.mhd")], capture_output=True, text=True)
+    out = subprocess.run([str(_build_example(tmp_path, libdir, libname)), str(tmp_path / "v.mhd"), *view], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert "48 x 40 x 32 voxels" in out.stdout and "normalised to G16" in out.stdout
     steps = [int(l.split(":")[1].split()[0]) for l in out.stdout.splitlines() if "march:" in l]
