@@ -179,3 +179,11 @@ def test_emulated_cpp_example_end_to_end(emulated, tmp_path):
     from pathlib import Path
 
     M.test_cpp_example_runs_end_to_end(tmp_path, Path(emulated._name).parent, "tbrm_emu", view=("96", "54", "40"))
+
+
+def test_emulated_cpp_actor_mirror_end_to_end(emulated, tmp_path):
+    """the C++ host mirror (ARaymarchVolume::Tick over URaymarchUtils over the C ABI) against the emulated build: reset, incremental
+    ChangeDirLight and a lit frame from C++, bit-identical to the oracle"""
+    from pathlib import Path
+
+    M.test_cpp_actor_mirror_end_to_end(tmp_path, Path(emulated._name).parent, "tbrm_emu")

@@ -296,3 +296,102 @@ def test_tma_sweep_with_one_and_two_pixels_per_thread(dims, px_flag):
         assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), (dims, px_flag)
         res.release()
     assert 3 in used  # the TMA-staged sweep took passes
+
+
+CPP_ACTOR_PROGRAM = r'''
+#include <array>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <vector>
+#include "tbraymarcherplugin_b200/csrc/RaymarchVolume.hpp"
+using namespace tbrm_ue;
+template <typename T>
+static std::vector<T> slurp(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    std::vector<char> b((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    return std::vector<T>((const T*) b.data(), (const T*) (b.data() + b.size()));
+}
+template <typename T>
+static void dump(const std::string& path, const std::vector<T>& v) {
+    std::ofstream(path, std::ios::binary).write((const char*) v.data(), (std::streamsize) (v.size() * sizeof(T)));
+}
+#define CHECK(c) do { if (!(c)) { std::printf("failed: %s (line %d): %s\n", #c, __LINE__, tbrm_last_error()); return 1; } } while (0)
+int main(int argc, char** argv) {
+    const std::string dir = argv[1];
+    const int32_t dims[3] = {std::atoi(argv[2]), std::atoi(argv[3]), std::atoi(argv[4])};
+    const std::vector<uint8_t> data = slurp<uint8_t>(dir + "/data.raw");
+    const std::vector<float> curve = slurp<float>(dir + "/curve.raw");
+    const std::vector<double> lights = slurp<double>(dir + "/lights.raw");  // 3 lights x (direction, intensity): two initial, one moved
+    const std::vector<tbrm_camera> cam = slurp<tbrm_camera>(dir + "/camera.raw");
+    CHECK(data.size() == (size_t) dims[0] * dims[1] * dims[2] && curve.size() == 1024 && lights.size() == 12 && cam.size() == 1);
+    ARaymarchVolume<> vol;  // the real operator surface: URaymarchUtils over the C ABI
+    vol.RaymarchResources.WindowingParameters = FWindowingParameters{0.45f, 0.5f, true, false};
+    CHECK(URaymarchUtils::InitializeRaymarchResources(vol.RaymarchResources, dims, TBRM_FMT_G8, data.data(), /*bLightVolume32Bit*/ true));
+    std::array<float, 1024> c;
+    for (int i = 0; i < 1024; ++i) c[i] = curve[i];
+    URaymarchUtils::ColorCurveToTexture(c, vol.RaymarchResources);
+    ARaymarchLight L[2];
+    for (int i = 0; i < 2; ++i) L[i].ForwardVector = FVector(lights[4 * i], lights[4 * i + 1], lights[4 * i + 2]), L[i].LightIntensity = (float) lights[4 * i + 3];
+    vol.LightsArray = {&L[0], &L[1]};
+    vol.OnConstruction();
+    vol.bRequestedRecompute = true;
+    CHECK(vol.Tick().action == FTickReport::Reset);
+    std::vector<float> light((size_t) dims[0] * dims[1] * dims[2]);
+    CHECK(tbrm_download_light_volume(vol.RaymarchResources.Handle, light.data()) == TBRM_OK);
+    dump(dir + "/light_reset.raw", light);
+    vol.LightParametersMap[&L[0]] = L[0].GetCurrentParameters();  // what the reset used (the reference leaves the map stale)
+    vol.LightParametersMap[&L[1]] = L[1].GetCurrentParameters();
+    L[0].ForwardVector = FVector(lights[8], lights[9], lights[10]);
+    const FTickReport rep = vol.Tick();
+    CHECK(rep.action == FTickReport::Incremental && rep.lights_updated == 1 && rep.errors.empty());
+    CHECK(tbrm_download_light_volume(vol.RaymarchResources.Handle, light.data()) == TBRM_OK);
+    dump(dir + "/light_changed.raw", light);
+    std::vector<float> frame((size_t) cam[0].width * cam[0].height * 4);
+    uint64_t steps = 0;
+    CHECK(URaymarchUtils::PerformWindowedLitRaymarch(vol.RaymarchResources, cam[0], vol.WorldParameters, 40.0f, frame.data(), &steps));
+    dump(dir + "/frame.raw", frame);
+    std::printf("steps %llu\n", (unsigned long long) steps);
+    URaymarchUtils::FreeRaymarchResources(vol.RaymarchResources);
+    return 0;
+}
+'''
+
+
+def test_cpp_actor_mirror_end_to_end(tmp_path, libdir=None, libname="tbrm"):
+    """csrc/RaymarchVolume.hpp + csrc/RaymarchUtils.hpp (the C++ host mirror of ARaymarchVolume / URaymarchUtils) driving the C ABI for real:
+    resources from a host volume, a full reset and an incremental ChangeDirLight decided by Tick, a lit frame — all three bit-identical to
+    the oracle."""
+    import ctypes as C
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    libdir = libdir or root / "tbraymarcherplugin_b200"
+    dims = (48, 32, 24)
+    data = synth.perlin_ct_volume(dims)
+    data.tofile(tmp_path / "data.raw")
+    synth.soft_ct_curve().astype(np.float32).tofile(tmp_path / "curve.raw")
+    moved = synth.rotate_about_z(synth.LIGHTS[0], 5.0)
+    lights = [synth.LIGHTS[0], synth.LIGHTS[1], moved]
+    np.array([[*l.LightDirection, l.LightIntensity] for l in lights], np.float64).tofile(tmp_path / "lights.raw")
+    cam = synth.benchmark_camera(48, 32, jitter=True, frame=1)
+    (tmp_path / "camera.raw").write_bytes(bytes(cam.to_c()))
+    (tmp_path / "p.cpp").write_text(CPP_ACTOR_PROGRAM)
+    exe = tmp_path / "p"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-I", str(root), str(tmp_path / "p.cpp"), "-L", str(libdir), f"-l{libname}",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(tmp_path), *map(str, dims)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    world = synth.identity_world()
+    vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win)
+    for l in lights[:2]:
+        vol.add_dir_light(l, True, world)
+    shape = dims[::-1]
+    assert np.array_equal(np.fromfile(tmp_path / "light_reset.raw", np.float32).reshape(shape), vol.light)
+    vol.change_dir_light(lights[0], moved, world)
+    assert np.array_equal(np.fromfile(tmp_path / "light_changed.raw", np.float32).reshape(shape), vol.light)
+    ref, ref_steps = vol.raymarch_lit(cam, world, 40.0)
+    assert np.array_equal(np.fromfile(tmp_path / "frame.raw", np.float32).reshape(ref.shape), ref)
+    assert int(out.stdout.split("steps")[1]) == ref_steps
