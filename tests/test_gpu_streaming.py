@@ -24,37 +24,52 @@ def step(res, world):
         assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True)
 
 
-def test_streaming_frames_equal_synchronous_frames():
-    import torch
-
-    dims = (64, 64, 64)
+def run_streaming(pin_volume, new_frame, dims=(64, 64, 64), view=(160, 96), steps=128.0):
+    """pin_volume(ndarray) -> host buffer the upload reads, new_frame(shape) -> host buffer a frame lands in (pinned memory on a GPU)"""
     base = synth.perlin_ct_volume(dims)
     volumes = [np.ascontiguousarray(np.roll(base, 7 * k, axis=k % 3)) for k in range(5)]
     world = synth.identity_world()
-    cam = synth.benchmark_camera(160, 96)
+    cam = synth.benchmark_camera(*view)
     # synchronous reference
     ref = make_res(dims)
     want = []
     for v in volumes:
         URaymarchUtils.SetDataVolume(ref, v)
         step(ref, world)
-        want.append(URaymarchUtils.PerformWindowedLitRaymarch(ref, cam, world, 128.0)[0])
+        want.append(URaymarchUtils.PerformWindowedLitRaymarch(ref, cam, world, steps)[0])
     assert not np.array_equal(want[0], want[1])
     # streaming: volume k+1 uploads while frame k is computed, frames download behind the next step
     res = make_res(dims)
-    pinned = [torch.from_numpy(v).pin_memory() for v in volumes]
-    frames = [torch.empty((cam.Height, cam.Width, 4), dtype=torch.float32).pin_memory() for _ in volumes]
-    URaymarchUtils.SetDataVolumeAsync(res, pinned[0].numpy())
+    pinned = [pin_volume(v) for v in volumes]
+    frames = [new_frame((cam.Height, cam.Width, 4)) for _ in volumes]
+    URaymarchUtils.SetDataVolumeAsync(res, pinned[0])
     for k in range(len(volumes)):
         URaymarchUtils.PresentDataVolume(res)
         if k + 1 < len(volumes):
-            URaymarchUtils.SetDataVolumeAsync(res, pinned[k + 1].numpy())
+            URaymarchUtils.SetDataVolumeAsync(res, pinned[k + 1])
         step(res, world)
-        URaymarchUtils.PerformWindowedLitRaymarchAsync(res, cam, world, 128.0, out=frames[k].numpy())
+        URaymarchUtils.PerformWindowedLitRaymarchAsync(res, cam, world, steps, out=frames[k])
     URaymarchUtils.WaitForDownloads(res)
     URaymarchUtils.FlushRenderingCommands(res)
     for k in range(len(volumes)):
-        assert np.array_equal(frames[k].numpy(), want[k]), f"frame {k}"
+        assert np.array_equal(frames[k], want[k]), f"frame {k}"
     # presenting without a pending upload is an error, not a silent reuse
     with pytest.raises(Exception):
         URaymarchUtils.PresentDataVolume(res)
+    ref.release(), res.release()
+
+
+def test_streaming_frames_equal_synchronous_frames():
+    import torch
+
+    keep = []  # the tensors own the pinned memory their numpy views point into
+
+    def pin(v):
+        keep.append(torch.from_numpy(v).pin_memory())
+        return keep[-1].numpy()
+
+    def frame(shape):
+        keep.append(torch.empty(shape, dtype=torch.float32).pin_memory())
+        return keep[-1].numpy()
+
+    run_streaming(pin, frame)

@@ -187,3 +187,11 @@ def test_emulated_cpp_actor_mirror_end_to_end(emulated, tmp_path):
     from pathlib import Path
 
     M.test_cpp_actor_mirror_end_to_end(tmp_path, Path(emulated._name).parent, "tbrm_emu")
+
+
+def test_emulated_streaming_entry_points(emulated):
+    """double-buffered upload / present / asynchronous frame download (tests/test_gpu_streaming.py) with plain host buffers: the state
+    machine of the streaming API gives, frame by frame, what the synchronous calls give"""
+    import test_gpu_streaming as T
+
+    T.run_streaming(lambda v: v, lambda shape: np.empty(shape, np.float32), dims=(32, 32, 32), view=(48, 32), steps=40.0)
