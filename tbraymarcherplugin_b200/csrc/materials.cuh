@@ -22,6 +22,12 @@ struct OctreeUniforms {
 
 __device__ __forceinline__ unsigned int quant16(float v) { return (unsigned int) floorf(saturatef(v) * 65535.0f + 0.5f); }
 
+// The shader's store of a loaded texel into the UNORM16 UAV, floor(saturate(Load(p).r) * 65535 + .5): for UNORM8 data that is the byte times
+// 257, for UNORM16 data the identity (both checked exhaustively in tests/test_host_cpu.py) — integer work; float data takes the float path.
+__device__ __forceinline__ unsigned int octree_texel(uint8_t v) { return (unsigned int) v * 257u; }
+__device__ __forceinline__ unsigned int octree_texel(uint16_t v) { return v; }
+__device__ __forceinline__ unsigned int octree_texel(float v) { return quant16(v * 1.0f); }
+
 template <typename T, int N>
 struct alignas(sizeof(T) * N) OctPack {
     T v[N];
@@ -140,11 +146,11 @@ __global__ void __launch_bounds__(256) octree_build_kernel(const OctreeUniforms 
             if (VEC4 && x + 3 < X) {
                 const OctPack<DataT, 4> p = *reinterpret_cast<const OctPack<DataT, 4>*>(data + row + x);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) q[k] = quant16(Texel<DataT>::decode(p.v[k]) * 1.0f);
+                for (int k = 0; k < 4; ++k) q[k] = octree_texel(p.v[k]);
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (x + k < X) q[k] = quant16(Texel<DataT>::decode(__ldg(data + row + x + k)) * 1.0f);
+                    if (x + k < X) q[k] = octree_texel(__ldg(data + row + x + k));
             }
         }
         OctPack<uint16_t, 4> o;

@@ -297,3 +297,6 @@ def test_unorm8_to_unorm16_through_the_float_round_trip_is_byte_replication():
     b = np.arange(256, dtype=np.float32)
     v = np.clip(b / np.float32(255.0), np.float32(0), np.float32(1)) * np.float32(65535.0) + np.float32(0.5)
     assert v.dtype == np.float32 and np.array_equal(np.floor(v).astype(np.int64), np.arange(256) * 257)
+    w = np.arange(65536, dtype=np.float32)  # UNORM16 data: the same round trip is the identity (octree_texel, csrc/materials.cuh)
+    v = np.clip(w / np.float32(65535.0), np.float32(0), np.float32(1)) * np.float32(65535.0) + np.float32(0.5)
+    assert np.array_equal(np.floor(v).astype(np.int64), np.arange(65536))
