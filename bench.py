@@ -104,6 +104,8 @@ def workload_config(n_gpus: int, slabs: bool = True) -> dict:
         "volume": [N_VOL] * 3, "view": list(VIEW), "steps": STEPS, "lights": len(LIGHT_IDS),
         "sharding": shard,
         "cache": "inputs larger than L2 (128 MiB data + 512 MiB light volume vs 126 MB L2): no flush needed between steps",
+        # kernel selection switches that were set for this run (A/B timing; none changes a result — INTEGRATION.md)
+        "switches": {k: os.environ[k] for k in ("TBRM_SWEEP_PX", "TBRM_RAYMARCH_ADDR64", "TBRM_RAYMARCH_V2") if k in os.environ},
     }
 
 
