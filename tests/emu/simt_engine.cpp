@@ -77,7 +77,7 @@ CUresult encode_tiled(CUtensorMap* out, CUtensorMapDataType type, cuuint32_t ran
 
 // ---- fibers ----------------------------------------------------------------------------------------------------------------------------------
 namespace {
-constexpr size_t kStackBytes = 256 << 10;
+constexpr size_t kStackBytes = 128 << 10;  // per fiber; only the touched pages are ever backed
 
 struct Warp {
     int alive = 0, arrived = 0;
