@@ -19,6 +19,10 @@ from tbraymarcherplugin_b200 import synth
 from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats, FWindowingParameters, URaymarchUtils
 
 
+# a protocol bug would show as a spin that never ends inside the emulated library (C code): bound it from outside
+pytestmark = pytest.mark.timeout(900, method="thread")
+
+
 @pytest.fixture
 def emulated(monkeypatch):
     yield emu_lib.use(monkeypatch)
