@@ -12,7 +12,8 @@ from test_gpu_zz_materials import make_res
 from tbraymarcherplugin_b200 import FMT_G8, synth
 from tbraymarcherplugin_b200.raymarch_utils import FWindowingParameters, URaymarchUtils
 
-pytestmark = pytest.mark.gpu
+# never run on a GPU yet: a hang (e.g. a barrier that never completes) must end the run instead of holding the box
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 def test_mandelbulb_power8_kernels_match_their_cpu_twin():
     """Power == 8 runs the transcendental-free iteration (mandelbulb_sdf_p8): only +, -, *, /, sqrt and one log, so the oracle's variant 1
