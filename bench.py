@@ -39,8 +39,8 @@ N_VOL = 512
 VIEW = (1920, 1080)
 STEPS = 512.0
 LIGHT_IDS = (0, 1)
-SAMPLE_ROWS = list(range(27, 1080, 54))  # 20 evenly spaced rows for the CPU baseline's raymarch sample
-SWEEP_SAMPLE_N = 256  # the CPU sweep sample runs one axis pass over a 256^3 rendition of the same volume (1/8 of the voxels)
+SAMPLE_ROWS = list(range(5, 1080, 10))  # 108 evenly spaced rows (10 % of the frame) for the CPU baseline's raymarch sample
+SWEEP_SAMPLE_N = 512  # the CPU sweep sample runs ONE WHOLE axis pass over the workload's own volume (no voxel extrapolation)
 
 
 def peaks():
@@ -105,7 +105,7 @@ def workload_config(n_gpus: int, slabs: bool = True) -> dict:
         "sharding": shard,
         "cache": "inputs larger than L2 (128 MiB data + 512 MiB light volume vs 126 MB L2): no flush needed between steps",
         # kernel selection switches that were set for this run (A/B timing; none changes a result — INTEGRATION.md)
-        "switches": {k: os.environ[k] for k in ("TBRM_SWEEP_PX", "TBRM_RAYMARCH_ADDR64", "TBRM_RAYMARCH_V2") if k in os.environ},
+        "switches": {k: os.environ[k] for k in ("TBRM_SWEEP_GEN", "TBRM_SWEEP_PX", "TBRM_RAYMARCH_ADDR64", "TBRM_RAYMARCH_V2") if k in os.environ},
     }
 
 
@@ -178,14 +178,16 @@ def oracle_sample(data, data_small, light_after_reset, threads: int, kind: str =
     scale = VIEW[1] / len(SAMPLE_ROWS)
     est_seconds = total_passes * t_pass + t_rows * scale
     est_steps = steps_rows * scale
-    detail = {"sweep_pass_s_scaled": t_pass, "raymarch_rows_s": t_rows, "rows": len(SAMPLE_ROWS), "row_steps": steps_rows}
+    detail = {"estimated": True, "sweep_pass_s": t_pass, "sweep_voxel_scale": (N_VOL / SWEEP_SAMPLE_N) ** 3, "sweep_pass_scale": total_passes,
+              "raymarch_rows_s": t_rows, "rows": len(SAMPLE_ROWS), "row_scale": scale, "row_steps": steps_rows}
     return est_seconds, est_steps, detail
 
 
 def sample_text() -> str:
-    return (f"per step: 1 sweep axis pass over a {SWEEP_SAMPLE_N}^3 rendition of the volume (x{(N_VOL // SWEEP_SAMPLE_N) ** 3} voxels, "
-            f"x{2 * len(LIGHT_IDS)} passes) + lit raymarch of {len(SAMPLE_ROWS)} evenly spaced rows of the {N_VOL}^3/{VIEW[1]}p frame "
-            f"(x{VIEW[1] // len(SAMPLE_ROWS)}), extrapolated linearly to the whole step")
+    vox = "the whole volume" if SWEEP_SAMPLE_N == N_VOL else f"a {SWEEP_SAMPLE_N}^3 rendition of the volume (x{(N_VOL // SWEEP_SAMPLE_N) ** 3} voxels)"
+    return (f"ESTIMATE from a bounded sample, per step: 1 of the {2 * len(LIGHT_IDS)} sweep axis passes over {vox} (x{2 * len(LIGHT_IDS)} passes) "
+            f"+ lit raymarch of {len(SAMPLE_ROWS)} evenly spaced rows of the {N_VOL}^3/{VIEW[1]}p frame "
+            f"(x{VIEW[1] / len(SAMPLE_ROWS):g}), extrapolated linearly to the whole step")
 
 
 REFERENCE_NOTE = {
@@ -206,11 +208,16 @@ def run_reference(args) -> int:
 
     threads = os.cpu_count() or 1
     kind = "reference" if reference_build_available() else "port"
+    # every step is one bounded sample; the row sample shrinks (never below 20 rows) when many steps are asked for, so that the whole
+    # run stays within a few minutes: 3 samples -> 10 % of the rows, 23 samples -> 20 rows
+    global SAMPLE_ROWS
+    n_rows = max(20, min(len(SAMPLE_ROWS), (3 * len(SAMPLE_ROWS)) // max(1, args.warmup + args.steps)))
+    SAMPLE_ROWS = [int((i + 0.5) * VIEW[1] / n_rows) for i in range(n_rows)]
     data = oracle.synth_volume("perlin", (N_VOL,) * 3)  # untimed set-up; bit-identical to the device generator
-    data_small = oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3)
-    times, steps = [], 0.0
+    data_small = data if SWEEP_SAMPLE_N == N_VOL else oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3)
+    times, steps, detail = [], 0.0, {}
     for i in range(args.warmup + args.steps):
-        est_s, est_steps, _ = oracle_sample(data, data_small, None, threads, kind)
+        est_s, est_steps, detail = oracle_sample(data, data_small, None, threads, kind)
         if i >= args.warmup:
             times.append(est_s)
             steps = est_steps
@@ -218,9 +225,10 @@ def run_reference(args) -> int:
     value = steps / (ms * 1e-3) / 1e6
     line = {
         "impl": "reference", "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": threads, "kind": kind, "sample": sample_text()},
+        "cpu_baseline": {"value": value, "unit": "Mray-steps/s", "cores": threads, "kind": kind, "sample": sample_text(), **detail},
+        "estimated": True,
         "e2e": {"value": value, "unit": "Mray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": REFERENCE_NOTE[kind],
     }
@@ -482,7 +490,8 @@ def run_ours(args) -> int:
         import oracle
 
         kind = "reference" if reference_build_available() else "port"
-        est_s, est_steps, detail = oracle_sample(h_vol.numpy(), oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3), light, threads, kind)
+        small = h_vol.numpy() if SWEEP_SAMPLE_N == n else oracle.synth_volume("perlin", (SWEEP_SAMPLE_N,) * 3)
+        est_s, est_steps, detail = oracle_sample(h_vol.numpy(), small, light, threads, kind)
         cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": kind, "sample": sample_text(),
                         "est_ms_per_step": est_s * 1e3, "note": REFERENCE_NOTE[kind], **detail}
 
@@ -492,7 +501,7 @@ def run_ours(args) -> int:
         frame_steps = all_steps if slabs else ray_steps
         line = {
             "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if slabs else "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if (world_size > 1 and not slabs) else "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world_size, slabs), "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "roofline_sweep": roofline_sweep, "cpu_baseline": cpu_baseline,
             "stages": {
@@ -530,7 +539,7 @@ def main() -> int:
     if args.workload == "cfg4":
         global N_VOL, VIEW, STEPS, LIGHT_IDS, SAMPLE_ROWS
         N_VOL, VIEW, STEPS, LIGHT_IDS = 1024, (3840, 2160), 768.0, (0, 1, 2)
-        SAMPLE_ROWS = list(range(54, 2160, 108))
+        SAMPLE_ROWS = list(range(54, 2160, 108))  # 20 rows: a 1024^3 CPU sample is bounded harder (the sweep pass runs at 512^3, x8)
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 2
         args.warmup = args.warmup if args.warmup is not None else 1

@@ -77,6 +77,6 @@ def frame():
 
 
 out = {"volume": N, "view": [W, H], "steps": steps,
-       "env": {k: os.environ.get(k) for k in ("TBRM_SWEEP_PX", "TBRM_RAYMARCH_ADDR64", "TBRM_RAYMARCH_V2")},
+       "env": {k: os.environ.get(k) for k in ("TBRM_SWEEP_GEN", "TBRM_SWEEP_PX", "TBRM_RAYMARCH_ADDR64", "TBRM_RAYMARCH_V2")},
        "reset_2_lights": timed(reset, 10), "frame": timed(frame, 10), "sweep_impl": impl[-2:]}
 print(json.dumps(out), flush=True)

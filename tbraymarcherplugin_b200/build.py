@@ -48,9 +48,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     build_dir = PKG_DIR / "build"
     build_dir.mkdir(exist_ok=True)
     procs = []
+    extra = os.environ.get("TBRM_EXTRA_NVCC_FLAGS", "").split()  # diagnostic builds (e.g. -DTBRM_CHAIN_TIMERS)
     for src in SOURCES:
         obj = build_dir / (src + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -251,6 +251,9 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
         if (r->octree[m]) cudaFree(r->octree[m]);
 
     if (r->flags) cudaFree(r->flags);
+    if (r->sweep_err) cudaFree(r->sweep_err);
+    if (r->tvol) cudaFree(r->tvol);
+    if (r->tones) cudaFree(r->tones);
     for (auto& axis : r->rw)
         for (void* b : axis)
             if (b) cudaFree(b);
@@ -738,6 +741,15 @@ tbrm_status tbrm_slab_check(tbrm_resources* r) {
     TBRM_REQUIRE(r, "tbrm_slab_check: null argument");
     TBRM_CUDA(cudaSetDevice(r->device));
     TBRM_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->sweep_err) {  // unsharded fused sweeps: a tile that waited on another tile longer than the timeout
+        unsigned int werr = 0;
+        TBRM_CUDA(cudaMemcpy(&werr, r->sweep_err, sizeof(werr), cudaMemcpyDeviceToHost));
+        if (werr) {
+            TBRM_CUDA(cudaMemset(r->sweep_err, 0, sizeof(werr)));
+            set_last_error("fused sweep timed out waiting for another tile of the same launch (results are void)");
+            return TBRM_ERR_CUDA;
+        }
+    }
     if (!r->arena) return TBRM_OK;
     unsigned int err = 0;
     TBRM_CUDA(cudaMemcpy(&err, (unsigned int*) r->arena + 2, sizeof(err), cudaMemcpyDeviceToHost));
@@ -1026,7 +1038,14 @@ float tbrm_debug_mandelbulb_sdf_p8(const float position[3], float bailout, int i
 
 tbrm_status tbrm_debug_download_derived(tbrm_resources* res, int which, void* dst, size_t capacity) {
     TBRM_REQUIRE(res && dst, "tbrm_debug_download_derived: null argument");
-    TBRM_REQUIRE(which == 0 || which == 1, "tbrm_debug_download_derived: which must be 0 (brick grid) or 1 (yzx replica)");
+    if (which == 3) {  // TBRM_CHAIN_TIMERS builds: the chain kernel's section timers of the last pass
+        TBRM_REQUIRE(res->dbg != nullptr, "tbrm_debug_download_derived: not a TBRM_CHAIN_TIMERS build");
+        TBRM_CUDA(cudaSetDevice(res->device));
+        TBRM_CUDA(cudaStreamSynchronize(res->stream));
+        TBRM_CUDA(cudaMemcpy(dst, res->dbg, std::min(capacity, (size_t) 4096 * 4 * 8 * sizeof(long long)), cudaMemcpyDeviceToHost));
+        return TBRM_OK;
+    }
+    TBRM_REQUIRE(which >= 0 && which <= 2, "tbrm_debug_download_derived: which must be 0 (brick grid), 1 (yzx replica) or 2 (T-brick flags of the last split sweep pass)");
     tbrm_resources* r = res;
     if (r->data_fmt != TBRM_FMT_G8 || !r->data_ready) {
         set_last_error("tbrm_debug_download_derived: needs an uploaded R8 data volume");
@@ -1039,9 +1058,13 @@ tbrm_status tbrm_debug_download_derived(tbrm_resources* res, int which, void* ds
         TBRM_CUDA(ensure_bricks(*r));
         bytes = (size_t) ((r->ddims[0] + 7) / 8) * ((r->ddims[1] + 7) / 8) * ((r->ddims[2] + 7) / 8);
         src = r->bricks;
-    } else {
+    } else if (which == 1) {
         TBRM_CUDA(build_replica_for_tests(*r));
         src = r->data_yzx;
+    } else {
+        TBRM_REQUIRE(r->tones != nullptr, "tbrm_debug_download_derived: no split sweep pass has run");
+        bytes = std::min(capacity, r->tones_bytes);
+        src = r->tones;
     }
     TBRM_REQUIRE(capacity >= bytes, "tbrm_debug_download_derived: destination too small");
     TBRM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, r->stream));

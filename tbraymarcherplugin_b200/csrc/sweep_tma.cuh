@@ -80,6 +80,13 @@ struct TmaParams {
     unsigned int epoch;     // distinguishes the ring tags of successive passes
     unsigned int cut_lo_mode, cut_lo_add;  // exact empty-space skip on tap bytes (see window_cut_byte); mode 0 = off
     int exp_flags;          // experiment switches (tbrm_options.reserved[0])
+    // second generation (sweep_split.cuh)
+    const float* tvol;            // T = 1 - occlusion bricks written by occlusion_kernel: [tile][native block][slot][row][p]
+    const unsigned char* tones;   // per brick: every T is exactly 1 (the brick was not written)
+    const float* scratch;   // the removed light's propagated light (kModeCombine), light-volume layout
+    long long* dbg;         // TBRM_CHAIN_TIMERS builds: per-warp section timers of the chain kernel
+    unsigned int* error;    // device word set when a wait on another tile / launch timed out
+    unsigned long long timeout_ns;
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
@@ -90,6 +97,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among `nthreads` threads of the block (whole warps) on hardware barrier `id` (0 is __syncthreads' own)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -104,10 +117,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// the same wait where the phase is expected to complete much later (a producer that is a block ahead): the hardware suspends the
+// thread for up to the hinted time instead of returning to the polling loop
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                      smem_u32(dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16), completing on an mbarrier like the tensor loads
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
@@ -129,6 +164,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 }  // namespace tbrm
 
 #include "sweep_tma_kernel.cuh"
+#include "sweep_split.cuh"
 
 namespace tbrm {
 
@@ -271,6 +307,20 @@ static cudaError_t upload(tbrm_resources& r, const void* src, size_t bytes, size
 static const void* tma_kernel(int axis, bool clip, bool slab, int px) {
 #define TBRM_K(A, PX) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true, PX> : (const void*) sweep_tma_kernel<A, false, true, PX>) \
                             : (clip ? (const void*) sweep_tma_kernel<A, true, false, PX> : (const void*) sweep_tma_kernel<A, false, false, PX>))
+    if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
+    return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
+#undef TBRM_K
+}
+
+static const void* chain_kernel(int axis, bool slab, int px) {
+#define TBRM_K(A, PX) (slab ? (const void*) sweep_chain_kernel<A, true, PX> : (const void*) sweep_chain_kernel<A, false, PX>)
+    if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
+    return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
+#undef TBRM_K
+}
+typedef void (*occlusion_fn)(const OccParams, const float4*);
+static occlusion_fn occlusion_kernel_of(int axis, bool clip, int px) {
+#define TBRM_K(A, PX) (clip ? (occlusion_fn) occlusion_kernel<A, true, PX> : (occlusion_fn) occlusion_kernel<A, false, PX>)
     if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
     return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
 #undef TBRM_K
@@ -473,6 +523,15 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // pixels per thread: two (tile 64 x 8), or one (tile 32 x 8) for launches that cannot fill the SMs — there a pass costs slices x one
     // tile's per-slice chain, which one pixel per thread shortens. Automatic by default (measured on a B200 in round 2: 256^3 reset of two
     // lights 1.52 -> 1.31 ms, the GPU suite green in both forms); TBRM_SWEEP_PX=1 / 2 (or bits 4-5 of reserved[0]) force a form.
+    // kernel generation: 1 = sweep_tma_kernel.cuh (the default: still the fastest measured), 2 = occlusion kernel + propagation-chain kernel
+    // (sweep_split.cuh; TBRM_SWEEP_GEN=2 or bit 6 of reserved[0]). Round 2 measured generation 2 at 4.9 ms against 4.67 ms for the cfg2
+    // reset (bit-identical results): its chain kernel runs at ~2300 cycles per slice, half of it waiting.
+    static const int env_gen = [] {
+        const char* e = getenv("TBRM_SWEEP_GEN");
+        return e ? atoi(e) : 1;
+    }();
+    // (the chain kernel of the second generation walks whole blocks of kSB slices: other slice counts take the first generation)
+    const bool ws = (env_gen == 2 || (r.options.reserved[0] & 64)) && u.td[2] % kSB == 0;
     int px = 2;
     {
         static const int env_px = [] {  // 1 / 2 forced, 3 automatic (default)
@@ -550,7 +609,12 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     P.data_off = mode == kModeCombine ? 2 * P.light_bytes : P.light_bytes;
     P.data_bytes = P.dext[0] * P.dext[1] * P.dext[2];
     P.stage_bytes = (P.data_off + P.data_bytes + 16 + 127) / 128 * 128;
-    const size_t smem = (size_t) kStages * P.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
+    size_t smem = (size_t) kStages * P.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
+    if (ws) {  // T bricks, light bricks, footprints, mbarriers
+        smem = (size_t) (kChTStages + kChLStages) * P.light_bytes + (size_t) 2 * kFpW * kFpH * sizeof(float) + (kChTStages + kChLStages) * sizeof(uint64_t) + 16;
+        if (P.bext[0] * P.bext[1] - kChThreads > kChHaloOverflow) return not_handled("halo list");
+    }
+    P.scratch = (const float*) r.change_scratch;
 
     const bool clip = !clip_is_inactive(u, T);
     // ---- which part of the pass this GPU runs, and in how many co-resident waves (bands of tile rows) ----
@@ -566,9 +630,9 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     }
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
-    const int threads = kTmaThreads;
-    const void* kern_plain = tma_kernel(u.axis, clip, false, px);
-    const void* kern_slab = tma_kernel(u.axis, clip, true, px);
+    const int threads = ws ? kChThreads : kTmaThreads;
+    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : tma_kernel(u.axis, clip, false, px);
+    const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : tma_kernel(u.axis, clip, true, px);
     for (const void* k : {kern_plain, kern_slab})
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) {
             cudaGetLastError();
@@ -654,6 +718,66 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     P.ring = (float*) r.ring;
     P.flags = r.flags;
     memset(&P.S, 0, sizeof(P.S));
+    // every wait on another tile or launch gives up after the timeout and raises the error word (tbrm_slab_check reads it)
+    if (!r.sweep_err) {
+        if ((e = cudaMalloc((void**) &r.sweep_err, sizeof(unsigned int))) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(r.sweep_err, 0, sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
+    }
+    P.timeout_ns = (unsigned long long) (r.slab_timeout_ms > 0 ? r.slab_timeout_ms : 4000) * 1000000ull;
+    P.error = use_slab ? arena_word(r.arena, 2) : r.sweep_err;
+    if (ws) {
+        // ---- occlusion_kernel: T = 1 - occlusion for this GPU's share of the pass (an ordinary launch: no inter-block dependency) ----
+        const int nblocks = (ns + kSB - 1) / kSB;
+        const size_t bricks = (size_t) ntiles * nblocks, tbytes = bricks * (size_t) P.light_bytes;
+        if (r.tvol_bytes < tbytes) {
+            if (r.tvol) cudaStreamSynchronize(r.stream), cudaFree(r.tvol);
+            r.tvol = nullptr, r.tvol_bytes = 0;
+            if ((e = cudaMalloc(&r.tvol, tbytes)) != cudaSuccess) return e;
+            r.tvol_bytes = tbytes;
+        }
+        if (r.tones_bytes < bricks) {
+            if (r.tones) cudaStreamSynchronize(r.stream), cudaFree(r.tones);
+            r.tones = nullptr, r.tones_bytes = 0;
+            if ((e = cudaMalloc(&r.tones, bricks)) != cudaSuccess) return e;
+            r.tones_bytes = bricks;
+        }
+        P.tvol = (const float*) r.tvol, P.tones = (const unsigned char*) r.tones;
+#ifdef TBRM_CHAIN_TIMERS
+        if (!r.dbg && (e = cudaMalloc(&r.dbg, (size_t) 4096 * 4 * 8 * sizeof(long long))) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(r.dbg, 0, (size_t) 4096 * 4 * 8 * sizeof(long long), r.stream)) != cudaSuccess) return e;
+        P.dbg = ntiles <= 4096 ? (long long*) r.dbg : nullptr;
+#endif
+        OccParams O;
+        memset(&O, 0, sizeof(O));
+        O.U = u, O.A = P.A;
+        const long long sx = 1, sy = X, sz = (long long) X * Y;
+        if (u.axis == 2) O.data = (const uint8_t*) r.data, O.dsq = sy, O.dss = sz;
+        else if (u.axis == 1) O.data = (const uint8_t*) r.data, O.dsq = sz, O.dss = sy;
+        else O.data = (const uint8_t*) r.data_yzx, O.dsq = Y, O.dss = (long long) Y * Z;  // the (y,z,x) replica: y fastest, then z, then x
+        (void) sx;
+        for (int t = 0; t < 3; ++t) O.data_dims_t[t] = P.data_dims_t[t];
+        O.tvol = (float*) r.tvol, O.tones = (unsigned char*) r.tones;
+        O.ntx = P.ntx, O.nblocks = nblocks;
+        O.tile_row0 = tr0, O.tile_rows = tr1 - tr0;
+        // native blocks of the slices this GPU walks (a sub-range only for the Z-slab of a sweep along Z)
+        O.nb_begin = (u.dirn > 0 ? k_begin : ns - k_end) / kSB;
+        O.nb_end = ((u.dirn > 0 ? k_end : ns - k_begin) + kSB - 1) / kSB;
+        O.cut_lo_mode = P.cut_lo_mode, O.cut_lo_add = P.cut_lo_add;
+        O.cut_byte = P.cut_lo_mode ? cut : -1;
+        O.bricks = nullptr;
+        if (O.cut_byte >= 0) {
+            if ((e = ensure_bricks(r)) != cudaSuccess) return e;
+            O.bricks = (const uint8_t*) r.bricks;
+            for (int a = 0; a < 3; ++a) O.bdims[a] = (r.ddims[a] + 7) / 8;
+            for (int t = 0; t < 3; ++t) O.tap_lo[t] = T.dmin[nat[t]], O.tap_hi[t] = T.dmax[nat[t]] + 1;
+        }
+        const int chunks = (O.nb_end - O.nb_begin + kOccChunk - 1) / kOccChunk;
+        occlusion_fn occ = occlusion_kernel_of(u.axis, clip, px);
+        occ<<<dim3((unsigned) (P.ntx * O.tile_rows * chunks)), dim3(256), 0, r.stream>>>(O, r.tf);
+        count_launch();
+        *launches += 1;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
     if (!use_slab) {
         if ((e = cudaMemsetAsync(r.flags, 0, flag_words * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
         if ((e = tma_launch(r, kern_plain, threads, lm, dm, sm, P, ntiles, smem)) != cudaSuccess) return e;

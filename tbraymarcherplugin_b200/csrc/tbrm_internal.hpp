@@ -61,6 +61,12 @@ struct tbrm_resources {
     unsigned int ring_epoch = 0;  // TMA sweep: tag epoch of the ring cells (0 = ring holds no valid tags)
     unsigned int* flags = nullptr;
     size_t flags_count = 0;
+    unsigned int* sweep_err = nullptr;  // device word raised by a fused sweep launch whose wait on another tile timed out
+    void* tvol = nullptr;               // split sweep: T = 1 - occlusion bricks of the pass in flight (4 B per light voxel)
+    size_t tvol_bytes = 0;
+    void* dbg = nullptr;                // TBRM_CHAIN_TIMERS builds only
+    void* tones = nullptr;              // ... and one byte per brick: every T of the brick is exactly 1
+    size_t tones_bytes = 0;
     unsigned long long* counters = nullptr;  // device scratch for step / iteration counts
     // TMA sweep: (y,z,x)-ordered replica of the data volume for sweeps along X, and the per-pass sampler tables
     void* data_yzx = nullptr;

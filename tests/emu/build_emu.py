@@ -121,7 +121,7 @@ def generate() -> Path:
         text = rewrite_ptx(rewrite_launches(src.read_text()))
         if src.name == "sweep_tma.cuh":
             text = splice_tma_helpers(text)
-        if src.name == "sweep_tma_kernel.cuh":
+        if src.name in ("sweep_tma_kernel.cuh", "sweep_split.cuh"):
             text = must_replace(text, "extern __shared__ __align__(128) unsigned char smem[];", "unsigned char* smem = tbrm_emu::dynamic_smem();")
             text = must_replace(text, 'asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', "")
         assert "asm volatile" not in text, f"{src.name}: inline PTX the emulator build does not know:\n" + text[text.index("asm volatile"):][:300]

@@ -37,6 +37,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static thread_local
@@ -249,6 +250,16 @@ inline void st_global(T* p, V v) {
 
 static inline void __syncthreads() { tbrm_emu::sync_block(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { tbrm_emu::sync_warp(); }
+static inline int __syncthreads_and(int pred) {  // three barriers: vote, read, reset (fibers of a block share the accumulator)
+    static thread_local int acc = 1;
+    if (!pred) acc = 0;
+    tbrm_emu::sync_block();
+    const int r = acc;
+    tbrm_emu::sync_block();
+    acc = 1;
+    tbrm_emu::sync_block();
+    return r;
+}
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }

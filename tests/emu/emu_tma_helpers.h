@@ -8,31 +8,53 @@
 
 namespace tbrm {
 
-struct EmuBar {          // lives in the 8 bytes of the kernel's mbarrier word
-    int32_t tx_pending;  // bytes still to arrive in the current phase
-    uint32_t state;      // bit 31: the phase's arrival (expect_tx) has happened; bits 0..30: completed phases
+struct EmuBar {           // lives in the 8 bytes of the kernel's mbarrier word
+    int32_t tx_pending;   // bytes still to arrive in the current phase
+    uint16_t phase;       // completed phases
+    uint8_t count;        // arrivals a phase needs
+    uint8_t pending;      // arrivals still missing in the current phase
 };
 static_assert(sizeof(EmuBar) == 8, "an mbarrier is one 64-bit word");
 
 inline void emu_bar_settle(EmuBar* b) {
-    if ((b->state & 0x80000000u) && b->tx_pending == 0) b->state = (b->state & 0x7fffffffu) + 1u;
+    if (b->pending == 0 && b->tx_pending == 0) b->phase++, b->pending = b->count;
 }
 inline void mbar_init(uint64_t* bar, int count) {
-    if (count != 1) tbrm_emu::fail("emulated mbarrier: only arrival count 1 is supported");
+    if (count < 1 || count > 255) tbrm_emu::fail("emulated mbarrier: arrival count out of range");
     EmuBar* b = (EmuBar*) bar;
-    b->tx_pending = 0, b->state = 0;
+    b->tx_pending = 0, b->phase = 0, b->count = b->pending = (uint8_t) count;
 }
-inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {  // mbarrier.arrive.expect_tx: one arrival + the transaction bytes to wait for
     EmuBar* b = (EmuBar*) bar;
-    if (b->state & 0x80000000u) tbrm_emu::fail("emulated mbarrier: second arrival in one phase");
+    if (b->pending == 0) tbrm_emu::fail("emulated mbarrier: more arrivals than the phase expects");
     b->tx_pending += (int32_t) bytes;
-    b->state |= 0x80000000u;
+    b->pending--;
+    emu_bar_settle(b);
+}
+inline void mbar_arrive(uint64_t* bar) {
+    EmuBar* b = (EmuBar*) bar;
+    if (b->pending == 0) tbrm_emu::fail("emulated mbarrier: more arrivals than the phase expects");
+    b->pending--;
     emu_bar_settle(b);
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     const volatile EmuBar* b = (const volatile EmuBar*) bar;
-    while (((b->state & 0x7fffffffu) & 1u) == (parity & 1u)) tbrm_emu::spin_hint();
+    while ((b->phase & 1u) == (parity & 1u)) tbrm_emu::spin_hint();
 }
+inline void mbar_wait_long(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+// bar.sync id, nthreads: the fibers of a block run on one OS thread and switch only at barriers / spin hints
+inline void named_bar_sync(int id, int nthreads) {
+    static thread_local int arrived[16];
+    static thread_local unsigned gen[16];
+    if (id < 1 || id > 15) tbrm_emu::fail("emulated named barrier: id out of range");
+    const unsigned g = gen[id];
+    if (++arrived[id] == nthreads) {
+        arrived[id] = 0, gen[id] = g + 1;
+        return;
+    }
+    while (*(volatile unsigned*) &gen[id] == g) tbrm_emu::spin_hint();
+}
+inline void prefetch_l1(const void*) {}
 
 inline void emu_tma_copy(void* smem, const CUtensorMap* map, int c0, int c1, int c2, bool load) {
     const tbrm_emu::TensorMap& m = *(const tbrm_emu::TensorMap*) map;
@@ -61,6 +83,15 @@ inline void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c
     const tbrm_emu::TensorMap& m = *(const tbrm_emu::TensorMap*) map;
     EmuBar* b = (EmuBar*) bar;
     b->tx_pending -= (int32_t) (m.box[0] * m.box[1] * m.box[2] * m.elem);
+    if (b->tx_pending < 0) tbrm_emu::fail("emulated mbarrier: more transaction bytes than expect_tx announced");
+    emu_bar_settle(b);
+}
+inline void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    if (((uintptr_t) dst & 15u) || ((uintptr_t) src & 15u) || (bytes & 15u)) tbrm_emu::fail("bulk copy: 16-byte alignment / size");
+    memcpy(dst, src, bytes);
+    EmuBar* b = (EmuBar*) bar;
+    b->tx_pending -= (int32_t) bytes;
+    if (b->tx_pending < 0) tbrm_emu::fail("emulated mbarrier: more transaction bytes than expect_tx announced");
     emu_bar_settle(b);
 }
 inline void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) { emu_tma_copy((void*) src, map, c0, c1, c2, false); }
