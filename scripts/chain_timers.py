@@ -37,3 +37,12 @@ print("tiles that wait least in (c) [tile: per-warp a c bar svc d end head]:")
 for o in order[:6]:
     print(f"  tile {idx[o]:4d} (row {idx[o] // (n // 64)}, col {idx[o] % (n // 64)}):", " | ".join(" ".join(f"{used[o, wi, i] / n:6.0f}" for i in range(7)) for wi in range(4)))
 print("c (max over warps 0-2) percentiles:", np.percentile(c0, [0, 5, 25, 50, 75, 95, 100]).round(0))
+g = np.zeros((n // 8, n // 64))
+tot = np.zeros((n // 8, n // 64))
+for o in range(used.shape[0]):
+    r, c = idx[o] // (n // 64), idx[o] % (n // 64)
+    g[r, c] = used[o, :3, 1].max() / n
+    tot[r, c] = used[o, 0, :7].sum() / n
+print("halo wait (c, max over warps 0-2) per tile, cycles per slice; rows = tile rows (every 4th), cols = tile columns")
+for r in range(0, n // 8, 4):
+    print(f"  row {r:2d}: " + " ".join(f"{g[r, c]:5.0f}" for c in range(n // 64)) + "   | lifetime/slice: " + " ".join(f"{tot[r, c]:5.0f}" for c in range(n // 64)))

@@ -31,7 +31,8 @@ constexpr int kChThreads = 128;  // 4 warps: CPX = 4 adjacent pixels per thread 
                                  // per-thread bookkeeping per slice, not arithmetic: fewer, fatter threads with registers to spare (no
                                  // rematerialisation at 4 CTAs x 128 threads per SM) beat 256 thin ones (measured: 250 instructions per
                                  // thread and slice for 2 pixels with 256 threads)
-constexpr int kChTStages = 3, kChLStages = 3;
+constexpr int kChTStages = 3, kChLStages = 2;
+constexpr int kChHaloDepth = 3;  // staging slots of a thread's halo cell: requested two slices before it is read
 constexpr int kChService = 96;  // the thread that issues the TMA copies and posts the progress word: lane 0 of the last warp, whose threads
                                 // hold no halo cell on ordinary footprints (<= 96 cells) and reach the barrier first
 constexpr int kChHaloOverflow = kFpW * kFpH - kChThreads;  // halo cells beyond the one a thread keeps in a register
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(kChThreads, 4)
     __shared__ volatile int s_abort;  // a wait on another tile / launch timed out; stop waiting (results are void)
     __shared__ int s_tones[kChTStages];  // the stage's brick is all ones (nothing was loaded)
     __shared__ unsigned short s_over_fp[kChHaloOverflow];  // footprint index of the halo cells beyond the per-thread register (0xffff: none)
+    __shared__ ulonglong2 s_hstage[kChHaloDepth][kChThreads];  // asynchronously fetched halo cells (the 16-byte pair holding the thread's cell)
 
     const int fx0 = x0 + P.bmin[0], fy0 = y0 + P.bmin[1], FW = P.bext[0], FH = P.bext[1];
     const int nblocks = (ns + kSB - 1) / kSB;
@@ -548,10 +550,12 @@ __global__ void __launch_bounds__(kChThreads, 4)
         __syncthreads();
     }
 
-    // The halo cell of slice k (read by slice k+1) is requested during slice k and checked a slice later: the L2 round trip stays off the
-    // per-slice chain. A request that comes too early (the upstream tile has not exported yet) falls into the polling path once; that
-    // delays this tile until it lags its upstream neighbour by about a slice, from where on every request hits. Same for the
-    // back-pressure probe (a progress word only grows: an early value that suffices stays valid).
+    // Reading a ring cell another SM wrote a moment ago costs ~1 200 cycles here (measured with in-kernel timers: a strong GPU-scope
+    // load of such a line, 4-5 times the L2 hit latency) — more than all the work of a slice. The halo cell slice k+2 reads (slice k+1 of
+    // the upstream tile) is therefore requested during slice k, as an asynchronous copy into a 3-slot SMEM queue. A request that comes too
+    // early (the upstream tile has not exported yet) delivers a stale tag and falls into the polling path once; that delays this tile
+    // until it lags its upstream neighbour by about two slices, from where on every request hits. Same idea for the back-pressure probe
+    // (a progress word only grows: an early value that suffices stays valid).
     //
     // The loop below is written for instruction count: a slice costs its per-thread bookkeeping, not its arithmetic (24 fp32 operations
     // for 4 pixels), and the pass runs at slices x (instructions of one warp per slice) x (issue interval of a warp). Blocks are whole
@@ -560,6 +564,8 @@ __global__ void __launch_bounds__(kChThreads, 4)
     const bool has_halo = halo_fp >= 0;
     const bool halo_inbox = SLAB && halo_ring < 0;
     const unsigned long long* const halo_base = halo_inbox ? P.S.inbox + (-1 - halo_ring) : ring + (unsigned int) halo_ring;
+    const bool halo_odd = ((halo_inbox ? -1 - halo_ring : halo_ring) & 1) != 0;  // which half of its 16-byte pair the cell is (planes hold an even number of cells)
+    const unsigned long long* const halo_pair = halo_base - (halo_odd ? 1 : 0);
     const unsigned int halo_stride = halo_inbox ? (unsigned int) inbox_plane : plane32;  // cells per slice (the inbox is full depth, the ring wraps)
     const unsigned int halo_wrap = halo_inbox ? 0xffffffffu : (unsigned int) (kRingDepth - 1);
     float* const halo_dst = s_fp + (has_halo ? halo_fp : 0);
@@ -578,8 +584,8 @@ __global__ void __launch_bounds__(kChThreads, 4)
 #else
 #define TBRM_T(i)
 #endif
-    unsigned long long hv_next = 0;
     unsigned int pv_next = 0;
+    for (int i = 0; i < kChHaloDepth; ++i) s_hstage[i][tid] = make_ulonglong2(0ull, 0ull);  // a tag that matches nothing
     int store_pending = -1;  // block whose light brick is complete in SMEM and waits for its TMA store (thread 0)
     for (int n = 0; n < nblk; ++n) {
         const int tst = n % kChTStages, lst = n % kChLStages;
@@ -617,7 +623,13 @@ __global__ void __launch_bounds__(kChThreads, 4)
             const int fp_par = (int) (k & 1u) * (FPW * kFpH);
             // ---- (a) the halo cell of slice k-1 was requested a slice ago; request the one slice k+1 will read (slice k, tag k+1) ----
             const unsigned int want_tag = tag_base + k;  // slice k-1 carries tag k
-            unsigned long long hv = hv_next;
+            // the copy issued two slices ago has landed (the one issued in the previous slice may still be in flight)
+            unsigned long long hv = 0;
+            if (has_halo) {
+                cp_async_wait_but_one();
+                const ulonglong2 pair = s_hstage[k % kChHaloDepth][tid];
+                hv = halo_odd ? pair.y : pair.x;
+            }
             // a ring slot is reused every kRingDepth slices: before exporting slices k..k+3 every reader must have consumed slice
             // k+3-kRingDepth, i.e. passed the barrier of its slice k+4-kRingDepth. Probed in the first slice of a block, read in the last
             // slice of the block before.
@@ -657,11 +669,12 @@ __global__ void __launch_bounds__(kChThreads, 4)
             TBRM_T(1)
             __syncthreads();
             TBRM_T(2)
-            // (issued after the check of the previous request: two requests in flight would share a scoreboard slot, and the check
-            // would wait for the younger one — measured: a full L2 round trip per slice)
-            if (has_halo && k + 1 < (unsigned int) k_end) {
-                const unsigned long long* ncell = halo_base + (size_t) ((k & halo_wrap) * halo_stride);
-                hv_next = halo_inbox ? ld_relaxed_sys_u64(ncell) : ld_relaxed_u64(ncell);
+            // request the cell slice k+2 will read (slice k+1 of the upstream tile, tag k+2): an asynchronous 16-byte copy L2 -> SMEM, so
+            // that no register scoreboard ties the check of an older request to a younger one
+            if (has_halo) {
+                if (k + 2 < (unsigned int) k_end)
+                    cp_async_16(&s_hstage[(k + 2) % kChHaloDepth][tid], halo_pair + (size_t) (((k + 1u) & halo_wrap) * halo_stride));
+                cp_async_commit();
             }
             if (tid == kChService) {
                 st_relaxed_u32(my_flag, k);  // every read of slice k-1 by this tile is done

@@ -145,6 +145,12 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                  "r"(smem_u32(bar))
                  : "memory");
 }
+// Ampere-style asynchronous copy of 16 bytes global -> shared through L2 only (.cg), tracked per thread in commit groups
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0), "r"(c1),
                  "r"(c2), "r"(smem_u32(src))

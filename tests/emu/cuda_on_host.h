@@ -68,6 +68,7 @@ TBRM_EMU_VEC(char, char)
 struct alignas(16) ulonglong2 {
     unsigned long long x, y;
 };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 
 // ---- runtime API (synchronous, one device) -------------------------------------------------------------------------------------------------
 enum cudaError_t {

@@ -94,6 +94,14 @@ inline void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* b
     if (b->tx_pending < 0) tbrm_emu::fail("emulated mbarrier: more transaction bytes than expect_tx announced");
     emu_bar_settle(b);
 }
+inline void cp_async_16(void* dst, const void* src) {
+    if (((uintptr_t) dst & 15u) || ((uintptr_t) src & 15u)) tbrm_emu::fail("cp.async: 16-byte alignment");
+    const unsigned long long* s = (const unsigned long long*) src;
+    unsigned long long* d = (unsigned long long*) dst;
+    d[0] = __atomic_load_n(s, __ATOMIC_ACQUIRE), d[1] = __atomic_load_n(s + 1, __ATOMIC_ACQUIRE);
+}
+inline void cp_async_commit() {}
+inline void cp_async_wait_but_one() {}
 inline void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src) { emu_tma_copy((void*) src, map, c0, c1, c2, false); }
 inline void tma_commit() {}
 template <int N>
