@@ -35,6 +35,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+WORKLOAD = "cfg2"
 N_VOL = 512
 VIEW = (1920, 1080)
 STEPS = 512.0
@@ -87,6 +88,38 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+GOLDEN_HASHES = ROOT / "tests" / "golden" / "ref_fullsize_hashes.json"  # SHA-256 digests of what the REFERENCE'S OWN shaders produce at full size
+HASH_BLOCK = 64  # leading-axis slices per digest block (tests/golden/make_golden_ref_fullsize.py)
+
+
+def digests(a) -> dict:
+    """SHA-256 of every block of 64 leading-axis slices of a C-contiguous array and of the concatenated block digests — the format of
+    tests/golden/ref_fullsize_hashes.json."""
+    import hashlib
+
+    import numpy as np
+
+    a = np.ascontiguousarray(a)
+    blocks = [hashlib.sha256(a[i:i + HASH_BLOCK].tobytes()).hexdigest() for i in range(0, a.shape[0], HASH_BLOCK)]
+    return {"shape": list(a.shape), "dtype": str(a.dtype), "blocks": blocks, "all": hashlib.sha256("".join(blocks).encode()).hexdigest()}
+
+
+def parity_against_reference(cfg: str, light=None, frame=None) -> dict:
+    """Bit-parity of this run's light volume / frame with the reference shaders' output for the same configuration (committed digests).
+    Runs outside every timed region; what the driver sees of the multi-GPU exchange path's correctness."""
+    out = {"against": f"tests/golden/ref_fullsize_hashes.json[{cfg}] (reference shaders compiled for the CPU)"}
+    if not GOLDEN_HASHES.exists():
+        return {**out, "available": False}
+    want = json.loads(GOLDEN_HASHES.read_text()).get(cfg)
+    if want is None:
+        return {**out, "available": False}
+    if light is not None:
+        out["light"] = digests(light)["all"] == want["light"]["all"]
+    if frame is not None and "frame" in want:
+        out["frame"] = digests(frame)["all"] == want["frame"]["all"]
+    return out
 
 
 def workload_config(n_gpus: int, slabs: bool = True) -> dict:
@@ -357,6 +390,20 @@ def run_ours(args) -> int:
     if slabs:
         vol.Check()
     trace("warm-up checked")
+    # ---- parity of what the warm-up produced with the reference shaders' output (untimed; rank 0) ----
+    parity = None
+    if not args.no_parity and (slabs or world_size == 1):
+        if slabs:
+            _, frame_t = raymarch(count=False)
+            vol.Flush()
+            if rank == 0:
+                parity = parity_against_reference(WORKLOAD, vol.light.cpu().numpy(), frame_t.cpu().numpy())
+        else:
+            fr, _ = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, STEPS, count_steps=False)
+            parity = parity_against_reference(WORKLOAD, URaymarchUtils.ReadLightVolume(res), fr)
+        if rank == 0 and parity and (parity.get("light") is False or parity.get("frame") is False):
+            print(f"bench.py: PARITY FAILURE against the reference shaders' digests: {parity}", file=sys.stderr, flush=True)
+        trace(f"parity: {parity}")
 
     # ---- timed region: K steps, device time on the library's stream, max over ranks ----
     clocks = ClockSampler(local)
@@ -417,10 +464,19 @@ def run_ours(args) -> int:
         "traffic": None, "peak_source": peak_src, "impl": list(st4.impl), "ms": pass_ms,
     }
     ncu = ROOT / "profiles" / "traffic.json"
-    if ncu.exists() and world_size == 1:  # dram bytes per launch from the committed `ncu --set full` captures (N_VOL = 512, one GPU)
+    if ncu.exists() and world_size == 1 and N_VOL == 512:
+        # DRAM bytes per launch measured by ncu on this workload (scripts/ncu_traffic.py writes the file together with the commit and the
+        # library checksum it measured; a number taken under the profiler is never a time, only a byte count)
         t = json.loads(ncu.read_text())
+        import hashlib
+
+        meta = dict(t.get("_meta") or {})
+        lib_path = ROOT / "tbraymarcherplugin_b200" / "libtbrm.so"
+        meta["same_library"] = bool(meta.get("libtbrm_sha256_16")) and lib_path.exists() and \
+            hashlib.sha256(lib_path.read_bytes()).hexdigest()[:16] == meta.get("libtbrm_sha256_16")
         roofline["traffic"] = t.get("raymarch_fast_kernel")
         roofline_sweep["traffic"] = t.get("sweep_tma_kernel")
+        roofline["traffic_source"] = roofline_sweep["traffic_source"] = meta
 
     # ---- end to end: the reference-facing API with HOST buffers, copies inside the timed region ----
     def e2e_step():
@@ -495,7 +551,76 @@ def run_ours(args) -> int:
         cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": kind, "sample": sample_text(),
                         "est_ms_per_step": est_s * 1e3, "note": REFERENCE_NOTE[kind], **detail}
 
-    if slabs:
+    # ---- BASELINE.json configs[3] (north_star's scaling figure): the illumination sweep of a 1024^3 volume, 3 lights, full reset, on the
+    # same N GPUs — sweep only, Mvoxels/s = light voxels x axis passes / device time (max over ranks), light volume checked bit-for-bit
+    # against the reference shaders' digest. Rides along in every line so that the driver's 1/2/4/8 runs carry it.
+    scale_cfg4 = None
+    if not args.no_cfg4 and WORKLOAD == "cfg2" and (slabs or world_size == 1):
+        trace("scale_cfg4: set-up")
+        n4, lights4 = 1024, [synth.LIGHTS[i] for i in (0, 1, 2)]
+        if slabs:
+            vol.release()
+            vol = None
+            vol4 = sharding.FShardedRaymarchVolume((n4, n4, n4), local)
+            res4 = vol4.res
+            za, zb = vol4.z0, vol4.z1
+            _capi.check(lib.tbrm_synth_volume_u8(local, _capi.SYNTH_PERLIN_CT, (C.c_int32 * 3)(n4, n4, n4), synth.PERLIN_SEED & 0xFFFFFFFF,
+                                                 C.c_void_p(vol4.data.data_ptr()), 1))
+            torch.cuda.synchronize()
+            _capi.check(lib.tbrm_bind_volume_device(res4.handle, C.c_void_p(vol4.data.data_ptr())))
+        else:
+            res.release()
+            d4 = torch.empty((n4, n4, n4), dtype=torch.uint8, device="cuda")
+            _capi.check(lib.tbrm_synth_volume_u8(local, _capi.SYNTH_PERLIN_CT, (C.c_int32 * 3)(n4, n4, n4), synth.PERLIN_SEED & 0xFFFFFFFF, C.c_void_p(d4.data_ptr()), 1))
+            res4 = URaymarchUtils.InitializeRaymarchResources((n4, n4, n4), FMT_G8, bLightVolume32Bit=True, device=local)
+            URaymarchUtils.SetDataVolumeDevice(res4, d4.data_ptr())
+            vol4 = None
+        URaymarchUtils.ColorCurveToTexture(res4, synth.soft_ct_curve())
+        URaymarchUtils.SetWindowingParameters(res4, win)
+        stats4 = []
+
+        def sweep4():
+            URaymarchUtils.ClearResourceLightVolumes(res4, 0.0)
+            stats4.clear()
+            for l in lights4:
+                st = FSweepStats()
+                assert URaymarchUtils.AddDirLightToSingleVolume(res4, l, True, world, bGPUSync=True, stats=st)
+                stats4.append(st)
+
+        sweep4()
+        URaymarchUtils.FlushRenderingCommands(res4)
+        if vol4 is not None:
+            vol4.Check()
+        barrier()
+        _capi.check(lib.tbrm_timer_begin(res4.handle))
+        reps4 = 3
+        for _ in range(reps4):
+            sweep4()
+        ms4 = C.c_float()
+        _capi.check(lib.tbrm_timer_end(res4.handle, C.byref(ms4)))
+        sweep4_ms = allreduce(ms4.value / reps4, MAX)
+        passes4 = sum(s.passes for s in stats4)
+        par4 = None
+        if not args.no_parity:
+            if vol4 is not None:
+                vol4.GatherLightVolume()
+                vol4.Flush()
+                vol4.Check()
+                if rank == 0:
+                    par4 = parity_against_reference("cfg4", light=vol4.light.cpu().numpy())
+            else:
+                par4 = parity_against_reference("cfg4", light=URaymarchUtils.ReadLightVolume(res4))
+        scale_cfg4 = {"workload": "cfg4 sweep: 1024^3 Perlin R8, R32F light volume, 3 dir lights full reset (clear + 6 axis passes), sweep only",
+                      "n_gpus": world_size, "sweep_ms": sweep4_ms, "axis_passes": passes4,
+                      "Mvoxels_per_s": float(n4) ** 3 * passes4 / (sweep4_ms * 1e-3) / 1e6,
+                      "GB_per_s": float(n4) ** 3 * (4.0 + 9.0 * passes4) / (sweep4_ms * 1e-3) / 1e9,
+                      "impl": [list(s.impl) for s in stats4], "parity": par4}
+        trace(f"scale_cfg4: {scale_cfg4}")
+        if vol4 is not None:
+            vol4.release()
+        else:
+            res4.release()
+    if slabs and vol is not None:
         vol.Check()
     if rank == 0:
         frame_steps = all_steps if slabs else ray_steps
@@ -503,7 +628,7 @@ def run_ours(args) -> int:
             "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if (world_size > 1 and not slabs) else "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world_size, slabs), "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_sweep": roofline_sweep, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "roofline_sweep": roofline_sweep, "cpu_baseline": cpu_baseline, "parity": parity, "scale_cfg4": scale_cfg4,
             "stages": {
                 "ray_steps_per_frame": frame_steps,
                 "raymarch": {"ms": ray_ms, "Mray_steps_per_s": all_steps / (ray_ms * 1e-3) / 1e6},
@@ -517,7 +642,7 @@ def run_ours(args) -> int:
         print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.barrier()
-        if slabs:
+        if slabs and vol is not None:
             vol.release()
         dist.destroy_process_group()
     return 0
@@ -530,12 +655,16 @@ def main() -> int:
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) digest comparison with the reference shaders' output")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the extra 1024^3 sweep measurement (scale_cfg4)")
     ap.add_argument("--trace", action="store_true", help="print progress lines to stderr (debugging multi-GPU runs)")
     ap.add_argument("--sharding", default="slabs", choices=["slabs", "volumes"],
                     help="N > 1: 'slabs' = ONE volume Z-slab sharded over the GPUs (strong scaling, default); 'volumes' = one volume per GPU (weak)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"],
                     help="cfg2 = 512^3 / 1080p / 512 steps / 2 lights (BASELINE.json configs[1], default); cfg4 = 1024^3 / 2160p / 768 steps / 3 lights")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.workload == "cfg4":
         global N_VOL, VIEW, STEPS, LIGHT_IDS, SAMPLE_ROWS
         N_VOL, VIEW, STEPS, LIGHT_IDS = 1024, (3840, 2160), 768.0, (0, 1, 2)

@@ -11,6 +11,22 @@
 
 #include "tbrm_internal.hpp"
 
+// NVTX ranges around the C-ABI operations — what SCOPED_GPU_STAT / SCOPED_DRAW_EVENT are to the reference's render commands
+// (LightingShaders.cpp:25-30, 57-58): Nsight Systems / Compute show "tbrm::AddDirLight" etc. Header-only NVTX v3: no link dependency, a
+// no-op unless a tool is attached.
+#ifndef TBRM_HOST_EMULATION
+#include <nvtx3/nvToolsExt.h>
+struct TbrmRange {
+    explicit TbrmRange(const char* name) { nvtxRangePushA(name); }
+    ~TbrmRange() { nvtxRangePop(); }
+};
+#else
+struct TbrmRange {
+    explicit TbrmRange(const char*) {}
+};
+#endif
+#define TBRM_RANGE(name) TbrmRange tbrm_range_(name)
+
 namespace tbrm {
 std::atomic<long long> g_kernel_launches{0};
 static thread_local std::string t_last_error;
@@ -43,16 +59,43 @@ static tbrm_status with_output(int device, cudaStream_t stream, void* dst, size_
         TBRM_CUDA(enqueue(dst));
         return TBRM_OK;
     }
-    void* tmp = nullptr;
-    TBRM_CUDA(cudaMalloc(&tmp, bytes));
-    cudaError_t e = enqueue(tmp);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, stream);
+    // grow-only staging buffer per host thread and device: cudaFree synchronises the whole device and would stall the upload / download
+    // streams of the streaming pipeline once per frame
+    struct Staging {
+        void* p = nullptr;
+        size_t cap = 0;
+        int dev = -1;
+        ~Staging() {
+            if (p && dev >= 0 && cudaSetDevice(dev) == cudaSuccess) cudaFree(p);
+        }
+    };
+    thread_local Staging st[8];
+    Staging& b = st[(unsigned) device % 8u];
+    if (b.dev != device || b.cap < bytes) {
+        if (b.p && b.dev >= 0) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(b.dev);
+            cudaFree(b.p);
+            cudaSetDevice(cur);
+        }
+        b.p = nullptr, b.cap = 0, b.dev = device;
+        TBRM_CUDA(cudaMalloc(&b.p, bytes));
+        b.cap = bytes;
+    }
+    cudaError_t e = enqueue(b.p);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFree(tmp);
-    (void) device;
     TBRM_CUDA(e);
     return TBRM_OK;
 }
+
+struct DeviceCounter {  // a device word that is released however the function is left
+    unsigned long long* p = nullptr;
+    ~DeviceCounter() {
+        if (p) cudaFree(p);
+    }
+};
 
 // runs `enqueue(d_out, d_counter)` on the per-thread stream, delivers `bytes` of output and the optional iteration count
 template <typename F>
@@ -62,7 +105,8 @@ static tbrm_status mandelbulb_op(int device, void* dst, size_t bytes, int dst_is
         return TBRM_ERR_NO_DEVICE;
     }
     TBRM_CUDA(cudaSetDevice(device));
-    unsigned long long* d_iters = nullptr;
+    DeviceCounter counter;  // freed on every exit path
+    unsigned long long*& d_iters = counter.p;
     if (out_iterations) {
         TBRM_CUDA(cudaMalloc((void**) &d_iters, sizeof(unsigned long long)));
         TBRM_CUDA(cudaMemsetAsync(d_iters, 0, sizeof(unsigned long long), cudaStreamPerThread));
@@ -76,7 +120,6 @@ static tbrm_status mandelbulb_op(int device, void* dst, size_t bytes, int dst_is
         if (e != cudaSuccess) s = TBRM_ERR_CUDA;
     }
     if (s == TBRM_OK && dst_is_device && cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) s = TBRM_ERR_CUDA;
-    if (d_iters) cudaFree(d_iters);
     return s;
 }
 
@@ -271,6 +314,7 @@ tbrm_status tbrm_set_options(tbrm_resources* r, const tbrm_options* opts) {
 }
 
 tbrm_status tbrm_upload_volume(tbrm_resources* r, const void* src, int src_is_device) {
+    TBRM_RANGE("tbrm::SetDataVolume");
     TBRM_REQUIRE(r && src, "tbrm_upload_volume: null argument");
     TBRM_CUDA(cudaSetDevice(r->device));
     const size_t bytes = r->data_voxels() * r->data_elem();
@@ -301,6 +345,7 @@ static tbrm_status ensure_streaming(tbrm_resources* r) {
 }
 
 tbrm_status tbrm_upload_volume_async(tbrm_resources* r, const void* src_host) {
+    TBRM_RANGE("tbrm::SetDataVolumeAsync");
     TBRM_REQUIRE(r && src_host, "tbrm_upload_volume_async: null argument");
     TBRM_CUDA(cudaSetDevice(r->device));
     tbrm_status s = ensure_streaming(r);
@@ -319,6 +364,7 @@ tbrm_status tbrm_upload_volume_async(tbrm_resources* r, const void* src_host) {
 }
 
 tbrm_status tbrm_present_volume(tbrm_resources* r) {
+    TBRM_RANGE("tbrm::PresentDataVolume");
     TBRM_REQUIRE(r, "tbrm_present_volume: null argument");
     TBRM_REQUIRE(r->upload_pending && r->data_back, "tbrm_present_volume: no tbrm_upload_volume_async since the last present");
     TBRM_CUDA(cudaSetDevice(r->device));
@@ -399,6 +445,7 @@ tbrm_status tbrm_set_windowing(tbrm_resources* r, const tbrm_windowing* w) {
 
 // ---- sweep ------------------------------------------------------------------------------------------------
 tbrm_status tbrm_clear_light_volume(tbrm_resources* r, float clear_value) {
+    TBRM_RANGE("tbrm::ClearLightVolume");
     if (!r || !r->light) return TBRM_OK;  // RaymarchUtils.cpp:106-109: silently returns without a render target
     TBRM_CUDA(cudaSetDevice(r->device));
     if (r->slab.nranks > 1) {  // a sharded volume: every rank clears the slab it owns
@@ -551,6 +598,7 @@ static void reset_stats(tbrm_sweep_stats* s) {
 
 tbrm_status tbrm_add_dir_light_stats(tbrm_resources* r, const tbrm_dir_light* light, int added, const tbrm_world* world,
                                      int* light_added, int gpu_sync, tbrm_sweep_stats* stats) {
+    TBRM_RANGE("tbrm::AddDirLight");
     reset_stats(stats);
     if (!resources_valid(r)) {  // RaymarchUtils.cpp:39-45
         if (light_added) *light_added = 0;
@@ -570,6 +618,7 @@ tbrm_status tbrm_add_dir_light(tbrm_resources* r, const tbrm_dir_light* light, i
 // ChangeDirLightInSingleLightVolume_RenderThread — LightingShaders.cpp:168-326
 tbrm_status tbrm_add_dir_lights_joined(tbrm_resources* r, const tbrm_dir_light* lights, int n_lights, int added, const tbrm_world* world,
                                        int* lights_added, tbrm_sweep_stats* stats) {
+    TBRM_RANGE("tbrm::AddDirLightsJoined");
     reset_stats(stats);
     if (lights_added) *lights_added = 0;
     if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
@@ -584,6 +633,7 @@ tbrm_status tbrm_add_dir_lights_joined(tbrm_resources* r, const tbrm_dir_light* 
 
 tbrm_status tbrm_change_dir_light_stats(tbrm_resources* r, const tbrm_dir_light* old_light, const tbrm_dir_light* new_light,
                                         const tbrm_world* world, int* light_added, int gpu_sync, tbrm_sweep_stats* stats) {
+    TBRM_RANGE("tbrm::ChangeDirLight");
     reset_stats(stats);
     if (!resources_valid(r)) {  // RaymarchUtils.cpp:74-80
         if (light_added) *light_added = 0;
@@ -769,6 +819,7 @@ tbrm_status tbrm_slab_set_timeout_ms(tbrm_resources* r, int timeout_ms) {
 
 tbrm_status tbrm_add_dir_light_pass(tbrm_resources* r, const tbrm_dir_light* light, int added, const tbrm_world* world, int pass,
                                     int gpu_sync, tbrm_sweep_stats* stats) {
+    TBRM_RANGE("tbrm::AddDirLightPass");
     reset_stats(stats);
     if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
     TBRM_REQUIRE(light && world && (pass == 0 || pass == 1), "tbrm_add_dir_light_pass: bad argument");
@@ -840,12 +891,14 @@ static tbrm_status raymarch_lit_impl(tbrm_resources* r, const tbrm_camera* cam, 
 
 tbrm_status tbrm_raymarch_lit(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
                               int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    TBRM_RANGE("tbrm::LitRaymarch");
     return raymarch_lit_impl(r, cam, world, step_count, row_begin, row_end, 8, 1, out_rgba, out_is_device, out_steps);
 }
 
 tbrm_status tbrm_raymarch_lit_interleaved(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count,
                                           int block_rows, int first_block, int block_stride, float* out_rgba, int out_is_device,
                                           uint64_t* out_steps) {
+    TBRM_RANGE("tbrm::LitRaymarchInterleaved");
     TBRM_REQUIRE(cam && block_rows > 0 && block_rows % 8 == 0 && first_block >= 0 && block_stride >= 1 && first_block < block_stride,
                  "tbrm_raymarch_lit_interleaved: block_rows must be a positive multiple of 8, 0 <= first_block < block_stride");
     const int row_begin = std::min(first_block * block_rows, cam->height);
@@ -854,6 +907,7 @@ tbrm_status tbrm_raymarch_lit_interleaved(tbrm_resources* r, const tbrm_camera* 
 
 tbrm_status tbrm_raymarch_lit_to_host_async(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count,
                                             float* out_host) {
+    TBRM_RANGE("tbrm::LitRaymarchToHostAsync");
     if (!resources_valid(r)) return TBRM_ERR_NOT_INITIALIZED;
     TBRM_REQUIRE(world && out_host && camera_valid(cam), "tbrm_raymarch_lit_to_host_async: bad argument");
     TBRM_CUDA(cudaSetDevice(r->device));
@@ -899,6 +953,7 @@ int tbrm_raymarch_interleaved_rows(int height, int block_rows, int first_block, 
 
 tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, const tbrm_camera* cam, const tbrm_world* world,
                                   int row_begin, int row_end, float* out_xy, int out_is_device, uint64_t* out_iterations) {
+    TBRM_RANGE("tbrm::MandelbulbMarch");
     TBRM_REQUIRE(params && world && out_xy, "tbrm_mandelbulb_march: null argument");
     TBRM_REQUIRE(camera_valid(cam), "tbrm_mandelbulb_march: invalid camera");
     TBRM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= cam->height, "tbrm_mandelbulb_march: bad row range");
@@ -914,7 +969,8 @@ tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, con
     TBRM_CUDA(cudaSetDevice(device));
     host::CameraUniforms cu;
     host::plan_camera(*cam, *world, cu);
-    unsigned long long* d_iters = nullptr;
+    DeviceCounter counter;  // freed on every exit path
+    unsigned long long*& d_iters = counter.p;
     if (out_iterations) {
         TBRM_CUDA(cudaMalloc((void**) &d_iters, sizeof(unsigned long long)));
         TBRM_CUDA(cudaMemsetAsync(d_iters, 0, sizeof(unsigned long long), cudaStreamPerThread));
@@ -933,12 +989,12 @@ tbrm_status tbrm_mandelbulb_march(int device, const tbrm_mandelbulb* params, con
     if (s == TBRM_OK && out_is_device) {
         if (cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) s = TBRM_ERR_CUDA;
     }
-    if (d_iters) cudaFree(d_iters);
     return s;
 }
 
 // ---- the other materials and the octree ----------------------------------------------
 tbrm_status tbrm_generate_octree(tbrm_resources* r) {
+    TBRM_RANGE("tbrm::GenerateOctree");
     // URaymarchUtils::GenerateOctree enqueues without checks (RaymarchUtils.cpp:94-102); the shader needs the data volume
     if (!r || !r->data || !r->data_ready) return TBRM_ERR_NOT_INITIALIZED;
     TBRM_CUDA(cudaSetDevice(r->device));
@@ -1001,11 +1057,13 @@ static tbrm_status raymarch_material_impl(tbrm_resources* r, int material, const
 
 tbrm_status tbrm_raymarch_intensity(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int row_begin,
                                     int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    TBRM_RANGE("tbrm::IntensityRaymarch");
     return raymarch_material_impl(r, 1, cam, world, step_count, 0, row_begin, row_end, out_rgba, out_is_device, out_steps);
 }
 
 tbrm_status tbrm_raymarch_octree(tbrm_resources* r, const tbrm_camera* cam, const tbrm_world* world, float step_count, int octree_mip,
                                  int row_begin, int row_end, float* out_rgba, int out_is_device, uint64_t* out_steps) {
+    TBRM_RANGE("tbrm::OctreeRaymarch");
     return raymarch_material_impl(r, 2, cam, world, step_count, octree_mip, row_begin, row_end, out_rgba, out_is_device, out_steps);
 }
 
@@ -1013,6 +1071,7 @@ tbrm_status tbrm_raymarch_octree(tbrm_resources* r, const tbrm_camera* cam, cons
 tbrm_status tbrm_mandelbulb_march_normal(int device, const tbrm_mandelbulb* params, float derivation_distance, const tbrm_camera* cam,
                                          const tbrm_world* world, int row_begin, int row_end, float* out_rgba, int out_is_device,
                                          uint64_t* out_iterations) {
+    TBRM_RANGE("tbrm::MandelbulbMarchNormal");
     TBRM_REQUIRE(params && world && out_rgba, "tbrm_mandelbulb_march_normal: null argument");
     TBRM_REQUIRE(camera_valid(cam), "tbrm_mandelbulb_march_normal: invalid camera");
     TBRM_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= cam->height, "tbrm_mandelbulb_march_normal: bad row range");
@@ -1119,6 +1178,7 @@ tbrm_status tbrm_converted_format(const tbrm_volume_info* info, int normalize, i
 
 tbrm_status tbrm_normalize_volume(int device, int voxel_format, const void* src, int src_is_device, uint64_t count, void* dst,
                                   int dst_is_device, float* out_min, float* out_max) {
+    TBRM_RANGE("tbrm::NormalizeVolume");
     TBRM_REQUIRE(src && dst && count > 0, "tbrm_normalize_volume: null argument or empty volume");
     const int ib = voxel_format_bytes(voxel_format);
     TBRM_REQUIRE(ib > 0, "tbrm_normalize_volume: unknown voxel format");
@@ -1216,8 +1276,24 @@ static tbrm_status load_volume_from_info(int device, const std::string& data_pat
     return TBRM_OK;
 }
 
-tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
-                                 tbrm_volume_info* info, tbrm_resources** out) {
+// no C++ exception may cross the C ABI (a header that promises 2^60 bytes must come back as a status, not terminate the host process)
+extern "C++" {
+template <typename F>
+static tbrm_status guarded(const char* what, F body) {
+    try {
+        return body();
+    } catch (const std::exception& e) {
+        set_last_error(std::string(what) + ": " + e.what());
+        return TBRM_ERR_INVALID_ARGUMENT;
+    } catch (...) {
+        set_last_error(std::string(what) + ": unknown failure");
+        return TBRM_ERR_INVALID_ARGUMENT;
+    }
+}
+}  // extern "C++"
+
+static tbrm_status load_mhd_volume_impl(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
+                                        tbrm_volume_info* info, tbrm_resources** out) {
     TBRM_REQUIRE(mhd_path && info && out, "tbrm_load_mhd_volume: null argument");
     *out = nullptr;
     std::string text;
@@ -1241,11 +1317,17 @@ tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize
     return load_volume_from_info(device, dir + "/" + info->data_file, normalize, convert_to_float, light_fmt, half_res, info, out, "tbrm_load_mhd_volume");
 }
 
-tbrm_status tbrm_load_raw_volume(int device, const char* raw_path, const int32_t dims[3], int voxel_format, int64_t compressed_bytes, int normalize,
-                                 int convert_to_float, tbrm_format light_fmt, int half_res, tbrm_volume_info* info, tbrm_resources** out) {
+tbrm_status tbrm_load_mhd_volume(int device, const char* mhd_path, int normalize, int convert_to_float, tbrm_format light_fmt, int half_res,
+                                 tbrm_volume_info* info, tbrm_resources** out) {
+    return guarded("tbrm_load_mhd_volume", [&] { return load_mhd_volume_impl(device, mhd_path, normalize, convert_to_float, light_fmt, half_res, info, out); });
+}
+
+static tbrm_status load_raw_volume_impl(int device, const char* raw_path, const int32_t dims[3], int voxel_format, int64_t compressed_bytes, int normalize,
+                                        int convert_to_float, tbrm_format light_fmt, int half_res, tbrm_volume_info* info, tbrm_resources** out) {
     TBRM_REQUIRE(raw_path && dims && info && out, "tbrm_load_raw_volume: null argument");
     *out = nullptr;
     TBRM_REQUIRE(voxel_format_bytes(voxel_format) > 0, "tbrm_load_raw_volume: unknown voxel format");
+    TBRM_REQUIRE(dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && compressed_bytes >= 0, "tbrm_load_raw_volume: bad dimensions / compressed size");
     std::memset(info, 0, sizeof(*info));
     info->parse_ok = 1;
     for (int k = 0; k < 3; ++k) info->dims[k] = dims[k], info->spacing[k] = 1.0, info->world_dims[k] = (double) dims[k];
@@ -1256,6 +1338,12 @@ tbrm_status tbrm_load_raw_volume(int device, const char* raw_path, const int32_t
     info->is_compressed = compressed_bytes > 0, info->compressed_bytes = compressed_bytes > 0 ? compressed_bytes : 0;
     std::snprintf(info->data_file, sizeof(info->data_file), "%s", raw_path);
     return load_volume_from_info(device, raw_path, normalize, convert_to_float, light_fmt, half_res, info, out, "tbrm_load_raw_volume");
+}
+
+tbrm_status tbrm_load_raw_volume(int device, const char* raw_path, const int32_t dims[3], int voxel_format, int64_t compressed_bytes, int normalize,
+                                 int convert_to_float, tbrm_format light_fmt, int half_res, tbrm_volume_info* info, tbrm_resources** out) {
+    return guarded("tbrm_load_raw_volume",
+                   [&] { return load_raw_volume_impl(device, raw_path, dims, voxel_format, compressed_bytes, normalize, convert_to_float, light_fmt, half_res, info, out); });
 }
 
 // ---- queue control ----------------------------------------------------------------------------------------

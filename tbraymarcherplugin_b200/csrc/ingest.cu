@@ -269,6 +269,7 @@ bool mhd_parse_header(const std::string& text, tbrm_volume_info& out) {
     std::istringstream in;
     if (!words_after(text, "DimSize", nullptr, in)) return false;
     in >> out.dims[0] >> out.dims[1] >> out.dims[2];
+    if (in.fail() || out.dims[0] <= 0 || out.dims[1] <= 0 || out.dims[2] <= 0) return false;  // a DimSize that did not parse leaves zeros
     if (!words_after(text, "ElementSpacing", "ElementSize", in)) return false;
     in >> out.spacing[0] >> out.spacing[1] >> out.spacing[2];
     for (int k = 0; k < 3; ++k) out.world_dims[k] = out.spacing[k] * (double) out.dims[k];  // WorldDimensions = Spacing * Dimensions
@@ -291,6 +292,7 @@ bool mhd_parse_header(const std::string& text, tbrm_volume_info& out) {
     if (words_after(text, "CompressedDataSize", nullptr, in)) {
         out.is_compressed = 1;
         in >> out.compressed_bytes;
+        if (in.fail() || out.compressed_bytes <= 0) return false;
     }
     if (!words_after(text, "ElementDataFile", nullptr, in)) return false;
     std::string file;
@@ -301,12 +303,33 @@ bool mhd_parse_header(const std::string& text, tbrm_volume_info& out) {
 }
 
 // LoadRawFileIntoArray / LoadZLibCompressedFileIntoArray (TextureUtilities.cpp:262-302): exactly `bytes` bytes of voxels
-bool load_voxel_file(const std::string& path, const tbrm_volume_info& info, std::vector<uint8_t>& voxels, std::string& err) {
-    const size_t bytes = (size_t) info.dims[0] * info.dims[1] * info.dims[2] * info.bytes_per_voxel;
+bool load_voxel_file(const std::string& path, const tbrm_volume_info& info, std::vector<uint8_t>& voxels, std::string& err) try {
+    // the header values come from a file: reject what cannot be a volume before sizing anything by them
+    constexpr long long kMaxSide = 1 << 16;
+    constexpr unsigned long long kMaxBytes = 1ull << 40;
+    if (info.dims[0] <= 0 || info.dims[1] <= 0 || info.dims[2] <= 0 || info.dims[0] > kMaxSide || info.dims[1] > kMaxSide || info.dims[2] > kMaxSide ||
+        info.bytes_per_voxel <= 0 || info.bytes_per_voxel > 8) {
+        err = "volume header: DimSize / ElementType out of range";
+        return false;
+    }
+    const unsigned long long want = (unsigned long long) info.dims[0] * info.dims[1] * info.dims[2] * (unsigned long long) info.bytes_per_voxel;
+    if (want > kMaxBytes || (info.is_compressed && (info.compressed_bytes <= 0 || (unsigned long long) info.compressed_bytes > kMaxBytes))) {
+        err = "volume header: DimSize x ElementType (or CompressedDataSize) is not a plausible size";
+        return false;
+    }
+    const size_t bytes = (size_t) want;
     std::ifstream f(path, std::ios::binary);
     if (!f) {
         err = "cannot open " + path;
         return false;
+    }
+    if (info.is_compressed) {  // the file must at least hold what the header promises before it is sized by it
+        f.seekg(0, std::ios::end);
+        if ((long long) f.tellg() < (long long) info.compressed_bytes) {
+            err = path + " holds fewer bytes than CompressedDataSize";
+            return false;
+        }
+        f.seekg(0, std::ios::beg);
     }
     voxels.resize(bytes);
     if (!info.is_compressed) {
@@ -329,6 +352,10 @@ bool load_voxel_file(const std::string& path, const tbrm_volume_info& info, std:
         return false;
     }
     return true;
+} catch (const std::exception& e) {  // std::bad_alloc / std::length_error must not cross the C ABI
+    err = std::string("loading ") + path + ": " + e.what();
+    voxels.clear();
+    return false;
 }
 
 }  // namespace tbrm

@@ -756,8 +756,9 @@ cudaError_t ensure_bricks(tbrm_resources& r) {
                                                              (uint8_t*) r.bricks);
         count_launch();
     }
-    r.bricks_valid = true;
-    return cudaGetLastError();
+    const cudaError_t le = cudaGetLastError();
+    r.bricks_valid = le == cudaSuccess;  // a failed launch must not leave a grid of garbage marked usable (samples would be skipped)
+    return le;
 }
 
 // conservative: the clip plane never rejects a march position (positions stay within the unit cube expanded by 1)

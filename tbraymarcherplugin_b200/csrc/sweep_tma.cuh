@@ -450,8 +450,9 @@ static cudaError_t ensure_replica(tbrm_resources& r) {
         permute_yzx_kernel<<<grid, block, 0, r.stream>>>((const uint8_t*) r.data, (uint8_t*) r.data_yzx, r.ddims[0], r.ddims[1], r.ddims[2]);
     }
     count_launch();
-    r.data_yzx_valid = true;
-    return cudaGetLastError();
+    const cudaError_t le = cudaGetLastError();
+    r.data_yzx_valid = le == cudaSuccess;
+    return le;
 }
 
 cudaError_t build_replica_for_tests(tbrm_resources& r) { return ensure_replica(r); }
@@ -690,7 +691,9 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         if ((e = cudaMemsetAsync(r.ring, 0, r.ring_bytes, r.stream)) != cudaSuccess) return e;
         r.ring_epoch = 1;
     }
-    P.epoch = ++r.pass_seq;
+    // the sequence number is committed only when nothing can fail before the launch any more: a rank that gave up on an allocation or a
+    // missing peer below must not have consumed a number its neighbours did not
+    P.epoch = r.pass_seq + 1;
     P.exp_flags = r.options.reserved[0];
     P.cut_lo_mode = 0, P.cut_lo_add = 0;
     int cut = -1;
@@ -785,6 +788,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (!use_slab) {
+        r.pass_seq = P.epoch;
         if ((e = cudaMemsetAsync(r.flags, 0, flag_words * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
         if ((e = tma_launch(r, kern_plain, threads, lm, dm, sm, P, ntiles, smem)) != cudaSuccess) return e;
         count_launch();
@@ -813,6 +817,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     }
     const unsigned long long timeout_ns = (unsigned long long) (r.slab_timeout_ms > 0 ? r.slab_timeout_ms : 4000) * 1000000ull;
     unsigned int* err_word = arena_word(r.arena, 2);
+    r.pass_seq = P.epoch;
     if (sharded && seq > 2) {  // the neighbours must be done with the arena regions this pass overwrites
         const unsigned int* a_lo = r.peer_arena[0] ? arena_word(r.arena, 0) : nullptr;
         const unsigned int* a_hi = r.peer_arena[1] ? arena_word(r.arena, 1) : nullptr;

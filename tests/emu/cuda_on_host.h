@@ -123,6 +123,10 @@ static inline cudaError_t cudaMemset(void* d, int v, size_t n) {
 }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(d, v, n); }
 static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+static inline cudaError_t cudaGetDevice(int* d) {
+    *d = 0;
+    return cudaSuccess;
+}
 static inline cudaError_t cudaGetDeviceCount(int* n) {
     *n = 1;
     return cudaSuccess;

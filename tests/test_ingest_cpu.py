@@ -138,6 +138,33 @@ def test_raw_loader_validates_before_touching_a_device(tmp_path):
     assert lib.tbrm_load_raw_volume(0, str(tmp_path / "i32.raw").encode(), dims, 5, 0, 0, 0, 0, 0, C.byref(info), C.byref(h)) == _capi.TBRM_ERR_UNSUPPORTED
 
 
+def test_hostile_headers_come_back_as_a_status_not_as_a_terminated_process(tmp_path):
+    """Header values come from a file: a negative CompressedDataSize used to become std::vector((size_t) -1) -> std::length_error across the C
+    ABI, a huge DimSize std::bad_alloc — both terminate the host process (Python or UE). They must come back as TBRM_ERR_INVALID_ARGUMENT."""
+    lib = _capi.load()
+    h, info = C.c_void_p(), _capi.VolumeInfo()
+    args = (1, 0, 0, 0, C.byref(info), C.byref(h))
+    (tmp_path / "x.raw").write_bytes(b"\0" * 64)
+    base = "ElementSpacing = 1 1 1\nElementType = MET_UCHAR\nElementDataFile = x.raw\n"
+    bad = {
+        "negative_compressed.mhd": "DimSize = 4 4 4\nCompressedDataSize = -1\n" + base,
+        "huge_compressed.mhd": "DimSize = 4 4 4\nCompressedDataSize = 4611686018427387904\n" + base,
+        "huge_dims.mhd": "DimSize = 60000 60000 60000\n" + base,
+        "overflowing_dims.mhd": "DimSize = 2000000000 2000000000 2000000000\n" + base,
+        "unparsed_dims.mhd": "DimSize = four 4 4\n" + base,
+        "zero_dims.mhd": "DimSize = 0 4 4\n" + base,
+    }
+    for name, text in bad.items():
+        (tmp_path / name).write_text(text)
+        assert lib.tbrm_load_mhd_volume(0, str(tmp_path / name).encode(), *args) == _capi.TBRM_ERR_INVALID_ARGUMENT, name
+        assert not h.value
+    dims = (C.c_int32 * 3)(4, 4, 4)
+    assert lib.tbrm_load_raw_volume(0, str(tmp_path / "x.raw").encode(), dims, 0, -5, *args) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    assert lib.tbrm_load_raw_volume(0, str(tmp_path / "x.raw").encode(), dims, 0, 1 << 50, *args) == _capi.TBRM_ERR_INVALID_ARGUMENT
+    zero = (C.c_int32 * 3)(4, 0, 4)
+    assert lib.tbrm_load_raw_volume(0, str(tmp_path / "x.raw").encode(), zero, 0, 0, *args) == _capi.TBRM_ERR_INVALID_ARGUMENT
+
+
 # ---- against the reference's own loaders (MHDLoader.cpp + VolumeLoader.cpp compiled from /root/reference, tests/golden/ref_loaders.npz) ---------
 import importlib.util  # noqa: E402
 
