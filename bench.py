@@ -495,6 +495,23 @@ def run_ours(args) -> int:
         else:
             URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, STEPS, out=h_img.numpy(), count_steps=False)  # D2H of the frame (pinned)
 
+    # the box's own pinned-copy rates (one plain copy each way, untimed region): round 1 saw the serial figure differ 3x between two boxes
+    # while the streamed figure agreed — the line now says what the PCIe path of THIS box delivers
+    def copy_rate(dst, src):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        return src.numel() * src.element_size() / (time.perf_counter() - t0) / 1e9
+
+    d_probe = torch.empty_like(h_vol, device="cuda")
+    copy_rate(d_probe, h_vol)
+    h2d_gbps = copy_rate(d_probe, h_vol)
+    d_frame_probe = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    copy_rate(h_img, d_frame_probe)
+    d2h_gbps = copy_rate(h_img, d_frame_probe)
+    del d_probe, d_frame_probe
+
     e2e_step()  # also switches an unsharded resource set to an owned device copy before timing
     e2e_step()
     barrier()
@@ -504,6 +521,31 @@ def run_ours(args) -> int:
     torch.cuda.synchronize()
     serial_ms = allreduce(1e3 * (time.perf_counter() - t0) / args.steps, MAX)
     e2e_ms, pipelined = serial_ms, False
+    if slabs:
+        # the sharded volume's streaming entry points: every rank uploads its slab of step i+1 and the ranks replicate it (all-gather on
+        # the upload stream, its own communicator) while step i computes; rank 0 downloads frame i while step i+1 computes
+        h_imgs = [h_img, torch.empty((H, W, 4), dtype=torch.float32).pin_memory()]
+
+        def e2e_pipelined_slabs(k):
+            vol.SetDataVolumeSlabAsync(h_vol)
+            for i in range(k):
+                vol.PresentDataVolume()
+                if i + 1 < k:
+                    vol.SetDataVolumeSlabAsync(h_vol)
+                sweep()
+                gather_light()
+                vol.RenderToHostAsync(cam, world, STEPS, h_imgs[i % 2])
+            vol.WaitForDownloads()
+            vol.Flush()
+
+        e2e_pipelined_slabs(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_pipelined_slabs(args.steps)
+        torch.cuda.synchronize()
+        e2e_ms = allreduce(1e3 * (time.perf_counter() - t0) / args.steps, MAX)
+        pipelined = True
+        vol.Check()
     if not slabs:
         # The same K steps through the streaming entry points: step i+1's volume is copied H2D on the upload stream while step i
         # computes, frame i is copied D2H on the download stream while step i+1 computes. Every step still uploads its own input
@@ -532,8 +574,12 @@ def run_ours(args) -> int:
     frames = 1 if slabs else world_size
     e2e = {"value": all_steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mray-steps/s", "h2d_bytes_per_step": int(n) ** 3 * frames,
            "d2h_bytes_per_step": H * W * 16 * frames, "ms_per_step": e2e_ms, "serial_ms_per_step": serial_ms,
-           "mode": ("streaming API: the H2D copy of step i+1 and the D2H copy of frame i overlap the compute of their neighbours "
-                    "(tbrm_upload_volume_async / tbrm_present_volume / tbrm_raymarch_lit_to_host_async)") if pipelined else
+           "pinned_copy_GBps": {"h2d": h2d_gbps, "d2h": d2h_gbps},
+           "mode": (("streaming API: the H2D copy of step i+1 and the D2H copy of frame i overlap the compute of their neighbours "
+                     "(tbrm_upload_volume_async / tbrm_present_volume / tbrm_raymarch_lit_to_host_async)") if not slabs else
+                    ("streaming API of the sharded volume: every rank's slab upload + the data all-gather of step i+1 (upload stream, own "
+                     "communicator) and rank 0's frame download of step i overlap the compute of their neighbours "
+                     "(SetDataVolumeSlabAsync / PresentDataVolume / RenderToHostAsync)")) if pipelined else
                    "serial: H2D copy, sweep, raymarch, D2H copy one after the other"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample ----

@@ -174,6 +174,78 @@ class FShardedRaymarchVolume:
         # the replica / brick grid derived from the data volume are rebuilt lazily
         _capi.check(self.lib.tbrm_bind_volume_device(self.res.handle, C.c_void_p(self.data.data_ptr())))
 
+    # ---- streaming inputs / outputs: copies and the data all-gather overlap the previous / next step's kernels ------------------
+    def _ensure_streaming(self) -> None:
+        import torch
+        import torch.distributed as dist
+
+        if getattr(self, "_upload_stream", None) is not None:
+            return
+        dev = self.light.device
+        self._upload_stream = torch.cuda.Stream(device=dev)
+        self._download_stream = torch.cuda.Stream(device=dev)
+        self._data_back = torch.empty_like(self.data)
+        self._ev_uploaded = torch.cuda.Event()
+        self._ev_back_free = torch.cuda.Event()
+        self._ev_back_free.record(self.stream)
+        self._upload_pending = False
+        # its own communicator: the all-gather of the NEXT step's data runs on the upload stream while the render queue's collectives
+        # (light all-gather, frame gather) run on the library's stream
+        self._upload_group = dist.new_group(ranks=list(range(self.world))) if self.group is None else self.group
+        self._downloads = []
+
+    def SetDataVolumeSlabAsync(self, slab) -> None:
+        """Start uploading this rank's slab of the NEXT data volume (pinned host tensor for a true overlap) into the back buffer and
+        replicating it with an all-gather, on the upload stream. PresentDataVolume makes it current."""
+        import torch
+        import torch.distributed as dist
+
+        self._ensure_streaming()
+        t = torch.as_tensor(slab) if not isinstance(slab, torch.Tensor) else slab
+        if tuple(t.shape) != (self.z1 - self.z0, self.dims[1], self.dims[0]) or t.dtype != torch.uint8:
+            raise ValueError("slab must be uint8 with shape (z1 - z0, Y, X)")
+        if self._upload_pending:
+            raise RuntimeError("an uploaded volume is waiting for PresentDataVolume")
+        with torch.cuda.stream(self._upload_stream):
+            self._upload_stream.wait_event(self._ev_back_free)  # the render queue no longer reads the back buffer
+            self._data_back[self.z0:self.z1].copy_(t, non_blocking=True)
+            dist.all_gather_into_tensor(self._data_back.view(-1), self._data_back[self.z0:self.z1].reshape(-1), group=self._upload_group)
+            self._ev_uploaded.record(self._upload_stream)
+        self._upload_pending = True
+
+    def PresentDataVolume(self) -> None:
+        """Make the uploaded volume current: the render queue waits for the upload, the buffers swap."""
+        if not getattr(self, "_upload_pending", False):
+            raise RuntimeError("no uploaded volume is pending")
+        self.stream.wait_event(self._ev_uploaded)
+        self.data, self._data_back = self._data_back, self.data
+        self._ev_back_free.record(self.stream)  # everything enqueued so far may still read the old buffer; what follows reads the new one
+        _capi.check(self.lib.tbrm_bind_volume_device(self.res.handle, C.c_void_p(self.data.data_ptr())))
+        self._upload_pending = False
+
+    def RenderToHostAsync(self, cam, world, step_count: float, out) -> None:
+        """Render (collective); rank 0 copies the assembled frame into `out` (pinned (H, W, 4) float32 tensor) on the download stream.
+        Read `out` after WaitForDownloads."""
+        import torch
+
+        self._ensure_streaming()
+        frame, _ = self.Render(cam, world, step_count, gather=True, count_steps=False)
+        if self.rank == 0:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            with torch.cuda.stream(self._download_stream):
+                self._download_stream.wait_event(ev)
+                out.copy_(frame, non_blocking=True)
+                frame.record_stream(self._download_stream)
+                done = torch.cuda.Event()
+                done.record(self._download_stream)
+            self._downloads.append(done)
+
+    def WaitForDownloads(self) -> None:
+        for ev in getattr(self, "_downloads", []):
+            ev.synchronize()
+        self._downloads = []
+
     # ---- sweep (collective; same arguments on every rank) ---------------------------------------------------
     def ClearLightVolume(self, value: float = 0.0) -> None:
         from .raymarch_utils import URaymarchUtils

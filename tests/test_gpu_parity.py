@@ -184,11 +184,14 @@ def test_mandelbulb_matches_oracle_within_tolerance():
     out, iters = URaymarchUtils.PerformMandelbulbRaymarchReturnDistance(params, cam, synth.identity_world())
     ref, ref_iters = oracle.mandelbulb(params, cam, synth.identity_world())
     assert (ref[..., 1] == 1).sum() > 200
-    # tolerance 1e-4 per channel; sphere tracing a fractal amplifies the ulp-level differences between libm and CUDA
-    # transcendentals, so a hit can land one march step earlier/later (value changes by k*10/MaxSteps): budget 2 %.
+    # tolerance 1e-4 per channel (BASELINE.json). Sphere tracing a fractal amplifies ulp-level differences (libm vs CUDA transcendentals; the
+    # Power == 8 kernel's transcendental-free iteration) next to the surface: a hit lands one march step earlier / later for a few pixels.
+    # Measured on a B200 in round 2 (scripts/mandelbulb_mismatch.py, profiles/r2_mandelbulb_mismatch_*.json): 0.10 % of the pixels here,
+    # 0.12 % of the 1080p cfg5 frame (0.11 - 0.15 % on the trigonometric path). Budget 0.5 %.
     bad = np.abs(out - ref).max(axis=-1) > 1e-4
-    assert bad.mean() < 0.02, f"{bad.sum()} of {bad.size} pixels differ"
-    assert abs(iters - ref_iters) / ref_iters < 0.02
+    print(f"mandelbulb: {bad.sum()} of {bad.size} pixels ({100 * bad.mean():.3f} %) beyond 1e-4; iterations {iters} vs {ref_iters}")
+    assert bad.mean() <= 0.005, f"{bad.sum()} of {bad.size} pixels differ"
+    assert abs(iters - ref_iters) / ref_iters < 1e-3
 
 
 @pytest.mark.parametrize("kind", ["sphere", "perlin"])

@@ -35,13 +35,16 @@ def test_mandelbulb_power8_kernels_match_their_cpu_twin():
     ref, _ = oracle.mandelbulb(mb, cam, world)
     bad_twin = (np.abs(got - twin).max(-1) > 1e-4).mean()
     bad_ref = (np.abs(got - ref).max(-1) > 1e-4).mean()
-    assert bad_twin <= 0.01 and bad_ref <= 0.02, (bad_twin, bad_ref)  # vs the twin only the final log differs (1 ulp, amplified near the surface)
+    # measured on a B200 (profiles/r2_mandelbulb_mismatch_p8.json): 0.009 % vs the twin (only the final log differs: 1 ulp, amplified next to
+    # the surface), 0.12 % vs the reference's formulation
+    print(f"mandelbulb p8: {100 * bad_twin:.4f} % of the pixels beyond 1e-4 vs the CPU twin, {100 * bad_ref:.4f} % vs the reference formulation")
+    assert bad_twin <= 0.001 and bad_ref <= 0.005, (bad_twin, bad_ref)
     assert abs(iters - twin_iters) / twin_iters < 5e-3
     assert (np.abs(gsdf - tsdf) > 1e-5).mean() <= 0.01
     mb6 = FMandelbulbParameters(MaxSteps=64.0, MaxIterations=8.0, Power=6.0)
     got6, _ = URaymarchUtils.PerformMandelbulbRaymarchReturnDistance(mb6, cam, world)
     ref6, _ = oracle.mandelbulb(mb6, cam, world)
-    assert (np.abs(got6 - ref6).max(-1) > 1e-4).mean() <= 0.02
+    assert (np.abs(got6 - ref6).max(-1) > 1e-4).mean() <= 0.005
 
 
 def test_headerless_raw_file_loads_like_the_mhd_path(tmp_path):
