@@ -520,7 +520,7 @@ def run_ours(args) -> int:
         e2e_step()
     torch.cuda.synchronize()
     serial_ms = allreduce(1e3 * (time.perf_counter() - t0) / args.steps, MAX)
-    e2e_ms, pipelined = serial_ms, False
+    e2e_ms, pipelined, streamed_ms = serial_ms, False, None
     if slabs:
         # the sharded volume's streaming entry points: every rank uploads its slab of step i+1 and the ranks replicate it (all-gather on
         # the upload stream, its own communicator) while step i computes; rank 0 downloads frame i while step i+1 computes
@@ -543,9 +543,11 @@ def run_ours(args) -> int:
         t0 = time.perf_counter()
         e2e_pipelined_slabs(args.steps)
         torch.cuda.synchronize()
-        e2e_ms = allreduce(1e3 * (time.perf_counter() - t0) / args.steps, MAX)
-        pipelined = True
+        streamed_ms = allreduce(1e3 * (time.perf_counter() - t0) / args.steps, MAX)
         vol.Check()
+        # both modes are the public API; the line reports the faster one as the end-to-end figure and keeps the other next to it
+        if streamed_ms < serial_ms:
+            e2e_ms, pipelined = streamed_ms, True
     if not slabs:
         # The same K steps through the streaming entry points: step i+1's volume is copied H2D on the upload stream while step i
         # computes, frame i is copied D2H on the download stream while step i+1 computes. Every step still uploads its own input
@@ -574,6 +576,7 @@ def run_ours(args) -> int:
     frames = 1 if slabs else world_size
     e2e = {"value": all_steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mray-steps/s", "h2d_bytes_per_step": int(n) ** 3 * frames,
            "d2h_bytes_per_step": H * W * 16 * frames, "ms_per_step": e2e_ms, "serial_ms_per_step": serial_ms,
+           "streamed_ms_per_step": streamed_ms if slabs else e2e_ms,
            "pinned_copy_GBps": {"h2d": h2d_gbps, "d2h": d2h_gbps},
            "mode": (("streaming API: the H2D copy of step i+1 and the D2H copy of frame i overlap the compute of their neighbours "
                      "(tbrm_upload_volume_async / tbrm_present_volume / tbrm_raymarch_lit_to_host_async)") if not slabs else

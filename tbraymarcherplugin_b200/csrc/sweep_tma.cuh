@@ -87,6 +87,7 @@ struct TmaParams {
     long long* dbg;         // TBRM_CHAIN_TIMERS builds: per-warp section timers of the chain kernel
     unsigned int* error;    // device word set when a wait on another tile / launch timed out
     unsigned long long timeout_ns;
+    unsigned int poll_limit;  // unsharded launches: polls after which a wait on another tile gives up (timeout_ns / 256 ns)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
@@ -734,6 +735,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     }
     P.timeout_ns = (unsigned long long) (r.slab_timeout_ms > 0 ? r.slab_timeout_ms : 4000) * 1000000ull;
     P.error = use_slab ? arena_word(r.arena, 2) : r.sweep_err;
+    P.poll_limit = (unsigned int) std::min<unsigned long long>(P.timeout_ns / 256ull, 0x7fffffffull);
     if (ws) {
         // ---- occlusion_kernel: T = 1 - occlusion for this GPU's share of the pass (an ordinary launch: no inter-block dependency) ----
         const int nblocks = (ns + kSB - 1) / kSB;

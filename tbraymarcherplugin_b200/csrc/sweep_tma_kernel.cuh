@@ -247,11 +247,18 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     __syncthreads();
     const int ndown = s_ndown;
     // give up on an exchange that does not complete (a peer that died or was never launched): flag it, stop waiting
+    // Every wait on another tile / launch gives up: waits of partial launches (another GPU may never answer) by the clock, waits inside an
+    // unsharded launch by counting polls (an L2 round trip takes well over 256 ns, so poll_limit = timeout / 256 ns bounds the wait by a few
+    // timeouts without a timer read or a call in the loop — round 1's unsharded waits had no bound at all)
     auto timed_out = [&](unsigned long long t0) {
-        if (global_timer_ns() - t0 < P.S.timeout_ns) return false;
+        if (global_timer_ns() - t0 < P.timeout_ns) return false;
         s_abort = 1;
-        atomicExch(P.S.error, 1u);
+        atomicExch(P.error, 1u);
         return true;
+    };
+    auto give_up = [&]() {
+        s_abort = 1;
+        atomicExch(P.error, 1u);
     };
     if (SLAB && k_begin > 0 && P.S.zin != nullptr) {
         // the slices before k_begin belong to the upstream slab: its last slice (tag k_begin) is our "slice k_begin - 1"
@@ -455,7 +462,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 for (int i = 0; i < kHaloPerThread; ++i)
                     if (halo_fp[i] >= 0) {
                         if (!SLAB) {
-                            while ((unsigned int) (hv[i] >> 32) != want_tag) hv[i] = ld_relaxed_u64(ring + (rd_slot + (unsigned int) halo_ring[i]));
+                            unsigned int polls = 0;
+                            while ((unsigned int) (hv[i] >> 32) != want_tag && ++polls <= P.poll_limit) hv[i] = ld_relaxed_u64(ring + (rd_slot + (unsigned int) halo_ring[i]));
+                            if (polls > P.poll_limit) give_up();
                         } else if ((unsigned int) (hv[i] >> 32) != want_tag) {
                             const unsigned long long t0 = global_timer_ns();
                             unsigned int polls = 0;
@@ -475,14 +484,20 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                     unsigned int polls = 0;
                     while ((unsigned int) (v >> 32) != want_tag && !(SLAB && s_abort)) {
                         v = SLAB ? ld_relaxed_sys_u64(cell) : ld_relaxed_u64(cell);
-                        if (SLAB && (++polls & 255u) == 0 && timed_out(t0)) break;
+                        ++polls;
+                        if (SLAB ? ((polls & 255u) == 0 && timed_out(t0)) : polls > P.poll_limit) {
+                            if (!SLAB) give_up();
+                            break;
+                        }
                     }
                     fp_cur[f] = __uint_as_float((unsigned int) v);
                 }
             }
             if (probe) {
                 const unsigned int need = (unsigned) (k + 4 - kRingDepth);
-                while (pv < need && !(SLAB && s_abort)) pv = ld_relaxed_u32(P.flags + (size_t) s_down[tid] * kFlagStride);
+                unsigned int polls = 0;
+                while (pv < need && !(SLAB && s_abort) && ++polls <= P.poll_limit) pv = ld_relaxed_u32(P.flags + (size_t) s_down[tid] * kFlagStride);
+                if (polls > P.poll_limit) give_up();
             }
             __syncthreads();
             // progress counter for back-pressure: every read of slice k-1 by this tile is done

@@ -77,6 +77,9 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+_PERM_CACHE: dict = {}  # (height, world, block_rows, device) -> source row of every frame row in the all-gathered buffer
+
+
 def gather_interleaved_rows(local_rows, height: int, block_rows: int, dst: int = 0, group=None):
     """Gather the compacted row blocks every rank rendered into the full frame on rank `dst` (None elsewhere).
 
@@ -94,6 +97,23 @@ def gather_interleaved_rows(local_rows, height: int, block_rows: int, dst: int =
     if send.shape[0] < pad:
         send = torch.cat([send, send.new_zeros((pad - send.shape[0],) + tuple(send.shape[1:]))], 0)
     send = send.contiguous()
+    if send.is_cuda:
+        # one collective + one gather kernel (the per-rank gather / index_copy loop cost 0.43 ms at 8 GPUs for a 33 MB frame: launch latency).
+        # Every rank receives every share (31 MB over NVSwitch: ~0.05 ms); only `dst` assembles the frame.
+        allbuf = send.new_empty((world * pad,) + tuple(send.shape[1:]))
+        dist.all_gather_into_tensor(allbuf, send, group=group)
+        if rank != dst:
+            return None
+        key = (height, world, block_rows, str(send.device))
+        perm = _PERM_CACHE.get(key)
+        if perm is None:
+            src_of_row = [0] * height
+            for r in range(world):
+                for j, row in enumerate(rows_of_rank(height, r, world, block_rows)):
+                    src_of_row[row] = r * pad + j
+            perm = torch.as_tensor(src_of_row, device=send.device)
+            _PERM_CACHE[key] = perm
+        return allbuf.index_select(0, perm)
     bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
     dist.gather(send, bufs, dst=dst, group=group)
     if rank != dst:
