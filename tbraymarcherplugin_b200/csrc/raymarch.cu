@@ -236,7 +236,6 @@ __global__ void __launch_bounds__(256) raymarch_lit_kernel(const MarchUniforms U
 //     test one byte load —, and a sample with zero opacity adds exactly 0 to every channel, so its light-volume fetch
 //     is skipped. The march position still advances by the same sequence of fp32 adds.
 constexpr int kBrick = 8;  // brick edge in voxels
-constexpr bool kRaymarchV2Default = false;  // raymarch_fast2_kernel becomes the default once validated on the GPU (TBRM_RAYMARCH_V2=1 forces it)
 
 struct FastUniforms {
     MarchUniforms M;
@@ -318,6 +317,44 @@ __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t
         b000 = __ldg(r00 + xs0), b100 = __ldg(r00 + xs1), b010 = __ldg(r01 + xs0), b110 = __ldg(r01 + xs1);
         b001 = __ldg(r10 + xs0), b101 = __ldg(r10 + xs1), b011 = __ldg(r11 + xs0), b111 = __ldg(r11 + xs1);
     }
+    // The light taps are requested NOW, before the data taps are even decoded: their addresses depend on the position only, and the chain
+    // data taps -> interpolation -> window -> TF -> pow in between (~150 cycles of dependent arithmetic) hides their latency. Round 2's
+    // profile has the march waiting on loads (long scoreboard 4.5 warps per issue-active cycle, a fifth of it on these eight taps). A
+    // sample the window rejects, or whose opacity is exactly 0, has fetched them for nothing (L1 hits, 97 %): same values either way.
+    float q000, q100, q010, q110, q001, q101, q011, q111;
+    float gx, gy, gz;
+    {
+        int li, lj, lk;
+        if (ADDR32) {
+            axis_taps_bounded(saturatef(p.x), F.fldims[0], li, gx);
+            axis_taps_bounded(saturatef(p.y), F.fldims[1], lj, gy);
+            axis_taps_bounded(saturatef(p.z), F.fldims[2], lk, gz);
+        } else {
+            axis_taps(saturatef(p.x), U.ldims[0], li, gx);
+            axis_taps(saturatef(p.y), U.ldims[1], lj, gy);
+            axis_taps(saturatef(p.z), U.ldims[2], lk, gz);
+        }
+        const int LX = U.ldims[0], LY = U.ldims[1], LZ = U.ldims[2];
+        const int x0 = li < 0 ? li + LX : li, x1 = li + 1 >= LX ? li + 1 - LX : li + 1;
+        const int y0 = lj < 0 ? lj + LY : lj, y1 = lj + 1 >= LY ? lj + 1 - LY : lj + 1;
+        const int z0 = lk < 0 ? lk + LZ : lk, z1 = lk + 1 >= LZ ? lk + 1 - LZ : lk + 1;
+        if (ADDR32) {
+            const unsigned int SX = (unsigned int) LX, SXY = SX * (unsigned int) LY;
+            const unsigned int zx00 = (unsigned int) z0 * SXY + (unsigned int) x0, zx01 = (unsigned int) z0 * SXY + (unsigned int) x1;
+            const unsigned int zx10 = (unsigned int) z1 * SXY + (unsigned int) x0, zx11 = (unsigned int) z1 * SXY + (unsigned int) x1;
+            const unsigned int ya = (unsigned int) y0 * SX, yb = (unsigned int) y1 * SX;
+            q000 = __ldg(light + (ya + zx00)), q100 = __ldg(light + (ya + zx01)), q010 = __ldg(light + (yb + zx00)), q110 = __ldg(light + (yb + zx01));
+            q001 = __ldg(light + (ya + zx10)), q101 = __ldg(light + (ya + zx11)), q011 = __ldg(light + (yb + zx10)), q111 = __ldg(light + (yb + zx11));
+        } else {
+            const size_t SX = LX, SXY = (size_t) LX * LY;
+            const float* q00 = light + SX * y0 + SXY * z0;
+            const float* q01 = light + SX * y1 + SXY * z0;
+            const float* q10 = light + SX * y0 + SXY * z1;
+            const float* q11 = light + SX * y1 + SXY * z1;
+            q000 = __ldg(q00 + x0), q100 = __ldg(q00 + x1), q010 = __ldg(q01 + x0), q110 = __ldg(q01 + x1);
+            q001 = __ldg(q10 + x0), q101 = __ldg(q10 + x1), q011 = __ldg(q11 + x0), q111 = __ldg(q11 + x1);
+        }
+    }
     const float c00 = lerpf(decode_u8_exact(b000), decode_u8_exact(b100), fx);
     const float c01 = lerpf(decode_u8_exact(b010), decode_u8_exact(b110), fx);
     const float c10 = lerpf(decode_u8_exact(b001), decode_u8_exact(b101), fx);
@@ -334,38 +371,8 @@ __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t
     float sx = lerpf(a.x, b.x, tf), sy = lerpf(a.y, b.y, tf), sz = lerpf(a.z, b.z, tf);
     // light volume: trilinear, wrap addressing, at saturate(p)
     {
-        int li, lj, lk;
-        float gx, gy, gz;
-        if (ADDR32) {
-            axis_taps_bounded(saturatef(p.x), F.fldims[0], li, gx);
-            axis_taps_bounded(saturatef(p.y), F.fldims[1], lj, gy);
-            axis_taps_bounded(saturatef(p.z), F.fldims[2], lk, gz);
-        } else {
-            axis_taps(saturatef(p.x), U.ldims[0], li, gx);
-            axis_taps(saturatef(p.y), U.ldims[1], lj, gy);
-            axis_taps(saturatef(p.z), U.ldims[2], lk, gz);
-        }
-        const int LX = U.ldims[0], LY = U.ldims[1], LZ = U.ldims[2];
-        const int x0 = li < 0 ? li + LX : li, x1 = li + 1 >= LX ? li + 1 - LX : li + 1;
-        const int y0 = lj < 0 ? lj + LY : lj, y1 = lj + 1 >= LY ? lj + 1 - LY : lj + 1;
-        const int z0 = lk < 0 ? lk + LZ : lk, z1 = lk + 1 >= LZ ? lk + 1 - LZ : lk + 1;
-        float d00, d01, d10, d11;
-        if (ADDR32) {
-            const unsigned int SX = (unsigned int) LX, SXY = SX * (unsigned int) LY;
-            const unsigned int zx00 = (unsigned int) z0 * SXY + (unsigned int) x0, zx01 = (unsigned int) z0 * SXY + (unsigned int) x1;
-            const unsigned int zx10 = (unsigned int) z1 * SXY + (unsigned int) x0, zx11 = (unsigned int) z1 * SXY + (unsigned int) x1;
-            const unsigned int ya = (unsigned int) y0 * SX, yb = (unsigned int) y1 * SX;
-            d00 = lerpf(__ldg(light + (ya + zx00)), __ldg(light + (ya + zx01)), gx), d01 = lerpf(__ldg(light + (yb + zx00)), __ldg(light + (yb + zx01)), gx);
-            d10 = lerpf(__ldg(light + (ya + zx10)), __ldg(light + (ya + zx11)), gx), d11 = lerpf(__ldg(light + (yb + zx10)), __ldg(light + (yb + zx11)), gx);
-        } else {
-            const size_t SX = LX, SXY = (size_t) LX * LY;
-            const float* q00 = light + SX * y0 + SXY * z0;
-            const float* q01 = light + SX * y1 + SXY * z0;
-            const float* q10 = light + SX * y0 + SXY * z1;
-            const float* q11 = light + SX * y1 + SXY * z1;
-            d00 = lerpf(__ldg(q00 + x0), __ldg(q00 + x1), gx), d01 = lerpf(__ldg(q01 + x0), __ldg(q01 + x1), gx);
-            d10 = lerpf(__ldg(q10 + x0), __ldg(q10 + x1), gx), d11 = lerpf(__ldg(q11 + x0), __ldg(q11 + x1), gx);
-        }
+        const float d00 = lerpf(q000, q100, gx), d01 = lerpf(q010, q110, gx);
+        const float d10 = lerpf(q001, q101, gx), d11 = lerpf(q011, q111, gx);
         const float l = lerpf(lerpf(d00, d01, gy), lerpf(d10, d11, gy), gz);
         sx = sx * l, sy = sy * l, sz = sz * l;
     }
@@ -465,7 +472,7 @@ __device__ __forceinline__ void axis_taps_raw(float u, int N, int& i0, float& f)
 }
 
 template <bool CLIP>
-__global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
+__global__ void __launch_bounds__(256, 5) raymarch_fast2_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
                                                              const float* __restrict__ light, const float4* __restrict__ tf,
                                                              float4* __restrict__ out, unsigned long long* __restrict__ steps_out) {
     const MarchUniforms& U = F.M;
@@ -518,12 +525,12 @@ __global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms 
             const bool interior = ((unsigned) i0 - 1u) < (unsigned) max(X - 2, 0) && ((unsigned) j0 - 1u) < (unsigned) max(Y - 2, 0) &&
                                   ((unsigned) k0 - 1u) < (unsigned) max(Z - 2, 0);
             if (!interior || !F.same_dims) {  // the one-voxel shell, half-resolution light volumes: the general sampler
-                fast_sample<false>(F, data, light, s_tf, cur, ssw, acc);
+                fast_sample<true>(F, data, light, s_tf, cur, ssw, acc);
             } else {
                 if (F.bricks) {
                     const int m = __ldg(F.bricks + (i0 >> 3) + F.bdims[0] * ((j0 >> 3) + F.bdims[1] * (k0 >> 3)));
                     if (m <= F.skip_byte) {  // tap indices >= 1 make the weights exact and < 1: the sample is exactly (0,0,0,0)
-                        if (!CLIP) {
+                        if (!CLIP && margin >= 0.0f) {
                             // positions i+1 .. i+n stay inside this brick: q + t*dq in [8b + margin, 8b + 8 - margin) on every axis
                             const float qx = (float) i0 + fx, qy = (float) j0 + fy, qz = (float) k0 + fz;
                             const float bx = (float) (i0 & ~7), by = (float) (j0 & ~7), bz = (float) (k0 & ~7);
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(256) raymarch_fast2_kernel(const FastUniforms 
                                       U.clip_dir[1], U.clip_dir[2]);
                 clipped = cd <= 0.0f;
             }
-            if (!clipped) fast_sample<false>(F, data, light, s_tf, cur, 100.0f * fin, acc);
+            if (!clipped) fast_sample<true>(F, data, light, s_tf, cur, 100.0f * fin, acc);
         }
         out[(size_t) lr * U.cam.width + ix] = acc;
     }
@@ -817,8 +824,14 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
         for (int k = 0; k < 3; ++k) F.fddims[k] = (float) r.ddims[k], F.fldims[k] = (float) r.ldims[k];
         static const bool addr64_forced = [] { const char* e = getenv("TBRM_RAYMARCH_ADDR64"); return e && e[0] == '1'; }();
         const bool addr32 = r.options.reserved[1] != 2 && !addr64_forced && r.data_voxels() < (1ull << 31) && r.light_voxels() < (1ull << 31);
-        static const bool v2_default = [] { const char* e = getenv("TBRM_RAYMARCH_V2"); return e ? e[0] == '1' : kRaymarchV2Default; }();
-        const bool v2 = (r.options.reserved[1] == 3 || (r.options.reserved[1] == 0 && v2_default)) && r.data_voxels() < (1ull << 31);
+        // Kernel choice (every form returns the same bits). Default: the second-generation kernel WITHOUT leaping — measured on a B200 in
+        // round 2 (cfg2 frame / the same frame of a 256^3 volume): first generation 4.61 / 4.00 ms, second generation with leaps 5.00 / 3.28 ms
+        // (13 % fewer instructions, but the leap loop diverges: 27.5 active lanes instead of 31.4, issue slots 60 % instead of 74 %), second
+        // generation without leaps 4.53 / 3.24 ms. TBRM_RAYMARCH_V2 = 0 / 1 / 2 or reserved[1] = 5 / 3 / 4 select first generation / leaps / no leaps.
+        static const int v2_env = [] { const char* e = getenv("TBRM_RAYMARCH_V2"); return e ? atoi(e) : 2; }();
+        const int form = r.options.reserved[1] == 3 ? 1 : (r.options.reserved[1] == 4 ? 2 : (r.options.reserved[1] == 5 ? 0 : (r.options.reserved[1] == 0 ? v2_env : 0)));
+        const bool v2 = form != 0 && r.data_voxels() < (1ull << 31);
+        if (form == 2) F.leap_margin = -1.0f;  // interior fast path only, no leaps
         const bool noclip = clip_never_rejects(clip_center, clip_dir);
         if (v2 && noclip)
             raymarch_fast2_kernel<false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);

@@ -18,6 +18,9 @@ SLAB_TIMEOUT_MS = int(os.environ.get("TBRM_TEST_SLAB_TIMEOUT_MS", "1500"))  # th
 WORLDS = {"identity": synth.identity_world, "scaled_rotated": synth.scaled_rotated_world, "clipped": synth.clipped_world}
 
 
+_STREAM_OWNERS = []
+
+
 def make_res(data, sweep_impl=2, band_rows=0):
     Z, Y, X = data.shape
     res = URaymarchUtils.InitializeRaymarchResources((X, Y, Z), FMT_G8, bLightVolume32Bit=True)
@@ -53,6 +56,13 @@ def virtual_ranks(data, nranks, band_rows=0):
         _capi.check(lib.tbrm_slab_configure(res.handle, C.byref(slab)))
         _capi.check(lib.tbrm_slab_set_timeout_ms(res.handle, SLAB_TIMEOUT_MS))
         ranks.append((res, z0.value, z1.value))
+    # All virtual ranks share ONE stream. On separate streams their cooperative launches run concurrently on the one GPU, and a downstream
+    # slab's launch (spinning on its inbox) can take the SM slots an upstream launch still needs for its last tiles: neither finishes until
+    # the exchange timeout fires (seen as a 1-in-18 flake of the 8-rank case in round 2). Real ranks own a GPU each (tests/test_gpu_multi.py).
+    shared_stream = lib.tbrm_stream(ranks[0][0].handle)
+    _STREAM_OWNERS.append(ranks[0][0])  # the stream's owner must outlive every resource set that borrows it
+    for res, _, _ in ranks[1:]:
+        _capi.check(lib.tbrm_set_stream(res.handle, C.c_void_p(shared_stream)))
     arenas = []
     for res, _, _ in ranks:
         p, n = C.c_void_p(), C.c_size_t()

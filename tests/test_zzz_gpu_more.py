@@ -265,14 +265,15 @@ def test_lit_march_with_64_bit_tap_addressing_still_matches_oracle(dims):
             vol.add_dir_light(l, True, world)
         cam = synth.benchmark_camera(40, 24, jitter=True, frame=2)
         ref, ref_steps = vol.raymarch_lit(cam, world, 33.0)
-        for flag in (0, 2):
+        for flag in (0, 2, 3, 4, 5):  # default (second generation without leaps), 64-bit addressing, leaps, no leaps, first generation (ADDR32)
             URaymarchUtils.SetOptions(res, debug_flags=(0, flag))
             rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 33.0)
             assert steps == ref_steps and np.array_equal(rgba, ref), (dims, flag)
         res.release()
 
 
-@pytest.mark.parametrize("px_flag", [16, 32, 48])  # bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread in sweep_tma_kernel, automatic
+# bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread, automatic; bit 6: the second kernel generation (occlusion kernel + chain kernel)
+@pytest.mark.parametrize("px_flag", [16, 32, 48, 64 + 16, 64 + 32])
 @pytest.mark.parametrize("dims", [(64, 48, 40), (80, 24, 16), (128, 16, 8)])
 def test_tma_sweep_with_one_and_two_pixels_per_thread(dims, px_flag):
     """The TMA-staged sweep has a one-pixel-per-thread form (tile 32 x 8) for launches that cannot fill the SMs next to the two-pixel form
