@@ -303,12 +303,13 @@ static void window_cut_byte(const Windowing& w, bool allow, unsigned int& mode, 
         mode = 2, add = (unsigned) (255 - lo) * 0x010101u;
 }
 
-static cudaError_t upload(tbrm_resources& r, const void* src, size_t bytes, size_t& off, const void** dptr) {
-    off = (off + 15) & ~(size_t) 15;
+// the per-pass sampler tables travel as ONE host-to-device copy: they are packed into a host staging vector first (eleven small copies per
+// pass were ~0.1 ms of host time — nothing on one GPU, where the kernels run for milliseconds, but a sixth of the step on eight)
+static void pack(std::vector<unsigned char>& staging, const tbrm_resources& r, const void* src, size_t bytes, const void** dptr) {
+    const size_t off = (staging.size() + 15) & ~(size_t) 15;
+    staging.resize(off + bytes);
+    memcpy(staging.data() + off, src, bytes);
     *dptr = (const char*) r.tables + off;
-    cudaError_t e = cudaMemcpyAsync((char*) r.tables + off, src, bytes, cudaMemcpyHostToDevice, r.stream);
-    off += bytes;
-    return e;
 }
 
 static const void* tma_kernel(int axis, bool clip, bool slab, int px) {
@@ -517,8 +518,15 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     if (!get_encode()) return not_handled("!get_encode()");
     int dev = r.device, sms = 0, coop = 0;
     cudaError_t e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev)) != cudaSuccess) return e;
+    {   // device attributes are queried once per device (host time per pass matters once the kernels are short: 8-GPU slabs)
+        static thread_local int cached_dev = -1, cached_sms = 0, cached_coop = 0;
+        if (cached_dev != dev) {
+            if ((e = cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+            if ((e = cudaDeviceGetAttribute(&cached_coop, cudaDevAttrCooperativeLaunch, dev)) != cudaSuccess) return e;
+            cached_dev = dev;
+        }
+        sms = cached_sms, coop = cached_coop;
+    }
     if (!coop) return not_handled("!coop");
 
     HostTabs T;
@@ -641,12 +649,32 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int threads = ws ? kChThreads : kTmaThreads;
     const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : tma_kernel(u.axis, clip, false, px);
     const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : tma_kernel(u.axis, clip, true, px);
-    for (const void* k : {kern_plain, kern_slab})
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) {
-            cudaGetLastError();
-            return not_handled("shared memory per block");
+    {   // the shared-memory attribute and the occupancy of a (kernel, shared-memory size) pair are set / queried once
+        struct Known {
+            const void* kern;
+            size_t smem;
+            int dev, per_sm;
+        };
+        static thread_local std::vector<Known> known;
+        for (const void* k : {kern_plain, kern_slab}) {
+            const Known* hit = nullptr;
+            for (const Known& kn : known)
+                if (kn.kern == k && kn.smem == smem && kn.dev == dev) hit = &kn;
+            if (!hit) {
+                if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) {
+                    cudaGetLastError();
+                    return not_handled("shared memory per block");
+                }
+                int occ = 0;
+                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem)) != cudaSuccess) return e;
+                // another size may have been set for this kernel in between: drop stale entries of the kernel
+                known.erase(std::remove_if(known.begin(), known.end(), [&](const Known& kn) { return kn.kern == k && kn.dev == dev; }), known.end());
+                known.push_back({k, smem, dev, occ});
+                hit = &known.back();
+            }
+            if (k == kern_slab) per_sm = hit->per_sm;
         }
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_slab, threads, smem)) != cudaSuccess) return e;
+    }
     int cap_rows = (int) std::min<long long>((long long) sms * per_sm / P.ntx, 1 << 20);  // tile rows of one co-resident wave
     if (r.options.reserved[2] > 0) cap_rows = std::min(cap_rows, r.options.reserved[2]);      // test hook: force banding on small planes
     if (cap_rows < 1) return not_handled("cap_rows < 1");
@@ -716,15 +744,20 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         r.tables_bytes = need;
     }
     // the previous pass may still be reading the tables: stream order makes the async copies wait for it
-    size_t off = 0;
-    for (int a = 0; a < 3; ++a) {
-        if ((e = upload(r, T.S[a].data(), T.S[a].size() * 4, off, (const void**) &P.A.ax[a].S)) != cudaSuccess) return e;
-        if ((e = upload(r, T.f[a].data(), T.f[a].size() * 4, off, (const void**) &P.A.ax[a].f)) != cudaSuccess) return e;
-        if ((e = upload(r, T.meta[a].data(), T.meta[a].size() * 8, off, (const void**) &P.A.ax[a].meta)) != cudaSuccess) return e;
+    {
+        static thread_local std::vector<unsigned char> staging;
+        staging.clear();
+        for (int a = 0; a < 3; ++a) {
+            pack(staging, r, T.S[a].data(), T.S[a].size() * 4, (const void**) &P.A.ax[a].S);
+            pack(staging, r, T.f[a].data(), T.f[a].size() * 4, (const void**) &P.A.ax[a].f);
+            pack(staging, r, T.meta[a].data(), T.meta[a].size() * 8, (const void**) &P.A.ax[a].meta);
+        }
+        pack(staging, r, T.bx.data(), T.bx.size() * 8, (const void**) &P.A.bx);
+        pack(staging, r, T.by.data(), T.by.size() * 8, (const void**) &P.A.by);
+        if (staging.size() > r.tables_bytes) return cudaErrorInvalidValue;
+        // a pageable-memory async copy returns once the source has been staged, so the vector may be reused by the next pass
+        if ((e = cudaMemcpyAsync(r.tables, staging.data(), staging.size(), cudaMemcpyHostToDevice, r.stream)) != cudaSuccess) return e;
     }
-    if ((e = upload(r, T.bx.data(), T.bx.size() * 8, off, (const void**) &P.A.bx)) != cudaSuccess) return e;
-    if ((e = upload(r, T.by.data(), T.by.size() * 8, off, (const void**) &P.A.by)) != cudaSuccess) return e;
-    // pageable-memory async copies return once the source has been staged, so T may go out of scope after this call
     P.ring = (float*) r.ring;
     P.flags = r.flags;
     memset(&P.S, 0, sizeof(P.S));
