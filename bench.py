@@ -127,8 +127,9 @@ def workload_config(n_gpus: int, slabs: bool = True) -> dict:
         shard = "1 volume, 1 GPU"
     elif slabs:
         shard = (f"ONE volume Z-slab sharded over {n_gpus} GPUs: data volume replicated (NCCL all-gather of the uploaded slabs), light sweep per "
-                 "slab with in-kernel NVLink peer-store halo exchange, NCCL all-gather of the light slabs, frame rendered in interleaved 8-row "
-                 "blocks and gathered on rank 0")
+                 "slab with in-kernel NVLink peer-store halo exchange, light slabs gathered by NCCL all-gather (2 GPUs: pushed into the peer's "
+                 "volume by TMA stores from the sweep's last pass instead, --push-gather), frame rendered in interleaved 8-row blocks and "
+                 "gathered on rank 0")
     else:
         shard = f"{n_gpus} independent volumes, one per GPU, no collective"
     return {
@@ -341,9 +342,14 @@ def run_ours(args) -> int:
     def sweep():
         URaymarchUtils.ClearResourceLightVolumes(res, 0.0)  # a sharded volume clears the slab it owns
         sweep_stats.clear()
-        for l in lights:
+        for i, l in enumerate(lights):
             st = FSweepStats()
-            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
+            if slabs:
+                # the last light of the reset pushes its finished bricks into every rank's light volume from inside the sweep kernel
+                # (push-gather): gather_light() then only synchronises instead of all-gathering the slabs
+                assert vol.AddDirLight(l, True, world, stats=st, push=(args.push_gather and i == len(lights) - 1))
+            else:
+                assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
             sweep_stats.append(st)
 
     def gather_light():
@@ -437,7 +443,11 @@ def run_ours(args) -> int:
         return allreduce(timer_end() / reps, MAX)
 
     sweep_ms = stage(sweep)
-    gather_ms = stage(gather_light) if slabs else 0.0
+    def gather_stage():  # what the step does after the sweep: a one-word all-reduce after a pushing sweep, else the all-gather of the slabs
+        vol._pushed = bool(args.push_gather)
+        vol.GatherLightVolume()
+
+    gather_ms = stage(gather_stage) if slabs else 0.0
     ray_ms = stage(lambda: raymarch(count=False, gather=False))
     frame_gather_ms = (stage(lambda: raymarch(count=False, gather=True)) - ray_ms) if slabs else 0.0
     # one axis pass of the fused sweep on its own (L4 = a single Z pass), the sweep's dominant kernel. On a sharded volume the
@@ -705,6 +715,10 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the (untimed) digest comparison with the reference shaders' output")
+    ap.add_argument("--push-gather", default="auto", choices=["auto", "on", "off"],
+                    help="N > 1: push the finished light bricks into every rank's volume from the sweep's last pass (TMA stores over NVLink) instead "
+                         "of an NCCL all-gather of the slabs. auto = on for 2 GPUs only: measured on B200s, the push wins at N = 2 (step 7.71 -> "
+                         "7.39 ms) and loses at N = 8 (5.31 -> 8.27 ms: seven unicast copies per brick against NCCL's switch multicast)")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the extra 1024^3 sweep measurement (scale_cfg4)")
     ap.add_argument("--trace", action="store_true", help="print progress lines to stderr (debugging multi-GPU runs)")
     ap.add_argument("--sharding", default="slabs", choices=["slabs", "volumes"],
@@ -724,6 +738,8 @@ def main() -> int:
         return run_reference(args)
     args.steps = args.steps if args.steps is not None else 20
     args.warmup = args.warmup if args.warmup is not None else 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.push_gather = args.push_gather == "on" or (args.push_gather == "auto" and world == 2)
     return run_ours(args)
 
 

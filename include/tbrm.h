@@ -258,6 +258,16 @@ tbrm_status tbrm_slab_open_peer(tbrm_resources* res, int side, const void* handl
 tbrm_status tbrm_slab_set_peer(tbrm_resources* res, int side, void* peer_arena_dptr);
 /* Clears the exchange arena and restarts the tag sequence. Call on every rank, between two barriers, with no sweep in
  * flight: after creating the peers' connections is not required, after TBRM_ERR_UNSUPPORTED "sequence used up" it is. */
+/* Push-gather (no reference counterpart: the reference is single-GPU). With the light volumes of all ranks mapped into each other
+ * (tbrm_slab_light_ipc_handle -> tbrm_slab_open_peer_light across processes, tbrm_slab_set_peer_light inside one) and
+ * tbrm_slab_push_light(res, 1), the LAST axis pass of every following tbrm_add_dir_light call stores each finished light brick into
+ * every other rank's volume as well (TMA stores over NVLink inside the sweep kernel): after the call's kernels have completed on all
+ * ranks, every rank holds the whole light volume and no all-gather of the slabs is needed. The light volume must be the library's
+ * own allocation (not tbrm_bind_light_volume_device). Enable it for the last light of a reset only: earlier pushes are wasted traffic. */
+tbrm_status tbrm_slab_light_ipc_handle(tbrm_resources* res, void* handle64);
+tbrm_status tbrm_slab_open_peer_light(tbrm_resources* res, int peer_rank, const void* handle64);
+tbrm_status tbrm_slab_set_peer_light(tbrm_resources* res, int peer_rank, void* peer_light_dptr);
+tbrm_status tbrm_slab_push_light(tbrm_resources* res, int enable);
 tbrm_status tbrm_slab_reset_comm(tbrm_resources* res);
 /* TBRM_ERR_CUDA if a slab exchange timed out since the last call (a neighbour died or ran different passes); synchronises. */
 tbrm_status tbrm_slab_check(tbrm_resources* res);

@@ -212,6 +212,10 @@ PROTOTYPES = {
     "tbrm_flush": (_I, [_P]),
     "tbrm_stream": (_P, [_P]),
     "tbrm_set_stream": (_I, [_P, _P]),
+    "tbrm_slab_light_ipc_handle": (_I, [_P, _P]),
+    "tbrm_slab_open_peer_light": (_I, [_P, C.c_int, _P]),
+    "tbrm_slab_set_peer_light": (_I, [_P, C.c_int, _P]),
+    "tbrm_slab_push_light": (_I, [_P, C.c_int]),
     "tbrm_timer_begin": (_I, [_P]),
     "tbrm_timer_end": (_I, [_P, C.POINTER(C.c_float)]),
     "tbrm_synth_volume_u8": (_I, [_I, _I, C.POINTER(C.c_int32), C.c_uint32, _P, _I]),

@@ -281,6 +281,8 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
     if (r->light && r->light_owned) cudaFree(r->light);
     for (int i = 0; i < 2; ++i)
         if (r->peer_arena[i] && r->peer_ipc[i]) cudaIpcCloseMemHandle(r->peer_arena[i]);
+    for (int i = 0; i <= tbrm_resources::kMaxPushPeers; ++i)
+        if (r->peer_light[i] && r->peer_light_ipc[i]) cudaIpcCloseMemHandle(r->peer_light[i]);
     if (r->arena) cudaFree(r->arena);
     if (r->change_scratch) cudaFree(r->change_scratch);
     if (r->tf) cudaFree(r->tf);
@@ -536,7 +538,10 @@ static tbrm_status add_dir_light_impl(tbrm_resources& r, const tbrm_dir_light& l
         SweepUniforms u;
         fill_uniforms(r, plan, i, u);
         u.sign = added ? 1.0f : -1.0f;
+        // push-gather (tbrm_slab_push_light): the call's last axis pass leaves final light values in every brick it stores
+        r.push_this_pass = r.push_light && only_pass < 0 && i == plan.add_passes - 1;
         tbrm_status s = run_pass(r, u, false, gpu_sync, stats);
+        r.push_this_pass = false;
         if (s != TBRM_OK) return s;
     }
     return TBRM_OK;
@@ -773,6 +778,51 @@ tbrm_status tbrm_slab_set_peer(tbrm_resources* r, int side, void* peer_arena_dpt
     tbrm_status s = drop_peer(r, i);
     if (s != TBRM_OK) return s;
     r->peer_arena[i] = peer_arena_dptr;
+    return TBRM_OK;
+}
+
+// ---- push-gather: every rank's light volume mapped into every other rank ----------------------------------------------------
+tbrm_status tbrm_slab_light_ipc_handle(tbrm_resources* r, void* handle64) {
+    TBRM_REQUIRE(r && handle64, "tbrm_slab_light_ipc_handle: null argument");
+    TBRM_REQUIRE(r->light && r->light_owned, "tbrm_slab_light_ipc_handle: the light volume must be the library's own allocation (an IPC handle names a whole allocation)");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    cudaIpcMemHandle_t h;
+    TBRM_CUDA(cudaIpcGetMemHandle(&h, r->light));
+    memcpy(handle64, &h, sizeof(h));
+    return TBRM_OK;
+}
+
+static tbrm_status drop_peer_light(tbrm_resources* r, int rank) {
+    if (r->peer_light[rank] && r->peer_light_ipc[rank]) TBRM_CUDA(cudaIpcCloseMemHandle(r->peer_light[rank]));
+    r->peer_light[rank] = nullptr, r->peer_light_ipc[rank] = false;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_open_peer_light(tbrm_resources* r, int peer_rank, const void* handle64) {
+    TBRM_REQUIRE(r && handle64 && peer_rank >= 0 && peer_rank <= tbrm_resources::kMaxPushPeers, "tbrm_slab_open_peer_light: bad argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    tbrm_status s = drop_peer_light(r, peer_rank);
+    if (s != TBRM_OK) return s;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    TBRM_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    r->peer_light[peer_rank] = p, r->peer_light_ipc[peer_rank] = true;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_set_peer_light(tbrm_resources* r, int peer_rank, void* peer_light_dptr) {
+    TBRM_REQUIRE(r && peer_rank >= 0 && peer_rank <= tbrm_resources::kMaxPushPeers, "tbrm_slab_set_peer_light: bad argument");
+    TBRM_CUDA(cudaSetDevice(r->device));
+    tbrm_status s = drop_peer_light(r, peer_rank);
+    if (s != TBRM_OK) return s;
+    r->peer_light[peer_rank] = peer_light_dptr;
+    return TBRM_OK;
+}
+
+tbrm_status tbrm_slab_push_light(tbrm_resources* r, int enable) {
+    TBRM_REQUIRE(r, "tbrm_slab_push_light: null argument");
+    r->push_light = enable != 0;
     return TBRM_OK;
 }
 

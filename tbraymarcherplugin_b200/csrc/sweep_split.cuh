@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(256) occlusion_kernel(const OccParams P, const
 template <int AXIS, bool SLAB, int PX>
 __global__ void __launch_bounds__(kChThreads, 4)
     sweep_chain_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
-                       const __grid_constant__ CUtensorMap scratch_map, const TmaParams P, const float4* __restrict__ tf) {
+                       const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ PushMaps push_maps, const TmaParams P,
+                     const float4* __restrict__ tf) {
     constexpr int PA = (AXIS == 0) ? 1 : 0, QA = (AXIS == 2) ? 1 : 2, SA = AXIS;
     constexpr int TW = 32 * PX, FPW = TW + 4;
     constexpr int CPX = 2 * PX;             // adjacent pixels of a thread
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kChThreads, 4)
     static_assert(PX == 1 || PX == 2, "tile width 32 or 64");
     static_assert(kSB == 4, "a pixel's slices of a block form one float4");
     static_assert(kChThreads * CPX == TW * kTH, "one thread per CPX pixels of the tile");
-    (void) data_map, (void) scratch_map, (void) tf;
+    (void) data_map, (void) scratch_map, (void) tf, (void) push_maps;
     const SweepUniforms& U = P.U;
     const int tx = U.td[0], ty = U.td[1], ns = U.td[2];
     const int tid = threadIdx.x;

@@ -62,6 +62,12 @@ enum { kModeAdd = 0,      // LightVolume += light * sign where |light| > 1e-3 (A
        kModeStore = 1,    // scratch volume = light (the removed light of a ChangeDirLight; light_map is the scratch volume's map)
        kModeCombine = 2 };// LightVolume += light - scratch where |light - scratch| > 1e-3 (the added light of a ChangeDirLight)
 
+// tensor maps of the OTHER ranks' light volumes (push-gather): the finished light brick is stored into them as well
+constexpr int kMaxPush = 15;
+struct alignas(64) PushMaps {
+    CUtensorMap m[kMaxPush];
+};
+
 struct TmaParams {
     SweepUniforms U;
     SlabParams S;
@@ -88,6 +94,7 @@ struct TmaParams {
     unsigned int* error;    // device word set when a wait on another tile / launch timed out
     unsigned long long timeout_ns;
     unsigned int poll_limit;  // unsharded launches: polls after which a wait on another tile gives up (timeout_ns / 256 ns)
+    int n_push;               // peers the light bricks are pushed to (0: none)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
@@ -335,9 +342,9 @@ static occlusion_fn occlusion_kernel_of(int axis, bool clip, int px) {
 }
 
 static cudaError_t tma_launch(tbrm_resources& r, const void* kern, int threads, const CUtensorMap& lm, const CUtensorMap& dm, const CUtensorMap& sm,
-                              const TmaParams& P, int ntiles, size_t smem) {
+                              const PushMaps& pm, const TmaParams& P, int ntiles, size_t smem) {
     const float4* tf = r.tf;
-    void* args[] = {(void*) &lm, (void*) &dm, (void*) &sm, (void*) &P, (void*) &tf};
+    void* args[] = {(void*) &lm, (void*) &dm, (void*) &sm, (void*) &pm, (void*) &P, (void*) &tf};
     return cudaLaunchCooperativeKernel(kern, dim3(ntiles), dim3(threads), args, smem, r.stream);
 }
 
@@ -604,6 +611,20 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     if (!make_map3(&sm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeCombine ? r.change_scratch : r.light, ldims, lbox))
         return not_handled("tensor map of the scratch volume");
     P.mode = mode;
+    // push-gather: the same box over every other rank's light volume (the brick that updates the LIGHT volume: add / combine launches)
+    static thread_local PushMaps pm;
+    P.n_push = 0;
+    if (r.push_this_pass && mode != kModeStore && r.slab.nranks > 1) {
+        for (int pr = 0; pr < r.slab.nranks; ++pr) {
+            if (pr == r.slab.rank) continue;
+            if (!r.peer_light[pr] || P.n_push >= kMaxPush) {
+                set_last_error("push-gather: the light volumes of all ranks must be connected (tbrm_slab_open_peer_light / tbrm_slab_set_peer_light)");
+                return cudaErrorNotSupported;
+            }
+            if (!make_map3(&pm.m[P.n_push], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, r.peer_light[pr], ldims, lbox)) return not_handled("tensor map of a peer light volume");
+            ++P.n_push;
+        }
+    }
     // light SMEM strides: box is stored with native x fastest, then y, then z
     {
         const int str[3] = {1, lbox[0], lbox[0] * lbox[1]};
@@ -825,7 +846,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     if (!use_slab) {
         r.pass_seq = P.epoch;
         if ((e = cudaMemsetAsync(r.flags, 0, flag_words * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
-        if ((e = tma_launch(r, kern_plain, threads, lm, dm, sm, P, ntiles, smem)) != cudaSuccess) return e;
+        if ((e = tma_launch(r, kern_plain, threads, lm, dm, sm, pm, P, ntiles, smem)) != cudaSuccess) return e;
         count_launch();
         *launches += 1;
         *handled = true;
@@ -895,7 +916,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         S.error = err_word;
         S.timeout_ns = timeout_ns;
         if ((e = cudaMemsetAsync(r.flags, 0, (size_t) ntiles * kFlagStride * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
-        if ((e = tma_launch(r, kern_slab, threads, lm, dm, sm, P, S.tile_rows * P.ntx, smem)) != cudaSuccess) return e;
+        if ((e = tma_launch(r, kern_slab, threads, lm, dm, sm, pm, P, S.tile_rows * P.ntx, smem)) != cudaSuccess) return e;
         count_launch();
         *launches += 1;
     }

@@ -84,7 +84,8 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 template <int AXIS, bool CLIP, bool SLAB, int PX>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
-                     const __grid_constant__ CUtensorMap scratch_map, const TmaParams P, const float4* __restrict__ tf) {
+                     const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ PushMaps push_maps, const TmaParams P,
+                     const float4* __restrict__ tf) {
     constexpr int PA = (AXIS == 0) ? 1 : 0;  // native axis of p
     constexpr int QA = (AXIS == 2) ? 1 : 2;  // native axis of q
     constexpr int SA = AXIS;                 // native axis of s
@@ -553,6 +554,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
             int lc[3];
             lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;
             tma_store_3d(&light_map, lc[0], lc[1], lc[2], s_light);
+            // push-gather: the finished brick also goes into every other rank's light volume (NVLink), in the same bulk group — the transfer
+            // overlaps the sweep tile by tile, and no all-gather of the light slabs follows the sweep
+            for (int pr = 0; pr < P.n_push; ++pr) tma_store_3d(&push_maps.m[pr], lc[0], lc[1], lc[2], s_light);
             tma_commit();
         }
     }

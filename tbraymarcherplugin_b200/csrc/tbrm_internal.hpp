@@ -93,6 +93,13 @@ struct tbrm_resources {
     void* peer_arena[2] = {nullptr, nullptr};  // arenas of the slabs below / above (peer-mapped or same-process pointers)
     bool peer_ipc[2] = {false, false};
     int slab_timeout_ms = 0;       // 0 = default (4 s)
+    // push-gather: the light volumes of ALL ranks of a sharded volume (peer-mapped); the last axis pass of a sweep call may store every
+    // finished light brick into them as well, which replaces the trailing all-gather of the light slabs (tbrm_slab_push_light)
+    static constexpr int kMaxPushPeers = 15;
+    void* peer_light[kMaxPushPeers + 1] = {};
+    bool peer_light_ipc[kMaxPushPeers + 1] = {};
+    bool push_light = false;       // the caller asked for the next AddDirLight / ChangeDirLight call to push its last pass
+    bool push_this_pass = false;   // set by the pass driver for that last pass
 
     size_t light_voxels() const { return (size_t) ldims[0] * ldims[1] * ldims[2]; }
     size_t data_voxels() const { return (size_t) ddims[0] * ddims[1] * ddims[2]; }

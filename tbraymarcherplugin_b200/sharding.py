@@ -155,10 +155,20 @@ class FShardedRaymarchVolume:
         dev = torch.device("cuda", device)
         # collectives run on these tensors, the library computes on them: caller-owned, bound into the resource set
         self.data = torch.empty((Z, Y, X), dtype=torch.uint8, device=dev)
-        self.light = torch.zeros((Z, Y, X), dtype=torch.float32, device=dev)
+        # the light volume stays the library's own allocation (a CUDA IPC handle names a whole allocation: the peers map it for the
+        # push-gather); torch sees it through the CUDA array interface, for the NCCL all-gather and for reads
+        self.lib.tbrm_light_volume_device_ptr.restype = C.c_void_p
+        light_ptr = self.lib.tbrm_light_volume_device_ptr(self.res.handle)
+
+        class _LightView:
+            __cuda_array_interface__ = {"shape": (Z, Y, X), "typestr": "<f4", "data": (int(light_ptr), False), "version": 2}
+
+        self._light_view = _LightView()
+        with torch.cuda.device(dev):
+            self.light = torch.as_tensor(self._light_view, device=dev)
+            self.light.zero_()
         torch.cuda.synchronize(dev)
         _capi.check(self.lib.tbrm_bind_volume_device(self.res.handle, C.c_void_p(self.data.data_ptr())))
-        _capi.check(self.lib.tbrm_bind_light_volume_device(self.res.handle, C.c_void_p(self.light.data_ptr())))
         self.res.bIsInitialized = True
         slab = _capi.Slab(self.rank, self.world, self.z0, self.z1)
         _capi.check(self.lib.tbrm_slab_configure(self.res.handle, C.byref(slab)))
@@ -171,6 +181,17 @@ class FShardedRaymarchVolume:
             if 0 <= peer < self.world:
                 buf = (C.c_ubyte * 64).from_buffer_copy(handles[peer])
                 _capi.check(self.lib.tbrm_slab_open_peer(self.res.handle, side, buf))
+        # push-gather: every rank maps every other rank's light volume
+        lhandle = (C.c_ubyte * 64)()
+        _capi.check(self.lib.tbrm_slab_light_ipc_handle(self.res.handle, lhandle))
+        lhandles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(lhandles, bytes(lhandle), group=group)
+        for peer in range(self.world):
+            if peer != self.rank:
+                buf = (C.c_ubyte * 64).from_buffer_copy(lhandles[peer])
+                _capi.check(self.lib.tbrm_slab_open_peer_light(self.res.handle, peer, buf))
+        self._pushed = False  # the last sweep call pushed its light bricks to the peers: no all-gather needed
+        self._sync_word = torch.zeros(1, dtype=torch.float32, device=dev)
         dist.barrier(group=group)
         # the library enqueues on a torch-owned stream, and the NCCL ops are issued under the same stream, so that
         # sweep -> all-gather -> raymarch -> gather stay stream-ordered without host synchronisation
@@ -270,12 +291,21 @@ class FShardedRaymarchVolume:
     def ClearLightVolume(self, value: float = 0.0) -> None:
         from .raymarch_utils import URaymarchUtils
 
+        self._pushed = False
         URaymarchUtils.ClearResourceLightVolumes(self.res, value)
 
-    def AddDirLight(self, light, added: bool, world, stats=None) -> bool:
+    def AddDirLight(self, light, added: bool, world, stats=None, push: bool = False) -> bool:
+        """`push=True` (collective: the same on every rank) for the LAST light of a reset: its last axis pass stores every finished light brick
+        into all peers' light volumes from inside the sweep kernel (TMA stores over NVLink), and GatherLightVolume only synchronises."""
         from .raymarch_utils import URaymarchUtils
 
-        return URaymarchUtils.AddDirLightToSingleVolume(self.res, light, added, world, bGPUSync=True, stats=stats)
+        _capi.check(self.lib.tbrm_slab_push_light(self.res.handle, 1 if push else 0))
+        try:
+            ok = URaymarchUtils.AddDirLightToSingleVolume(self.res, light, added, world, bGPUSync=True, stats=stats)
+        finally:
+            _capi.check(self.lib.tbrm_slab_push_light(self.res.handle, 0))
+        self._pushed = bool(push and ok)
+        return ok
 
     def ChangeDirLight(self, old_light, new_light, world, stats=None) -> bool:
         from .raymarch_utils import URaymarchUtils
@@ -288,7 +318,13 @@ class FShardedRaymarchVolume:
         import torch.distributed as dist
 
         with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(self.light.view(-1), self.light[self.z0:self.z1].reshape(-1), group=self.group)
+            if self._pushed:
+                # the bricks already sit in every rank's volume; what remains is to know that every rank's sweep (and with it its
+                # stores) has completed before anybody reads: a one-word all-reduce, stream-ordered after the sweep on every rank
+                dist.all_reduce(self._sync_word, group=self.group)
+            else:
+                dist.all_gather_into_tensor(self.light.view(-1), self.light[self.z0:self.z1].reshape(-1), group=self.group)
+        self._pushed = False
 
     # ---- frame ------------------------------------------------------------------------------------------
     def local_rows(self, height: int) -> int:

@@ -98,7 +98,7 @@ def must_replace(text: str, old: str, new: str) -> str:
     return text.replace(old, new)
 
 
-TMA_KERNEL_TYPE = "void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TmaParams, const float4*)"
+TMA_KERNEL_TYPE = "void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const PushMaps, const TmaParams, const float4*)"
 
 
 def splice_tma_helpers(text: str) -> str:

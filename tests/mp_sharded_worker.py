@@ -81,6 +81,35 @@ def main():
     else:
         assert frame is None
     dist.barrier()
+
+    # push-gather: a full reset whose LAST light pushes its finished bricks into every rank's volume from inside the sweep kernel; no
+    # all-gather follows (GatherLightVolume only synchronises). Every rank must hold the unsharded result bit for bit.
+    vol.light.fill_(-7.0)  # whatever the peers do not deliver stays recognisable
+    torch.cuda.synchronize()
+    dist.barrier()
+    vol.ClearLightVolume(0.0)
+    for i, l in enumerate(synth.LIGHTS):
+        assert vol.AddDirLight(l, True, world, push=(i == len(synth.LIGHTS) - 1))
+    vol.GatherLightVolume()
+    frame2, _ = vol.Render(cam, world, 200.0)
+    vol.Check()
+    vol.Flush()
+    ref2 = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True, device=local)
+    URaymarchUtils.SetDataVolumeDevice(ref2, d_vol.data_ptr())
+    URaymarchUtils.ColorCurveToTexture(ref2, synth.soft_ct_curve())
+    URaymarchUtils.SetWindowingParameters(ref2, win)
+    URaymarchUtils.ClearResourceLightVolumes(ref2, 0.0)
+    for l in synth.LIGHTS:
+        URaymarchUtils.AddDirLightToSingleVolume(ref2, l, True, world, bGPUSync=True)
+    L2_ref = URaymarchUtils.ReadLightVolume(ref2)
+    L2 = vol.light.cpu().numpy()
+    d2 = np.abs(L2 - L2_ref)
+    assert np.array_equal(L2, L2_ref), f"push-gather, rank {rank}: {np.count_nonzero(d2)} voxels differ, max {d2.max():.3e}, first {np.argwhere(d2 > 0)[:3].tolist()}"
+    if rank == 0:
+        img2_ref, _ = URaymarchUtils.PerformWindowedLitRaymarch(ref2, cam, world, 200.0)
+        assert np.array_equal(frame2.cpu().numpy(), img2_ref), "frame after push-gather"
+    ref2.release()
+    dist.barrier()
     vol.release()
     dist.destroy_process_group()
     print(f"sharded ok rank {rank}/{world_size} n={n}", flush=True)
