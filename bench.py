@@ -464,10 +464,17 @@ def run_ours(args) -> int:
     sweep_bytes = vox * (4.0 + passes * 9.0)  # clear (4 B) + per axis pass 1 B data + 4 B read + 4 B write
     ray_bytes = vox * 1.0 + vox * 4.0 + 256 * 16 * 8 + W * H * 16.0  # compulsory bytes of the raymarch
     roofline = {  # dominant kernel by time: the raymarch (instruction-issue bound, not HBM bound — reported honestly)
-        "kernel": "raymarch_fast_kernel", "bound": "hbm", "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9, "peak": hbm_peak * world_size, "unit": "GB/s",
+        "kernel": "raymarch_fast2_kernel (lit march, second generation without leaps)", "bound": "hbm", "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9, "peak": hbm_peak * world_size, "unit": "GB/s",
         "frac": ray_bytes / (ray_ms * 1e-3) / 1e9 / (hbm_peak * world_size), "traffic": None, "peak_source": peak_src,
-        "note": "compulsory bytes / kernel time; ~200 instr per non-empty sample make this kernel issue-bound (DESIGN.md §6)",
+        "note": "compulsory bytes / kernel time; ~350 instr per non-empty sample make this kernel issue-bound (DESIGN.md §5.3, §6)",
     }
+    # the march is bounded by instruction issue, not by HBM: the same launch against the FP32 pipes, with SURVEY's count of
+    # 110 flop per executed step (an upper bound on useful work: skipped empty samples are counted) and peak = SMs x 128 lanes x 2 x SM clock
+    sm_clock_ghz = (clock_info.get("sm_mhz") or 1965.0) / 1e3
+    fp32_peak = 148 * 128 * 2 * sm_clock_ghz / 1e3  # TFLOP/s
+    roofline["fp32"] = {"flop_per_step": 110, "achieved_TFLOPs": all_steps * 110.0 / (ray_ms * 1e-3) / 1e12, "peak_TFLOPs": fp32_peak * world_size,
+                        "frac": all_steps * 110.0 / (ray_ms * 1e-3) / 1e12 / (fp32_peak * world_size),
+                        "ncu": "profiles/r2_raymarch_fast2_kernel_ncu.txt: issue slots ~74 % busy, ALU pipe 46 %, FMA pipes 33 %, DRAM 0.6 %"}
     roofline_sweep = {
         "kernel": "sweep_tma_kernel (one axis pass along Z; on a sharded volume its slabs run as a chain)", "bound": "hbm",
         "achieved": vox * 9.0 / (pass_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": vox * 9.0 / (pass_ms * 1e-3) / 1e9 / hbm_peak,
@@ -484,7 +491,7 @@ def run_ours(args) -> int:
         lib_path = ROOT / "tbraymarcherplugin_b200" / "libtbrm.so"
         meta["same_library"] = bool(meta.get("libtbrm_sha256_16")) and lib_path.exists() and \
             hashlib.sha256(lib_path.read_bytes()).hexdigest()[:16] == meta.get("libtbrm_sha256_16")
-        roofline["traffic"] = t.get("raymarch_fast_kernel")
+        roofline["traffic"] = t.get("raymarch_fast2_kernel", t.get("raymarch_fast_kernel"))
         roofline_sweep["traffic"] = t.get("sweep_tma_kernel")
         roofline["traffic_source"] = roofline_sweep["traffic_source"] = meta
 
@@ -610,6 +617,43 @@ def run_ours(args) -> int:
         cpu_baseline = {"value": est_steps / est_s / 1e6, "unit": "Mray-steps/s", "cores": threads, "kind": kind, "sample": sample_text(),
                         "est_ms_per_step": est_s * 1e3, "note": REFERENCE_NOTE[kind], **detail}
 
+    # ---- the reference's other light-volume formats (N = 1): G8 is its DEFAULT (RaymarchVolume.h:198-199), half resolution its "massive
+    # speedup" option (Readme.md:214). Same reset + frame as the step, timed once each; these run the generic fused sweep today.
+    formats = None
+    if world_size == 1 and WORKLOAD == "cfg2" and not args.no_formats:
+        formats = {}
+        for name, l32, half in (("g8", False, False), ("r32f_half", True, True), ("g8_half", False, True)):
+            rf = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=l32, LightVolumeHalfResolution=half, device=local)
+            URaymarchUtils.SetDataVolumeDevice(rf, d_vol.data_ptr())
+            URaymarchUtils.ColorCurveToTexture(rf, synth.soft_ct_curve())
+            URaymarchUtils.SetWindowingParameters(rf, win)
+            stf = []
+
+            def sweep_f():
+                URaymarchUtils.ClearResourceLightVolumes(rf, 0.0)
+                stf.clear()
+                for l in lights:
+                    st = FSweepStats()
+                    assert URaymarchUtils.AddDirLightToSingleVolume(rf, l, True, world, bGPUSync=True, stats=st)
+                    stf.append(st)
+
+            def frame_f():
+                URaymarchUtils.PerformWindowedLitRaymarch(rf, cam, world, STEPS, device_out_ptr=d_img.data_ptr(), count_steps=False)
+
+            def timed(fn, reps=3):
+                fn()
+                ms = C.c_float()
+                _capi.check(lib.tbrm_timer_begin(rf.handle))
+                for _ in range(reps):
+                    fn()
+                _capi.check(lib.tbrm_timer_end(rf.handle, C.byref(ms)))
+                return ms.value / reps
+
+            formats[name] = {"sweep_ms": timed(sweep_f), "raymarch_ms": timed(frame_f), "sweep_impl": [list(s.impl) for s in stf],
+                             "light_dims": list(rf.LightDims)}
+            rf.release()
+        trace(f"formats: {formats}")
+
     # ---- BASELINE.json configs[3] (north_star's scaling figure): the illumination sweep of a 1024^3 volume, 3 lights, full reset, on the
     # same N GPUs — sweep only, Mvoxels/s = light voxels x axis passes / device time (max over ranks), light volume checked bit-for-bit
     # against the reference shaders' digest. Rides along in every line so that the driver's 1/2/4/8 runs carry it.
@@ -687,7 +731,7 @@ def run_ours(args) -> int:
             "metric": "Mray-steps/s", "value": value, "unit": "Mray-steps/s", "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if (world_size > 1 and not slabs) else "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world_size, slabs), "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_sweep": roofline_sweep, "cpu_baseline": cpu_baseline, "parity": parity, "scale_cfg4": scale_cfg4,
+            "roofline": roofline, "roofline_sweep": roofline_sweep, "cpu_baseline": cpu_baseline, "parity": parity, "scale_cfg4": scale_cfg4, "formats": formats,
             "stages": {
                 "ray_steps_per_frame": frame_steps,
                 "raymarch": {"ms": ray_ms, "Mray_steps_per_s": all_steps / (ray_ms * 1e-3) / 1e6},
@@ -719,6 +763,7 @@ def main() -> int:
                     help="N > 1: push the finished light bricks into every rank's volume from the sweep's last pass (TMA stores over NVLink) instead "
                          "of an NCCL all-gather of the slabs. auto = on for 2 GPUs only: measured on B200s, the push wins at N = 2 (step 7.71 -> "
                          "7.39 ms) and loses at N = 8 (5.31 -> 8.27 ms: seven unicast copies per brick against NCCL's switch multicast)")
+    ap.add_argument("--no-formats", action="store_true", help="skip the extra timings of the G8 / half-resolution light-volume formats")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the extra 1024^3 sweep measurement (scale_cfg4)")
     ap.add_argument("--trace", action="store_true", help="print progress lines to stderr (debugging multi-GPU runs)")
     ap.add_argument("--sharding", default="slabs", choices=["slabs", "volumes"],

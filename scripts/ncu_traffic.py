@@ -12,7 +12,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-CMD = [sys.executable, "bench.py", "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-parity", "--no-cfg4"]
+CMD = [sys.executable, "bench.py", "--steps", "1", "--warmup", "3", "--no-cpu-baseline", "--no-parity", "--no-cfg4", "--no-formats"]
 NCU = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:sweep_tma_kernel|sweep_chain_kernel|occlusion_kernel|raymarch_fast", "-c", "40", "--csv"]
 out = subprocess.run(NCU + CMD, cwd=ROOT, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out[out.index('"ID"'):]))) if '"ID"' in out else []

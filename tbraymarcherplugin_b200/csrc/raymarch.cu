@@ -3,6 +3,8 @@
 //            Source/Raymarcher/Shaders/Private/WindowedRaymarchMaterials.usf:21-96.
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "tbrm_internal.hpp"
 
 namespace tbrm {
@@ -274,9 +276,19 @@ __device__ __forceinline__ void axis_taps_bounded(float u, float fN, int& i0, fl
     i0 = (int) fl;
 }
 
+// a light-volume texel: R32F as stored, G8 (the reference's default light format, RaymarchVolume.h:198-199) decoded as UNORM8 — v / 255,
+// correctly rounded, the generic kernel's light_load
+template <typename LightT, typename I>
+__device__ __forceinline__ float light_tap(const LightT* p, I i) {
+    if constexpr (sizeof(LightT) == 1)
+        return decode_u8_exact((uint32_t) __ldg(p + i));
+    else
+        return __ldg(p + i);
+}
+
 // one march sample (AccumulateWindowedRaymarchStep); returns nothing, updates acc
-template <bool ADDR32>
-__device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t* __restrict__ data, const float* __restrict__ light,
+template <bool ADDR32, typename LightT>
+__device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t* __restrict__ data, const LightT* __restrict__ light,
                                             const float4* s_tf, V3 p, float step, float4& acc) {
     const MarchUniforms& U = F.M;
     int i0, j0, k0;
@@ -343,16 +355,16 @@ __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t
             const unsigned int zx00 = (unsigned int) z0 * SXY + (unsigned int) x0, zx01 = (unsigned int) z0 * SXY + (unsigned int) x1;
             const unsigned int zx10 = (unsigned int) z1 * SXY + (unsigned int) x0, zx11 = (unsigned int) z1 * SXY + (unsigned int) x1;
             const unsigned int ya = (unsigned int) y0 * SX, yb = (unsigned int) y1 * SX;
-            q000 = __ldg(light + (ya + zx00)), q100 = __ldg(light + (ya + zx01)), q010 = __ldg(light + (yb + zx00)), q110 = __ldg(light + (yb + zx01));
-            q001 = __ldg(light + (ya + zx10)), q101 = __ldg(light + (ya + zx11)), q011 = __ldg(light + (yb + zx10)), q111 = __ldg(light + (yb + zx11));
+            q000 = light_tap(light, ya + zx00), q100 = light_tap(light, ya + zx01), q010 = light_tap(light, yb + zx00), q110 = light_tap(light, yb + zx01);
+            q001 = light_tap(light, ya + zx10), q101 = light_tap(light, ya + zx11), q011 = light_tap(light, yb + zx10), q111 = light_tap(light, yb + zx11);
         } else {
             const size_t SX = LX, SXY = (size_t) LX * LY;
-            const float* q00 = light + SX * y0 + SXY * z0;
-            const float* q01 = light + SX * y1 + SXY * z0;
-            const float* q10 = light + SX * y0 + SXY * z1;
-            const float* q11 = light + SX * y1 + SXY * z1;
-            q000 = __ldg(q00 + x0), q100 = __ldg(q00 + x1), q010 = __ldg(q01 + x0), q110 = __ldg(q01 + x1);
-            q001 = __ldg(q10 + x0), q101 = __ldg(q10 + x1), q011 = __ldg(q11 + x0), q111 = __ldg(q11 + x1);
+            const LightT* q00 = light + SX * y0 + SXY * z0;
+            const LightT* q01 = light + SX * y1 + SXY * z0;
+            const LightT* q10 = light + SX * y0 + SXY * z1;
+            const LightT* q11 = light + SX * y1 + SXY * z1;
+            q000 = light_tap(q00, x0), q100 = light_tap(q00, x1), q010 = light_tap(q01, x0), q110 = light_tap(q01, x1);
+            q001 = light_tap(q10, x0), q101 = light_tap(q10, x1), q011 = light_tap(q11, x0), q111 = light_tap(q11, x1);
         }
     }
     const float c00 = lerpf(decode_u8_exact(b000), decode_u8_exact(b100), fx);
@@ -383,9 +395,9 @@ __device__ __forceinline__ void fast_sample(const FastUniforms& F, const uint8_t
     acc.w = acc.w + (alpha * oma);
 }
 
-template <bool CLIP, bool ADDR32>
+template <bool CLIP, bool ADDR32, typename LightT>
 __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
-                                                            const float* __restrict__ light, const float4* __restrict__ tf,
+                                                            const LightT* __restrict__ light, const float4* __restrict__ tf,
                                                             float4* __restrict__ out, unsigned long long* __restrict__ steps_out) {
     const MarchUniforms& U = F.M;
     __shared__ float4 s_tf[256];
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F
                                       U.clip_dir[1], U.clip_dir[2]);
                 if (cd <= 0.0f) continue;
             }
-            fast_sample<ADDR32>(F, data, light, s_tf, cur, ssw, acc);
+            fast_sample<ADDR32, LightT>(F, data, light, s_tf, cur, ssw, acc);
             if (acc.w > 0.95f) {
                 acc.w = 1.0f;
                 break;
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(256) raymarch_fast_kernel(const FastUniforms F
                                       U.clip_dir[1], U.clip_dir[2]);
                 clipped = cd <= 0.0f;
             }
-            if (!clipped) fast_sample<ADDR32>(F, data, light, s_tf, cur, 100.0f * fin, acc);
+            if (!clipped) fast_sample<ADDR32, LightT>(F, data, light, s_tf, cur, 100.0f * fin, acc);
         }
         out[(size_t) lr * U.cam.width + ix] = acc;
     }
@@ -471,9 +483,9 @@ __device__ __forceinline__ void axis_taps_raw(float u, int N, int& i0, float& f)
     i0 = (int) fl;
 }
 
-template <bool CLIP>
+template <bool CLIP, typename LightT>
 __global__ void __launch_bounds__(256, 5) raymarch_fast2_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
-                                                             const float* __restrict__ light, const float4* __restrict__ tf,
+                                                             const LightT* __restrict__ light, const float4* __restrict__ tf,
                                                              float4* __restrict__ out, unsigned long long* __restrict__ steps_out) {
     const MarchUniforms& U = F.M;
     __shared__ float4 s_tf[256];
@@ -525,7 +537,7 @@ __global__ void __launch_bounds__(256, 5) raymarch_fast2_kernel(const FastUnifor
             const bool interior = ((unsigned) i0 - 1u) < (unsigned) max(X - 2, 0) && ((unsigned) j0 - 1u) < (unsigned) max(Y - 2, 0) &&
                                   ((unsigned) k0 - 1u) < (unsigned) max(Z - 2, 0);
             if (!interior || !F.same_dims) {  // the one-voxel shell, half-resolution light volumes: the general sampler
-                fast_sample<true>(F, data, light, s_tf, cur, ssw, acc);
+                fast_sample<true, LightT>(F, data, light, s_tf, cur, ssw, acc);
             } else {
                 if (F.bricks) {
                     const int m = __ldg(F.bricks + (i0 >> 3) + F.bdims[0] * ((j0 >> 3) + F.bdims[1] * (k0 >> 3)));
@@ -565,9 +577,9 @@ __global__ void __launch_bounds__(256, 5) raymarch_fast2_kernel(const FastUnifor
                 if (alpha == 0.0f) continue;  // adds exactly 0 to every channel
                 float sx = lerpf(a.x, b.x, tfw), sy = lerpf(a.y, b.y, tfw), sz = lerpf(a.z, b.z, tfw);
                 // light sampler: interior => saturate(p) == p and wrap == identity, same dimensions => same taps and weights
-                const float* l0 = light + o;
-                const float d00 = lerpf(__ldg(l0), __ldg(l0 + 1), fx), d01 = lerpf(__ldg(l0 + X), __ldg(l0 + X + 1), fx);
-                const float d10 = lerpf(__ldg(l0 + XY), __ldg(l0 + XY + 1), fx), d11 = lerpf(__ldg(l0 + XY + X), __ldg(l0 + XY + X + 1), fx);
+                const LightT* l0 = light + o;
+                const float d00 = lerpf(light_tap(l0, 0), light_tap(l0, 1), fx), d01 = lerpf(light_tap(l0, X), light_tap(l0, X + 1), fx);
+                const float d10 = lerpf(light_tap(l0, XY), light_tap(l0, XY + 1), fx), d11 = lerpf(light_tap(l0, XY + X), light_tap(l0, XY + X + 1), fx);
                 const float l = lerpf(lerpf(d00, d01, fy), lerpf(d10, d11, fy), fz);
                 sx = sx * l, sy = sy * l, sz = sz * l;
                 const float oma = 1.0f - acc.w;
@@ -591,7 +603,7 @@ __global__ void __launch_bounds__(256, 5) raymarch_fast2_kernel(const FastUnifor
                                       U.clip_dir[1], U.clip_dir[2]);
                 clipped = cd <= 0.0f;
             }
-            if (!clipped) fast_sample<true>(F, data, light, s_tf, cur, 100.0f * fin, acc);
+            if (!clipped) fast_sample<true, LightT>(F, data, light, s_tf, cur, 100.0f * fin, acc);
         }
         out[(size_t) lr * U.cam.width + ix] = acc;
     }
@@ -802,7 +814,7 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
     U.row_block = row_block, U.block_stride = block_stride;
     U.data_wrap = r.options.data_addr_wrap;
     const bool l8 = r.light_fmt == TBRM_FMT_G8;
-    if (r.data_fmt == TBRM_FMT_G8 && !l8 && !U.data_wrap && r.options.reserved[1] != 1) {
+    if (r.data_fmt == TBRM_FMT_G8 && !U.data_wrap && r.options.reserved[1] != 1) {  // both light formats (round 2: G8 took the generic kernel, 22 ms)
         FastUniforms F;
         F.M = U;
         F.rwidth = 1.0f / U.win.width;
@@ -833,18 +845,27 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
         const bool v2 = form != 0 && r.data_voxels() < (1ull << 31);
         if (form == 2) F.leap_margin = -1.0f;  // interior fast path only, no leaps
         const bool noclip = clip_never_rejects(clip_center, clip_dir);
-        if (v2 && noclip)
-            raymarch_fast2_kernel<false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
-        else if (v2)
-            raymarch_fast2_kernel<true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
-        else if (noclip && addr32)
-            raymarch_fast_kernel<false, true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
-        else if (addr32)
-            raymarch_fast_kernel<true, true><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
-        else if (noclip)
-            raymarch_fast_kernel<false, false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+        const uint8_t* d8 = (const uint8_t*) r.data;
+        float4* o4 = (float4*) d_out;
+        auto launch = [&](auto light_ptr) {  // light_ptr: const float* (R32F) or const uint8_t* (G8)
+            using LightT = std::remove_cv_t<std::remove_pointer_t<decltype(light_ptr)>>;
+            if (v2 && noclip)
+                raymarch_fast2_kernel<false, LightT><<<grid, 256, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+            else if (v2)
+                raymarch_fast2_kernel<true, LightT><<<grid, 256, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+            else if (noclip && addr32)
+                raymarch_fast_kernel<false, true, LightT><<<grid, 256, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+            else if (addr32)
+                raymarch_fast_kernel<true, true, LightT><<<grid, 256, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+            else if (noclip)
+                raymarch_fast_kernel<false, false, LightT><<<grid, 256, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+            else
+                raymarch_fast_kernel<true, false, LightT><<<grid, 256, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+        };
+        if (l8)
+            launch((const uint8_t*) r.light);
         else
-            raymarch_fast_kernel<true, false><<<grid, 256, 0, r.stream>>>(F, (const uint8_t*) r.data, (const float*) r.light, r.tf, (float4*) d_out, d_steps);
+            launch((const float*) r.light);
         count_launch();
         return cudaGetLastError();
     }

@@ -319,6 +319,13 @@ static void pack(std::vector<unsigned char>& staging, const tbrm_resources& r, c
     *dptr = (const char*) r.tables + off;
 }
 
+static const void* tma_kernel_l8(int axis, bool clip, int px) {  // G8 light volume: AddDirLight, sweeps along Y / Z, unsharded
+#define TBRM_K(A, PX) (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, true> : (const void*) sweep_tma_kernel<A, false, false, PX, true>)
+    if (px == 1) return axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1);
+    return axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2);
+#undef TBRM_K
+}
+
 static const void* tma_kernel(int axis, bool clip, bool slab, int px) {
 #define TBRM_K(A, PX) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true, PX> : (const void*) sweep_tma_kernel<A, false, true, PX>) \
                             : (clip ? (const void*) sweep_tma_kernel<A, true, false, PX> : (const void*) sweep_tma_kernel<A, false, false, PX>))
@@ -518,7 +525,11 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
 
 static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u, int mode, int* launches, bool* handled) {
     *handled = false;
-    if (r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res) return not_handled("r.data_fmt != TBRM_FMT_G8 || r.light_fmt != TBRM_FMT_R32F || r.half_res");
+    if (r.data_fmt != TBRM_FMT_G8 || r.half_res) return not_handled("r.data_fmt != TBRM_FMT_G8 || r.half_res");
+    // a G8 light volume (the reference's default format): byte bricks — AddDirLight, sweeps along Y / Z, unsharded (a byte brick of 4 slices
+    // along X has 4-byte rows, below TMA's 16-byte minimum; ChangeDirLight keeps its removed light in an R32F scratch volume)
+    const bool l8 = r.light_fmt == TBRM_FMT_G8;
+    if (l8 && (u.axis == 0 || mode != kModeAdd || r.slab.nranks > 1)) return not_handled("G8 light volume: sweep along X / ChangeDirLight / sharded volume");
     const int X = r.ddims[0], Y = r.ddims[1], Z = r.ddims[2];
     if (X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)) return not_handled("X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)");  // TMA global strides must be multiples of 16 bytes
     if (((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)) return not_handled("((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)");
@@ -554,7 +565,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         return e ? atoi(e) : 1;
     }();
     // (the chain kernel of the second generation walks whole blocks of kSB slices: other slice counts take the first generation)
-    const bool ws = (env_gen == 2 || (r.options.reserved[0] & 64)) && u.td[2] % kSB == 0;
+    const bool ws = (env_gen == 2 || (r.options.reserved[0] & 64)) && u.td[2] % kSB == 0 && r.light_fmt == TBRM_FMT_R32F;
     int px = 2;
     {
         static const int env_px = [] {  // 1 / 2 forced, 3 automatic (default)
@@ -606,9 +617,12 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     lbox[pa] = kTW, lbox[qa] = kTH, lbox[sa] = kSB;
     CUtensorMap lm, dm, sm;
     // the brick that is loaded, updated and stored: the light volume, or the scratch volume when the light is only stored
-    if (!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeStore ? r.change_scratch : r.light, ldims, lbox))
+    if (l8 ? !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.light, ldims, lbox)
+           : !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeStore ? r.change_scratch : r.light, ldims, lbox))
         return not_handled("tensor map of the light volume");
-    if (!make_map3(&sm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeCombine ? r.change_scratch : r.light, ldims, lbox))
+    if (l8)
+        sm = lm;  // never read (AddDirLight only)
+    else if (!make_map3(&sm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeCombine ? r.change_scratch : r.light, ldims, lbox))
         return not_handled("tensor map of the scratch volume");
     P.mode = mode;
     // push-gather: the same box over every other rank's light volume (the brick that updates the LIGHT volume: add / combine launches)
@@ -642,7 +656,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         const int str[3] = {1, db[0], db[0] * db[1]};
         P.ds_q = str[qa], P.ds_s = str[sa];
     }
-    P.light_bytes = kTW * kTH * kSB * 4;
+    P.light_bytes = kTW * kTH * kSB * (l8 ? 1 : 4);
     P.data_off = mode == kModeCombine ? 2 * P.light_bytes : P.light_bytes;
     P.data_bytes = P.dext[0] * P.dext[1] * P.dext[2];
     P.stage_bytes = (P.data_off + P.data_bytes + 16 + 127) / 128 * 128;
@@ -668,7 +682,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
     const int threads = ws ? kChThreads : kTmaThreads;
-    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : tma_kernel(u.axis, clip, false, px);
+    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, px) : tma_kernel(u.axis, clip, false, px));
     const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : tma_kernel(u.axis, clip, true, px);
     {   // the shared-memory attribute and the occupancy of a (kernel, shared-memory size) pair are set / queried once
         struct Known {
@@ -704,6 +718,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int nbands = bands_of(q_begin, q_end);
     const int rows_per_band = (tr1 - tr0 + nbands - 1) / nbands;
     const bool use_slab = sharded || nbands > 1;
+    if (l8 && use_slab) return not_handled("G8 light volume on a plane that needs several co-resident waves");
     if (use_slab) {
         if (reach_lo + reach_hi > kInboxSlots) return not_handled("the footprints reach more than 8 rows into the neighbouring bands");
         // a footprint must not reach past the adjacent band (bands and slabs are at least 8 rows)

@@ -81,7 +81,11 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 // PX = pixels per thread along p: 2 (tile 64 x 8, the two pixels share their middle tap column) or 1 (tile 32 x 8). A pass costs
 // slices x the per-slice instruction chain of ONE tile once its tiles no longer fill the SMs (256^3, the slab of a sharded volume):
 // one pixel per thread shortens that chain by the second pixel's work and doubles the tiles; the host picks it for such launches.
-template <int AXIS, bool CLIP, bool SLAB, int PX>
+// L8 = the light volume is G8 (UNORM8, the reference's default: RaymarchVolume.h:198-199, RaymarchVolume.cpp:857-861): the light brick is a
+// byte brick (load -> v / 255, store -> floor(saturate(v) * 255 + 0.5)), and what a slice forwards to the next one is the value its G8
+// read / write buffer would hold (the propagation buffers have the light volume's pixel format) — the light volume itself is updated with the
+// unquantised value, as in the shader. AddDirLight, sweeps along Y and Z (a byte brick of 4 slices along X has 4-byte rows: below TMA's 16).
+template <int AXIS, bool CLIP, bool SLAB, int PX, bool L8 = false>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
                      const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ PushMaps push_maps, const TmaParams P,
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     for (int c = tid; c < FPW * kFpH; c += kTmaThreads) {
         const int gx = fx0 + c % FPW, gy = fy0 + c / FPW;
         const bool in = (unsigned) gx < (unsigned) tx && (unsigned) gy < (unsigned) ty;
-        const float v = in ? U.a.light_alpha : U.a.border;
+        const float v = in ? (L8 ? decode_u8((uint32_t) quant8(U.a.light_alpha)) : U.a.light_alpha) : U.a.border;
         s_fp[c] = v;
         s_fp[FPW * kFpH + c] = v;
     }
@@ -512,28 +516,34 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
                 const float prev0 = lerpf(lerpf(t00, t10, bfx0), lerpf(t01, t11, bfx0), bfy);
                 const float prev1 = lerpf(lerpf(t10, t20, bfx1), lerpf(t11, t21, bfx1), bfy);
                 const float cur0 = prev0 * (1.0f - cs0), cur1 = prev1 * (1.0f - cs1);
-                if (own_in0) fp_next[own_idx] = cur0;
-                if (own_in1) fp_next[own_idx + 1] = cur1;
+                // what the next slice reads: the value as a read / write buffer of the light volume's format holds it
+                const float fwd0 = L8 ? decode_u8((uint32_t) quant8(cur0)) : cur0, fwd1 = L8 ? decode_u8((uint32_t) quant8(cur1)) : cur1;
+                if (own_in0) fp_next[own_idx] = fwd0;
+                if (own_in1) fp_next[own_idx + 1] = fwd1;
                 unsigned long long* wr = ring + (((unsigned int) k % kRingDepth) * plane32 + own_cell);
                 const unsigned long long tag = (unsigned long long) (tag_base + (unsigned) k + 1u) << 32;
-                if (exp0) st_relaxed_u64(wr, tag | __float_as_uint(cur0));
-                if (exp1) st_relaxed_u64(wr + 1, tag | __float_as_uint(cur1));
+                if (exp0) st_relaxed_u64(wr, tag | __float_as_uint(fwd0));
+                if (exp1) st_relaxed_u64(wr + 1, tag | __float_as_uint(fwd1));
                 if (SLAB) {
                     const size_t ko = (size_t) k * inbox_plane;
-                    if (xlo0) st_relaxed_sys_u64(P.S.out_lo + ko + xlo_idx, tag | __float_as_uint(cur0));
-                    if (xlo1) st_relaxed_sys_u64(P.S.out_lo + ko + xlo_idx + 1, tag | __float_as_uint(cur1));
-                    if (xhi0) st_relaxed_sys_u64(P.S.out_hi + ko + xhi_idx, tag | __float_as_uint(cur0));
-                    if (xhi1) st_relaxed_sys_u64(P.S.out_hi + ko + xhi_idx + 1, tag | __float_as_uint(cur1));
+                    if (xlo0) st_relaxed_sys_u64(P.S.out_lo + ko + xlo_idx, tag | __float_as_uint(fwd0));
+                    if (xlo1) st_relaxed_sys_u64(P.S.out_lo + ko + xlo_idx + 1, tag | __float_as_uint(fwd1));
+                    if (xhi0) st_relaxed_sys_u64(P.S.out_hi + ko + xhi_idx, tag | __float_as_uint(fwd0));
+                    if (xhi1) st_relaxed_sys_u64(P.S.out_hi + ko + xhi_idx + 1, tag | __float_as_uint(fwd1));
                     if (P.S.zout != nullptr && k == k_end - 1) {  // hand the last slice of this slab to the next one
                         unsigned long long* zo = P.S.zout + (size_t) px + (size_t) tx * py;
-                        if (v0) st_relaxed_sys_u64(zo, tag | __float_as_uint(cur0));
-                        if (v1) st_relaxed_sys_u64(zo + 1, tag | __float_as_uint(cur1));
+                        if (v0) st_relaxed_sys_u64(zo, tag | __float_as_uint(fwd0));
+                        if (v1) st_relaxed_sys_u64(zo + 1, tag | __float_as_uint(fwd1));
                     }
                 }
                 // pixels beyond a ragged plane edge (v0 / v1 false) update their cell of the SMEM brick too: the TMA store clips the brick
                 // to the light volume, so those cells never reach memory — no validity test per slice
                 float* lp = s_light + light_off + (loop - s0) * P.ls_s;
-                if (P.mode == kModeAdd) {  // AddDirLightShader.usf:121-126
+                if (L8) {  // AddDirLightShader.usf:121-126 on a G8 light volume (the host sends only AddDirLight here)
+                    unsigned char* lp8 = (unsigned char*) s_light + light_off + (loop - s0) * P.ls_s;
+                    if (fabsf(cur0) > 1e-3f) lp8[0] = quant8(decode_u8((uint32_t) lp8[0]) + (cur0 * U.sign));
+                    if (PX == 2 && fabsf(cur1) > 1e-3f) lp8[P.ls_p] = quant8(decode_u8((uint32_t) lp8[P.ls_p]) + (cur1 * U.sign));
+                } else if (P.mode == kModeAdd) {  // AddDirLightShader.usf:121-126
                     if (fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
                     if (PX == 2 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
                 } else if (P.mode == kModeStore) {  // the removed light of a ChangeDirLight: its light goes to the scratch volume

@@ -91,6 +91,35 @@ def test_g8_and_half_resolution_light_volumes(light32, half_res, impl):
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"light32={light32} half_res={half_res}")
 
 
+@pytest.mark.parametrize("world_name", ["identity", "clipped"])
+@pytest.mark.parametrize("dims", [(64, 48, 40), (128, 32, 16), (64, 64, 64)])
+def test_g8_light_volume_through_the_tma_staged_sweep_and_the_fast_march(dims, world_name):
+    """G8 is the reference's DEFAULT light-volume format (RaymarchVolume.h:198-199). Sweeps along Y / Z of an AddDirLight run the TMA-staged
+    kernel on byte bricks (forwarded values quantised like the G8 read / write buffers, the light volume updated with the unquantised value);
+    sweeps along X take the generic fused kernel; the lit march's fast kernels decode the G8 light taps. All bit-exact against the oracle."""
+    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats
+
+    data = synth.perlin_ct_volume(dims)
+    world = WORLDS[world_name]()
+    res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, light32=False, sweep_impl=2)
+    impls = []
+    for light in synth.LIGHTS + [FDirLightParameters((0.0, -1.0, 0.0), 0.3), FDirLightParameters((0.1, 0.2, 1.0), 0.4)]:
+        st = FSweepStats()
+        assert URaymarchUtils.AddDirLightToSingleVolume(res, light, True, world, bGPUSync=True, stats=st)
+        ora.add_dir_light(light, True, world)
+        impls.append(tuple(st.impl))
+        assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"G8 light volume after {light.LightDirection} (impl {st.impl})")
+    assert any(3 in i for i in impls), f"the TMA-staged sweep must have taken the Y / Z passes: {impls}"
+    URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[2], False, world, bGPUSync=True)
+    ora.add_dir_light(synth.LIGHTS[2], False, world)
+    assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "G8 light volume after a removal")
+    cam = synth.benchmark_camera(96, 64)
+    rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 80.0)
+    ref, ref_steps = ora.raymarch_lit(cam, world, 80.0)
+    assert steps == ref_steps
+    assert_same(rgba, ref, "lit march over a G8 light volume")
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("data_dtype", [np.uint16, np.float32])
 def test_g16_and_float_data_volumes(data_dtype, impl):
