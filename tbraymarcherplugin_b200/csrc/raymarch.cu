@@ -562,6 +562,12 @@ __global__ void __launch_bounds__(256, 5) raymarch_fast2_kernel(const FastUnifor
                 const uint8_t* d0 = data + o;
                 const uint32_t b000 = __ldg(d0), b100 = __ldg(d0 + 1), b010 = __ldg(d0 + X), b110 = __ldg(d0 + X + 1);
                 const uint32_t b001 = __ldg(d0 + XY), b101 = __ldg(d0 + XY + 1), b011 = __ldg(d0 + XY + X), b111 = __ldg(d0 + XY + X + 1);
+                // light sampler: interior => saturate(p) == p and wrap == identity, same dimensions => same taps and weights. Requested before
+                // the data taps are decoded: the window / TF / pow chain in between hides their latency (this kernel waits on loads: long
+                // scoreboard 6.4 warps per issue-active cycle at 62 % issue utilisation, profiles/r2_raymarch_fast2_kernel_ncu.txt)
+                const LightT* l0 = light + o;
+                const float q000 = light_tap(l0, 0), q100 = light_tap(l0, 1), q010 = light_tap(l0, X), q110 = light_tap(l0, X + 1);
+                const float q001 = light_tap(l0, XY), q101 = light_tap(l0, XY + 1), q011 = light_tap(l0, XY + X), q111 = light_tap(l0, XY + X + 1);
                 const float c00 = lerpf(decode_u8_exact(b000), decode_u8_exact(b100), fx);
                 const float c01 = lerpf(decode_u8_exact(b010), decode_u8_exact(b110), fx);
                 const float c10 = lerpf(decode_u8_exact(b001), decode_u8_exact(b101), fx);
@@ -576,10 +582,8 @@ __global__ void __launch_bounds__(256, 5) raymarch_fast2_kernel(const FastUnifor
                 const float alpha = step_opacity(lerpf(a.w, b.w, tfw), ssw);
                 if (alpha == 0.0f) continue;  // adds exactly 0 to every channel
                 float sx = lerpf(a.x, b.x, tfw), sy = lerpf(a.y, b.y, tfw), sz = lerpf(a.z, b.z, tfw);
-                // light sampler: interior => saturate(p) == p and wrap == identity, same dimensions => same taps and weights
-                const LightT* l0 = light + o;
-                const float d00 = lerpf(light_tap(l0, 0), light_tap(l0, 1), fx), d01 = lerpf(light_tap(l0, X), light_tap(l0, X + 1), fx);
-                const float d10 = lerpf(light_tap(l0, XY), light_tap(l0, XY + 1), fx), d11 = lerpf(light_tap(l0, XY + X), light_tap(l0, XY + X + 1), fx);
+                const float d00 = lerpf(q000, q100, fx), d01 = lerpf(q010, q110, fx);
+                const float d10 = lerpf(q001, q101, fx), d11 = lerpf(q011, q111, fx);
                 const float l = lerpf(lerpf(d00, d01, fy), lerpf(d10, d11, fy), fz);
                 sx = sx * l, sy = sy * l, sz = sz * l;
                 const float oma = 1.0f - acc.w;
