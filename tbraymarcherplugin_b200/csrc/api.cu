@@ -297,6 +297,8 @@ tbrm_status tbrm_destroy(tbrm_resources* r) {
 
     if (r->flags) cudaFree(r->flags);
     if (r->sweep_err) cudaFree(r->sweep_err);
+    if (r->light_perm[0]) cudaFree(r->light_perm[0]);
+    if (r->light_perm[1]) cudaFree(r->light_perm[1]);
     if (r->tvol) cudaFree(r->tvol);
     if (r->tones) cudaFree(r->tones);
     for (auto& axis : r->rw)

@@ -319,10 +319,10 @@ static void pack(std::vector<unsigned char>& staging, const tbrm_resources& r, c
     *dptr = (const char*) r.tables + off;
 }
 
-static const void* tma_kernel_l8(int axis, bool clip, int px) {  // G8 light volume: AddDirLight, sweeps along Y / Z, unsharded
+static const void* tma_kernel_l8(int axis, bool clip, int px) {  // G8 light volume: AddDirLight, unsharded
 #define TBRM_K(A, PX) (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, true> : (const void*) sweep_tma_kernel<A, false, false, PX, true>)
-    if (px == 1) return axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1);
-    return axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2);
+    if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
+    return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
 #undef TBRM_K
 }
 
@@ -452,6 +452,20 @@ __global__ void __launch_bounds__(256) permute_yzx_vec_kernel(const uint8_t* __r
     *reinterpret_cast<uint4*>(dst + (size_t) y + (size_t) Y * ((size_t) z + (size_t) Z * x)) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// dst[i1 + D1 (i2 + D2 i0)] = src[i0 + D0 (i1 + D1 i2)]: the byte transpose behind the (y,z,x) replicas. Applied three times it is the identity,
+// so two more applications (with the dimensions rotated) undo one.
+static cudaError_t permute_bytes(tbrm_resources& r, const uint8_t* src, uint8_t* dst, int D0, int D1, int D2) {
+    if ((D0 & 15) == 0 && (D1 & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+        const dim3 grid((D0 + 63) / 64, (D1 + 63) / 64, D2);
+        permute_yzx_vec_kernel<<<grid, 256, 0, r.stream>>>(src, dst, D0, D1, D2);
+    } else {
+        const dim3 block(32, 8), grid((D0 + 31) / 32, (D1 + 31) / 32, D2);
+        permute_yzx_kernel<<<grid, block, 0, r.stream>>>(src, dst, D0, D1, D2);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
 // the (y,z,x)-ordered replica of the data volume used by sweeps along X; rebuilt lazily after an upload
 static cudaError_t ensure_replica(tbrm_resources& r) {
     if (r.data_yzx_valid) return cudaSuccess;
@@ -529,7 +543,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // a G8 light volume (the reference's default format): byte bricks — AddDirLight, sweeps along Y / Z, unsharded (a byte brick of 4 slices
     // along X has 4-byte rows, below TMA's 16-byte minimum; ChangeDirLight keeps its removed light in an R32F scratch volume)
     const bool l8 = r.light_fmt == TBRM_FMT_G8;
-    if (l8 && (u.axis == 0 || mode != kModeAdd || r.slab.nranks > 1)) return not_handled("G8 light volume: sweep along X / ChangeDirLight / sharded volume");
+    if (l8 && (mode != kModeAdd || r.slab.nranks > 1)) return not_handled("G8 light volume: ChangeDirLight / sharded volume");
     const int X = r.ddims[0], Y = r.ddims[1], Z = r.ddims[2];
     if (X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)) return not_handled("X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)");  // TMA global strides must be multiples of 16 bytes
     if (((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)) return not_handled("((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)");
@@ -617,7 +631,19 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     lbox[pa] = kTW, lbox[qa] = kTH, lbox[sa] = kSB;
     CUtensorMap lm, dm, sm;
     // the brick that is loaded, updated and stored: the light volume, or the scratch volume when the light is only stored
-    if (l8 ? !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.light, ldims, lbox)
+    const bool l8_x = l8 && u.axis == 0;  // a G8 volume's sweep along X works on a (y,z,x)-ordered copy of the light volume (see the kernel)
+    if (l8_x) {
+        const size_t lbytes = r.light_voxels();
+        if (r.light_perm_bytes < lbytes) {
+            if (r.light_perm[0]) cudaStreamSynchronize(r.stream), cudaFree(r.light_perm[0]), cudaFree(r.light_perm[1]);
+            r.light_perm[0] = r.light_perm[1] = nullptr, r.light_perm_bytes = 0;
+            if ((e = cudaMalloc(&r.light_perm[0], lbytes)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&r.light_perm[1], lbytes)) != cudaSuccess) return e;
+            r.light_perm_bytes = lbytes;
+        }
+        const int pd[3] = {r.ldims[1], r.ldims[2], r.ldims[0]}, pb[3] = {kTW, kTH, kSB};  // (p,q,s) = (y,z,x)
+        if (!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.light_perm[0], pd, pb)) return not_handled("tensor map of the permuted G8 light volume");
+    } else if (l8 ? !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.light, ldims, lbox)
            : !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeStore ? r.change_scratch : r.light, ldims, lbox))
         return not_handled("tensor map of the light volume");
     if (l8)
@@ -643,6 +669,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     {
         const int str[3] = {1, lbox[0], lbox[0] * lbox[1]};
         P.ls_p = str[pa], P.ls_q = str[qa], P.ls_s = str[sa];
+        if (l8_x) P.ls_p = 1, P.ls_q = kTW, P.ls_s = kTW * kTH;
     }
     if (u.axis == 0) {
         if ((e = ensure_replica(r)) != cudaSuccess) return e;
@@ -861,9 +888,15 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     if (!use_slab) {
         r.pass_seq = P.epoch;
         if ((e = cudaMemsetAsync(r.flags, 0, flag_words * sizeof(unsigned int), r.stream)) != cudaSuccess) return e;
+        if (l8_x && (e = permute_bytes(r, (const uint8_t*) r.light, (uint8_t*) r.light_perm[0], r.ldims[0], r.ldims[1], r.ldims[2])) != cudaSuccess) return e;
         if ((e = tma_launch(r, kern_plain, threads, lm, dm, sm, pm, P, ntiles, smem)) != cudaSuccess) return e;
         count_launch();
         *launches += 1;
+        if (l8_x) {  // back to (x,y,z): two more applications of the same transpose
+            if ((e = permute_bytes(r, (const uint8_t*) r.light_perm[0], (uint8_t*) r.light_perm[1], r.ldims[1], r.ldims[2], r.ldims[0])) != cudaSuccess) return e;
+            if ((e = permute_bytes(r, (const uint8_t*) r.light_perm[1], (uint8_t*) r.light, r.ldims[2], r.ldims[0], r.ldims[1])) != cudaSuccess) return e;
+            *launches += 3;
+        }
         *handled = true;
         return cudaSuccess;
     }

@@ -84,7 +84,8 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 // L8 = the light volume is G8 (UNORM8, the reference's default: RaymarchVolume.h:198-199, RaymarchVolume.cpp:857-861): the light brick is a
 // byte brick (load -> v / 255, store -> floor(saturate(v) * 255 + 0.5)), and what a slice forwards to the next one is the value its G8
 // read / write buffer would hold (the propagation buffers have the light volume's pixel format) — the light volume itself is updated with the
-// unquantised value, as in the shader. AddDirLight, sweeps along Y and Z (a byte brick of 4 slices along X has 4-byte rows: below TMA's 16).
+// unquantised value, as in the shader. AddDirLight only. A byte brick of 4 slices along X has 4-byte rows (below TMA's 16): a sweep along X
+// works on a (y,z,x)-ordered copy of the light volume (the host permutes it there and back: three byte transposes, ~0.3 ms at 512^3).
 template <int AXIS, bool CLIP, bool SLAB, int PX, bool L8 = false>
 __global__ void __launch_bounds__(kTmaThreads, 4)
     sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
@@ -298,6 +299,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         const int s0 = block_s0(b);
         int lc[3], dc[3];
         lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;  // light map is over native (x,y,z)
+        if (L8 && AXIS == 0) lc[0] = x0, lc[1] = y0, lc[2] = s0;  // ... except a G8 volume's sweep along X: its (y,z,x)-ordered copy, i.e. (p,q,s)
         tma_load_3d(sb, &light_map, lc[0], lc[1], lc[2], &s_bar[st]);
         if (P.mode == kModeCombine) tma_load_3d(sb + P.light_bytes, &scratch_map, lc[0], lc[1], lc[2], &s_bar[st]);
         // data map: native dims for Z / Y sweeps, the (y,z,x) replica for X sweeps, i.e. (p,q,s)-ordered for X
@@ -563,6 +565,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         if (tid == 0) {
             int lc[3];
             lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;
+            if (L8 && AXIS == 0) lc[0] = x0, lc[1] = y0, lc[2] = s0;
             tma_store_3d(&light_map, lc[0], lc[1], lc[2], s_light);
             // push-gather: the finished brick also goes into every other rank's light volume (NVLink), in the same bulk group — the transfer
             // overlaps the sweep tile by tile, and no all-gather of the light slabs follows the sweep

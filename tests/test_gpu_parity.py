@@ -109,7 +109,12 @@ def test_g8_light_volume_through_the_tma_staged_sweep_and_the_fast_march(dims, w
         ora.add_dir_light(light, True, world)
         impls.append(tuple(st.impl))
         assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"G8 light volume after {light.LightDirection} (impl {st.impl})")
-    assert any(3 in i for i in impls), f"the TMA-staged sweep must have taken the Y / Z passes: {impls}"
+    # every pass of the oblique lights runs the TMA-staged kernel (sweeps along X on a permuted copy of the light volume); an exactly
+    # axis-aligned light on a dimension that is not a power of two has non-uniform tap pairs and takes the generic kernel
+    # (on the flat 128 x 32 x 16 volume some passes have non-uniform tap pairs as well)
+    if dims != (128, 32, 16):
+        assert all(set(i) == {3} for i in impls[:3]), f"the TMA-staged sweep must have taken every pass of the oblique lights: {impls}"
+    assert any(3 in i for i in impls), impls
     URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[2], False, world, bGPUSync=True)
     ora.add_dir_light(synth.LIGHTS[2], False, world)
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "G8 light volume after a removal")
