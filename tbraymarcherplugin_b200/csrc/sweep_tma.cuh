@@ -29,7 +29,6 @@ constexpr int kStages = 3;
 constexpr int kRingDepth = 16;
 constexpr int kHaloPerThread = 2;          // footprint cells owned by other tiles, fetched per thread
 constexpr int kFpW = kTW + 4, kFpH = kTH + 4;  // SMEM footprint of the previous slice
-constexpr int kHaloOverflow = kFpW * kFpH - kHaloPerThread * kTmaThreads;  // halo cells beyond the per-thread registers
 
 struct AxisTab {  // per native coordinate c of one axis (device pointers)
     const float* S;   // GetUVW(c) + UVWOffset
@@ -326,12 +325,18 @@ static const void* tma_kernel_l8(int axis, bool clip, int px) {  // G8 light vol
 #undef TBRM_K
 }
 
-static const void* tma_kernel(int axis, bool clip, bool slab, int px) {
+static const void* tma_kernel(int axis, bool clip, bool slab, int px, int th = 8) {
 #define TBRM_K(A, PX) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true, PX> : (const void*) sweep_tma_kernel<A, false, true, PX>) \
                             : (clip ? (const void*) sweep_tma_kernel<A, true, false, PX> : (const void*) sweep_tma_kernel<A, false, false, PX>))
+#define TBRM_K7(A, PX) (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, false, 7> : (const void*) sweep_tma_kernel<A, false, false, PX, false, 7>)
+    if (th == 7 && !slab) {  // 7-row tiles: unsharded single-wave passes only
+        if (px == 1) return axis == 0 ? TBRM_K7(0, 1) : (axis == 1 ? TBRM_K7(1, 1) : TBRM_K7(2, 1));
+        return axis == 0 ? TBRM_K7(0, 2) : (axis == 1 ? TBRM_K7(1, 2) : TBRM_K7(2, 2));
+    }
     if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
     return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
 #undef TBRM_K
+#undef TBRM_K7
 }
 
 static const void* chain_kernel(int axis, bool slab, int px) {
@@ -506,6 +511,36 @@ int slab_pass_order(const SweepUniforms& u) {
 
 static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u, int mode, int* launches, bool* handled);
 
+// resident blocks per SM of a kernel at a dynamic shared-memory size; the attribute and the query are made once per (kernel, size, device).
+// *fits = false when the size cannot be set for the kernel.
+static cudaError_t blocks_per_sm(const void* kern, int threads, size_t smem, int dev, int* per_sm, bool* fits) {
+    struct Known {
+        const void* kern;
+        size_t smem;
+        int dev, per_sm;
+    };
+    static thread_local std::vector<Known> known;
+    *fits = true;
+    for (const Known& kn : known)
+        if (kn.kern == kern && kn.smem == smem && kn.dev == dev) {
+            *per_sm = kn.per_sm;
+            return cudaSuccess;
+        }
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
+        cudaGetLastError();
+        *fits = false, *per_sm = 0;
+        return cudaSuccess;
+    }
+    int occ = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    // another size may have been set for this kernel in between: drop stale entries of the kernel
+    known.erase(std::remove_if(known.begin(), known.end(), [&](const Known& kn) { return kn.kern == kern && kn.dev == dev; }), known.end());
+    known.push_back({kern, smem, dev, occ});
+    *per_sm = occ;
+    return cudaSuccess;
+}
+
 // One axis pass. ChangeDirLight (LightingShaders.cpp:168-326) runs as two launches that share the exchange machinery of the
 // Add sweep: the removed light's sweep leaves its propagated light in a scratch volume, the added light's sweep combines
 // LightVolume += added - removed under the reference's threshold on the difference — the same values, voxel by voxel, as
@@ -599,23 +634,62 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         }
     }
     const int kTW = 32 * px, kFpW = kTW + 4;  // shadow the two-pixel constants below
-    P.ntx = (tx + kTW - 1) / kTW, P.nty = (ty + kTH - 1) / kTH;
-    const int ntiles = P.ntx * P.nty;
+    const bool clip = !clip_is_inactive(u, T);
     // transposed axis order (p,q,s) in native axes
     const int pa = u.axis == 0 ? 1 : 0, qa = u.axis == 2 ? 1 : 2, sa = u.axis;
+    // data box extents: tile (+1 tap, + spread of i0 - c), inner extent rounded up to 16 bytes (+4 for the funnel read)
+    // TMA needs the box origin 16-byte aligned along the innermost dimension: round the u8 box start down to 16 voxels
+    // (tile origins are multiples of 64), and widen the box accordingly.
+    const int dmin_p_al = (int) floorf((float) T.dmin[pa] / 16.0f) * 16;
+    struct StageLayout {
+        int dext[3], light_bytes, data_off, data_bytes, stage_bytes;
+        size_t smem;
+    };
+    auto layout_of = [&](int h) {  // SMEM of the first-generation kernel for tiles of h rows
+        StageLayout L;
+        const int ext_p = kTW + (T.dmax[pa] - dmin_p_al) + 1, ext_q = h + (T.dmax[qa] - T.dmin[qa]) + 1, ext_s = kSB + (T.dmax[sa] - T.dmin[sa]) + 1;
+        L.dext[0] = (ext_p + 4 + 15) / 16 * 16, L.dext[1] = ext_q, L.dext[2] = ext_s;
+        L.light_bytes = kTW * h * kSB * (l8 ? 1 : 4);
+        L.data_off = mode == kModeCombine ? 2 * L.light_bytes : L.light_bytes;
+        L.data_bytes = L.dext[0] * L.dext[1] * L.dext[2];
+        L.stage_bytes = (L.data_off + L.data_bytes + 16 + 127) / 128 * 128;
+        L.smem = (size_t) kStages * L.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
+        return L;
+    };
+    // Tile rows. All tiles of a pass are co-resident and advance in lock step (each waits for its upstream neighbours every slice), so the pass
+    // runs at the pace of the fullest SM: 512^2 pixels in 64 x 8 tiles are 512 tiles on 148 SMs — 4 on most, 3 on the rest. 64 x 7 tiles are
+    // 592 = 4 x 148: every SM holds four 7-warp blocks, an eighth less work on the SMs that set the pace (measured: 5.02 -> 4.65 ms for the cfg2
+    // reset; 6 rows: 5.03 ms). First generation, R32F, unsharded single-wave passes (the slab exchange is laid out in 8-row units).
+    // TBRM_SWEEP_TH=7|8 or bits 8-9 of reserved[0] (2 / 3) ask for a height.
+    int th = ::tbrm::kTH;
+    if (!ws && !l8 && r.slab.nranks <= 1 && r.options.reserved[2] <= 0) {
+        static const int env_th = [] {
+            const char* e = getenv("TBRM_SWEEP_TH");
+            return e ? atoi(e) : 0;
+        }();
+        const int opt_th = (r.options.reserved[0] >> 8) & 3;
+        const int want = opt_th >= 2 ? 5 + opt_th : env_th;
+        const long long ntx_ = (tx + kTW - 1) / kTW;
+        auto tiles_of = [&](int h) { return ntx_ * ((ty + h - 1) / h); };
+        const bool pays = tiles_of(8) > sms && tiles_of(8) <= 4ll * sms && (tiles_of(7) + sms - 1) / sms * 7 < (tiles_of(8) + sms - 1) / sms * 8;
+        if (want == 7 || (want != 8 && pays)) {  // ... if the 7-row tiles are co-resident
+            int occ = 0;
+            bool fits = false;
+            if ((e = blocks_per_sm(tma_kernel(u.axis, clip, false, px, 7), 32 * 7, layout_of(7).smem, dev, &occ, &fits)) != cudaSuccess) return e;
+            if (fits && (long long) occ * sms >= tiles_of(7)) th = 7;
+        }
+    }
+    const int kTH = th;  // shadow the 8-row constant below
+    P.ntx = (tx + kTW - 1) / kTW, P.nty = (ty + kTH - 1) / kTH;
+    const int ntiles = P.ntx * P.nty;
     const int nat[3] = {pa, qa, sa};
     for (int t = 0; t < 3; ++t) {
         P.dmin[t] = T.dmin[nat[t]];
         P.data_dims_t[t] = r.ddims[nat[t]];
     }
-    // data box extents: tile (+1 tap, + spread of i0 - c), inner extent rounded up to 16 bytes (+4 for the funnel read)
-    // TMA needs the box origin 16-byte aligned along the innermost dimension: round the u8 box start down to 16 voxels
-    // (tile origins are multiples of 64), and widen the box accordingly.
-    const int dmin_p_al = (int) floorf((float) T.dmin[pa] / 16.0f) * 16;
     P.dmin[0] = dmin_p_al;
-    const int ext_p = kTW + (T.dmax[pa] - dmin_p_al) + 1, ext_q = kTH + (T.dmax[qa] - T.dmin[qa]) + 1,
-              ext_s = kSB + (T.dmax[sa] - T.dmin[sa]) + 1;
-    P.dext[0] = (ext_p + 4 + 15) / 16 * 16, P.dext[1] = ext_q, P.dext[2] = ext_s;
+    const StageLayout L = layout_of(th);
+    for (int t = 0; t < 3; ++t) P.dext[t] = L.dext[t];
     if (P.dext[0] > 256 || P.dext[1] > 256 || P.dext[2] > 256) return not_handled("P.dext[0] > 256 || P.dext[1] > 256 || P.dext[2] > 256");
     for (int d = 0; d < 2; ++d) P.bmin[d] = T.bmin[d], P.bext[d] = (d ? kTH : kTW) + (T.bmax[d] - T.bmin[d]) + 1;
     if (P.bext[0] > kFpW || P.bext[1] > kFpH) return not_handled("P.bext[0] > kFpW || P.bext[1] > kFpH");
@@ -683,18 +757,15 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         const int str[3] = {1, db[0], db[0] * db[1]};
         P.ds_q = str[qa], P.ds_s = str[sa];
     }
-    P.light_bytes = kTW * kTH * kSB * (l8 ? 1 : 4);
-    P.data_off = mode == kModeCombine ? 2 * P.light_bytes : P.light_bytes;
-    P.data_bytes = P.dext[0] * P.dext[1] * P.dext[2];
-    P.stage_bytes = (P.data_off + P.data_bytes + 16 + 127) / 128 * 128;
-    size_t smem = (size_t) kStages * P.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
+    P.light_bytes = L.light_bytes, P.data_off = L.data_off, P.data_bytes = L.data_bytes, P.stage_bytes = L.stage_bytes;
+    const int threads = ws ? kChThreads : 32 * th;
+    size_t smem = L.smem;
     if (ws) {  // T bricks, light bricks, footprints, mbarriers
         smem = (size_t) (kChTStages + kChLStages) * P.light_bytes + (size_t) 2 * kFpW * kFpH * sizeof(float) + (kChTStages + kChLStages) * sizeof(uint64_t) + 16;
         if (P.bext[0] * P.bext[1] - kChThreads > kChHaloOverflow) return not_handled("halo list");
     }
     P.scratch = (const float*) r.change_scratch;
 
-    const bool clip = !clip_is_inactive(u, T);
     // ---- which part of the pass this GPU runs, and in how many co-resident waves (bands of tile rows) ----
     const tbrm_slab& sl = r.slab;
     const bool sharded = sl.nranks > 1;
@@ -708,34 +779,16 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     }
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
-    const int threads = ws ? kChThreads : kTmaThreads;
-    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, px) : tma_kernel(u.axis, clip, false, px));
+    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, px) : tma_kernel(u.axis, clip, false, px, th));
     const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : tma_kernel(u.axis, clip, true, px);
-    {   // the shared-memory attribute and the occupancy of a (kernel, shared-memory size) pair are set / queried once
-        struct Known {
-            const void* kern;
-            size_t smem;
-            int dev, per_sm;
-        };
-        static thread_local std::vector<Known> known;
-        for (const void* k : {kern_plain, kern_slab}) {
-            const Known* hit = nullptr;
-            for (const Known& kn : known)
-                if (kn.kern == k && kn.smem == smem && kn.dev == dev) hit = &kn;
-            if (!hit) {
-                if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess) {
-                    cudaGetLastError();
-                    return not_handled("shared memory per block");
-                }
-                int occ = 0;
-                if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem)) != cudaSuccess) return e;
-                // another size may have been set for this kernel in between: drop stale entries of the kernel
-                known.erase(std::remove_if(known.begin(), known.end(), [&](const Known& kn) { return kn.kern == k && kn.dev == dev; }), known.end());
-                known.push_back({k, smem, dev, occ});
-                hit = &known.back();
-            }
-            if (k == kern_slab) per_sm = hit->per_sm;
-        }
+    {
+        int occ_plain = 0, occ_slab = 0;
+        bool fits = false;
+        if ((e = blocks_per_sm(kern_plain, threads, smem, dev, &occ_plain, &fits)) != cudaSuccess) return e;
+        if (!fits) return not_handled("shared memory per block");
+        if ((e = blocks_per_sm(kern_slab, threads, smem, dev, &occ_slab, &fits)) != cudaSuccess) return e;
+        if (!fits) return not_handled("shared memory per block");
+        per_sm = th == 7 ? occ_plain : occ_slab;  // 7-row tiles were chosen because one wave of the plain kernel holds them all
     }
     int cap_rows = (int) std::min<long long>((long long) sms * per_sm / P.ntx, 1 << 20);  // tile rows of one co-resident wave
     if (r.options.reserved[2] > 0) cap_rows = std::min(cap_rows, r.options.reserved[2]);      // test hook: force banding on small planes

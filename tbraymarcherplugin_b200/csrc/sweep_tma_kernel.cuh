@@ -86,8 +86,8 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 // read / write buffer would hold (the propagation buffers have the light volume's pixel format) — the light volume itself is updated with the
 // unquantised value, as in the shader. AddDirLight only. A byte brick of 4 slices along X has 4-byte rows (below TMA's 16): a sweep along X
 // works on a (y,z,x)-ordered copy of the light volume (the host permutes it there and back: three byte transposes, ~0.3 ms at 512^3).
-template <int AXIS, bool CLIP, bool SLAB, int PX, bool L8 = false>
-__global__ void __launch_bounds__(kTmaThreads, 4)
+template <int AXIS, bool CLIP, bool SLAB, int PX, bool L8 = false, int TH = 8>
+__global__ void __launch_bounds__(32 * TH, 4)
     sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
                      const __grid_constant__ CUtensorMap scratch_map, const __grid_constant__ PushMaps push_maps, const TmaParams P,
                      const float4* __restrict__ tf) {
@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
     const SweepUniforms& U = P.U;
     const int tx = U.td[0], ty = U.td[1], ns = U.td[2];
     const int tid = threadIdx.x;
+    // tile height (rows = warps of the block): 8, or 7 where that fills every SM with the same number of tiles (see the host's choice of th)
+    constexpr int kTH = TH, kTmaThreads = 32 * TH, kHaloOverflow = kFpW * kFpH - kHaloPerThread * kTmaThreads;  // shadow the constants of the 8-row tile
+    static_assert(TH == 7 || TH == 8, "tile rows");
     const int tix = (int) blockIdx.x % P.ntx, tiy = (SLAB ? P.S.tile_row0 : 0) + (int) blockIdx.x / P.ntx;
     const int tile = tiy * P.ntx + tix;
     const int row_lo = SLAB ? P.S.tile_row0 : 0, row_hi = SLAB ? P.S.tile_row0 + P.S.tile_rows : P.nty;  // tile rows of this launch
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4)
         }
         s_ndown = ndown;
     }
-    s_alpha[tid] = __ldg(&tf[tid]).w;
+    for (int c = tid; c < 256; c += kTmaThreads) s_alpha[c] = __ldg(&tf[c]).w;  // (one per thread for 8 rows)
     // footprint buffers: out-of-plane cells hold the sampler border colour for good, in-plane cells start as the
     // cleared buffer (LightAlpha) = "slice -1"
     for (int c = tid; c < FPW * kFpH; c += kTmaThreads) {

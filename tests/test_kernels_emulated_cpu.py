@@ -172,7 +172,7 @@ def test_emulated_lit_march_in_both_addressing_forms(emulated):
     M.test_lit_march_with_64_bit_tap_addressing_still_matches_oracle((1, 7, 1))
 
 
-@pytest.mark.parametrize("px_flag", [16, 32, 48])
+@pytest.mark.parametrize("px_flag", [16, 32, 48, 256 + 32, 512 + 16, 512 + 32])
 def test_emulated_tma_sweep_with_one_and_two_pixels_per_thread(emulated, px_flag):
     M.test_tma_sweep_with_one_and_two_pixels_per_thread((80, 24, 16), px_flag)
     M.test_tma_sweep_with_one_and_two_pixels_per_thread((64, 48, 40), px_flag)

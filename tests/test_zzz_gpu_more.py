@@ -272,8 +272,9 @@ def test_lit_march_with_64_bit_tap_addressing_still_matches_oracle(dims):
         res.release()
 
 
-# bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread, automatic; bit 6: the second kernel generation (occlusion kernel + chain kernel)
-@pytest.mark.parametrize("px_flag", [16, 32, 48, 64 + 16, 64 + 32])
+# bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread, automatic; bit 6: the second kernel generation (occlusion kernel + chain kernel);
+# bits 8-9: tiles of 6 / 7 / 8 rows (256 / 512 / 768; 0 = chosen per launch)
+@pytest.mark.parametrize("px_flag", [16, 32, 48, 64 + 16, 64 + 32, 256 + 16, 256 + 32, 512 + 16, 512 + 32, 768 + 48])
 @pytest.mark.parametrize("dims", [(64, 48, 40), (80, 24, 16), (128, 16, 8)])
 def test_tma_sweep_with_one_and_two_pixels_per_thread(dims, px_flag):
     """The TMA-staged sweep has a one-pixel-per-thread form (tile 32 x 8) for launches that cannot fill the SMs next to the two-pixel form
