@@ -76,7 +76,8 @@ struct TmaParams {
     int ntx, nty;
     float* ring;
     unsigned int* flags;
-    int dmin[3], dext[3];   // data-box offset / extent along transposed (p,q,s): box_p0 = tile_p0 + dmin[0], ...
+    int dmin[3], dext[3];   // data-box offset / extent along transposed (p,q,s): box_p0 = dk[0] * tile_p0 + dmin[0], ...
+    int dk[3];              // data voxels per light voxel along (p,q,s): 1, or 2 for a half-resolution light volume (one-pixel form only)
     int ds_q, ds_s;         // SMEM strides (bytes) of the data box along q and s
     int ls_p, ls_q, ls_s;   // SMEM strides (floats) of the light box
     int bmin[2], bext[2];   // footprint offset / extent in the buffer plane
@@ -216,9 +217,10 @@ struct HostTabs {
     std::vector<float> S[3], f[3];
     std::vector<int2> meta[3];
     std::vector<int2> bx, by;
-    int dmin[3], dmax[3];  // min / max of (i0 - c) per native axis
+    int dk[3];             // data voxels per light voxel along each native axis (1; 2 for a half-resolution light volume)
+    int dmin[3], dmax[3];  // min / max of (i0 - dk * c) per native axis
     int bmin[2], bmax[2];
-    bool pairs_ok = true;  // i0(c+1) == i0(c) + 1 everywhere along each axis
+    bool pairs_ok = true;  // i0(c+1) == i0(c) + 1 everywhere along each axis (the two-pixel forms share tap columns between neighbours)
     bool weights_lt_one = true;  // every trilinear weight is < 1 (needed by the exact empty-space skip)
 };
 
@@ -227,6 +229,7 @@ static void build_tabs(const SweepUniforms& u, const LightPass& L, HostTabs& T) 
         const int n = u.ldims[a], nd = u.ddims[a];
         T.S[a].resize(n), T.f[a].resize(n), T.meta[a].resize(n);
         T.dmin[a] = 1 << 30, T.dmax[a] = -(1 << 30);
+        const int dk = T.dk[a] = (n > 0 && nd % n == 0) ? nd / n : 1;
         for (int c = 0; c < n; ++c) {
             const float s = ((float) c + 0.5f) / (float) n + L.uvw_off[a];  // GetUVW + UVWOffset
             const float x = s * (float) nd - 0.5f;
@@ -237,7 +240,7 @@ static void build_tabs(const SweepUniforms& u, const LightPass& L, HostTabs& T) 
             const float sat = fminf(fmaxf(s, 0.0f), 1.0f);
             T.S[a][c] = s, T.f[a][c] = fr, T.meta[a][c] = make_int2(i0, s == sat ? 1 : 0);
             if (!(fr >= 0.0f && fr < 1.0f)) T.weights_lt_one = false;
-            T.dmin[a] = std::min(T.dmin[a], i0 - c), T.dmax[a] = std::max(T.dmax[a], i0 - c);
+            T.dmin[a] = std::min(T.dmin[a], i0 - dk * c), T.dmax[a] = std::max(T.dmax[a], i0 - dk * c);
             if (c > 0 && T.meta[a][c - 1].x + 1 != i0) T.pairs_ok = false;
         }
     }
@@ -574,7 +577,7 @@ cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool chang
 
 static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u, int mode, int* launches, bool* handled) {
     *handled = false;
-    if (r.data_fmt != TBRM_FMT_G8 || r.half_res) return not_handled("r.data_fmt != TBRM_FMT_G8 || r.half_res");
+    if (r.data_fmt != TBRM_FMT_G8) return not_handled("r.data_fmt != TBRM_FMT_G8");
     // a G8 light volume (the reference's default format): byte bricks — AddDirLight, sweeps along Y / Z, unsharded (a byte brick of 4 slices
     // along X has 4-byte rows, below TMA's 16-byte minimum; ChangeDirLight keeps its removed light in an R32F scratch volume)
     const bool l8 = r.light_fmt == TBRM_FMT_G8;
@@ -598,7 +601,9 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
 
     HostTabs T;
     build_tabs(u, u.a, T);
-    if (!T.pairs_ok) return not_handled("!T.pairs_ok");
+    // the two-pixel forms (and the second generation) share tap columns between neighbouring pixels: unit stride from pixel to data voxel.
+    // A half-resolution light volume (two data voxels per light voxel) or irregular tap tables take the one-pixel form.
+    const bool unit_stride = T.pairs_ok && T.dk[0] == 1 && T.dk[1] == 1 && T.dk[2] == 1;
     const int tx = u.td[0], ty = u.td[1];
     TmaParams P;
     memset(&P, 0, sizeof(P));
@@ -614,7 +619,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         return e ? atoi(e) : 1;
     }();
     // (the chain kernel of the second generation walks whole blocks of kSB slices: other slice counts take the first generation)
-    const bool ws = (env_gen == 2 || (r.options.reserved[0] & 64)) && u.td[2] % kSB == 0 && r.light_fmt == TBRM_FMT_R32F;
+    const bool ws = (env_gen == 2 || (r.options.reserved[0] & 64)) && u.td[2] % kSB == 0 && r.light_fmt == TBRM_FMT_R32F && unit_stride;
     int px = 2;
     {
         static const int env_px = [] {  // 1 / 2 forced, 3 automatic (default)
@@ -632,6 +637,10 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
             // doubled tiles still fit three to an SM: max(0.73 L, ceil(2 t / SMs) * 0.73 T) < max(L, ceil(t / SMs) * T)
             px = (2 * tiles64 <= 3ll * sms) ? 1 : 2;
         }
+        if (!unit_stride) {
+            if (want == 2) return not_handled("two pixels per thread need unit stride from pixel to data voxel");
+            px = 1;
+        }
     }
     const int kTW = 32 * px, kFpW = kTW + 4;  // shadow the two-pixel constants below
     const bool clip = !clip_is_inactive(u, T);
@@ -647,7 +656,9 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     };
     auto layout_of = [&](int h) {  // SMEM of the first-generation kernel for tiles of h rows
         StageLayout L;
-        const int ext_p = kTW + (T.dmax[pa] - dmin_p_al) + 1, ext_q = h + (T.dmax[qa] - T.dmin[qa]) + 1, ext_s = kSB + (T.dmax[sa] - T.dmin[sa]) + 1;
+        // first tap of the first pixel .. second tap of the last pixel: dk * (pixels - 1) + spread of (i0 - dk * c) + 2
+        const int ext_p = T.dk[pa] * (kTW - 1) + (T.dmax[pa] - dmin_p_al) + 2, ext_q = T.dk[qa] * (h - 1) + (T.dmax[qa] - T.dmin[qa]) + 2,
+                  ext_s = T.dk[sa] * (kSB - 1) + (T.dmax[sa] - T.dmin[sa]) + 2;
         L.dext[0] = (ext_p + 4 + 15) / 16 * 16, L.dext[1] = ext_q, L.dext[2] = ext_s;
         L.light_bytes = kTW * h * kSB * (l8 ? 1 : 4);
         L.data_off = mode == kModeCombine ? 2 * L.light_bytes : L.light_bytes;
@@ -684,7 +695,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int ntiles = P.ntx * P.nty;
     const int nat[3] = {pa, qa, sa};
     for (int t = 0; t < 3; ++t) {
-        P.dmin[t] = T.dmin[nat[t]];
+        P.dmin[t] = T.dmin[nat[t]], P.dk[t] = T.dk[nat[t]];
         P.data_dims_t[t] = r.ddims[nat[t]];
     }
     P.dmin[0] = dmin_p_al;

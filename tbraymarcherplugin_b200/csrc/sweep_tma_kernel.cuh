@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(32 * TH, 4)
     const int2 mp0 = __ldg(&P.A.ax[PA].meta[pxc]), mp1 = __ldg(&P.A.ax[PA].meta[px1c]), mq = __ldg(&P.A.ax[QA].meta[pyc]);
     const float fp0 = __ldg(&P.A.ax[PA].f[pxc]), fp1 = __ldg(&P.A.ax[PA].f[px1c]), fq = __ldg(&P.A.ax[QA].f[pyc]);
     const int dN_p = P.data_dims_t[0], dN_q = P.data_dims_t[1], dN_s = P.data_dims_t[2];
-    const int col = mp0.x - (x0 + P.dmin[0]);  // column of the first tap inside the data box
-    const int rowq = mq.x - (y0 + P.dmin[1]);
+    const int col = mp0.x - (x0 * P.dk[0] + P.dmin[0]);  // column of the first tap inside the data box
+    const int rowq = mq.x - (y0 * P.dk[1] + P.dmin[1]);
     const bool inP0 = (unsigned) mp0.x < (unsigned) dN_p, inP1 = (unsigned) (mp0.x + 1) < (unsigned) dN_p,
                inP2 = PX == 1 || (unsigned) (mp0.x + 2) < (unsigned) dN_p;  // the third tap column belongs to the second pixel
     const bool inQ0 = (unsigned) mq.x < (unsigned) dN_q, inQ1 = (unsigned) (mq.x + 1) < (unsigned) dN_q;
@@ -307,9 +307,9 @@ __global__ void __launch_bounds__(32 * TH, 4)
         if (P.mode == kModeCombine) tma_load_3d(sb + P.light_bytes, &scratch_map, lc[0], lc[1], lc[2], &s_bar[st]);
         // data map: native dims for Z / Y sweeps, the (y,z,x) replica for X sweeps, i.e. (p,q,s)-ordered for X
         if (AXIS == 0) {
-            tma_load_3d(sb + P.data_off, &data_map, x0 + P.dmin[0], y0 + P.dmin[1], s0 + P.dmin[2], &s_bar[st]);
+            tma_load_3d(sb + P.data_off, &data_map, x0 * P.dk[0] + P.dmin[0], y0 * P.dk[1] + P.dmin[1], s0 * P.dk[2] + P.dmin[2], &s_bar[st]);
         } else {
-            dc[PA] = x0 + P.dmin[0], dc[QA] = y0 + P.dmin[1], dc[SA] = s0 + P.dmin[2];
+            dc[PA] = x0 * P.dk[0] + P.dmin[0], dc[QA] = y0 * P.dk[1] + P.dmin[1], dc[SA] = s0 * P.dk[2] + P.dmin[2];
             tma_load_3d(sb + P.data_off, &data_map, dc[0], dc[1], dc[2], &s_bar[st]);
         }
     };
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(32 * TH, 4)
             // ---- (b) opacity toward the light for this thread's two voxels (independent of the previous slice) ----
             const int2 ms = __ldg(&P.A.ax[SA].meta[loop]);
             const float fs = __ldg(&P.A.ax[SA].f[loop]);
-            const int rows = ms.x - (s0 + P.dmin[2]);
+            const int rows = ms.x - (s0 * P.dk[2] + P.dmin[2]);
             const bool inS01 = (unsigned) ms.x < (unsigned) (dN_s - 1);  // taps ms.x and ms.x + 1 both inside (dN_s >= 1)
             float w0 = 1.0f, w1 = 1.0f;
             if (CLIP) {

@@ -172,6 +172,11 @@ def test_emulated_lit_march_in_both_addressing_forms(emulated):
     M.test_lit_march_with_64_bit_tap_addressing_still_matches_oracle((1, 7, 1))
 
 
+@pytest.mark.parametrize("light32", [True, False])
+def test_emulated_half_resolution_light_volume_through_the_tma_staged_sweep(emulated, light32):
+    M.test_half_resolution_light_volume_through_the_tma_staged_sweep((64, 64, 40), light32)
+
+
 @pytest.mark.parametrize("px_flag", [16, 32, 48, 256 + 32, 512 + 16, 512 + 32])
 def test_emulated_tma_sweep_with_one_and_two_pixels_per_thread(emulated, px_flag):
     M.test_tma_sweep_with_one_and_two_pixels_per_thread((80, 24, 16), px_flag)

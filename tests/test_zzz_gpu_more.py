@@ -272,6 +272,43 @@ def test_lit_march_with_64_bit_tap_addressing_still_matches_oracle(dims):
         res.release()
 
 
+@pytest.mark.parametrize("light32", [True, False])
+@pytest.mark.parametrize("dims", [(64, 64, 40), (96, 32, 64)])  # (a G8 light volume's TMA strides: X and Y of the LIGHT volume multiples of 16)
+def test_half_resolution_light_volume_through_the_tma_staged_sweep(dims, light32):
+    """A half-resolution light volume (RaymarchVolume.h: LightVolumeHalfResolution; two data voxels per light voxel along every axis) runs the
+    TMA-staged sweep in its one-pixel form: the data box of a tile starts at twice the tile's origin and spans twice its extent. R32F and G8,
+    AddDirLight (oblique and axis-aligned lights), ChangeDirLight on R32F, with and without a clip plane — bit-exact against the oracle."""
+    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats
+
+    data = synth.perlin_ct_volume(dims)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    for world in (synth.identity_world(), synth.clipped_world()):
+        res = URaymarchUtils.InitializeRaymarchResources(dims, FMT_G8, bLightVolume32Bit=light32, LightVolumeHalfResolution=True)
+        URaymarchUtils.SetDataVolume(res, data)
+        URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
+        URaymarchUtils.SetWindowingParameters(res, win)
+        URaymarchUtils.SetOptions(res, sweep_impl=2)
+        vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win, light32=light32, half_res=True)
+        assert tuple(res.LightDims) == tuple(vol.ldims) == tuple(d // 2 for d in dims)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        used = []
+        for l in synth.LIGHTS + [FDirLightParameters((1, 0, 0), 0.7), FDirLightParameters((0.1, 0.2, 1.0), 0.4)]:
+            st = FSweepStats()
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
+            vol.add_dir_light(l, True, world)
+            used.append(tuple(st.impl))
+            assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), (dims, light32, l.LightDirection, st.impl)
+        if dims == (64, 64, 40):  # (on the flat volume a second-axis pass reads further across the plane than the kernel's footprint holds)
+            assert all(set(i) == {3} for i in used[:3]), f"the TMA-staged sweep must have taken every pass of the oblique lights: {used}"
+        assert all(3 in i for i in used[:3]), used
+        if light32:
+            n = synth.rotate_about_z(synth.LIGHTS[0], 20.0)
+            assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], n, world, bGPUSync=True)
+            vol.change_dir_light(synth.LIGHTS[0], n, world)
+            assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), (dims, "change")
+        res.release()
+
+
 # bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread, automatic; bit 6: the second kernel generation (occlusion kernel + chain kernel);
 # bits 8-9: tiles of 6 / 7 / 8 rows (256 / 512 / 768; 0 = chosen per launch)
 @pytest.mark.parametrize("px_flag", [16, 32, 48, 64 + 16, 64 + 32, 256 + 16, 256 + 32, 512 + 16, 512 + 32, 768 + 48])
