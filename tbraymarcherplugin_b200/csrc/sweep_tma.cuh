@@ -79,7 +79,8 @@ struct TmaParams {
     int dmin[3], dext[3];   // data-box offset / extent along transposed (p,q,s): box_p0 = dk[0] * tile_p0 + dmin[0], ...
     int dk[3];              // data voxels per light voxel along (p,q,s): 1, or 2 for a half-resolution light volume (one-pixel form only)
     int ds_q, ds_s;         // SMEM strides (bytes) of the data box along q and s
-    int ls_p, ls_q, ls_s;   // SMEM strides (floats) of the light box
+    int ls_p, ls_q, ls_s;   // SMEM strides (elements) of the light box
+    int ss_p, ss_q, ss_s;   // ... of the scratch box of a combining launch (differs from the light box's for a G8 sweep along X)
     int bmin[2], bext[2];   // footprint offset / extent in the buffer plane
     int data_dims_t[3];     // data dims in transposed (p,q,s) order
     int stage_bytes, light_bytes, data_bytes;
@@ -321,11 +322,14 @@ static void pack(std::vector<unsigned char>& staging, const tbrm_resources& r, c
     *dptr = (const char*) r.tables + off;
 }
 
-static const void* tma_kernel_l8(int axis, bool clip, int px) {  // G8 light volume: AddDirLight, unsharded
+static const void* tma_kernel_l8(int axis, bool clip, int px, int th = 8) {  // G8 light volume: AddDirLight, unsharded
 #define TBRM_K(A, PX) (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, true> : (const void*) sweep_tma_kernel<A, false, false, PX, true>)
+#define TBRM_K7(A) (clip ? (const void*) sweep_tma_kernel<A, true, false, 2, true, 7> : (const void*) sweep_tma_kernel<A, false, false, 2, true, 7>)
+    if (th == 7 && px == 2) return axis == 0 ? TBRM_K7(0) : (axis == 1 ? TBRM_K7(1) : TBRM_K7(2));  // 7-row tiles: two-pixel form only
     if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
     return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
 #undef TBRM_K
+#undef TBRM_K7
 }
 
 static const void* tma_kernel(int axis, bool clip, bool slab, int px, int th = 8) {
@@ -551,7 +555,6 @@ static cudaError_t blocks_per_sm(const void* kern, int threads, size_t smem, int
 cudaError_t sweep_pass_tma(tbrm_resources& r, const SweepUniforms& u, bool change, int* launches, bool* handled) {
     if (!change) return sweep_pass_tma_mode(r, u, kModeAdd, launches, handled);
     *handled = false;
-    if (r.light_fmt != TBRM_FMT_R32F) return not_handled("ChangeDirLight on a G8 light volume");
     cudaError_t e;
     if (!r.change_scratch && (e = cudaMalloc(&r.change_scratch, r.light_voxels() * sizeof(float))) != cudaSuccess) return e;
     SweepUniforms ur = u;
@@ -581,7 +584,10 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // a G8 light volume (the reference's default format): byte bricks — AddDirLight, sweeps along Y / Z, unsharded (a byte brick of 4 slices
     // along X has 4-byte rows, below TMA's 16-byte minimum; ChangeDirLight keeps its removed light in an R32F scratch volume)
     const bool l8 = r.light_fmt == TBRM_FMT_G8;
-    if (l8 && (mode != kModeAdd || r.slab.nranks > 1)) return not_handled("G8 light volume: ChangeDirLight / sharded volume");
+    if (l8 && r.slab.nranks > 1) return not_handled("G8 light volume of a sharded volume");
+    // the brick a G8 pass loads, updates and stores is bytes of the light volume — except for the removed light of a ChangeDirLight, whose
+    // propagated light goes to the R32F scratch volume (its forwarded values are still quantised like the G8 propagation buffers)
+    const bool byte_brick = l8 && mode != kModeStore;
     const int X = r.ddims[0], Y = r.ddims[1], Z = r.ddims[2];
     if (X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)) return not_handled("X % 16 != 0 || (u.axis == 0 && Y % 16 != 0)");  // TMA global strides must be multiples of 16 bytes
     if (((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)) return not_handled("((uintptr_t) r.data & 15) || ((uintptr_t) r.light & 15)");
@@ -660,8 +666,8 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         const int ext_p = T.dk[pa] * (kTW - 1) + (T.dmax[pa] - dmin_p_al) + 2, ext_q = T.dk[qa] * (h - 1) + (T.dmax[qa] - T.dmin[qa]) + 2,
                   ext_s = T.dk[sa] * (kSB - 1) + (T.dmax[sa] - T.dmin[sa]) + 2;
         L.dext[0] = (ext_p + 4 + 15) / 16 * 16, L.dext[1] = ext_q, L.dext[2] = ext_s;
-        L.light_bytes = kTW * h * kSB * (l8 ? 1 : 4);
-        L.data_off = mode == kModeCombine ? 2 * L.light_bytes : L.light_bytes;
+        L.light_bytes = kTW * h * kSB * (byte_brick ? 1 : 4);
+        L.data_off = L.light_bytes + (mode == kModeCombine ? kTW * h * kSB * 4 : 0);  // combining: the removed light's R32F brick follows
         L.data_bytes = L.dext[0] * L.dext[1] * L.dext[2];
         L.stage_bytes = (L.data_off + L.data_bytes + 16 + 127) / 128 * 128;
         L.smem = (size_t) kStages * L.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
@@ -670,10 +676,10 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // Tile rows. All tiles of a pass are co-resident and advance in lock step (each waits for its upstream neighbours every slice), so the pass
     // runs at the pace of the fullest SM: 512^2 pixels in 64 x 8 tiles are 512 tiles on 148 SMs — 4 on most, 3 on the rest. 64 x 7 tiles are
     // 592 = 4 x 148: every SM holds four 7-warp blocks, an eighth less work on the SMs that set the pace (measured: 5.02 -> 4.65 ms for the cfg2
-    // reset; 6 rows: 5.03 ms). First generation, R32F, unsharded single-wave passes (the slab exchange is laid out in 8-row units).
+    // reset; 6 rows: 5.03 ms). First generation, unsharded single-wave passes (the slab exchange is laid out in 8-row units).
     // TBRM_SWEEP_TH=7|8 or bits 8-9 of reserved[0] (2 / 3) ask for a height.
     int th = ::tbrm::kTH;
-    if (!ws && !l8 && r.slab.nranks <= 1 && r.options.reserved[2] <= 0) {
+    if (!ws && !(l8 && px == 1) && r.slab.nranks <= 1 && r.options.reserved[2] <= 0) {
         static const int env_th = [] {
             const char* e = getenv("TBRM_SWEEP_TH");
             return e ? atoi(e) : 0;
@@ -686,7 +692,8 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         if (want == 7 || (want != 8 && pays)) {  // ... if the 7-row tiles are co-resident
             int occ = 0;
             bool fits = false;
-            if ((e = blocks_per_sm(tma_kernel(u.axis, clip, false, px, 7), 32 * 7, layout_of(7).smem, dev, &occ, &fits)) != cudaSuccess) return e;
+            const void* k7 = l8 ? tma_kernel_l8(u.axis, clip, px, 7) : tma_kernel(u.axis, clip, false, px, 7);
+            if ((e = blocks_per_sm(k7, 32 * 7, layout_of(7).smem, dev, &occ, &fits)) != cudaSuccess) return e;
             if (fits && (long long) occ * sms >= tiles_of(7)) th = 7;
         }
     }
@@ -716,7 +723,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     lbox[pa] = kTW, lbox[qa] = kTH, lbox[sa] = kSB;
     CUtensorMap lm, dm, sm;
     // the brick that is loaded, updated and stored: the light volume, or the scratch volume when the light is only stored
-    const bool l8_x = l8 && u.axis == 0;  // a G8 volume's sweep along X works on a (y,z,x)-ordered copy of the light volume (see the kernel)
+    const bool l8_x = byte_brick && u.axis == 0;  // a G8 volume's sweep along X works on a (y,z,x)-ordered copy of the light volume (see the kernel)
     if (l8_x) {
         const size_t lbytes = r.light_voxels();
         if (r.light_perm_bytes < lbytes) {
@@ -728,11 +735,11 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         }
         const int pd[3] = {r.ldims[1], r.ldims[2], r.ldims[0]}, pb[3] = {kTW, kTH, kSB};  // (p,q,s) = (y,z,x)
         if (!make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.light_perm[0], pd, pb)) return not_handled("tensor map of the permuted G8 light volume");
-    } else if (l8 ? !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.light, ldims, lbox)
+    } else if (byte_brick ? !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, r.light, ldims, lbox)
            : !make_map3(&lm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeStore ? r.change_scratch : r.light, ldims, lbox))
         return not_handled("tensor map of the light volume");
-    if (l8)
-        sm = lm;  // never read (AddDirLight only)
+    if (l8 && mode != kModeCombine)
+        sm = lm;  // never read
     else if (!make_map3(&sm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, mode == kModeCombine ? r.change_scratch : r.light, ldims, lbox))
         return not_handled("tensor map of the scratch volume");
     P.mode = mode;
@@ -754,6 +761,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     {
         const int str[3] = {1, lbox[0], lbox[0] * lbox[1]};
         P.ls_p = str[pa], P.ls_q = str[qa], P.ls_s = str[sa];
+        P.ss_p = P.ls_p, P.ss_q = P.ls_q, P.ss_s = P.ls_s;  // the scratch brick (combining) is always in native order
         if (l8_x) P.ls_p = 1, P.ls_q = kTW, P.ls_s = kTW * kTH;
     }
     if (u.axis == 0) {
@@ -790,7 +798,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     }
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
-    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, px) : tma_kernel(u.axis, clip, false, px, th));
+    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, px, th) : tma_kernel(u.axis, clip, false, px, th));
     const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : tma_kernel(u.axis, clip, true, px);
     {
         int occ_plain = 0, occ_slab = 0;

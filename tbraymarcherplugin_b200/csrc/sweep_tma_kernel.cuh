@@ -84,8 +84,13 @@ __device__ __forceinline__ float opacity_from_value(float v, const Windowing& wi
 // L8 = the light volume is G8 (UNORM8, the reference's default: RaymarchVolume.h:198-199, RaymarchVolume.cpp:857-861): the light brick is a
 // byte brick (load -> v / 255, store -> floor(saturate(v) * 255 + 0.5)), and what a slice forwards to the next one is the value its G8
 // read / write buffer would hold (the propagation buffers have the light volume's pixel format) — the light volume itself is updated with the
-// unquantised value, as in the shader. AddDirLight only. A byte brick of 4 slices along X has 4-byte rows (below TMA's 16): a sweep along X
-// works on a (y,z,x)-ordered copy of the light volume (the host permutes it there and back: three byte transposes, ~0.3 ms at 512^3).
+// unquantised value, as in the shader. ChangeDirLight: the removed light's launch keeps an R32F brick (the scratch volume) and only quantises
+// what it forwards; the added light's launch has the byte brick with the removed light's R32F brick behind it. A byte brick of 4 slices along
+// X has 4-byte rows (below TMA's 16): a sweep along X works on a (y,z,x)-ordered copy of the light volume (the host permutes it there and
+// back: three byte transposes, ~0.3 ms at 512^3).
+// TH = rows of a tile (= warps of a block): 8, or 7 where 64 x 7 tiles fill every SM with the same number of blocks (the host's choice of th).
+// A half-resolution light volume (P.dk = 2 data voxels per light voxel) runs in the one-pixel form: the data box of a tile starts at
+// dk * the tile's origin and spans dk * its extent.
 template <int AXIS, bool CLIP, bool SLAB, int PX, bool L8 = false, int TH = 8>
 __global__ void __launch_bounds__(32 * TH, 4)
     sweep_tma_kernel(const __grid_constant__ CUtensorMap light_map, const __grid_constant__ CUtensorMap data_map,
@@ -300,11 +305,12 @@ __global__ void __launch_bounds__(32 * TH, 4)
         unsigned char* sb = stage_base + (size_t) st * P.stage_bytes;
         mbar_expect_tx(&s_bar[st], (uint32_t) (P.data_off + P.data_bytes));
         const int s0 = block_s0(b);
-        int lc[3], dc[3];
-        lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;  // light map is over native (x,y,z)
-        if (L8 && AXIS == 0) lc[0] = x0, lc[1] = y0, lc[2] = s0;  // ... except a G8 volume's sweep along X: its (y,z,x)-ordered copy, i.e. (p,q,s)
+        int lc[3], nc[3], dc[3];
+        nc[PA] = x0, nc[QA] = y0, nc[SA] = s0;  // light and scratch maps are over native (x,y,z)
+        lc[0] = nc[0], lc[1] = nc[1], lc[2] = nc[2];
+        if (L8 && AXIS == 0 && P.mode != kModeStore) lc[0] = x0, lc[1] = y0, lc[2] = s0;  // ... except the byte brick of a G8 volume's sweep along X: its (y,z,x)-ordered copy, i.e. (p,q,s)
         tma_load_3d(sb, &light_map, lc[0], lc[1], lc[2], &s_bar[st]);
-        if (P.mode == kModeCombine) tma_load_3d(sb + P.light_bytes, &scratch_map, lc[0], lc[1], lc[2], &s_bar[st]);
+        if (P.mode == kModeCombine) tma_load_3d(sb + P.light_bytes, &scratch_map, nc[0], nc[1], nc[2], &s_bar[st]);
         // data map: native dims for Z / Y sweeps, the (y,z,x) replica for X sweeps, i.e. (p,q,s)-ordered for X
         if (AXIS == 0) {
             tma_load_3d(sb + P.data_off, &data_map, x0 * P.dk[0] + P.dmin[0], y0 * P.dk[1] + P.dmin[1], s0 * P.dk[2] + P.dmin[2], &s_bar[st]);
@@ -544,10 +550,16 @@ __global__ void __launch_bounds__(32 * TH, 4)
                 // pixels beyond a ragged plane edge (v0 / v1 false) update their cell of the SMEM brick too: the TMA store clips the brick
                 // to the light volume, so those cells never reach memory — no validity test per slice
                 float* lp = s_light + light_off + (loop - s0) * P.ls_s;
-                if (L8) {  // AddDirLightShader.usf:121-126 on a G8 light volume (the host sends only AddDirLight here)
+                if (L8 && P.mode == kModeAdd) {  // AddDirLightShader.usf:121-126 on a G8 light volume
                     unsigned char* lp8 = (unsigned char*) s_light + light_off + (loop - s0) * P.ls_s;
                     if (fabsf(cur0) > 1e-3f) lp8[0] = quant8(decode_u8((uint32_t) lp8[0]) + (cur0 * U.sign));
                     if (PX == 2 && fabsf(cur1) > 1e-3f) lp8[P.ls_p] = quant8(decode_u8((uint32_t) lp8[P.ls_p]) + (cur1 * U.sign));
+                } else if (L8 && P.mode == kModeCombine) {  // ChangeDirLightShader.usf:146-153 on a G8 light volume: byte brick, R32F brick of the removed light behind it
+                    unsigned char* lp8 = (unsigned char*) s_light + light_off + (loop - s0) * P.ls_s;
+                    const float* rp = (const float*) ((const unsigned char*) s_light + P.light_bytes) + lx * P.ss_p + ly * P.ss_q + (loop - s0) * P.ss_s;
+                    const float r0c = rp[0], r1c = PX == 2 ? rp[P.ss_p] : 0.0f;
+                    if (fabsf(cur0 - r0c) > 1e-3f) lp8[0] = quant8(decode_u8((uint32_t) lp8[0]) + cur0 - r0c);
+                    if (PX == 2 && fabsf(cur1 - r1c) > 1e-3f) lp8[P.ls_p] = quant8(decode_u8((uint32_t) lp8[P.ls_p]) + cur1 - r1c);
                 } else if (P.mode == kModeAdd) {  // AddDirLightShader.usf:121-126
                     if (fabsf(cur0) > 1e-3f) lp[0] = lp[0] + (cur0 * U.sign);
                     if (PX == 2 && fabsf(cur1) > 1e-3f) lp[P.ls_p] = lp[P.ls_p] + (cur1 * U.sign);
@@ -568,7 +580,7 @@ __global__ void __launch_bounds__(32 * TH, 4)
         if (tid == 0) {
             int lc[3];
             lc[PA] = x0, lc[QA] = y0, lc[SA] = s0;
-            if (L8 && AXIS == 0) lc[0] = x0, lc[1] = y0, lc[2] = s0;
+            if (L8 && AXIS == 0 && P.mode != kModeStore) lc[0] = x0, lc[1] = y0, lc[2] = s0;
             tma_store_3d(&light_map, lc[0], lc[1], lc[2], s_light);
             // push-gather: the finished brick also goes into every other rank's light volume (NVLink), in the same bulk group — the transfer
             // overlaps the sweep tile by tile, and no all-gather of the light slabs follows the sweep

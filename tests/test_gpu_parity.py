@@ -91,9 +91,10 @@ def test_g8_and_half_resolution_light_volumes(light32, half_res, impl):
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"light32={light32} half_res={half_res}")
 
 
+@pytest.mark.parametrize("th_flag", [0, 512 + 32])  # bits 8-9 of reserved[0] = 2: tiles of 7 rows (what a 512^2 plane takes on 148 SMs), two pixels per thread
 @pytest.mark.parametrize("world_name", ["identity", "clipped"])
 @pytest.mark.parametrize("dims", [(64, 48, 40), (128, 32, 16), (64, 64, 64)])
-def test_g8_light_volume_through_the_tma_staged_sweep_and_the_fast_march(dims, world_name):
+def test_g8_light_volume_through_the_tma_staged_sweep_and_the_fast_march(dims, world_name, th_flag):
     """G8 is the reference's DEFAULT light-volume format (RaymarchVolume.h:198-199). Sweeps along Y / Z of an AddDirLight run the TMA-staged
     kernel on byte bricks (forwarded values quantised like the G8 read / write buffers, the light volume updated with the unquantised value);
     sweeps along X take the generic fused kernel; the lit march's fast kernels decode the G8 light taps. All bit-exact against the oracle."""
@@ -102,6 +103,7 @@ def test_g8_light_volume_through_the_tma_staged_sweep_and_the_fast_march(dims, w
     data = synth.perlin_ct_volume(dims)
     world = WORLDS[world_name]()
     res, ora = make_pair(data, synth.soft_ct_curve(), CT_WINDOW, light32=False, sweep_impl=2)
+    URaymarchUtils.SetOptions(res, sweep_impl=2, debug_flags=(th_flag, 0))
     impls = []
     for light in synth.LIGHTS + [FDirLightParameters((0.0, -1.0, 0.0), 0.3), FDirLightParameters((0.1, 0.2, 1.0), 0.4)]:
         st = FSweepStats()
@@ -118,6 +120,15 @@ def test_g8_light_volume_through_the_tma_staged_sweep_and_the_fast_march(dims, w
     URaymarchUtils.AddDirLightToSingleVolume(res, synth.LIGHTS[2], False, world, bGPUSync=True)
     ora.add_dir_light(synth.LIGHTS[2], False, world)
     assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, "G8 light volume after a removal")
+    # ChangeDirLight on the G8 volume: the removed light's sweep writes an R32F scratch volume, the added light's combines it into the byte bricks
+    for old, deg in ((synth.LIGHTS[0], 20.0), (synth.LIGHTS[1], -35.0)):
+        new = synth.rotate_about_z(old, deg)
+        st = FSweepStats()
+        assert URaymarchUtils.ChangeDirLightInSingleVolume(res, old, new, world, bGPUSync=True, stats=st)
+        ora.change_dir_light(old, new, world)
+        assert_same(URaymarchUtils.ReadLightVolume(res), ora.light, f"G8 light volume after ChangeDirLight by {deg} degrees (impl {st.impl})")
+        if dims != (128, 32, 16):
+            assert 3 in st.impl, st.impl
     cam = synth.benchmark_camera(96, 64)
     rgba, steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 80.0)
     ref, ref_steps = ora.raymarch_lit(cam, world, 80.0)

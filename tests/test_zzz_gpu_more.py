@@ -277,7 +277,7 @@ def test_lit_march_with_64_bit_tap_addressing_still_matches_oracle(dims):
 def test_half_resolution_light_volume_through_the_tma_staged_sweep(dims, light32):
     """A half-resolution light volume (RaymarchVolume.h: LightVolumeHalfResolution; two data voxels per light voxel along every axis) runs the
     TMA-staged sweep in its one-pixel form: the data box of a tile starts at twice the tile's origin and spans twice its extent. R32F and G8,
-    AddDirLight (oblique and axis-aligned lights), ChangeDirLight on R32F, with and without a clip plane — bit-exact against the oracle."""
+    AddDirLight (oblique and axis-aligned lights), ChangeDirLight, with and without a clip plane — bit-exact against the oracle."""
     from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats
 
     data = synth.perlin_ct_volume(dims)
@@ -301,11 +301,10 @@ def test_half_resolution_light_volume_through_the_tma_staged_sweep(dims, light32
         if dims == (64, 64, 40):  # (on the flat volume a second-axis pass reads further across the plane than the kernel's footprint holds)
             assert all(set(i) == {3} for i in used[:3]), f"the TMA-staged sweep must have taken every pass of the oblique lights: {used}"
         assert all(3 in i for i in used[:3]), used
-        if light32:
-            n = synth.rotate_about_z(synth.LIGHTS[0], 20.0)
-            assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], n, world, bGPUSync=True)
-            vol.change_dir_light(synth.LIGHTS[0], n, world)
-            assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), (dims, "change")
+        n = synth.rotate_about_z(synth.LIGHTS[0], 20.0)
+        assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], n, world, bGPUSync=True)
+        vol.change_dir_light(synth.LIGHTS[0], n, world)
+        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), (dims, light32, "change")
         res.release()
 
 
