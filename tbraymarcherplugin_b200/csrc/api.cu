@@ -722,8 +722,10 @@ tbrm_status tbrm_slab_configure(tbrm_resources* r, const tbrm_slab* slab) {
         int32_t zb, ze;
         slab_partition(r->ldims[2], slab->nranks, slab->rank, &zb, &ze);
         TBRM_REQUIRE(zb == slab->z_begin && ze == slab->z_end && zb < ze, "tbrm_slab_configure: the slab must follow tbrm_slab_partition and be non-empty");
-        if (r->data_fmt != TBRM_FMT_G8 || r->light_fmt != TBRM_FMT_R32F || r->half_res || r->ddims[0] % 16 || r->ddims[1] % 16 || r->ddims[2] % 8) {
-            set_last_error("tbrm_slab_configure: sharding needs R8 data, an R32F full-resolution light volume, X % 16 == 0, Y % 16 == 0, Z % 8 == 0");
+        const bool l8 = r->light_fmt == TBRM_FMT_G8;  // byte bricks: the light volume's own X and Y are TMA strides
+        if (r->data_fmt != TBRM_FMT_G8 || (r->light_fmt != TBRM_FMT_R32F && !l8) || r->ddims[0] % 16 || r->ddims[1] % 16 || r->ddims[2] % 8 || r->ldims[2] % 8 ||
+            (l8 && (r->ldims[0] % 16 || r->ldims[1] % 16))) {
+            set_last_error("tbrm_slab_configure: sharding needs R8 data, an R32F or G8 light volume, X % 16 == 0, Y % 16 == 0, Z % 8 == 0 (G8: of the light volume too)");
             return TBRM_ERR_UNSUPPORTED;
         }
     }

@@ -322,10 +322,11 @@ static void pack(std::vector<unsigned char>& staging, const tbrm_resources& r, c
     *dptr = (const char*) r.tables + off;
 }
 
-static const void* tma_kernel_l8(int axis, bool clip, int px, int th = 8) {  // G8 light volume: AddDirLight, unsharded
-#define TBRM_K(A, PX) (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, true> : (const void*) sweep_tma_kernel<A, false, false, PX, true>)
+static const void* tma_kernel_l8(int axis, bool clip, bool slab, int px, int th = 8) {  // G8 light volume
+#define TBRM_K(A, PX) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true, PX, true> : (const void*) sweep_tma_kernel<A, false, true, PX, true>) \
+                            : (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, true> : (const void*) sweep_tma_kernel<A, false, false, PX, true>))
 #define TBRM_K7(A) (clip ? (const void*) sweep_tma_kernel<A, true, false, 2, true, 7> : (const void*) sweep_tma_kernel<A, false, false, 2, true, 7>)
-    if (th == 7 && px == 2) return axis == 0 ? TBRM_K7(0) : (axis == 1 ? TBRM_K7(1) : TBRM_K7(2));  // 7-row tiles: two-pixel form only
+    if (th == 7 && px == 2 && !slab) return axis == 0 ? TBRM_K7(0) : (axis == 1 ? TBRM_K7(1) : TBRM_K7(2));  // 7-row tiles: two-pixel form only
     if (px == 1) return axis == 0 ? TBRM_K(0, 1) : (axis == 1 ? TBRM_K(1, 1) : TBRM_K(2, 1));
     return axis == 0 ? TBRM_K(0, 2) : (axis == 1 ? TBRM_K(1, 2) : TBRM_K(2, 2));
 #undef TBRM_K
@@ -584,7 +585,6 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // a G8 light volume (the reference's default format): byte bricks — AddDirLight, sweeps along Y / Z, unsharded (a byte brick of 4 slices
     // along X has 4-byte rows, below TMA's 16-byte minimum; ChangeDirLight keeps its removed light in an R32F scratch volume)
     const bool l8 = r.light_fmt == TBRM_FMT_G8;
-    if (l8 && r.slab.nranks > 1) return not_handled("G8 light volume of a sharded volume");
     // the brick a G8 pass loads, updates and stores is bytes of the light volume — except for the removed light of a ChangeDirLight, whose
     // propagated light goes to the R32F scratch volume (its forwarded values are still quantised like the G8 propagation buffers)
     const bool byte_brick = l8 && mode != kModeStore;
@@ -692,7 +692,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         if (want == 7 || (want != 8 && pays)) {  // ... if the 7-row tiles are co-resident
             int occ = 0;
             bool fits = false;
-            const void* k7 = l8 ? tma_kernel_l8(u.axis, clip, px, 7) : tma_kernel(u.axis, clip, false, px, 7);
+            const void* k7 = l8 ? tma_kernel_l8(u.axis, clip, false, px, 7) : tma_kernel(u.axis, clip, false, px, 7);
             if ((e = blocks_per_sm(k7, 32 * 7, layout_of(7).smem, dev, &occ, &fits)) != cudaSuccess) return e;
             if (fits && (long long) occ * sms >= tiles_of(7)) th = 7;
         }
@@ -746,6 +746,10 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // push-gather: the same box over every other rank's light volume (the brick that updates the LIGHT volume: add / combine launches)
     static thread_local PushMaps pm;
     P.n_push = 0;
+    if (r.push_this_pass && mode != kModeStore && r.slab.nranks > 1 && l8) {
+        set_last_error("push-gather: R32F light volumes only (the pushed bricks are float boxes)");
+        return cudaErrorNotSupported;
+    }
     if (r.push_this_pass && mode != kModeStore && r.slab.nranks > 1) {
         for (int pr = 0; pr < r.slab.nranks; ++pr) {
             if (pr == r.slab.rank) continue;
@@ -798,8 +802,8 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     }
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
-    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, px, th) : tma_kernel(u.axis, clip, false, px, th));
-    const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : tma_kernel(u.axis, clip, true, px);
+    const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, false, px, th) : tma_kernel(u.axis, clip, false, px, th));
+    const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : (l8 ? tma_kernel_l8(u.axis, clip, true, px) : tma_kernel(u.axis, clip, true, px));
     {
         int occ_plain = 0, occ_slab = 0;
         bool fits = false;
@@ -817,7 +821,6 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int nbands = bands_of(q_begin, q_end);
     const int rows_per_band = (tr1 - tr0 + nbands - 1) / nbands;
     const bool use_slab = sharded || nbands > 1;
-    if (l8 && use_slab) return not_handled("G8 light volume on a plane that needs several co-resident waves");
     if (use_slab) {
         if (reach_lo + reach_hi > kInboxSlots) return not_handled("the footprints reach more than 8 rows into the neighbouring bands");
         // a footprint must not reach past the adjacent band (bands and slabs are at least 8 rows)
@@ -1001,6 +1004,8 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         count_launch();
         *launches += 1;
     }
+    // a G8 volume's sweep along X works on the (y,z,x)-ordered copy of the light volume (whole volume: only this GPU's slab matters)
+    if (l8_x && (e = permute_bytes(r, (const uint8_t*) r.light, (uint8_t*) r.light_perm[0], r.ldims[0], r.ldims[1], r.ldims[2])) != cudaSuccess) return e;
     int nb_lo = nbands;  // bands of the lower neighbour's slab (same partition rule on every rank: tbrm_slab_partition)
     if (shard_q && sl.rank > 0) {
         int32_t zb, ze;
@@ -1039,6 +1044,11 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         if ((e = tma_launch(r, kern_slab, threads, lm, dm, sm, pm, P, S.tile_rows * P.ntx, smem)) != cudaSuccess) return e;
         count_launch();
         *launches += 1;
+    }
+    if (l8_x) {  // back to (x,y,z): two more applications of the same transpose
+        if ((e = permute_bytes(r, (const uint8_t*) r.light_perm[0], (uint8_t*) r.light_perm[1], r.ldims[1], r.ldims[2], r.ldims[0])) != cudaSuccess) return e;
+        if ((e = permute_bytes(r, (const uint8_t*) r.light_perm[1], (uint8_t*) r.light, r.ldims[2], r.ldims[0], r.ldims[1])) != cudaSuccess) return e;
+        *launches += 3;
     }
     if (sharded) {  // tell the neighbours this slab is done with pass `seq` (acks live in THEIR arenas: word 1 = "from hi" for our lower neighbour)
         unsigned int* to_lo = r.peer_arena[0] ? arena_word(r.peer_arena[0], 1) : nullptr;

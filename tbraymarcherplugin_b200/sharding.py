@@ -135,7 +135,7 @@ class FShardedRaymarchVolume:
 
     BLOCK_ROWS = 8
 
-    def __init__(self, data_dims: Sequence[int], device: int, group=None):
+    def __init__(self, data_dims: Sequence[int], device: int, group=None, bLightVolume32Bit: bool = True, LightVolumeHalfResolution: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -147,11 +147,19 @@ class FShardedRaymarchVolume:
         self.device = device
         X, Y, Z = (int(d) for d in data_dims)
         self.dims = (X, Y, Z)
+        # data slabs (upload + all-gather) and light slabs (sweep + all-gather) follow the same partition rule on their own slice counts
         self.z0, self.z1 = slab_of_rank(Z, self.rank, self.world)
         slabs = [slab_of_rank(Z, r, self.world) for r in range(self.world)]
         if any(b - a != self.z1 - self.z0 or b <= a for a, b in slabs):
             raise ValueError(f"{Z} slices do not split into {self.world} equal slabs of a multiple of 8 slices")
-        self.res = URaymarchUtils.InitializeRaymarchResources(self.dims, FMT_G8, bLightVolume32Bit=True, device=device)
+        self.res = URaymarchUtils.InitializeRaymarchResources(self.dims, FMT_G8, bLightVolume32Bit=bLightVolume32Bit,
+                                                              LightVolumeHalfResolution=LightVolumeHalfResolution, device=device)
+        self.light32 = bool(bLightVolume32Bit)
+        LX, LY, LZ = (int(d) for d in self.res.LightDims)
+        self.lz0, self.lz1 = slab_of_rank(LZ, self.rank, self.world)
+        lslabs = [slab_of_rank(LZ, r, self.world) for r in range(self.world)]
+        if any(b - a != self.lz1 - self.lz0 or b <= a for a, b in lslabs):
+            raise ValueError(f"{LZ} light-volume slices do not split into {self.world} equal slabs of a multiple of 8 slices")
         dev = torch.device("cuda", device)
         # collectives run on these tensors, the library computes on them: caller-owned, bound into the resource set
         self.data = torch.empty((Z, Y, X), dtype=torch.uint8, device=dev)
@@ -161,7 +169,8 @@ class FShardedRaymarchVolume:
         light_ptr = self.lib.tbrm_light_volume_device_ptr(self.res.handle)
 
         class _LightView:
-            __cuda_array_interface__ = {"shape": (Z, Y, X), "typestr": "<f4", "data": (int(light_ptr), False), "version": 2}
+            __cuda_array_interface__ = {"shape": (LZ, LY, LX), "typestr": "<f4" if bLightVolume32Bit else "|u1", "data": (int(light_ptr), False),
+                                        "version": 2}
 
         self._light_view = _LightView()
         with torch.cuda.device(dev):
@@ -170,7 +179,7 @@ class FShardedRaymarchVolume:
         torch.cuda.synchronize(dev)
         _capi.check(self.lib.tbrm_bind_volume_device(self.res.handle, C.c_void_p(self.data.data_ptr())))
         self.res.bIsInitialized = True
-        slab = _capi.Slab(self.rank, self.world, self.z0, self.z1)
+        slab = _capi.Slab(self.rank, self.world, self.lz0, self.lz1)
         _capi.check(self.lib.tbrm_slab_configure(self.res.handle, C.byref(slab)))
         # exchange arenas: CUDA IPC handles travel through the process group, neighbours map each other's arena
         handle = (C.c_ubyte * 64)()
@@ -299,6 +308,7 @@ class FShardedRaymarchVolume:
         into all peers' light volumes from inside the sweep kernel (TMA stores over NVLink), and GatherLightVolume only synchronises."""
         from .raymarch_utils import URaymarchUtils
 
+        push = bool(push and self.light32)  # the pushed bricks are float boxes: a G8 volume is gathered by NCCL
         _capi.check(self.lib.tbrm_slab_push_light(self.res.handle, 1 if push else 0))
         try:
             ok = URaymarchUtils.AddDirLightToSingleVolume(self.res, light, added, world, bGPUSync=True, stats=stats)
@@ -310,6 +320,7 @@ class FShardedRaymarchVolume:
     def ChangeDirLight(self, old_light, new_light, world, stats=None) -> bool:
         from .raymarch_utils import URaymarchUtils
 
+        self._pushed = False  # this rank's slab changes again: the peers' copies of it are stale until the next gather
         return URaymarchUtils.ChangeDirLightInSingleVolume(self.res, old_light, new_light, world, bGPUSync=True, stats=stats)
 
     def GatherLightVolume(self) -> None:
@@ -323,7 +334,7 @@ class FShardedRaymarchVolume:
                 # stores) has completed before anybody reads: a one-word all-reduce, stream-ordered after the sweep on every rank
                 dist.all_reduce(self._sync_word, group=self.group)
             else:
-                dist.all_gather_into_tensor(self.light.view(-1), self.light[self.z0:self.z1].reshape(-1), group=self.group)
+                dist.all_gather_into_tensor(self.light.view(-1), self.light[self.lz0:self.lz1].reshape(-1), group=self.group)
         self._pushed = False
 
     # ---- frame ------------------------------------------------------------------------------------------

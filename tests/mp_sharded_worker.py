@@ -111,8 +111,48 @@ def main():
     ref2.release()
     dist.barrier()
     vol.release()
+    # the other light-volume settings of the reference on a sharded volume: G8 (its default format), half resolution, both
+    # (light-volume slabs must be multiples of 8 slices: half resolution needs n / 2 / world_size % 8 == 0)
+    for light32, half in ((False, False), (True, True), (False, True)):
+        if half and (n // 2) % (8 * world_size) != 0:
+            continue
+        other_formats(lib, d_vol, n, local, rank, world, win, cam, light32, half)
     dist.destroy_process_group()
     print(f"sharded ok rank {rank}/{world_size} n={n}", flush=True)
+
+
+def other_formats(lib, d_vol, n, local, rank, world, win, cam, light32, half):
+    vol = sharding.FShardedRaymarchVolume((n, n, n), local, bLightVolume32Bit=light32, LightVolumeHalfResolution=half)
+    URaymarchUtils.ColorCurveToTexture(vol.res, synth.soft_ct_curve())
+    URaymarchUtils.SetWindowingParameters(vol.res, win)
+    vol.SetDataVolumeSlab(d_vol[vol.z0:vol.z1])
+    vol.Flush()
+    vol.ClearLightVolume(0.0)
+    for i, l in enumerate(synth.LIGHTS):
+        st = FSweepStats()
+        assert vol.AddDirLight(l, True, world, stats=st, push=(i == len(synth.LIGHTS) - 1))  # (pushes only an R32F volume)
+        assert set(st.impl) == {3}, st.impl
+    new = synth.rotate_about_z(synth.LIGHTS[0], 15.0)
+    assert vol.ChangeDirLight(synth.LIGHTS[0], new, world)
+    vol.GatherLightVolume()
+    frame, _ = vol.Render(cam, world, 200.0)
+    vol.Check()
+    if rank == 0:
+        ref = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=light32, LightVolumeHalfResolution=half, device=local)
+        URaymarchUtils.SetDataVolumeDevice(ref, d_vol.data_ptr())
+        URaymarchUtils.ColorCurveToTexture(ref, synth.soft_ct_curve())
+        URaymarchUtils.SetWindowingParameters(ref, win)
+        URaymarchUtils.ClearResourceLightVolumes(ref, 0.0)
+        for l in synth.LIGHTS:
+            URaymarchUtils.AddDirLightToSingleVolume(ref, l, True, world, bGPUSync=True)
+        URaymarchUtils.ChangeDirLightInSingleVolume(ref, synth.LIGHTS[0], new, world, bGPUSync=True)
+        L_ref, L = URaymarchUtils.ReadLightVolume(ref), vol.light.cpu().numpy()
+        assert L_ref.max() > 0 and np.array_equal(L, L_ref), f"light32={light32} half={half}: {np.count_nonzero(L != L_ref)} light voxels differ"
+        img_ref, _ = URaymarchUtils.PerformWindowedLitRaymarch(ref, cam, world, 200.0)
+        assert np.array_equal(frame.cpu().numpy(), img_ref), f"light32={light32} half={half}: frame differs"
+        ref.release()
+    dist.barrier()
+    vol.release()
 
 
 if __name__ == "__main__":

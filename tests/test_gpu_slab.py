@@ -21,9 +21,9 @@ WORLDS = {"identity": synth.identity_world, "scaled_rotated": synth.scaled_rotat
 _STREAM_OWNERS = []
 
 
-def make_res(data, sweep_impl=2, band_rows=0):
+def make_res(data, sweep_impl=2, band_rows=0, light32=True, half_res=False):
     Z, Y, X = data.shape
-    res = URaymarchUtils.InitializeRaymarchResources((X, Y, Z), FMT_G8, bLightVolume32Bit=True)
+    res = URaymarchUtils.InitializeRaymarchResources((X, Y, Z), FMT_G8, bLightVolume32Bit=light32, LightVolumeHalfResolution=half_res)
     URaymarchUtils.SetDataVolume(res, data)
     URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
     URaymarchUtils.SetWindowingParameters(res, CT_WINDOW)
@@ -31,8 +31,8 @@ def make_res(data, sweep_impl=2, band_rows=0):
     return res
 
 
-def unsharded(data, lights, world):
-    res = make_res(data)
+def unsharded(data, lights, world, light32=True, half_res=False):
+    res = make_res(data, light32=light32, half_res=half_res)
     URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
     for l in lights:
         st = FSweepStats()
@@ -44,14 +44,14 @@ def unsharded(data, lights, world):
     return URaymarchUtils.ReadLightVolume(res)
 
 
-def virtual_ranks(data, nranks, band_rows=0):
+def virtual_ranks(data, nranks, band_rows=0, light32=True, half_res=False):
     lib = _capi.load()
     Z = data.shape[0]
     ranks = []
     for r in range(nranks):
-        res = make_res(data, band_rows=band_rows)
+        res = make_res(data, band_rows=band_rows, light32=light32, half_res=half_res)
         z0, z1 = C.c_int32(), C.c_int32()
-        lib.tbrm_slab_partition(Z, nranks, r, C.byref(z0), C.byref(z1))
+        lib.tbrm_slab_partition(res.LightDims[2], nranks, r, C.byref(z0), C.byref(z1))  # slabs are slices of the LIGHT volume
         slab = _capi.Slab(r, nranks, z0.value, z1.value)
         _capi.check(lib.tbrm_slab_configure(res.handle, C.byref(slab)))
         _capi.check(lib.tbrm_slab_set_timeout_ms(res.handle, SLAB_TIMEOUT_MS))
@@ -126,6 +126,48 @@ def test_sharded_sweep_is_bit_identical(dims, nranks, world_name):
     URaymarchUtils.WriteLightVolume(res1, ref)
     URaymarchUtils.AddDirLightToSingleVolume(res1, synth.LIGHTS[0], False, world, bGPUSync=True)
     assert np.array_equal(merged(ranks), URaymarchUtils.ReadLightVolume(res1))
+
+
+@pytest.mark.parametrize("dims,nranks", [((64, 64, 64), 2), ((64, 64, 64), 4), ((128, 64, 96), 3)])
+def test_sharded_sweep_of_a_g8_light_volume_is_bit_identical(dims, nranks):
+    """The reference's default light-volume format on a sharded volume: byte bricks, exchange cells carrying what the G8 propagation buffers
+    would hold, sweeps along X on the (y,z,x)-ordered copy of each rank's light volume; banded on one GPU as well."""
+    data = synth.perlin_ct_volume(dims)
+    world = synth.identity_world()
+    ref = unsharded(data, synth.LIGHTS, world, light32=False)
+    ranks = virtual_ranks(data, nranks, light32=False)
+    for res, _, _ in ranks:
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    sharded_sweep(ranks, synth.LIGHTS, world)
+    got = merged(ranks)
+    assert ref.max() > 0.5 and np.array_equal(got, ref), f"{np.count_nonzero(got != ref)} voxels differ"
+    sharded_sweep(ranks, [synth.LIGHTS[0]], world, added=False)
+    res1 = make_res(data, light32=False)
+    URaymarchUtils.WriteLightVolume(res1, ref)
+    URaymarchUtils.AddDirLightToSingleVolume(res1, synth.LIGHTS[0], False, world, bGPUSync=True)
+    assert np.array_equal(merged(ranks), URaymarchUtils.ReadLightVolume(res1))
+    banded = make_res(data, band_rows=3, light32=False)
+    URaymarchUtils.ClearResourceLightVolumes(banded, 0.0)
+    for l in synth.LIGHTS:
+        st = FSweepStats()
+        assert URaymarchUtils.AddDirLightToSingleVolume(banded, l, True, world, bGPUSync=True, stats=st)
+        assert set(st.impl) == {3} and st.kernel_launches > st.passes
+    assert np.array_equal(URaymarchUtils.ReadLightVolume(banded), ref)
+
+
+@pytest.mark.parametrize("light32", [True, False])
+@pytest.mark.parametrize("dims,nranks", [((64, 64, 64), 2), ((128, 64, 64), 4)])
+def test_sharded_sweep_of_a_half_resolution_light_volume_is_bit_identical(dims, nranks, light32):
+    """LightVolumeHalfResolution on a sharded volume: the slabs are slices of the light volume, every rank's data boxes span twice its tiles."""
+    data = synth.perlin_ct_volume(dims)
+    world = synth.identity_world()
+    ref = unsharded(data, synth.LIGHTS[:3], world, light32=light32, half_res=True)
+    ranks = virtual_ranks(data, nranks, light32=light32, half_res=True)
+    for res, _, _ in ranks:
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    sharded_sweep(ranks, synth.LIGHTS[:3], world)
+    got = merged(ranks)
+    assert ref.max() > 0.5 and np.array_equal(got, ref), f"{np.count_nonzero(got != ref)} voxels differ"
 
 
 @pytest.mark.parametrize("band_rows", [1, 3])

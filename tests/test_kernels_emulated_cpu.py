@@ -148,6 +148,14 @@ def test_emulated_concurrent_slabs_equal_the_unsharded_sweep(emulated, dims, nra
     assert np.array_equal(S.merged(ranks), URaymarchUtils.ReadLightVolume(ref_res))
 
 
+def test_emulated_slabs_of_g8_and_half_resolution_light_volumes(emulated):
+    import test_gpu_slab as S
+
+    S.test_sharded_sweep_of_a_g8_light_volume_is_bit_identical((64, 64, 64), 2)
+    S.test_sharded_sweep_of_a_half_resolution_light_volume_is_bit_identical((64, 64, 64), 2, False)
+    S.test_sharded_sweep_of_a_half_resolution_light_volume_is_bit_identical((128, 64, 64), 4, True)
+
+
 @pytest.mark.parametrize("dims", [(16, 1, 1), (48, 20, 9), (144, 16, 24), (40, 12, 8)])
 def test_emulated_octree_build_kernels(emulated, dims):
     """octree_build_u8x16_kernel (R8 data, X % 16 == 0: 16-byte loads, byte replication instead of the float round trip) and the generic
