@@ -336,8 +336,9 @@ static const void* tma_kernel_l8(int axis, bool clip, bool slab, int px, int th 
 static const void* tma_kernel(int axis, bool clip, bool slab, int px, int th = 8) {
 #define TBRM_K(A, PX) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true, PX> : (const void*) sweep_tma_kernel<A, false, true, PX>) \
                             : (clip ? (const void*) sweep_tma_kernel<A, true, false, PX> : (const void*) sweep_tma_kernel<A, false, false, PX>))
-#define TBRM_K7(A, PX) (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, false, 7> : (const void*) sweep_tma_kernel<A, false, false, PX, false, 7>)
-    if (th == 7 && !slab) {  // 7-row tiles: unsharded single-wave passes only
+#define TBRM_K7(A, PX) (slab ? (clip ? (const void*) sweep_tma_kernel<A, true, true, PX, false, 7> : (const void*) sweep_tma_kernel<A, false, true, PX, false, 7>) \
+                             : (clip ? (const void*) sweep_tma_kernel<A, true, false, PX, false, 7> : (const void*) sweep_tma_kernel<A, false, false, PX, false, 7>))
+    if (th == 7) {  // 7-row tiles
         if (px == 1) return axis == 0 ? TBRM_K7(0, 1) : (axis == 1 ? TBRM_K7(1, 1) : TBRM_K7(2, 1));
         return axis == 0 ? TBRM_K7(0, 2) : (axis == 1 ? TBRM_K7(1, 2) : TBRM_K7(2, 2));
     }
@@ -673,28 +674,44 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         L.smem = (size_t) kStages * L.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
         return L;
     };
-    // Tile rows. All tiles of a pass are co-resident and advance in lock step (each waits for its upstream neighbours every slice), so the pass
+    // Tile rows. All tiles of a wave are co-resident and advance in lock step (each waits for its upstream neighbours every slice), so a wave
     // runs at the pace of the fullest SM: 512^2 pixels in 64 x 8 tiles are 512 tiles on 148 SMs — 4 on most, 3 on the rest. 64 x 7 tiles are
     // 592 = 4 x 148: every SM holds four 7-warp blocks, an eighth less work on the SMs that set the pace (measured: 5.02 -> 4.65 ms for the cfg2
-    // reset; 6 rows: 5.03 ms). First generation, unsharded single-wave passes (the slab exchange is laid out in 8-row units).
-    // TBRM_SWEEP_TH=7|8 or bits 8-9 of reserved[0] (2 / 3) ask for a height.
+    // reset; 6 rows: 5.03 ms). The same holds for the waves (bands) of a larger plane: 1024^2 is 4 bands of 512 tiles or of 592. Passes whose
+    // tile rows are cut by slab boundaries (sweeps along X / Y of a sharded volume: the exchange is laid out in 8-row units) keep 8 rows; so do
+    // G8 slabs and the one-pixel G8 form. TBRM_SWEEP_TH=7|8 or bits 8-9 of reserved[0] (2 / 3) ask for a height.
     int th = ::tbrm::kTH;
-    if (!ws && !(l8 && px == 1) && r.slab.nranks <= 1 && r.options.reserved[2] <= 0) {
+    const bool slab_launch = r.slab.nranks > 1 || r.options.reserved[2] > 0;  // (more bands than one are found below)
+    if (!ws && !(l8 && (px == 1 || slab_launch)) && !(r.slab.nranks > 1 && u.axis != 2)) {
         static const int env_th = [] {
             const char* e = getenv("TBRM_SWEEP_TH");
             return e ? atoi(e) : 0;
         }();
         const int opt_th = (r.options.reserved[0] >> 8) & 3;
         const int want = opt_th >= 2 ? 5 + opt_th : env_th;
-        const long long ntx_ = (tx + kTW - 1) / kTW;
+        const long long ntx_ = (tx + kTW - 1) / kTW, slots = 4ll * sms;  // launch bounds: four blocks per SM
         auto tiles_of = [&](int h) { return ntx_ * ((ty + h - 1) / h); };
-        const bool pays = tiles_of(8) > sms && tiles_of(8) <= 4ll * sms && (tiles_of(7) + sms - 1) / sms * 7 < (tiles_of(8) + sms - 1) / sms * 8;
-        if (want == 7 || (want != 8 && pays)) {  // ... if the 7-row tiles are co-resident
-            int occ = 0;
-            bool fits = false;
+        // cost of the pass in (rows of the fullest SM) x bands: bands of at most `slots` tiles, split evenly
+        auto cost_of = [&](int h) {
+            const long long nty_ = (ty + h - 1) / h, cap = std::max(1ll, slots / ntx_), bands = (nty_ + cap - 1) / cap, rows = (nty_ + bands - 1) / bands;
+            return bands * ((rows * ntx_ + sms - 1) / sms) * h;
+        };
+        const bool pays = tiles_of(8) > sms && cost_of(7) < cost_of(8) && !l8;
+        const bool pays_l8 = l8 && tiles_of(8) > sms && tiles_of(7) <= slots && cost_of(7) < cost_of(8);  // G8: single wave only
+        if (want == 7 || (want != 8 && (pays || pays_l8))) {  // ... if four 7-row blocks are resident per SM (or one wave holds the plane anyway)
+            int occ = 0, occ_s = 4;
+            bool fits = false, fits_s = true;
             const void* k7 = l8 ? tma_kernel_l8(u.axis, clip, false, px, 7) : tma_kernel(u.axis, clip, false, px, 7);
             if ((e = blocks_per_sm(k7, 32 * 7, layout_of(7).smem, dev, &occ, &fits)) != cudaSuccess) return e;
-            if (fits && (long long) occ * sms >= tiles_of(7)) th = 7;
+            if (!l8 && (e = blocks_per_sm(tma_kernel(u.axis, clip, true, px, 7), 32 * 7, layout_of(7).smem, dev, &occ_s, &fits_s)) != cudaSuccess) return e;
+            const long long per = std::min(occ, occ_s);
+            // the rule of the banded launches below, for 7-row tiles: a footprint must not reach past the adjacent band (the last one may be thin)
+            const long long reach = std::max(std::max(0, -T.bmin[1]), std::max(0, T.bmax[1] + 1)), nty7 = (ty + 6) / 7;
+            long long cap = std::max(1ll, per * sms / ntx_);
+            if (r.options.reserved[2] > 0) cap = std::min<long long>(cap, r.options.reserved[2]);
+            const long long nb = (nty7 + cap - 1) / cap, rpb = (nty7 + nb - 1) / nb;
+            const bool bands_ok = (nb == 1 && r.slab.nranks <= 1) || reach <= std::min<long long>(7, ty - (nb - 1) * rpb * 7);
+            if (fits && fits_s && bands_ok && (per * sms >= tiles_of(7) || (!l8 && per >= 4))) th = 7;  // (G8: one wave of the plain kernel must hold the plane)
         }
     }
     const int kTH = th;  // shadow the 8-row constant below
@@ -803,7 +820,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     int per_sm = 0;
     const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, false, px, th) : tma_kernel(u.axis, clip, false, px, th));
-    const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : (l8 ? tma_kernel_l8(u.axis, clip, true, px) : tma_kernel(u.axis, clip, true, px));
+    const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : (l8 ? tma_kernel_l8(u.axis, clip, true, px) : tma_kernel(u.axis, clip, true, px, th));
     {
         int occ_plain = 0, occ_slab = 0;
         bool fits = false;
@@ -811,7 +828,8 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         if (!fits) return not_handled("shared memory per block");
         if ((e = blocks_per_sm(kern_slab, threads, smem, dev, &occ_slab, &fits)) != cudaSuccess) return e;
         if (!fits) return not_handled("shared memory per block");
-        per_sm = th == 7 ? occ_plain : occ_slab;  // 7-row tiles were chosen because one wave of the plain kernel holds them all
+        // (an unsharded pass in one wave runs the plain kernel; the G8 slab kernels have 8-row tiles only)
+        per_sm = (th == 7 && !sharded) ? (l8 ? occ_plain : std::min(occ_plain, occ_slab)) : occ_slab;
     }
     int cap_rows = (int) std::min<long long>((long long) sms * per_sm / P.ntx, 1 << 20);  // tile rows of one co-resident wave
     if (r.options.reserved[2] > 0) cap_rows = std::min(cap_rows, r.options.reserved[2]);      // test hook: force banding on small planes

@@ -21,13 +21,13 @@ WORLDS = {"identity": synth.identity_world, "scaled_rotated": synth.scaled_rotat
 _STREAM_OWNERS = []
 
 
-def make_res(data, sweep_impl=2, band_rows=0, light32=True, half_res=False):
+def make_res(data, sweep_impl=2, band_rows=0, light32=True, half_res=False, flags=0):
     Z, Y, X = data.shape
     res = URaymarchUtils.InitializeRaymarchResources((X, Y, Z), FMT_G8, bLightVolume32Bit=light32, LightVolumeHalfResolution=half_res)
     URaymarchUtils.SetDataVolume(res, data)
     URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
     URaymarchUtils.SetWindowingParameters(res, CT_WINDOW)
-    URaymarchUtils.SetOptions(res, sweep_impl=sweep_impl, debug_flags=(0, 0, band_rows))
+    URaymarchUtils.SetOptions(res, sweep_impl=sweep_impl, debug_flags=(flags, 0, band_rows))
     return res
 
 
@@ -44,12 +44,12 @@ def unsharded(data, lights, world, light32=True, half_res=False):
     return URaymarchUtils.ReadLightVolume(res)
 
 
-def virtual_ranks(data, nranks, band_rows=0, light32=True, half_res=False):
+def virtual_ranks(data, nranks, band_rows=0, light32=True, half_res=False, flags=0):
     lib = _capi.load()
     Z = data.shape[0]
     ranks = []
     for r in range(nranks):
-        res = make_res(data, band_rows=band_rows, light32=light32, half_res=half_res)
+        res = make_res(data, band_rows=band_rows, light32=light32, half_res=half_res, flags=flags)
         z0, z1 = C.c_int32(), C.c_int32()
         lib.tbrm_slab_partition(res.LightDims[2], nranks, r, C.byref(z0), C.byref(z1))  # slabs are slices of the LIGHT volume
         slab = _capi.Slab(r, nranks, z0.value, z1.value)
@@ -184,6 +184,34 @@ def test_banded_passes_are_bit_identical(dims, band_rows):
         assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
         assert set(st.impl) == {3} and st.kernel_launches > st.passes
     assert np.array_equal(URaymarchUtils.ReadLightVolume(res), ref)
+
+
+@pytest.mark.parametrize("flags,dims", [(512 + 32, (128, 64, 64)), (512 + 16, (128, 64, 96))])  # bits 8-9 = 2: tiles of 7 rows; bits 4-5: two / one pixel per thread
+def test_seven_row_tiles_in_banded_and_sharded_passes(flags, dims):
+    """Tiles of 7 rows (what fills 148 SMs with four blocks each on 512^2 and 1024^2 planes) in the launches that exchange light between
+    bands and slabs: banded passes of one GPU, and the sweeps along Z of a sharded volume (its sweeps along X / Y keep 8-row tiles)."""
+    data = synth.perlin_ct_volume(dims)
+    world = synth.identity_world()
+    lights = synth.LIGHTS[1:] if flags & 32 else synth.LIGHTS  # (the two-pixel form needs uniform tap pairs: not the first light on this volume)
+    ref = unsharded(data, lights, world)
+    for band_rows in (2, 5):  # (3 would leave a last band of one pixel row, thinner than the footprints reach: such a pass takes the generic kernel)
+        res = make_res(data, band_rows=band_rows, flags=flags)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        for l in lights:
+            st = FSweepStats()
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
+            assert set(st.impl) == {3} and st.kernel_launches > st.passes
+        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), ref), band_rows
+    ranks = virtual_ranks(data, 4 if dims[2] == 64 else 3, flags=flags)
+    for res, _, _ in ranks:
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    sharded_sweep(ranks, lights, world)
+    assert np.array_equal(merged(ranks), ref)
+    ranks = virtual_ranks(data, 2, band_rows=2, flags=flags)
+    for res, _, _ in ranks:
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    sharded_sweep(ranks, lights, world)
+    assert np.array_equal(merged(ranks), ref)
 
 
 def test_sharded_and_banded_together():
