@@ -118,8 +118,10 @@ typedef struct tbrm_options {
     int32_t data_addr_wrap;   /* raymarch data sampler address mode: 0 clamp (default), 1 wrap (Q5) */
     int32_t sweep_impl;       /* 0: auto (gpu_sync ? fused : per-slice), 1: per-slice launches (reference schedule),
                                  2: fused persistent sweep (TMA-staged when eligible), 3: generic fused sweep only */
-    int32_t reserved[5];      /* debug / test hooks: [0] bit 0 disables the sweep's exact empty-space skip; [1] = 1 forces the generic
-                                 raymarch kernel; [2] > 0 caps the tile rows of one sweep launch (forces banded passes) */
+    int32_t reserved[5];      /* debug / test hooks (INTEGRATION.md has the table): [0] bit 0 disables the sweep's exact empty-space skip,
+                                 bits 4-5 pixels per thread, bit 6 second kernel generation, bits 8-9 tile rows (2: 7, 3: 8); [1] = 1 forces
+                                 the generic raymarch kernel (2..5: other forms); [2] > 0 caps the tile rows of one sweep launch (forces
+                                 banded passes) */
 } tbrm_options;
 
 /* Per-op counters written by the *_stats calls (for the metric definitions of SURVEY.md §8d). */
