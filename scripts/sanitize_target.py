@@ -14,7 +14,8 @@ data = synth.perlin_ct_volume((n, n, n))
 win = FWindowingParameters(0.45, 0.5, True, False)
 results = {}
 for world_name, world in (("identity", synth.identity_world()), ("clipped", synth.clipped_world())):
-    for impl, sync, bits in ((1, False, 0), (3, True, 0), (2, True, 0), (2, True, 64)):  # reserved[0] bit 6: second kernel generation
+    # reserved[0] bit 6: second kernel generation; bits 8-9 = 2 with bits 4-5 = 2: tiles of 7 rows, two pixels per thread
+    for impl, sync, bits in ((1, False, 0), (3, True, 0), (2, True, 0), (2, True, 64), (2, True, 512 + 32)):
         res = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=True)
         URaymarchUtils.SetDataVolume(res, data)
         URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
@@ -33,4 +34,23 @@ for world_name, world in (("identity", synth.identity_world()), ("clipped", synt
     for k, v in results.items():
         if k[0] == world_name:
             assert np.array_equal(v, ref), k
+# the other light-volume settings through the TMA-staged kernel: G8 (byte bricks, ChangeDirLight with the R32F scratch brick), half resolution
+for light32, half in ((False, False), (True, True), (False, True)):
+    out = []
+    for impl in (3, 2):
+        res = URaymarchUtils.InitializeRaymarchResources((n, n, n), FMT_G8, bLightVolume32Bit=light32, LightVolumeHalfResolution=half)
+        URaymarchUtils.SetDataVolume(res, data)
+        URaymarchUtils.ColorCurveToTexture(res, synth.soft_ct_curve())
+        URaymarchUtils.SetWindowingParameters(res, win)
+        URaymarchUtils.SetOptions(res, sweep_impl=impl)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        world = synth.identity_world()
+        for l in synth.LIGHTS[:3]:
+            st = FSweepStats()
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, world, bGPUSync=True, stats=st)
+            assert impl == 3 or 3 in st.impl, st.impl
+        assert URaymarchUtils.ChangeDirLightInSingleVolume(res, synth.LIGHTS[0], synth.rotate_about_z(synth.LIGHTS[0], 5.0), world, bGPUSync=True)
+        out.append(URaymarchUtils.ReadLightVolume(res))
+        res.release()
+    assert np.array_equal(out[0], out[1]), (light32, half)
 print("sanitize target ok: schedules agree bit for bit", {k: float(v.max()) for k, v in results.items()})
