@@ -2,7 +2,7 @@
 # multi-GPU: bit-parity tests of the sharded volume + the bench line (cfg2 step, streaming e2e, scale_cfg4) on N GPUs of one box
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/multi_tests_n$N.txt; tail -3 gpurun_out/multi_tests_n$N.txt
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu ${2:+-k "$2"} 2>&1 | tail -5 > gpurun_out/multi_tests_n$N.txt; tail -3 gpurun_out/multi_tests_n$N.txt
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
 python - <<PY
 import json
