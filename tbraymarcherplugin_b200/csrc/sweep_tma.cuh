@@ -96,6 +96,7 @@ struct TmaParams {
     unsigned long long timeout_ns;
     unsigned int poll_limit;  // unsharded launches: polls after which a wait on another tile gives up (timeout_ns / 256 ns)
     int n_push;               // peers the light bricks are pushed to (0: none)
+    int q_org;                // first generation: buffer row of tile row 0 (0, or negative where a slab does not start on a multiple of the tile height)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------
@@ -674,6 +675,18 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         L.smem = (size_t) kStages * L.stage_bytes + (2 * kFpW * kFpH + 256) * sizeof(float) + kStages * sizeof(uint64_t) + 16;
         return L;
     };
+    // ---- which part of the pass this GPU runs, and in how many co-resident waves (bands of tile rows) ----
+    const tbrm_slab& sl = r.slab;
+    const bool sharded = sl.nranks > 1;
+    const bool shard_q = sharded && u.axis != 2, shard_s = sharded && u.axis == 2;  // q = z for sweeps along X and Y
+    const int ns = u.td[2];
+    int q_begin = 0, q_end = ty, k_begin = 0, k_end = ns;
+    if (shard_q) q_begin = sl.z_begin, q_end = sl.z_end;
+    if (shard_s) {
+        k_begin = u.dirn > 0 ? sl.z_begin : ns - sl.z_end;
+        k_end = u.dirn > 0 ? sl.z_end : ns - sl.z_begin;
+    }
+    const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
     // Tile rows. All tiles of a wave are co-resident and advance in lock step (each waits for its upstream neighbours every slice), so a wave
     // runs at the pace of the fullest SM: 512^2 pixels in 64 x 8 tiles are 512 tiles on 148 SMs — 4 on most, 3 on the rest. 64 x 7 tiles are
     // 592 = 4 x 148: every SM holds four 7-warp blocks, an eighth less work on the SMs that set the pace (measured: 5.02 -> 4.65 ms for the cfg2
@@ -681,8 +694,11 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // tile rows are cut by slab boundaries (sweeps along X / Y of a sharded volume: the exchange is laid out in 8-row units) keep 8 rows; so do
     // G8 slabs and the one-pixel G8 form. TBRM_SWEEP_TH=7|8 or bits 8-9 of reserved[0] (2 / 3) ask for a height.
     int th = ::tbrm::kTH;
-    const bool slab_launch = r.slab.nranks > 1 || r.options.reserved[2] > 0;  // (more bands than one are found below)
-    if (!ws && !(l8 && (px == 1 || slab_launch)) && !(r.slab.nranks > 1 && u.axis != 2)) {
+    const bool slab_launch = sharded || r.options.reserved[2] > 0;  // (more bands than one are found below)
+    // the slabs of a sweep along X / Y must tile alike on every rank (a rank addresses its neighbours' bands): equal slabs only
+    const bool equal_slabs = !shard_q || (u.ldims[2] % (8 * sl.nranks) == 0);
+    const int span = q_end - q_begin;  // buffer rows this GPU sweeps
+    if (!ws && !(l8 && (px == 1 || slab_launch)) && equal_slabs) {
         static const int env_th = [] {
             const char* e = getenv("TBRM_SWEEP_TH");
             return e ? atoi(e) : 0;
@@ -690,10 +706,10 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         const int opt_th = (r.options.reserved[0] >> 8) & 3;
         const int want = opt_th >= 2 ? 5 + opt_th : env_th;
         const long long ntx_ = (tx + kTW - 1) / kTW, slots = 4ll * sms;  // launch bounds: four blocks per SM
-        auto tiles_of = [&](int h) { return ntx_ * ((ty + h - 1) / h); };
+        auto tiles_of = [&](int h) { return ntx_ * ((span + h - 1) / h); };
         // cost of the pass in (rows of the fullest SM) x bands: bands of at most `slots` tiles, split evenly
         auto cost_of = [&](int h) {
-            const long long nty_ = (ty + h - 1) / h, cap = std::max(1ll, slots / ntx_), bands = (nty_ + cap - 1) / cap, rows = (nty_ + bands - 1) / bands;
+            const long long nty_ = (span + h - 1) / h, cap = std::max(1ll, slots / ntx_), bands = (nty_ + cap - 1) / cap, rows = (nty_ + bands - 1) / bands;
             return bands * ((rows * ntx_ + sms - 1) / sms) * h;
         };
         const bool pays = tiles_of(8) > sms && cost_of(7) < cost_of(8) && !l8;
@@ -706,16 +722,21 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
             if (!l8 && (e = blocks_per_sm(tma_kernel(u.axis, clip, true, px, 7), 32 * 7, layout_of(7).smem, dev, &occ_s, &fits_s)) != cudaSuccess) return e;
             const long long per = std::min(occ, occ_s);
             // the rule of the banded launches below, for 7-row tiles: a footprint must not reach past the adjacent band (the last one may be thin)
-            const long long reach = std::max(std::max(0, -T.bmin[1]), std::max(0, T.bmax[1] + 1)), nty7 = (ty + 6) / 7;
+            const long long reach = std::max(reach_lo, reach_hi), nty7 = (span + 6) / 7;
             long long cap = std::max(1ll, per * sms / ntx_);
             if (r.options.reserved[2] > 0) cap = std::min<long long>(cap, r.options.reserved[2]);
             const long long nb = (nty7 + cap - 1) / cap, rpb = (nty7 + nb - 1) / nb;
-            const bool bands_ok = (nb == 1 && r.slab.nranks <= 1) || reach <= std::min<long long>(7, ty - (nb - 1) * rpb * 7);
+            const bool bands_ok = (nb == 1 && !sharded) || reach <= std::min<long long>(7, span - (nb - 1) * rpb * 7);
             if (fits && fits_s && bands_ok && (per * sms >= tiles_of(7) || (!l8 && per >= 4))) th = 7;  // (G8: one wave of the plain kernel must hold the plane)
         }
     }
+    // Tile rows are anchored at the first row this GPU sweeps (row j covers [q_org + j th, q_org + (j + 1) th), q_org in (-th, 0]): the slab
+    // of a sweep along X / Y starts on a tile row whatever th; its last tile row may end past the slab — those pixels are masked and the
+    // light maps are clipped at the slab's end (below).
+    const int j_first = (q_begin + th - 1) / th, q_org = q_begin - j_first * th;
+    P.q_org = q_org;
     const int kTH = th;  // shadow the 8-row constant below
-    P.ntx = (tx + kTW - 1) / kTW, P.nty = (ty + kTH - 1) / kTH;
+    P.ntx = (tx + kTW - 1) / kTW, P.nty = (ty - q_org + kTH - 1) / kTH;
     const int ntiles = P.ntx * P.nty;
     const int nat[3] = {pa, qa, sa};
     for (int t = 0; t < 3; ++t) {
@@ -738,6 +759,9 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     // tensor maps. Light: native (X,Y,Z) fp32, box = tile x SB along the sweep axis.
     int lbox[3], ldims[3] = {r.ldims[0], r.ldims[1], r.ldims[2]};
     lbox[pa] = kTW, lbox[qa] = kTH, lbox[sa] = kSB;
+    // a slab that ends inside its last tile row: the light, scratch and push maps end with the slab (q = z is the outermost dimension, so
+    // the strides stay), loads beyond it read zeros nobody uses and stores beyond it are dropped
+    if (shard_q && (q_end - q_org) % kTH != 0) ldims[2] = q_end;
     CUtensorMap lm, dm, sm;
     // the brick that is loaded, updated and stored: the light volume, or the scratch volume when the light is only stored
     const bool l8_x = byte_brick && u.axis == 0;  // a G8 volume's sweep along X works on a (y,z,x)-ordered copy of the light volume (see the kernel)
@@ -806,18 +830,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     }
     P.scratch = (const float*) r.change_scratch;
 
-    // ---- which part of the pass this GPU runs, and in how many co-resident waves (bands of tile rows) ----
-    const tbrm_slab& sl = r.slab;
-    const bool sharded = sl.nranks > 1;
-    const bool shard_q = sharded && u.axis != 2, shard_s = sharded && u.axis == 2;  // q = z for sweeps along X and Y
-    const int ns = u.td[2];
-    int q_begin = 0, q_end = ty, k_begin = 0, k_end = ns;
-    if (shard_q) q_begin = sl.z_begin, q_end = sl.z_end;
-    if (shard_s) {
-        k_begin = u.dirn > 0 ? sl.z_begin : ns - sl.z_end;
-        k_end = u.dirn > 0 ? sl.z_end : ns - sl.z_begin;
-    }
-    const int reach_lo = std::max(0, -T.bmin[1]), reach_hi = std::max(0, T.bmax[1] + 1);
+    // ---- in how many co-resident waves (bands of tile rows) this GPU's part of the pass runs ----
     int per_sm = 0;
     const void* kern_plain = ws ? chain_kernel(u.axis, false, px) : (l8 ? tma_kernel_l8(u.axis, clip, false, px, th) : tma_kernel(u.axis, clip, false, px, th));
     const void* kern_slab = ws ? chain_kernel(u.axis, true, px) : (l8 ? tma_kernel_l8(u.axis, clip, true, px) : tma_kernel(u.axis, clip, true, px, th));
@@ -834,18 +847,20 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     int cap_rows = (int) std::min<long long>((long long) sms * per_sm / P.ntx, 1 << 20);  // tile rows of one co-resident wave
     if (r.options.reserved[2] > 0) cap_rows = std::min(cap_rows, r.options.reserved[2]);      // test hook: force banding on small planes
     if (cap_rows < 1) return not_handled("cap_rows < 1");
-    const int tr0 = q_begin / kTH, tr1 = (q_end + kTH - 1) / kTH;
-    auto bands_of = [&](int qb, int qe) { return ((qe + kTH - 1) / kTH - qb / kTH + cap_rows - 1) / cap_rows; };
+    const int tr0 = j_first, tr1 = (q_end - q_org + kTH - 1) / kTH;
+    auto bands_of = [&](int qb, int qe) { return ((qe - qb + kTH - 1) / kTH + cap_rows - 1) / cap_rows; };  // (every slab is anchored at its own first row)
     const int nbands = bands_of(q_begin, q_end);
     const int rows_per_band = (tr1 - tr0 + nbands - 1) / nbands;
     const bool use_slab = sharded || nbands > 1;
     if (use_slab) {
         if (reach_lo + reach_hi > kInboxSlots) return not_handled("the footprints reach more than 8 rows into the neighbouring bands");
         // a footprint must not reach past the adjacent band (bands and slabs are at least 8 rows)
-        if (std::max(reach_lo, reach_hi) > std::min(kTH, q_end - (tr0 + (nbands - 1) * rows_per_band) * kTH))
+        if (std::max(reach_lo, reach_hi) > std::min(kTH, q_end - (q_org + (tr0 + (nbands - 1) * rows_per_band) * kTH)))
             return not_handled("the footprints reach past the adjacent band");
         if (nbands > 1 && reach_lo > 0 && reach_hi > 0) return not_handled("nbands > 1 && reach_lo > 0 && reach_hi > 0");  // bands run one after the other: one-way dependencies only
-        if (q_begin % kTH != 0 || (q_end % kTH != 0 && q_end != ty)) return not_handled("q_begin % kTH != 0 || (q_end % kTH != 0 && q_end != ty)");
+        // a slab that ends inside its last tile row needs the clipped light maps: 7-row R32F tiles (the G8 slab kernels have 8 rows, where
+        // slabs of multiples of 8 slices end on a tile row)
+        if ((q_end - q_org) % kTH != 0 && q_end != ty && (l8 || th != 7)) return not_handled("(q_end - q_org) % kTH != 0 && q_end != ty");
         if (k_begin % kSB != 0 || (k_end % kSB != 0 && k_end != ns) || (shard_s && ns % kSB != 0)) return not_handled("k_begin % kSB != 0 || (k_end % kSB != 0 && k_end != ns) || (shard_s && ns % kSB != 0)");
         if ((e = slab_ensure_arena(r)) != cudaSuccess) return e;
     }
@@ -1037,7 +1052,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
         S.tile_row0 = tr0 + bi * rows_per_band;
         S.tile_rows = std::min(rows_per_band, tr1 - S.tile_row0);
         if (S.tile_rows <= 0) continue;
-        S.q_lo = S.tile_row0 * kTH, S.q_hi = std::min(q_end, (S.tile_row0 + S.tile_rows) * kTH);
+        S.q_lo = q_org + S.tile_row0 * kTH, S.q_hi = std::min(q_end, q_org + (S.tile_row0 + S.tile_rows) * kTH);
         S.k_begin = k_begin, S.k_end = k_end;
         S.reach_lo = reach_lo, S.reach_hi = reach_hi;
         S.inbox = arena_inbox(r.arena, r.ldims, arena_region(seq, bi));

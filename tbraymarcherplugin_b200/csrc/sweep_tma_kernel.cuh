@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(32 * TH, 4)
     const int tile = tiy * P.ntx + tix;
     const int row_lo = SLAB ? P.S.tile_row0 : 0, row_hi = SLAB ? P.S.tile_row0 + P.S.tile_rows : P.nty;  // tile rows of this launch
     const int k_begin = SLAB ? P.S.k_begin : 0, k_end = SLAB ? P.S.k_end : ns;
-    const int x0 = tix * TW, y0 = tiy * kTH;
+    const int x0 = tix * TW, y0 = P.q_org + tiy * kTH;  // (q_org: tile rows are anchored at the first row of the launch's slab)
+    const int q_stop = SLAB ? min(U.td[1], P.S.q_hi) : U.td[1];  // rows from here on are not this launch's (a slab may end inside its last tile row)
     const size_t plane = (size_t) tx * ty;
     const unsigned int plane32 = (unsigned int) (tx * ty);  // ring cells are indexed in 32 bits (the host checks kRingDepth * plane < 2^31)
 
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(32 * TH, 4)
         int ndown = 0;
         s_abort = 0;
         for (int j = row_lo; j < row_hi; ++j) {
-            const int gy = j * kTH + P.bmin[1];
+            const int gy = P.q_org + j * kTH + P.bmin[1];
             if (gy + FH <= y0 || gy >= y0 + kTH) continue;
             for (int i = 0; i < P.ntx; ++i) {
                 const int gx = i * TW + P.bmin[0];
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(32 * TH, 4)
     // ---- per-thread invariants: 2 adjacent pixels (px, px+1) of row py --------------------------------------
     const int lx = (tid & 31) * PX, ly = tid >> 5;
     const int px = x0 + lx, py = y0 + ly;
-    const bool v0 = px < tx && py < ty, v1 = PX == 2 && px + 1 < tx && py < ty;  // PX == 1: every use of the second pixel folds away
+    const bool v0 = px < tx && py < q_stop, v1 = PX == 2 && px + 1 < tx && py < q_stop;  // PX == 1: every use of the second pixel folds away
     const int pxc = min(px, tx - 1), px1c = min(px + 1, tx - 1), pyc = min(py, ty - 1);
     const int2 mp0 = __ldg(&P.A.ax[PA].meta[pxc]), mp1 = __ldg(&P.A.ax[PA].meta[px1c]), mq = __ldg(&P.A.ax[QA].meta[pyc]);
     const float fp0 = __ldg(&P.A.ax[PA].f[pxc]), fp1 = __ldg(&P.A.ax[PA].f[px1c]), fq = __ldg(&P.A.ax[QA].f[pyc]);
@@ -185,12 +186,12 @@ __global__ void __launch_bounds__(32 * TH, 4)
     const unsigned int own_cell = (unsigned int) (px + tx * py);  // this thread's first pixel in a ring slice (used where v0 / v1 hold)
     // is a pixel read by another tile? tile (i,j) reads [i*TW + bmin, +FW) x [j*TH + bmin, +FH)
     auto exported = [&](int gx, int gy) {
-        const int rx = gx - P.bmin[0], ry = gy - P.bmin[1];  // tile origin i*TW must lie in (rx - FW, rx]
+        const int rx = gx - P.bmin[0], ry = gy - P.bmin[1] - P.q_org;  // tile origin i*TW must lie in (rx - FW, rx]
         const int ia = max(0, (rx - FW + TW) / TW), ib = rx >= 0 ? min(P.ntx - 1, rx / TW) : -1;
         const int ja = max(row_lo, (ry - FH + kTH) / kTH), jb = ry >= 0 ? min(row_hi - 1, ry / kTH) : -1;
         for (int j = ja; j <= jb; ++j)
             for (int i = ia; i <= ib; ++i) {
-                const int gx0 = i * TW + P.bmin[0], gy0 = j * kTH + P.bmin[1];
+                const int gx0 = i * TW + P.bmin[0], gy0 = P.q_org + j * kTH + P.bmin[1];
                 if ((i != tix || j != tiy) && gx >= gx0 && gx < gx0 + FW && gy >= gy0 && gy < gy0 + FH) return true;
             }
         return false;
@@ -204,7 +205,8 @@ __global__ void __launch_bounds__(32 * TH, 4)
     __shared__ int s_over_fp[kHaloOverflow], s_over_ring[kHaloOverflow];
     int n_halo;  // footprint cells outside the own tile
     {
-        const int ox0 = max(fx0, x0), ox1 = min(fx0 + FW, x0 + TW), oy0 = max(fy0, y0), oy1 = min(fy0 + FH, y0 + kTH);
+        // (rows of the tile past the end of the slab belong to the neighbour: they arrive through the inbox like any other halo cell)
+        const int ox0 = max(fx0, x0), ox1 = min(fx0 + FW, x0 + TW), oy0 = max(fy0, y0), oy1 = min(fy0 + FH, SLAB ? min(y0 + kTH, P.S.q_hi) : y0 + kTH);
         const int ow = max(0, ox1 - ox0), oh = (ow > 0) ? max(0, oy1 - oy0) : 0;
         const int top = (oh > 0 ? oy0 - fy0 : FH) * FW, mid = oh * (FW - ow);
         n_halo = FW * FH - ow * oh;
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(32 * TH, 4)
                 if (SLAB && (gy < P.S.q_lo || gy >= P.S.q_hi)) {  // owned by a neighbouring band: inbox row slot
                     const int slot = gy < P.S.q_lo ? gy - (P.S.q_lo - P.S.reach_lo) : P.S.reach_lo + gy - P.S.q_hi;
                     ring_idx = -1 - (slot * tx + gx);
+                    // rows only the masked pixels of a last tile row would read (a slab that ends inside the row) are nobody's to deliver
+                    if (slot < 0 || slot >= P.S.reach_lo + P.S.reach_hi) fp_idx = -1;
                 }
             }
         };

@@ -214,6 +214,29 @@ def test_seven_row_tiles_in_banded_and_sharded_passes(flags, dims):
     assert np.array_equal(merged(ranks), ref)
 
 
+@pytest.mark.parametrize("flags", [512 + 32, 512 + 16])
+@pytest.mark.parametrize("dims,nranks", [((128, 64, 64), 2), ((128, 64, 64), 4), ((64, 64, 96), 3), ((256, 256, 256), 2)])
+def test_seven_row_tiles_in_the_slabs_of_sweeps_along_x_and_y(dims, nranks, flags):
+    """Slabs of 32 / 16 / 128 slices are not multiples of 7 rows: the tile rows of a slab are anchored at its first row, its last tile row ends
+    past the slab (those pixels are masked, the light maps end with the slab, the rows come from the neighbour's exchange cells)."""
+    data = synth.perlin_ct_volume(dims)
+    world = synth.identity_world()
+    lights = synth.LIGHTS[1:] if flags & 32 and dims[0] != dims[1] else synth.LIGHTS
+    ref = unsharded(data, lights, world)
+    for band_rows in ((0, 2) if dims[2] < 256 else (0,)):
+        ranks = virtual_ranks(data, nranks, band_rows=band_rows, flags=flags)
+        for res, _, _ in ranks:
+            URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        sharded_sweep(ranks, lights, world)
+        got = merged(ranks)
+        assert np.array_equal(got, ref), (band_rows, np.count_nonzero(got != ref), np.argwhere(got != ref)[:4].tolist())
+        sharded_sweep(ranks, [lights[0]], world, added=False)
+        res1 = make_res(data)
+        URaymarchUtils.WriteLightVolume(res1, ref)
+        URaymarchUtils.AddDirLightToSingleVolume(res1, lights[0], False, world, bGPUSync=True)
+        assert np.array_equal(merged(ranks), URaymarchUtils.ReadLightVolume(res1))
+
+
 def test_sharded_and_banded_together():
     data = synth.perlin_ct_volume((64, 64, 64))
     world = synth.identity_world()
