@@ -247,8 +247,11 @@ tbrm_status tbrm_bind_light_volume_device(tbrm_resources* res, void* dptr);
  * [z_begin, z_end): after tbrm_slab_configure the sweep ops (clear / add / change) touch only the owned slab, and the
  * propagated light crosses slab boundaries inside the sweep kernel through the neighbours' exchange arenas (NVLink peer
  * stores for sweeps along X / Y, a plane hand-off for sweeps along Z). The result is bit-identical to the unsharded sweep.
- * Gathering the slabs (an all-gather of the light volume, in place) is the caller's collective. Requires R8 data, an R32F
- * full-resolution light volume, X % 16 == 0, Y % 16 == 0 and Z % 8 == 0; other configurations return TBRM_ERR_UNSUPPORTED. */
+ * Gathering the slabs (an all-gather of the light volume, in place) is the caller's collective. The slabs are slices of the
+ * LIGHT volume (tbrm_slab_partition(light_dims[2], ...): half of the data slices for a half-resolution light volume).
+ * Requires R8 data, an R32F or G8 light volume (full or half resolution), X % 16 == 0, Y % 16 == 0 and Z % 8 == 0 of the data
+ * volume, light Z % 8 == 0, and for a G8 light volume its own X % 16 == 0 and Y % 16 == 0; other configurations return
+ * TBRM_ERR_UNSUPPORTED. */
 void tbrm_slab_partition(int32_t z_slices, int32_t nranks, int32_t rank, int32_t* z_begin, int32_t* z_end);
 tbrm_status tbrm_slab_configure(tbrm_resources* res, const tbrm_slab* slab);
 /* The exchange arena of this rank: device pointer + size, and its CUDA IPC handle (64 bytes) for the neighbour processes. */
