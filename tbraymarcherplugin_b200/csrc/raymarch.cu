@@ -483,7 +483,7 @@ __device__ __forceinline__ void axis_taps_raw(float u, int N, int& i0, float& f)
     i0 = (int) fl;
 }
 
-template <bool CLIP, typename LightT, int NT = 256>
+template <bool CLIP, typename LightT, int NT = 256, int WXP = 4, int WW = 8>
 __global__ void __launch_bounds__(NT, 1280 / NT) raymarch_fast2_kernel(const FastUniforms F, const uint8_t* __restrict__ data,
                                                              const LightT* __restrict__ light, const float4* __restrict__ tf,
                                                              float4* __restrict__ out, unsigned long long* __restrict__ steps_out) {
@@ -492,9 +492,10 @@ __global__ void __launch_bounds__(NT, 1280 / NT) raymarch_fast2_kernel(const Fas
     for (int c = threadIdx.x; c < 256; c += NT) s_tf[c] = __ldg(&tf[c]);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int WX = NT >= 128 ? 4 : NT / 32;  // warps across a block: a block is 8 WX x (NT / 8 WX) pixels, a warp 8 x 4
-    const int ix = blockIdx.x * (8 * WX) + (warp % WX) * 8 + (lane & 7);
-    const int lr = blockIdx.y * (NT / (8 * WX)) + (warp / WX) * 4 + (lane >> 3);  // row of the output buffer
+    constexpr int WX = NT >= 128 ? WXP : NT / 32;  // warps across a block
+    constexpr int WH = 32 / WW;  // a warp covers WW x WH pixels
+    const int ix = blockIdx.x * (WW * WX) + (warp % WX) * WW + (lane % WW);
+    const int lr = blockIdx.y * (NT / 32 / WX * WH) + (warp / WX) * WH + (lane / WW);  // row of the output buffer
     const int iy = U.row_begin + (lr / U.row_block) * U.row_block * U.block_stride + lr % U.row_block;
     unsigned int steps = 0;
     if (ix < U.cam.width && iy < U.row_end) {
@@ -854,14 +855,16 @@ cudaError_t raymarch_lit(tbrm_resources& r, const host::CameraUniforms& cam, con
         float4* o4 = (float4*) d_out;
         auto launch = [&](auto light_ptr) {  // light_ptr: const float* (R32F) or const uint8_t* (G8)
             using LightT = std::remove_cv_t<std::remove_pointer_t<decltype(light_ptr)>>;
-            // blocks of 128 threads (32 x 4 pixels): the SM's slots refill in finer grains as rays end (cfg2 frame 4.54 -> 4.45 ms; 64 threads: the same);
-            // TBRM_MARCH_NT=256 keeps round 1's 32 x 8 blocks
+            // blocks of 128 threads instead of 256: the SM's slots refill in finer grains as rays end (cfg2 frame 4.54 -> 4.45 ms as 32 x 4 pixels;
+            // 64 threads: the same). Shape, measured on one box at cfg2: warps of 4 x 8 pixels in blocks of 2 x 2 warps (8 x 16 pixels) 4.35-4.39 ms,
+            // 8 x 4 warps 4.45 ms, 16 x 2 4.94 ms, 2 x 16 4.85 ms, blocks of 4 x 1 or 1 x 4 warps 4.39-4.42 ms. TBRM_MARCH_NT=256 keeps round 1's
+            // 32 x 8 blocks of 8 x 4 warps.
             static const bool nt256 = [] { const char* e = getenv("TBRM_MARCH_NT"); return e && atoi(e) == 256; }();
-            const dim3 grid128(grid.x, (rows + 3) / 4);
+            const dim3 grid128((cam.width + 7) / 8, (rows + 15) / 16);
             if (v2 && noclip && !nt256)
-                raymarch_fast2_kernel<false, LightT, 128><<<grid128, 128, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+                raymarch_fast2_kernel<false, LightT, 128, 2, 4><<<grid128, 128, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
             else if (v2 && !nt256)
-                raymarch_fast2_kernel<true, LightT, 128><<<grid128, 128, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
+                raymarch_fast2_kernel<true, LightT, 128, 2, 4><<<grid128, 128, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
             else if (v2 && noclip)
                 raymarch_fast2_kernel<false, LightT><<<grid, 256, 0, r.stream>>>(F, d8, light_ptr, r.tf, o4, d_steps);
             else if (v2)
