@@ -464,7 +464,7 @@ def run_ours(args) -> int:
     sweep_bytes = vox * (4.0 + passes * 9.0)  # clear (4 B) + per axis pass 1 B data + 4 B read + 4 B write
     ray_bytes = vox * 1.0 + vox * 4.0 + 256 * 16 * 8 + W * H * 16.0  # compulsory bytes of the raymarch
     roofline = {  # dominant kernel by time: the raymarch (instruction-issue bound, not HBM bound — reported honestly)
-        "kernel": "raymarch_fast2_kernel (lit march, second generation without leaps, 128-thread blocks)", "bound": "hbm", "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9, "peak": hbm_peak * world_size, "unit": "GB/s",
+        "kernel": "raymarch_fast2_kernel (lit march, second generation without leaps, 128-thread blocks of 2 x 2 warps of 4 x 8 pixels)", "bound": "hbm", "achieved": ray_bytes / (ray_ms * 1e-3) / 1e9, "peak": hbm_peak * world_size, "unit": "GB/s",
         "frac": ray_bytes / (ray_ms * 1e-3) / 1e9 / (hbm_peak * world_size), "traffic": None, "peak_source": peak_src,
         "note": "compulsory bytes / kernel time; ~350 instr per non-empty sample make this kernel issue-bound (DESIGN.md §5.3, §6)",
     }
@@ -474,8 +474,8 @@ def run_ours(args) -> int:
     fp32_peak = 148 * 128 * 2 * sm_clock_ghz / 1e3  # TFLOP/s
     roofline["fp32"] = {"flop_per_step": 110, "achieved_TFLOPs": all_steps * 110.0 / (ray_ms * 1e-3) / 1e12, "peak_TFLOPs": fp32_peak * world_size,
                         "frac": all_steps * 110.0 / (ray_ms * 1e-3) / 1e12 / (fp32_peak * world_size),
-                        "ncu": "profiles/r2_raymarch_fast2_kernel_ncu.txt: 130 thread-instructions per executed step, issue slots 63 % busy, ALU pipe 36 %, "
-                               "FMA pipes 27 %, DRAM 0.7 %, top stall long scoreboard (L1 hits, 94 %)"}
+                        "ncu": "profiles/r2_raymarch_fast2_kernel_ncu.txt: 129 thread-instructions per executed step, issue slots 64 % busy, ALU pipe 36 %, "
+                               "FMA pipes 27 %, DRAM 0.7 %, top stall long scoreboard (L1 hits, 96 %)"}
     roofline_sweep = {
         "kernel": "sweep_tma_kernel (one axis pass along Z, 64 x 7 tiles where they fill the SMs; on a sharded volume its slabs run as a chain)", "bound": "hbm",
         "achieved": vox * 9.0 / (pass_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": vox * 9.0 / (pass_ms * 1e-3) / 1e9 / hbm_peak,
