@@ -1,5 +1,5 @@
 """Static SASS of the per-slice loop of sweep_tma_kernel<AXIS, CLIP, SLAB> with the instructions attributed to source lines (needs -lineinfo, which
-build.py passes): `python scripts/sass_loop_count.py [AXIS=2] [CLIP=0] [SLAB=0] [top=25] [PX=2]`. Round 1's breakdown is profiles/r1_sweep_sass_breakdown.txt."""
+build.py passes): `python scripts/sass_loop_count.py [AXIS=2] [CLIP=0] [SLAB=0] [top=25] [PX=2] [L8=0] [TH=7]`. Round 1's breakdown is profiles/r1_sweep_sass_breakdown.txt."""
 import collections
 import re
 import subprocess
@@ -8,13 +8,13 @@ import tempfile
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-axis, clip, slab, top, px = (int(a) for a in (sys.argv[1:] + ["2", "0", "0", "25", "2"][len(sys.argv) - 1:])[:5])
+axis, clip, slab, top, px, l8, th = (int(a) for a in (sys.argv[1:] + ["2", "0", "0", "25", "2", "0", "7"][len(sys.argv) - 1:])[:7])
 K = "sweep_tma_kernel.cuh"
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "tbraymarcherplugin_b200" / "build" / "sweep.cu.o")], cwd=tmp, check=True, capture_output=True)
     cubin = next(Path(tmp).glob("*.cubin"))
     text = subprocess.run(["nvdisasm", "--print-line-info", str(cubin)], capture_output=True, text=True, check=True).stdout
-name = f".text._ZN4tbrm16sweep_tma_kernelILi{axis}ELb{clip}ELb{slab}ELi{px}E"
+name = f".text._ZN4tbrm16sweep_tma_kernelILi{axis}ELb{clip}ELb{slab}ELi{px}ELb{l8}ELi{th}E"  # <AXIS, CLIP, SLAB, PX, L8, TH>
 lines = text.splitlines()
 begin = next(i for i, l in enumerate(lines) if l.startswith(name))
 seq, cur = [], None
