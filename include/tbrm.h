@@ -351,7 +351,9 @@ tbrm_status tbrm_mandelbulb_sdf(int device, const int32_t dims[3], const float c
 float tbrm_debug_mandelbulb_sdf_p8(const float position[3], float bailout, int iterations, uint32_t* out_iterations);
 /* Test hook: builds (if it is stale) and downloads a structure the kernels derive from an R8 data volume. which = 0: the lit march's brick
  * grid, one byte per 8^3 brick = the largest data byte over voxels [8b, 8b + 8] on every axis, ceil(dims / 8) bricks per axis, x fastest;
- * which = 1: the (y,z,x)-ordered replica the sweeps along X read, dst[y + Y * (z + Z * x)] = data[x + X * (y + Y * z)]. */
+ * which = 1: the (y,z,x)-ordered replica the sweeps along X read, dst[y + Y * (z + Z * x)] = data[x + X * (y + Y * z)];
+ * which = 4: four int32 describing the last TMA-staged sweep launch — tile rows (7 or 8), pixels per thread, tiles this GPU launched, bands
+ * (2 and 3 belong to the second kernel generation: T-brick flags, section timers of diagnostic builds). */
 tbrm_status tbrm_debug_download_derived(tbrm_resources* res, int which, void* dst, size_t capacity);
 
 /* ---- volume ingest ------------------------------------------------------------------ */

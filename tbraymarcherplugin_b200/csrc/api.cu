@@ -1158,7 +1158,12 @@ tbrm_status tbrm_debug_download_derived(tbrm_resources* res, int which, void* ds
         TBRM_CUDA(cudaMemcpy(dst, res->dbg, std::min(capacity, (size_t) 4096 * 4 * 8 * sizeof(long long)), cudaMemcpyDeviceToHost));
         return TBRM_OK;
     }
-    TBRM_REQUIRE(which >= 0 && which <= 2, "tbrm_debug_download_derived: which must be 0 (brick grid), 1 (yzx replica) or 2 (T-brick flags of the last split sweep pass)");
+    if (which == 4) {  // geometry of the last TMA-staged sweep launch: tile rows, pixels per thread, tiles this GPU launched, bands
+        TBRM_REQUIRE(capacity >= sizeof(res->last_geom), "tbrm_debug_download_derived: destination too small");
+        memcpy(dst, res->last_geom, sizeof(res->last_geom));
+        return TBRM_OK;
+    }
+    TBRM_REQUIRE(which >= 0 && which <= 2, "tbrm_debug_download_derived: which must be 0 (brick grid), 1 (yzx replica), 2 (T-brick flags of the last split sweep pass) or 4 (launch geometry)");
     tbrm_resources* r = res;
     if (r->data_fmt != TBRM_FMT_G8 || !r->data_ready) {
         set_last_error("tbrm_debug_download_derived: needs an uploaded R8 data volume");

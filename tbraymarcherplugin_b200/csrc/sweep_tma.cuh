@@ -852,6 +852,7 @@ static cudaError_t sweep_pass_tma_mode(tbrm_resources& r, const SweepUniforms& u
     const int nbands = bands_of(q_begin, q_end);
     const int rows_per_band = (tr1 - tr0 + nbands - 1) / nbands;
     const bool use_slab = sharded || nbands > 1;
+    r.last_geom[0] = th, r.last_geom[1] = px, r.last_geom[2] = P.ntx * (tr1 - tr0), r.last_geom[3] = nbands;
     if (use_slab) {
         if (reach_lo + reach_hi > kInboxSlots) return not_handled("the footprints reach more than 8 rows into the neighbouring bands");
         // a footprint must not reach past the adjacent band (bands and slabs are at least 8 rows)

@@ -62,6 +62,7 @@ struct tbrm_resources {
     unsigned int* flags = nullptr;
     size_t flags_count = 0;
     unsigned int* sweep_err = nullptr;  // device word raised by a fused sweep launch whose wait on another tile timed out
+    int32_t last_geom[4] = {0, 0, 0, 0};  // the last TMA-staged sweep launch: tile rows, pixels per thread, tiles of the plane, bands (tbrm_debug_download_derived 4)
     void* light_perm[2] = {nullptr, nullptr};  // G8 light volume, sweeps along X: its (y,z,x)- and (z,x,y)-ordered copies
     size_t light_perm_bytes = 0;
     void* tvol = nullptr;               // split sweep: T = 1 - occlusion bricks of the pass in flight (4 B per light voxel)

@@ -180,6 +180,10 @@ def test_emulated_lit_march_in_both_addressing_forms(emulated):
     M.test_lit_march_with_64_bit_tap_addressing_still_matches_oracle((1, 7, 1))
 
 
+def test_emulated_choice_of_seven_row_tiles_on_a_512_squared_plane(emulated):
+    M.test_a_512_squared_plane_takes_seven_row_tiles_and_stays_bit_exact()
+
+
 @pytest.mark.parametrize("light32", [True, False])
 def test_emulated_half_resolution_light_volume_through_the_tma_staged_sweep(emulated, light32):
     M.test_half_resolution_light_volume_through_the_tma_staged_sweep((64, 64, 40), light32)

@@ -308,6 +308,35 @@ def test_half_resolution_light_volume_through_the_tma_staged_sweep(dims, light32
         res.release()
 
 
+def test_a_512_squared_plane_takes_seven_row_tiles_and_stays_bit_exact():
+    """What the headline workload runs, on a thin volume: a sweep along Z over a 512 x 512 plane is 592 tiles of 64 x 7 pixels = four blocks on
+    each of 148 SMs (512 tiles of 64 x 8 would leave SMs with three), chosen by the host, bit-exact against the oracle; a 256 x 512 plane
+    (256 tiles of 8 rows: two blocks on most SMs, one on the rest) takes 7 rows as well (296 = 2 x 148), a 128 x 128 plane keeps 8."""
+    import ctypes as C
+
+    from tbraymarcherplugin_b200 import _capi
+    from tbraymarcherplugin_b200.raymarch_utils import FDirLightParameters, FSweepStats
+
+    lib = _capi.load()
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    for dims, want in (((512, 512, 8), (7, 2, 592, 1)), ((512, 256, 8), (7, 2, 296, 1)), ((128, 128, 8), (8, 1, 64, 1))):
+        data = synth.perlin_ct_volume(dims)
+        res = make_res(data, win)
+        URaymarchUtils.SetOptions(res, sweep_impl=2)
+        vol = oracle.OracleVolume(data, oracle.prepare_tf(synth.soft_ct_curve()), win)
+        URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+        for l in (FDirLightParameters((0.0, 0.0, -1.0), 0.9), FDirLightParameters((0.0, 0.0, 1.0), 0.4)):  # one sweep along Z each, both directions
+            st = FSweepStats()
+            assert URaymarchUtils.AddDirLightToSingleVolume(res, l, True, synth.identity_world(), bGPUSync=True, stats=st)
+            vol.add_dir_light(l, True, synth.identity_world())
+            assert tuple(st.impl) == (3,), st.impl
+            geom = (C.c_int32 * 4)()
+            _capi.check(lib.tbrm_debug_download_derived(res.handle, 4, geom, C.sizeof(geom)))
+            assert tuple(geom) == want, (dims, tuple(geom))
+        assert np.array_equal(URaymarchUtils.ReadLightVolume(res), vol.light), dims
+        res.release()
+
+
 # bits 4-5 of tbrm_options.reserved[0]: one / two pixels per thread, automatic; bit 6: the second kernel generation (occlusion kernel + chain kernel);
 # bits 8-9: tiles of 6 / 7 / 8 rows (256 / 512 / 768; 0 = chosen per launch)
 @pytest.mark.parametrize("px_flag", [16, 32, 48, 64 + 16, 64 + 32, 256 + 16, 256 + 32, 512 + 16, 512 + 32, 768 + 48])
