@@ -180,6 +180,10 @@ def test_emulated_lit_march_in_both_addressing_forms(emulated):
     M.test_lit_march_with_64_bit_tap_addressing_still_matches_oracle((1, 7, 1))
 
 
+def test_emulated_interleaved_rows_of_a_frame(emulated):
+    M.test_interleaved_rows_of_a_frame_equal_the_whole_frame(70)
+
+
 def test_emulated_choice_of_seven_row_tiles_on_a_512_squared_plane(emulated):
     M.test_a_512_squared_plane_takes_seven_row_tiles_and_stays_bit_exact()
 

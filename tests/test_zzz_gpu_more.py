@@ -308,6 +308,45 @@ def test_half_resolution_light_volume_through_the_tma_staged_sweep(dims, light32
         res.release()
 
 
+@pytest.mark.parametrize("height", [64, 70, 33])
+def test_interleaved_rows_of_a_frame_equal_the_whole_frame(height):
+    """What the ranks of a sharded volume render (tbrm_raymarch_lit_interleaved: blocks of 8 image rows dealt round-robin, compacted per
+    rank) assembled back into the frame, for 2 / 3 / 4 ranks on ONE GPU: equal to the frame marched in one piece, step counts included —
+    the march's thread blocks (8 x 16 pixels) span two 8-row blocks of a rank's compacted rows."""
+    import ctypes as C
+
+    from tbraymarcherplugin_b200 import _capi, sharding
+
+    lib = _capi.load()
+    dims = (48, 40, 56)
+    data = synth.perlin_ct_volume(dims)
+    win = FWindowingParameters(0.45, 0.5, True, False)
+    res = make_res(data, win)
+    URaymarchUtils.ClearResourceLightVolumes(res, 0.0)
+    for l in synth.LIGHTS[:2]:
+        URaymarchUtils.AddDirLightToSingleVolume(res, l, True, synth.identity_world(), bGPUSync=True)
+    cam = synth.benchmark_camera(100, height)
+    for world in (synth.identity_world(), synth.clipped_world()):
+        whole, whole_steps = URaymarchUtils.PerformWindowedLitRaymarch(res, cam, world, 48.0)
+        c, w = cam.to_c(), world.to_c()
+        for nranks in (2, 3, 4):
+            parts, total = [], 0
+            for rank in range(nranks):
+                rows = int(lib.tbrm_raymarch_interleaved_rows(height, 8, rank, nranks))
+                assert rows == len(sharding.rows_of_rank(height, rank, nranks, 8))
+                out = np.full((max(rows, 1), cam.Width, 4), -1.0, np.float32)
+                steps = C.c_uint64(0)
+                _capi.check(lib.tbrm_raymarch_lit_interleaved(res.handle, C.byref(c), C.byref(w), 48.0, 8, rank, nranks,
+                                                              out.ctypes.data_as(C.c_void_p), 0, C.byref(steps)))
+                parts.append([out[i:i + (e - b)] for i, (b, e) in zip(np.cumsum([0] + [e - b for b, e in sharding.row_blocks_of_rank(height, rank, nranks, 8)])[:-1],
+                                                                          sharding.row_blocks_of_rank(height, rank, nranks, 8))])
+                total += steps.value
+            frame = sharding.assemble_rows(height, nranks, parts, 8)
+            assert np.array_equal(frame, whole), (height, nranks)
+            assert total == whole_steps, (height, nranks, total, whole_steps)
+    res.release()
+
+
 def test_a_512_squared_plane_takes_seven_row_tiles_and_stays_bit_exact():
     """What the headline workload runs, on a thin volume: a sweep along Z over a 512 x 512 plane is 592 tiles of 64 x 7 pixels = four blocks on
     each of 148 SMs (512 tiles of 64 x 8 would leave SMs with three), chosen by the host, bit-exact against the oracle; a 256 x 512 plane
